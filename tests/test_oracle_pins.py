@@ -1,0 +1,120 @@
+"""Pin the CPU oracle against every known-answer vector the reference's own tests hold
+for the hot path.  Expected values are copied from the cited
+reference tests (data, not code)."""
+import numpy as np
+import pytest
+
+from oracle import dsp as O
+
+
+def _noise():
+    np.random.seed(42)
+    return np.random.randn(12000).astype(np.float32)
+
+
+SEL = [0, 1, 2, 63, 126, 127]
+
+
+class TestQwen3MelSnapshot:
+    """mlx_audio/tts/tests/test_qwen3_tts.py:175-353 (rtol/atol 2e-3 there; we hold 2e-5)."""
+    TOL = dict(rtol=2e-5, atol=2e-5)
+
+    def test_shape(self):
+        assert O.qwen3_mel_spectrogram(_noise()).shape == (1, 46, 128)
+
+    def test_frame0(self):
+        mel = O.qwen3_mel_spectrogram(_noise())[0]
+        exp = [-0.21803714, 0.06630915, -0.31858957, -0.02480409, -0.4512914, -0.5911693]
+        np.testing.assert_allclose(mel[0, SEL], exp, **self.TOL)
+
+    def test_frame23(self):
+        mel = O.qwen3_mel_spectrogram(_noise())[0]
+        exp = [0.08127937, 0.4368576, 0.43200976, -0.7714137, -0.24601418, 0.04274124]
+        np.testing.assert_allclose(mel[23, SEL], exp, **self.TOL)
+
+    def test_last_frame_reflect(self):
+        mel = O.qwen3_mel_spectrogram(_noise())[0]
+        exp = [-0.16861804, 0.0474052, -0.3970174, -0.01738772, -0.28846806, -0.10941511]
+        np.testing.assert_allclose(mel[-1, SEL], exp, **self.TOL)
+
+    def test_sine(self):
+        t = np.arange(12000, dtype=np.float32) / 24000.0
+        mel = O.qwen3_mel_spectrogram(np.sin(2 * np.pi * 1000 * t).astype(np.float32))[0]
+        exp = [-1.2959518, -1.2937515, -1.2902284, -1.2074544, -0.9268621, -2.3822036, -5.331841, -5.33782]
+        np.testing.assert_allclose(mel[0, [0, 1, 2, 10, 20, 63, 126, 127]], exp, rtol=2e-4, atol=2e-4)
+
+    def test_stats(self):
+        mel = O.qwen3_mel_spectrogram(_noise())
+        np.testing.assert_allclose(mel.mean(), -0.37329558, atol=2e-5)
+        np.testing.assert_allclose(mel.std(), 0.37445435, atol=2e-5)
+
+
+def test_convtranspose_scatter_rule_pin():
+    """tts/tests/test_istftnet_fidelity.py:18-31: depthwise ConvTranspose(k3,s2,p0)[1:] with
+    w=[1,2,3], x=[1,2,3,4] -> [2,5,4,9,6,13,8,12] (scatter rule, no kernel flip)."""
+    from oracle import nn as N
+    x = np.array([1.0, 2, 3, 4]).reshape(1, 4, 1)
+    w = np.array([1.0, 2, 3]).reshape(1, 3, 1)          # (Cout, K, Cin/g) MLX layout
+    y = N.conv_transpose1d(x, w, stride=2, padding=0, groups=1)[:, 1:, :]
+    np.testing.assert_allclose(y.reshape(-1), [2, 5, 4, 9, 6, 13, 8, 12], rtol=1e-12)
+
+
+def test_kokoro_stft_roundtrip_pin():
+    """tts/tests/test_istftnet_fidelity.py:34-46: MLXSTFT(20,5,20) transform->inverse is unity gain."""
+    from oracle import kokoro as K
+    t = np.arange(2000, dtype=np.float32)
+    x = (0.5 * np.sin(2 * np.pi * 220 * t / 24000)).astype(np.float32)
+    mag, ph = K.mlxstft_transform(x[None, :], 20, 5, 20)
+    rec = K.mlxstft_inverse(mag, ph, 20, 5, 20).reshape(-1)[: x.shape[0]]
+    np.testing.assert_allclose(rec[20:-20], x[20:-20], atol=1e-5)   # reference tolerance 1e-3
+
+
+def test_interpolate_pins():
+    """tts/tests/test_interpolate.py:40-91."""
+    x = np.array([[[1.0, 2.0, 3.0, 4.0]]])
+    np.testing.assert_allclose(O.interpolate1d(x, 8, "nearest"), [[[1, 1, 2, 2, 3, 3, 4, 4]]])
+    np.testing.assert_allclose(O.interpolate1d(x, 2, "nearest"), [[[1, 3]]])
+    x = np.array([[[1.0, 3.0, 5.0, 7.0]]])
+    np.testing.assert_allclose(O.interpolate1d(x, 7, "linear", True), [[[1, 2, 3, 4, 5, 6, 7]]], rtol=1e-6)
+    np.testing.assert_allclose(O.interpolate1d(x, 7, "linear", False),
+                               [[[1.0, 1.7142857, 2.8571429, 4.0, 5.1428576, 6.2857141, 7.0]]], rtol=1e-6)
+    np.testing.assert_allclose(O.interpolate1d(np.array([[[5.0]]]), 4, "linear"), [[[5, 5, 5, 5]]])
+    assert O.interpolate(np.zeros((2, 3, 4)), scale_factor=2).shape == (2, 3, 8)
+
+
+def test_sinegen_shapes_pin():
+    """tts/tests/test_sinegen_length_alignment.py:9-17."""
+    from oracle import kokoro as K
+    f0 = np.ones((1, 2, 1)) * 120
+    sw, uv, noise = K.sinegen(f0, upsample_scale=300, harmonic_num=8,
+                              rand_ini=np.zeros((1, 9)), noise=np.zeros((1, 2, 9)))
+    assert sw.shape == (1, 2, 9) and uv.shape == (1, 2, 1) and noise.shape == (1, 2, 9)
+
+
+def test_resample_pins():
+    """mlx_audio/tests/test_dsp.py:299-324: alias rejection < 0.01 RMS; passband gain 0.70-0.72."""
+    orig, target = 24000, 16000
+    t = np.arange(2 * orig) / orig
+    out = O.resample(np.sin(2 * np.pi * 8200.0 * t).astype(np.float32), orig, target)
+    assert float(np.sqrt(np.mean(out[400:-400] ** 2))) < 0.01
+    for f in (1000.0, 7000.0):
+        out = O.resample(np.sin(2 * np.pi * f * t).astype(np.float32), orig, target)
+        assert 0.70 < float(np.sqrt(np.mean(out[400:-400] ** 2))) < 0.72
+    assert abs(len(O.resample(np.zeros(24000, np.float32), 24000, 16000)) - 16000) <= 1
+
+
+def test_config1_whisper_logmel_shapes():
+    """BASELINE config 1: 1 s 16 kHz 440 Hz sine -> (100, 80); with padding=480000 -> (3100, 80)."""
+    x = np.sin(2 * np.pi * 440 * np.arange(16000) / 16000).astype(np.float32)
+    m = O.whisper_log_mel(x)
+    assert m.shape == (100, 80)
+    assert O.whisper_log_mel(x, padding=480000).shape == (3100, 80)
+    assert np.isfinite(m).all() and m.max() <= (np.log10(np.abs(m).max() * 0 + 1e10) + 4) / 4
+
+
+def test_stft_errors_match_reference_messages():
+    """dsp.py:402,426-428."""
+    with pytest.raises(ValueError, match="Unknown window function"):
+        O.stft(np.zeros(1000), window="nope")
+    with pytest.raises(ValueError, match="Input is too short"):
+        O.stft(np.zeros(10), n_fft=400, center=False)
