@@ -1,0 +1,169 @@
+/* b200audio -- C ABI of the B200-native speech-inference hot path.
+ *
+ * The reference (Blaizzy/mlx-audio) is pure Python on Apple MLX: it has no FFI for this path.
+ * Each entry point below replaces the MLX primitive call sites listed beside it (paths relative
+ * to /root/reference/mlx_audio); INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions (SURVEY.md section 8b "C-ABI layer"):
+ *   - every function returns 0 on success or a negative B2A_E_* code; b2a_last_error() gives a
+ *     thread-local message; nothing is ever allocated -- the caller owns every buffer, including
+ *     the workspaces, whose sizes the *_ws_bytes helpers report;
+ *   - all pointers are DEVICE pointers unless the name ends in _host; activations are float32,
+ *     channels-last [B, L, C] with explicit batch / row strides in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are asynchronous on it.
+ */
+#ifndef B200AUDIO_H
+#define B200AUDIO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2A_OK 0
+#define B2A_E_INVALID (-1)   /* bad argument (ValueError on the Python side) */
+#define B2A_E_CUDA (-2)      /* CUDA runtime error (RuntimeError) */
+#define B2A_E_UNSUPPORTED (-3)
+
+/* activation codes used by prologues / epilogues */
+enum {
+  B2A_ACT_NONE = 0,
+  B2A_ACT_LRELU = 1,      /* p0 = negative slope                (istftnet.py:721, nn.LeakyReLU) */
+  B2A_ACT_SNAKE = 2,      /* x + b[c]*sin(a[c]*x)^2             (istftnet.py:382, snac/layers.py:124, speech_tokenizer.py:123) */
+  B2A_ACT_ELU = 3,        /* alpha = 1                          (mimi/modules/seanet.py:102) */
+  B2A_ACT_GELU = 4,       /* exact erf                          (whisper.py:415, modules.py:536) */
+  B2A_ACT_GELU_TANH = 5,  /* tanh approximation                 (mimi/modules/transformer.py:141) */
+  B2A_ACT_TANH = 6,
+  B2A_ACT_SIGMOID = 7,
+  B2A_ACT_SILU = 8,
+  B2A_ACT_CLIP1 = 9       /* clip to [-1, 1]                    (speech_tokenizer.py:880) */
+};
+
+const char* b2a_last_error(void);
+int32_t b2a_version(void);
+int32_t b2a_device_sm_count(void);
+
+/* ---- 1-D convolution family --------------------------------------------------------------
+ * Replaces mx.conv1d / mx.conv_transpose1d / nn.Linear call sites:
+ *   tts/models/kokoro/istftnet.py:128-166,811,915; codec/models/mimi/modules/conv.py:41-48,103-109;
+ *   codec/models/snac/layers.py:58,111-118; stt/models/whisper/whisper.py:430-431; every nn.Linear
+ *   (a Linear is the K=1 case with L = rows).
+ * y[b,l,co] = epilogue( bias[co] + sum_{k,ci} W[k][ci][co] * pre(x[b, l*stride - pad_left + k*dilation, ci]) )
+ *   pre(v)   = act_pre( v*pre_scale[b,ci] + pre_shift[b,ci] ), and 0 outside [0,L) (pad_mode 0) or
+ *              the clamped edge sample (pad_mode 1)
+ *   epilogue(v) = ( act_post(v) * post_cscale[b?,co] + res[b, l/res_div, co] ) * out_scale   (+= y if accumulate)
+ * Transposed form (scatter rule of mx.conv_transpose1d, no kernel flip), with q = l + pad_left:
+ *   y[b,l,co] = epilogue( bias[co] + sum_{ci} sum_{k: (q-k)%stride==0} W[k][ci][co] * pre(x[b,(q-k)/stride,ci]) )
+ * Weights are pre-packed by the host as float32 [K][Cin/groups][Cout] (bf16-exact values).
+ * groups must be 1 (dense) or == Cin == Cout (depthwise, W is [K][C]).
+ */
+typedef struct {
+  const float* x; int64_t x_bs; int64_t x_ld;
+  int32_t B, L, Cin;
+  const float* w; const float* bias;
+  float* y; int64_t y_bs; int64_t y_ld;
+  int32_t Lout, Cout;
+  int32_t K, stride, dilation, pad_left, groups, pad_mode;
+  const float* pre_scale; const float* pre_shift;      /* [B,Cin] or NULL */
+  int32_t pre_act; float pre_p0; const float* pre_a; const float* pre_b;   /* per-Cin snake params */
+  int32_t post_act; float post_p0;
+  const float* post_cscale; int64_t post_cscale_bs;    /* [Cout] (bs 0) or [B,Cout] or NULL */
+  const float* res; int64_t res_bs; int64_t res_ld; int32_t res_div;
+  float out_scale; int32_t accumulate;
+} b2a_conv1d_t;
+
+int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream);
+int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream);
+
+/* strided 2-D copy (concat without torch.cat): dst[r, c] = src[r, c] */
+int32_t b2a_copy2d(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int32_t cols, void* stream);
+/* dst[r, :] = src[idx[r], :]  -- the alignment expansion `x @ pred_aln_trg` of kokoro.py:148-170 and nn.Embedding */
+int32_t b2a_gather_rows(const float* src, int64_t src_ld, const int64_t* idx, float* dst, int64_t dst_ld,
+                        int64_t rows, int32_t cols, int64_t n_src_rows, void* stream);
+/* Duration head + alignment (kokoro.py:140-164): if dur_f != NULL, pred_dur[t] = clip(round_half_even(dur_f[t] / speed), 1, 100)
+ * with nan->1, +inf->100, -inf->1 (mx.nan_to_num / mx.round / mx.clip); else pred_dur = dur_i.  Then idx_out[f] = token of
+ * frame f (device prefix sum, frames beyond max_frames dropped) and *total_dev = sum(pred_dur). */
+int32_t b2a_durations_to_index(const float* dur_f, const int64_t* dur_i, int32_t T, float speed, int64_t* pred_dur_out,
+                               int64_t* idx_out, int64_t max_frames, int64_t* total_dev, void* stream);
+
+/* ---- normalisation -----------------------------------------------------------------------
+ * InstanceNorm statistics folded with the AdaIN affine (istftnet.py:216-268,327-338):
+ *   scale[b,c] = (1+gamma[b,c]) * rstd[b,c],  shift[b,c] = beta[b,c] - scale[b,c]*mean[b,c]
+ * with gb = [B, 2C] (gamma | beta) or NULL for plain InstanceNorm; biased variance, eps inside sqrt.
+ * ws: float64 workspace of b2a_adain_ws_bytes(B,L,C) bytes. */
+int64_t b2a_adain_ws_bytes(int32_t B, int32_t L, int32_t C);
+int32_t b2a_adain_coeffs(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C,
+                         const float* gb, float eps, float* scale, float* shift, void* ws, void* stream);
+/* y[r,:] = LN(x[r,:] + res[r,:]) * w + b, or (1+ada[c])*LN + ada[C+c] when ada != NULL
+ * (nn.LayerNorm, modules.py:71-90 AdaLayerNorm). rms != 0 -> RMSNorm (no mean, talker.py:267). */
+int32_t b2a_layernorm(const float* x, int64_t x_ld, const float* res, int64_t res_ld, float* y, int64_t y_ld,
+                      int64_t rows, int32_t C, const float* w, const float* b, const float* ada, float eps,
+                      int32_t rms, int32_t post_act, float post_p0, void* stream);
+
+/* ---- attention -----------------------------------------------------------------------------
+ * softmax(scale * q k^T + mask) v with fp32 softmax; replaces mx.fast.scaled_dot_product_attention
+ * (mimi/modules/transformer.py:109, talker.py:307) and the unfused form (whisper.py:371-385, modules.py:497-505).
+ * q [B,Tq,H,D], k/v [B,Tk,Hkv,D] with token strides *_ld and batch strides *_bs (elements); head h at +h*D.
+ * causal != 0: key j visible to query i iff j <= i + q_offset; window > 0: also i + q_offset - j < window. */
+typedef struct {
+  const float* q; const float* k; const float* v; float* o;
+  int64_t q_bs, q_ld, k_bs, k_ld, v_bs, v_ld, o_bs, o_ld;
+  int32_t B, Tq, Tk, H, Hkv, D;
+  float scale; int32_t causal, q_offset, window;
+  const int32_t* k_len;     /* [B] valid key count or NULL */
+} b2a_attn_t;
+int32_t b2a_attention(const b2a_attn_t* p, void* stream);
+/* in-place rotary embedding on x [B,T,H,D] (token stride ld): traditional != 0 rotates pairs (2i,2i+1)
+ * (nn.RoPE(traditional=True), mimi/modules/transformer.py:75-77), else (i, i+D/2) (talker.py:14-18). */
+int32_t b2a_rope(float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t T, int32_t H, int32_t D,
+                 int32_t offset, float base, int32_t traditional, void* stream);
+
+/* ---- bidirectional LSTM recurrence (modules.py:93-285) ------------------------------------
+ * xproj [B,T,2,4H] = x @ Wx^T + b_ih + b_hh for (forward|backward), gate order i,f,g,o;
+ * wh [2,4H,H]; out [B,T,2H] (forward | backward).  H must be 256 (Kokoro) -- one 8-CTA cluster
+ * per (direction, batch) keeps Wh in registers and exchanges h through distributed shared memory. */
+int32_t b2a_lstm_bidir(const float* xproj, const float* wh, float* out, int64_t out_ld, int32_t B, int32_t T, int32_t H, void* stream);
+
+/* ---- DSP ------------------------------------------------------------------------------------
+ * b2a_stft: dsp.py:385-433 on a batch of 1-D signals. out_re/out_im [B, frames, n_fft/2+1].
+ * pad_mode: 0 none (center=False), 1 reflect, 2 constant.  window [n_fft] (already zero-padded). */
+int32_t b2a_stft(const float* x, int64_t x_bs, int32_t B, int64_t n, const float* window, int32_t n_fft, int32_t hop,
+                 int32_t pad_mode, int64_t frames, float* out_re, float* out_im, void* stream);
+/* Whisper log-mel (stt/models/whisper/audio.py:41-82): frames-major [B, frames, n_mels]; `frames` excludes the
+ * dropped last STFT frame; n = samples per signal (right zero padding of `padding` samples is virtual).
+ * gmax [B] scratch for the per-utterance max. */
+int32_t b2a_whisper_logmel(const float* x, int64_t x_bs, int32_t B, int64_t n, int64_t padding, const float* window,
+                           const float* filters, int32_t n_mels, int64_t frames, float* out, float* gmax, void* stream);
+/* dsp.py:436-513 / 663-738: inverse rFFT per frame, synthesis window, overlap-add, divide by sum(w^2) (norm_sq) or
+ * sum(w), clamp denominators as the reference does (mode 0: where(wsum>1e-10); mode 1: max(wsum,1e-10)).
+ * re/im [B, n_freq, T]; out [B, out_len] starting at sample `trim` of the OLA buffer. ws: B*T*n_fft floats. */
+int32_t b2a_istft(const float* re, const float* im, int32_t B, int32_t n_fft, int32_t T, int32_t hop, const float* window,
+                  int32_t norm_sq, int32_t clamp_mode, int64_t trim, int64_t out_len, float* out, float* ws, void* stream);
+
+/* ---- Kokoro hn-NSF source + iSTFT head (istftnet.py:548-709, 453-545, 826-835) ------------
+ * f0 [B, n_frames] (the F0 curve, one value per 300 samples); noise [B, n_frames*300, 9] injected N(0,1) (or NULL);
+ * lin_w [9], lin_b [1] = m_source.l_linear.  har [B, n_frames*60+1, 22] = (|STFT| , angle) of the tanh-merged source,
+ * n_fft 20 hop 5 periodic Hann, reflect-centred.  src_ws: float [B, n_frames*300]; ph_ws: double [B, n_frames, 9]. */
+int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, const float* noise, const float* lin_w,
+                          const float* lin_b, float* har, float* src_ws, double* ph_ws, void* stream);
+/* x [B, T, 22] = conv_post output -> audio [B, (T-1)*5] : exp / sin heads, cos/sin, 20-point inverse rFFT, periodic Hann,
+ * overlap-add, / sum(w^2), trim 10 samples each side (phase in [-1,1] so mlx_unwrap is the identity). */
+int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t T, float* audio, void* stream);
+
+/* ---- codec (RVQ decode) ---------------------------------------------------------------------
+ * out[b,t,:] (+)= sum_q codebooks[q][codes[b,q,t]][:]   (mimi/modules/quantization.py:47-49,103-108;
+ * speech_tokenizer.py:431-490).  codes int64 [B, nq, T]; codebooks [nq, bins, dim]. Returns B2A_E_INVALID if any code
+ * is out of range (checked on device, reported via *err_flag_dev != 0). */
+int32_t b2a_rvq_decode(const int64_t* codes, int64_t codes_bs, int64_t codes_qs, int32_t B, int32_t nq, int64_t T,
+                       const float* codebooks, int32_t bins, int32_t dim, float* out, int64_t out_ld, int32_t* err_flag_dev, void* stream);
+/* SNAC from_codes (snac/vq.py:111-131): z[b,t,:] = sum_l ( W_l @ E_l[codes_l[b, t / stride_l]] + bias_l ),
+ * codes_l int64 [B, T/stride_l]; E_l [bins, cd]; W_l [cd][dim] (packed, K=1); out [B,T,dim]. */
+int32_t b2a_snac_from_codes(const int64_t* const* codes_host_ptrs, const int32_t* strides_host, int32_t n_levels,
+                            const float* const* emb_host_ptrs, const float* const* w_host_ptrs, const float* const* bias_host_ptrs,
+                            int32_t B, int64_t T, int32_t bins, int32_t cd, int32_t dim, float* out, int32_t* err_flag_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AUDIO_H */

@@ -1,0 +1,372 @@
+// 1-D convolution family on channels-last fp32 activations (include/b200audio.h: b2a_conv1d_cl,
+// b2a_convtr1d_cl).  CUDA-core path: shared-memory tiled implicit GEMM for dense layers, a
+// coalesced gather kernel for depthwise layers.  Every layer fuses its input transform
+// (InstanceNorm/AdaIN apply + Snake/LeakyReLU/ELU), bias, activation, LayerScale/noise gain,
+// residual add, output scale and accumulation, so each conv reads x once and writes y once.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64;          // output positions per CTA
+constexpr int NT = 256;         // threads per CTA
+
+struct Pre {                    // input transform, evaluated while staging x into shared memory
+  const float* scale; const float* shift; int act; float p0; const float* a; const float* b; int cin;
+  __device__ __forceinline__ float operator()(float v, int bidx, int c) const {
+    if (scale) v = fmaf(v, __ldg(scale + (int64_t)bidx * cin + c), __ldg(shift + (int64_t)bidx * cin + c));
+    if (act) v = b2a_act(v, act, p0, a ? __ldg(a + c) : 1.f, b ? __ldg(b + c) : 1.f);
+    return v;
+  }
+};
+
+__device__ __forceinline__ void epilogue_store(const b2a_conv1d_t& p, int b, int l, int co, float v) {
+  if (p.bias) v += __ldg(p.bias + co);
+  if (p.post_act) v = b2a_act(v, p.post_act, p.post_p0, 1.f, 1.f);
+  if (p.post_cscale) v *= __ldg(p.post_cscale + (int64_t)b * p.post_cscale_bs + co);
+  if (p.res) v += __ldg(p.res + (int64_t)b * p.res_bs + (int64_t)(l / p.res_div) * p.res_ld + co);
+  v *= p.out_scale;
+  float* yp = p.y + (int64_t)b * p.y_bs + (int64_t)l * p.y_ld + co;
+  if (p.accumulate) v += *yp;
+  *yp = v;
+}
+
+__device__ __forceinline__ Pre make_pre(const b2a_conv1d_t& p) {
+  return Pre{p.pre_scale, p.pre_shift, p.pre_act, p.pre_p0, p.pre_a, p.pre_b, p.Cin};
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense conv1d: CTA tile = 64 positions x BN channels; K-loop over channel chunks of CI with all
+// taps resident: xs[rows][CI+1] holds the transformed input span once (no per-tap re-reads),
+// ws[K][CI][BN] the weights.  Thread (tm,tn) owns 4 positions x NJ channels.
+template <int BN>
+__global__ void __launch_bounds__(NT) conv1d_dense_kernel(const b2a_conv1d_t p, int CI, int rows) {
+  constexpr int NJ = BN / 16;
+  extern __shared__ float smem[];
+  float* xs = smem;                                   // [rows][CI+1]
+  float* ws = smem + (size_t)rows * (CI + 1);         // [K][CI][BN]
+  const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
+  const int l0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const Pre pre = make_pre(p);
+  const float* xb = p.x + (int64_t)b * p.x_bs;
+  const int64_t pos0 = (int64_t)l0 * p.stride - p.pad_left;
+  float acc[4][NJ];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < p.Cin; c0 += CI) {
+    for (int idx = tid; idx < rows * CI; idx += NT) {
+      int ci = idx % CI, r = idx / CI;
+      int64_t pos = pos0 + r;
+      int c = c0 + ci;
+      float v = 0.f;
+      if (c < p.Cin) {
+        if (pos >= 0 && pos < p.L) v = pre(__ldg(xb + pos * p.x_ld + c), b, c);
+        else if (p.pad_mode == 1) { int64_t q = pos < 0 ? 0 : p.L - 1; v = pre(__ldg(xb + q * p.x_ld + c), b, c); }
+      }
+      xs[r * (CI + 1) + ci] = v;
+    }
+    for (int idx = tid; idx < p.K * CI * BN; idx += NT) {
+      int n = idx % BN, ci = (idx / BN) % CI, k = idx / (BN * CI);
+      int c = c0 + ci, co = n0 + n;
+      ws[idx] = (c < p.Cin && co < p.Cout) ? __ldg(p.w + ((int64_t)k * p.Cin + c) * p.Cout + co) : 0.f;
+    }
+    __syncthreads();
+    for (int k = 0; k < p.K; k++) {
+      const float* xr = xs + (size_t)(tm * 4 * p.stride + k * p.dilation) * (CI + 1);
+      const float* wr = ws + (size_t)k * CI * BN + tn * NJ;
+#pragma unroll 4
+      for (int ci = 0; ci < CI; ci++) {
+        float a[4], w[NJ];
+#pragma unroll
+        for (int i = 0; i < 4; i++) a[i] = xr[(size_t)i * p.stride * (CI + 1) + ci];
+        if constexpr (NJ == 4) {
+          float4 t = *reinterpret_cast<const float4*>(wr + ci * BN);
+          w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < NJ; j++) w[j] = wr[ci * BN + j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+          for (int j = 0; j < NJ; j++) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int l = l0 + tm * 4 + i;
+    if (l >= p.Lout) continue;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      int co = n0 + tn * NJ + j;
+      if (co < p.Cout) epilogue_store(p, b, l, co, acc[i][j]);
+    }
+  }
+}
+
+// Depthwise conv1d (groups == C): one thread per (l, c); consecutive threads take consecutive
+// channels so every tap is a coalesced row segment; taps hit L1/L2 (HBM sees x once).
+__global__ void __launch_bounds__(NT) conv1d_dw_kernel(const b2a_conv1d_t p) {
+  const Pre pre = make_pre(p);
+  const int64_t total = (int64_t)p.B * p.Lout * p.Cout;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    int c = (int)(idx % p.Cout);
+    int64_t t = idx / p.Cout;
+    int l = (int)(t % p.Lout), b = (int)(t / p.Lout);
+    const float* xb = p.x + (int64_t)b * p.x_bs + c;
+    float acc = 0.f;
+    int64_t pos = (int64_t)l * p.stride - p.pad_left;
+    for (int k = 0; k < p.K; k++, pos += p.dilation) {
+      float v = 0.f;
+      if (pos >= 0 && pos < p.L) v = pre(__ldg(xb + pos * p.x_ld), b, c);
+      else if (p.pad_mode == 1) v = pre(__ldg(xb + (pos < 0 ? 0 : (int64_t)p.L - 1) * p.x_ld), b, c);
+      acc = fmaf(v, __ldg(p.w + (int64_t)k * p.Cout + c), acc);
+    }
+    epilogue_store(p, b, l, c, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense transposed conv, gather (polyphase) form: output l (q = l + pad_left) takes taps
+// k = q%s + j*s from input rows q/s - j.  Tile = 64 positions x 64 channels.
+__global__ void __launch_bounds__(NT) convtr1d_dense_kernel(const b2a_conv1d_t p, int CI, int rows, int J) {
+  constexpr int BN = 64;
+  extern __shared__ float smem[];
+  float* xs = smem;                                   // [rows][CI+1]
+  float* ws = smem + (size_t)rows * (CI + 1);         // [K][CI][BN]
+  const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
+  const int l0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const int s = p.stride;
+  const Pre pre = make_pre(p);
+  const float* xb = p.x + (int64_t)b * p.x_bs;
+  const int ibase = (l0 + p.pad_left) / s - (J - 1);
+  int r_[4], ih_[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int q = l0 + tm * 4 + i + p.pad_left;
+    r_[i] = q % s; ih_[i] = q / s - ibase;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < p.Cin; c0 += CI) {
+    for (int idx = tid; idx < rows * CI; idx += NT) {
+      int ci = idx % CI, r = idx / CI;
+      int64_t pos = (int64_t)ibase + r;
+      int c = c0 + ci;
+      float v = 0.f;
+      if (c < p.Cin && pos >= 0 && pos < p.L) v = pre(__ldg(xb + pos * p.x_ld + c), b, c);
+      xs[r * (CI + 1) + ci] = v;
+    }
+    for (int idx = tid; idx < p.K * CI * BN; idx += NT) {
+      int n = idx % BN, ci = (idx / BN) % CI, k = idx / (BN * CI);
+      int c = c0 + ci, co = n0 + n;
+      ws[idx] = (c < p.Cin && co < p.Cout) ? __ldg(p.w + ((int64_t)k * p.Cin + c) * p.Cout + co) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      for (int j = 0; j < J; j++) {
+        int k = r_[i] + j * s;
+        if (k >= p.K) break;
+        const float* xr = xs + (size_t)(ih_[i] - j) * (CI + 1);
+        const float* wr = ws + (size_t)k * CI * BN + tn * 4;
+#pragma unroll 4
+        for (int ci = 0; ci < CI; ci++) {
+          float a = xr[ci];
+          float4 t = *reinterpret_cast<const float4*>(wr + ci * BN);
+          acc[i][0] = fmaf(a, t.x, acc[i][0]); acc[i][1] = fmaf(a, t.y, acc[i][1]);
+          acc[i][2] = fmaf(a, t.z, acc[i][2]); acc[i][3] = fmaf(a, t.w, acc[i][3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    int l = l0 + tm * 4 + i;
+    if (l >= p.Lout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int co = n0 + tn * 4 + j;
+      if (co < p.Cout) epilogue_store(p, b, l, co, acc[i][j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT) convtr1d_dw_kernel(const b2a_conv1d_t p) {
+  const Pre pre = make_pre(p);
+  const int s = p.stride;
+  const int64_t total = (int64_t)p.B * p.Lout * p.Cout;
+  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
+    int c = (int)(idx % p.Cout);
+    int64_t t = idx / p.Cout;
+    int l = (int)(t % p.Lout), b = (int)(t / p.Lout);
+    const float* xb = p.x + (int64_t)b * p.x_bs + c;
+    int q = l + p.pad_left;
+    int r = q % s, ih = q / s;
+    float acc = 0.f;
+    for (int k = r, i = ih; k < p.K && i >= 0; k += s, i--) {
+      if (i < p.L) acc = fmaf(pre(__ldg(xb + (int64_t)i * p.x_ld), b, c), __ldg(p.w + (int64_t)k * p.Cout + c), acc);
+    }
+    epilogue_store(p, b, l, c, acc);
+  }
+}
+
+__global__ void copy2d_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst, int64_t dst_ld,
+                              int64_t rows, int cols) {
+  int64_t total = rows * cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / cols; int c = (int)(idx % cols);
+    dst[r * dst_ld + c] = src[r * src_ld + c];
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, int64_t src_ld, const int64_t* __restrict__ idx_,
+                                   float* __restrict__ dst, int64_t dst_ld, int64_t rows, int cols, int64_t n_src) {
+  int64_t total = rows * cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / cols; int c = (int)(idx % cols);
+    int64_t s = idx_[r];
+    s = s < 0 ? 0 : (s >= n_src ? n_src - 1 : s);
+    dst[r * dst_ld + c] = src[s * src_ld + c];
+  }
+}
+
+// single-CTA duration head + exclusive scan, then each token writes its own run of frame indices
+__global__ void durations_to_index_kernel(const float* __restrict__ dur_f, const int64_t* __restrict__ dur_i, int T, float speed,
+                                          int64_t* __restrict__ pred, int64_t* __restrict__ out, int64_t max_frames,
+                                          int64_t* __restrict__ total) {
+  extern __shared__ long long sc[];
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    long long d;
+    if (dur_f) {
+      float v = dur_f[i] / speed;
+      if (isnan(v)) v = 1.f; else if (isinf(v)) v = v > 0 ? 100.f : 1.f;
+      v = fminf(fmaxf(rintf(v), 1.f), 100.f);          // rintf = round-half-to-even like mx.round
+      d = (long long)v;
+    } else {
+      d = dur_i[i] < 0 ? 0 : dur_i[i];
+    }
+    sc[i] = d; pred[i] = d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {               // T <= 512 tokens: a serial scan is a few hundred ns
+    long long run = 0;
+    for (int i = 0; i < T; i++) { long long d = sc[i]; sc[i] = run; run += d; }
+    *total = run;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T; i += blockDim.x) {
+    long long beg = sc[i], n = pred[i];
+    for (long long f = beg; f < beg + n && f < max_frames; f++) out[f] = i;
+  }
+}
+
+int check_common(const b2a_conv1d_t* p) {
+  if (!p || !p->x || !p->w || !p->y) return 1;
+  if (p->B <= 0 || p->L <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->Lout <= 0) return 2;
+  if (p->K <= 0 || p->stride <= 0 || p->dilation <= 0 || p->res_div <= 0) return 3;
+  if ((p->pre_scale == nullptr) != (p->pre_shift == nullptr)) return 4;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
+  int bad = check_common(p);
+  if (bad) { b2a_set_error("b2a_conv1d_cl: invalid argument (check %d)", bad); return B2A_E_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->groups == 1) {
+    const int CI = p->K <= 4 ? 32 : (p->K <= 12 ? 16 : 8);
+    const int rows = (BM - 1) * p->stride + (p->K - 1) * p->dilation + 1;
+    const int BN = p->Cout > 16 ? 64 : 16;
+    size_t smem = ((size_t)rows * (CI + 1) + (size_t)p->K * CI * BN) * sizeof(float);
+    if (smem > 200 * 1024) { b2a_set_error("b2a_conv1d_cl: tile needs %zu B of shared memory", smem); return B2A_E_UNSUPPORTED; }
+    dim3 grid(cdiv(p->Lout, BM), cdiv(p->Cout, BN), p->B);
+    if (BN == 64) {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(conv1d_dense_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      conv1d_dense_kernel<64><<<grid, NT, smem, st>>>(*p, CI, rows);
+    } else {
+      static bool attr = false;
+      if (!attr) { cudaFuncSetAttribute(conv1d_dense_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+      conv1d_dense_kernel<16><<<grid, NT, smem, st>>>(*p, CI, rows);
+    }
+  } else if (p->groups == p->Cin && p->Cin == p->Cout) {
+    int64_t total = (int64_t)p->B * p->Lout * p->Cout;
+    int blocks = (int)((total + NT - 1) / NT); if (blocks > 148 * 32) blocks = 148 * 32;
+    conv1d_dw_kernel<<<blocks, NT, 0, st>>>(*p);
+  } else {
+    b2a_set_error("b2a_conv1d_cl: groups must be 1 or Cin==Cout==groups (got %d)", p->groups);
+    return B2A_E_UNSUPPORTED;
+  }
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream) {
+  int bad = check_common(p);
+  if (bad) { b2a_set_error("b2a_convtr1d_cl: invalid argument (check %d)", bad); return B2A_E_INVALID; }
+  B2A_CHECK_ARG(p->dilation == 1, "dilation must be 1");
+  B2A_CHECK_ARG(p->pad_left >= 0, "pad_left (crop) must be >= 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p->groups == 1) {
+    const int CI = p->K <= 12 ? 16 : 8;
+    const int J = (p->K + p->stride - 1) / p->stride;
+    const int rows = (BM - 1) / p->stride + J + 1;
+    size_t smem = ((size_t)rows * (CI + 1) + (size_t)p->K * CI * 64) * sizeof(float);
+    if (smem > 200 * 1024) { b2a_set_error("b2a_convtr1d_cl: tile needs %zu B of shared memory", smem); return B2A_E_UNSUPPORTED; }
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(convtr1d_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+    dim3 grid(cdiv(p->Lout, BM), cdiv(p->Cout, 64), p->B);
+    convtr1d_dense_kernel<<<grid, NT, smem, st>>>(*p, CI, rows, J);
+  } else if (p->groups == p->Cin && p->Cin == p->Cout) {
+    int64_t total = (int64_t)p->B * p->Lout * p->Cout;
+    int blocks = (int)((total + NT - 1) / NT); if (blocks > 148 * 32) blocks = 148 * 32;
+    convtr1d_dw_kernel<<<blocks, NT, 0, st>>>(*p);
+  } else {
+    b2a_set_error("b2a_convtr1d_cl: groups must be 1 or Cin==Cout==groups (got %d)", p->groups);
+    return B2A_E_UNSUPPORTED;
+  }
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_copy2d(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int32_t cols, void* stream) {
+  B2A_CHECK_ARG(src && dst && rows >= 0 && cols > 0, "bad pointers/shape");
+  if (rows == 0) return B2A_OK;
+  int64_t total = rows * cols;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  copy2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, dst, dst_ld, rows, cols);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_gather_rows(const float* src, int64_t src_ld, const int64_t* idx, float* dst, int64_t dst_ld,
+                                   int64_t rows, int32_t cols, int64_t n_src_rows, void* stream) {
+  B2A_CHECK_ARG(src && dst && idx && rows >= 0 && cols > 0 && n_src_rows > 0, "bad pointers/shape");
+  if (rows == 0) return B2A_OK;
+  int64_t total = rows * cols;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, idx, dst, dst_ld, rows, cols, n_src_rows);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_durations_to_index(const float* dur_f, const int64_t* dur_i, int32_t T, float speed, int64_t* pred_dur_out,
+                                          int64_t* idx_out, int64_t max_frames, int64_t* total_dev, void* stream) {
+  B2A_CHECK_ARG((dur_f || dur_i) && pred_dur_out && idx_out && total_dev && T > 0 && T <= 4096 && speed > 0.f,
+                "bad pointers / T out of range / speed <= 0");
+  durations_to_index_kernel<<<1, 256, T * sizeof(long long), (cudaStream_t)stream>>>(dur_f, dur_i, T, speed, pred_dur_out, idx_out,
+                                                                                     max_frames, total_dev);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

@@ -1,0 +1,346 @@
+// DSP frontend / backend kernels (include/b200audio.h): STFT, Whisper log-mel, iSTFT, and the Kokoro
+// hn-NSF source + iSTFT head.  All HBM-bound or latency-bound; the transforms are direct DFTs against
+// an exact twiddle table in shared memory (index (k*n) mod N, so no angle accumulates error).
+#include "common.cuh"
+
+namespace {
+
+constexpr int FT = 8;   // frames per CTA
+
+__device__ __forceinline__ float load_padded(const float* __restrict__ x, int64_t n, int64_t n_total, int64_t i,
+                                              int pad, int pad_mode) {
+  // i indexes the (virtually) centre-padded signal; samples in [n, n_total) are the caller's zero padding
+  int64_t s = i - pad;
+  if (s < 0) { if (pad_mode == 1) s = -s; else return 0.f; }
+  else if (s >= n_total) { if (pad_mode == 1) s = 2 * (n_total - 1) - s; else return 0.f; }
+  return (s >= 0 && s < n) ? __ldg(x + s) : 0.f;
+}
+
+// Power or complex spectrum of FT frames per CTA. smem: tw_c[N], tw_s[N], fr[FT][N]
+template <bool POWER>
+__device__ void dft_frames(const float* __restrict__ x, int64_t n, int64_t n_total, const float* __restrict__ window,
+                           int N, int hop, int pad, int pad_mode, int64_t f0, int64_t frames, float* sm,
+                           float* out_a, float* out_b, int64_t out_stride /* per frame */) {
+  float* tw_c = sm; float* tw_s = sm + N; float* fr = sm + 2 * N;
+  const int nf = N / 2 + 1;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { float s, c; sincospif(2.f * i / N, &s, &c); tw_c[i] = c; tw_s[i] = s; }
+  for (int idx = threadIdx.x; idx < FT * N; idx += blockDim.x) {
+    int f = idx / N, i = idx % N;
+    int64_t fr_idx = f0 + f;
+    fr[idx] = fr_idx < frames ? load_padded(x, n, n_total, fr_idx * hop + i, pad, pad_mode) * __ldg(window + i) : 0.f;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < FT * nf; idx += blockDim.x) {
+    int f = idx / nf, k = idx % nf;
+    if (f0 + f >= frames) continue;
+    const float* xr = fr + f * N;
+    float re = 0.f, im = 0.f;
+    int ph = 0;
+    for (int i = 0; i < N; i++) {
+      re = fmaf(xr[i], tw_c[ph], re); im = fmaf(-xr[i], tw_s[ph], im);
+      ph += k; if (ph >= N) ph -= N;
+    }
+    if (POWER) out_a[f * out_stride + k] = re * re + im * im;
+    else { out_a[(f0 + f) * out_stride + k] = re; out_b[(f0 + f) * out_stride + k] = im; }
+  }
+}
+
+__global__ void stft_kernel(const float* __restrict__ x, int64_t x_bs, int64_t n, const float* __restrict__ window, int N,
+                            int hop, int pad_mode, int64_t frames, float* __restrict__ out_re, float* __restrict__ out_im) {
+  extern __shared__ float sm[];
+  const int b = blockIdx.y;
+  const int nf = N / 2 + 1;
+  dft_frames<false>(x + (int64_t)b * x_bs, n, n, window, N, hop, pad_mode ? N / 2 : 0, pad_mode, (int64_t)blockIdx.x * FT, frames,
+                    sm, out_re + (int64_t)b * frames * nf, out_im + (int64_t)b * frames * nf, nf);
+}
+
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) { atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v)); }
+
+// log10(max(mel,1e-10)) per frame + per-utterance max (stored with a +16 offset so the int atomicMax trick is valid)
+__global__ void whisper_logmel_kernel(const float* __restrict__ x, int64_t x_bs, int64_t n, int64_t padding,
+                                      const float* __restrict__ window, const float* __restrict__ filters, int n_mels,
+                                      int64_t frames, float* __restrict__ out, float* __restrict__ gmax) {
+  constexpr int N = 400, HOP = 160, NF = 201;
+  extern __shared__ float sm[];
+  float* pw = sm + 2 * N + FT * N;       // [FT][NF]
+  __shared__ float bmax[8];
+  const int b = blockIdx.y;
+  const int64_t f0 = (int64_t)blockIdx.x * FT, n_total = n + padding;
+  float* ob = out + (int64_t)b * frames * n_mels;
+  float lmax = -16.f;
+  // frames that only see the caller's zero padding: log10(1e-10) = -10 without doing the transform
+  const bool all_zero = (f0 * HOP - N / 2 >= n) && ((f0 + FT - 1) * HOP - N / 2 + N <= n_total || padding >= N);
+  if (all_zero) {
+    for (int idx = threadIdx.x; idx < FT * n_mels; idx += blockDim.x) {
+      int f = idx / n_mels; if (f0 + f < frames) ob[(f0 + f) * n_mels + idx % n_mels] = -10.f;
+    }
+    lmax = -10.f;
+  } else {
+    dft_frames<true>(x + (int64_t)b * x_bs, n, n_total, window, N, HOP, N / 2, 1, f0, frames, sm, pw, nullptr, NF);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < FT * n_mels; idx += blockDim.x) {
+      int f = idx / n_mels, m = idx % n_mels;
+      if (f0 + f >= frames) continue;
+      const float* fl = filters + (int64_t)m * NF;
+      const float* pr = pw + f * NF;
+      float acc = 0.f;
+      for (int k = 0; k < NF; k++) acc = fmaf(pr[k], __ldg(fl + k), acc);
+      float lv = log10f(fmaxf(acc, 1e-10f));
+      ob[(f0 + f) * n_mels + m] = lv;
+      lmax = fmaxf(lmax, lv);
+    }
+  }
+  lmax = warp_max(lmax);
+  if ((threadIdx.x & 31) == 0) bmax[threadIdx.x >> 5] = lmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = bmax[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) v = fmaxf(v, bmax[i]);
+    atomic_max_pos(gmax + b, v + 16.f);
+  }
+}
+
+__global__ void whisper_logmel_finish(float* __restrict__ out, const float* __restrict__ gmax, int64_t per_batch, int B) {
+  int64_t total = per_batch * B;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float mx = gmax[i / per_batch] - 16.f;
+    out[i] = (fmaxf(out[i], mx - 8.f) + 4.f) * 0.25f;
+  }
+}
+
+// inverse rFFT of every frame times the synthesis window -> ws [B, T, N]
+__global__ void irfft_frames_kernel(const float* __restrict__ re, const float* __restrict__ im, int N, int T,
+                                    const float* __restrict__ window, float* __restrict__ ws) {
+  extern __shared__ float sm[];
+  float* tw_c = sm; float* tw_s = sm + N; float* sr = sm + 2 * N; float* si = sr + (N / 2 + 1);
+  const int nf = N / 2 + 1, t = blockIdx.x, b = blockIdx.y;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) { float s, c; sincospif(2.f * i / N, &s, &c); tw_c[i] = c; tw_s[i] = s; }
+  for (int k = threadIdx.x; k < nf; k += blockDim.x) {
+    sr[k] = re[((int64_t)b * nf + k) * T + t]; si[k] = im[((int64_t)b * nf + k) * T + t];
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < N; m += blockDim.x) {
+    float acc = sr[0];
+    int ph = 0;
+    for (int k = 1; k < nf; k++) {
+      ph += m; if (ph >= N) ph -= N;
+      float wgt = (2 * k == N) ? 1.f : 2.f;              // Nyquist bin counted once; its imaginary part is ignored
+      float term = sr[k] * tw_c[ph] - ((2 * k == N) ? 0.f : si[k] * tw_s[ph]);
+      acc = fmaf(wgt, term, acc);
+    }
+    ws[((int64_t)b * T + t) * N + m] = acc / N * __ldg(window + m);
+  }
+}
+
+__global__ void ola_kernel(const float* __restrict__ ws, int N, int T, int hop, const float* __restrict__ window,
+                           int norm_sq, int clamp_mode, int64_t trim, int64_t out_len, float* __restrict__ out, int B) {
+  int64_t total = out_len * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / out_len);
+    int64_t pos = idx % out_len + trim;
+    int64_t f_hi = pos / hop; if (f_hi > T - 1) f_hi = T - 1;
+    int64_t f_lo = (pos - N + hop) / hop; if (pos - N + 1 <= 0) f_lo = 0; if (f_lo < 0) f_lo = 0;
+    float acc = 0.f, wsum = 0.f;
+    for (int64_t f = f_lo; f <= f_hi; f++) {
+      int m = (int)(pos - f * hop);
+      if (m < 0 || m >= N) continue;
+      acc += ws[((int64_t)b * T + f) * N + m];
+      float w = __ldg(window + m);
+      wsum += norm_sq ? w * w : w;
+    }
+    if (clamp_mode == 0) out[idx] = wsum > 1e-10f ? acc / wsum : acc;
+    else out[idx] = acc / fmaxf(wsum, 1e-10f);
+  }
+}
+
+// ---------------------------------------------------------------- Kokoro hn-NSF source
+constexpr int KH = 9;              // harmonics (fundamental + 8)
+constexpr int KUP = 300;           // samples per F0 frame
+constexpr double KSR = 24000.0;
+
+// cumulative phase (in cycles) per frame and harmonic: C[b,i,h] = sum_{j<=i} frac(f0[j]*(h+1)/sr)
+__global__ void ksrc_phase_kernel(const float* __restrict__ f0, int nF, double* __restrict__ ph) {
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double part[256];
+  const int per = (nF + nt - 1) / nt, beg = tid * per, end = min(nF, beg + per);
+  double s = 0;
+  for (int i = beg; i < end; i++) { double r = (double)f0[(int64_t)b * nF + i] * (h + 1) / KSR; s += r - floor(r); }
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) { double run = 0; for (int i = 0; i < nt; i++) { double v = part[i]; part[i] = run; run += v; } }
+  __syncthreads();
+  double run = part[tid];
+  for (int i = beg; i < end; i++) {
+    double r = (double)f0[(int64_t)b * nF + i] * (h + 1) / KSR; run += r - floor(r);
+    ph[((int64_t)b * nF + i) * KH + h] = run;
+  }
+}
+
+__global__ void ksrc_sample_kernel(const float* __restrict__ f0, int nF, const double* __restrict__ ph,
+                                   const float* __restrict__ noise, const float* __restrict__ lin_w,
+                                   const float* __restrict__ lin_b, float* __restrict__ src, int B) {
+  const int64_t n_s = (int64_t)nF * KUP, total = n_s * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / n_s); int64_t n = idx % n_s;
+    int fi = (int)(n / KUP);
+    float f0v = f0[(int64_t)b * nF + fi];
+    float uv = f0v > 10.f ? 1.f : 0.f;
+    // linear x300 upsample of the frame-rate phase (interpolate.py:94-115, align_corners False, coords clamped at 0)
+    double pos = ((double)n + 0.5) / KUP - 0.5; if (pos < 0) pos = 0;
+    int lo = (int)floor(pos); int hi = min(lo + 1, nF - 1); double fr = pos - lo;
+    const double* p_lo = ph + ((int64_t)b * nF + lo) * KH; const double* p_hi = ph + ((int64_t)b * nF + hi) * KH;
+    float namp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
+    float accv = lin_b[0];
+#pragma unroll
+    for (int h = 0; h < KH; h++) {
+      double cyc = ((1.0 - fr) * p_lo[h] + fr * p_hi[h]) * KUP;     // phase / 2pi
+      cyc -= floor(cyc);
+      float sv = (float)sinpi(2.0 * cyc) * 0.1f;
+      float nz = noise ? noise[idx * KH + h] : 0.f;
+      accv = fmaf(lin_w[h], sv * uv + namp * nz, accv);
+    }
+    src[idx] = tanhf(accv);
+  }
+}
+
+__constant__ double c_tw20_c[20], c_tw20_s[20], c_hann20[20];
+
+// STFT(n_fft 20, hop 5, periodic Hann, reflect centre) of the merged source -> |X| (11) | angle (11), float64 inside
+__global__ void ksrc_stft_kernel(const float* __restrict__ src, int64_t n_s, float* __restrict__ har, int B) {
+  const int64_t T = n_s / 5 + 1, total = T * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / T); int64_t t = idx % T;
+    const float* sp = src + (int64_t)b * n_s;
+    double xw[20];
+#pragma unroll
+    for (int i = 0; i < 20; i++) {
+      int64_t s = t * 5 + i - 10;
+      if (s < 0) s = -s; else if (s >= n_s) s = 2 * (n_s - 1) - s;
+      xw[i] = (double)sp[s] * c_hann20[i];
+    }
+    float* hp = har + idx * 22;
+#pragma unroll
+    for (int k = 0; k < 11; k++) {
+      double re = 0, im = 0;
+#pragma unroll
+      for (int i = 0; i < 20; i++) { int p = (k * i) % 20; re += xw[i] * c_tw20_c[p]; im -= xw[i] * c_tw20_s[p]; }
+      hp[k] = (float)sqrt(re * re + im * im);
+      hp[11 + k] = (float)atan2(im, re);
+    }
+  }
+}
+
+// conv_post output [T,22] -> waveform: spec = exp(x[:11]), phase = sin(x[11:]), X = spec*e^{j phase},
+// 20-point inverse rFFT, periodic Hann, overlap-add (hop 5), / sum w^2, trim 10 each side.
+__global__ void kokoro_istft_head_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int T,
+                                         float* __restrict__ audio, int B) {
+  const int64_t out_len = (int64_t)(T - 1) * 5, total = out_len * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int b = (int)(idx / out_len); int64_t pos = idx % out_len + 10;
+    int64_t f_hi = pos / 5; if (f_hi > T - 1) f_hi = T - 1;
+    int64_t f_lo = (pos - 19 + 4) / 5; if (f_lo < 0) f_lo = 0;
+    float acc = 0.f, wsum = 0.f;
+    for (int64_t f = f_lo; f <= f_hi; f++) {
+      int m = (int)(pos - f * 5);
+      if (m < 0 || m >= 20) continue;
+      const float* xp = x + (int64_t)b * x_bs + f * x_ld;
+      float tsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        float mag = expf(xp[k]);
+        float phs = sinf(xp[11 + k]);
+        float sn, cs; sincosf(phs, &sn, &cs);
+        int p = (k * m) % 20;
+        float c = (float)c_tw20_c[p], s = (float)c_tw20_s[p];
+        if (k == 0) tsum += mag * cs;
+        else if (k == 10) tsum += mag * cs * c;                      // Nyquist: real part only, cos(pi m)
+        else tsum += 2.f * mag * (cs * c - sn * s);
+      }
+      float w = (float)c_hann20[m];
+      acc = fmaf(tsum * 0.05f, w, acc);
+      wsum = fmaf(w, w, wsum);
+    }
+    audio[idx] = wsum > 1e-10f ? acc / wsum : acc;
+  }
+}
+
+bool g_tw20_init = false;
+void init_tw20() {
+  if (g_tw20_init) return;
+  double c[20], s[20], w[20];
+  for (int i = 0; i < 20; i++) {
+    c[i] = cos(2.0 * M_PI * i / 20.0); s[i] = sin(2.0 * M_PI * i / 20.0);
+    w[i] = 0.5 * (1.0 - cos(2.0 * M_PI * i / 20.0));                // periodic Hann(20), istftnet.py:469
+  }
+  cudaMemcpyToSymbol(c_tw20_c, c, sizeof(c)); cudaMemcpyToSymbol(c_tw20_s, s, sizeof(s)); cudaMemcpyToSymbol(c_hann20, w, sizeof(w));
+  g_tw20_init = true;
+}
+
+int grid_for(int64_t total, int bs) { int64_t g = (total + bs - 1) / bs; return (int)(g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g)); }
+
+}  // namespace
+
+extern "C" int32_t b2a_stft(const float* x, int64_t x_bs, int32_t B, int64_t n, const float* window, int32_t n_fft, int32_t hop,
+                            int32_t pad_mode, int64_t frames, float* out_re, float* out_im, void* stream) {
+  B2A_CHECK_ARG(x && window && out_re && out_im && B > 0 && n > 0 && hop > 0 && frames > 0, "bad pointers/shape");
+  B2A_CHECK_ARG(n_fft >= 2 && n_fft <= 4096 && n_fft % 2 == 0, "n_fft must be even and <= 4096");
+  if (pad_mode == 1) B2A_CHECK_ARG(n > n_fft / 2, "reflect padding needs n > n_fft/2");
+  size_t smem = (size_t)(2 + FT) * n_fft * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(stft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
+  dim3 grid(cdiv(frames, FT), B);
+  stft_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, x_bs, n, window, n_fft, hop, pad_mode, frames, out_re, out_im);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_whisper_logmel(const float* x, int64_t x_bs, int32_t B, int64_t n, int64_t padding, const float* window,
+                                      const float* filters, int32_t n_mels, int64_t frames, float* out, float* gmax, void* stream) {
+  B2A_CHECK_ARG(x && window && filters && out && gmax && B > 0 && n > 0 && padding >= 0 && frames > 0 && n_mels > 0, "bad pointers/shape");
+  B2A_CHECK_ARG(n + padding > 200, "reflect padding needs more than 200 samples");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(gmax, 0, sizeof(float) * B, st);
+  size_t smem = (size_t)((2 + FT) * 400 + FT * 201) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(whisper_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+  dim3 grid(cdiv(frames, FT), B);
+  whisper_logmel_kernel<<<grid, 256, smem, st>>>(x, x_bs, n, padding, window, filters, n_mels, frames, out, gmax);
+  int64_t per = frames * n_mels;
+  whisper_logmel_finish<<<grid_for(per * B, 256), 256, 0, st>>>(out, gmax, per, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_istft(const float* re, const float* im, int32_t B, int32_t n_fft, int32_t T, int32_t hop, const float* window,
+                             int32_t norm_sq, int32_t clamp_mode, int64_t trim, int64_t out_len, float* out, float* ws, void* stream) {
+  B2A_CHECK_ARG(re && im && window && out && ws && B > 0 && T > 0 && hop > 0 && out_len > 0 && trim >= 0, "bad pointers/shape");
+  B2A_CHECK_ARG(n_fft >= 2 && n_fft <= 4096 && n_fft % 2 == 0, "n_fft must be even and <= 4096");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t smem = (size_t)(2 * n_fft + 2 * (n_fft / 2 + 1)) * sizeof(float);
+  dim3 grid(T, B);
+  irfft_frames_kernel<<<grid, 128, smem, st>>>(re, im, n_fft, T, window, ws);
+  ola_kernel<<<grid_for(out_len * B, 256), 256, 0, st>>>(ws, n_fft, T, hop, window, norm_sq, clamp_mode, trim, out_len, out, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, const float* noise, const float* lin_w,
+                                     const float* lin_b, float* har, float* src_ws, double* ph_ws, void* stream) {
+  B2A_CHECK_ARG(f0 && lin_w && lin_b && har && src_ws && ph_ws && B > 0 && n_frames > 0, "bad pointers/shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  init_tw20();
+  ksrc_phase_kernel<<<dim3(KH, B), 256, 0, st>>>(f0, n_frames, ph_ws);
+  int64_t n_s = (int64_t)n_frames * KUP;
+  ksrc_sample_kernel<<<grid_for(n_s * B, 256), 256, 0, st>>>(f0, n_frames, ph_ws, noise, lin_w, lin_b, src_ws, B);
+  ksrc_stft_kernel<<<grid_for((n_s / 5 + 1) * B, 128), 128, 0, st>>>(src_ws, n_s, har, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t T, float* audio, void* stream) {
+  B2A_CHECK_ARG(x && audio && B > 0 && T > 1, "bad pointers/shape");
+  init_tw20();
+  kokoro_istft_head_kernel<<<grid_for((int64_t)(T - 1) * 5 * B, 256), 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, T, audio, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

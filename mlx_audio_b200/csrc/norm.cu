@@ -1,0 +1,106 @@
+// Normalisation kernels: InstanceNorm/AdaIN coefficient folding and row LayerNorm / RMSNorm
+// (include/b200audio.h: b2a_adain_coeffs, b2a_layernorm).  Statistics are accumulated in float64
+// so that var = E[x^2] - mean^2 stays exact for long sequences; the normalisation itself is
+// applied for free inside the consuming conv's prologue (conv.cu: Pre).
+#include "common.cuh"
+
+namespace {
+
+constexpr int ROWS_PER_CHUNK = 256;
+
+// grid (ceil(C/32), nchunk, B), block (32, 8): thread column c sums rows ty, ty+8, ...
+__global__ void adain_partial_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int L, int C,
+                                     double* __restrict__ ws, int nchunk) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+  const int r0 = chunk * ROWS_PER_CHUNK, r1 = min(L, r0 + ROWS_PER_CHUNK);
+  float a1 = 0.f, a2 = 0.f;                       // <= 32 rows per thread: fp32 partials are safe
+  if (c < C) {
+    const float* xp = x + (int64_t)b * x_bs + c;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) { float v = __ldg(xp + (int64_t)r * x_ld); a1 += v; a2 = fmaf(v, v, a2); }
+  }
+  s1[threadIdx.y][threadIdx.x] = a1; s2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double t1 = 0, t2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+    double* w = ws + (((int64_t)b * nchunk + chunk) * C + c) * 2;
+    w[0] = t1; w[1] = t2;
+  }
+}
+
+__global__ void adain_final_kernel(const double* __restrict__ ws, int nchunk, int L, int C, const float* __restrict__ gb,
+                                   float eps, float* __restrict__ scale, float* __restrict__ shift, int B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  int b = i / C, c = i % C;
+  double t1 = 0, t2 = 0;
+  for (int k = 0; k < nchunk; k++) { const double* w = ws + (((int64_t)b * nchunk + k) * C + c) * 2; t1 += w[0]; t2 += w[1]; }
+  double mean = t1 / L, var = t2 / L - mean * mean;
+  if (var < 0) var = 0;
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  double g = 1.0, be = 0.0;
+  if (gb) { g = 1.0 + (double)gb[(int64_t)b * 2 * C + c]; be = (double)gb[(int64_t)b * 2 * C + C + c]; }
+  double sc = g * rstd;
+  scale[i] = (float)sc;
+  shift[i] = (float)(be - sc * mean);
+}
+
+// one warp per row; C up to a few thousand
+__global__ void layernorm_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ res, int64_t res_ld,
+                                 float* __restrict__ y, int64_t y_ld, int64_t rows, int C, const float* __restrict__ w,
+                                 const float* __restrict__ bb, const float* __restrict__ ada, float eps, int rms,
+                                 int post_act, float post_p0) {
+  int64_t row = (int64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xp = x + row * x_ld;
+  const float* rp = res ? res + row * res_ld : nullptr;
+  float s1 = 0.f;
+  for (int c = lane; c < C; c += 32) { float v = xp[c] + (rp ? rp[c] : 0.f); s1 += v; }
+  s1 = warp_sum(s1);
+  const float mean = rms ? 0.f : s1 / C;
+  float s2 = 0.f;
+  for (int c = lane; c < C; c += 32) { float v = xp[c] + (rp ? rp[c] : 0.f) - mean; s2 = fmaf(v, v, s2); }
+  s2 = warp_sum(s2);
+  const float rstd = rsqrtf(s2 / C + eps);
+  float* yp = y + row * y_ld;
+  for (int c = lane; c < C; c += 32) {
+    float v = (xp[c] + (rp ? rp[c] : 0.f) - mean) * rstd;
+    if (ada) v = fmaf(1.f + ada[c], v, ada[C + c]);
+    else { if (w) v *= w[c]; if (bb) v += bb[c]; }
+    if (post_act) v = b2a_act(v, post_act, post_p0, 1.f, 1.f);
+    yp[c] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int64_t b2a_adain_ws_bytes(int32_t B, int32_t L, int32_t C) {
+  int64_t nchunk = (L + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  return (int64_t)B * nchunk * C * 2 * (int64_t)sizeof(double);
+}
+
+extern "C" int32_t b2a_adain_coeffs(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C,
+                                    const float* gb, float eps, float* scale, float* shift, void* ws, void* stream) {
+  B2A_CHECK_ARG(x && scale && shift && ws && B > 0 && L > 0 && C > 0, "bad pointers/shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  int nchunk = (L + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
+  dim3 grid(cdiv(C, 32), nchunk, B), block(32, 8);
+  adain_partial_kernel<<<grid, block, 0, st>>>(x, x_bs, x_ld, L, C, (double*)ws, nchunk);
+  adain_final_kernel<<<cdiv((int64_t)B * C, 256), 256, 0, st>>>((const double*)ws, nchunk, L, C, gb, eps, scale, shift, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_layernorm(const float* x, int64_t x_ld, const float* res, int64_t res_ld, float* y, int64_t y_ld,
+                                 int64_t rows, int32_t C, const float* w, const float* b, const float* ada, float eps,
+                                 int32_t rms, int32_t post_act, float post_p0, void* stream) {
+  B2A_CHECK_ARG(x && y && rows >= 0 && C > 0, "bad pointers/shape");
+  if (rows == 0) return B2A_OK;
+  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, x_ld, res, res_ld, y, y_ld, rows, C, w, b, ada, eps,
+                                                                      rms, post_act, post_p0);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

@@ -1,0 +1,355 @@
+"""Host-side wrappers: torch CUDA tensors -> C-ABI calls on torch's current stream.
+
+torch is plumbing only (device memory, streams); every compute op here is one of our sm_100a
+kernels.  All activations are float32 channels-last ``[B, L, C]``; tensors may be channel-slice
+views of wider buffers (row stride = ``stride(1)``), which is how concatenations are avoided.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import AttnParams, Conv1dParams
+
+ACT = {"none": 0, "lrelu": 1, "snake": 2, "elu": 3, "gelu": 4, "gelu_tanh": 5, "tanh": 6, "sigmoid": 7,
+       "silu": 8, "clip1": 9}
+
+LAUNCHES = [0]        # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk3(x: torch.Tensor, name: str):
+    if x.dtype != torch.float32 or not x.is_cuda or x.dim() != 3 or x.stride(2) != 1:
+        raise ValueError(f"{name}: expected a CUDA float32 [B, L, C] tensor with unit channel stride, got "
+                         f"{tuple(x.shape)} {x.dtype} {x.device} strides {x.stride()}")
+
+
+@dataclass
+class Pre:
+    """Input transform fused into a conv: x*scale[b,c]+shift[b,c] then an activation."""
+    scale: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+    act: int = 0
+    p0: float = 0.0
+    a: Optional[torch.Tensor] = None
+    b: Optional[torch.Tensor] = None
+
+
+@dataclass
+class ConvW:
+    """Packed conv weights: ``w`` float32 [K, Cin/groups, Cout] (depthwise: [K, C]), optional bias [Cout]."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    K: int
+    cin: int
+    cout: int
+    groups: int = 1
+
+
+def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
+    """MLX-layout conv weight [Cout, K, Cin/g] -> packed [K, Cin/g, Cout]."""
+    cout, k, cin_g = w_mlx.shape
+    if groups == 1:
+        w = w_mlx.permute(1, 2, 0).contiguous()
+        cin = cin_g
+    else:
+        if not (cin_g == 1 and groups == cout):
+            raise NotImplementedError("only dense or depthwise convolutions are on the hot path")
+        w = w_mlx[:, :, 0].t().contiguous()              # [K, C]
+        cin = cout
+    return ConvW(w.to(device=device, dtype=torch.float32), None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous(),
+                 k, cin, cout, groups)
+
+
+def pack_linear(w: torch.Tensor, bias=None, device="cuda") -> ConvW:
+    """nn.Linear weight [out, in] -> K=1 conv."""
+    return pack_conv(w[:, None, :], bias, 1, device)
+
+
+def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout=None, pad_mode=0,
+           pre: Optional[Pre] = None, post_act=0, post_p0=0.0, cscale=None, res=None, res_div=1,
+           out_scale=1.0, out=None, accumulate=False, transpose=False) -> torch.Tensor:
+    """b2a_conv1d_cl / b2a_convtr1d_cl.  For ``transpose`` ``pad_left`` is the left crop of the scatter output."""
+    _chk3(x, "conv1d x")
+    B, L, cin = x.shape
+    if cin != cw.cin:
+        raise ValueError(f"conv1d: input has {cin} channels, weight expects {cw.cin}")
+    if lout is None:
+        if transpose:
+            lout = (L - 1) * stride + cw.K - 2 * pad_left
+        else:
+            lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
+    if out is None:
+        out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
+    else:
+        _chk3(out, "conv1d out")
+        if out.shape != (B, lout, cw.cout):
+            raise ValueError(f"conv1d: out has shape {tuple(out.shape)}, expected {(B, lout, cw.cout)}")
+    p = Conv1dParams()
+    p.x, p.x_bs, p.x_ld = x.data_ptr(), x.stride(0), x.stride(1)
+    p.B, p.L, p.Cin = B, L, cin
+    p.w, p.bias = cw.w.data_ptr(), _p(cw.bias)
+    p.y, p.y_bs, p.y_ld = out.data_ptr(), out.stride(0), out.stride(1)
+    p.Lout, p.Cout = lout, cw.cout
+    p.K, p.stride, p.dilation, p.pad_left, p.groups, p.pad_mode = cw.K, stride, dilation, pad_left, cw.groups, pad_mode
+    if pre is not None:
+        p.pre_scale, p.pre_shift = _p(pre.scale), _p(pre.shift)
+        p.pre_act, p.pre_p0, p.pre_a, p.pre_b = pre.act, pre.p0, _p(pre.a), _p(pre.b)
+    p.post_act, p.post_p0 = post_act, post_p0
+    if cscale is not None:
+        p.post_cscale = cscale.data_ptr()
+        p.post_cscale_bs = cscale.stride(0) if cscale.dim() == 2 else 0
+    if res is not None:
+        _chk3(res, "conv1d res")
+        p.res, p.res_bs, p.res_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
+    p.res_div = res_div
+    p.out_scale, p.accumulate = out_scale, int(accumulate)
+    fn = _lib.lib().b2a_convtr1d_cl if transpose else _lib.lib().b2a_conv1d_cl
+    _lib.check(fn(C.byref(p), _stream()))
+    LAUNCHES[0] += 1
+    return out
+
+
+def linear(x: torch.Tensor, cw: ConvW, **kw) -> torch.Tensor:
+    """nn.Linear on [..., in] via the K=1 conv; accepts [rows, in] or [B, L, in]."""
+    if x.dim() == 2:
+        o = kw.get("out")
+        if o is not None and o.dim() == 2:
+            kw["out"] = o[None]
+        r = kw.get("res")
+        if r is not None and r.dim() == 2:
+            kw["res"] = r[None]
+        return conv1d(x[None], cw, **kw)[0]
+    return conv1d(x, cw, **kw)
+
+
+def copy2d(src: torch.Tensor, dst: torch.Tensor) -> None:
+    """dst[r, c] = src[r, c] for 2-D (row-strided) float32 views."""
+    rows, cols = src.shape
+    assert dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
+    _lib.check(_lib.lib().b2a_copy2d(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, _stream()))
+    LAUNCHES[0] += 1
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r, :] = src[idx[r], :]; src [N, C] float32, idx int64 [R]."""
+    assert src.dim() == 2 and src.stride(1) == 1 and idx.dtype == torch.int64 and idx.is_contiguous()
+    rows, cols = idx.shape[0], src.shape[1]
+    if out is None:
+        out = torch.empty(rows, cols, device=src.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b2a_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(), out.stride(0),
+                                          rows, cols, src.shape[0], _stream()))
+    LAUNCHES[0] += 1
+    return out
+
+
+def durations_to_index(dur, max_frames: int, speed: float = 1.0):
+    """Durations [T] (float32 pre-round sums, or int64 already-rounded) -> (pred_dur int64 [T], idx int64 [max_frames]
+    whose first `total` entries are valid, total int64 [1] on device)."""
+    assert dur.is_contiguous() and dur.dtype in (torch.float32, torch.int64)
+    T = dur.shape[0]
+    pred = torch.empty(T, device=dur.device, dtype=torch.int64)
+    idx = torch.zeros(max_frames, device=dur.device, dtype=torch.int64)
+    total = torch.zeros(1, device=dur.device, dtype=torch.int64)
+    f, i = (dur.data_ptr(), None) if dur.dtype == torch.float32 else (None, dur.data_ptr())
+    _lib.check(_lib.lib().b2a_durations_to_index(f, i, T, speed, pred.data_ptr(), idx.data_ptr(), max_frames, total.data_ptr(), _stream()))
+    LAUNCHES[0] += 1
+    return pred, idx, total
+
+
+_WS = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _WS[key] = ws
+    return ws
+
+
+def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5):
+    """InstanceNorm stats of x [B,L,C] folded with AdaIN (gamma|beta) [B,2C] -> (scale, shift) [B,C]."""
+    _chk3(x, "adain_coeffs x")
+    B, L, Cc = x.shape
+    scale = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    shift = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    ws = _workspace(_lib.lib().b2a_adain_ws_bytes(B, L, Cc), x.device)
+    _lib.check(_lib.lib().b2a_adain_coeffs(x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
+                                           scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream()))
+    LAUNCHES[0] += 2
+    return scale, shift
+
+
+def layernorm(x: torch.Tensor, w=None, b=None, *, eps=1e-5, res=None, ada=None, rms=False, post_act=0, post_p0=0.0,
+              out=None) -> torch.Tensor:
+    """Row LayerNorm / RMSNorm over the last dim of a 2-D row-strided view."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1]) if x.dim() != 2 else x
+    assert x2.stride(1) == 1
+    r2 = None
+    if res is not None:
+        r2 = res.reshape(-1, shp[-1]) if res.dim() != 2 else res
+    if out is None:
+        out = torch.empty(x2.shape, device=x.device, dtype=torch.float32)
+    o2 = out.reshape(-1, shp[-1]) if out.dim() != 2 else out
+    _lib.check(_lib.lib().b2a_layernorm(x2.data_ptr(), x2.stride(0), _p(r2), 0 if r2 is None else r2.stride(0), o2.data_ptr(),
+                                        o2.stride(0), x2.shape[0], shp[-1], _p(w), _p(b), _p(ada), eps, int(rms), post_act,
+                                        post_p0, _stream()))
+    LAUNCHES[0] += 1
+    return out.reshape(shp) if out.dim() == 2 and len(shp) != 2 else out
+
+
+def attention(q, k, v, *, n_heads, n_kv_heads=None, scale, causal=False, q_offset=0, window=0, k_len=None, out=None):
+    """softmax(scale q k^T + mask) v.  q [B,Tq,H*D], k/v [B,Tk,Hkv*D] (row-strided views allowed)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _chk3(t, "attention " + n)
+    B, Tq, hd = q.shape
+    H = n_heads
+    Hkv = n_kv_heads or H
+    D = hd // H
+    if out is None:
+        out = torch.empty(B, Tq, hd, device=q.device, dtype=torch.float32)
+    p = AttnParams()
+    p.q, p.k, p.v, p.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    p.q_bs, p.q_ld, p.k_bs, p.k_ld = q.stride(0), q.stride(1), k.stride(0), k.stride(1)
+    p.v_bs, p.v_ld, p.o_bs, p.o_ld = v.stride(0), v.stride(1), out.stride(0), out.stride(1)
+    p.B, p.Tq, p.Tk, p.H, p.Hkv, p.D = B, Tq, k.shape[1], H, Hkv, D
+    p.scale, p.causal, p.q_offset, p.window = scale, int(causal), q_offset, window
+    p.k_len = _p(k_len)
+    _lib.check(_lib.lib().b2a_attention(C.byref(p), _stream()))
+    LAUNCHES[0] += 1
+    return out
+
+
+def rope_(x: torch.Tensor, n_heads: int, *, offset=0, base=10000.0, traditional=True) -> torch.Tensor:
+    """In-place rotary embedding on x [B,T,H*D]."""
+    _chk3(x, "rope x")
+    B, T, hd = x.shape
+    _lib.check(_lib.lib().b2a_rope(x.data_ptr(), x.stride(0), x.stride(1), B, T, n_heads, hd // n_heads, offset, base,
+                                   int(traditional), _stream()))
+    LAUNCHES[0] += 1
+    return x
+
+
+def lstm_bidir(xproj: torch.Tensor, wh: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xproj [B,T,2*4H] (forward|backward input projections incl. biases), wh [2,4H,H] -> [B,T,2H]."""
+    B, T, g8 = xproj.shape
+    H = g8 // 8
+    assert xproj.is_contiguous() and wh.is_contiguous() and wh.shape == (2, 4 * H, H)
+    if out is None:
+        out = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
+    assert out.stride(2) == 1 and (B == 1 or out.stride(0) == T * out.stride(1))
+    _lib.check(_lib.lib().b2a_lstm_bidir(xproj.data_ptr(), wh.data_ptr(), out.data_ptr(), out.stride(1), B, T, H, _stream()))
+    LAUNCHES[0] += 1
+    return out
+
+
+def stft(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int, pad_mode: int, frames: int):
+    """x [B,n] -> (re, im) each [B, frames, n_fft//2+1]; pad_mode 0 none / 1 reflect / 2 constant."""
+    B, n = x.shape
+    assert x.stride(1) == 1 and window.shape[0] == n_fft
+    nf = n_fft // 2 + 1
+    re = torch.empty(B, frames, nf, device=x.device, dtype=torch.float32)
+    im = torch.empty(B, frames, nf, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b2a_stft(x.data_ptr(), x.stride(0), B, n, window.data_ptr(), n_fft, hop, pad_mode, frames,
+                                   re.data_ptr(), im.data_ptr(), _stream()))
+    LAUNCHES[0] += 1
+    return re, im
+
+
+def whisper_logmel(x: torch.Tensor, padding: int, window: torch.Tensor, filters: torch.Tensor, frames: int) -> torch.Tensor:
+    """x [B,n] float32 -> log-mel [B, frames, n_mels] (audio.py:41-82)."""
+    B, n = x.shape
+    assert x.stride(1) == 1 and filters.is_contiguous() and filters.shape[1] == 201
+    out = torch.empty(B, frames, filters.shape[0], device=x.device, dtype=torch.float32)
+    gmax = torch.empty(B, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b2a_whisper_logmel(x.data_ptr(), x.stride(0), B, n, padding, window.data_ptr(), filters.data_ptr(),
+                                             filters.shape[0], frames, out.data_ptr(), gmax.data_ptr(), _stream()))
+    LAUNCHES[0] += 2
+    return out
+
+
+def istft(re: torch.Tensor, im: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, *, norm_sq: bool, clamp_mode: int,
+          trim: int, out_len: int) -> torch.Tensor:
+    """re/im [B, n_freq, T] -> [B, out_len]."""
+    B, nf, T = re.shape
+    assert re.is_contiguous() and im.is_contiguous() and nf == n_fft // 2 + 1
+    out = torch.empty(B, out_len, device=re.device, dtype=torch.float32)
+    ws = torch.empty(B, T, n_fft, device=re.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b2a_istft(re.data_ptr(), im.data_ptr(), B, n_fft, T, hop, window.data_ptr(), int(norm_sq), clamp_mode,
+                                    trim, out_len, out.data_ptr(), ws.data_ptr(), _stream()))
+    LAUNCHES[0] += 2
+    return out
+
+
+def kokoro_source(f0: torch.Tensor, noise: Optional[torch.Tensor], lin_w: torch.Tensor, lin_b: torch.Tensor) -> torch.Tensor:
+    """F0 curve [B, nF] -> har [B, nF*60+1, 22] (magnitude | phase of the hn-NSF source STFT)."""
+    B, nF = f0.shape
+    assert f0.is_contiguous()
+    har = torch.empty(B, nF * 60 + 1, 22, device=f0.device, dtype=torch.float32)
+    src = torch.empty(B, nF * 300, device=f0.device, dtype=torch.float32)
+    ph = torch.empty(B, nF, 9, device=f0.device, dtype=torch.float64)
+    if noise is not None:
+        assert noise.is_contiguous() and noise.shape == (B, nF * 300, 9)
+    _lib.check(_lib.lib().b2a_kokoro_source(f0.data_ptr(), B, nF, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
+                                            src.data_ptr(), ph.data_ptr(), _stream()))
+    LAUNCHES[0] += 3
+    return har
+
+
+def kokoro_istft_head(x: torch.Tensor) -> torch.Tensor:
+    """conv_post output [B,T,22] -> waveform [B, (T-1)*5]."""
+    _chk3(x, "kokoro_istft_head x")
+    B, T, _ = x.shape
+    audio = torch.empty(B, (T - 1) * 5, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().b2a_kokoro_istft_head(x.data_ptr(), x.stride(0), x.stride(1), B, T, audio.data_ptr(), _stream()))
+    LAUNCHES[0] += 1
+    return audio
+
+
+def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch.Tensor] = None, check=True) -> torch.Tensor:
+    """codes int64 [B,nq,T], codebooks [nq,bins,dim] -> sum of gathers [B,T,dim]."""
+    assert codes.dtype == torch.int64 and codes.stride(2) == 1 and codebooks.is_contiguous()
+    B, nq, T = codes.shape
+    _, bins, dim = codebooks.shape
+    if out is None:
+        out = torch.empty(B, T, dim, device=codes.device, dtype=torch.float32)
+    err = torch.zeros(1, device=codes.device, dtype=torch.int32)
+    _lib.check(_lib.lib().b2a_rvq_decode(codes.data_ptr(), codes.stride(0), codes.stride(1), B, nq, T, codebooks.data_ptr(), bins,
+                                         dim, out.data_ptr(), out.stride(1), err.data_ptr(), _stream()))
+    LAUNCHES[0] += 1
+    if check and int(err.item()) != 0:
+        raise ValueError(f"rvq_decode: code index out of range [0, {bins})")
+    return out
+
+
+def snac_from_codes(codes, strides, embs, ws, biases, dim: int, check=True) -> torch.Tensor:
+    """SNAC quantizer.from_codes: codes[l] int64 [B, T/stride_l]; embs[l] [bins, cd]; ws[l] [cd, dim]; -> [B,T,dim]."""
+    n = len(codes)
+    B = codes[0].shape[0]
+    T = codes[-1].shape[1] * strides[-1]
+    bins, cd = embs[0].shape
+    out = torch.empty(B, T, dim, device=codes[0].device, dtype=torch.float32)
+    err = torch.zeros(1, device=out.device, dtype=torch.int32)
+    arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+    for c in codes:
+        assert c.dtype == torch.int64 and c.is_contiguous()
+    _lib.check(_lib.lib().b2a_snac_from_codes(arr(codes), (C.c_int32 * n)(*strides), n, arr(embs), arr(ws), arr(biases), B, T, bins,
+                                              cd, dim, out.data_ptr(), err.data_ptr(), _stream()))
+    LAUNCHES[0] += 1
+    if check and int(err.item()) != 0:
+        raise ValueError(f"snac_from_codes: code index out of range [0, {bins})")
+    return out

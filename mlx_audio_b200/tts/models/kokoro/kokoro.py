@@ -1,0 +1,465 @@
+"""Kokoro-82M on B200: ``Model(config)`` / ``load_weights`` / ``__call__`` / ``generate`` with the
+reference's signatures (tts/models/kokoro/kokoro.py:57-370) over our CUDA kernels.
+
+B200-first structure (not a translation of the MLX graph):
+  * one device-resident weight set, weight-norm folded once at load (the reference recomputes
+    g*v/||v|| every forward, istftnet.py:130) and rounded to the checkpoint's bf16 grid;
+  * activations channels-last fp32; "concatenations" are channel-slice views of one buffer;
+  * InstanceNorm/AdaIN statistics -> per-(batch,channel) scale/shift that the consuming conv applies
+    in its prologue together with Snake / LeakyReLU; residuals, 1/sqrt(2), the 1/3 resblock average
+    are conv epilogues -- every conv reads its input once and writes its output once;
+  * all 49 AdaIN / AdaLayerNorm style projections are ONE batched GEMV per utterance;
+  * the 6 BiLSTMs run as 8-CTA-cluster persistent recurrences (csrc/lstm.cu);
+  * the alignment matrix of kokoro.py:148-170 is a device prefix sum + row gather (one host read of
+    the frame count instead of one sync per phoneme).
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from numbers import Number
+from typing import Dict, Optional
+
+import torch
+
+from .... import ops
+from ....ops import ACT, ConvW, Pre
+from ..base import BaseModelArgs, GenerationResult, check_array_shape
+
+
+@dataclass
+class ModelConfig(BaseModelArgs):
+    """Reference: kokoro.py:39-54."""
+    istftnet: dict
+    dim_in: int
+    dropout: float
+    hidden_dim: int
+    max_conv_dim: int
+    max_dur: int
+    multispeaker: bool
+    n_layer: int
+    n_mels: int
+    n_token: int
+    style_dim: int
+    text_encoder_kernel_size: int
+    plbert: dict
+    vocab: Dict[str, int] = None
+    sample_rate: int = 24000
+
+
+def _bf16(x: torch.Tensor) -> torch.Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def fold_weight_norm(v: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """w = g * v / (||v|| + 1e-7) over all axes but 0 (istftnet.py:53-93), evaluated once in fp32 and
+    rounded to bf16 -- the dtype in which the reference's bf16 checkpoint evaluates it every forward."""
+    v32, g32 = v.float(), g.float()
+    nrm = torch.sqrt((v32 * v32).sum(dim=tuple(range(1, v.dim())), keepdim=True))
+    return _bf16(v32 / (nrm + 1e-7) * g32)
+
+
+class _AdaSlots:
+    """Collects every style->(gamma|beta) Linear so one GEMV serves the whole utterance."""
+
+    def __init__(self):
+        self.ws, self.bs, self.slices, self.off = [], [], {}, 0
+
+    def add(self, name, w, b):
+        n = w.shape[0]
+        self.ws.append(w.float())
+        self.bs.append(b.float())
+        self.slices[name] = (self.off, n)
+        self.off += n
+
+
+class Model:
+    """Drop-in for ``mlx_audio.tts.models.kokoro.Model`` (duck-typed protocol of utils.py:387-414)."""
+
+    REPO_ID = "prince-canuma/Kokoro-82M"
+
+    @dataclass
+    class Output:
+        audio: torch.Tensor
+        pred_dur: Optional[torch.Tensor] = None
+
+    def __init__(self, config: ModelConfig, repo_id: str = None, device="cuda"):
+        self.config = config
+        self.repo_id = repo_id
+        self.vocab = config.vocab or {}
+        self.device = torch.device(device)
+        self.context_length = config.plbert["max_position_embeddings"]
+        self._w = None
+        self._pipelines = {}
+        self.tap = None            # set to a dict to capture intermediates (parity tests)
+
+    # ------------------------------------------------------------------ protocol
+    @property
+    def sample_rate(self):
+        return self.config.sample_rate
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return self._raw
+
+    def sanitize(self, weights: dict) -> dict:
+        """PyTorch-checkpoint -> reference parameter tree (kokoro.py:179-276, istftnet.py:999-1011)."""
+        lstm_map = {"weight_ih_l0_reverse": "Wx_backward", "weight_hh_l0_reverse": "Wh_backward",
+                    "bias_ih_l0_reverse": "bias_ih_backward", "bias_hh_l0_reverse": "bias_hh_backward",
+                    "weight_ih_l0": "Wx_forward", "weight_hh_l0": "Wh_forward",
+                    "bias_ih_l0": "bias_ih_forward", "bias_hh_l0": "bias_hh_forward"}
+        out = {}
+        for key, val in weights.items():
+            if key.startswith("bert"):
+                if "position_ids" in key:
+                    continue
+                out[key] = val
+                continue
+            base, _, leaf = key.rpartition(".")
+            if leaf in lstm_map and (key.startswith("text_encoder") or key.startswith("predictor")):
+                out[f"{base}.{lstm_map[leaf]}"] = val
+            elif key.startswith("text_encoder") and leaf in ("gamma", "beta"):
+                out[f"{base}.{'weight' if leaf == 'gamma' else 'bias'}"] = val
+            elif "F0_proj.weight" in key or "N_proj.weight" in key:
+                out[key] = val.transpose(1, 2)
+            elif "noise_convs" in key and key.endswith(".weight"):
+                out[key] = val.transpose(1, 2)
+            elif "weight_v" in key:
+                out[key] = val if check_array_shape(val) else val.transpose(1, 2)
+            else:
+                out[key] = val
+        return out
+
+    def load_weights(self, weights, strict: bool = True):
+        """weights: list of (name, tensor) pairs or a dict, names = the reference's parameter tree."""
+        P = dict(weights)
+        self._raw = P
+        self._prepare(P, strict)
+        return self
+
+    # ------------------------------------------------------------------ weight preparation
+    def _cw(self, P, pre, *, groups=1, transpose_layout=False, bias=True) -> ConvW:
+        w = fold_weight_norm(P[pre + ".weight_v"], P[pre + ".weight_g"])
+        if transpose_layout:                       # ConvWeighted's `weight.T` branch (istftnet.py:159-166)
+            w = w.permute(2, 1, 0)
+        b = P.get(pre + ".bias") if bias else None
+        return ops.pack_conv(w, b, groups, self.device)
+
+    def _lin(self, P, pre, bias=True) -> ConvW:
+        return ops.pack_linear(P[pre + ".weight"].float(), P.get(pre + ".bias") if bias else None, self.device)
+
+    def _lstm(self, P, pre):
+        wx = torch.cat([P[f"{pre}.Wx_forward"], P[f"{pre}.Wx_backward"]], 0).float()               # [2*4H, In]
+        b = torch.cat([P[f"{pre}.bias_ih_forward"] + P[f"{pre}.bias_hh_forward"],
+                       P[f"{pre}.bias_ih_backward"] + P[f"{pre}.bias_hh_backward"]], 0).float()
+        wh = torch.stack([P[f"{pre}.Wh_forward"], P[f"{pre}.Wh_backward"]], 0).float().contiguous().to(self.device)
+        return ops.pack_linear(wx, b, self.device), wh
+
+    def _resblk1d(self, P, pre, ada, upsample=False):
+        blk = {"conv1": self._cw(P, pre + ".conv1"), "conv2": self._cw(P, pre + ".conv2"), "up": upsample, "name": pre}
+        ada.add(pre + ".norm1", P[pre + ".norm1.fc.weight"], P[pre + ".norm1.fc.bias"])
+        ada.add(pre + ".norm2", P[pre + ".norm2.fc.weight"], P[pre + ".norm2.fc.bias"])
+        if (pre + ".conv1x1.weight_v") in P:
+            blk["sc"] = self._cw(P, pre + ".conv1x1", bias=False)
+        if upsample:
+            blk["pool"] = self._cw(P, pre + ".pool", groups=P[pre + ".pool.weight_v"].shape[0])
+        return blk
+
+    def _resblock1(self, P, pre, ada, k, dils):
+        blk = {"k": k, "dils": dils, "name": pre, "c1": [], "c2": [], "a1": [], "a2": []}
+        for j in range(3):
+            blk["c1"].append(self._cw(P, f"{pre}.convs1.{j}"))
+            blk["c2"].append(self._cw(P, f"{pre}.convs2.{j}"))
+            ada.add(f"{pre}.adain1.{j}", P[f"{pre}.adain1.{j}.fc.weight"], P[f"{pre}.adain1.{j}.fc.bias"])
+            ada.add(f"{pre}.adain2.{j}", P[f"{pre}.adain2.{j}.fc.weight"], P[f"{pre}.adain2.{j}.fc.bias"])
+            for nm, lst in (("alpha1", "a1"), ("alpha2", "a2")):
+                a = P[f"{pre}.{nm}.{j}"].float().reshape(-1).to(self.device)
+                blk[lst].append((a.contiguous(), (1.0 / a).contiguous()))          # Snake: x + (1/a) sin^2(a x)
+        return blk
+
+    def _prepare(self, P, strict):
+        cfg, dev = self.config, self.device
+        W = {}
+        ada = _AdaSlots()
+        f = lambda t: t.float().to(dev).contiguous()
+        # --- ALBERT (modules.py:434-645)
+        B = "bert."
+        W["word_emb"] = f(P[B + "embeddings.word_embeddings.weight"])
+        W["pos_type"] = f(P[B + "embeddings.position_embeddings.weight"].float()
+                          + P[B + "embeddings.token_type_embeddings.weight"][0].float()[None])
+        W["emb_ln"] = (f(P[B + "embeddings.LayerNorm.weight"]), f(P[B + "embeddings.LayerNorm.bias"]))
+        W["map_in"] = self._lin(P, B + "encoder.embedding_hidden_mapping_in")
+        L = B + "encoder.albert_layer_groups.0.albert_layers.0."
+        wqkv = torch.cat([P[L + f"attention.{n}.weight"].float() for n in ("query", "key", "value")], 0)
+        bqkv = torch.cat([P[L + f"attention.{n}.bias"].float() for n in ("query", "key", "value")], 0)
+        W["qkv"] = ops.pack_linear(wqkv, bqkv, dev)
+        W["attn_out"] = self._lin(P, L + "attention.dense")
+        W["attn_ln"] = (f(P[L + "attention.LayerNorm.weight"]), f(P[L + "attention.LayerNorm.bias"]))
+        W["ffn"] = self._lin(P, L + "ffn")
+        W["ffn_out"] = self._lin(P, L + "ffn_output")
+        W["full_ln"] = (f(P[L + "full_layer_layer_norm.weight"]), f(P[L + "full_layer_layer_norm.bias"]))
+        W["bert_encoder"] = self._lin(P, "bert_encoder")
+        # --- prosody predictor (modules.py:288-411)
+        W["dur_lstms"] = []
+        for i in range(cfg.n_layer):
+            W["dur_lstms"].append(self._lstm(P, f"predictor.text_encoder.lstms.{2 * i}"))
+            ada.add(f"adaln.{i}", P[f"predictor.text_encoder.lstms.{2 * i + 1}.fc.weight"], P[f"predictor.text_encoder.lstms.{2 * i + 1}.fc.bias"])
+        W["pred_lstm"] = self._lstm(P, "predictor.lstm")
+        W["dur_proj"] = self._lin(P, "predictor.duration_proj.linear_layer")
+        W["dur_sum"] = ops.pack_linear(torch.ones(1, cfg.max_dur), None, dev)
+        W["shared"] = self._lstm(P, "predictor.shared")
+        for name in ("F0", "N"):
+            W[name] = [self._resblk1d(P, f"predictor.{name}.0", ada), self._resblk1d(P, f"predictor.{name}.1", ada, True),
+                       self._resblk1d(P, f"predictor.{name}.2", ada)]
+            W[name + "_proj"] = ops.pack_conv(P[f"predictor.{name}_proj.weight"].float(), P[f"predictor.{name}_proj.bias"], 1, dev)
+        # --- text encoder (modules.py:21-68)
+        W["te_emb"] = f(P["text_encoder.embedding.weight"])
+        W["te_cnn"] = [(self._cw(P, f"text_encoder.cnn.{i}.0"), f(P[f"text_encoder.cnn.{i}.1.weight"]), f(P[f"text_encoder.cnn.{i}.1.bias"]))
+                       for i in range(cfg.n_layer)]
+        W["te_lstm"] = self._lstm(P, "text_encoder.lstm")
+        # --- decoder (istftnet.py:936-997)
+        W["encode"] = self._resblk1d(P, "decoder.encode", ada)
+        W["decode"] = [self._resblk1d(P, f"decoder.decode.{i}", ada, (f"decoder.decode.{i}.pool.weight_v") in P) for i in range(4)]
+        W["F0_conv"] = self._cw(P, "decoder.F0_conv")
+        W["N_conv"] = self._cw(P, "decoder.N_conv")
+        W["asr_res"] = self._cw(P, "decoder.asr_res.0")
+        # --- generator (istftnet.py:725-835)
+        ist = cfg.istftnet
+        G = "decoder.generator"
+        W["src_lin"] = (f(P[G + ".m_source.l_linear.weight"]).reshape(-1), f(P[G + ".m_source.l_linear.bias"]).reshape(-1))
+        rates, ks, rk, rd = ist["upsample_rates"], ist["upsample_kernel_sizes"], ist["resblock_kernel_sizes"], ist["resblock_dilation_sizes"]
+        W["ups"], W["noise_convs"], W["noise_res"], W["resblocks"] = [], [], [], []
+        for i in range(len(rates)):
+            W["ups"].append(self._cw(P, f"{G}.ups.{i}", transpose_layout=True))
+            W["noise_convs"].append(ops.pack_conv(P[f"{G}.noise_convs.{i}.weight"].float(), P[f"{G}.noise_convs.{i}.bias"], 1, dev))
+            W["noise_res"].append(self._resblock1(P, f"{G}.noise_res.{i}", ada, 7 if i + 1 < len(rates) else 11, (1, 3, 5)))
+            for j in range(len(rk)):
+                W["resblocks"].append(self._resblock1(P, f"{G}.resblocks.{i * len(rk) + j}", ada, rk[j], tuple(rd[j])))
+        W["conv_post"] = self._cw(P, G + ".conv_post")
+        # --- one batched style projection
+        W["ada_all"] = ops.pack_linear(torch.cat(ada.ws, 0), torch.cat(ada.bs, 0), dev)
+        self._ada_slices = ada.slices
+        self._ada_pred = [k for k in ada.slices if k.startswith("adaln.") or k.startswith("predictor.")]
+        self._w = W
+
+    def _tap(self, name, t):
+        if self.tap is not None:
+            self.tap[name] = t.detach().clone()
+
+    # ------------------------------------------------------------------ building blocks
+    def _gb(self, name):
+        off, n = self._ada_slices[name]
+        src = self._gb_pred if name in self._pred_set else self._gb_dec
+        return src[:, off:off + n]
+
+    def _lstm_run(self, x2d, lw, out=None):
+        xproj = ops.linear(x2d, lw[0])                           # [T, 2*4H]
+        return ops.lstm_bidir(xproj[None], lw[1], out=None if out is None else out[None])[0]
+
+    def _adain_resblk1d(self, x, blk, out=None):
+        """AdainResBlk1d (istftnet.py:853-933) on x [1,L,Cin] -> [1,L or 2L,Cout]."""
+        s1, h1 = ops.adain_coeffs(x, self._gb(blk["name"] + ".norm1").contiguous())
+        pre1 = Pre(s1, h1, ACT["lrelu"], 0.2)
+        L = x.shape[1]
+        if blk["up"]:
+            r = ops.conv1d(x, blk["pool"], stride=2, pad_left=1, lout=2 * L, pre=pre1, transpose=True)
+            r = ops.conv1d(r, blk["conv1"], pad_left=1)
+        else:
+            r = ops.conv1d(x, blk["conv1"], pad_left=1, pre=pre1)
+        s2, h2 = ops.adain_coeffs(r, self._gb(blk["name"] + ".norm2").contiguous())
+        sc = ops.conv1d(x, blk["sc"]) if "sc" in blk else x
+        return ops.conv1d(r, blk["conv2"], pad_left=1, pre=Pre(s2, h2, ACT["lrelu"], 0.2), res=sc,
+                          res_div=2 if blk["up"] else 1, out_scale=1.0 / math.sqrt(2.0), out=out)
+
+    def _adain_resblock1(self, x, blk, out=None, out_scale=1.0, accumulate=False):
+        """AdaINResBlock1 (istftnet.py:341-396) on x [1,L,C]."""
+        k = blk["k"]
+        for j, d in enumerate(blk["dils"]):
+            s1, h1 = ops.adain_coeffs(x, self._gb(f"{blk['name']}.adain1.{j}").contiguous())
+            a, ia = blk["a1"][j]
+            xt = ops.conv1d(x, blk["c1"][j], dilation=d, pad_left=(k * d - d) // 2, pre=Pre(s1, h1, ACT["snake"], 0.0, a, ia))
+            s2, h2 = ops.adain_coeffs(xt, self._gb(f"{blk['name']}.adain2.{j}").contiguous())
+            a, ia = blk["a2"][j]
+            last = j == len(blk["dils"]) - 1
+            x = ops.conv1d(xt, blk["c2"][j], pad_left=(k - 1) // 2, pre=Pre(s2, h2, ACT["snake"], 0.0, a, ia), res=x,
+                           out=out if last else None, out_scale=out_scale if last else 1.0, accumulate=accumulate and last)
+        return x
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward_ids(self, input_ids, ref_s, speed: float = 1.0, *, noise=None, pred_dur=None, n_frames: Optional[int] = None):
+        """Token ids (BOS/EOS 0 included) + style [1,256] -> (audio [samples], pred_dur int64 [T]).
+
+        ``noise`` [1, 600F, 9] injects the SineGen Gaussian (istftnet.py:649); None -> noiseless source
+        (production draws Philox noise with torch).  ``pred_dur`` overrides the duration head.
+        ``n_frames``: the caller already knows sum(pred_dur) (CUDA-graph capture) -> no host sync.
+        """
+        W, cfg, dev = self._w, self.config, self.device
+        if W is None:
+            raise RuntimeError("Kokoro: load_weights() has not been called")
+        ids = torch.as_tensor(input_ids, dtype=torch.int64, device=dev).reshape(-1).contiguous()
+        T = ids.shape[0]
+        assert T <= self.context_length, (T, self.context_length)
+        ref_s = ref_s.to(device=dev, dtype=torch.float32).reshape(1, -1).contiguous()
+        s_dec, s_pred = ref_s[:, :128].contiguous(), ref_s[:, 128:].contiguous()
+        self._pred_set = set(self._ada_pred)
+        self._gb_pred = ops.linear(s_pred, W["ada_all"])              # [1, sum 2C]  (all style projections at once)
+        self._gb_dec = ops.linear(s_dec, W["ada_all"])
+        hd = cfg.hidden_dim
+        # ---- ALBERT
+        e = ops.gather_rows(W["word_emb"], ids)
+        e = ops.layernorm(e, *W["emb_ln"], eps=1e-12, res=W["pos_type"][:T])
+        h = ops.linear(e, W["map_in"])
+        nh = cfg.plbert["num_attention_heads"]
+        hs = cfg.plbert["hidden_size"]
+        for _ in range(cfg.plbert["num_hidden_layers"]):
+            qkv = ops.linear(h, W["qkv"])[None]                       # [1,T,3*hs]
+            ctx = ops.attention(qkv[:, :, :hs], qkv[:, :, hs:2 * hs], qkv[:, :, 2 * hs:], n_heads=nh, scale=1.0 / math.sqrt(hs // nh))[0]
+            a = ops.linear(ctx, W["attn_out"], res=h)
+            a = ops.layernorm(a, *W["attn_ln"], eps=1e-12)
+            f1 = ops.linear(a, W["ffn"], post_act=ACT["gelu"])
+            f2 = ops.linear(f1, W["ffn_out"], res=a)
+            h = ops.layernorm(f2, *W["full_ln"], eps=1e-12)
+        self._tap("bert", h)
+        # ---- duration encoder: X640 = [d_en | style]
+        st = cfg.style_dim
+        X = torch.empty(T, hd + st, device=dev, dtype=torch.float32)
+        ops.linear(h, W["bert_encoder"], out=X[:, :hd])
+        ops.copy2d(s_pred.expand(T, st), X[:, hd:])
+        for i in range(cfg.n_layer):
+            o = self._lstm_run(X, W["dur_lstms"][i])
+            ops.layernorm(o, eps=1e-5, ada=self._gb(f"adaln.{i}").reshape(-1).contiguous(), out=X[:, :hd])
+        xl = self._lstm_run(X, W["pred_lstm"])
+        dsig = ops.linear(xl, W["dur_proj"], post_act=ACT["sigmoid"])
+        dsum = ops.linear(dsig, W["dur_sum"]).reshape(-1).contiguous()
+        self._tap("d", X)
+        self._tap("dur", dsum)
+        max_frames = 100 * T
+        if pred_dur is not None:
+            pd = torch.as_tensor(pred_dur, dtype=torch.int64, device=dev).contiguous()
+            pred, idx, total = ops.durations_to_index(pd, max_frames)
+        else:
+            pred, idx, total = ops.durations_to_index(dsum, max_frames, float(speed))
+        F = int(total.item()) if n_frames is None else int(n_frames)   # the one host sync of the utterance
+        if F <= 0:
+            return torch.zeros(1, device=dev), pred
+        idx = idx[:F]
+        # ---- F0 / N prediction
+        en = ops.gather_rows(X, idx)                                   # [F,640]  == d^T @ aln
+        xs = self._lstm_run(en, W["shared"])[None]                     # [1,F,512]
+        F0N = torch.empty(2, 2 * F, 1, device=dev, dtype=torch.float32)
+        for n_i, name in enumerate(("F0", "N")):
+            hcur = xs
+            for blk in W[name]:
+                hcur = self._adain_resblk1d(hcur, blk)
+            ops.conv1d(hcur, W[name + "_proj"], out=F0N[n_i:n_i + 1])
+        f0_curve, n_curve = F0N[0:1], F0N[1:2]                         # [1,2F,1]
+        self._tap("en", en)
+        self._tap("F0", f0_curve)
+        self._tap("N", n_curve)
+        # ---- text encoder
+        te = ops.gather_rows(W["te_emb"], ids)[None]
+        k = cfg.text_encoder_kernel_size
+        for cw, lw, lb in W["te_cnn"]:
+            te = ops.conv1d(te, cw, pad_left=(k - 1) // 2)
+            te = ops.layernorm(te, lw, lb, eps=1e-5, post_act=ACT["lrelu"], post_p0=0.2)
+        t_en = self._lstm_run(te[0], W["te_lstm"])                     # [T,512]
+        self._tap("t_en", t_en)
+        # ---- decoder
+        b514 = torch.empty(1, F, hd + 2, device=dev, dtype=torch.float32)
+        ops.gather_rows(t_en, idx, out=b514[0, :, :hd])                # asr = t_en @ aln
+        ops.conv1d(f0_curve, W["F0_conv"], stride=2, pad_left=1, out=b514[:, :, hd:hd + 1])
+        ops.conv1d(n_curve, W["N_conv"], stride=2, pad_left=1, out=b514[:, :, hd + 1:hd + 2])
+        bufs = [torch.empty(1, F, 1024 + 64 + 2, device=dev, dtype=torch.float32) for _ in range(2)]
+        ops.conv1d(b514[:, :, :hd], W["asr_res"], out=bufs[0][:, :, 1024:1088])
+        ops.copy2d(b514[0, :, hd:], bufs[0][0, :, 1088:])
+        ops.copy2d(bufs[0][0, :, 1024:], bufs[1][0, :, 1024:])
+        self._adain_resblk1d(b514, W["encode"], out=bufs[0][:, :, :1024])
+        self._tap("dec_encode", bufs[0][:, :, :1024])
+        cur = 0
+        x = None
+        for i, blk in enumerate(W["decode"]):
+            if blk["up"]:
+                x = self._adain_resblk1d(bufs[cur], blk)              # [1,2F,512]
+            else:
+                self._adain_resblk1d(bufs[cur], blk, out=bufs[1 - cur][:, :, :1024])
+                cur = 1 - cur
+        self._tap("dec_out", x)
+        # ---- generator
+        ist = cfg.istftnet
+        rates, ks = ist["upsample_rates"], ist["upsample_kernel_sizes"]
+        har = ops.kokoro_source(f0_curve.reshape(1, 2 * F), noise, *W["src_lin"])      # [1,120F+1,22]
+        self._tap("har", har)
+        nk = len(ist["resblock_kernel_sizes"])
+        for i, (u, kk) in enumerate(zip(rates, ks)):
+            last = i == len(rates) - 1
+            if not last:
+                sf0 = math.prod(rates[i + 1:])
+                xsrc = ops.conv1d(har, W["noise_convs"][i], stride=sf0, pad_left=(sf0 + 1) // 2)
+            else:
+                xsrc = ops.conv1d(har, W["noise_convs"][i])
+            xsrc = self._adain_resblock1(xsrc, W["noise_res"][i])
+            L = x.shape[1]
+            lout = (L - 1) * u + kk - 2 * ((kk - u) // 2)
+            cout = W["ups"][i].cout
+            if last:                                                   # "ReflectionPad1d((1,0))" is a zero pad on the left
+                y = torch.empty(1, lout + 1, cout, device=dev, dtype=torch.float32)
+                ops.copy2d(xsrc[0, :1], y[0, :1])
+                ops.conv1d(x, W["ups"][i], stride=u, pad_left=(kk - u) // 2, pre=Pre(act=ACT["lrelu"], p0=0.1), transpose=True,
+                           res=xsrc[:, 1:], out=y[:, 1:])
+            else:
+                y = ops.conv1d(x, W["ups"][i], stride=u, pad_left=(kk - u) // 2, pre=Pre(act=ACT["lrelu"], p0=0.1), transpose=True, res=xsrc)
+            acc = torch.empty_like(y)
+            for j in range(nk):
+                self._adain_resblock1(y, W["resblocks"][i * nk + j], out=acc, out_scale=1.0 / nk, accumulate=j > 0)
+            x = acc
+            self._tap(f"gen_stage{i}", x)
+        xpost = ops.conv1d(x, W["conv_post"], pad_left=3, pre=Pre(act=ACT["lrelu"], p0=0.01))
+        self._tap("xpost", xpost)
+        audio = ops.kokoro_istft_head(xpost)[0]
+        return audio, pred
+
+    def __call__(self, phonemes: str, ref_s, speed: Number = 1, return_output: bool = False, decoder=None, **kw):
+        """kokoro.py:111-177: phoneme string -> waveform [1, samples] (or Output)."""
+        ids = [i for i in (self.vocab.get(p) for p in phonemes) if i is not None]
+        assert len(ids) + 2 <= self.context_length, (len(ids) + 2, self.context_length)
+        audio, pred = self.forward_ids([0, *ids, 0], ref_s, float(speed), **kw)
+        audio = audio[None]
+        return self.Output(audio=audio, pred_dur=pred) if return_output else audio
+
+    # ------------------------------------------------------------------ generate (kokoro.py:293-370)
+    def generate(self, text: str, voice=None, speed: float = 1.0, lang_code: str = "a", split_pattern: str = r"\n+", **kwargs):
+        """Generator of GenerationResult.  G2P (misaki) is host-side and outside the hot path; when it is
+        unavailable pass ``phonemes=...`` and ``ref_s=...`` (or a voice pack tensor [N,1,256] as ``voice``)."""
+        phonemes = kwargs.pop("phonemes", None)
+        ref_s = kwargs.pop("ref_s", None)
+        if phonemes is None:
+            try:
+                from misaki import en  # noqa: F401
+            except ImportError as e:
+                raise ImportError("Kokoro G2P needs `misaki` (pip install misaki[en]); or call generate(text, phonemes=..., ref_s=...)") from e
+            raise NotImplementedError("misaki G2P bridge is host-side glue outside the accelerated path")
+        segments = phonemes if isinstance(phonemes, (list, tuple)) else [phonemes]
+        start = time.time()
+        for seg_idx, ps in enumerate(segments):
+            rs = ref_s
+            if rs is None:
+                if not isinstance(voice, torch.Tensor):
+                    raise ValueError("pass ref_s [1,256] or a voice pack tensor [N,1,256] as `voice`")
+                rs = voice[len(ps) - 1]                                # pipeline.py:303
+            audio = self(ps, rs, speed)
+            torch.cuda.synchronize(self.device)
+            now = time.time()
+            seg_t, start = now - start, now
+            samples = audio.shape[1]
+            dur = samples / self.sample_rate
+            yield GenerationResult(
+                audio=audio[0], samples=samples, sample_rate=self.sample_rate, segment_idx=seg_idx, token_count=len(ps),
+                audio_duration=f"{int(dur // 3600):02d}:{int(dur // 60) % 60:02d}:{int(dur % 60):02d}.{int((dur % 1) * 1000):03d}",
+                real_time_factor=round(seg_t / dur, 2) if dur > 0 else 0,
+                prompt={"tokens": len(ps), "tokens-per-sec": round(len(ps) / seg_t, 2) if seg_t > 0 else 0},
+                audio_samples={"samples": samples, "samples-per-sec": round(samples / seg_t, 2) if seg_t > 0 else 0},
+                processing_time_seconds=seg_t, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)

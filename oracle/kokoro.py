@@ -19,6 +19,13 @@ import torch
 from . import dsp as D
 from . import nn as N
 
+TAP = None   # set to a dict to capture intermediates (tests only)
+
+
+def _tap(name, value):
+    if TAP is not None:
+        TAP[name] = value
+
 # ----------------------------------------------------------------------------- config
 
 KOKORO_CONFIG = {   # tts/tests/test_models.py:143-173 (the public Kokoro-82M config)
@@ -262,6 +269,7 @@ def generator(P, pre, x, s, f0_curve, cfg, rand_ini, noise):
     har_src = torch.tanh(N.linear(sw, P[pre + ".m_source.l_linear.weight"], P[pre + ".m_source.l_linear.bias"]))[:, :, 0]
     mag, ph = mlxstft_transform(har_src.numpy(), n_fft, hop, n_fft)
     har = torch.as_tensor(np.concatenate([mag, ph], axis=1)).to(dt).transpose(1, 2)        # NLC [B, T, 22]
+    _tap("har", har)
     nk = len(rk)
     for i in range(len(rates)):
         x = N.leaky_relu(x, 0.1)
@@ -282,8 +290,11 @@ def generator(P, pre, x, s, f0_curve, cfg, rand_ini, noise):
             r = adain_resblock1(P, f"{pre}.resblocks.{i * nk + j}", x, s, rk[j], rd[j])
             acc = r if acc is None else acc + r
         x = acc / nk
+        _tap(f"gen_stage{i}", x.transpose(1, 2))
     x = N.leaky_relu(x, 0.01)
+    _tap("gen_pre_post", x.transpose(1, 2))
     x = conv_weighted(P, pre + ".conv_post", x.transpose(1, 2), padding=3).transpose(1, 2)
+    _tap("xpost", x.transpose(1, 2))
     nb = n_fft // 2 + 1
     spec = torch.exp(x[:, :nb])
     phase = torch.sin(x[:, nb:])
@@ -297,6 +308,7 @@ def decoder(P, asr, f0_curve, n_curve, s, cfg, rand_ini, noise):
     nn_ = conv_weighted(P, pre + ".N_conv", n_curve[:, :, None], stride=2, padding=1).transpose(1, 2)
     x = torch.cat([asr, f0, nn_], dim=1)
     x = adain_resblk1d(P, pre + ".encode", x, s)
+    _tap("dec_encode", x.transpose(1, 2))
     asr_res = conv_weighted(P, pre + ".asr_res.0", asr.transpose(1, 2), padding=0).transpose(1, 2)
     res = True
     for i in range(4):
@@ -306,6 +318,7 @@ def decoder(P, asr, f0_curve, n_curve, s, cfg, rand_ini, noise):
         x = adain_resblk1d(P, pre + f".decode.{i}", x, s, upsample=up)
         if up:
             res = False
+    _tap("dec_out", x.transpose(1, 2))
     return generator(P, pre + ".generator", x, s, f0_curve, cfg, rand_ini, noise)
 
 # ----------------------------------------------------------------------------- text side
