@@ -1,0 +1,131 @@
+"""SNAC multi-scale RVQ codec, decode side, on B200 (reference: codec/models/snac/{snac,layers,vq}.py).
+
+``SNAC(**config).load_weights(...)``, ``decode(codes) -> [B, T_out, 1]`` with the reference's
+signature (snac.py:101-104).  Weight-norm is folded once at load; every Snake, bias, residual add
+and NoiseBlock gain is a conv prologue/epilogue; the three codebook levels are gathered, projected,
+repeat-interleaved and summed by one kernel (b2a_snac_from_codes).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+
+from ... import ops
+from ...ops import ACT, Pre
+
+
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _fold_wn(v, g, except_dim=0):
+    """snac/layers.py:9-14,57: g * v / ||v||; evaluated once in fp32 and rounded to the bf16 grid."""
+    v, g = v.float(), g.float()
+    axes = tuple(i for i in range(v.dim()) if i != except_dim)
+    return _bf16(g * v / torch.sqrt((v * v).sum(dim=axes, keepdim=True)))
+
+
+class SNAC:
+    def __init__(self, sampling_rate=44100, encoder_dim=64, encoder_rates=(3, 3, 7, 7), latent_dim=None, decoder_dim=1536,
+                 decoder_rates=(7, 7, 3, 3), attn_window_size=32, codebook_size=4096, codebook_dim=8, vq_strides=(8, 4, 2, 1),
+                 noise=True, depthwise=True, device="cuda"):
+        self.sampling_rate = sampling_rate
+        self.encoder_dim, self.encoder_rates = encoder_dim, list(encoder_rates)
+        self.decoder_dim, self.decoder_rates = decoder_dim, list(decoder_rates)
+        self.latent_dim = latent_dim or encoder_dim * (2 ** len(encoder_rates))
+        self.hop_length = math.prod(encoder_rates)
+        self.codebook_size, self.codebook_dim, self.vq_strides = codebook_size, codebook_dim, list(vq_strides)
+        self.n_codebooks = len(vq_strides)
+        self.attn_window_size, self.noise, self.depthwise = attn_window_size, noise, depthwise
+        if attn_window_size is not None:
+            raise NotImplementedError("SNAC LocalMHA (attn_window_size) is outside the accelerated configs (24 kHz model has none)")
+        self.device = torch.device(device)
+        self._w = None
+
+    @classmethod
+    def from_config(cls, config: dict, device="cuda"):
+        return cls(**config, device=device)
+
+    @property
+    def sample_rate(self):
+        return self.sampling_rate
+
+    def load_weights(self, weights, strict=True):
+        P = dict(weights)
+        dev = self.device
+        f = lambda t: t.float().to(dev).contiguous()
+
+        def wnconv(pre, groups=1):
+            return ops.pack_conv(_fold_wn(P[pre + ".weight_v"], P[pre + ".weight_g"]), P.get(pre + ".bias"), groups, dev)
+
+        def snake(name):
+            a = P[name].float().reshape(-1)
+            return f(a), f(1.0 / (a + 1e-9))                                   # x + sin(a x)^2 / (a + 1e-9), layers.py:124-130
+
+        W = {"emb": [], "proj_w": [], "proj_b": []}
+        for i in range(self.n_codebooks):
+            q = f"quantizer.quantizers.{i}"
+            W["emb"].append(f(P[q + ".codebook.weight"]))
+            w = _fold_wn(P[q + ".out_proj.weight_v"], P[q + ".out_proj.weight_g"])      # [D,1,cd]
+            W["proj_w"].append(f(w[:, 0, :].t()))                                          # [cd, D]
+            W["proj_b"].append(f(P[q + ".out_proj.bias"]))
+        pre = "decoder.model.layers"
+        li = 0
+        if self.depthwise:
+            W["in_dw"] = wnconv(f"{pre}.{li}", groups=self.latent_dim); li += 1
+            W["in_pw"] = wnconv(f"{pre}.{li}"); li += 1
+        else:
+            W["in_pw"] = wnconv(f"{pre}.{li}"); li += 1
+        W["blocks"] = []
+        for i, stride in enumerate(self.decoder_rates):
+            cout = self.decoder_dim // (2 ** (i + 1))
+            bp = f"{pre}.{li}.block.layers"; li += 1
+            blk = {"stride": stride, "snake": snake(f"{bp}.0.alpha")}
+            wt = _fold_wn(P[f"{bp}.1.weight_v"], P[f"{bp}.1.weight_g"], except_dim=0).permute(2, 1, 0)     # (in,K,out)->(out,K,in)
+            blk["up"] = ops.pack_conv(wt, P.get(f"{bp}.1.bias"), 1, dev)
+            bi = 2
+            if self.noise:
+                blk["noise"] = wnconv(f"{bp}.{bi}.linear"); bi += 1
+            blk["res"] = []
+            for d in (1, 3, 9):
+                rp = f"{bp}.{bi}.block.layers"; bi += 1
+                blk["res"].append({"d": d, "s1": snake(rp + ".0.alpha"), "c1": wnconv(rp + ".1", groups=cout if self.depthwise else 1),
+                                   "s2": snake(rp + ".2.alpha"), "c2": wnconv(rp + ".3")})
+            W["blocks"].append(blk)
+        W["out_snake"] = snake(f"{pre}.{li}.alpha"); li += 1
+        W["out_conv"] = wnconv(f"{pre}.{li}")
+        self._w = W
+        return self
+
+    @torch.no_grad()
+    def decode(self, codes: List[torch.Tensor], noises: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+        """snac.py:101-104.  codes[l] int64 [B, T/stride_l] -> audio [B, T_out, 1].
+        ``noises[i]`` [B,1,C_i] injects the NoiseBlock draw (one per channel, layers.py:261-267); None draws it."""
+        W, dev = self._w, self.device
+        codes = [c.to(device=dev, dtype=torch.int64).contiguous() for c in codes]
+        z = ops.snac_from_codes(codes, self.vq_strides, W["emb"], W["proj_w"], W["proj_b"], self.latent_dim)     # [B,T,latent]
+        B = z.shape[0]
+        x = ops.conv1d(z, W["in_dw"], pad_left=3) if self.depthwise else z
+        x = ops.conv1d(x, W["in_pw"], pad_left=0 if self.depthwise else 3)
+        for i, blk in enumerate(W["blocks"]):
+            s = blk["stride"]
+            L = x.shape[1]
+            p = math.ceil(s / 2)
+            lout = (L - 1) * s - 2 * p + (2 * s - 1) + 1 + 1          # output_padding = 1 (the reference's positional-arg quirk)
+            a, ia = blk["snake"]
+            y = ops.conv1d(x, blk["up"], stride=s, pad_left=p, lout=lout, pre=Pre(act=ACT["snake"], a=a, b=ia), transpose=True)
+            if self.noise:
+                nz = noises[i] if noises is not None else torch.randn(B, 1, y.shape[2], device=dev)
+                nz = nz.to(device=dev, dtype=torch.float32).reshape(B, -1).contiguous()
+                y = ops.conv1d(y, blk["noise"], cscale=nz, res=y)                   # x + noise * linear(x)
+            for ru in blk["res"]:
+                t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=Pre(act=ACT["snake"], a=ru["s1"][0], b=ru["s1"][1]))
+                y = ops.conv1d(t, ru["c2"], pre=Pre(act=ACT["snake"], a=ru["s2"][0], b=ru["s2"][1]), res=y)
+            x = y
+        a, ia = W["out_snake"]
+        return ops.conv1d(x, W["out_conv"], pad_left=3, pre=Pre(act=ACT["snake"], a=a, b=ia), post_act=ACT["tanh"])
+
+    def encode(self, audio_data):
+        raise NotImplementedError("SNAC.encode is the 'next' row 2 of SURVEY.md section 8f (codec encode side)")

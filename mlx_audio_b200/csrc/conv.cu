@@ -41,9 +41,9 @@ __device__ __forceinline__ Pre make_pre(const b2a_conv1d_t& p) {
 template <int BN>
 __global__ void __launch_bounds__(NT) conv1d_dense_kernel(const b2a_conv1d_t p, int CI, int rows) {
   constexpr int NJ = BN / 16;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* xs = smem;                                   // [rows][CI+1]
-  float* ws = smem + (size_t)rows * (CI + 1);         // [K][CI][BN]
+  float* ws = smem + (((size_t)rows * (CI + 1) + 3) & ~(size_t)3);   // [K][CI][BN], 16-byte aligned for float4 reads
   const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
   const int l0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
   const Pre pre = make_pre(p);
@@ -135,9 +135,9 @@ __global__ void __launch_bounds__(NT) conv1d_dw_kernel(const b2a_conv1d_t p) {
 // k = q%s + j*s from input rows q/s - j.  Tile = 64 positions x 64 channels.
 __global__ void __launch_bounds__(NT) convtr1d_dense_kernel(const b2a_conv1d_t p, int CI, int rows, int J) {
   constexpr int BN = 64;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* xs = smem;                                   // [rows][CI+1]
-  float* ws = smem + (size_t)rows * (CI + 1);         // [K][CI][BN]
+  float* ws = smem + (((size_t)rows * (CI + 1) + 3) & ~(size_t)3);   // [K][CI][BN], 16-byte aligned for float4 reads
   const int tid = threadIdx.x, tn = tid & 15, tm = tid >> 4;
   const int l0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
   const int s = p.stride;
@@ -288,7 +288,7 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
     const int CI = p->K <= 4 ? 32 : (p->K <= 12 ? 16 : 8);
     const int rows = (BM - 1) * p->stride + (p->K - 1) * p->dilation + 1;
     const int BN = p->Cout > 16 ? 64 : 16;
-    size_t smem = ((size_t)rows * (CI + 1) + (size_t)p->K * CI * BN) * sizeof(float);
+    size_t smem = ((((size_t)rows * (CI + 1) + 3) & ~(size_t)3) + (size_t)p->K * CI * BN) * sizeof(float);
     if (smem > 200 * 1024) { b2a_set_error("b2a_conv1d_cl: tile needs %zu B of shared memory", smem); return B2A_E_UNSUPPORTED; }
     dim3 grid(cdiv(p->Lout, BM), cdiv(p->Cout, BN), p->B);
     if (BN == 64) {
@@ -322,7 +322,7 @@ extern "C" int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream) {
     const int CI = p->K <= 12 ? 16 : 8;
     const int J = (p->K + p->stride - 1) / p->stride;
     const int rows = (BM - 1) / p->stride + J + 1;
-    size_t smem = ((size_t)rows * (CI + 1) + (size_t)p->K * CI * 64) * sizeof(float);
+    size_t smem = ((((size_t)rows * (CI + 1) + 3) & ~(size_t)3) + (size_t)p->K * CI * 64) * sizeof(float);
     if (smem > 200 * 1024) { b2a_set_error("b2a_convtr1d_cl: tile needs %zu B of shared memory", smem); return B2A_E_UNSUPPORTED; }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(convtr1d_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }

@@ -47,7 +47,7 @@ __device__ void dft_frames(const float* __restrict__ x, int64_t n, int64_t n_tot
 
 __global__ void stft_kernel(const float* __restrict__ x, int64_t x_bs, int64_t n, const float* __restrict__ window, int N,
                             int hop, int pad_mode, int64_t frames, float* __restrict__ out_re, float* __restrict__ out_im) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.y;
   const int nf = N / 2 + 1;
   dft_frames<false>(x + (int64_t)b * x_bs, n, n, window, N, hop, pad_mode ? N / 2 : 0, pad_mode, (int64_t)blockIdx.x * FT, frames,
@@ -61,7 +61,7 @@ __global__ void whisper_logmel_kernel(const float* __restrict__ x, int64_t x_bs,
                                       const float* __restrict__ window, const float* __restrict__ filters, int n_mels,
                                       int64_t frames, float* __restrict__ out, float* __restrict__ gmax) {
   constexpr int N = 400, HOP = 160, NF = 201;
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* pw = sm + 2 * N + FT * N;       // [FT][NF]
   __shared__ float bmax[8];
   const int b = blockIdx.y;
@@ -111,7 +111,7 @@ __global__ void whisper_logmel_finish(float* __restrict__ out, const float* __re
 // inverse rFFT of every frame times the synthesis window -> ws [B, T, N]
 __global__ void irfft_frames_kernel(const float* __restrict__ re, const float* __restrict__ im, int N, int T,
                                     const float* __restrict__ window, float* __restrict__ ws) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* tw_c = sm; float* tw_s = sm + N; float* sr = sm + 2 * N; float* si = sr + (N / 2 + 1);
   const int nf = N / 2 + 1, t = blockIdx.x, b = blockIdx.y;
   for (int i = threadIdx.x; i < N; i += blockDim.x) { float s, c; sincospif(2.f * i / N, &s, &c); tw_c[i] = c; tw_s[i] = s; }

@@ -164,3 +164,150 @@ def kokoro_noise(n_samples, seed=3):
     """Injected randomness for SineGen: rand_ini [1,9] U[0,1), noise [1,n,9] N(0,1)."""
     g = torch.Generator().manual_seed(seed)
     return torch.rand(1, 9, generator=g), torch.randn(1, n_samples, 9, generator=g)
+
+
+# ============================================================================= codecs
+
+def _fan(g, name, *shape, fan_in):
+    return g.normal(name, *shape, std=1.0 / math.sqrt(fan_in))
+
+
+FINAL_GAIN_DIV = 1.0e6     # keeps the pre-tanh signal O(0.5) so the tanh is not saturated in parity tests
+
+
+def snac_weights(cfg, seed=6):
+    """Parameter tree of codec/models/snac/snac.py:SNAC (decode side: quantizer + decoder), random values.
+    weight_v ~ N(0, 1/fan_in), weight_g = ||v|| (so the effective weight is v), Snake alpha ~ U(0.5, 1.5)."""
+    g = _Gen(seed)
+    gen = g.g
+
+    def wn(pre, shape, fan_in, except_dim=0, bias=None):
+        v = _fan(g, pre + ".weight_v", *shape, fan_in=fan_in)
+        axes = tuple(i for i in range(3) if i != except_dim)
+        g.P[pre + ".weight_g"] = _bf16(torch.sqrt((v * v).sum(dim=axes, keepdim=True)))
+        if bias:
+            g.normal(pre + ".bias", bias, std=0.05)
+
+    def alpha(name, c):
+        g.P[name] = _bf16(0.5 + torch.rand(1, c, 1, generator=gen))
+
+    latent = cfg["encoder_dim"] * (2 ** len(cfg["encoder_rates"]))
+    cd = cfg["codebook_dim"]
+    for i, _ in enumerate(cfg["vq_strides"]):
+        q = f"quantizer.quantizers.{i}"
+        g.normal(q + ".codebook.weight", cfg["codebook_size"], cd, std=1.0)
+        wn(q + ".out_proj", (latent, 1, cd), cd, bias=latent)
+    pre = "decoder.model.layers"
+    li = 0
+    wn(f"{pre}.{li}", (latent, 7, 1), 7, bias=latent); li += 1
+    ch = cfg["decoder_dim"]
+    wn(f"{pre}.{li}", (ch, 1, latent), latent, bias=ch); li += 1
+    for i, stride in enumerate(cfg["decoder_rates"]):
+        cin, cout = ch // (2 ** i), ch // (2 ** (i + 1))
+        bp = f"{pre}.{li}.block.layers"; li += 1
+        bi = 0
+        alpha(f"{bp}.{bi}.alpha", cin); bi += 1
+        wn(f"{bp}.{bi}", (cin, 2 * stride, cout), cin * 2, bias=cout); bi += 1          # (in, K, out); ~2 taps hit each output
+        if cfg["noise"]:
+            wn(f"{bp}.{bi}.linear", (cout, 1, cout), cout); bi += 1
+        for _d in (1, 3, 9):
+            rp = f"{bp}.{bi}.block.layers"; bi += 1
+            alpha(rp + ".0.alpha", cout)
+            wn(rp + ".1", (cout, 7, 1) if cfg["depthwise"] else (cout, 7, cout), 7 if cfg["depthwise"] else 7 * cout, bias=cout)
+            alpha(rp + ".2.alpha", cout)
+            wn(rp + ".3", (cout, 1, cout), cout, bias=cout)
+    alpha(f"{pre}.{li}.alpha", cout); li += 1
+    wn(f"{pre}.{li}", (1, 7, cout), 7 * cout * FINAL_GAIN_DIV, bias=1)
+    return g.P
+
+
+def snac_codes(cfg, t_fine, batch=1, seed=6):
+    """cfg5 SNAC inputs: codes[l] int64 [B, t_fine / stride_l] (t_fine must be a multiple of max stride)."""
+    gen = torch.Generator().manual_seed(seed)
+    return [torch.randint(0, cfg["codebook_size"], (batch, t_fine // s), generator=gen) for s in cfg["vq_strides"]]
+
+
+def snac_noises(cfg, batch=1, seed=7):
+    """Injected NoiseBlock draws: one N(0,1) per (batch, channel) per decoder block (snac/layers.py:261-267 quirk)."""
+    gen = torch.Generator().manual_seed(seed)
+    return [torch.randn(batch, 1, cfg["decoder_dim"] // (2 ** (i + 1)), generator=gen) for i in range(len(cfg["decoder_rates"]))]
+
+
+def mimi_weights(cfg, seed=5):
+    """Parameter tree of codec/models/mimi/mimi.py:Mimi (decode side), random values at the mimi_202407 shapes."""
+    g = _Gen(seed)
+    gen = g.g
+    d, nf = cfg["dimension"], cfg["nfilters"]
+    for name, nq in (("rvq_first", 1), ("rvq_rest", cfg["nq"] - 1)):
+        for li in range(nq):
+            cb = f"quantizer.{name}.vq.layers.{li}.codebook"
+            g.normal(cb + ".embedding_sum", cfg["bins"], cfg["qdim"], std=1.0)
+            g.P[cb + ".cluster_usage"] = _bf16(0.5 + 1.5 * torch.rand(cfg["bins"], generator=gen))
+        _fan(g, f"quantizer.{name}.output_proj.weight", d, 1, cfg["qdim"], fan_in=cfg["qdim"] * (1 if nq == 1 else 4))
+    s = cfg["upsample_stride"]
+    _fan(g, "upsample.convtr.convtr.convtr.weight", d, 2 * s, 1, fan_in=2)
+    for li in range(cfg["num_layers"]):
+        L = f"decoder_transformer.transformer.layers.{li}"
+        g.layer_norm(L + ".norm1", d)
+        g.layer_norm(L + ".norm2", d)
+        _fan(g, L + ".self_attn.in_proj.weight", 3 * d, d, fan_in=d)
+        _fan(g, L + ".self_attn.out_proj.weight", d, d, fan_in=d)
+        _fan(g, L + ".gating.linear1.weight", cfg["dim_feedforward"], d, fan_in=d)
+        _fan(g, L + ".gating.linear2.weight", d, cfg["dim_feedforward"], fan_in=cfg["dim_feedforward"])
+        g.P[L + ".layer_scale_1.scale"] = _bf16(torch.full((d,), 0.3) + 0.1 * torch.rand(d, generator=gen))
+        g.P[L + ".layer_scale_2.scale"] = _bf16(torch.full((d,), 0.3) + 0.1 * torch.rand(d, generator=gen))
+    mult = 1 << len(cfg["ratios"])
+    _fan(g, "decoder.init_conv1d.conv.conv.weight", mult * nf, cfg["ksize"], d, fan_in=cfg["ksize"] * d)
+    g.normal("decoder.init_conv1d.conv.conv.bias", mult * nf, std=0.05)
+    for li, r in enumerate(cfg["ratios"]):
+        cin, cout = mult * nf, mult * nf // 2
+        L = f"decoder.layers.{li}"
+        _fan(g, L + ".upsample.convtr.convtr.weight", cout, 2 * r, cin, fan_in=2 * cin)
+        g.normal(L + ".upsample.convtr.convtr.bias", cout, std=0.05)
+        hid = cout // cfg["compress"]
+        _fan(g, L + ".residuals.0.block.0.conv.conv.weight", hid, cfg["residual_ksize"], cout, fan_in=cfg["residual_ksize"] * cout)
+        g.normal(L + ".residuals.0.block.0.conv.conv.bias", hid, std=0.05)
+        _fan(g, L + ".residuals.0.block.1.conv.conv.weight", cout, 1, hid, fan_in=hid)
+        g.normal(L + ".residuals.0.block.1.conv.conv.bias", cout, std=0.05)
+        mult //= 2
+    _fan(g, "decoder.final_conv1d.conv.conv.weight", 1, cfg["last_ksize"], nf, fan_in=cfg["last_ksize"] * nf)
+    g.normal("decoder.final_conv1d.conv.conv.bias", 1, std=0.05)
+    return g.P
+
+
+def mimi_codes(cfg, t, batch=1, seed=5):
+    return torch.randint(0, cfg["bins"], (batch, cfg["nq"], t), generator=torch.Generator().manual_seed(seed))
+
+
+# ============================================================================= Whisper
+
+def _f16(x):
+    return x.to(torch.float16).to(torch.float32)
+
+
+def whisper_encoder_weights(dims, seed=0):
+    """Parameter tree of stt/models/whisper/whisper.py:AudioEncoder (fp16 checkpoint, cfg3): N(0, 0.02), LN gains 1."""
+    g = _Gen(seed)
+    d, nm = dims["n_audio_state"], dims["n_mels"]
+
+    def n(name, *shape):
+        g.P[name] = _f16(torch.randn(*shape, generator=g.g) * 0.02)
+
+    n("encoder.conv1.weight", d, 3, nm); n("encoder.conv1.bias", d)
+    n("encoder.conv2.weight", d, 3, d); n("encoder.conv2.bias", d)
+    for i in range(dims["n_audio_layer"]):
+        L = f"encoder.blocks.{i}"
+        for nm_ in ("query", "value", "out"):
+            n(f"{L}.attn.{nm_}.weight", d, d); n(f"{L}.attn.{nm_}.bias", d)
+        n(f"{L}.attn.key.weight", d, d)
+        g.layer_norm(L + ".attn_ln", d)
+        g.layer_norm(L + ".mlp_ln", d)
+        n(L + ".mlp1.weight", 4 * d, d); n(L + ".mlp1.bias", 4 * d)
+        n(L + ".mlp2.weight", d, 4 * d); n(L + ".mlp2.bias", d)
+    g.layer_norm("encoder.ln_post", d)
+    return g.P
+
+
+def whisper_audio(batch, n_samples=480000, seed=4):
+    """cfg3 input: 0.1 * N(0,1) float32 [B, n]."""
+    return 0.1 * torch.randn(batch, n_samples, generator=torch.Generator().manual_seed(seed))

@@ -1,0 +1,72 @@
+"""Codec decode parity (BASELINE config 5): SNAC-24k and Mimi through the CUDA path vs the float64 oracle.
+Waveform tolerance 1e-3 relative RMS (north_star); output lengths are the reference's own pins
+(codec/tests/test_snac.py:36 -> 120 907, codec/tests/test_mimi.py:18-21 -> 120 960)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from mlx_audio_b200 import synth
+from oracle import codec as OC
+
+
+def rel_rms(a, b):
+    a, b = torch.as_tensor(a).double().cpu().reshape(-1), torch.as_tensor(b).double().cpu().reshape(-1)
+    return float(torch.sqrt(((a - b) ** 2).mean()) / torch.sqrt((b ** 2).mean()))
+
+
+@pytest.fixture(scope="module")
+def snac():
+    from mlx_audio_b200.codec import SNAC
+    P = synth.snac_weights(OC.SNAC_24K)
+    return SNAC.from_config(OC.SNAC_24K, device="cuda:0").load_weights(P), {k: v.double() for k, v in P.items()}
+
+
+@pytest.fixture(scope="module")
+def mimi():
+    from mlx_audio_b200.codec import Mimi, mimi_202407
+    P = synth.mimi_weights(OC.MIMI_202407)
+    return Mimi(mimi_202407(32), device="cuda:0").load_weights(P), {k: v.double() for k, v in P.items()}
+
+
+@pytest.mark.parametrize("t_fine,batch", [(64, 1), (100, 2)])
+def test_snac_decode_parity(snac, t_fine, batch):
+    model, P64 = snac
+    codes = synth.snac_codes(OC.SNAC_24K, t_fine, batch)
+    noises = synth.snac_noises(OC.SNAC_24K, batch)
+    ref = OC.snac_decode(P64, codes, noises=[n.double() for n in noises])
+    y = model.decode(codes, noises=noises)
+    assert y.shape == ref.shape
+    assert rel_rms(y, ref) < 1e-3
+
+
+def test_snac_reference_length_pin_and_bad_codes(snac):
+    model, _ = snac
+    codes = synth.snac_codes(OC.SNAC_24K, 236)
+    assert [c.shape[1] for c in codes] == [59, 118, 236]
+    y = model.decode(codes, noises=synth.snac_noises(OC.SNAC_24K))
+    assert y.shape == (1, 120907, 1) and bool(torch.isfinite(y).all()) and float(y.abs().max()) <= 1.0
+    codes[1][0, 3] = 4096
+    with pytest.raises(ValueError):
+        model.decode(codes, noises=synth.snac_noises(OC.SNAC_24K))
+
+
+@pytest.mark.parametrize("t,batch", [(20, 1), (140, 2)])
+def test_mimi_decode_parity(mimi, t, batch):
+    """T=140 -> 280 transformer positions: exercises the context-250 window."""
+    model, P64 = mimi
+    codes = synth.mimi_codes(OC.MIMI_202407, t, batch)
+    ref = OC.mimi_decode(P64, codes)
+    y = model.decode(codes)
+    assert y.shape == ref.shape == (batch, 1, 1920 * t)
+    assert rel_rms(y, ref) < 1e-3
+
+
+def test_mimi_reference_length_pin_and_prefix_causality(mimi):
+    """63 frames -> 120 960 samples; the stack is causal, so decoding a prefix gives a prefix (size-independent property)."""
+    model, _ = mimi
+    codes = synth.mimi_codes(OC.MIMI_202407, 63)
+    y = model.decode(codes)
+    assert y.shape == (1, 1, 120960)
+    y2 = model.decode(codes[:, :, :40])
+    assert torch.allclose(y2, y[:, :, : 40 * 1920], atol=1e-5, rtol=1e-4)
