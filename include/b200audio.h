@@ -151,6 +151,10 @@ int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, const fl
  * overlap-add, / sum(w^2), trim 10 samples each side (phase in [-1,1] so mlx_unwrap is the identity). */
 int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t T, float* audio, void* stream);
 
+/* out[i] ~ N(0,1), i < n: Philox4x32-10 keyed by `seed`, counter `offset + i/4`, Box-Muller.  The production replacement for
+ * mx.random.normal in SineGen / NoiseBlock (istftnet.py:649, snac/layers.py:263); parity tests inject the noise instead. */
+int32_t b2a_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
 /* ---- codec (RVQ decode) ---------------------------------------------------------------------
  * out[b,t,:] (+)= sum_q codebooks[q][codes[b,q,t]][:]   (mimi/modules/quantization.py:47-49,103-108;
  * speech_tokenizer.py:431-490).  codes int64 [B, nq, T]; codebooks [nq, bins, dim]. Returns B2A_E_INVALID if any code

@@ -344,3 +344,38 @@ extern "C" int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
+
+// ---------------------------------------------------------------- counter-based Gaussian noise (Philox4x32-10 + Box-Muller)
+// Replaces mx.random.normal for the SineGen / NoiseBlock draws (istftnet.py:649, snac/layers.py:263) in production runs.
+namespace {
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0, hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+  uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+  int64_t n4 = (n + 3) / 4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t ctr = offset + (uint64_t)i;
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x2545F491u, c3 = 0x9E3779B9u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) { philox_round(c0, c1, c2, c3, k0, k1); k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    float u0 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f, u1 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+    float u2 = ((float)c2 + 0.5f) * 2.3283064365386963e-10f, u3 = ((float)c3 + 0.5f) * 2.3283064365386963e-10f;
+    float r0 = sqrtf(-2.f * logf(u0)), r1 = sqrtf(-2.f * logf(u2));
+    float s0, cs0, s1, cs1; sincospif(2.f * u1, &s0, &cs0); sincospif(2.f * u3, &s1, &cs1);
+    float v[4] = {r0 * cs0, r0 * s0, r1 * cs1, r1 * s1};
+    for (int j = 0; j < 4; j++) { int64_t o = i * 4 + j; if (o < n) out[o] = v[j]; }
+  }
+}
+}  // namespace
+
+extern "C" int32_t b2a_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
+  B2A_CHECK_ARG(out && n >= 0, "bad pointer/size");
+  if (n == 0) return B2A_OK;
+  randn_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

@@ -21,6 +21,24 @@ ACT = {"none": 0, "lrelu": 1, "snake": 2, "elu": 3, "gelu": 4, "gelu_tanh": 5, "
 LAUNCHES = [0]        # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
+PROFILE = None        # dict kind -> [(start_event, end_event)] when bench.py instruments a pass
+
+
+def _call(kind, fn, n_launches, *args):
+    """Invoke a C-ABI entry point, map its status to an exception, count its kernel launches and (when
+    bench.py asks) bracket it with CUDA events on the launching stream."""
+    if PROFILE is not None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        PROFILE.setdefault(kind, []).append((a, b))
+    else:
+        rc = fn(*args)
+    _lib.check(rc)
+    LAUNCHES[0] += n_launches
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -116,8 +134,7 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     p.res_div = res_div
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     fn = _lib.lib().b2a_convtr1d_cl if transpose else _lib.lib().b2a_conv1d_cl
-    _lib.check(fn(C.byref(p), _stream()))
-    LAUNCHES[0] += 1
+    _call("conv" if cw.groups == 1 and cw.cin * cw.K >= 64 else "other", fn, 1, C.byref(p), _stream())
     return out
 
 
@@ -138,8 +155,7 @@ def copy2d(src: torch.Tensor, dst: torch.Tensor) -> None:
     """dst[r, c] = src[r, c] for 2-D (row-strided) float32 views."""
     rows, cols = src.shape
     assert dst.shape == src.shape and src.stride(1) == 1 and dst.stride(1) == 1
-    _lib.check(_lib.lib().b2a_copy2d(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_copy2d, 1, src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, _stream())
 
 
 def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -148,9 +164,8 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor
     rows, cols = idx.shape[0], src.shape[1]
     if out is None:
         out = torch.empty(rows, cols, device=src.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b2a_gather_rows(src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(), out.stride(0),
-                                          rows, cols, src.shape[0], _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_gather_rows, 1, src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(), out.stride(0),
+                                          rows, cols, src.shape[0], _stream())
     return out
 
 
@@ -163,8 +178,7 @@ def durations_to_index(dur, max_frames: int, speed: float = 1.0):
     idx = torch.zeros(max_frames, device=dur.device, dtype=torch.int64)
     total = torch.zeros(1, device=dur.device, dtype=torch.int64)
     f, i = (dur.data_ptr(), None) if dur.dtype == torch.float32 else (None, dur.data_ptr())
-    _lib.check(_lib.lib().b2a_durations_to_index(f, i, T, speed, pred.data_ptr(), idx.data_ptr(), max_frames, total.data_ptr(), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_durations_to_index, 1, f, i, T, speed, pred.data_ptr(), idx.data_ptr(), max_frames, total.data_ptr(), _stream())
     return pred, idx, total
 
 
@@ -187,9 +201,8 @@ def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5):
     scale = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
     shift = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
     ws = _workspace(_lib.lib().b2a_adain_ws_bytes(B, L, Cc), x.device)
-    _lib.check(_lib.lib().b2a_adain_coeffs(x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
-                                           scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream()))
-    LAUNCHES[0] += 2
+    _call("other", _lib.lib().b2a_adain_coeffs, 2, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
+                                           scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream())
     return scale, shift
 
 
@@ -205,10 +218,9 @@ def layernorm(x: torch.Tensor, w=None, b=None, *, eps=1e-5, res=None, ada=None, 
     if out is None:
         out = torch.empty(x2.shape, device=x.device, dtype=torch.float32)
     o2 = out.reshape(-1, shp[-1]) if out.dim() != 2 else out
-    _lib.check(_lib.lib().b2a_layernorm(x2.data_ptr(), x2.stride(0), _p(r2), 0 if r2 is None else r2.stride(0), o2.data_ptr(),
+    _call("other", _lib.lib().b2a_layernorm, 1, x2.data_ptr(), x2.stride(0), _p(r2), 0 if r2 is None else r2.stride(0), o2.data_ptr(),
                                         o2.stride(0), x2.shape[0], shp[-1], _p(w), _p(b), _p(ada), eps, int(rms), post_act,
-                                        post_p0, _stream()))
-    LAUNCHES[0] += 1
+                                        post_p0, _stream())
     return out.reshape(shp) if out.dim() == 2 and len(shp) != 2 else out
 
 
@@ -229,8 +241,7 @@ def attention(q, k, v, *, n_heads, n_kv_heads=None, scale, causal=False, q_offse
     p.B, p.Tq, p.Tk, p.H, p.Hkv, p.D = B, Tq, k.shape[1], H, Hkv, D
     p.scale, p.causal, p.q_offset, p.window = scale, int(causal), q_offset, window
     p.k_len = _p(k_len)
-    _lib.check(_lib.lib().b2a_attention(C.byref(p), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_attention, 1, C.byref(p), _stream())
     return out
 
 
@@ -238,9 +249,8 @@ def rope_(x: torch.Tensor, n_heads: int, *, offset=0, base=10000.0, traditional=
     """In-place rotary embedding on x [B,T,H*D]."""
     _chk3(x, "rope x")
     B, T, hd = x.shape
-    _lib.check(_lib.lib().b2a_rope(x.data_ptr(), x.stride(0), x.stride(1), B, T, n_heads, hd // n_heads, offset, base,
-                                   int(traditional), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_rope, 1, x.data_ptr(), x.stride(0), x.stride(1), B, T, n_heads, hd // n_heads, offset, base,
+                                   int(traditional), _stream())
     return x
 
 
@@ -252,8 +262,7 @@ def lstm_bidir(xproj: torch.Tensor, wh: torch.Tensor, out: Optional[torch.Tensor
     if out is None:
         out = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
     assert out.stride(2) == 1 and (B == 1 or out.stride(0) == T * out.stride(1))
-    _lib.check(_lib.lib().b2a_lstm_bidir(xproj.data_ptr(), wh.data_ptr(), out.data_ptr(), out.stride(1), B, T, H, _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_lstm_bidir, 1, xproj.data_ptr(), wh.data_ptr(), out.data_ptr(), out.stride(1), B, T, H, _stream())
     return out
 
 
@@ -264,9 +273,8 @@ def stft(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int, pad_mode: 
     nf = n_fft // 2 + 1
     re = torch.empty(B, frames, nf, device=x.device, dtype=torch.float32)
     im = torch.empty(B, frames, nf, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b2a_stft(x.data_ptr(), x.stride(0), B, n, window.data_ptr(), n_fft, hop, pad_mode, frames,
-                                   re.data_ptr(), im.data_ptr(), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_stft, 1, x.data_ptr(), x.stride(0), B, n, window.data_ptr(), n_fft, hop, pad_mode, frames,
+                                   re.data_ptr(), im.data_ptr(), _stream())
     return re, im
 
 
@@ -276,9 +284,8 @@ def whisper_logmel(x: torch.Tensor, padding: int, window: torch.Tensor, filters:
     assert x.stride(1) == 1 and filters.is_contiguous() and filters.shape[1] == 201
     out = torch.empty(B, frames, filters.shape[0], device=x.device, dtype=torch.float32)
     gmax = torch.empty(B, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b2a_whisper_logmel(x.data_ptr(), x.stride(0), B, n, padding, window.data_ptr(), filters.data_ptr(),
-                                             filters.shape[0], frames, out.data_ptr(), gmax.data_ptr(), _stream()))
-    LAUNCHES[0] += 2
+    _call("other", _lib.lib().b2a_whisper_logmel, 2, x.data_ptr(), x.stride(0), B, n, padding, window.data_ptr(), filters.data_ptr(),
+                                             filters.shape[0], frames, out.data_ptr(), gmax.data_ptr(), _stream())
     return out
 
 
@@ -289,9 +296,8 @@ def istft(re: torch.Tensor, im: torch.Tensor, n_fft: int, hop: int, window: torc
     assert re.is_contiguous() and im.is_contiguous() and nf == n_fft // 2 + 1
     out = torch.empty(B, out_len, device=re.device, dtype=torch.float32)
     ws = torch.empty(B, T, n_fft, device=re.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b2a_istft(re.data_ptr(), im.data_ptr(), B, n_fft, T, hop, window.data_ptr(), int(norm_sq), clamp_mode,
-                                    trim, out_len, out.data_ptr(), ws.data_ptr(), _stream()))
-    LAUNCHES[0] += 2
+    _call("other", _lib.lib().b2a_istft, 2, re.data_ptr(), im.data_ptr(), B, n_fft, T, hop, window.data_ptr(), int(norm_sq), clamp_mode,
+                                    trim, out_len, out.data_ptr(), ws.data_ptr(), _stream())
     return out
 
 
@@ -304,9 +310,8 @@ def kokoro_source(f0: torch.Tensor, noise: Optional[torch.Tensor], lin_w: torch.
     ph = torch.empty(B, nF, 9, device=f0.device, dtype=torch.float64)
     if noise is not None:
         assert noise.is_contiguous() and noise.shape == (B, nF * 300, 9)
-    _lib.check(_lib.lib().b2a_kokoro_source(f0.data_ptr(), B, nF, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
-                                            src.data_ptr(), ph.data_ptr(), _stream()))
-    LAUNCHES[0] += 3
+    _call("other", _lib.lib().b2a_kokoro_source, 3, f0.data_ptr(), B, nF, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
+                                            src.data_ptr(), ph.data_ptr(), _stream())
     return har
 
 
@@ -315,9 +320,15 @@ def kokoro_istft_head(x: torch.Tensor) -> torch.Tensor:
     _chk3(x, "kokoro_istft_head x")
     B, T, _ = x.shape
     audio = torch.empty(B, (T - 1) * 5, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().b2a_kokoro_istft_head(x.data_ptr(), x.stride(0), x.stride(1), B, T, audio.data_ptr(), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_kokoro_istft_head, 1, x.data_ptr(), x.stride(0), x.stride(1), B, T, audio.data_ptr(), _stream())
     return audio
+
+
+def randn_(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
+    """Fill a contiguous float32 tensor with N(0,1) draws from our Philox kernel."""
+    assert out.is_contiguous() and out.dtype == torch.float32
+    _call("other", _lib.lib().b2a_randn, 1, out.data_ptr(), out.numel(), seed, offset, _stream())
+    return out
 
 
 def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch.Tensor] = None, check=True) -> torch.Tensor:
@@ -328,9 +339,8 @@ def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch
     if out is None:
         out = torch.empty(B, T, dim, device=codes.device, dtype=torch.float32)
     err = torch.zeros(1, device=codes.device, dtype=torch.int32)
-    _lib.check(_lib.lib().b2a_rvq_decode(codes.data_ptr(), codes.stride(0), codes.stride(1), B, nq, T, codebooks.data_ptr(), bins,
-                                         dim, out.data_ptr(), out.stride(1), err.data_ptr(), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_rvq_decode, 1, codes.data_ptr(), codes.stride(0), codes.stride(1), B, nq, T, codebooks.data_ptr(), bins,
+                                         dim, out.data_ptr(), out.stride(1), err.data_ptr(), _stream())
     if check and int(err.item()) != 0:
         raise ValueError(f"rvq_decode: code index out of range [0, {bins})")
     return out
@@ -347,9 +357,8 @@ def snac_from_codes(codes, strides, embs, ws, biases, dim: int, check=True) -> t
     arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
     for c in codes:
         assert c.dtype == torch.int64 and c.is_contiguous()
-    _lib.check(_lib.lib().b2a_snac_from_codes(arr(codes), (C.c_int32 * n)(*strides), n, arr(embs), arr(ws), arr(biases), B, T, bins,
-                                              cd, dim, out.data_ptr(), err.data_ptr(), _stream()))
-    LAUNCHES[0] += 1
+    _call("other", _lib.lib().b2a_snac_from_codes, 1, arr(codes), (C.c_int32 * n)(*strides), n, arr(embs), arr(ws), arr(biases), B, T, bins,
+                                              cd, dim, out.data_ptr(), err.data_ptr(), _stream())
     if check and int(err.item()) != 0:
         raise ValueError(f"snac_from_codes: code index out of range [0, {bins})")
     return out

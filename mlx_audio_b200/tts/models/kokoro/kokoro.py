@@ -463,3 +463,59 @@ class Model:
                 prompt={"tokens": len(ps), "tokens-per-sec": round(len(ps) / seg_t, 2) if seg_t > 0 else 0},
                 audio_samples={"samples": samples, "samples-per-sec": round(samples / seg_t, 2) if seg_t > 0 else 0},
                 processing_time_seconds=seg_t, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
+
+
+class CapturedUtterance:
+    """One Kokoro utterance shape (T tokens, F frames) captured as a CUDA graph.
+
+    The utterance is ~700 dependent kernel launches on tens of microseconds of work each, so it is
+    launch-bound from Python; replaying a graph removes the host from the loop.  Inputs live in static
+    device buffers (``ids``, ``ref_s``, ``dur``); SineGen noise is drawn inside the graph by our Philox
+    kernel from a device-side counter, so every replay sees fresh noise like the reference's
+    ``mx.random.normal`` (istftnet.py:649)."""
+
+    def __init__(self, model: "Model", T: int, F: int, seed: int = 1234, with_noise: bool = True):
+        dev = model.device
+        self.model, self.T, self.F = model, T, F
+        self.ids = torch.zeros(T, dtype=torch.int64, device=dev)
+        self.ref_s = torch.zeros(1, 256, dtype=torch.float32, device=dev)
+        self.dur = torch.full((T,), max(F // T, 1), dtype=torch.int64, device=dev)
+        self.dur[0] += F - int(self.dur.sum().item())
+        self.noise = torch.zeros(1, F * 600, 9, dtype=torch.float32, device=dev) if with_noise else None
+        self.seed, self.step = seed, 0
+        self.graph = None
+        self.audio = None
+        self.launches = 0
+
+    def _run(self):
+        if self.noise is not None:
+            ops.randn_(self.noise, self.seed, 0)
+        audio, _ = self.model.forward_ids(self.ids, self.ref_s, noise=self.noise, pred_dur=self.dur, n_frames=self.F)
+        return audio
+
+    def capture(self, warmup: int = 2):
+        s = torch.cuda.Stream(device=self.model.device)
+        s.wait_stream(torch.cuda.current_stream(self.model.device))
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._run()
+        torch.cuda.current_stream(self.model.device).wait_stream(s)
+        torch.cuda.synchronize(self.model.device)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(self.graph):
+            self.audio = self._run()
+        self.launches = ops.LAUNCHES[0] - n0
+        return self
+
+    def set_inputs(self, ids: torch.Tensor, ref_s: torch.Tensor, dur: Optional[torch.Tensor] = None):
+        """Async copies (host pinned or device) into the static buffers; sum(dur) must equal F."""
+        self.ids.copy_(ids.reshape(-1), non_blocking=True)
+        self.ref_s.copy_(ref_s.reshape(1, -1), non_blocking=True)
+        if dur is not None:
+            self.dur.copy_(dur.reshape(-1), non_blocking=True)
+
+    def replay(self) -> torch.Tensor:
+        self.graph.replay()
+        ops.LAUNCHES[0] += self.launches
+        return self.audio

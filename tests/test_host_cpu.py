@@ -1,0 +1,152 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/b200audio.h declares, host
+logic (weight packing, sanitize, synthetic checkpoints, sharding) and a world_size-2 gloo run of the
+multi-GPU plumbing.  No compute calls: there is no GPU here and no CPU fallback by design."""
+import os
+import re
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mlx_audio_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "b200audio.h")).read()
+    declared = set(re.findall(r"\b(b2a_\w+)\s*\(", header))
+    declared -= {"b2a_conv1d_t", "b2a_attn_t"}
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.PROTOTYPES), f"header vs ctypes prototypes differ: {declared ^ set(_lib.PROTOTYPES)}"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.b2a_version() == 100
+
+
+def test_ctypes_struct_matches_c_layout(tmp_path):
+    """sizeof/offsetof of the parameter structs as the C compiler sees them == the ctypes mirrors."""
+    from mlx_audio_b200 import _lib
+    src = tmp_path / "sz.c"
+    src.write_text(textwrap.dedent('''
+        #include <stdio.h>
+        #include <stddef.h>
+        #include "b200audio.h"
+        int main(void) {
+          printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2a_conv1d_t), offsetof(b2a_conv1d_t, pre_scale), offsetof(b2a_conv1d_t, res),
+                 offsetof(b2a_conv1d_t, accumulate), sizeof(b2a_attn_t), offsetof(b2a_attn_t, k_len));
+          return 0; }'''))
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    C, A = _lib.Conv1dParams, _lib.AttnParams
+    import ctypes
+    assert got == [ctypes.sizeof(C), C.pre_scale.offset, C.res.offset, C.accumulate.offset, ctypes.sizeof(A), A.k_len.offset]
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from mlx_audio_b200 import _lib
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libb200audio.so")
+    with pytest.raises(ImportError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_pack_conv_layouts():
+    from mlx_audio_b200 import ops
+    w = torch.arange(2 * 3 * 4, dtype=torch.float32).reshape(2, 3, 4)          # [Cout, K, Cin]
+    cw = ops.pack_conv(w, torch.zeros(2), 1, "cpu")
+    assert cw.w.shape == (3, 4, 2) and cw.K == 3 and cw.cin == 4 and cw.cout == 2
+    assert float(cw.w[1, 2, 1]) == float(w[1, 1, 2])
+    dw = ops.pack_conv(torch.arange(15.0).reshape(5, 3, 1), None, 5, "cpu")
+    assert dw.w.shape == (3, 5) and float(dw.w[2, 4]) == 14.0
+    with pytest.raises(NotImplementedError):
+        ops.pack_conv(torch.zeros(4, 3, 2), None, 2, "cpu")
+    lin = ops.pack_linear(torch.zeros(7, 5), None, "cpu")
+    assert lin.K == 1 and lin.cin == 5 and lin.cout == 7
+
+
+def test_kokoro_synthetic_checkpoint_and_sanitize():
+    from mlx_audio_b200 import synth
+    from mlx_audio_b200.tts.models.kokoro import Model, ModelConfig
+    from oracle.kokoro import KOKORO_CONFIG
+    P = synth.kokoro_weights(KOKORO_CONFIG)
+    n = sum(v.numel() for v in P.values())
+    assert 81.0e6 < n < 82.5e6                                                    # Kokoro-82M
+    assert all(torch.equal(v, v.to(torch.bfloat16).float()) for v in P.values())  # a bf16 checkpoint
+    cfg = ModelConfig.from_dict({**KOKORO_CONFIG, "unknown_key": 1})              # from_dict filters unknown keys (base.py:10-18)
+    m = Model(cfg, device="cpu")
+    # torch-layout checkpoint keys -> reference tree (kokoro.py:179-276)
+    torch_ckpt = {"predictor.lstm.weight_ih_l0_reverse": torch.zeros(1024, 640), "text_encoder.cnn.0.1.gamma": torch.ones(512),
+                  "decoder.generator.noise_convs.0.weight": torch.zeros(256, 22, 12), "bert.embeddings.position_ids": torch.zeros(1, 512),
+                  "decoder.encode.conv1.weight_v": torch.zeros(1024, 514, 3), "predictor.F0_proj.weight": torch.zeros(1, 256, 1)}
+    s = m.sanitize(torch_ckpt)
+    assert "predictor.lstm.Wx_backward" in s and "text_encoder.cnn.0.1.weight" in s and "bert.embeddings.position_ids" not in s
+    assert s["decoder.generator.noise_convs.0.weight"].shape == (256, 12, 22)
+    assert s["decoder.encode.conv1.weight_v"].shape == (1024, 3, 514) and s["predictor.F0_proj.weight"].shape == (1, 1, 256)
+
+
+def test_fold_weight_norm_matches_oracle_rule():
+    from mlx_audio_b200.tts.models.kokoro.kokoro import fold_weight_norm
+    from oracle.kokoro import weight_norm
+    g = torch.Generator().manual_seed(0)
+    v = (torch.randn(8, 3, 5, generator=g) * 0.02).to(torch.bfloat16).float()
+    gg = torch.rand(8, 1, 1, generator=g).to(torch.bfloat16).float()
+    assert torch.equal(fold_weight_norm(v, gg), weight_norm(v, gg))
+
+
+def test_codec_oracle_reference_length_pins():
+    """codec/tests/test_snac.py:30-36 (59/118/236 codes -> 120 907 samples) and test_mimi.py:18-21 (63 -> 120 960)."""
+    from mlx_audio_b200 import synth
+    from oracle import codec as OC
+    P = synth.snac_weights(OC.SNAC_24K)
+    y = OC.snac_decode(P, synth.snac_codes(OC.SNAC_24K, 236), noises=synth.snac_noises(OC.SNAC_24K))
+    assert y.shape == (1, 120907, 1)
+    y = OC.mimi_decode(synth.mimi_weights(OC.MIMI_202407), synth.mimi_codes(OC.MIMI_202407, 63))
+    assert y.shape == (1, 1, 120960)
+
+
+def test_shard_units_and_spans():
+    from mlx_audio_b200.parallel import shard_span, shard_units
+    lengths = [5, 50, 7, 30, 30, 1, 9, 12]
+    parts = [shard_units(lengths, r, 3) for r in range(3)]
+    assert sorted(sum(parts, [])) == list(range(8))
+    loads = [sum(lengths[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= max(lengths)
+    spans = [shard_span(10000, r, 8, halo_left=25) for r in range(8)]
+    assert spans[0][:2] == (0, 1250) and spans[3] == (3750 - 25, 5000, 3750, 5000)
+    assert [s[2] for s in spans] == [i * 1250 for i in range(8)] and spans[-1][3] == 10000
+    s = shard_span(10000, 1, 3, halo_left=10, halo_right=10, multiple=4)
+    assert s[2] % 4 == 0 and s[0] % 4 == 0 and s[0] <= s[2] - 10
+
+
+GLOO_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from mlx_audio_b200.parallel import gather_waveforms, shard_units, world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, ws = world()
+lengths = [300, 100, 250, 50, 120]
+mine = shard_units(lengths, rank, ws)
+waves = [torch.full((lengths[i],), float(i)) for i in mine]          # stand-in for per-utterance synthesis
+out = gather_waveforms(waves, mine, len(lengths), dst=0)
+if rank == 0:
+    assert [int(o.numel()) for o in out] == lengths and all(float(o[0]) == i for i, o in enumerate(out))
+    print("GATHER_OK", mine)
+else:
+    assert out is None
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_gloo_world2_sharding_and_trailing_gather(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]
