@@ -21,10 +21,11 @@ def _bf16(x):
 
 
 def _fold_wn(v, g, except_dim=0):
-    """snac/layers.py:9-14,57: g * v / ||v||; evaluated once in fp32 and rounded to the bf16 grid."""
-    v, g = v.float(), g.float()
+    """snac/layers.py:9-14,57: g * v / ||v||, folded once at load in the checkpoint's dtype (SNAC checkpoints are
+    float32 and the reference does not cast them, snac.py:184-199), so no rounding is applied."""
+    v, g = v.double(), g.double()
     axes = tuple(i for i in range(v.dim()) if i != except_dim)
-    return _bf16(g * v / torch.sqrt((v * v).sum(dim=axes, keepdim=True)))
+    return (g * v / torch.sqrt((v * v).sum(dim=axes, keepdim=True))).float()
 
 
 class SNAC:

@@ -14,10 +14,10 @@ __global__ void adain_partial_kernel(const float* __restrict__ x, int64_t x_bs, 
   __shared__ double s1[8][33], s2[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x, chunk = blockIdx.y, b = blockIdx.z;
   const int r0 = chunk * ROWS_PER_CHUNK, r1 = min(L, r0 + ROWS_PER_CHUNK);
-  float a1 = 0.f, a2 = 0.f;                       // <= 32 rows per thread: fp32 partials are safe
+  double a1 = 0.0, a2 = 0.0;                      // float64 partials: exact var = E[x^2]-mean^2 even when |mean| >> std
   if (c < C) {
     const float* xp = x + (int64_t)b * x_bs + c;
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) { float v = __ldg(xp + (int64_t)r * x_ld); a1 += v; a2 = fmaf(v, v, a2); }
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) { double v = (double)__ldg(xp + (int64_t)r * x_ld); a1 += v; a2 = fma(v, v, a2); }
   }
   s1[threadIdx.y][threadIdx.x] = a1; s2[threadIdx.y][threadIdx.x] = a2;
   __syncthreads();

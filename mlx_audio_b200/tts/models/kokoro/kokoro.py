@@ -290,12 +290,15 @@ class Model:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward_ids(self, input_ids, ref_s, speed: float = 1.0, *, noise=None, pred_dur=None, n_frames: Optional[int] = None):
+    def forward_ids(self, input_ids, ref_s, speed: float = 1.0, *, noise=None, pred_dur=None, n_frames: Optional[int] = None,
+                    f0n_override=None):
         """Token ids (BOS/EOS 0 included) + style [1,256] -> (audio [samples], pred_dur int64 [T]).
 
         ``noise`` [1, 600F, 9] injects the SineGen Gaussian (istftnet.py:649); None -> noiseless source
         (production draws Philox noise with torch).  ``pred_dur`` overrides the duration head.
         ``n_frames``: the caller already knows sum(pred_dur) (CUDA-graph capture) -> no host sync.
+        ``f0n_override`` = (F0 [2F], N [2F]) replaces the predicted curves (parity tests: the hn-NSF phase integrates F0
+        over the whole utterance x300, so decoder parity is checked on identical curves).
         """
         W, cfg, dev = self._w, self.config, self.device
         if W is None:
@@ -356,6 +359,9 @@ class Model:
             for blk in W[name]:
                 hcur = self._adain_resblk1d(hcur, blk)
             ops.conv1d(hcur, W[name + "_proj"], out=F0N[n_i:n_i + 1])
+        if f0n_override is not None:
+            F0N[0, :, 0].copy_(torch.as_tensor(f0n_override[0]).to(device=dev, dtype=torch.float32).reshape(-1))
+            F0N[1, :, 0].copy_(torch.as_tensor(f0n_override[1]).to(device=dev, dtype=torch.float32).reshape(-1))
         f0_curve, n_curve = F0N[0:1], F0N[1:2]                         # [1,2F,1]
         self._tap("en", en)
         self._tap("F0", f0_curve)

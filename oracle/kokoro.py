@@ -369,7 +369,7 @@ def round_half_even(x: torch.Tensor) -> torch.Tensor:
 
 
 def forward(P, input_ids, ref_s, cfg=KOKORO_CONFIG, speed=1.0, rand_ini=None, noise=None,
-            pred_dur_override=None, return_intermediates=False):
+            pred_dur_override=None, return_intermediates=False, f0n_override=None):
     """kokoro.py:111-177 from token ids (``[0, *ids, 0]`` already applied by the caller).
 
     input_ids: LongTensor [1,T]; ref_s [1,256].  Returns (audio [samples], pred_dur [T]).
@@ -395,8 +395,15 @@ def forward(P, input_ids, ref_s, cfg=KOKORO_CONFIG, speed=1.0, rand_ini=None, no
     aln[idx, torch.arange(idx.shape[0])] = 1
     en = d.transpose(1, 2) @ aln[None]
     f0_pred, n_pred = f0n_train(P, en, s)
+    _tap("F0", f0_pred)
+    _tap("N", n_pred)
+    _tap("en", en.transpose(1, 2))
+    if f0n_override is not None:
+        f0_pred, n_pred = (torch.as_tensor(v).to(dt).reshape(1, -1) for v in f0n_override)
     t_en = text_encoder(P, input_ids, cfg)
     asr = t_en @ aln[None]
+    _tap("asr", asr.transpose(1, 2))
+    _tap("d", d)
     n_samples = idx.shape[0] * 600
     nz = noise(n_samples) if callable(noise) else noise
     audio = decoder(P, asr, f0_pred, n_pred, ref_s[:, :128], cfg, rand_ini, nz)[0, 0]
