@@ -1,0 +1,319 @@
+// Tensor-core path for the genuinely dense layers (include/b200audio.h: b2a_prep_bf16, b2a_conv1d_tc).
+//
+// A stride-1 1-D convolution over channels-last activations is a sum of row-shifted GEMMs:
+//     Y[l, n] = sum_tap sum_ci  A[l + shift_tap, ci] * W[tap][n][ci]
+// so one tcgen05 kernel serves every dense conv (and every Linear: one tap, shift 0).  TMA fetches the
+// shifted A tile for each tap straight from the activation matrix -- rows outside [0, L) are zero-filled by
+// the TMA unit, which IS the convolution's zero padding -- and the weight tile, both into 128B-swizzled
+// shared memory that tcgen05.mma consumes through shared-memory descriptors; the fp32 accumulator lives in
+// TMEM and is drained by four epilogue warps (tcgen05.ld) that fuse bias / activation / LayerScale /
+// residual / scale / accumulate.
+//
+// Precision: activations are stored as TWO bf16 planes (hi = bf16(a), lo = bf16(a - hi)) written by the
+// prologue kernel together with the AdaIN/Snake/LeakyReLU input transform; weights are bf16-exact
+// (bf16 checkpoint), so  (hi + lo) * w  reproduces the fp32 product to ~2^-17 while running on the bf16
+// tensor pipe (2 MMAs per tile instead of 1).  `planes = 1` drops the lo plane (pure bf16 activations).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane),
+// warps 2..5 = epilogue (warp_id % 4 selects the TMEM lane quarter).  One 128 x BN output tile per CTA.
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int TM = 128;            // rows (positions) per CTA tile == UMMA_M
+constexpr int TK = 64;             // bf16 elements per 128-byte swizzle row == K extent of one stage
+constexpr int UMMA_K = 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major, 128B-swizzled operand tile whose rows are 128 bytes: 8-row groups 1024 B apart (SBO), descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);              // start address
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+  int B, L, Lout, Cout, cin_pad, taps, planes, BN, stages;
+  int shift[32];
+  const float* bias; int post_act; float post_p0;
+  const float* cscale; int64_t cscale_bs;
+  const float* res; int64_t res_bs, res_ld; int res_div;
+  float out_scale; int accumulate;
+  float* y; int64_t y_bs, y_ld;
+};
+
+// smem: [stages] x { A_hi 16 KB | A_lo 16 KB (planes==2) | W BN*128 B }, then barriers
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_bytes = TM * 128, w_bytes = p.BN * 128;
+  const int stage_bytes = a_bytes * p.planes + w_bytes;
+  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int l0 = blockIdx.x * TM, n0 = blockIdx.y * p.BN, b = blockIdx.z;
+  const int kchunks = p.cin_pad / TK;
+  const int iters = p.taps * kchunks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < p.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {                                    // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int it = 0; it < iters; it++) {
+        const int s = it % p.stages, ph = (it / p.stages) & 1;
+        mbar_wait(empty + s, ph ^ 1);
+        const int tap = it / kchunks, kc = it % kchunks;
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+        tma_load_3d(st, &map_hi, full + s, kc * TK, l0 + p.shift[tap], b);
+        if (p.planes == 2) tma_load_3d(st + a_bytes, &map_lo, full + s, kc * TK, l0 + p.shift[tap], b);
+        tma_load_2d(st + (size_t)a_bytes * p.planes, &map_w, full + s, kc * TK, tap * p.Cout + n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    for (int it = 0; it < iters; it++) {
+      const int s = it % p.stages, ph = (it / p.stages) & 1;
+      mbar_wait(full + s, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes);
+        for (int pl = 0; pl < p.planes; pl++) {
+          const uint64_t adesc = umma_desc_sw128(st + pl * a_bytes);
+#pragma unroll
+          for (int k = 0; k < TK / UMMA_K; k++)        // advance 32 B (16 bf16) inside the 128 B swizzle row
+            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (it | pl | k) != 0);
+        }
+        umma_commit(empty + s);                        // frees the stage when these MMAs retire
+        if (it == iters - 1) umma_commit(tmem_full);   // accumulator complete
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int l = l0 + quarter * 32 + lane;
+    const bool row_ok = l < p.Lout;
+    float* yrow = p.y + (int64_t)b * p.y_bs + (int64_t)l * p.y_ld;
+    const float* rrow = p.res ? p.res + (int64_t)b * p.res_bs + (int64_t)(l / p.res_div) * p.res_ld : nullptr;
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int n = n0 + c0 + j;
+        if (n >= p.Cout) break;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          float t = __uint_as_float(r[j + q]);
+          if (p.bias) t += __ldg(p.bias + n + q);
+          if (p.post_act) t = b2a_act(t, p.post_act, p.post_p0, 1.f, 1.f);
+          if (p.cscale) t *= __ldg(p.cscale + (int64_t)b * p.cscale_bs + n + q);
+          v[q] = t;
+        }
+        if (rrow) { float4 rr = *reinterpret_cast<const float4*>(rrow + n); v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) v[q] *= p.out_scale;
+        float4* yp = reinterpret_cast<float4*>(yrow + n);
+        if (p.accumulate) { float4 o = *yp; v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
+        *yp = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.BN) : "memory");
+  }
+}
+
+// ---- prologue: fp32 activations -> (hi, lo) bf16 planes with the fused input transform; pad channels are zeroed
+__global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int B, int L, int C, int cpad,
+                                 const float* __restrict__ scale, const float* __restrict__ shift, int act, float p0,
+                                 const float* __restrict__ a, const float* __restrict__ bb, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo) {
+  const int cp2 = cpad / 2;
+  const int64_t total = (int64_t)B * L * cp2;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(idx % cp2) * 2;
+    int64_t r = idx / cp2;
+    int l = (int)(r % L), b = (int)(r / L);
+    float v[2] = {0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      int cc = c + q;
+      if (cc < C) {
+        float t = __ldg(x + (int64_t)b * x_bs + (int64_t)l * x_ld + cc);
+        if (scale) t = fmaf(t, __ldg(scale + (int64_t)b * C + cc), __ldg(shift + (int64_t)b * C + cc));
+        if (act) t = b2a_act(t, act, p0, a ? __ldg(a + cc) : 1.f, bb ? __ldg(bb + cc) : 1.f);
+        v[q] = t;
+      }
+    }
+    __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+    __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
+    *reinterpret_cast<__nv_bfloat162*>(hi + r * cpad + c) = hv;
+    if (lo) {
+      __nv_bfloat162 lv;
+      lv.x = __float2bfloat16_rn(v[0] - __bfloat162float(h0));
+      lv.y = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
+      *reinterpret_cast<__nv_bfloat162*>(lo + r * cpad + c) = lv;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+  g_encode = (EncodeTiledFn)fn;
+  return 0;
+}
+
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  cuuint64_t gd[3]; cuuint64_t gs[2]; cuuint32_t bx[3]; cuuint32_t es[3] = {1, 1, 1};
+  for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank - 1; i++) gs[i] = strides_bytes[i];
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace
+
+extern "C" int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int32_t cpad,
+                                 const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
+                                 void* hi, void* lo, void* stream) {
+  B2A_CHECK_ARG(x && hi && B > 0 && L > 0 && C > 0 && cpad >= C && cpad % 64 == 0, "bad pointers/shape (cpad must be a multiple of 64)");
+  B2A_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift come together");
+  int64_t total = (int64_t)B * L * (cpad / 2);
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  prep_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
+                                                             (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
+                                 int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
+                                 int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
+                                 int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
+                                 int64_t y_bs, int64_t y_ld, void* stream) {
+  B2A_CHECK_ARG(a_hi && w_bf16 && y && shifts_host, "null pointer");
+  B2A_CHECK_ARG(B > 0 && L > 0 && Lout > 0 && taps > 0 && taps <= 32 && cin_pad % 64 == 0 && res_div > 0, "bad shape");
+  B2A_CHECK_ARG(Cout % 32 == 0 && y_ld % 4 == 0 && (res == nullptr || res_ld % 4 == 0), "Cout must be a multiple of 32; row strides multiples of 4");
+  if (get_encode() != 0) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled entry point not found"); return B2A_E_CUDA; }
+  TcParams p;
+  p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
+  p.BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32));
+  for (int i = 0; i < taps; i++) p.shift[i] = shifts_host[i];
+  p.bias = bias; p.post_act = post_act; p.post_p0 = post_p0; p.cscale = cscale; p.cscale_bs = cscale_bs;
+  p.res = res; p.res_bs = res_bs; p.res_ld = res_ld; p.res_div = res_div; p.out_scale = out_scale; p.accumulate = accumulate;
+  p.y = y; p.y_bs = y_bs; p.y_ld = y_ld;
+  const int stage_bytes = TM * 128 * p.planes + p.BN * 128;
+  p.stages = (200 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 16;
+
+  CUtensorMap mh, ml, mw;
+  uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
+  uint64_t astr[2] = {(uint64_t)cin_pad * 2, (uint64_t)cin_pad * 2 * (uint64_t)L};
+  uint32_t abox[3] = {TK, TM, 1};
+  int e = make_map(&mh, a_hi, 3, adims, astr, abox);
+  if (!e) e = make_map(&ml, a_lo ? a_lo : a_hi, 3, adims, astr, abox);
+  uint64_t wdims[2] = {(uint64_t)cin_pad, (uint64_t)taps * Cout};
+  uint64_t wstr[1] = {(uint64_t)cin_pad * 2};
+  uint32_t wbox[2] = {TK, (uint32_t)p.BN};
+  if (!e) e = make_map(&mw, w_bf16, 2, wdims, wstr, wbox);
+  if (e) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled failed (%d)", e); return B2A_E_CUDA; }
+
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  dim3 grid(cdiv(Lout, TM), Cout / p.BN, B);
+  conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mh, ml, mw, p);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

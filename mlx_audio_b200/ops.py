@@ -7,6 +7,7 @@ views of wider buffers (row stride = ``stride(1)``), which is how concatenations
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -66,13 +67,27 @@ class Pre:
 
 @dataclass
 class ConvW:
-    """Packed conv weights: ``w`` float32 [K, Cin/groups, Cout] (depthwise: [K, C]), optional bias [Cout]."""
+    """Packed conv weights: ``w`` float32 [K, Cin/groups, Cout] (depthwise: [K, C]), optional bias [Cout];
+    ``w_tc`` bf16 [K, Cout, cin_pad] for the tcgen05 path (dense layers only)."""
     w: torch.Tensor
     bias: Optional[torch.Tensor]
     K: int
     cin: int
     cout: int
     groups: int = 1
+    w_tc: Optional[torch.Tensor] = None
+    cin_pad: int = 0
+
+
+# Tensor-core dispatch policy: "off" = CUDA-core fp32 everywhere; "x2" = tcgen05 with (hi, lo) bf16 activation planes
+# (fp32-grade products); "x1" = tcgen05 with a single bf16 plane.
+TC_MODE = [os.environ.get("B2A_TC", "off")]
+TC_MIN_MACS_PER_ROW = 64 * 96          # below this the layer is launch/HBM-bound and stays on the CUDA-core kernel
+
+
+def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int) -> bool:
+    return (TC_MODE[0] != "off" and cw.w_tc is not None and stride == 1 and not transpose and pad_mode == 0
+            and cw.cout % 32 == 0 and cw.cin * cw.K * cw.cout >= TC_MIN_MACS_PER_ROW * 32 and L >= 32)
 
 
 def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
@@ -86,8 +101,16 @@ def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
             raise NotImplementedError("only dense or depthwise convolutions are on the hot path")
         w = w_mlx[:, :, 0].t().contiguous()              # [K, C]
         cin = cout
-    return ConvW(w.to(device=device, dtype=torch.float32), None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous(),
-                 k, cin, cout, groups)
+    cwo = ConvW(w.to(device=device, dtype=torch.float32), None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous(),
+                k, cin, cout, groups)
+    if groups == 1 and cout % 32 == 0 and torch.device(device).type == "cuda":
+        wb = w_mlx.float().to(torch.bfloat16)
+        if torch.equal(wb.float(), w_mlx.float()):                     # bf16-exact weights only (bf16 checkpoints; fp16/fp32 ones stay fp32)
+            cpad = -(-cin // 64) * 64
+            wt = torch.zeros(k, cout, cpad, dtype=torch.bfloat16)
+            wt[:, :, :cin] = wb.permute(1, 0, 2)
+            cwo.w_tc, cwo.cin_pad = wt.to(device).contiguous(), cpad
+    return cwo
 
 
 def pack_linear(w: torch.Tensor, bias=None, device="cuda") -> ConvW:
@@ -108,6 +131,8 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L - 1) * stride + cw.K - 2 * pad_left
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
+    if _tc_eligible(cw, L, stride, transpose, pad_mode):
+        return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate)
     if out is None:
         out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
     else:
@@ -135,6 +160,39 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     fn = _lib.lib().b2a_convtr1d_cl if transpose else _lib.lib().b2a_conv1d_cl
     _call("conv" if cw.groups == 1 and cw.cin * cw.K >= 64 else "other", fn, 1, C.byref(p), _stream())
+    return out
+
+
+def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2):
+    """Conv prologue -> (hi, lo) bf16 planes [B, L, cpad] (lo None when planes == 1)."""
+    _chk3(x, "prep_bf16 x")
+    B, L, Cc = x.shape
+    hi = torch.empty(B, L, cpad, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(B, L, cpad, device=x.device, dtype=torch.bfloat16) if planes == 2 else None
+    pre = pre or Pre()
+    _call("prep", _lib.lib().b2a_prep_bf16, 1, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, cpad, _p(pre.scale), _p(pre.shift),
+          pre.act, pre.p0, _p(pre.a), _p(pre.b), hi.data_ptr(), _p(lo), _stream())
+    return hi, lo
+
+
+def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate):
+    B, L, _ = x.shape
+    hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1)
+    if out is None:
+        out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
+    else:
+        _chk3(out, "conv1d out")
+        if out.shape != (B, lout, cw.cout):
+            raise ValueError(f"conv1d: out has shape {tuple(out.shape)}, expected {(B, lout, cw.cout)}")
+    shifts = (C.c_int32 * cw.K)(*[k * dilation - pad_left for k in range(cw.K)])
+    cs, cs_bs = (None, 0) if cscale is None else (cscale.data_ptr(), cscale.stride(0) if cscale.dim() == 2 else 0)
+    r, r_bs, r_ld = (None, 0, 0)
+    if res is not None:
+        _chk3(res, "conv1d res")
+        r, r_bs, r_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
+    _call("conv", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), B, L, cw.cin_pad, cw.w_tc.data_ptr(), cw.K, shifts, cw.cout, lout,
+          _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
+          out.stride(1), _stream())
     return out
 
 
