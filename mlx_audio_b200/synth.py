@@ -311,3 +311,21 @@ def whisper_encoder_weights(dims, seed=0):
 def whisper_audio(batch, n_samples=480000, seed=4):
     """cfg3 input: 0.1 * N(0,1) float32 [B, n]."""
     return 0.1 * torch.randn(batch, n_samples, generator=torch.Generator().manual_seed(seed))
+
+
+def kokoro_to_torch_checkpoint(P):
+    """Reference-tree (MLX layout) Kokoro weights -> the PyTorch-layout checkpoint the hub ships, i.e. the input that
+    ``Model.sanitize`` (kokoro.py:179-276) converts: conv weights (out, in, K), LSTM ``weight_ih_l0[_reverse]`` names."""
+    inv = {"Wx_forward": "weight_ih_l0", "Wh_forward": "weight_hh_l0", "bias_ih_forward": "bias_ih_l0", "bias_hh_forward": "bias_hh_l0",
+           "Wx_backward": "weight_ih_l0_reverse", "Wh_backward": "weight_hh_l0_reverse", "bias_ih_backward": "bias_ih_l0_reverse",
+           "bias_hh_backward": "bias_hh_l0_reverse"}
+    out = {}
+    for k, v in P.items():
+        base, _, leaf = k.rpartition(".")
+        if leaf in inv:
+            out[f"{base}.{inv[leaf]}"] = v
+        elif "weight_v" in k or ("noise_convs" in k and leaf == "weight") or "F0_proj.weight" in k or "N_proj.weight" in k:
+            out[k] = v.transpose(1, 2).contiguous()
+        else:
+            out[k] = v
+    return out

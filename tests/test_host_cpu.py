@@ -150,3 +150,30 @@ def test_gloo_world2_sharding_and_trailing_gather(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_drop_in_import_surface_and_loader(tmp_path):
+    """The reference's import paths resolve and load_model follows utils.py:321-416 on a local dir."""
+    import json
+    from safetensors.torch import save_file
+    import mlx_audio.dsp as d
+    from mlx_audio.codec import SNAC, Mimi  # noqa: F401
+    from mlx_audio.stt.models.whisper.audio import N_FRAMES, log_mel_spectrogram  # noqa: F401
+    from mlx_audio.tts.utils import load_model
+    from mlx_audio.utils import hanning, mel_filters, stft  # noqa: F401  (utils.py:31-40 re-exports)
+    from mlx_audio_b200 import synth
+    from oracle.kokoro import KOKORO_CONFIG
+    assert N_FRAMES == 3000 and d.hanning(400).shape == (400,)
+    with pytest.raises(FileNotFoundError):
+        load_model(tmp_path / "missing")
+    (tmp_path / "m").mkdir()
+    with pytest.raises(FileNotFoundError, match="Config not found"):
+        load_model(tmp_path / "m")
+    json.dump({**KOKORO_CONFIG, "model_type": "kokoro", "vocab": {"a": 1}}, open(tmp_path / "m" / "config.json", "w"))
+    P = synth.kokoro_weights(KOKORO_CONFIG)
+    save_file({k: v.to(torch.bfloat16).contiguous() for k, v in synth.kokoro_to_torch_checkpoint(P).items()},
+              str(tmp_path / "m" / "model.safetensors"))
+    model = load_model(tmp_path / "m", device="cpu")
+    assert model.sample_rate == 24000 and model._w is not None and model.vocab == {"a": 1}
+    assert model._w["ups"][0].w.shape == (20, 512, 256)                    # ConvTranspose 512->256 k20 packed [K, Cin, Cout]
+    assert all(torch.equal(model.parameters()[k].float(), P[k]) for k in P)  # sanitize inverted the torch layout exactly
