@@ -83,6 +83,7 @@ def cpu_port_run(n_utts: int, threads: int):
     from mlx_audio_b200 import synth
     from oracle import kokoro as OK
     torch.set_num_threads(threads)
+    print(f"[bench] cpu port: {n_utts} utterance(s) on {threads} threads", file=sys.stderr, flush=True)
     P = synth.kokoro_weights(OK.KOKORO_CONFIG)
     ids, ref = synth.kokoro_inputs(N_PHONEMES)
     T = ids.shape[1]
@@ -96,12 +97,29 @@ def cpu_port_run(n_utts: int, threads: int):
     return times
 
 
+def host_threads() -> int:
+    """Threads the CPU arm may use: the cores this process is actually allowed to run on (cgroup / affinity aware), capped
+    at 32 -- the restatement's small ops stop scaling long before that."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+            if q != "max":
+                n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU implementation of the path, here its restatement (MLX cannot be installed)."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    cpu_port_run(max(args.warmup, 1) if args.warmup < 2 else 1, cores)           # warm-up (bounded: one utterance)
+    cores = host_threads()
+    cpu_port_run(1, cores)           # warm-up (bounded: one utterance)
     times = cpu_port_run(args.steps, cores)
     total = sum(times)
     v = AUDIO_S_PER_UTT * len(times) / total
@@ -147,6 +165,8 @@ def main():
 
     W = max(args.warmup, 3)
     K = args.steps
+    log = lambda m: print(f"[bench r{rank} {time.strftime('%H:%M:%S')}] {m}", file=sys.stderr, flush=True)
+    log("building synthetic checkpoint")
     P = synth.kokoro_weights(KOKORO_CONFIG, seed=0)
     model = Model(ModelConfig.from_dict(KOKORO_CONFIG), device=dev).load_weights(list(P.items()))
     ids, ref_s = synth.kokoro_inputs(N_PHONEMES, seed=1 + rank)
@@ -157,6 +177,7 @@ def main():
     dur_d = torch.full((T,), DUR, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
 
+    log("model ready; capturing")
     cap = CapturedUtterance(model, T, F, seed=1234 + rank)
     cap.set_inputs(ids_d, ref_d, dur_d)
     noise_buf = torch.empty(1, n_samples, 9, device=dev)
@@ -178,6 +199,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    log("timing device-resident steps")
     # ---------------- device-resident timing
     for _ in range(W):
         step()
@@ -212,6 +234,7 @@ def main():
     ms_max = float(t.item())
     value = world * K * AUDIO_S_PER_UTT / (ms_max / 1e3)
 
+    log(f"value done: {ms_max / K:.3f} ms/step; timing e2e")
     # ---------------- end-to-end through the public call with host buffers
     ids_h = ids[0].clone().pin_memory()
     ref_h = ref_s.clone().pin_memory()
@@ -242,6 +265,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * K * AUDIO_S_PER_UTT / float(t.item())
 
+    log("e2e done; instrumented pass")
     # ---------------- roofline of the dominant kernel family (instrumented eager pass, CUDA events per launch)
     prof = {"conv": [], "other": []}
     ops.PROFILE = prof
@@ -261,8 +285,9 @@ def main():
                 "launches_per_utterance": n_conv, "kernel_ms_per_utterance": conv_ms, "other_kernels_ms_per_utterance": other_ms,
                 "algorithmic_bytes_per_utterance": alg_bytes}
 
+    log("instrumented pass done")
     if rank == 0:
-        cores = os.cpu_count() or 1
+        cores = host_threads()
         cpu = None
         if world == 1 and args.cpu_utts > 0:
             times = cpu_port_run(args.cpu_utts, cores)

@@ -160,8 +160,10 @@ int32_t b2a_istft(const float* re, const float* im, int32_t B, int32_t n_fft, in
 /* ---- Kokoro hn-NSF source + iSTFT head (istftnet.py:548-709, 453-545, 826-835) ------------
  * f0 [B, n_frames] (the F0 curve, one value per 300 samples); noise [B, n_frames*300, 9] injected N(0,1) (or NULL);
  * lin_w [9], lin_b [1] = m_source.l_linear.  har [B, n_frames*60+1, 22] = (|STFT| , angle) of the tanh-merged source,
- * n_fft 20 hop 5 periodic Hann, reflect-centred.  src_ws: float [B, n_frames*300]; ph_ws: double [B, n_frames, 9]. */
-int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, const float* noise, const float* lin_w,
+ * n_fft 20 hop 5 periodic Hann, reflect-centred.  n_down = ceil(float(300*n_frames) * float(1/300)) is the length of the
+ * reference's down-sampled phase track (interpolate.py:43-50; n_frames or n_frames+1 by floating-point rounding -- a parity
+ * quirk the host evaluates exactly as the reference does).  src_ws: float [B, n_frames*300]; ph_ws: double [B, n_down, 9]. */
+int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, int32_t n_down, const float* noise, const float* lin_w,
                           const float* lin_b, float* har, float* src_ws, double* ph_ws, void* stream);
 /* x [B, T, 22] = conv_post output -> audio [B, (T-1)*5] : exp / sin heads, cos/sin, 20-point inverse rFFT, periodic Hann,
  * overlap-add, / sum(w^2), trim 10 samples each side (phase in [-1,1] so mlx_unwrap is the identity). */

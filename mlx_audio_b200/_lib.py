@@ -63,7 +63,7 @@ PROTOTYPES = {
     "b2a_stft": (i32, [c_f, i64, i32, i64, c_f, i32, i32, i32, i64, c_f, c_f, C.c_void_p]),
     "b2a_whisper_logmel": (i32, [c_f, i64, i32, i64, i64, c_f, c_f, i32, i64, c_f, c_f, C.c_void_p]),
     "b2a_istft": (i32, [c_f, c_f, i32, i32, i32, i32, c_f, i32, i32, i64, i64, c_f, c_f, C.c_void_p]),
-    "b2a_kokoro_source": (i32, [c_f, i32, i32, c_f, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
+    "b2a_kokoro_source": (i32, [c_f, i32, i32, i32, c_f, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
     "b2a_kokoro_istft_head": (i32, [c_f, i64, i64, i32, i32, c_f, C.c_void_p]),
     "b2a_randn": (i32, [c_f, i64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b2a_rvq_decode": (i32, [c_f, i64, i64, i32, i32, i64, c_f, i32, i32, c_f, i64, c_f, C.c_void_p]),

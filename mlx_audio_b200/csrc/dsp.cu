@@ -158,42 +158,59 @@ constexpr int KH = 9;              // harmonics (fundamental + 8)
 constexpr int KUP = 300;           // samples per F0 frame
 constexpr double KSR = 24000.0;
 
-// cumulative phase (in cycles) per frame and harmonic: C[b,i,h] = sum_{j<=i} frac(f0[j]*(h+1)/sr)
-__global__ void ksrc_phase_kernel(const float* __restrict__ f0, int nF, double* __restrict__ ph) {
+// Frame-rate phase of the reference (istftnet.py:585-591): the sample-rate rad values (piecewise constant per F0 frame) are
+// linearly DOWN-sampled to n_down points (interpolate1d, align_corners False), then cumulatively summed.  n_down =
+// ceil(float(L) * float(1/300)) is computed by the host exactly as the reference does and is nF or nF+1 depending on
+// floating-point rounding, so the positions are NOT frame-aligned in general.
+__device__ __forceinline__ double ksrc_rad(const float* __restrict__ f0b, int64_t n, int h) {
+  double r = (double)f0b[n / KUP] * (h + 1) / KSR;
+  return r - floor(r);
+}
+__device__ __forceinline__ double ksrc_rad_down(const float* __restrict__ f0b, int64_t L, int n_down, int i, int h) {
+  const double sc = (double)L / (double)n_down;
+  double x = (double)i * sc + 0.5 * sc - 0.5; if (x < 0) x = 0;
+  int64_t lo = (int64_t)floor(x); int64_t hi = lo + 1 < L ? lo + 1 : L - 1; double fr = x - (double)lo;
+  return ksrc_rad(f0b, lo, h) * (1.0 - fr) + ksrc_rad(f0b, hi, h) * fr;
+}
+// C[b,i,h] = sum_{j<=i} rad_down[j,h]  (phase in cycles)
+__global__ void ksrc_phase_kernel(const float* __restrict__ f0, int nF, int n_down, double* __restrict__ ph) {
   const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
   __shared__ double part[256];
-  const int per = (nF + nt - 1) / nt, beg = tid * per, end = min(nF, beg + per);
+  const float* f0b = f0 + (int64_t)b * nF;
+  const int64_t L = (int64_t)nF * KUP;
+  const int per = (n_down + nt - 1) / nt, beg = tid * per, end = min(n_down, beg + per);
   double s = 0;
-  for (int i = beg; i < end; i++) { double r = (double)f0[(int64_t)b * nF + i] * (h + 1) / KSR; s += r - floor(r); }
+  for (int i = beg; i < end; i++) s += ksrc_rad_down(f0b, L, n_down, i, h);
   part[tid] = s;
   __syncthreads();
   if (tid == 0) { double run = 0; for (int i = 0; i < nt; i++) { double v = part[i]; part[i] = run; run += v; } }
   __syncthreads();
   double run = part[tid];
   for (int i = beg; i < end; i++) {
-    double r = (double)f0[(int64_t)b * nF + i] * (h + 1) / KSR; run += r - floor(r);
-    ph[((int64_t)b * nF + i) * KH + h] = run;
+    run += ksrc_rad_down(f0b, L, n_down, i, h);
+    ph[((int64_t)b * n_down + i) * KH + h] = run;
   }
 }
 
-__global__ void ksrc_sample_kernel(const float* __restrict__ f0, int nF, const double* __restrict__ ph,
+__global__ void ksrc_sample_kernel(const float* __restrict__ f0, int nF, int n_down, const double* __restrict__ ph,
                                    const float* __restrict__ noise, const float* __restrict__ lin_w,
                                    const float* __restrict__ lin_b, float* __restrict__ src, int B) {
   const int64_t n_s = (int64_t)nF * KUP, total = n_s * B;
+  const double s2 = (double)n_down / (double)((int64_t)n_down * KUP);     // in_width / size of the x300 up-sampling
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int b = (int)(idx / n_s); int64_t n = idx % n_s;
     int fi = (int)(n / KUP);
     float f0v = f0[(int64_t)b * nF + fi];
     float uv = f0v > 10.f ? 1.f : 0.f;
-    // linear x300 upsample of the frame-rate phase (interpolate.py:94-115, align_corners False, coords clamped at 0)
-    double pos = ((double)n + 0.5) / KUP - 0.5; if (pos < 0) pos = 0;
-    int lo = (int)floor(pos); int hi = min(lo + 1, nF - 1); double fr = pos - lo;
-    const double* p_lo = ph + ((int64_t)b * nF + lo) * KH; const double* p_hi = ph + ((int64_t)b * nF + hi) * KH;
+    // linear x300 up-sampling of the frame-rate phase (interpolate.py:94-115, align_corners False, coords clamped at 0)
+    double pos = (double)n * s2 + 0.5 * s2 - 0.5; if (pos < 0) pos = 0;
+    int lo = (int)floor(pos); int hi = min(lo + 1, n_down - 1); double fr = pos - lo;
+    const double* p_lo = ph + ((int64_t)b * n_down + lo) * KH; const double* p_hi = ph + ((int64_t)b * n_down + hi) * KH;
     float namp = uv * 0.003f + (1.f - uv) * (0.1f / 3.f);
     float accv = lin_b[0];
 #pragma unroll
     for (int h = 0; h < KH; h++) {
-      double cyc = ((1.0 - fr) * p_lo[h] + fr * p_hi[h]) * KUP;     // phase / 2pi
+      double cyc = (p_lo[h] * (1.0 - fr) + p_hi[h] * fr) * KUP;       // phase / 2pi
       cyc -= floor(cyc);
       float sv = (float)sinpi(2.0 * cyc) * 0.1f;
       float nz = noise ? noise[idx * KH + h] : 0.f;
@@ -324,14 +341,15 @@ extern "C" int32_t b2a_istft(const float* re, const float* im, int32_t B, int32_
   return B2A_OK;
 }
 
-extern "C" int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, const float* noise, const float* lin_w,
+extern "C" int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, int32_t n_down, const float* noise, const float* lin_w,
                                      const float* lin_b, float* har, float* src_ws, double* ph_ws, void* stream) {
   B2A_CHECK_ARG(f0 && lin_w && lin_b && har && src_ws && ph_ws && B > 0 && n_frames > 0, "bad pointers/shape");
+  B2A_CHECK_ARG(n_down >= n_frames && n_down <= n_frames + 1, "n_down must be ceil(float(300*n_frames) * float(1/300))");
   cudaStream_t st = (cudaStream_t)stream;
   init_tw20();
-  ksrc_phase_kernel<<<dim3(KH, B), 256, 0, st>>>(f0, n_frames, ph_ws);
+  ksrc_phase_kernel<<<dim3(KH, B), 256, 0, st>>>(f0, n_frames, n_down, ph_ws);
   int64_t n_s = (int64_t)n_frames * KUP;
-  ksrc_sample_kernel<<<grid_for(n_s * B, 256), 256, 0, st>>>(f0, n_frames, ph_ws, noise, lin_w, lin_b, src_ws, B);
+  ksrc_sample_kernel<<<grid_for(n_s * B, 256), 256, 0, st>>>(f0, n_frames, n_down, ph_ws, noise, lin_w, lin_b, src_ws, B);
   ksrc_stft_kernel<<<grid_for((n_s / 5 + 1) * B, 128), 128, 0, st>>>(src_ws, n_s, har, B);
   B2A_CHECK_LAUNCH();
   return B2A_OK;

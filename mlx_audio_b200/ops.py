@@ -7,6 +7,7 @@ views of wider buffers (row stride = ``stride(1)``), which is how concatenations
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -365,10 +366,13 @@ def kokoro_source(f0: torch.Tensor, noise: Optional[torch.Tensor], lin_w: torch.
     assert f0.is_contiguous()
     har = torch.empty(B, nF * 60 + 1, 22, device=f0.device, dtype=torch.float32)
     src = torch.empty(B, nF * 300, device=f0.device, dtype=torch.float32)
-    ph = torch.empty(B, nF, 9, device=f0.device, dtype=torch.float64)
+    # length of the reference's down-sampled phase track: size = ceil(float(W) * float(scale)) with scale = 1/300
+    # (tts/models/interpolate.py:43-50) -- nF or nF + 1 depending on floating-point rounding; evaluated the same way here.
+    n_down = max(1, int(math.ceil(float(nF * 300) * float(1 / 300))))
+    ph = torch.empty(B, n_down, 9, device=f0.device, dtype=torch.float64)
     if noise is not None:
         assert noise.is_contiguous() and noise.shape == (B, nF * 300, 9)
-    _call("other", _lib.lib().b2a_kokoro_source, 3, f0.data_ptr(), B, nF, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
+    _call("other", _lib.lib().b2a_kokoro_source, 3, f0.data_ptr(), B, nF, n_down, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
                                             src.data_ptr(), ph.data_ptr(), _stream())
     return har
 

@@ -297,12 +297,14 @@ def test_istft_generic_matches_both_reference_variants():
     assert float(np.abs(y.cpu().numpy() - ref)[:, : -n_fft].max()) / np.abs(ref[:, :-n_fft]).max() < 1e-5
 
 
-def test_kokoro_source_and_istft_head():
+@pytest.mark.parametrize("nF", [46, 14, 30, 124])
+def test_kokoro_source_and_istft_head(nF):
+    """nF = 14, 30, 124: the reference's ceil(float(L) * float(1/300)) down-sample length is nF + 1 there (parity quirk)."""
     from mlx_audio_b200 import ops
     from oracle import kokoro as OK
     dev = _dev()
-    nF = 46
-    f0 = torch.cat([torch.zeros(6), 80 + 300 * torch.rand(30, generator=torch.Generator().manual_seed(1)), torch.zeros(10)])[None]
+    nv = nF - nF // 3
+    f0 = torch.cat([torch.zeros(nF // 6), 80 + 300 * torch.rand(nv, generator=torch.Generator().manual_seed(1)), torch.zeros(nF - nv - nF // 6)])[None]
     f0 = torch.cat([f0, f0.flip(1) * 0.5], 0)                                                # B=2, voiced + unvoiced spans
     noise = _rand(2, nF * 300, 9, seed=2)
     lw, lb = _rand(1, 9, seed=3, scale=0.3), _rand(1, seed=4, scale=0.1)
