@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--cpu-utts", type=int, default=4, help="utterances in the cpu_baseline sample")
+    ap.add_argument("--ncu", action="store_true", help="profiling aid: 2 eager warm-up steps, then ONE eager step between "
+                    "cudaProfilerStart/Stop (run under `ncu --profile-from-start off`); prints no bench line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,6 +188,15 @@ def main():
         ops.randn_(noise_buf, 1234 + rank, 0)
         return model.forward_ids(ids_d, ref_d, noise=noise_buf, pred_dur=dur_d, n_frames=F)[0]
 
+    if args.ncu:
+        for _ in range(2):
+            step_eager()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step_eager()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
     if args.no_graph:
         step = step_eager
         launches_per_step = None

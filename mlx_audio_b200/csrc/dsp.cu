@@ -241,6 +241,7 @@ __global__ void ksrc_stft_kernel(const float* __restrict__ src, int64_t n_s, flo
       double re = 0, im = 0;
 #pragma unroll
       for (int i = 0; i < 20; i++) { int p = (k * i) % 20; re += xw[i] * c_tw20_c[p]; im -= xw[i] * c_tw20_s[p]; }
+      if (k == 0 || k == 10) im = 0.0;        // DC / Nyquist of a real signal are exactly real: angle is 0 or +pi (np.fft.rfft convention)
       hp[k] = (float)sqrt(re * re + im * im);
       hp[11 + k] = (float)atan2(im, re);
     }

@@ -83,12 +83,12 @@ class ConvW:
 # Tensor-core dispatch policy: "off" = CUDA-core fp32 everywhere; "x2" = tcgen05 with (hi, lo) bf16 activation planes
 # (fp32-grade products); "x1" = tcgen05 with a single bf16 plane.
 TC_MODE = [os.environ.get("B2A_TC", "off")]
-TC_MIN_MACS_PER_ROW = 64 * 96          # below this the layer is launch/HBM-bound and stays on the CUDA-core kernel
+TC_MIN_K = 128                         # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
 
 
 def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int) -> bool:
     return (TC_MODE[0] != "off" and cw.w_tc is not None and stride == 1 and not transpose and pad_mode == 0
-            and cw.cout % 32 == 0 and cw.cin * cw.K * cw.cout >= TC_MIN_MACS_PER_ROW * 32 and L >= 32)
+            and cw.cout % 32 == 0 and cw.cin * cw.K >= TC_MIN_K and L >= 32)
 
 
 def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
