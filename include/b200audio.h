@@ -82,11 +82,12 @@ int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream);
  * lo == NULL stores hi only.
  * b2a_conv1d_tc: Y[b,l,n] = epilogue( sum_tap sum_ci (hi+lo)[b, l + shifts[tap], ci] * W[tap][n][ci] ), rows outside
  * [0,L) read as zero (TMA out-of-bounds fill == the conv's zero padding).  W is bf16 [taps][Cout][cin_pad]; Cout % 32 == 0.
- * tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by TMA; epilogue fields as in b2a_conv1d_t. */
+ * tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by TMA; epilogue fields as in b2a_conv1d_t.
+ * f16 != 0: planes and weights are IEEE fp16 instead of bf16 (fp16 checkpoints such as Whisper's: weights stay exact). */
 int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int32_t cpad,
                       const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
-                      void* hi, void* lo, void* stream);
-int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
+                      void* hi, void* lo, int32_t f16, void* stream);
+int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
                       int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                       int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                       int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,

@@ -241,7 +241,10 @@ __global__ void ksrc_stft_kernel(const float* __restrict__ src, int64_t n_s, flo
       double re = 0, im = 0;
 #pragma unroll
       for (int i = 0; i < 20; i++) { int p = (k * i) % 20; re += xw[i] * c_tw20_c[p]; im -= xw[i] * c_tw20_s[p]; }
-      if (k == 0 || k == 10) im = 0.0;        // DC / Nyquist of a real signal are exactly real: angle is 0 or +pi (np.fft.rfft convention)
+      // Exactly-real bins (DC, Nyquist, and every bin of the reflect-symmetric frame 0) have an imaginary part that is pure
+      // rounding noise; its sign would pick +pi or -pi at random (in the reference's FFT too).  Canonical choice on both
+      // sides of the parity test: treat |im| <= 1e-12 |re| as +0, i.e. angle 0 or +pi.
+      if (fabs(im) <= 1e-12 * fabs(re)) im = 0.0;
       hp[k] = (float)sqrt(re * re + im * im);
       hp[11 + k] = (float)atan2(im, re);
     }

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -81,7 +82,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 }
 
 struct TcParams {
-  int B, L, Lout, Cout, cin_pad, taps, planes, BN, stages;
+  int B, L, Lout, Cout, cin_pad, taps, planes, BN, stages, f16;
   int shift[32];
   const float* bias; int post_act; float post_p0;
   const float* cscale; int64_t cscale_bs;
@@ -143,7 +144,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer =====
     // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t fmt = p.f16 ? 0u : 1u;                 // F16F32Format: 0 = f16, 1 = bf16
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     for (int it = 0; it < iters; it++) {
       const int s = it % p.stages, ph = (it / p.stages) & 1;
       mbar_wait(full + s, ph);
@@ -206,10 +208,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 }
 
 // ---- prologue: fp32 activations -> (hi, lo) bf16 planes with the fused input transform; pad channels are zeroed
+template <typename T> __device__ __forceinline__ T to16(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half to16<__half>(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float from16(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float from16(__half v) { return __half2float(v); }
+
+template <typename T16>
 __global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int B, int L, int C, int cpad,
                                  const float* __restrict__ scale, const float* __restrict__ shift, int act, float p0,
-                                 const float* __restrict__ a, const float* __restrict__ bb, __nv_bfloat16* __restrict__ hi,
-                                 __nv_bfloat16* __restrict__ lo) {
+                                 const float* __restrict__ a, const float* __restrict__ bb, T16* __restrict__ hi,
+                                 T16* __restrict__ lo) {
   const int cp2 = cpad / 2;
   const int64_t total = (int64_t)B * L * cp2;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -227,14 +236,12 @@ __global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int6
         v[q] = t;
       }
     }
-    __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-    __nv_bfloat162 hv; hv.x = h0; hv.y = h1;
-    *reinterpret_cast<__nv_bfloat162*>(hi + r * cpad + c) = hv;
+    T16 h0 = to16<T16>(v[0]), h1 = to16<T16>(v[1]);
+    T16 hv[2] = {h0, h1};
+    *reinterpret_cast<uint32_t*>(hi + r * cpad + c) = *reinterpret_cast<uint32_t*>(hv);
     if (lo) {
-      __nv_bfloat162 lv;
-      lv.x = __float2bfloat16_rn(v[0] - __bfloat162float(h0));
-      lv.y = __float2bfloat16_rn(v[1] - __bfloat162float(h1));
-      *reinterpret_cast<__nv_bfloat162*>(lo + r * cpad + c) = lv;
+      T16 lv[2] = {to16<T16>(v[0] - from16(h0)), to16<T16>(v[1] - from16(h1))};
+      *reinterpret_cast<uint32_t*>(lo + r * cpad + c) = *reinterpret_cast<uint32_t*>(lv);
     }
   }
 }
@@ -253,11 +260,11 @@ int get_encode() {
   return 0;
 }
 
-int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int f16) {
   cuuint64_t gd[3]; cuuint64_t gs[2]; cuuint32_t bx[3]; cuuint32_t es[3] = {1, 1, 1};
   for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i < rank - 1; i++) gs[i] = strides_bytes[i];
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = g_encode(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
@@ -267,18 +274,20 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
 
 extern "C" int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int32_t cpad,
                                  const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
-                                 void* hi, void* lo, void* stream) {
+                                 void* hi, void* lo, int32_t f16, void* stream) {
   B2A_CHECK_ARG(x && hi && B > 0 && L > 0 && C > 0 && cpad >= C && cpad % 64 == 0, "bad pointers/shape (cpad must be a multiple of 64)");
   B2A_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift come together");
   int64_t total = (int64_t)B * L * (cpad / 2);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  prep_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
-                                                             (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+  if (f16) prep_bf16_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
+                                                                              (__half*)hi, (__half*)lo);
+  else prep_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
+                                                                                 (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
 
-extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
+extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
                                  int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                                  int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                                  int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
@@ -288,6 +297,7 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t B, 
   B2A_CHECK_ARG(Cout % 32 == 0 && y_ld % 4 == 0 && (res == nullptr || res_ld % 4 == 0), "Cout must be a multiple of 32; row strides multiples of 4");
   if (get_encode() != 0) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled entry point not found"); return B2A_E_CUDA; }
   TcParams p;
+  p.f16 = f16 ? 1 : 0;
   p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
   p.BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32));
   for (int i = 0; i < taps; i++) p.shift[i] = shifts_host[i];
@@ -302,12 +312,12 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t B, 
   uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
   uint64_t astr[2] = {(uint64_t)cin_pad * 2, (uint64_t)cin_pad * 2 * (uint64_t)L};
   uint32_t abox[3] = {TK, TM, 1};
-  int e = make_map(&mh, a_hi, 3, adims, astr, abox);
-  if (!e) e = make_map(&ml, a_lo ? a_lo : a_hi, 3, adims, astr, abox);
+  int e = make_map(&mh, a_hi, 3, adims, astr, abox, p.f16);
+  if (!e) e = make_map(&ml, a_lo ? a_lo : a_hi, 3, adims, astr, abox, p.f16);
   uint64_t wdims[2] = {(uint64_t)cin_pad, (uint64_t)taps * Cout};
   uint64_t wstr[1] = {(uint64_t)cin_pad * 2};
   uint32_t wbox[2] = {TK, (uint32_t)p.BN};
-  if (!e) e = make_map(&mw, w_bf16, 2, wdims, wstr, wbox);
+  if (!e) e = make_map(&mw, w_bf16, 2, wdims, wstr, wbox, p.f16);
   if (e) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled failed (%d)", e); return B2A_E_CUDA; }
 
   static bool attr = false;

@@ -41,6 +41,42 @@ def _call(kind, fn, n_launches, *args):
     LAUNCHES[0] += n_launches
 
 
+_SIDE_POOL = {}      # device -> [streams];  _SIDE_BUSY: streams handed out by fork() and not yet joined
+_SIDE_BUSY = set()
+
+
+def fork(device, n: int = 1):
+    """Start ``n`` concurrent branches: returns side streams that wait on the current stream's present point.  Use
+    ``with torch.cuda.stream(s): ...`` for each branch, then ``join(device, streams)``.  Inside a CUDA-graph capture
+    the branches become parallel graph paths.  Tensors that cross branches must be allocated BEFORE the fork (on the
+    joining stream); branch temporaries stay stream-local, and because every fork waits on the forking stream and every
+    join waits on the branches, block reuse by the caching allocator stays ordered."""
+    device = torch.device(device)
+    cur = torch.cuda.current_stream(device)
+    pool = _SIDE_POOL.setdefault(device, [])
+    out = []
+    for s in pool:
+        if len(out) == n:
+            break
+        if s not in _SIDE_BUSY and s != cur:
+            out.append(s)
+    while len(out) < n:
+        s = torch.cuda.Stream(device=device)
+        pool.append(s)
+        out.append(s)
+    for s in out:
+        _SIDE_BUSY.add(s)
+        s.wait_stream(cur)
+    return out
+
+
+def join(device, streams) -> None:
+    cur = torch.cuda.current_stream(torch.device(device))
+    for s in streams:
+        cur.wait_stream(s)
+        _SIDE_BUSY.discard(s)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -78,12 +114,18 @@ class ConvW:
     groups: int = 1
     w_tc: Optional[torch.Tensor] = None
     cin_pad: int = 0
+    f16: bool = False          # w_tc is IEEE fp16 (fp16 checkpoints) instead of bf16
 
 
 # Tensor-core dispatch policy: "off" = CUDA-core fp32 everywhere; "x2" = tcgen05 with (hi, lo) bf16 activation planes
 # (fp32-grade products); "x1" = tcgen05 with a single bf16 plane.
 TC_MODE = [os.environ.get("B2A_TC", "off")]
 TC_MIN_K = 128                         # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
+
+
+def _vec4_ok(t: Optional[torch.Tensor]) -> bool:
+    """The tensor-core epilogue reads/writes rows as float4: 16-byte aligned base and row stride."""
+    return t is None or (t.data_ptr() % 16 == 0 and t.stride(1) % 4 == 0 and (t.shape[0] == 1 or t.stride(0) % 4 == 0))
 
 
 def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int) -> bool:
@@ -105,12 +147,14 @@ def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
     cwo = ConvW(w.to(device=device, dtype=torch.float32), None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous(),
                 k, cin, cout, groups)
     if groups == 1 and cout % 32 == 0 and torch.device(device).type == "cuda":
-        wb = w_mlx.float().to(torch.bfloat16)
-        if torch.equal(wb.float(), w_mlx.float()):                     # bf16-exact weights only (bf16 checkpoints; fp16/fp32 ones stay fp32)
-            cpad = -(-cin // 64) * 64
-            wt = torch.zeros(k, cout, cpad, dtype=torch.bfloat16)
-            wt[:, :, :cin] = wb.permute(1, 0, 2)
-            cwo.w_tc, cwo.cin_pad = wt.to(device).contiguous(), cpad
+        for dt in (torch.bfloat16, torch.float16):                     # 16-bit-exact weights only (bf16 / fp16 checkpoints)
+            wb = w_mlx.float().to(dt)
+            if torch.equal(wb.float(), w_mlx.float()):
+                cpad = -(-cin // 64) * 64
+                wt = torch.zeros(k, cout, cpad, dtype=dt)
+                wt[:, :, :cin] = wb.permute(1, 0, 2)
+                cwo.w_tc, cwo.cin_pad, cwo.f16 = wt.to(device).contiguous(), cpad, dt == torch.float16
+                break
     return cwo
 
 
@@ -132,7 +176,7 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L - 1) * stride + cw.K - 2 * pad_left
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
-    if _tc_eligible(cw, L, stride, transpose, pad_mode):
+    if _tc_eligible(cw, L, stride, transpose, pad_mode) and _vec4_ok(out) and _vec4_ok(res):
         return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate)
     if out is None:
         out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
@@ -164,21 +208,22 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     return out
 
 
-def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2):
-    """Conv prologue -> (hi, lo) bf16 planes [B, L, cpad] (lo None when planes == 1)."""
+def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2, f16: bool = False):
+    """Conv prologue -> (hi, lo) bf16 (or fp16) planes [B, L, cpad] (lo None when planes == 1)."""
     _chk3(x, "prep_bf16 x")
     B, L, Cc = x.shape
-    hi = torch.empty(B, L, cpad, device=x.device, dtype=torch.bfloat16)
-    lo = torch.empty(B, L, cpad, device=x.device, dtype=torch.bfloat16) if planes == 2 else None
+    dt = torch.float16 if f16 else torch.bfloat16
+    hi = torch.empty(B, L, cpad, device=x.device, dtype=dt)
+    lo = torch.empty(B, L, cpad, device=x.device, dtype=dt) if planes == 2 else None
     pre = pre or Pre()
     _call("prep", _lib.lib().b2a_prep_bf16, 1, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, cpad, _p(pre.scale), _p(pre.shift),
-          pre.act, pre.p0, _p(pre.a), _p(pre.b), hi.data_ptr(), _p(lo), _stream())
+          pre.act, pre.p0, _p(pre.a), _p(pre.b), hi.data_ptr(), _p(lo), int(f16), _stream())
     return hi, lo
 
 
 def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate):
     B, L, _ = x.shape
-    hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1)
+    hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1, cw.f16)
     if out is None:
         out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
     else:
@@ -191,7 +236,7 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
     if res is not None:
         _chk3(res, "conv1d res")
         r, r_bs, r_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
-    _call("conv", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), B, L, cw.cin_pad, cw.w_tc.data_ptr(), cw.K, shifts, cw.cout, lout,
+    _call("conv", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, cw.w_tc.data_ptr(), cw.K, shifts, cw.cout, lout,
           _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
           out.stride(1), _stream())
     return out

@@ -93,6 +93,7 @@ class Model:
         self._w = None
         self._pipelines = {}
         self.tap = None            # set to a dict to capture intermediates (parity tests)
+        self.concurrent = True     # independent sub-graphs (text encoder, F0/N heads, source path, resblocks) on parallel streams
 
     # ------------------------------------------------------------------ protocol
     @property
@@ -274,8 +275,9 @@ class Model:
         return ops.conv1d(r, blk["conv2"], pad_left=1, pre=Pre(s2, h2, ACT["lrelu"], 0.2), res=sc,
                           res_div=2 if blk["up"] else 1, out_scale=1.0 / math.sqrt(2.0), out=out)
 
-    def _adain_resblock1(self, x, blk, out=None, out_scale=1.0, accumulate=False):
-        """AdaINResBlock1 (istftnet.py:341-396) on x [1,L,C]."""
+    def _adain_resblock1(self, x, blk, out=None, out_scale=1.0, accumulate=False, defer_last=False):
+        """AdaINResBlock1 (istftnet.py:341-396) on x [1,L,C].  ``defer_last`` returns a closure issuing the final conv
+        (the one that writes / accumulates into ``out``) so parallel branches can serialise only that step."""
         k = blk["k"]
         for j, d in enumerate(blk["dils"]):
             s1, h1 = ops.adain_coeffs(x, self._gb(f"{blk['name']}.adain1.{j}").contiguous())
@@ -284,6 +286,11 @@ class Model:
             s2, h2 = ops.adain_coeffs(xt, self._gb(f"{blk['name']}.adain2.{j}").contiguous())
             a, ia = blk["a2"][j]
             last = j == len(blk["dils"]) - 1
+            if last and defer_last:
+                def final(xt=xt, s2=s2, h2=h2, a=a, ia=ia, x=x, j=j):
+                    return ops.conv1d(xt, blk["c2"][j], pad_left=(k - 1) // 2, pre=Pre(s2, h2, ACT["snake"], 0.0, a, ia), res=x,
+                                      out=out, out_scale=out_scale, accumulate=accumulate)
+                return final
             x = ops.conv1d(xt, blk["c2"][j], pad_left=(k - 1) // 2, pre=Pre(s2, h2, ACT["snake"], 0.0, a, ia), res=x,
                            out=out if last else None, out_scale=out_scale if last else 1.0, accumulate=accumulate and last)
         return x
@@ -312,6 +319,22 @@ class Model:
         self._gb_pred = ops.linear(s_pred, W["ada_all"])              # [1, sum 2C]  (all style projections at once)
         self._gb_dec = ops.linear(s_dec, W["ada_all"])
         hd = cfg.hidden_dim
+        par = self.concurrent
+        # ---- text encoder: independent of the ALBERT / duration chain -> its own branch (parallel graph path)
+        t_en = torch.empty(T, hd, device=dev, dtype=torch.float32)
+
+        def text_branch():
+            te = ops.gather_rows(W["te_emb"], ids)[None]
+            k = cfg.text_encoder_kernel_size
+            for cw, lw, lb in W["te_cnn"]:
+                te = ops.conv1d(te, cw, pad_left=(k - 1) // 2)
+                te = ops.layernorm(te, lw, lb, eps=1e-5, post_act=ACT["lrelu"], post_p0=0.2)
+            self._lstm_run(te[0], W["te_lstm"], out=t_en)
+
+        if par:
+            side_text = ops.fork(dev, 1)
+            with torch.cuda.stream(side_text[0]):
+                text_branch()
         # ---- ALBERT
         e = ops.gather_rows(W["word_emb"], ids)
         e = ops.layernorm(e, *W["emb_ln"], eps=1e-12, res=W["pos_type"][:T])
@@ -354,11 +377,21 @@ class Model:
         en = ops.gather_rows(X, idx)                                   # [F,640]  == d^T @ aln
         xs = self._lstm_run(en, W["shared"])[None]                     # [1,F,512]
         F0N = torch.empty(2, 2 * F, 1, device=dev, dtype=torch.float32)
-        for n_i, name in enumerate(("F0", "N")):
+        def head(n_i, name):
             hcur = xs
             for blk in W[name]:
                 hcur = self._adain_resblk1d(hcur, blk)
             ops.conv1d(hcur, W[name + "_proj"], out=F0N[n_i:n_i + 1])
+
+        if par:
+            side = ops.fork(dev, 1)
+            with torch.cuda.stream(side[0]):
+                head(1, "N")
+            head(0, "F0")
+            ops.join(dev, side)
+        else:
+            head(0, "F0")
+            head(1, "N")
         if f0n_override is not None:
             F0N[0, :, 0].copy_(torch.as_tensor(f0n_override[0]).to(device=dev, dtype=torch.float32).reshape(-1))
             F0N[1, :, 0].copy_(torch.as_tensor(f0n_override[1]).to(device=dev, dtype=torch.float32).reshape(-1))
@@ -366,20 +399,46 @@ class Model:
         self._tap("en", en)
         self._tap("F0", f0_curve)
         self._tap("N", n_curve)
-        # ---- text encoder
-        te = ops.gather_rows(W["te_emb"], ids)[None]
-        k = cfg.text_encoder_kernel_size
-        for cw, lw, lb in W["te_cnn"]:
-            te = ops.conv1d(te, cw, pad_left=(k - 1) // 2)
-            te = ops.layernorm(te, lw, lb, eps=1e-5, post_act=ACT["lrelu"], post_p0=0.2)
-        t_en = self._lstm_run(te[0], W["te_lstm"])                     # [T,512]
+        # ---- text encoder (joined here)
+        if par:
+            ops.join(dev, side_text)
+        else:
+            text_branch()
         self._tap("t_en", t_en)
+        # ---- harmonic-source path (depends on the F0 curve only): source -> STFT -> noise convs -> noise resblocks, run as a
+        #      branch concurrent with the decoder blocks
+        ist = cfg.istftnet
+        rates, ks = ist["upsample_rates"], ist["upsample_kernel_sizes"]
+        nk = len(ist["resblock_kernel_sizes"])
+        n_har = 120 * F + 1
+        xsrcs, Lh = [], n_har
+        for i in range(len(rates)):
+            sf0 = math.prod(rates[i + 1:]) if i + 1 < len(rates) else 1
+            Li = (n_har + 2 * ((sf0 + 1) // 2) - (2 * sf0 - 1) - 1) // sf0 + 1 if sf0 > 1 else n_har
+            xsrcs.append(torch.empty(1, Li, W["noise_convs"][i].cout, device=dev, dtype=torch.float32))
+        del Lh
+
+        def source_branch():
+            har = ops.kokoro_source(f0_curve.reshape(1, 2 * F), noise, *W["src_lin"])      # [1,120F+1,22]
+            self._tap("har", har)
+            for i in range(len(rates)):
+                if i + 1 < len(rates):
+                    sf0 = math.prod(rates[i + 1:])
+                    t = ops.conv1d(har, W["noise_convs"][i], stride=sf0, pad_left=(sf0 + 1) // 2)
+                else:
+                    t = ops.conv1d(har, W["noise_convs"][i])
+                self._adain_resblock1(t, W["noise_res"][i], out=xsrcs[i])
+
+        if par:
+            side_src = ops.fork(dev, 1)
+            with torch.cuda.stream(side_src[0]):
+                source_branch()
         # ---- decoder
-        b514 = torch.empty(1, F, hd + 2, device=dev, dtype=torch.float32)
+        b514 = torch.empty(1, F, hd + 4, device=dev, dtype=torch.float32)[:, :, :hd + 2]     # row stride padded to a multiple of 4 floats
         ops.gather_rows(t_en, idx, out=b514[0, :, :hd])                # asr = t_en @ aln
         ops.conv1d(f0_curve, W["F0_conv"], stride=2, pad_left=1, out=b514[:, :, hd:hd + 1])
         ops.conv1d(n_curve, W["N_conv"], stride=2, pad_left=1, out=b514[:, :, hd + 1:hd + 2])
-        bufs = [torch.empty(1, F, 1024 + 64 + 2, device=dev, dtype=torch.float32) for _ in range(2)]
+        bufs = [torch.empty(1, F, 1024 + 64 + 4, device=dev, dtype=torch.float32)[:, :, :1024 + 64 + 2] for _ in range(2)]
         ops.conv1d(b514[:, :, :hd], W["asr_res"], out=bufs[0][:, :, 1024:1088])
         ops.copy2d(b514[0, :, hd:], bufs[0][0, :, 1088:])
         ops.copy2d(bufs[0][0, :, 1024:], bufs[1][0, :, 1024:])
@@ -394,20 +453,14 @@ class Model:
                 self._adain_resblk1d(bufs[cur], blk, out=bufs[1 - cur][:, :, :1024])
                 cur = 1 - cur
         self._tap("dec_out", x)
+        if par:
+            ops.join(dev, side_src)
+        else:
+            source_branch()
         # ---- generator
-        ist = cfg.istftnet
-        rates, ks = ist["upsample_rates"], ist["upsample_kernel_sizes"]
-        har = ops.kokoro_source(f0_curve.reshape(1, 2 * F), noise, *W["src_lin"])      # [1,120F+1,22]
-        self._tap("har", har)
-        nk = len(ist["resblock_kernel_sizes"])
         for i, (u, kk) in enumerate(zip(rates, ks)):
             last = i == len(rates) - 1
-            if not last:
-                sf0 = math.prod(rates[i + 1:])
-                xsrc = ops.conv1d(har, W["noise_convs"][i], stride=sf0, pad_left=(sf0 + 1) // 2)
-            else:
-                xsrc = ops.conv1d(har, W["noise_convs"][i])
-            xsrc = self._adain_resblock1(xsrc, W["noise_res"][i])
+            xsrc = xsrcs[i]
             L = x.shape[1]
             lout = (L - 1) * u + kk - 2 * ((kk - u) // 2)
             cout = W["ups"][i].cout
@@ -419,8 +472,20 @@ class Model:
             else:
                 y = ops.conv1d(x, W["ups"][i], stride=u, pad_left=(kk - u) // 2, pre=Pre(act=ACT["lrelu"], p0=0.1), transpose=True, res=xsrc)
             acc = torch.empty_like(y)
-            for j in range(nk):
-                self._adain_resblock1(y, W["resblocks"][i * nk + j], out=acc, out_scale=1.0 / nk, accumulate=j > 0)
+            if par:                                                    # the nk resblocks read the same y: parallel branches; only the
+                sides = ops.fork(dev, nk - 1)                          # final accumulate-into-acc convs are serialised after the join
+                finals = [None] * nk
+                for j in range(1, nk):
+                    with torch.cuda.stream(sides[j - 1]):
+                        finals[j] = self._adain_resblock1(y, W["resblocks"][i * nk + j], out=acc, out_scale=1.0 / nk, accumulate=True,
+                                                          defer_last=True)
+                finals[0] = self._adain_resblock1(y, W["resblocks"][i * nk], out=acc, out_scale=1.0 / nk, accumulate=False, defer_last=True)
+                ops.join(dev, sides)
+                for fn in finals:
+                    fn()
+            else:
+                for j in range(nk):
+                    self._adain_resblock1(y, W["resblocks"][i * nk + j], out=acc, out_scale=1.0 / nk, accumulate=j > 0)
             x = acc
             self._tap(f"gen_stage{i}", x)
         xpost = ops.conv1d(x, W["conv_post"], pad_left=3, pre=Pre(act=ACT["lrelu"], p0=0.01))

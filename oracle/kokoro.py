@@ -239,7 +239,11 @@ def mlxstft_transform(x, n_fft, hop, win):
     for row in np.asarray(x, dtype=np.float64):
         sp = D.stft(row, n_fft=n_fft, hop_length=hop, win_length=win, window=w, center=True, pad_mode="reflect").T
         mags.append(np.abs(sp))
-        phs.append(np.arctan2(sp.imag, sp.real))
+        # Exactly-real bins (DC, Nyquist, every bin of the reflect-symmetric first frame): the imaginary part is FFT rounding
+        # noise whose sign would pick +pi or -pi at random -- in MLX's FFT as in NumPy's.  Canonicalised to +0 (angle 0 / +pi)
+        # here and in the CUDA kernel (csrc/dsp.cu:ksrc_stft_kernel); everything else is the plain arctan2 of mlx_angle.
+        im = np.where(np.abs(sp.imag) <= 1e-12 * np.abs(sp.real), 0.0, sp.imag)
+        phs.append(np.arctan2(im, sp.real))
     return np.stack(mags), np.stack(phs)
 
 
