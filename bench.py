@@ -285,15 +285,18 @@ def main():
         step_eager()
     torch.cuda.synchronize(dev)
     ops.PROFILE = None
-    conv_ms = sum(a.elapsed_time(b) for a, b in prof["conv"]) / nprof
-    other_ms = sum(a.elapsed_time(b) for a, b in prof["other"]) / nprof
-    n_conv = len(prof["conv"]) // nprof
+    by_kind = {k: sum(a.elapsed_time(b) for a, b in v) / nprof for k, v in prof.items()}
+    conv_kinds = ("conv", "conv_tc", "prep")                   # the dense conv stack: CUDA-core convs, tcgen05 convs + their bf16 prologue
+    conv_ms = sum(by_kind.get(k, 0.0) for k in conv_kinds)
+    other_ms = sum(v for k, v in by_kind.items() if k not in conv_kinds)
+    n_conv = sum(len(prof.get(k, [])) for k in conv_kinds) // nprof
     peaks, peak_kind = _peaks()
     alg_bytes = CONV_STACK_MB_PER_AUDIO_S * 1e6 * AUDIO_S_PER_UTT                # per utterance, all conv launches
     achieved = alg_bytes / (conv_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": None, "peak_kind": peak_kind, "kernel": "conv1d_dense/convtr1d_dense (decoder+generator conv stack)",
+                "traffic": None, "peak_kind": peak_kind, "kernel": "dense conv stack: conv_tc_kernel (tcgen05) + prep_bf16_kernel, conv1d_dense/convtr1d_dense (CUDA-core)",
                 "launches_per_utterance": n_conv, "kernel_ms_per_utterance": conv_ms, "other_kernels_ms_per_utterance": other_ms,
+                "ms_by_kind": {k: round(v, 3) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
                 "algorithmic_bytes_per_utterance": alg_bytes}
 
     log("instrumented pass done")
@@ -305,12 +308,12 @@ def main():
             cpu = {"value": AUDIO_S_PER_UTT * len(times) / sum(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
                    "sample": f"{len(times)} full cfg2 utterances ({sum(times):.1f} s), torch-CPU fp32 restatement of the reference"}
         line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if ops.TC_MODE[0] == "off" else ("bf16x2" if ops.TC_MODE[0] == "x2" else "bf16"), "data": "synthetic",
                 "config": {"workload": "kokoro-82m cfg2: 128 phonemes (T=130), durations pinned to 3 -> F=390 frames, 234000 samples = 9.75 s per step per GPU",
                            "parallelism": f"utterance-sharded x{world} (no data-path collective)", "l2": "256 MiB flush between timed steps (its cost subtracted)",
                            "launch": "eager" if args.no_graph else "cuda-graph replay", "weights": "synthetic bf16 checkpoint, 81.8 M params",
-                           "activations": "fp32, weights bf16-exact values in fp32 registers"},
+                           "activations": "fp32 in HBM; tensor-core mode " + ops.TC_MODE[0] + " (x2 = hi+lo bf16 planes, fp32-grade products)"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(ids_h.numel() * 8 + ref_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel() * 4)},

@@ -236,7 +236,7 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
     if res is not None:
         _chk3(res, "conv1d res")
         r, r_bs, r_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
-    _call("conv", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, cw.w_tc.data_ptr(), cw.K, shifts, cw.cout, lout,
+    _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, cw.w_tc.data_ptr(), cw.K, shifts, cw.cout, lout,
           _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
           out.stride(1), _stream())
     return out
@@ -305,7 +305,7 @@ def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5):
     scale = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
     shift = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
     ws = _workspace(_lib.lib().b2a_adain_ws_bytes(B, L, Cc), x.device)
-    _call("other", _lib.lib().b2a_adain_coeffs, 2, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
+    _call("adain_stats", _lib.lib().b2a_adain_coeffs, 2, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
                                            scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream())
     return scale, shift
 
@@ -322,7 +322,7 @@ def layernorm(x: torch.Tensor, w=None, b=None, *, eps=1e-5, res=None, ada=None, 
     if out is None:
         out = torch.empty(x2.shape, device=x.device, dtype=torch.float32)
     o2 = out.reshape(-1, shp[-1]) if out.dim() != 2 else out
-    _call("other", _lib.lib().b2a_layernorm, 1, x2.data_ptr(), x2.stride(0), _p(r2), 0 if r2 is None else r2.stride(0), o2.data_ptr(),
+    _call("layernorm", _lib.lib().b2a_layernorm, 1, x2.data_ptr(), x2.stride(0), _p(r2), 0 if r2 is None else r2.stride(0), o2.data_ptr(),
                                         o2.stride(0), x2.shape[0], shp[-1], _p(w), _p(b), _p(ada), eps, int(rms), post_act,
                                         post_p0, _stream())
     return out.reshape(shp) if out.dim() == 2 and len(shp) != 2 else out
@@ -345,7 +345,7 @@ def attention(q, k, v, *, n_heads, n_kv_heads=None, scale, causal=False, q_offse
     p.B, p.Tq, p.Tk, p.H, p.Hkv, p.D = B, Tq, k.shape[1], H, Hkv, D
     p.scale, p.causal, p.q_offset, p.window = scale, int(causal), q_offset, window
     p.k_len = _p(k_len)
-    _call("other", _lib.lib().b2a_attention, 1, C.byref(p), _stream())
+    _call("attention", _lib.lib().b2a_attention, 1, C.byref(p), _stream())
     return out
 
 
@@ -353,7 +353,7 @@ def rope_(x: torch.Tensor, n_heads: int, *, offset=0, base=10000.0, traditional=
     """In-place rotary embedding on x [B,T,H*D]."""
     _chk3(x, "rope x")
     B, T, hd = x.shape
-    _call("other", _lib.lib().b2a_rope, 1, x.data_ptr(), x.stride(0), x.stride(1), B, T, n_heads, hd // n_heads, offset, base,
+    _call("rope", _lib.lib().b2a_rope, 1, x.data_ptr(), x.stride(0), x.stride(1), B, T, n_heads, hd // n_heads, offset, base,
                                    int(traditional), _stream())
     return x
 
@@ -366,7 +366,7 @@ def lstm_bidir(xproj: torch.Tensor, wh: torch.Tensor, out: Optional[torch.Tensor
     if out is None:
         out = torch.empty(B, T, 2 * H, device=xproj.device, dtype=torch.float32)
     assert out.stride(2) == 1 and (B == 1 or out.stride(0) == T * out.stride(1))
-    _call("other", _lib.lib().b2a_lstm_bidir, 1, xproj.data_ptr(), wh.data_ptr(), out.data_ptr(), out.stride(1), B, T, H, _stream())
+    _call("lstm", _lib.lib().b2a_lstm_bidir, 1, xproj.data_ptr(), wh.data_ptr(), out.data_ptr(), out.stride(1), B, T, H, _stream())
     return out
 
 
@@ -388,7 +388,7 @@ def whisper_logmel(x: torch.Tensor, padding: int, window: torch.Tensor, filters:
     assert x.stride(1) == 1 and filters.is_contiguous() and filters.shape[1] == 201
     out = torch.empty(B, frames, filters.shape[0], device=x.device, dtype=torch.float32)
     gmax = torch.empty(B, device=x.device, dtype=torch.float32)
-    _call("other", _lib.lib().b2a_whisper_logmel, 2, x.data_ptr(), x.stride(0), B, n, padding, window.data_ptr(), filters.data_ptr(),
+    _call("logmel", _lib.lib().b2a_whisper_logmel, 2, x.data_ptr(), x.stride(0), B, n, padding, window.data_ptr(), filters.data_ptr(),
                                              filters.shape[0], frames, out.data_ptr(), gmax.data_ptr(), _stream())
     return out
 
@@ -417,7 +417,7 @@ def kokoro_source(f0: torch.Tensor, noise: Optional[torch.Tensor], lin_w: torch.
     ph = torch.empty(B, n_down, 9, device=f0.device, dtype=torch.float64)
     if noise is not None:
         assert noise.is_contiguous() and noise.shape == (B, nF * 300, 9)
-    _call("other", _lib.lib().b2a_kokoro_source, 3, f0.data_ptr(), B, nF, n_down, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
+    _call("source", _lib.lib().b2a_kokoro_source, 3, f0.data_ptr(), B, nF, n_down, _p(noise), lin_w.data_ptr(), lin_b.data_ptr(), har.data_ptr(),
                                             src.data_ptr(), ph.data_ptr(), _stream())
     return har
 
@@ -427,7 +427,7 @@ def kokoro_istft_head(x: torch.Tensor) -> torch.Tensor:
     _chk3(x, "kokoro_istft_head x")
     B, T, _ = x.shape
     audio = torch.empty(B, (T - 1) * 5, device=x.device, dtype=torch.float32)
-    _call("other", _lib.lib().b2a_kokoro_istft_head, 1, x.data_ptr(), x.stride(0), x.stride(1), B, T, audio.data_ptr(), _stream())
+    _call("istft_head", _lib.lib().b2a_kokoro_istft_head, 1, x.data_ptr(), x.stride(0), x.stride(1), B, T, audio.data_ptr(), _stream())
     return audio
 
 
@@ -446,7 +446,7 @@ def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch
     if out is None:
         out = torch.empty(B, T, dim, device=codes.device, dtype=torch.float32)
     err = torch.zeros(1, device=codes.device, dtype=torch.int32)
-    _call("other", _lib.lib().b2a_rvq_decode, 1, codes.data_ptr(), codes.stride(0), codes.stride(1), B, nq, T, codebooks.data_ptr(), bins,
+    _call("rvq", _lib.lib().b2a_rvq_decode, 1, codes.data_ptr(), codes.stride(0), codes.stride(1), B, nq, T, codebooks.data_ptr(), bins,
                                          dim, out.data_ptr(), out.stride(1), err.data_ptr(), _stream())
     if check and int(err.item()) != 0:
         raise ValueError(f"rvq_decode: code index out of range [0, {bins})")
@@ -464,7 +464,7 @@ def snac_from_codes(codes, strides, embs, ws, biases, dim: int, check=True) -> t
     arr = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
     for c in codes:
         assert c.dtype == torch.int64 and c.is_contiguous()
-    _call("other", _lib.lib().b2a_snac_from_codes, 1, arr(codes), (C.c_int32 * n)(*strides), n, arr(embs), arr(ws), arr(biases), B, T, bins,
+    _call("rvq", _lib.lib().b2a_snac_from_codes, 1, arr(codes), (C.c_int32 * n)(*strides), n, arr(embs), arr(ws), arr(biases), B, T, bins,
                                               cd, dim, out.data_ptr(), err.data_ptr(), _stream())
     if check and int(err.item()) != 0:
         raise ValueError(f"snac_from_codes: code index out of range [0, {bins})")
