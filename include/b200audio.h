@@ -83,7 +83,10 @@ int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream);
  * b2a_conv1d_tc: Y[b,l,n] = epilogue( sum_tap sum_ci (hi+lo)[b, l + shifts[tap], ci] * W[tap][n][ci] ), rows outside
  * [0,L) read as zero (TMA out-of-bounds fill == the conv's zero padding).  W is bf16 [taps][Cout][cin_pad]; Cout % 32 == 0.
  * tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), operands staged by TMA; epilogue fields as in b2a_conv1d_t.
- * f16 != 0: planes and weights are IEEE fp16 instead of bf16 (fp16 checkpoints such as Whisper's: weights stay exact). */
+ * f16 != 0: planes and weights are IEEE fp16 instead of bf16 (fp16 checkpoints such as Whisper's: weights stay exact).
+ * up_stride > 0: TRANSPOSED conv with K = taps * up_stride in polyphase form -- Cout = up_stride * C, W[tap j][r*C + co][ci] =
+ * w[k = r + j*up_stride][ci][co], shifts[j] = -j; GEMM row m / column (r, co) lands on output row m*up_stride + r - up_crop
+ * (rows outside [0, Lout) dropped), i.e. the GEMM output IS the up-sampled signal, no col2im pass. */
 int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int32_t cpad,
                       const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
                       void* hi, void* lo, int32_t f16, void* stream);
@@ -91,7 +94,11 @@ int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B
                       int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                       int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                       int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
-                      int64_t y_bs, int64_t y_ld, void* stream);
+                      int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, void* stream);
+
+/* profiling aid: CTA (0,0,0) of subsequent b2a_conv1d_tc launches stamps clock64() at its phase boundaries into dbg8[0..6]
+ * (entry, setup done, first operands landed, last operands landed, accumulator ready, epilogue done, exit); NULL disables. */
+int32_t b2a_conv1d_tc_debug(void* dbg8);
 
 /* strided 2-D copy (concat without torch.cat): dst[r, c] = src[r, c] */
 int32_t b2a_copy2d(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int32_t cols, void* stream);

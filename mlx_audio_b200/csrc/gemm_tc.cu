@@ -83,12 +83,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 
 struct TcParams {
   int B, L, Lout, Cout, cin_pad, taps, planes, BN, stages, f16;
+  int Mrows, up_s, up_crop, C;     // transposed-conv mode: N = up_s * C, GEMM row m & column (r, co) -> output row m*up_s + r - up_crop
   int shift[32];
   const float* bias; int post_act; float post_p0;
   const float* cscale; int64_t cscale_bs;
   const float* res; int64_t res_bs, res_ld; int res_div;
   float out_scale; int accumulate;
   float* y; int64_t y_bs, y_ld;
+  long long* dbg;                 // optional: 8 clock64 stamps from CTA (0,0,0) (b2a_conv1d_tc_debug)
 };
 
 // smem: [stages] x { A_hi 16 KB | A_lo 16 KB (planes==2) | W BN*128 B }, then barriers
@@ -105,6 +107,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   uint64_t* tmem_full = empty + p.stages;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
+  const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = clock64();
   const int l0 = blockIdx.x * TM, n0 = blockIdx.y * p.BN, b = blockIdx.z;
   const int kchunks = p.cin_pad / TK;
   const int iters = p.taps * kchunks;
@@ -126,6 +130,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -150,6 +155,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const int s = it % p.stages, ph = (it / p.stages) & 1;
       mbar_wait(full + s, ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (dbg && lane == 0 && it == 0) p.dbg[2] = clock64();
+      if (dbg && lane == 0 && it == iters - 1) p.dbg[3] = clock64();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
         const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes);
@@ -165,42 +172,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       __syncwarp();
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (per-warp shared-memory transpose) -> coalesced global =====
+    // tcgen05.ld hands lane i the 32 columns of ROW i; writing that straight out makes every global access touch 32
+    // different rows (32 sectors per instruction, latencies exposed one after another: measured 9k cycles per 32-column
+    // chunk, 5x the main loop).  Each warp therefore transposes its 32x32 chunk through a padded smem tile and then
+    // reads/writes whole 128-byte row segments: residual and previous-output loads for all 32 rows are issued first.
     const int quarter = warp & 3;
+    float* stage = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * (32 * 33);
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int l = l0 + quarter * 32 + lane;
-    const bool row_ok = l < p.Lout;
-    float* yrow = p.y + (int64_t)b * p.y_bs + (int64_t)l * p.y_ld;
-    const float* rrow = p.res ? p.res + (int64_t)b * p.res_bs + (int64_t)(l / p.res_div) * p.res_ld : nullptr;
+    if (dbg && warp == 2 && lane == 0) p.dbg[4] = clock64();
+    const int mrow0 = l0 + quarter * 32;                           // first GEMM row of this warp's quarter
+    const int mul = p.up_s ? p.up_s : 1;
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-      if (!row_ok) continue;
+      if (mrow0 >= p.Mrows) continue;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = n0 + c0 + j;
-        if (n >= p.Cout) break;
-        float v[4];
+      for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      const int n = n0 + c0 + lane;                               // GEMM column of this lane for every row below
+      const int ph = p.up_s ? n / p.C : 0;                         // up-sampling phase (uniform over the 32-column chunk)
+      const int co = n - ph * p.C;                                 // output channel
+      const int add = p.up_s ? ph - p.up_crop : 0;
+      const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
+      const float cs = p.cscale ? __ldg(p.cscale + (int64_t)b * p.cscale_bs + co) : 1.f;
+      float* ycol = p.y + (int64_t)b * p.y_bs + co;
+      const float* rcol = p.res ? p.res + (int64_t)b * p.res_bs + co : nullptr;
+      float rr[32], oo[32];
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          float t = __uint_as_float(r[j + q]);
-          if (p.bias) t += __ldg(p.bias + n + q);
-          if (p.post_act) t = b2a_act(t, p.post_act, p.post_p0, 1.f, 1.f);
-          if (p.cscale) t *= __ldg(p.cscale + (int64_t)b * p.cscale_bs + n + q);
-          v[q] = t;
-        }
-        if (rrow) { float4 rr = *reinterpret_cast<const float4*>(rrow + n); v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w; }
-#pragma unroll
-        for (int q = 0; q < 4; q++) v[q] *= p.out_scale;
-        float4* yp = reinterpret_cast<float4*>(yrow + n);
-        if (p.accumulate) { float4 o = *yp; v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
-        *yp = make_float4(v[0], v[1], v[2], v[3]);
+      for (int i = 0; i < 32; i++) {
+        const int64_t row = (int64_t)(mrow0 + i) * mul + add;
+        const bool ok = (mrow0 + i) < p.Mrows && row >= 0 && row < p.Lout;
+        rr[i] = (rcol && ok) ? __ldg(rcol + (row / p.res_div) * p.res_ld) : 0.f;
+        oo[i] = (p.accumulate && ok) ? ycol[row * p.y_ld] : 0.f;
       }
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const int64_t row = (int64_t)(mrow0 + i) * mul + add;
+        if ((mrow0 + i) < p.Mrows && row >= 0 && row < p.Lout) {
+          float t = stage[i * 33 + lane] + bias;
+          if (p.post_act) t = b2a_act(t, p.post_act, p.post_p0, 1.f, 1.f);
+          ycol[row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
+        }
+      }
+      __syncwarp();
     }
   }
+  if (dbg && warp == 2 && lane == 0) p.dbg[5] = clock64();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (dbg && threadIdx.x == 0) p.dbg[6] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.BN) : "memory");
@@ -214,35 +236,44 @@ template <> __device__ __forceinline__ __half to16<__half>(float v) { return __f
 __device__ __forceinline__ float from16(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float from16(__half v) { return __half2float(v); }
 
+// 8 channels per thread: 2 x 16-byte reads, one 16-byte write per plane
 template <typename T16>
 __global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int B, int L, int C, int cpad,
                                  const float* __restrict__ scale, const float* __restrict__ shift, int act, float p0,
                                  const float* __restrict__ a, const float* __restrict__ bb, T16* __restrict__ hi,
                                  T16* __restrict__ lo) {
-  const int cp2 = cpad / 2;
-  const int64_t total = (int64_t)B * L * cp2;
+  const int cp8 = cpad / 8;
+  const int64_t total = (int64_t)B * L * cp8;
+  const bool vec = (x_ld % 4 == 0) && (x_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    int c = (int)(idx % cp2) * 2;
-    int64_t r = idx / cp2;
-    int l = (int)(r % L), b = (int)(r / L);
-    float v[2] = {0.f, 0.f};
+    const int c = (int)(idx % cp8) * 8;
+    const int64_t r = idx / cp8;
+    const int l = (int)(r % L), b = (int)(r / L);
+    const float* xp = x + (int64_t)b * x_bs + (int64_t)l * x_ld + c;
+    float v[8];
+    if (vec && c + 8 <= C) {
+      float4 t0 = __ldg(reinterpret_cast<const float4*>(xp)), t1 = __ldg(reinterpret_cast<const float4*>(xp) + 1);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    } else {
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-      int cc = c + q;
+      for (int q = 0; q < 8; q++) v[q] = (c + q < C) ? __ldg(xp + q) : 0.f;
+    }
+    __align__(16) T16 h[8];
+    __align__(16) T16 lw[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int cc = c + q;
+      float t = 0.f;
       if (cc < C) {
-        float t = __ldg(x + (int64_t)b * x_bs + (int64_t)l * x_ld + cc);
+        t = v[q];
         if (scale) t = fmaf(t, __ldg(scale + (int64_t)b * C + cc), __ldg(shift + (int64_t)b * C + cc));
         if (act) t = b2a_act(t, act, p0, a ? __ldg(a + cc) : 1.f, bb ? __ldg(bb + cc) : 1.f);
-        v[q] = t;
       }
+      h[q] = to16<T16>(t);
+      lw[q] = to16<T16>(t - from16(h[q]));
     }
-    T16 h0 = to16<T16>(v[0]), h1 = to16<T16>(v[1]);
-    T16 hv[2] = {h0, h1};
-    *reinterpret_cast<uint32_t*>(hi + r * cpad + c) = *reinterpret_cast<uint32_t*>(hv);
-    if (lo) {
-      T16 lv[2] = {to16<T16>(v[0] - from16(h0)), to16<T16>(v[1] - from16(h1))};
-      *reinterpret_cast<uint32_t*>(lo + r * cpad + c) = *reinterpret_cast<uint32_t*>(lv);
-    }
+    *reinterpret_cast<uint4*>(hi + r * cpad + c) = *reinterpret_cast<uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + r * cpad + c) = *reinterpret_cast<uint4*>(lw);
   }
 }
 
@@ -250,6 +281,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+long long* g_dbg = nullptr;
 
 int get_encode() {
   if (g_encode) return 0;
@@ -272,12 +304,15 @@ int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, c
 
 }  // namespace
 
+/* debug aid: device buffer of 8 int64 that the next b2a_conv1d_tc launches stamp with clock64() at their phase boundaries */
+extern "C" int32_t b2a_conv1d_tc_debug(void* dbg8) { g_dbg = (long long*)dbg8; return B2A_OK; }
+
 extern "C" int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int32_t cpad,
                                  const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
                                  void* hi, void* lo, int32_t f16, void* stream) {
   B2A_CHECK_ARG(x && hi && B > 0 && L > 0 && C > 0 && cpad >= C && cpad % 64 == 0, "bad pointers/shape (cpad must be a multiple of 64)");
   B2A_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift come together");
-  int64_t total = (int64_t)B * L * (cpad / 2);
+  int64_t total = (int64_t)B * L * (cpad / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   if (f16) prep_bf16_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
                                                                               (__half*)hi, (__half*)lo);
@@ -291,22 +326,27 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
                                  int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                                  int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                                  int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
-                                 int64_t y_bs, int64_t y_ld, void* stream) {
+                                 int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, void* stream) {
   B2A_CHECK_ARG(a_hi && w_bf16 && y && shifts_host, "null pointer");
+  B2A_CHECK_ARG(up_stride >= 0 && up_crop >= 0 && (up_stride == 0 || (Cout % up_stride == 0 && (Cout / up_stride) % 32 == 0)),
+                "transposed mode: Cout = up_stride * C with C a multiple of 32");
   B2A_CHECK_ARG(B > 0 && L > 0 && Lout > 0 && taps > 0 && taps <= 32 && cin_pad % 64 == 0 && res_div > 0, "bad shape");
   B2A_CHECK_ARG(Cout % 32 == 0 && y_ld % 4 == 0 && (res == nullptr || res_ld % 4 == 0), "Cout must be a multiple of 32; row strides multiples of 4");
   if (get_encode() != 0) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled entry point not found"); return B2A_E_CUDA; }
   TcParams p;
   p.f16 = f16 ? 1 : 0;
+  p.up_s = up_stride; p.up_crop = up_crop; p.C = up_stride ? Cout / up_stride : Cout;
+  p.Mrows = up_stride ? L + taps - 1 : Lout;
   p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
   p.BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32));
   for (int i = 0; i < taps; i++) p.shift[i] = shifts_host[i];
   p.bias = bias; p.post_act = post_act; p.post_p0 = post_p0; p.cscale = cscale; p.cscale_bs = cscale_bs;
   p.res = res; p.res_bs = res_bs; p.res_ld = res_ld; p.res_div = res_div; p.out_scale = out_scale; p.accumulate = accumulate;
   p.y = y; p.y_bs = y_bs; p.y_ld = y_ld;
+  p.dbg = g_dbg;
   const int stage_bytes = TM * 128 * p.planes + p.BN * 128;
-  p.stages = (200 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 16;
+  p.stages = (196 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 32 + 4 * 32 * 33 * sizeof(float);
 
   CUtensorMap mh, ml, mw;
   uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
@@ -322,7 +362,7 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
 
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
-  dim3 grid(cdiv(Lout, TM), Cout / p.BN, B);
+  dim3 grid(cdiv(p.Mrows, TM), Cout / p.BN, B);
   conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mh, ml, mw, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;

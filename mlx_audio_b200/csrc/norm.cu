@@ -30,13 +30,16 @@ __global__ void adain_partial_kernel(const float* __restrict__ x, int64_t x_bs, 
   }
 }
 
+// one warp per (b, c): lanes stride the chunk partials (a serial walk over ~200 chunks per thread cost 20 us per call)
 __global__ void adain_final_kernel(const double* __restrict__ ws, int nchunk, int L, int C, const float* __restrict__ gb,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift, int B) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (i >= B * C) return;
-  int b = i / C, c = i % C;
+  const int b = i / C, c = i % C;
   double t1 = 0, t2 = 0;
-  for (int k = 0; k < nchunk; k++) { const double* w = ws + (((int64_t)b * nchunk + k) * C + c) * 2; t1 += w[0]; t2 += w[1]; }
+  for (int k = lane; k < nchunk; k += 32) { const double* w = ws + (((int64_t)b * nchunk + k) * C + c) * 2; t1 += w[0]; t2 += w[1]; }
+  t1 = warp_sum_d(t1); t2 = warp_sum_d(t2);
+  if (lane) return;
   double mean = t1 / L, var = t2 / L - mean * mean;
   if (var < 0) var = 0;
   double rstd = 1.0 / sqrt(var + (double)eps);
@@ -89,7 +92,7 @@ extern "C" int32_t b2a_adain_coeffs(const float* x, int64_t x_bs, int64_t x_ld, 
   int nchunk = (L + ROWS_PER_CHUNK - 1) / ROWS_PER_CHUNK;
   dim3 grid(cdiv(C, 32), nchunk, B), block(32, 8);
   adain_partial_kernel<<<grid, block, 0, st>>>(x, x_bs, x_ld, L, C, (double*)ws, nchunk);
-  adain_final_kernel<<<cdiv((int64_t)B * C, 256), 256, 0, st>>>((const double*)ws, nchunk, L, C, gb, eps, scale, shift, B);
+  adain_final_kernel<<<cdiv((int64_t)B * C, 8), 256, 0, st>>>((const double*)ws, nchunk, L, C, gb, eps, scale, shift, B);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

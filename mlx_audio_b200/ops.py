@@ -123,14 +123,24 @@ TC_MODE = [os.environ.get("B2A_TC", "off")]
 TC_MIN_K = 128                         # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
 
 
-def _vec4_ok(t: Optional[torch.Tensor]) -> bool:
-    """The tensor-core epilogue reads/writes rows as float4: 16-byte aligned base and row stride."""
-    return t is None or (t.data_ptr() % 16 == 0 and t.stride(1) % 4 == 0 and (t.shape[0] == 1 or t.stride(0) % 4 == 0))
+def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int, dilation: int = 1) -> bool:
+    if TC_MODE[0] == "off" or cw.w_tc is None or pad_mode != 0 or cw.cout % 32 != 0 or L < 32:
+        return False
+    if transpose:                      # polyphase form: K = taps * stride, every phase is a `taps`-tap stride-1 conv
+        return dilation == 1 and cw.K % stride == 0 and cw.cin * (cw.K // stride) >= TC_MIN_K
+    return stride == 1 and cw.cin * cw.K >= TC_MIN_K
 
 
-def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int) -> bool:
-    return (TC_MODE[0] != "off" and cw.w_tc is not None and stride == 1 and not transpose and pad_mode == 0
-            and cw.cout % 32 == 0 and cw.cin * cw.K >= TC_MIN_K and L >= 32)
+def _tc_transposed_weights(cw: "ConvW", stride: int) -> torch.Tensor:
+    """[J, stride*Cout, cin_pad] with W[j, r*Cout + co, ci] = w[k = r + j*stride][ci][co] (cached per stride)."""
+    cache = cw.__dict__.setdefault("_w_tc_tr", {})
+    if stride not in cache:
+        J = cw.K // stride
+        w = cw.w.reshape(J, stride, cw.cin, cw.cout).permute(0, 1, 3, 2).reshape(J, stride * cw.cout, cw.cin)   # k = j*stride + r
+        wt = torch.zeros(J, stride * cw.cout, cw.cin_pad, device=cw.w.device, dtype=cw.w_tc.dtype)
+        wt[:, :, :cw.cin] = w.to(cw.w_tc.dtype)
+        cache[stride] = wt.contiguous()
+    return cache[stride]
 
 
 def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
@@ -176,8 +186,9 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L - 1) * stride + cw.K - 2 * pad_left
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
-    if _tc_eligible(cw, L, stride, transpose, pad_mode) and _vec4_ok(out) and _vec4_ok(res):
-        return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate)
+    if _tc_eligible(cw, L, stride, transpose, pad_mode, dilation):
+        return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
+                          up_stride=stride if transpose else 0)
     if out is None:
         out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
     else:
@@ -221,7 +232,8 @@ def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2, f
     return hi, lo
 
 
-def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate):
+def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
+               up_stride=0):
     B, L, _ = x.shape
     hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1, cw.f16)
     if out is None:
@@ -230,15 +242,20 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
         _chk3(out, "conv1d out")
         if out.shape != (B, lout, cw.cout):
             raise ValueError(f"conv1d: out has shape {tuple(out.shape)}, expected {(B, lout, cw.cout)}")
-    shifts = (C.c_int32 * cw.K)(*[k * dilation - pad_left for k in range(cw.K)])
+    if up_stride:
+        taps, n_total, w_tc = cw.K // up_stride, up_stride * cw.cout, _tc_transposed_weights(cw, up_stride)
+        shifts = (C.c_int32 * taps)(*[-j for j in range(taps)])
+    else:
+        taps, n_total, w_tc = cw.K, cw.cout, cw.w_tc
+        shifts = (C.c_int32 * taps)(*[k * dilation - pad_left for k in range(taps)])
     cs, cs_bs = (None, 0) if cscale is None else (cscale.data_ptr(), cscale.stride(0) if cscale.dim() == 2 else 0)
     r, r_bs, r_ld = (None, 0, 0)
     if res is not None:
         _chk3(res, "conv1d res")
         r, r_bs, r_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
-    _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, cw.w_tc.data_ptr(), cw.K, shifts, cw.cout, lout,
+    _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, w_tc.data_ptr(), taps, shifts, n_total, lout,
           _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
-          out.stride(1), _stream())
+          out.stride(1), up_stride, pad_left if up_stride else 0, _stream())
     return out
 
 

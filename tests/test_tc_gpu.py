@@ -85,3 +85,28 @@ def test_conv1d_tc_epilogue_variants():
         ops.TC_MODE[0] = old
     assert rel_err(y, ref) < 2e-5 and rel_err(big[:, :, 8:72], ref) < 2e-5
     assert float(big[:, :, :8].abs().max()) == 0 and float(big[:, :, 72:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,K,stride,pad,opad", [(1, 780, 512, 256, 20, 10, 5, 0), (1, 500, 256, 128, 12, 6, 3, 0),
+                                                             (2, 300, 128, 64, 16, 8, 4, 1), (1, 257, 64, 32, 4, 2, 1, 1), (1, 100, 256, 128, 8, 4, 0, 0)])
+def test_convtr1d_tc_polyphase(B, L, Cin, Cout, K, stride, pad, opad):
+    """Transposed conv on the tensor-core path (K = 2*stride, polyphase: the GEMM output is the up-sampled signal)."""
+    from mlx_audio_b200 import ops
+    dev = torch.device("cuda:0")
+    x = _rand(B, L, Cin, seed=1)
+    w = _rand(Cout, K, Cin, seed=2, scale=0.05).to(torch.bfloat16).float()
+    bias = _rand(Cout, seed=3, scale=0.1)
+    ref = ON.conv_transpose1d(ON.leaky_relu(x.double(), 0.1), w.double(), stride, pad, 1, opad, 1, bias.double())
+    res = _rand(*ref.shape, seed=5)
+    ref = ref + res.double()
+    cw = ops.pack_conv(w, bias, 1, dev)
+    old = ops.TC_MODE[0]
+    try:
+        ops.TC_MODE[0] = "x2"
+        assert ops._tc_eligible(cw, L, stride, True, 0)
+        y = ops.conv1d(x.to(dev), cw, stride=stride, pad_left=pad, lout=ref.shape[1], pre=ops.Pre(act=ops.ACT["lrelu"], p0=0.1),
+                       res=res.to(dev), transpose=True)
+        torch.cuda.synchronize()
+    finally:
+        ops.TC_MODE[0] = old
+    assert y.shape == ref.shape and rel_err(y, ref) < 2e-5
