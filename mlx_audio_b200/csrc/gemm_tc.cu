@@ -199,21 +199,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const float cs = p.cscale ? __ldg(p.cscale + (int64_t)b * p.cscale_bs + co) : 1.f;
       float* ycol = p.y + (int64_t)b * p.y_bs + co;
       const float* rcol = p.res ? p.res + (int64_t)b * p.res_bs + co : nullptr;
+      // 32-bit row arithmetic only (a 64-bit divide per element made this loop 20k cycles per chunk); res_div is 1 or 2
+      const int row0 = mrow0 * mul + add;
+      const int rdiv = p.res_div;
+      const int mvalid = min(32, p.Mrows - mrow0);
       float rr[32], oo[32];
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        const int64_t row = (int64_t)(mrow0 + i) * mul + add;
-        const bool ok = (mrow0 + i) < p.Mrows && row >= 0 && row < p.Lout;
-        rr[i] = (rcol && ok) ? __ldg(rcol + (row / p.res_div) * p.res_ld) : 0.f;
-        oo[i] = (p.accumulate && ok) ? ycol[row * p.y_ld] : 0.f;
+        const int row = row0 + i * mul;
+        const bool ok = i < mvalid && row >= 0 && row < p.Lout;
+        const int rrow = rdiv == 1 ? row : (int)((unsigned)max(row, 0) / (unsigned)rdiv);
+        rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)rrow * p.res_ld) : 0.f;
+        oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
       }
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        const int64_t row = (int64_t)(mrow0 + i) * mul + add;
-        if ((mrow0 + i) < p.Mrows && row >= 0 && row < p.Lout) {
+        const int row = row0 + i * mul;
+        if (i < mvalid && row >= 0 && row < p.Lout) {
           float t = stage[i * 33 + lane] + bias;
           if (p.post_act) t = b2a_act(t, p.post_act, p.post_p0, 1.f, 1.f);
-          ycol[row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
+          ycol[(int64_t)row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
         }
       }
       __syncwarp();
