@@ -81,6 +81,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __noinline__ float act_noinline(float v, int act, float p0) { return b2a_act(v, act, p0, 1.f, 1.f); }
+
 struct TcParams {
   int B, L, Lout, Cout, cin_pad, taps, planes, BN, stages, f16;
   int Mrows, up_s, up_crop, C;     // transposed-conv mode: N = up_s * C, GEMM row m & column (r, co) -> output row m*up_s + r - up_crop
@@ -199,26 +201,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const float cs = p.cscale ? __ldg(p.cscale + (int64_t)b * p.cscale_bs + co) : 1.f;
       float* ycol = p.y + (int64_t)b * p.y_bs + co;
       const float* rcol = p.res ? p.res + (int64_t)b * p.res_bs + co : nullptr;
-      // 32-bit row arithmetic only (a 64-bit divide per element made this loop 20k cycles per chunk); res_div is 1 or 2
+      // Rows go out in 4 groups of 8 (loads of a group issued before its stores).  Code size matters here: a full 32x
+      // unroll with a variable divide and the inlined activation switch produced ~200 KB of SASS and ~13k cycles per chunk.
       const int row0 = mrow0 * mul + add;
-      const int rdiv = p.res_div;
+      const int rsh = p.res_div == 2 ? 1 : 0;                      // res_div is 1 or 2 (nearest x2 shortcut, istftnet.py:838-850)
       const int mvalid = min(32, p.Mrows - mrow0);
-      float rr[32], oo[32];
+#pragma unroll 1
+      for (int g = 0; g < 32; g += 8) {
+        float rr[8], oo[8];
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const int row = row0 + i * mul;
-        const bool ok = i < mvalid && row >= 0 && row < p.Lout;
-        const int rrow = rdiv == 1 ? row : (int)((unsigned)max(row, 0) / (unsigned)rdiv);
-        rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)rrow * p.res_ld) : 0.f;
-        oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
-      }
+        for (int i = 0; i < 8; i++) {
+          const int row = row0 + (g + i) * mul;
+          const bool ok = (g + i) < mvalid && row >= 0 && row < p.Lout;
+          rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)(row >> rsh) * p.res_ld) : 0.f;
+          oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
+        }
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const int row = row0 + i * mul;
-        if (i < mvalid && row >= 0 && row < p.Lout) {
-          float t = stage[i * 33 + lane] + bias;
-          if (p.post_act) t = b2a_act(t, p.post_act, p.post_p0, 1.f, 1.f);
-          ycol[(int64_t)row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
+        for (int i = 0; i < 8; i++) {
+          const int row = row0 + (g + i) * mul;
+          if ((g + i) < mvalid && row >= 0 && row < p.Lout) {
+            float t = stage[(g + i) * 33 + lane] + bias;
+            if (p.post_act) t = act_noinline(t, p.post_act, p.post_p0);
+            ycol[(int64_t)row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
+          }
         }
       }
       __syncwarp();
@@ -335,7 +340,7 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   B2A_CHECK_ARG(a_hi && w_bf16 && y && shifts_host, "null pointer");
   B2A_CHECK_ARG(up_stride >= 0 && up_crop >= 0 && (up_stride == 0 || (Cout % up_stride == 0 && (Cout / up_stride) % 32 == 0)),
                 "transposed mode: Cout = up_stride * C with C a multiple of 32");
-  B2A_CHECK_ARG(B > 0 && L > 0 && Lout > 0 && taps > 0 && taps <= 32 && cin_pad % 64 == 0 && res_div > 0, "bad shape");
+  B2A_CHECK_ARG(B > 0 && L > 0 && Lout > 0 && taps > 0 && taps <= 32 && cin_pad % 64 == 0 && (res_div == 1 || res_div == 2), "bad shape (res_div must be 1 or 2)");
   B2A_CHECK_ARG(Cout % 32 == 0 && y_ld % 4 == 0 && (res == nullptr || res_ld % 4 == 0), "Cout must be a multiple of 32; row strides multiples of 4");
   if (get_encode() != 0) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled entry point not found"); return B2A_E_CUDA; }
   TcParams p;
