@@ -102,9 +102,11 @@ int32_t b2a_conv1d_tc_debug(void* dbg8);
 
 /* strided 2-D copy (concat without torch.cat): dst[r, c] = src[r, c] */
 int32_t b2a_copy2d(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int32_t cols, void* stream);
-/* dst[r, :] = src[idx[r], :]  -- the alignment expansion `x @ pred_aln_trg` of kokoro.py:148-170 and nn.Embedding */
+/* dst[r, :] = src[idx[r], :] (+ add[r % add_period, :] if add != NULL) -- the alignment expansion `x @ pred_aln_trg` of
+ * kokoro.py:148-170, nn.Embedding, and token + positional embedding (whisper.py:483-486) */
 int32_t b2a_gather_rows(const float* src, int64_t src_ld, const int64_t* idx, float* dst, int64_t dst_ld,
-                        int64_t rows, int32_t cols, int64_t n_src_rows, void* stream);
+                        int64_t rows, int32_t cols, int64_t n_src_rows, const float* add, int64_t add_ld, int64_t add_period,
+                        void* stream);
 /* Duration head + alignment (kokoro.py:140-164): if dur_f != NULL, pred_dur[t] = clip(round_half_even(dur_f[t] / speed), 1, 100)
  * with nan->1, +inf->100, -inf->1 (mx.nan_to_num / mx.round / mx.clip); else pred_dur = dur_i.  Then idx_out[f] = token of
  * frame f (device prefix sum, frames beyond max_frames dropped) and *total_dev = sum(pred_dur). */
@@ -180,6 +182,17 @@ int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_
 /* out[i] ~ N(0,1), i < n: Philox4x32-10 keyed by `seed`, counter `offset + i/4`, Box-Muller.  The production replacement for
  * mx.random.normal in SineGen / NoiseBlock (istftnet.py:649, snac/layers.py:263); parity tests inject the noise instead. */
 int32_t b2a_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- Whisper decode step (stt/models/whisper/decoding.py:307-325,349-442) -----------------------------------
+ * One launch = SuppressBlank + SuppressTokens + ApplyTimestampRules + GreedyDecoder.update(temperature 0) for every row:
+ * next_out[b] = argmax of the filtered logits (eot once a row has ended), sum_logprobs[b] += its log-probability while the row
+ * is live, *not_done += 1 per row whose next token is not eot.  tokens [B, >= cur_len] is the device-resident history
+ * (no per-step tolist()); suppress_mask / blank_mask are additive 0/-inf vectors [V] (NULL = none); max_initial_ts < 0 = off. */
+int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_bs, const int64_t* tokens, int64_t tokens_bs,
+                                int32_t B, int32_t cur_len, int32_t sample_begin, int32_t V, const float* suppress_mask,
+                                const float* blank_mask, int32_t eot, int32_t no_timestamps, int32_t timestamp_begin,
+                                int32_t max_initial_ts, int32_t without_timestamps, int64_t* next_out,
+                                float* sum_logprobs, int32_t* not_done, void* stream);
 
 /* ---- codec (RVQ decode) ---------------------------------------------------------------------
  * out[b,t,:] (+)= sum_q codebooks[q][codes[b,q,t]][:]   (mimi/modules/quantization.py:47-49,103-108;

@@ -53,7 +53,7 @@ PROTOTYPES = {
                             c_f, i64, i64, i32, i32, C.c_void_p]),
     "b2a_conv1d_tc_debug": (i32, [c_f]),
     "b2a_copy2d": (i32, [c_f, i64, c_f, i64, i64, i32, C.c_void_p]),
-    "b2a_gather_rows": (i32, [c_f, i64, c_f, c_f, i64, i64, i32, i64, C.c_void_p]),
+    "b2a_gather_rows": (i32, [c_f, i64, c_f, c_f, i64, i64, i32, i64, c_f, i64, i64, C.c_void_p]),
     "b2a_durations_to_index": (i32, [c_f, c_f, i32, f32, c_f, c_f, i64, c_f, C.c_void_p]),
     "b2a_adain_ws_bytes": (i64, [i32, i32, i32]),
     "b2a_adain_coeffs": (i32, [c_f, i64, i64, i32, i32, i32, c_f, f32, c_f, c_f, c_f, C.c_void_p]),
@@ -67,6 +67,7 @@ PROTOTYPES = {
     "b2a_kokoro_source": (i32, [c_f, i32, i32, i32, c_f, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
     "b2a_kokoro_istft_head": (i32, [c_f, i64, i64, i32, i32, c_f, C.c_void_p]),
     "b2a_randn": (i32, [c_f, i64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b2a_whisper_greedy_step": (i32, [c_f, i64, c_f, i64, i32, i32, i32, i32, c_f, c_f, i32, i32, i32, i32, i32, c_f, c_f, c_f, C.c_void_p]),
     "b2a_rvq_decode": (i32, [c_f, i64, i64, i32, i32, i64, c_f, i32, i32, c_f, i64, c_f, C.c_void_p]),
     "b2a_snac_from_codes": (i32, [C.POINTER(C.c_void_p), C.POINTER(i32), i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), i32, i64, i32, i32, i32, c_f, c_f, C.c_void_p]),

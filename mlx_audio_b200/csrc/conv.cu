@@ -230,13 +230,16 @@ __global__ void copy2d_kernel(const float* __restrict__ src, int64_t src_ld, flo
 }
 
 __global__ void gather_rows_kernel(const float* __restrict__ src, int64_t src_ld, const int64_t* __restrict__ idx_,
-                                   float* __restrict__ dst, int64_t dst_ld, int64_t rows, int cols, int64_t n_src) {
+                                   float* __restrict__ dst, int64_t dst_ld, int64_t rows, int cols, int64_t n_src,
+                                   const float* __restrict__ add, int64_t add_ld, int64_t add_period) {
   int64_t total = rows * cols;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = idx / cols; int c = (int)(idx % cols);
     int64_t s = idx_[r];
     s = s < 0 ? 0 : (s >= n_src ? n_src - 1 : s);
-    dst[r * dst_ld + c] = src[s * src_ld + c];
+    float v = src[s * src_ld + c];
+    if (add) v += add[(r % add_period) * add_ld + c];          // e.g. token embedding + positional embedding (whisper.py:483-486)
+    dst[r * dst_ld + c] = v;
   }
 }
 
@@ -351,12 +354,14 @@ extern "C" int32_t b2a_copy2d(const float* src, int64_t src_ld, float* dst, int6
 }
 
 extern "C" int32_t b2a_gather_rows(const float* src, int64_t src_ld, const int64_t* idx, float* dst, int64_t dst_ld,
-                                   int64_t rows, int32_t cols, int64_t n_src_rows, void* stream) {
-  B2A_CHECK_ARG(src && dst && idx && rows >= 0 && cols > 0 && n_src_rows > 0, "bad pointers/shape");
+                                   int64_t rows, int32_t cols, int64_t n_src_rows, const float* add, int64_t add_ld,
+                                   int64_t add_period, void* stream) {
+  B2A_CHECK_ARG(src && dst && idx && rows >= 0 && cols > 0 && n_src_rows > 0 && (!add || add_period > 0), "bad pointers/shape");
   if (rows == 0) return B2A_OK;
   int64_t total = rows * cols;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, idx, dst, dst_ld, rows, cols, n_src_rows);
+  gather_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, idx, dst, dst_ld, rows, cols, n_src_rows, add, add_ld,
+                                                               add_period);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -279,15 +279,29 @@ def copy2d(src: torch.Tensor, dst: torch.Tensor) -> None:
     _call("other", _lib.lib().b2a_copy2d, 1, src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, _stream())
 
 
-def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r, :] = src[idx[r], :]; src [N, C] float32, idx int64 [R]."""
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r, :] = src[idx[r], :] (+ add[r % add.shape[0], :]); src [N, C] float32, idx int64 [R]."""
     assert src.dim() == 2 and src.stride(1) == 1 and idx.dtype == torch.int64 and idx.is_contiguous()
     rows, cols = idx.shape[0], src.shape[1]
     if out is None:
         out = torch.empty(rows, cols, device=src.device, dtype=torch.float32)
+    a, a_ld, a_per = (None, 0, 0) if add is None else (add.data_ptr(), add.stride(0), add.shape[0])
     _call("other", _lib.lib().b2a_gather_rows, 1, src.data_ptr(), src.stride(0), idx.data_ptr(), out.data_ptr(), out.stride(0),
-                                          rows, cols, src.shape[0], _stream())
+          rows, cols, src.shape[0], a, a_ld, a_per, _stream())
     return out
+
+
+def whisper_greedy_step(logits: torch.Tensor, tokens: torch.Tensor, cur_len: int, sample_begin: int, *, suppress_mask, blank_mask,
+                        eot: int, no_timestamps: int, timestamp_begin: int, max_initial_ts: int, without_timestamps: bool,
+                        sum_logprobs: torch.Tensor, not_done: torch.Tensor) -> torch.Tensor:
+    """Fused logit filters + greedy update (decoding.py:307-325,349-442).  logits [B,V] fp32, tokens [B, >=cur_len] int64."""
+    B, V = logits.shape
+    assert logits.stride(1) == 1 and tokens.dtype == torch.int64 and tokens.stride(1) == 1
+    nxt = torch.empty(B, device=logits.device, dtype=torch.int64)
+    _call("sampler", _lib.lib().b2a_whisper_greedy_step, 1, logits.data_ptr(), logits.stride(0), tokens.data_ptr(), tokens.stride(0), B, cur_len,
+          sample_begin, V, _p(suppress_mask), _p(blank_mask), eot, no_timestamps, timestamp_begin, max_initial_ts, int(without_timestamps),
+          nxt.data_ptr(), sum_logprobs.data_ptr(), not_done.data_ptr(), _stream())
+    return nxt
 
 
 def durations_to_index(dur, max_frames: int, speed: float = 1.0):

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
+from typing import Optional
 
 import torch
 
@@ -86,12 +87,106 @@ class AudioEncoder:
         return ops.layernorm(x, *W["ln_post"])
 
 
+@dataclass
+class TokenizerSpec:
+    """The tokenizer constants the decode loop needs (decoding.py:349-442; HFTokenizerWrapper properties, whisper.py:46-175).
+    Defaults: Whisper's multilingual vocabulary.  ``suppress`` = ids to suppress (the reference's "-1" expands to
+    tokenizer.non_speech_tokens, which needs the tokenizer files; pass the list when they are available)."""
+    eot: int = 50257
+    sot: int = 50258
+    no_timestamps: int = 50363
+    timestamp_begin: int = 50364
+    no_speech: int = 50362
+    blank_ids: tuple = (220,)
+    language: int = 50259
+    task: int = 50359
+    suppress: tuple = ()
+
+    @property
+    def sot_sequence(self):
+        return (self.sot, self.language, self.task)
+
+
+@dataclass
+class DecodingResult:
+    """decoding.py:152-162 (numeric fields; text needs the tokenizer files)."""
+    audio_features: torch.Tensor
+    tokens: list
+    avg_logprob: float
+    no_speech_prob: float
+    temperature: float = 0.0
+
+
+class TextDecoder:
+    """whisper.py:451-498 with an in-place KV cache: self-attention K|V rows are written by the projection GEMM straight
+    into a preallocated [B, n_ctx, 2d] buffer (the reference concatenates every step, whisper.py:359-361); cross-attention
+    K|V are computed once per audio window."""
+
+    def __init__(self, dims: ModelDimensions, device):
+        self.dims, self.device, self._w = dims, device, None
+
+    def load(self, P):
+        dev, d = self.device, self.dims.n_text_state
+        f = lambda t: t.float().to(dev).contiguous()
+        emb = P["decoder.token_embedding.weight"].float()
+        W = {"emb": f(emb), "pos": f(P["decoder.positional_embedding"]), "logits": ops.pack_linear(emb, None, dev), "blocks": []}
+        for i in range(self.dims.n_text_layer):
+            L = f"decoder.blocks.{i}"
+            kv = lambda a: ops.pack_linear(torch.cat([P[f"{L}.{a}.key.weight"].float(), P[f"{L}.{a}.value.weight"].float()], 0),
+                                           torch.cat([torch.zeros(d), P[f"{L}.{a}.value.bias"].float()], 0), dev)
+            lin = lambda n: ops.pack_linear(P[f"{L}.{n}.weight"].float(), P[f"{L}.{n}.bias"], dev)
+            ln = lambda n: (f(P[f"{L}.{n}.weight"]), f(P[f"{L}.{n}.bias"]))
+            W["blocks"].append({"attn_ln": ln("attn_ln"), "cross_ln": ln("cross_attn_ln"), "mlp_ln": ln("mlp_ln"),
+                                "q": lin("attn.query"), "kv": kv("attn"), "o": lin("attn.out"),
+                                "cq": lin("cross_attn.query"), "ckv": kv("cross_attn"), "co": lin("cross_attn.out"),
+                                "mlp1": lin("mlp1"), "mlp2": lin("mlp2")})
+        W["ln"] = (f(P["decoder.ln.weight"]), f(P["decoder.ln.bias"]))
+        self._w = W
+
+    def new_cache(self, xa: torch.Tensor):
+        """Allocate the self-attention cache and project the cross-attention K|V of ``xa`` [B,1500,d] once."""
+        W, d = self._w, self.dims.n_text_state
+        B = xa.shape[0]
+        xa = xa.to(device=self.device, dtype=torch.float32).contiguous()
+        return {"offset": 0, "self": [torch.empty(B, self.dims.n_text_ctx, 2 * d, device=self.device) for _ in W["blocks"]],
+                "cross": [ops.linear(xa, blk["ckv"]) for blk in W["blocks"]]}
+
+    @torch.no_grad()
+    def __call__(self, tokens: torch.Tensor, cache: dict, last_only: bool = True, also_first: bool = False):
+        """tokens int64 [B,n] -> logits [B,V] of the last position (and of position 0 when ``also_first``)."""
+        W, dims = self._w, self.dims
+        d, nh = dims.n_text_state, dims.n_text_head
+        B, n = tokens.shape
+        off = cache["offset"]
+        x = ops.gather_rows(W["emb"], tokens.reshape(-1).contiguous(), add=W["pos"][off:off + n]).reshape(B, n, d)
+        scale = (d // nh) ** -0.5                                           # q and k each carry d^-0.25 (whisper.py:373-375)
+        for blk, kvbuf, ckv in zip(W["blocks"], cache["self"], cache["cross"]):
+            h = ops.layernorm(x, *blk["attn_ln"])
+            q = ops.linear(h, blk["q"])
+            ops.linear(h, blk["kv"], out=kvbuf[:, off:off + n])               # K|V rows land in the cache
+            att = ops.attention(q, kvbuf[:, :off + n, :d], kvbuf[:, :off + n, d:], n_heads=nh, scale=scale, causal=True, q_offset=off)
+            x = ops.linear(att, blk["o"], res=x)
+            h = ops.layernorm(x, *blk["cross_ln"])
+            q = ops.linear(h, blk["cq"])
+            att = ops.attention(q, ckv[:, :, :d], ckv[:, :, d:], n_heads=nh, scale=scale)
+            x = ops.linear(att, blk["co"], res=x)
+            h = ops.layernorm(x, *blk["mlp_ln"])
+            m = ops.linear(h, blk["mlp1"], post_act=ACT["gelu"])
+            x = ops.linear(m, blk["mlp2"], res=x)
+        cache["offset"] = off + n
+        rows = x[:, -1:] if not also_first else torch.cat([x[:, -1:], x[:, :1]], 1)
+        hl = ops.layernorm(rows.contiguous(), *W["ln"])
+        logits = ops.linear(hl, W["logits"])                                  # tied embedding (whisper.py:498)
+        return (logits[:, 0], logits[:, 1]) if also_first else logits[:, 0]
+
+
 class Model:
-    """whisper.py:501-530 (encoder side)."""
+    """whisper.py:501-530."""
 
     def __init__(self, dims: ModelDimensions, dtype=torch.float16, device="cuda"):
         self.dims, self.dtype, self.device = dims, dtype, torch.device(device)
         self.encoder = AudioEncoder(dims, self.device)
+        self.decoder = TextDecoder(dims, self.device)
 
     @property
     def sample_rate(self):
@@ -104,8 +199,56 @@ class Model:
         return {k: v for k, v in weights.items() if "_positional_embedding" not in k}
 
     def load_weights(self, weights, strict=False):
-        self.encoder.load(dict(weights))
+        P = dict(weights)
+        if any(k.startswith("encoder.") for k in P):
+            self.encoder.load(P)
+        if any(k.startswith("decoder.") for k in P):
+            self.decoder.load(P)
         return self
+
+    @torch.no_grad()
+    def greedy_decode(self, audio_features: torch.Tensor, spec: Optional[TokenizerSpec] = None, sample_len: Optional[int] = None,
+                      max_initial_timestamp_index: Optional[int] = 50, without_timestamps: bool = False):
+        """DecodingTask.run with GreedyDecoder(temperature=0) (decoding.py:588-722) on encoder features [B,1500,d]:
+        the whole step -- logit filters, argmax, log-prob bookkeeping -- is one fused kernel on the device-resident token
+        history; the only host read per step is the `completed` flag (the reference also syncs on it, decoding.py:625).
+        Returns (tokens list per row incl. the sot sequence, sum_logprobs [B], no_speech_probs [B])."""
+        spec = spec or TokenizerSpec()
+        dims, dev = self.dims, self.device
+        B = audio_features.shape[0]
+        sample_len = sample_len or dims.n_text_ctx // 2
+        V = dims.n_vocab
+        init = list(spec.sot_sequence)
+        sb = len(init)
+        tokens = torch.zeros(B, dims.n_text_ctx + 2, dtype=torch.int64, device=dev)
+        tokens[:, :sb] = torch.tensor(init, device=dev)
+        neg = float("-inf")
+        sup = torch.zeros(V, device=dev)
+        if spec.suppress:
+            sup[list(spec.suppress)] = neg
+        blank = torch.zeros(V, device=dev)
+        blank[list(spec.blank_ids) + [spec.eot]] = neg
+        sum_lp = torch.zeros(B, device=dev)
+        not_done = torch.zeros(1, dtype=torch.int32, device=dev)
+        cache = self.decoder.new_cache(audio_features)
+        cur = sb
+        no_speech = None
+        for i in range(sample_len):
+            if i == 0:
+                logits, first = self.decoder(tokens[:, :cur], cache, also_first=True)
+                no_speech = torch.softmax(first, dim=-1)[:, spec.no_speech]            # one-off, not on the per-step path
+            else:
+                logits = self.decoder(tokens[:, cur - 1:cur], cache)
+            not_done.zero_()
+            nxt = ops.whisper_greedy_step(logits, tokens, cur, sb, suppress_mask=sup if spec.suppress else None, blank_mask=blank,
+                                          eot=spec.eot, no_timestamps=spec.no_timestamps, timestamp_begin=spec.timestamp_begin,
+                                          max_initial_ts=-1 if max_initial_timestamp_index is None else max_initial_timestamp_index,
+                                          without_timestamps=without_timestamps, sum_logprobs=sum_lp, not_done=not_done)
+            tokens[:, cur] = nxt
+            cur += 1
+            if int(not_done.item()) == 0 or cur > dims.n_text_ctx:
+                break
+        return tokens[:, :cur].cpu().tolist(), sum_lp, no_speech
 
     def embed_audio(self, mel):
         return self.encoder(mel)
@@ -117,4 +260,5 @@ class Model:
         return self.encoder(mel[:, :N_FRAMES])
 
     def generate(self, audio, **kw):
-        raise NotImplementedError("the Whisper decode loop is row next-1 of SURVEY.md section 8f; use embed_audio / encode_audio")
+        raise NotImplementedError("text in/out needs the tokenizer files (not available offline); the numeric path is "
+                                  "encode_audio(audio) -> greedy_decode(features, TokenizerSpec(...))")

@@ -329,3 +329,29 @@ def kokoro_to_torch_checkpoint(P):
         else:
             out[k] = v
     return out
+
+
+def whisper_decoder_weights(dims, seed=1):
+    """Parameter tree of stt/models/whisper/whisper.py:TextDecoder (fp16 checkpoint): N(0, 0.02), LN gains 1."""
+    g = _Gen(seed)
+    d = dims["n_text_state"]
+
+    def n(name, *shape, std=0.02):
+        g.P[name] = _f16(torch.randn(*shape, generator=g.g) * std)
+
+    n("decoder.token_embedding.weight", dims["n_vocab"], d, std=0.3)      # peaky logits so the decode rules see text/timestamp competition
+    n("decoder.positional_embedding", dims["n_text_ctx"], d)
+    for i in range(dims["n_text_layer"]):
+        L = f"decoder.blocks.{i}"
+        for a in ("attn", "cross_attn"):
+            for nm_ in ("query", "value", "out"):
+                n(f"{L}.{a}.{nm_}.weight", d, d); n(f"{L}.{a}.{nm_}.bias", d)
+            n(f"{L}.{a}.key.weight", d, d)
+        for ln in ("attn_ln", "cross_attn_ln", "mlp_ln"):
+            g.layer_norm(f"{L}.{ln}", d)
+        n(L + ".mlp1.weight", 4 * d, d); n(L + ".mlp1.bias", 4 * d)
+        n(L + ".mlp2.weight", d, 4 * d); n(L + ".mlp2.bias", d)
+    g.layer_norm("decoder.ln", d)
+    g.P["decoder.token_embedding.weight"][50364:] *= 0.25      # damp timestamp logits (random weights would otherwise let the
+    g.P["decoder.token_embedding.weight"] = _f16(g.P["decoder.token_embedding.weight"])   # 1501 timestamps out-vote every text token)
+    return g.P

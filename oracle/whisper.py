@@ -54,3 +54,142 @@ def encoder(P, mel, dims=WHISPER_SMALL):
         h = N.layer_norm(x, P[L + ".mlp_ln.weight"], P[L + ".mlp_ln.bias"])
         x = x + N.linear(N.gelu(N.linear(h, P[L + ".mlp1.weight"], P[L + ".mlp1.bias"])), P[L + ".mlp2.weight"], P[L + ".mlp2.bias"])
     return N.layer_norm(x, P["encoder.ln_post.weight"], P["encoder.ln_post.bias"])
+
+
+# ============================================================================= text decoder + greedy decoding (row a8)
+
+class TokenizerSpec:
+    """The tokenizer constants the decode loop touches (decoding.py:349-442, whisper.py:46-175).  Defaults are the public
+    ids of Whisper's multilingual vocabulary; no tokenizer files are needed for the numeric path."""
+    def __init__(self, eot=50257, sot=50258, no_timestamps=50363, timestamp_begin=50364, no_speech=50362, blank_ids=(220,),
+                 language=50259, task=50359):
+        self.eot, self.sot, self.no_timestamps, self.timestamp_begin, self.no_speech = eot, sot, no_timestamps, timestamp_begin, no_speech
+        self.blank_ids, self.language, self.task = tuple(blank_ids), language, task
+
+    @property
+    def sot_sequence(self):
+        return (self.sot, self.language, self.task)
+
+
+def decoder_forward(P, tokens, xa, kv_cache=None, dims=WHISPER_SMALL):
+    """TextDecoder.__call__ (whisper.py:476-498): tokens [B,n] int64, xa [B,1500,d] -> (logits [B,n,V], kv_cache)."""
+    dt = xa.dtype
+    nl, nh = dims["n_text_layer"], dims["n_text_head"]
+    offset = kv_cache[0][0][0].shape[1] if kv_cache else 0
+    x = P["decoder.token_embedding.weight"].to(dt)[tokens] + P["decoder.positional_embedding"].to(dt)[offset:offset + tokens.shape[-1]]
+    n_ctx = dims["n_text_ctx"]
+    mask = torch.triu(torch.full((n_ctx, n_ctx), float("-inf"), dtype=dt), diagonal=1)     # create_additive_causal_mask
+    if kv_cache is None:
+        kv_cache = [None] * nl
+    new_cache = []
+    for i in range(nl):
+        L = f"decoder.blocks.{i}"
+        kv, cross_kv = kv_cache[i] if kv_cache[i] else (None, None)
+        # self attention with concatenated KV (whisper.py:354-361)
+        h = N.layer_norm(x, P[L + ".attn_ln.weight"], P[L + ".attn_ln.bias"])
+        q = N.linear(h, P[L + ".attn.query.weight"], P[L + ".attn.query.bias"])
+        k = N.linear(h, P[L + ".attn.key.weight"])
+        v = N.linear(h, P[L + ".attn.value.weight"], P[L + ".attn.value.bias"])
+        if kv is not None:
+            k, v = torch.cat([kv[0], k], 1), torch.cat([kv[1], v], 1)
+        x = x + N.linear(_qkv_attention(q, k, v, nh, mask), P[L + ".attn.out.weight"], P[L + ".attn.out.bias"])
+        # cross attention, K/V computed once (whisper.py:362-366)
+        h = N.layer_norm(x, P[L + ".cross_attn_ln.weight"], P[L + ".cross_attn_ln.bias"])
+        q = N.linear(h, P[L + ".cross_attn.query.weight"], P[L + ".cross_attn.query.bias"])
+        if cross_kv is None:
+            cross_kv = (N.linear(xa, P[L + ".cross_attn.key.weight"]), N.linear(xa, P[L + ".cross_attn.value.weight"], P[L + ".cross_attn.value.bias"]))
+        x = x + N.linear(_qkv_attention(q, cross_kv[0], cross_kv[1], nh, None), P[L + ".cross_attn.out.weight"], P[L + ".cross_attn.out.bias"])
+        h = N.layer_norm(x, P[L + ".mlp_ln.weight"], P[L + ".mlp_ln.bias"])
+        x = x + N.linear(N.gelu(N.linear(h, P[L + ".mlp1.weight"], P[L + ".mlp1.bias"])), P[L + ".mlp2.weight"], P[L + ".mlp2.bias"])
+        new_cache.append(((k, v), cross_kv))
+    x = N.layer_norm(x, P["decoder.ln.weight"], P["decoder.ln.bias"])
+    return x @ P["decoder.token_embedding.weight"].to(dt).T, new_cache
+
+
+def _qkv_attention(q, k, v, n_head, mask):
+    """whisper.py:371-385 (q and k each scaled by d^-0.25; mask[:n_ctx,:n_ctx] added)."""
+    b, t, d = q.shape
+    scale = (d // n_head) ** -0.25
+    qh = q.reshape(b, t, n_head, -1).permute(0, 2, 1, 3) * scale
+    kh = k.reshape(b, k.shape[1], n_head, -1).permute(0, 2, 3, 1) * scale
+    vh = v.reshape(b, v.shape[1], n_head, -1).permute(0, 2, 1, 3)
+    qk = qh @ kh
+    if mask is not None:
+        qk = qk + mask[:t, :t]
+    return (torch.softmax(qk, dim=-1) @ vh).permute(0, 2, 1, 3).reshape(b, t, d)
+
+
+def apply_filters(logits, tokens, spec, sample_begin, suppress, max_initial_timestamp_index=50, without_timestamps=False):
+    """SuppressBlank -> SuppressTokens -> ApplyTimestampRules (decoding.py:349-442) on logits [B,V], tokens [B,n] (lists)."""
+    logits = logits.clone()
+    V = logits.shape[1]
+    if len(tokens[0]) == sample_begin:                                               # SuppressBlank
+        logits[:, list(spec.blank_ids) + [spec.eot]] = float("-inf")
+    if suppress:
+        logits[:, list(suppress)] = float("-inf")                                    # SuppressTokens
+    if without_timestamps:
+        return logits
+    mask = torch.zeros_like(logits)
+    mask[:, spec.no_timestamps] = float("-inf")
+    tb = spec.timestamp_begin
+    for k, row in enumerate(tokens):
+        seq = row[sample_begin:]
+        last_ts = len(seq) >= 1 and seq[-1] >= tb
+        pen_ts = len(seq) < 2 or seq[-2] >= tb
+        if last_ts:
+            if pen_ts:
+                mask[k, tb:] = float("-inf")
+            else:
+                mask[k, :spec.eot] = float("-inf")
+        # Quirk kept (decoding.py:400-408): the reference collects the POSITIONS `i` of the timestamp tokens, not their
+        # values, so `mask[k, timestamp_begin : last_timestamp]` slices [50364 : small index) -- an empty range.  The
+        # "timestamps must not decrease" rule of the original Whisper is therefore inert here; restated literally.
+        ts = [i for i, v in enumerate(seq) if v > tb]
+        if ts:
+            last = ts[-1]
+            if not last or pen_ts:
+                last += 1
+            mask[k, tb:last] = float("-inf")
+    if len(tokens[0]) == sample_begin:
+        mask[:, :tb] = float("-inf")
+        if max_initial_timestamp_index is not None:
+            mask[:, tb + max_initial_timestamp_index + 1:] = float("-inf")
+    logprobs = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
+    ts_lp = torch.logsumexp(logprobs[:, tb:], dim=-1, keepdim=True)
+    max_text = logprobs[:, :tb].max(dim=-1, keepdim=True).values
+    mask[:, :tb] = torch.where(ts_lp > max_text, torch.full_like(mask[:, :tb], float("-inf")), mask[:, :tb])
+    return logits + mask
+
+
+def greedy_update(tokens, logits, sum_logprobs, eot):
+    """GreedyDecoder.update at temperature 0 (decoding.py:307-325)."""
+    nxt = logits.argmax(dim=-1)
+    logprobs = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
+    cur = logprobs[torch.arange(logits.shape[0]), nxt]
+    last = torch.tensor([t[-1] for t in tokens])
+    sum_logprobs = sum_logprobs + cur * (last != eot)
+    nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
+    tokens = [t + [int(n)] for t, n in zip(tokens, nxt)]
+    return tokens, bool((nxt == eot).all()), sum_logprobs
+
+
+def greedy_decode(P, xa, spec, sample_len=16, suppress=(), dims=WHISPER_SMALL, max_initial_timestamp_index=50):
+    """DecodingTask._main_loop with GreedyDecoder(temperature=0) (decoding.py:588-632) on encoder features xa [B,1500,d].
+    Returns (tokens incl. the sot sequence, sum_logprobs, no_speech_probs)."""
+    B = xa.shape[0]
+    init = list(spec.sot_sequence)
+    tokens = [list(init) for _ in range(B)]
+    sample_begin = len(init)
+    sum_lp = torch.zeros(B, dtype=xa.dtype)
+    cache = None
+    no_speech = None
+    for i in range(sample_len):
+        inp = torch.tensor(tokens if i == 0 else [[t[-1]] for t in tokens])
+        pre, cache = decoder_forward(P, inp, xa, cache, dims)
+        if i == 0:
+            no_speech = torch.softmax(pre[:, 0], dim=-1)[:, spec.no_speech]          # sot_index = 0
+        logits = apply_filters(pre[:, -1], tokens, spec, sample_begin, suppress, max_initial_timestamp_index)
+        tokens, completed, sum_lp = greedy_update(tokens, logits, sum_lp, spec.eot)
+        if completed or len(tokens[0]) > dims["n_text_ctx"]:
+            break
+    return tokens, sum_lp, no_speech
