@@ -91,6 +91,7 @@ int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int
                       const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
                       void* hi, void* lo, int32_t f16, void* stream);
 int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
+                      const void* w_lo, /* NULL, or the low plane bf16(w - w_hi) of an fp32 checkpoint's weights */
                       int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                       int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                       int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,

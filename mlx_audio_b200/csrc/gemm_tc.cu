@@ -84,7 +84,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __noinline__ float act_noinline(float v, int act, float p0) { return b2a_act(v, act, p0, 1.f, 1.f); }
 
 struct TcParams {
-  int B, L, Lout, Cout, cin_pad, taps, planes, BN, stages, f16;
+  int B, L, Lout, Cout, cin_pad, taps, planes, wplanes, BN, stages, f16;
   int Mrows, up_s, up_crop, C;     // transposed-conv mode: N = up_s * C, GEMM row m & column (r, co) -> output row m*up_s + r - up_crop
   int shift[32];
   const float* bias; int post_act; float post_p0;
@@ -98,12 +98,12 @@ struct TcParams {
 // smem: [stages] x { A_hi 16 KB | A_lo 16 KB (planes==2) | W BN*128 B }, then barriers
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
-               const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+               const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_bytes = TM * 128, w_bytes = p.BN * 128;
-  const int stage_bytes = a_bytes * p.planes + w_bytes;
+  const int stage_bytes = a_bytes * p.planes + w_bytes * p.wplanes;
   uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
@@ -119,6 +119,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
     for (int s = 0; s < p.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -146,6 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         tma_load_3d(st, &map_hi, full + s, kc * TK, l0 + p.shift[tap], b);
         if (p.planes == 2) tma_load_3d(st + a_bytes, &map_lo, full + s, kc * TK, l0 + p.shift[tap], b);
         tma_load_2d(st + (size_t)a_bytes * p.planes, &map_w, full + s, kc * TK, tap * p.Cout + n0);
+        if (p.wplanes == 2) tma_load_2d(st + (size_t)a_bytes * p.planes + w_bytes, &map_wlo, full + s, kc * TK, tap * p.Cout + n0);
       }
     }
   } else if (warp == 1) {
@@ -161,12 +163,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       if (dbg && lane == 0 && it == iters - 1) p.dbg[3] = clock64();
       if (lane == 0) {
         const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes);
-        for (int pl = 0; pl < p.planes; pl++) {
-          const uint64_t adesc = umma_desc_sw128(st + pl * a_bytes);
+        // products kept: a_hi*w_hi, a_lo*w_hi, and (fp32 checkpoints: weights split too) a_hi*w_lo; a_lo*w_lo ~ 2^-17*2^-9 is dropped
+        for (int wp = 0; wp < p.wplanes; wp++) {
+          const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes + wp * w_bytes);
+          const int npl = wp == 0 ? p.planes : 1;
+          for (int pl = 0; pl < npl; pl++) {
+            const uint64_t adesc = umma_desc_sw128(st + pl * a_bytes);
 #pragma unroll
-          for (int k = 0; k < TK / UMMA_K; k++)        // advance 32 B (16 bf16) inside the 128 B swizzle row
-            umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (it | pl | k) != 0);
+            for (int k = 0; k < TK / UMMA_K; k++)        // advance 32 B (16 bf16) inside the 128 B swizzle row
+              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (it | wp | pl | k) != 0);
+          }
         }
         umma_commit(empty + s);                        // frees the stage when these MMAs retire
         if (it == iters - 1) umma_commit(tmem_full);   // accumulator complete
@@ -201,29 +207,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const float cs = p.cscale ? __ldg(p.cscale + (int64_t)b * p.cscale_bs + co) : 1.f;
       float* ycol = p.y + (int64_t)b * p.y_bs + co;
       const float* rcol = p.res ? p.res + (int64_t)b * p.res_bs + co : nullptr;
-      // Rows go out in 4 groups of 8 (loads of a group issued before its stores).  Code size matters here: a full 32x
-      // unroll with a variable divide and the inlined activation switch produced ~200 KB of SASS and ~13k cycles per chunk.
+      // Code size matters here: a 32x unroll with a variable divide and the inlined activation switch produced ~200 KB of
+      // SASS and ~13k cycles per chunk; the body below is a shift, two predicated loads, an FMA chain and a store.
       const int row0 = mrow0 * mul + add;
       const int rsh = p.res_div == 2 ? 1 : 0;                      // res_div is 1 or 2 (nearest x2 shortcut, istftnet.py:838-850)
       const int mvalid = min(32, p.Mrows - mrow0);
-#pragma unroll 1
-      for (int g = 0; g < 32; g += 8) {
-        float rr[8], oo[8];
+      // all 32 (64 with accumulate) row loads are in flight before the first store: one L2 round trip per chunk, not four
+      float rr[32], oo[32];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int row = row0 + (g + i) * mul;
-          const bool ok = (g + i) < mvalid && row >= 0 && row < p.Lout;
-          rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)(row >> rsh) * p.res_ld) : 0.f;
-          oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
-        }
+      for (int i = 0; i < 32; i++) {
+        const int row = row0 + i * mul;
+        const bool ok = i < mvalid && row >= 0 && row < p.Lout;
+        rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)(row >> rsh) * p.res_ld) : 0.f;
+        oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
+      }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int row = row0 + (g + i) * mul;
-          if ((g + i) < mvalid && row >= 0 && row < p.Lout) {
-            float t = stage[(g + i) * 33 + lane] + bias;
-            if (p.post_act) t = act_noinline(t, p.post_act, p.post_p0);
-            ycol[(int64_t)row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
-          }
+      for (int i = 0; i < 32; i++) {
+        const int row = row0 + i * mul;
+        if (i < mvalid && row >= 0 && row < p.Lout) {
+          float t = stage[i * 33 + lane] + bias;
+          if (p.post_act) t = act_noinline(t, p.post_act, p.post_p0);
+          ycol[(int64_t)row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
         }
       }
       __syncwarp();
@@ -333,6 +337,7 @@ extern "C" int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int
 }
 
 extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B, int32_t L, int32_t cin_pad, const void* w_bf16,
+                                 const void* w_lo,
                                  int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                                  int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                                  int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
@@ -345,6 +350,7 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   if (get_encode() != 0) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled entry point not found"); return B2A_E_CUDA; }
   TcParams p;
   p.f16 = f16 ? 1 : 0;
+  p.wplanes = w_lo ? 2 : 1;
   p.up_s = up_stride; p.up_crop = up_crop; p.C = up_stride ? Cout / up_stride : Cout;
   p.Mrows = up_stride ? L + taps - 1 : Lout;
   p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
@@ -354,11 +360,11 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   p.res = res; p.res_bs = res_bs; p.res_ld = res_ld; p.res_div = res_div; p.out_scale = out_scale; p.accumulate = accumulate;
   p.y = y; p.y_bs = y_bs; p.y_ld = y_ld;
   p.dbg = g_dbg;
-  const int stage_bytes = TM * 128 * p.planes + p.BN * 128;
+  const int stage_bytes = TM * 128 * p.planes + p.BN * 128 * p.wplanes;
   p.stages = (196 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
   size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 32 + 4 * 32 * 33 * sizeof(float);
 
-  CUtensorMap mh, ml, mw;
+  CUtensorMap mh, ml, mw, mwl;
   uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
   uint64_t astr[2] = {(uint64_t)cin_pad * 2, (uint64_t)cin_pad * 2 * (uint64_t)L};
   uint32_t abox[3] = {TK, TM, 1};
@@ -368,12 +374,13 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   uint64_t wstr[1] = {(uint64_t)cin_pad * 2};
   uint32_t wbox[2] = {TK, (uint32_t)p.BN};
   if (!e) e = make_map(&mw, w_bf16, 2, wdims, wstr, wbox, p.f16);
+  if (!e) e = make_map(&mwl, w_lo ? w_lo : w_bf16, 2, wdims, wstr, wbox, p.f16);
   if (e) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled failed (%d)", e); return B2A_E_CUDA; }
 
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
   dim3 grid(cdiv(p.Mrows, TM), Cout / p.BN, B);
-  conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mh, ml, mw, p);
+  conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mh, ml, mw, mwl, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

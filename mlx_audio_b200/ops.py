@@ -115,6 +115,7 @@ class ConvW:
     w_tc: Optional[torch.Tensor] = None
     cin_pad: int = 0
     f16: bool = False          # w_tc is IEEE fp16 (fp16 checkpoints) instead of bf16
+    w_tc_lo: Optional[torch.Tensor] = None   # fp32 checkpoints: w = w_tc + w_tc_lo (both bf16), kept to ~2^-17
 
 
 # Tensor-core dispatch policy: "off" = CUDA-core fp32 everywhere; "x2" = tcgen05 with (hi, lo) bf16 activation planes
@@ -131,15 +132,19 @@ def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: in
     return stride == 1 and cw.cin * cw.K >= TC_MIN_K
 
 
-def _tc_transposed_weights(cw: "ConvW", stride: int) -> torch.Tensor:
-    """[J, stride*Cout, cin_pad] with W[j, r*Cout + co, ci] = w[k = r + j*stride][ci][co] (cached per stride)."""
+def _tc_transposed_weights(cw: "ConvW", stride: int):
+    """([J, stride*Cout, cin_pad] hi, lo-or-None) with W[j, r*Cout + co, ci] = w[k = r + j*stride][ci][co] (cached per stride)."""
     cache = cw.__dict__.setdefault("_w_tc_tr", {})
     if stride not in cache:
         J = cw.K // stride
         w = cw.w.reshape(J, stride, cw.cin, cw.cout).permute(0, 1, 3, 2).reshape(J, stride * cw.cout, cw.cin)   # k = j*stride + r
         wt = torch.zeros(J, stride * cw.cout, cw.cin_pad, device=cw.w.device, dtype=cw.w_tc.dtype)
         wt[:, :, :cw.cin] = w.to(cw.w_tc.dtype)
-        cache[stride] = wt.contiguous()
+        wl = None
+        if cw.w_tc_lo is not None:
+            wl = torch.zeros_like(wt)
+            wl[:, :, :cw.cin] = (w - wt[:, :, :cw.cin].float()).to(wt.dtype)
+        cache[stride] = (wt.contiguous(), None if wl is None else wl.contiguous())
     return cache[stride]
 
 
@@ -165,6 +170,14 @@ def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
                 wt[:, :, :cin] = wb.permute(1, 0, 2)
                 cwo.w_tc, cwo.cin_pad, cwo.f16 = wt.to(device).contiguous(), cpad, dt == torch.float16
                 break
+        else:                                                          # fp32 checkpoint (SNAC): split the weights as well
+            cpad = -(-cin // 64) * 64
+            w32 = w_mlx.float().permute(1, 0, 2)
+            hi = w32.to(torch.bfloat16)
+            lo = (w32 - hi.float()).to(torch.bfloat16)
+            wt, wl = torch.zeros(k, cout, cpad, dtype=torch.bfloat16), torch.zeros(k, cout, cpad, dtype=torch.bfloat16)
+            wt[:, :, :cin], wl[:, :, :cin] = hi, lo
+            cwo.w_tc, cwo.w_tc_lo, cwo.cin_pad = wt.to(device).contiguous(), wl.to(device).contiguous(), cpad
     return cwo
 
 
@@ -243,17 +256,18 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
         if out.shape != (B, lout, cw.cout):
             raise ValueError(f"conv1d: out has shape {tuple(out.shape)}, expected {(B, lout, cw.cout)}")
     if up_stride:
-        taps, n_total, w_tc = cw.K // up_stride, up_stride * cw.cout, _tc_transposed_weights(cw, up_stride)
+        taps, n_total = cw.K // up_stride, up_stride * cw.cout
+        w_tc, w_lo = _tc_transposed_weights(cw, up_stride)
         shifts = (C.c_int32 * taps)(*[-j for j in range(taps)])
     else:
-        taps, n_total, w_tc = cw.K, cw.cout, cw.w_tc
+        taps, n_total, w_tc, w_lo = cw.K, cw.cout, cw.w_tc, cw.w_tc_lo
         shifts = (C.c_int32 * taps)(*[k * dilation - pad_left for k in range(taps)])
     cs, cs_bs = (None, 0) if cscale is None else (cscale.data_ptr(), cscale.stride(0) if cscale.dim() == 2 else 0)
     r, r_bs, r_ld = (None, 0, 0)
     if res is not None:
         _chk3(res, "conv1d res")
         r, r_bs, r_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
-    _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, w_tc.data_ptr(), taps, shifts, n_total, lout,
+    _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, w_tc.data_ptr(), _p(w_lo), taps, shifts, n_total, lout,
           _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
           out.stride(1), up_stride, pad_left if up_stride else 0, _stream())
     return out
