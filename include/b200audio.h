@@ -168,6 +168,12 @@ int32_t b2a_whisper_logmel(const float* x, int64_t x_bs, int32_t B, int64_t n, i
 int32_t b2a_istft(const float* re, const float* im, int32_t B, int32_t n_fft, int32_t T, int32_t hop, const float* window,
                   int32_t norm_sq, int32_t clamp_mode, int64_t trim, int64_t out_len, float* out, float* ws, void* stream);
 
+/* Polyphase resampling, the arithmetic of scipy.signal.resample_poly(x, up, down, window=h, padtype="edge") that the reference
+ * calls on the host (resample.py:29-47): x [B, n_in] float32, h float64 FIR ALREADY multiplied by `up`, n_pre_pad / n_pre_remove
+ * as SciPy derives them (host side: mlx_audio_b200/resample.py), out [B, n_out] float32, float64 accumulation. */
+int32_t b2a_resample_poly(const float* x, int64_t x_bs, int32_t B, int64_t n_in, const double* h, int32_t n_h, int32_t up,
+                          int32_t down, int64_t n_pre_pad, int64_t n_pre_remove, float* out, int64_t n_out, void* stream);
+
 /* ---- Kokoro hn-NSF source + iSTFT head (istftnet.py:548-709, 453-545, 826-835) ------------
  * f0 [B, n_frames] (the F0 curve, one value per 300 samples); noise [B, n_frames*300, 9] injected N(0,1) (or NULL);
  * lin_w [9], lin_b [1] = m_source.l_linear.  har [B, n_frames*60+1, 22] = (|STFT| , angle) of the tanh-merged source,
@@ -194,6 +200,14 @@ int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_bs, const in
                                 const float* blank_mask, int32_t eot, int32_t no_timestamps, int32_t timestamp_begin,
                                 int32_t max_initial_ts, int32_t without_timestamps, int64_t* next_out,
                                 float* sum_logprobs, int32_t* not_done, void* stream);
+
+/* Fused LM sampler (tts/models/qwen3_tts/qwen3_tts.py:805-860 over lm/sample_utils.py:131-239,279): additive suppress mask ->
+ * sign-aware repetition penalty on the `seen` set -> temperature (<= 0: argmax) -> top-k -> top-p -> min-p -> categorical draw
+ * by inverse CDF in index order with the caller's uniform u[b] (MLX's PRNG is not reproducible; tests inject u).  V <= 4096.
+ * filtered_out (optional) receives the filtered, temperature-scaled logits the draw is made from. */
+int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int32_t V, const float* suppress_mask,
+                         const uint8_t* seen, int64_t seen_bs, float repetition_penalty, float temperature, int32_t top_k,
+                         float top_p, float min_p, const float* u, int64_t* out, float* filtered_out, void* stream);
 
 /* ---- codec (RVQ decode) ---------------------------------------------------------------------
  * out[b,t,:] (+)= sum_q codebooks[q][codes[b,q,t]][:]   (mimi/modules/quantization.py:47-49,103-108;

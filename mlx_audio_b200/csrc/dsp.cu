@@ -401,3 +401,37 @@ extern "C" int32_t b2a_randn(float* out, int64_t n, uint64_t seed, uint64_t offs
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
+
+// ---------------------------------------------------------------- polyphase resampler (resample.py:10-47 -> scipy.signal.resample_poly)
+// out[b, n] = sum_t h[t] * xu[c(n) - t],  c(n) = (n + n_pre_remove)*down - n_pre_pad,  xu[i] = x[clamp(i/up)] when up | i (edge
+// padding of the input, padtype="edge"), else 0 -- i.e. only taps t == c (mod up) contribute.  h is the float64 Kaiser-sinc FIR
+// already scaled by `up`; accumulation is float64 like SciPy's (float32 x, float64 h), result cast to float32.
+namespace {
+__global__ void resample_poly_kernel(const float* __restrict__ x, int64_t x_bs, int64_t n_in, const double* __restrict__ h, int n_h,
+                                     int up, int down, int64_t n_pre_pad, int64_t n_pre_remove, float* __restrict__ out,
+                                     int64_t n_out, int B) {
+  const int64_t total = n_out * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / n_out); const int64_t n = idx % n_out;
+    const float* xb = x + (int64_t)b * x_bs;
+    const int64_t c = (n + n_pre_remove) * down - n_pre_pad;
+    int64_t t0 = c % up; if (t0 < 0) t0 += up;                       // smallest t >= 0 with t == c (mod up)
+    double acc = 0.0;
+    for (int64_t t = t0; t < n_h; t += up) {
+      int64_t i = (c - t) / up;                                      // exact: up | (c - t)
+      i = i < 0 ? 0 : (i >= n_in ? n_in - 1 : i);
+      acc += h[t] * (double)__ldg(xb + i);
+    }
+    out[idx] = (float)acc;
+  }
+}
+}  // namespace
+
+extern "C" int32_t b2a_resample_poly(const float* x, int64_t x_bs, int32_t B, int64_t n_in, const double* h, int32_t n_h, int32_t up,
+                                     int32_t down, int64_t n_pre_pad, int64_t n_pre_remove, float* out, int64_t n_out, void* stream) {
+  B2A_CHECK_ARG(x && h && out && B > 0 && n_in > 0 && n_h > 0 && up > 0 && down > 0 && n_out > 0, "bad pointers/shape");
+  resample_poly_kernel<<<grid_for(n_out * B, 256), 256, 0, (cudaStream_t)stream>>>(x, x_bs, n_in, h, n_h, up, down, n_pre_pad,
+                                                                                   n_pre_remove, out, n_out, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

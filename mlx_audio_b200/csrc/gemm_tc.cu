@@ -195,10 +195,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+      if (dbg && warp == 2 && lane == 0 && c0 == 0) p.dbg[8] = clock64();
       if (mrow0 >= p.Mrows) continue;
 #pragma unroll
       for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
       __syncwarp();
+      if (dbg && warp == 2 && lane == 0 && c0 == 0) p.dbg[9] = clock64();
       const int n = n0 + c0 + lane;                               // GEMM column of this lane for every row below
       const int ph = p.up_s ? n / p.C : 0;                         // up-sampling phase (uniform over the 32-column chunk)
       const int co = n - ph * p.C;                                 // output channel
@@ -221,6 +223,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)(row >> rsh) * p.res_ld) : 0.f;
         oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
       }
+      if (dbg && warp == 2 && lane == 0 && c0 == 0) p.dbg[10] = clock64();
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         const int row = row0 + i * mul;
@@ -231,6 +234,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         }
       }
       __syncwarp();
+      if (dbg && warp == 2 && lane == 0 && c0 == 0) p.dbg[11] = clock64();
     }
   }
   if (dbg && warp == 2 && lane == 0) p.dbg[5] = clock64();

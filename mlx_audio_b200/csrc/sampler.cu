@@ -132,3 +132,145 @@ extern "C" int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_b
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Fused LM sampler (include/b200audio.h: b2a_sample_token): suppress -> repetition penalty -> temperature -> top-k -> top-p
+// -> min-p -> categorical draw, the chain of tts/models/qwen3_tts/qwen3_tts.py:805-860 over lm/sample_utils.py:131-239,279.
+// One CTA per row; the row (V <= 4096) is bitonic-sorted once in shared memory (value desc, index asc) and every filter is a
+// rank / prefix test on that order.  The categorical draw is an inverse-CDF lookup in INDEX order driven by a caller-supplied
+// uniform (MLX's PRNG cannot be reproduced, so parity tests inject u; production draws it with b2a_randn's Philox stream).
+namespace {
+
+constexpr int SV = 4096;
+
+struct SampleParams {
+  const float* logits; int64_t logits_bs; int V;
+  const float* suppress;                  // [V] additive 0/-inf or NULL
+  const uint8_t* seen; int64_t seen_bs;   // [B,V] 1 = token already generated (repetition penalty set) or NULL
+  float rep_penalty, temperature; int top_k; float top_p, min_p;
+  const float* u;                         // [B] uniforms in [0,1)
+  int64_t* out;                           // [B]
+  float* filtered;                        // [B,V] optional: the filtered logits the draw is made from (tests)
+};
+
+__global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
+  __shared__ float sv[SV];
+  __shared__ unsigned short si[SV];               // indices < 4096 fit 16 bits (keeps static shared memory under 48 KB)
+  __shared__ float red[32];
+  __shared__ float s_scan[SV];
+  const int b = blockIdx.x, tid = threadIdx.x, V = p.V;
+  const float NEG = -INFINITY;
+  const float* lg = p.logits + (int64_t)b * p.logits_bs;
+  auto base = [&](int v) -> float {
+    float x = lg[v];
+    if (p.suppress) x += p.suppress[v];
+    if (p.seen && p.seen[(int64_t)b * p.seen_bs + v] && p.rep_penalty != 1.f) x = x < 0.f ? x * p.rep_penalty : x / p.rep_penalty;
+    return x;
+  };
+  if (p.temperature <= 0.f) {                                       // greedy (qwen3_tts.py:845-846): argmax, lowest index on ties
+    float best = NEG; int bi = 0x7fffffff;
+    for (int v = tid; v < V; v += blockDim.x) { float x = base(v); if (x > best) { best = x; bi = v; } }
+    int* gi = reinterpret_cast<int*>(s_scan);
+    sv[tid] = best; gi[tid] = bi;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+      if (tid < s) { if (sv[tid + s] > sv[tid] || (sv[tid + s] == sv[tid] && gi[tid + s] < gi[tid])) { sv[tid] = sv[tid + s]; gi[tid] = gi[tid + s]; } }
+      __syncthreads();
+    }
+    if (tid == 0) p.out[b] = gi[0] == 0x7fffffff ? 0 : gi[0];
+    return;
+  }
+  const float inv_t = 1.f / p.temperature;
+  for (int v = tid; v < SV; v += blockDim.x) { sv[v] = v < V ? base(v) * inv_t : NEG; si[v] = v; }
+  __syncthreads();
+  // bitonic sort: descending value, ascending index among equals
+  for (int k = 2; k <= SV; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < SV; i += blockDim.x) {
+        int l = i ^ j;
+        if (l > i) {
+          bool desc = (i & k) == 0;
+          float a = sv[i], c = sv[l]; unsigned short ai = si[i], ci = si[l];
+          bool a_first = a > c || (a == c && ai < ci);              // a should come before c in the final order
+          if (a_first != desc) { sv[i] = c; sv[l] = a; si[i] = ci; si[l] = ai; }
+        }
+      }
+      __syncthreads();
+    }
+  // top-k: ranks >= k are removed
+  const bool use_k = p.top_k > 0 && p.top_k < V;
+  const int kcut = use_k ? p.top_k : V;
+  const float vmax = sv[0];
+  // softmax over the survivors (log_softmax of the top-k-masked logits)
+  float se = 0.f;
+  for (int r = tid; r < kcut; r += blockDim.x) se += sv[r] > NEG ? expf(sv[r] - vmax) : 0.f;
+  se = warp_sum(se);
+  if ((tid & 31) == 0) red[tid >> 5] = se;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += red[i];
+  __syncthreads();
+  const float lse = vmax + logf(tot);
+  // top-p (ascending inclusive cumulative probability > 1 - top_p survives) and min-p on the sorted order
+  const bool use_p = p.top_p > 0.f && p.top_p < 1.f;
+  // inclusive prefix over DESCENDING ranks; ascending-inclusive cum of rank r = 1 - (prefix_desc_incl(r) - prob_r)
+  for (int r = tid; r < SV; r += blockDim.x) s_scan[r] = (r < kcut && sv[r] > NEG) ? expf(sv[r] - lse) : 0.f;
+  __syncthreads();
+  for (int off = 1; off < SV; off <<= 1) {                          // Hillis-Steele scan (4096 elements, 1024 threads)
+    float t[4];
+    for (int q = 0; q < 4; q++) { int r = tid + q * blockDim.x; t[q] = (r >= off && r < SV) ? s_scan[r - off] : 0.f; }
+    __syncthreads();
+    for (int q = 0; q < 4; q++) { int r = tid + q * blockDim.x; if (r < SV) s_scan[r] += t[q]; }
+    __syncthreads();
+  }
+  const float logminp = p.min_p > 0.f ? logf(p.min_p) : NEG;
+  for (int r = tid; r < SV; r += blockDim.x) {
+    bool keep = r < kcut && sv[r] > NEG;
+    if (keep && use_p) {
+      float pr = expf(sv[r] - lse);
+      float cum_asc = 1.f - (s_scan[r] - pr);                       // sum of this and all smaller probabilities
+      keep = cum_asc > 1.f - p.top_p;
+    }
+    if (keep && p.min_p > 0.f) keep = !((sv[r] - lse) < (vmax - lse) + logminp);     // remove logprob < max logprob + log(min_p)
+    if (!keep) sv[r] = NEG;
+  }
+  __syncthreads();
+  // scatter the filtered logits back to index order (s_scan reused as [V] buffer)
+  for (int r = tid; r < SV; r += blockDim.x) if (si[r] < V) s_scan[si[r]] = sv[r];
+  __syncthreads();
+  if (p.filtered) for (int v = tid; v < V; v += blockDim.x) p.filtered[(int64_t)b * V + v] = s_scan[v];
+  // categorical draw: inverse CDF in index order with the supplied uniform
+  float m2 = NEG;
+  for (int v = tid; v < V; v += blockDim.x) m2 = fmaxf(m2, s_scan[v]);
+  m2 = warp_max(m2);
+  if ((tid & 31) == 0) red[tid >> 5] = m2;
+  __syncthreads();
+  float gm = red[0];
+  for (int i = 1; i < (int)(blockDim.x >> 5); i++) gm = fmaxf(gm, red[i]);
+  __syncthreads();
+  if (tid == 0) {
+    double z = 0.0;
+    for (int v = 0; v < V; v++) if (s_scan[v] > NEG) z += exp((double)(s_scan[v] - gm));
+    double target = (double)p.u[b] * z, run = 0.0;
+    int pick = -1, lastv = 0;
+    for (int v = 0; v < V; v++) {
+      if (s_scan[v] > NEG) { run += exp((double)(s_scan[v] - gm)); lastv = v; if (run > target) { pick = v; break; } }
+    }
+    p.out[b] = pick >= 0 ? pick : lastv;
+  }
+}
+
+}  // namespace
+
+extern "C" int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int32_t V, const float* suppress_mask,
+                                    const uint8_t* seen, int64_t seen_bs, float repetition_penalty, float temperature, int32_t top_k,
+                                    float top_p, float min_p, const float* u, int64_t* out, float* filtered_out, void* stream) {
+  B2A_CHECK_ARG(logits && out && B > 0 && V > 0, "bad pointers/shape");
+  B2A_CHECK_ARG(temperature <= 0.f || u != nullptr, "a uniform draw per row is required when temperature > 0");
+  if (V > SV) { b2a_set_error("b2a_sample_token: vocab %d > %d not supported", V, SV); return B2A_E_UNSUPPORTED; }
+  B2A_CHECK_ARG(min_p >= 0.f && min_p <= 1.f, "`min_p` has to be a float in the [0, 1] interval");
+  SampleParams p{logits, logits_bs, V, suppress_mask, seen, seen_bs, repetition_penalty, temperature, top_k, top_p, min_p, u, out, filtered_out};
+  sample_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(p);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

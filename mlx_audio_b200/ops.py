@@ -450,6 +450,15 @@ def istft(re: torch.Tensor, im: torch.Tensor, n_fft: int, hop: int, window: torc
     return out
 
 
+def resample_poly(x: torch.Tensor, h: torch.Tensor, up: int, down: int, n_pre_pad: int, n_pre_remove: int, n_out: int) -> torch.Tensor:
+    """x [B,n] float32, h float64 FIR (already * up) -> [B, n_out] (scipy.signal.resample_poly, padtype='edge')."""
+    assert x.dim() == 2 and x.stride(1) == 1 and h.dtype == torch.float64 and h.is_contiguous()
+    out = torch.empty(x.shape[0], n_out, device=x.device, dtype=torch.float32)
+    _call("resample", _lib.lib().b2a_resample_poly, 1, x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], h.data_ptr(), h.shape[0], up, down,
+          n_pre_pad, n_pre_remove, out.data_ptr(), n_out, _stream())
+    return out
+
+
 def kokoro_source(f0: torch.Tensor, noise: Optional[torch.Tensor], lin_w: torch.Tensor, lin_b: torch.Tensor) -> torch.Tensor:
     """F0 curve [B, nF] -> har [B, nF*60+1, 22] (magnitude | phase of the hn-NSF source STFT)."""
     B, nF = f0.shape
@@ -481,6 +490,18 @@ def randn_(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
     assert out.is_contiguous() and out.dtype == torch.float32
     _call("other", _lib.lib().b2a_randn, 1, out.data_ptr(), out.numel(), seed, offset, _stream())
     return out
+
+
+def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, u=None,
+                 suppress_mask=None, seen=None, repetition_penalty: float = 1.0, return_filtered: bool = False):
+    """Fused sampler on logits [B,V] (V <= 4096) -> int64 tokens [B] (and the filtered logits when asked)."""
+    B, V = logits.shape
+    assert logits.stride(1) == 1 and (seen is None or (seen.dtype == torch.uint8 and seen.stride(1) == 1))
+    out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    filt = torch.empty(B, V, device=logits.device, dtype=torch.float32) if return_filtered else None
+    _call("sampler", _lib.lib().b2a_sample_token, 1, logits.data_ptr(), logits.stride(0), B, V, _p(suppress_mask), _p(seen),
+          0 if seen is None else seen.stride(0), repetition_penalty, temperature, top_k, top_p, min_p, _p(u), out.data_ptr(), _p(filt), _stream())
+    return (out, filt) if return_filtered else out
 
 
 def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch.Tensor] = None, check=True) -> torch.Tensor:

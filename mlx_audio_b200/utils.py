@@ -87,9 +87,7 @@ def load_model(model_path, lazy: bool = False, strict: bool = False, **kwargs):
 
 
 def resample_audio(audio, orig_sr: int, target_sr: int, axis: int = -1):
-    """utils.py:541-578 (host-side in the reference: SciPy polyphase, resample.py:29-47).  A GPU polyphase resampler is
-    row next-2 of SURVEY.md section 8f; until then this is the same SciPy call the reference makes."""
+    """utils.py:541-578: same type out as in -- NumPy through the reference's SciPy call, torch CUDA tensors through our
+    polyphase kernel (same filter, same indexing)."""
     from .resample import resample_audio_array
-    is_t = isinstance(audio, torch.Tensor)
-    out = resample_audio_array(audio.detach().cpu().numpy() if is_t else np.asarray(audio), orig_sr, target_sr, axis=axis)
-    return torch.as_tensor(out, device=audio.device) if is_t else out
+    return resample_audio_array(audio, orig_sr, target_sr, axis=axis)

@@ -1,0 +1,44 @@
+"""GPU polyphase resampler vs the reference's arithmetic (scipy.signal.resample_poly with the reference's Kaiser filter,
+resample.py:10-47) and the reference's own pins (tests/test_dsp.py:299-378): alias rejection, pass-band gain, and
+chunk-invariance (every output sample is an independent fixed-order sum)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import dsp as OD
+
+
+@pytest.mark.parametrize("orig,target,n", [(24000, 16000, 48137), (44100, 16000, 88337), (48000, 16000, 96137), (16000, 24000, 20011)])
+def test_resample_matches_scipy(orig, target, n):
+    from mlx_audio_b200.utils import resample_audio
+    rng = np.random.default_rng(orig)
+    x = rng.normal(0.0, 0.1, size=(2, n)).astype(np.float32)
+    ref = OD.resample(x, orig, target, axis=-1)
+    y = resample_audio(torch.as_tensor(x).cuda(), orig, target)
+    assert isinstance(y, torch.Tensor) and y.is_cuda and y.shape == ref.shape
+    assert float(np.abs(y.cpu().numpy() - ref).max()) <= 1.5e-7          # float32 rounding of a float64 sum
+    # time-first layout through `axis`
+    y2 = resample_audio(torch.as_tensor(x.T.copy()).cuda(), orig, target, axis=0)
+    assert torch.equal(y2.T.contiguous(), y)
+
+
+def test_resample_reference_pins_and_chunk_invariance():
+    from mlx_audio_b200.utils import resample_audio
+    orig, target = 24000, 16000
+    t = np.arange(2 * orig) / orig
+    out = resample_audio(torch.as_tensor(np.sin(2 * np.pi * 8200.0 * t).astype(np.float32)).cuda(), orig, target).cpu().numpy()
+    assert float(np.sqrt(np.mean(out[400:-400] ** 2))) < 0.01
+    for f in (1000.0, 7000.0):
+        out = resample_audio(torch.as_tensor(np.sin(2 * np.pi * f * t).astype(np.float32)).cuda(), orig, target).cpu().numpy()
+        assert 0.70 < float(np.sqrt(np.mean(out[400:-400] ** 2))) < 0.72
+    x = torch.randn(48000, generator=torch.Generator().manual_seed(1)).cuda()
+    whole = resample_audio(x, orig, target)
+    # a chunk with enough halo reproduces the interior of the whole-buffer result bit-for-bit (tests/test_dsp.py:350-378 property)
+    lo, hi, halo = 12000, 30000, 600
+    part = resample_audio(x[lo - halo:hi + halo], orig, target)
+    o_lo, o_hi = lo * 2 // 3, hi * 2 // 3
+    off = (lo - halo) * 2 // 3
+    assert torch.equal(part[o_lo - off:o_hi - off], whole[o_lo:o_hi])
+    assert resample_audio(x, 16000, 16000) is x

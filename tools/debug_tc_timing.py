@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mlx_audio_b200 import ops, _lib
 dev = torch.device("cuda:0")
-dbg = torch.zeros(8, dtype=torch.int64, device=dev)
+dbg = torch.zeros(16, dtype=torch.int64, device=dev)
 ops.TC_MODE[0] = sys.argv[1] if len(sys.argv) > 1 else "x2"
 for (L, Cin, Cout, K) in [(130, 768, 512, 1), (130, 768, 2304, 1), (390, 1090, 1024, 3), (7800, 256, 256, 7), (46801, 128, 128, 11), (46801, 128, 128, 3)]:
     x = torch.randn(1, L, Cin, device=dev)
@@ -25,5 +25,6 @@ for (L, Cin, Cout, K) in [(130, 768, 512, 1), (130, 768, 2304, 1), (390, 1090, 1
     _lib.lib().b2a_conv1d_tc_debug(None)
     t = dbg.cpu().tolist()
     d = [(t[i] - t[0]) for i in range(7)]
+    e = [t[i] - t[4] for i in (8, 9, 10, 11)]
     iters = K * cw.cin_pad // 64
-    print(f"L={L} Cin={Cin} Cout={Cout} K={K} iters={iters} prep+conv event {e0.elapsed_time(e1)*1e3:.1f} us | cycles since entry: setup {d[1]} first_full {d[2]} last_full {d[3]} acc_ready {d[4]} epi_done {d[5]} exit {d[6]}  (1.9 cycles/ns)")
+    print(f"L={L} Cin={Cin} Cout={Cout} K={K} iters={iters} prep+conv event {e0.elapsed_time(e1)*1e3:.1f} us | cycles since entry: setup {d[1]} first_full {d[2]} last_full {d[3]} acc_ready {d[4]} epi_done {d[5]} | chunk0 since acc_ready: ldtm {e[0]} staged {e[1]} loads_issued {e[2]} stored {e[3]}")
