@@ -209,28 +209,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const float cs = p.cscale ? __ldg(p.cscale + (int64_t)b * p.cscale_bs + co) : 1.f;
       float* ycol = p.y + (int64_t)b * p.y_bs + co;
       const float* rcol = p.res ? p.res + (int64_t)b * p.res_bs + co : nullptr;
-      // Code size matters here: a 32x unroll with a variable divide and the inlined activation switch produced ~200 KB of
-      // SASS and ~13k cycles per chunk; the body below is a shift, two predicated loads, an FMA chain and a store.
+      // The four epilogue warps are the only warps on their schedulers, so this code is issue-latency bound: per-row work is
+      // kept to one load / one FMA chain / one store off incrementally advanced pointers.  Valid rows form a contiguous range
+      // [i_lo, i_hi) of the 32 (row = row0 + i*mul is monotonic); full tiles take the predicate-free path.
       const int row0 = mrow0 * mul + add;
-      const int rsh = p.res_div == 2 ? 1 : 0;                      // res_div is 1 or 2 (nearest x2 shortcut, istftnet.py:838-850)
       const int mvalid = min(32, p.Mrows - mrow0);
-      // all 32 (64 with accumulate) row loads are in flight before the first store: one L2 round trip per chunk, not four
-      float rr[32], oo[32];
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const int row = row0 + i * mul;
-        const bool ok = i < mvalid && row >= 0 && row < p.Lout;
-        rr[i] = (rcol && ok) ? __ldg(rcol + (int64_t)(row >> rsh) * p.res_ld) : 0.f;
-        oo[i] = (p.accumulate && ok) ? ycol[(int64_t)row * p.y_ld] : 0.f;
-      }
+      int i_lo = 0, i_hi = mvalid;
+      if (row0 < 0) i_lo = (-row0 + mul - 1) / mul;
+      if (row0 + (mvalid - 1) * mul >= p.Lout) i_hi = p.Lout > row0 ? (p.Lout - row0 + mul - 1) / mul : 0;
+      const int64_t ystride = (int64_t)mul * p.y_ld;
+      float* yp = ycol + (int64_t)row0 * p.y_ld;
+      const bool half_res = p.res_div == 2;                        // nearest x2 shortcut (istftnet.py:838-850); only with mul == 1
+      const int odd = row0 & 1;
+      const float* rp = rcol ? rcol + (int64_t)(half_res ? (row0 >> 1) : row0) * p.res_ld : nullptr;
+      const int64_t rstride = (int64_t)mul * p.res_ld;
+      const float osc = p.out_scale;
       if (dbg && warp == 2 && lane == 0 && c0 == 0) p.dbg[10] = clock64();
+      if (i_lo == 0 && i_hi == 32) {
+        float rr[32];
+        if (rp) {
+          if (!half_res) {
 #pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const int row = row0 + i * mul;
-        if (i < mvalid && row >= 0 && row < p.Lout) {
+            for (int i = 0; i < 32; i++) rr[i] = __ldg(rp + i * rstride);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) rr[i] = __ldg(rp + (int64_t)((i + odd) >> 1) * p.res_ld);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) rr[i] = 0.f;
+        }
+        if (p.accumulate) {
+          float oo[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) oo[i] = yp[i * ystride];
+#pragma unroll
+          for (int i = 0; i < 32; i++) rr[i] = rr[i] * osc + oo[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) rr[i] *= osc;
+        }
+        const float cso = cs * osc;
+        if (p.post_act) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) yp[i * ystride] = act_noinline(stage[i * 33 + lane] + bias, p.post_act, p.post_p0) * cso + rr[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) yp[i * ystride] = (stage[i * 33 + lane] + bias) * cso + rr[i];
+        }
+      } else {
+        for (int i = i_lo; i < i_hi; i++) {                        // ragged edge tiles: plain loop
+          const int row = row0 + i * mul;
           float t = stage[i * 33 + lane] + bias;
           if (p.post_act) t = act_noinline(t, p.post_act, p.post_p0);
-          ycol[(int64_t)row * p.y_ld] = (t * cs + rr[i]) * p.out_scale + oo[i];
+          float r = rcol ? __ldg(rcol + (int64_t)(half_res ? (row >> 1) : row) * p.res_ld) : 0.f;
+          float o = p.accumulate ? ycol[(int64_t)row * p.y_ld] : 0.f;
+          ycol[(int64_t)row * p.y_ld] = (t * cs + r) * osc + o;
         }
       }
       __syncwarp();
