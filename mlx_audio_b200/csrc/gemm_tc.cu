@@ -96,7 +96,7 @@ struct TcParams {
 };
 
 // smem: [stages] x { A_hi 16 KB | A_lo 16 KB (planes==2) | W BN*128 B }, then barriers
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -186,7 +186,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     // chunk, 5x the main loop).  Each warp therefore transposes its 32x32 chunk through a padded smem tile and then
     // reads/writes whole 128-byte row segments: residual and previous-output loads for all 32 rows are issued first.
     const int quarter = warp & 3;
-    float* stage = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * (32 * 33);
+    // the transpose staging tile reuses pipeline stage 0: every TMA write and MMA read of it has retired once tmem_full fires
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * 33);
+    // while the main loop runs, pull this warp's residual / previous-output rows towards L2 (lane = row, one request per 128 B)
+    if (!p.up_s) {
+      const int prow = l0 + quarter * 32 + lane;
+      if (prow < p.Lout) {
+        if (p.res) {
+          const float* q = p.res + (int64_t)b * p.res_bs + (int64_t)(p.res_div == 2 ? (prow >> 1) : prow) * p.res_ld + n0;
+          for (int c = 0; c < p.BN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+        }
+        if (p.accumulate) {
+          const float* q = p.y + (int64_t)b * p.y_bs + (int64_t)prow * p.y_ld + n0;
+          for (int c = 0; c < p.BN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+        }
+      }
+    }
     mbar_wait(tmem_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (dbg && warp == 2 && lane == 0) p.dbg[4] = clock64();
@@ -392,15 +407,22 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   p.up_s = up_stride; p.up_crop = up_crop; p.C = up_stride ? Cout / up_stride : Cout;
   p.Mrows = up_stride ? L + taps - 1 : Lout;
   p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
-  p.BN = (Cout % 256 == 0) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32));
+  // N tile: 256 halves the A re-reads per output but only pays once the grid fills the machine; otherwise 128 (more CTAs)
+  const int mtiles = cdiv(up_stride ? L + taps - 1 : Lout, TM) * B;
+  p.BN = (Cout % 256 == 0 && mtiles * (Cout / 256) >= 148) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32));
   for (int i = 0; i < taps; i++) p.shift[i] = shifts_host[i];
   p.bias = bias; p.post_act = post_act; p.post_p0 = post_p0; p.cscale = cscale; p.cscale_bs = cscale_bs;
   p.res = res; p.res_bs = res_bs; p.res_ld = res_ld; p.res_div = res_div; p.out_scale = out_scale; p.accumulate = accumulate;
   p.y = y; p.y_bs = y_bs; p.y_ld = y_ld;
   p.dbg = g_dbg;
   const int stage_bytes = TM * 128 * p.planes + p.BN * 128 * p.wplanes;
-  p.stages = (196 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 2) p.stages = 2;
-  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 32 + 4 * 32 * 33 * sizeof(float);
+  // Two CTAs per SM whenever two 2-stage pipelines fit (<= ~113 KB each): one CTA's epilogue then overlaps the other's main
+  // loop.  Otherwise one CTA per SM with as many stages as fit.  (Stage 0 doubles as the 17 KB epilogue staging tile.)
+  const int per_cta_2 = 2 * stage_bytes + 1024 + 128;
+  if (2 * per_cta_2 <= 226 * 1024 && 2 * stage_bytes >= 4 * 32 * 33 * 4) p.stages = 2;
+  else { p.stages = (212 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 1) p.stages = 1; }
+  if ((size_t)p.stages * stage_bytes < 4 * 32 * 33 * 4) { b2a_set_error("b2a_conv1d_tc: tile too small for the epilogue staging"); return B2A_E_UNSUPPORTED; }
+  size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 64;
 
   CUtensorMap mh, ml, mw, mwl;
   uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
