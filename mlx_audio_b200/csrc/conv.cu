@@ -130,6 +130,49 @@ __global__ void __launch_bounds__(NT) conv1d_dw_kernel(const b2a_conv1d_t p) {
   }
 }
 
+// Depthwise conv1d, stride 1, staged: a CTA owns DW_TL positions x 32 channels.  The input span
+// (DW_TL + (K-1)*dilation rows) is transformed ONCE (AdaIN/Snake prologue) while it is staged in
+// shared memory, so the transcendental is paid per input element rather than per tap, and every
+// tap is a conflict-free shared-memory read (lane == channel).  Halo rows are shared with the
+// neighbouring CTAs through L2, so HBM sees x once.
+constexpr int DW_TL = 128;
+template <int KT>
+__global__ void __launch_bounds__(NT) conv1d_dw_tiled_kernel(const b2a_conv1d_t p, int rows) {
+  extern __shared__ __align__(16) float smem[];      // [rows][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int l0 = blockIdx.x * DW_TL, c = blockIdx.y * 32 + lane, b = blockIdx.z;
+  const bool cok = c < p.Cout;
+  const Pre pre = make_pre(p);
+  const int K = KT ? KT : p.K;
+  const float* xb = p.x + (int64_t)b * p.x_bs + c;
+  const int64_t pos0 = (int64_t)l0 - p.pad_left;
+  for (int r = warp; r < rows; r += NT / 32) {
+    int64_t pos = pos0 + r;
+    float v = 0.f;
+    if (cok) {
+      if (pos >= 0 && pos < p.L) v = pre(__ldg(xb + pos * p.x_ld), b, c);
+      else if (p.pad_mode == 1) v = pre(__ldg(xb + (pos < 0 ? 0 : (int64_t)p.L - 1) * p.x_ld), b, c);
+    }
+    smem[r * 32 + lane] = v;
+  }
+  float w[KT ? KT : 16];
+#pragma unroll
+  for (int k = 0; k < (KT ? KT : 16); k++) w[k] = (cok && k < K) ? __ldg(p.w + (int64_t)k * p.Cout + c) : 0.f;
+  __syncthreads();
+  if (!cok) return;
+  const int d = p.dilation;
+#pragma unroll 4
+  for (int i = warp; i < DW_TL; i += NT / 32) {
+    int l = l0 + i;
+    if (l >= p.Lout) break;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < (KT ? KT : 16); k++)
+      if (KT || k < K) acc = fmaf(smem[(i + k * d) * 32 + lane], w[k], acc);
+    epilogue_store(p, b, l, c, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Dense transposed conv, gather (polyphase) form: output l (q = l + pad_left) takes taps
 // k = q%s + j*s from input rows q/s - j.  Tile = 64 positions x 64 channels.
@@ -304,9 +347,22 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
       conv1d_dense_kernel<16><<<grid, NT, smem, st>>>(*p, CI, rows);
     }
   } else if (p->groups == p->Cin && p->Cin == p->Cout) {
-    int64_t total = (int64_t)p->B * p->Lout * p->Cout;
-    int blocks = (int)((total + NT - 1) / NT); if (blocks > 148 * 32) blocks = 148 * 32;
-    conv1d_dw_kernel<<<blocks, NT, 0, st>>>(*p);
+    int rows = DW_TL + (p->K - 1) * p->dilation;
+    if (p->stride == 1 && p->K <= 16 && rows * 32 * 4 <= 96 * 1024 && p->Lout >= DW_TL) {
+      dim3 grid((p->Lout + DW_TL - 1) / DW_TL, (p->Cout + 31) / 32, p->B);
+      size_t sm = (size_t)rows * 32 * sizeof(float);
+      if (p->K == 7) {
+        if (sm > 48 * 1024) cudaFuncSetAttribute(conv1d_dw_tiled_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        conv1d_dw_tiled_kernel<7><<<grid, NT, sm, st>>>(*p, rows);
+      } else {
+        if (sm > 48 * 1024) cudaFuncSetAttribute(conv1d_dw_tiled_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        conv1d_dw_tiled_kernel<0><<<grid, NT, sm, st>>>(*p, rows);
+      }
+    } else {
+      int64_t total = (int64_t)p->B * p->Lout * p->Cout;
+      int blocks = (int)((total + NT - 1) / NT); if (blocks > 148 * 32) blocks = 148 * 32;
+      conv1d_dw_kernel<<<blocks, NT, 0, st>>>(*p);
+    }
   } else {
     b2a_set_error("b2a_conv1d_cl: groups must be 1 or Cin==Cout==groups (got %d)", p->groups);
     return B2A_E_UNSUPPORTED;

@@ -121,7 +121,7 @@ class ConvW:
 # Tensor-core dispatch policy: "off" = CUDA-core fp32 everywhere; "x2" = tcgen05 with (hi, lo) bf16 activation planes
 # (fp32-grade products); "x1" = tcgen05 with a single bf16 plane.
 TC_MODE = [os.environ.get("B2A_TC", "x2")]
-TC_MIN_K = 128                         # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
+TC_MIN_K = 64                          # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
 
 
 def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int, dilation: int = 1) -> bool:

@@ -107,7 +107,8 @@ def test_conv1d_strided_views_and_edge_pad():
     assert float(big_out[:, :, :5].abs().max()) == 0 and float(big_out[:, :, 37:].abs().max()) == 0
 
 
-@pytest.mark.parametrize("B,L,C,K,stride,dil,pad", [(1, 100, 96, 7, 1, 1, 3), (2, 64, 33, 7, 1, 9, 27), (1, 50, 8, 4, 2, 1, 1)])
+@pytest.mark.parametrize("B,L,C,K,stride,dil,pad", [(1, 100, 96, 7, 1, 1, 3), (2, 64, 33, 7, 1, 9, 27), (1, 50, 8, 4, 2, 1, 1),
+    (2, 700, 64, 7, 1, 9, 27), (1, 515, 33, 7, 1, 3, 9), (1, 300, 40, 5, 1, 2, 4), (1, 129, 512, 7, 1, 1, 3)])
 def test_conv1d_depthwise(B, L, C, K, stride, dil, pad):
     from mlx_audio_b200 import ops
     dev = _dev()

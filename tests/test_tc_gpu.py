@@ -27,6 +27,7 @@ CASES = [
     (2, 257, 64, 64, 3, 1, 1),
     (1, 129, 96, 32, 5, 2, 4),
     (1, 5000, 128, 128, 3, 1, 1),
+    (1, 3000, 64, 64, 1, 1, 0),
 ]
 
 
