@@ -204,10 +204,54 @@ int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_bs, const in
 /* Fused LM sampler (tts/models/qwen3_tts/qwen3_tts.py:805-860 over lm/sample_utils.py:131-239,279): additive suppress mask ->
  * sign-aware repetition penalty on the `seen` set -> temperature (<= 0: argmax) -> top-k -> top-p -> min-p -> categorical draw
  * by inverse CDF in index order with the caller's uniform u[b] (MLX's PRNG is not reproducible; tests inject u).  V <= 4096.
+ * out[b * out_stride] receives the token; mark_seen != 0 also sets seen[b][token] (generated_token_ids.append, :1402).
  * filtered_out (optional) receives the filtered, temperature-scaled logits the draw is made from. */
 int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int32_t V, const float* suppress_mask,
-                         const uint8_t* seen, int64_t seen_bs, float repetition_penalty, float temperature, int32_t top_k,
-                         float top_p, float min_p, const float* u, int64_t* out, float* filtered_out, void* stream);
+                         uint8_t* seen, int64_t seen_bs, int32_t mark_seen, float repetition_penalty, float temperature,
+                         int32_t top_k, float top_p, float min_p, const float* u, int64_t* out, int64_t out_stride,
+                         float* filtered_out, void* stream);
+
+/* ---- autoregressive LM step (Qwen3-TTS talker / code predictor, tts/models/qwen3_tts/talker.py) -----------------------
+ * All position-dependent scalars may come from device memory (base_dev, step_dev) so that one captured CUDA graph replays
+ * every frame of Model.generate's loop (qwen3_tts.py:1323-1404) without host round trips.
+ *
+ * b2a_gemv_bf16: y[m, n] = sum_k W[n,k] xn[m,k] (+ bias[n]) (+ res[m,n]) for M <= 8 activation rows -- nn.Linear at decode
+ * time (talker.py:284-286,314,335).  W bf16 row-major [N, w_ld].  norm_w != NULL fuses the preceding nn.RMSNorm
+ * (talker.py:388,395; x * rsqrt(mean(x^2) + eps) * norm_w).  mode 1 fuses SwiGLU (talker.py:319-321): W rows interleaved
+ * (gate_0, up_0, gate_1, ...), y[m, n/2] = silu(gate) * up, y has N/2 columns. */
+int32_t b2a_gemv_bf16(const float* x, int64_t x_ld, int32_t M, int32_t K, const void* w_bf16, int64_t w_ld, int32_t N,
+                      const float* bias, const float* norm_w, float norm_eps, int32_t mode, const float* res, int64_t res_ld,
+                      float* y, int64_t y_ld, void* stream);
+/* TalkerAttention / CodePredictorAttention / DecoderAttention up to the cache update (talker.py:288-307,558-572;
+ * speech_tokenizer.py:291-296): qkv [B,S,(Hq+2Hkv) D] -> per-head RMSNorm of q and k (weights [D], NULL = none), rotary
+ * embedding in the rotate_half convention, q_out [B,S,Hq,D], k/v appended to the caches [B,Smax,Hkv,D] at row base + s,
+ * base = *base_dev (or base_host when base_dev is NULL).  Rotary position of frequency slot i: pos3[axis,b,s] with the
+ * interleaved-MRoPE axis rule of talker.py:139-184 (axis 1 if i%3==1 && i<3*sec_h, axis 2 if i%3==2 && i<3*sec_w, else 0);
+ * pos3 NULL = base + s on every axis (sec_h = sec_w = 0 gives the standard RoPE of talker.py:68-113). */
+int32_t b2a_qknorm_rope_cache(const float* qkv, int64_t qkv_bs, int64_t qkv_ss, int32_t B, int32_t S, int32_t Hq, int32_t Hkv,
+                              int32_t D, const float* q_norm_w, const float* k_norm_w, float eps, const int32_t* pos3,
+                              const int32_t* base_dev, int32_t base_host, int32_t sec_h, int32_t sec_w, float theta,
+                              float* q_out, int64_t qo_bs, int64_t qo_ss, float* k_cache, float* v_cache, int64_t c_bs,
+                              int64_t c_ss, int32_t smax, void* stream);
+/* mx.fast.scaled_dot_product_attention against the KV cache with GQA (talker.py:309-312): query s attends cache rows
+ * [kv_start[b], base + s] (causal inside the new block; kv_start NULL = 0, else the left-padding count of
+ * qwen3_tts.py:486-604's batches).  out [B,S,Hq*D].  max_k bounds base + S (shared-memory sizing). */
+int32_t b2a_attn_decode(const float* q, int64_t q_bs, int64_t q_ss, const float* k_cache, const float* v_cache, int64_t c_bs,
+                        int64_t c_ss, float* out, int64_t o_bs, int64_t o_ss, int32_t B, int32_t S, int32_t Hq, int32_t Hkv,
+                        int32_t D, float scale, const int32_t* base_dev, int32_t base_host, const int32_t* kv_start,
+                        int32_t max_k, void* stream);
+/* y[r, i] = silu(gate) * up (talker.py:319-321, speech_tokenizer.py:321-322) for the batched (prefill) path: x [rows, 2I] holds
+ * (gate | up) halves, or interleaved (gate_0, up_0, gate_1, ...) pairs -- the row order b2a_gemv_bf16 mode 1 uses. */
+int32_t b2a_swiglu(const float* x, int64_t x_ld, int64_t rows, int32_t I, int32_t interleaved, float* y, int64_t y_ld, void* stream);
+/* Next talker input (qwen3_tts.py:1383-1398): out[b] = text(b) + sum_g tables[g][codes[b,g]], text(b) = text[b, step] while
+ * step = *step_dev - step_sub < n_text, else pad (tts_pad_embed); text/pad NULL = 0.  tables_dev / bins_dev are DEVICE arrays
+ * of G table pointers / table sizes; an out-of-range code sets *err_flag_dev. */
+int32_t b2a_embed_sum(const int64_t* codes, int64_t codes_bs, int32_t B, int32_t G, int32_t dim, const float* const* tables_dev,
+                      const int32_t* bins_dev, const float* text, int64_t text_bs, int64_t text_ss, int32_t n_text,
+                      const float* pad, const int32_t* step_dev, int32_t step_sub, float* out, int64_t out_bs,
+                      int32_t* err_flag_dev, void* stream);
+/* *p += v on the stream (KVCache.offset bookkeeping, lm/models/cache.py:112-155, kept on the device). */
+int32_t b2a_incr_i32(int32_t* p, int32_t v, void* stream);
 
 /* ---- codec (RVQ decode) ---------------------------------------------------------------------
  * out[b,t,:] (+)= sum_q codebooks[q][codes[b,q,t]][:]   (mimi/modules/quantization.py:47-49,103-108;

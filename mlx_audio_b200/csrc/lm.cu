@@ -1,0 +1,398 @@
+// Autoregressive-LM step kernels for the Qwen3-TTS talker / code predictor (include/b200audio.h: b2a_gemv_bf16,
+// b2a_qknorm_rope_cache, b2a_attn_decode, b2a_swiglu, b2a_embed_sum, b2a_incr_i32).  A decode step multiplies 1..8 activation
+// rows by every weight of the model, so it is HBM-bound on the bf16 weights: the GEMV streams each weight row exactly once
+// with 16-byte loads, fuses the RMSNorm that precedes the projection and the SwiGLU / residual that follows it, and all
+// position-dependent scalars (KV length, trailing-text index) are read from device memory so one CUDA graph replays
+// every frame.
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int GV_THREADS = 128;     // 4 warps split K
+constexpr int GV_ROWS = 4;          // weight rows per CTA
+
+struct GemvParams {
+  const float* x; int64_t x_ld; int M, K;
+  const __nv_bfloat16* w; int64_t w_ld; int N;     // N = weight rows
+  const float* bias; const float* norm_w; float norm_eps; int mode;
+  const float* res; int64_t res_ld; float* y; int64_t y_ld;
+};
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// y[m, n] = epilogue( sum_k W[n,k] * xn[m,k] ),  xn = x (plain) or x * rsqrt(mean(x^2)+eps) * norm_w (RMSNorm prologue).
+// mode 1 (SwiGLU): weight rows are interleaved (gate_0, up_0, gate_1, up_1, ...) and y[m, n/2] = silu(gate) * up.
+template <int MT>
+__global__ void __launch_bounds__(GV_THREADS) gemv_bf16_kernel(const GemvParams p) {
+  __shared__ float red[GV_THREADS / 32][MT][GV_ROWS];
+  __shared__ float ssq[GV_THREADS / 32][MT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * GV_ROWS;
+  float acc[MT][GV_ROWS];
+  float sq[MT];
+#pragma unroll
+  for (int m = 0; m < MT; m++) { sq[m] = 0.f;
+#pragma unroll
+    for (int r = 0; r < GV_ROWS; r++) acc[m][r] = 0.f; }
+  const int chunks = p.K >> 3;
+  for (int c = tid; c < chunks; c += GV_THREADS) {
+    const int k = c << 3;
+    uint4 wv[GV_ROWS];
+#pragma unroll
+    for (int r = 0; r < GV_ROWS; r++)
+      wv[r] = (n0 + r < p.N) ? __ldcs(reinterpret_cast<const uint4*>(p.w + (int64_t)(n0 + r) * p.w_ld + k)) : make_uint4(0, 0, 0, 0);
+    float g[8];
+    if (p.norm_w) {
+      float4 g0 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k)), g1 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k + 4));
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    }
+    float xv[MT][8];
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      if (m < p.M) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)m * p.x_ld + k));
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)m * p.x_ld + k + 4));
+        xv[m][0] = a.x; xv[m][1] = a.y; xv[m][2] = a.z; xv[m][3] = a.w; xv[m][4] = b.x; xv[m][5] = b.y; xv[m][6] = b.z; xv[m][7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) xv[m][j] = 0.f;
+      }
+      if (p.norm_w) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { sq[m] = fmaf(xv[m][j], xv[m][j], sq[m]); xv[m][j] *= g[j]; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < GV_ROWS; r++) {
+      float wf[8];
+      bf16x8_to_float(wv[r], wf);
+#pragma unroll
+      for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[m][r] = fmaf(wf[j], xv[m][j], acc[m][r]);
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MT; m++) {
+#pragma unroll
+    for (int r = 0; r < GV_ROWS; r++) { float v = warp_sum(acc[m][r]); if (lane == 0) red[warp][m][r] = v; }
+    if (p.norm_w) { float v = warp_sum(sq[m]); if (lane == 0) ssq[warp][m] = v; }
+  }
+  __syncthreads();
+  if (tid < MT * GV_ROWS) {
+    const int m = tid / GV_ROWS, r = tid % GV_ROWS, n = n0 + r;
+    if (m < p.M && n < p.N) {
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < GV_THREADS / 32; w++) v += red[w][m][r];
+      if (p.norm_w) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < GV_THREADS / 32; w++) s += ssq[w][m];
+        v *= rsqrtf(s / (float)p.K + p.norm_eps);
+      }
+      if (p.bias) v += __ldg(p.bias + n);
+      red[0][m][r] = v;                                   // own slot: (m, r) is written by this thread only
+    }
+  }
+  __syncthreads();
+  if (p.mode == 1) {
+    if (tid < MT * (GV_ROWS / 2)) {
+      const int m = tid / (GV_ROWS / 2), q = tid % (GV_ROWS / 2), n = n0 + 2 * q;
+      if (m < p.M && n + 1 < p.N) {
+        float gte = red[0][m][2 * q], up = red[0][m][2 * q + 1];
+        float v = gte / (1.f + expf(-gte)) * up;
+        const int no = n >> 1;
+        if (p.res) v += __ldg(p.res + (int64_t)m * p.res_ld + no);
+        p.y[(int64_t)m * p.y_ld + no] = v;
+      }
+    }
+  } else if (tid < MT * GV_ROWS) {
+    const int m = tid / GV_ROWS, r = tid % GV_ROWS, n = n0 + r;
+    if (m < p.M && n < p.N) {
+      float v = red[0][m][r];
+      if (p.res) v += __ldg(p.res + (int64_t)m * p.res_ld + n);
+      p.y[(int64_t)m * p.y_ld + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-head RMSNorm of q and k + (multimodal) rotary embedding + KV-cache append.  One warp per (b, s, head); a lane
+// owns elements lane + 32 j, so the rotate_half partner (i, i + D/2) sits in the same lane.
+struct QkParams {
+  const float* qkv; int64_t qkv_bs, qkv_ss;        // [B,S,(Hq+2Hkv) D]: q heads | k heads | v heads
+  int B, S, Hq, Hkv, D;
+  const float* qn; const float* kn; float eps;     // per-head RMSNorm weights [D] (NULL = no norm)
+  const int* pos3; const int* base_dev; int base_host;
+  int sec_h, sec_w; float theta;
+  float* q_out; int64_t qo_bs, qo_ss;              // [B,S,Hq,D]
+  float* kc; float* vc; int64_t c_bs, c_ss;        // caches [B,Smax,Hkv,D]
+  int smax;
+};
+
+template <int D>
+__global__ void qknorm_rope_cache_kernel(const QkParams p) {
+  constexpr int E = D / 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int HT = p.Hq + 2 * p.Hkv;
+  if (wid >= (int64_t)p.B * p.S * HT) return;
+  const int h = (int)(wid % HT);
+  const int s = (int)((wid / HT) % p.S), b = (int)(wid / ((int64_t)HT * p.S));
+  const int base = p.base_dev ? *p.base_dev : p.base_host;
+  const int cpos = base + s;
+  const float* src = p.qkv + (int64_t)b * p.qkv_bs + (int64_t)s * p.qkv_ss + (int64_t)h * D;
+  float v[E];
+#pragma unroll
+  for (int j = 0; j < E; j++) v[j] = src[lane + 32 * j];
+  if (h >= p.Hq + p.Hkv) {                         // v head: straight into the cache
+    if (cpos < p.smax) {
+      float* dst = p.vc + (int64_t)b * p.c_bs + (int64_t)cpos * p.c_ss + (int64_t)(h - p.Hq - p.Hkv) * D;
+#pragma unroll
+      for (int j = 0; j < E; j++) dst[lane + 32 * j] = v[j];
+    }
+    return;
+  }
+  const bool is_q = h < p.Hq;
+  const float* nw = is_q ? p.qn : p.kn;
+  if (nw) {
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < E; j++) ss = fmaf(v[j], v[j], ss);
+    ss = warp_sum(ss);
+    const float rinv = rsqrtf(ss / (float)D + p.eps);
+#pragma unroll
+    for (int j = 0; j < E; j++) v[j] = v[j] * rinv * __ldg(nw + lane + 32 * j);
+  }
+  // rotary: frequency slot i = (lane + 32 j) mod D/2
+  float o[E];
+#pragma unroll
+  for (int j = 0; j < E / 2; j++) {
+    const int i = lane + 32 * j;                   // < D/2
+    int axis = 0;
+    if (i % 3 == 1 && i < 3 * p.sec_h) axis = 1; else if (i % 3 == 2 && i < 3 * p.sec_w) axis = 2;
+    const int pos = p.pos3 ? p.pos3[((int64_t)axis * p.B + b) * p.S + s] : cpos;
+    const double inv = exp2(-(double)(2 * i) / (double)D * log2((double)p.theta));
+    double sn, cs;
+    sincos((double)pos * inv, &sn, &cs);
+    const float c = (float)cs, sf = (float)sn;
+    const float x1 = v[j], x2 = v[j + E / 2];
+    o[j] = x1 * c - x2 * sf;                        // q*cos + rotate_half(q)*sin, first half: -x2
+    o[j + E / 2] = x2 * c + x1 * sf;
+  }
+  if (is_q) {
+    float* dst = p.q_out + (int64_t)b * p.qo_bs + (int64_t)s * p.qo_ss + (int64_t)h * D;
+#pragma unroll
+    for (int j = 0; j < E; j++) dst[lane + 32 * j] = o[j];
+  } else if (cpos < p.smax) {
+    float* dst = p.kc + (int64_t)b * p.c_bs + (int64_t)cpos * p.c_ss + (int64_t)(h - p.Hq) * D;
+#pragma unroll
+    for (int j = 0; j < E; j++) dst[lane + 32 * j] = o[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Attention for decode / short prefill against the KV cache: one CTA per (head, query, batch).
+// Phase 1: warps stride over keys, lanes over D (coalesced rows), scores to shared memory.  Phase 2: softmax.
+// Phase 3: warps stride over keys again accumulating p * v (lane owns D/32 channels), cross-warp reduce.
+struct AdParams {
+  const float* q; int64_t q_bs, q_ss;
+  const float* kc; const float* vc; int64_t c_bs, c_ss;
+  float* o; int64_t o_bs, o_ss;
+  int B, S, Hq, Hkv; float scale;
+  const int* base_dev; int base_host; const int* kv_start; int max_k;
+};
+
+constexpr int AD_THREADS = 256;
+
+template <int D>
+__global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AdParams p) {
+  constexpr int E = D / 32, NW = AD_THREADS / 32;
+  extern __shared__ __align__(16) float sc[];       // [max_k] scores, then [NW][D] partial outputs
+  __shared__ float redm[NW], reds[NW];
+  const int h = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int base = p.base_dev ? *p.base_dev : p.base_host;
+  int klen = base + s + 1;
+  if (klen > p.max_k) klen = p.max_k;
+  const int k0 = p.kv_start ? p.kv_start[b] : 0;
+  const int hk = h / (p.Hq / p.Hkv);
+  const float* qp = p.q + (int64_t)b * p.q_bs + (int64_t)s * p.q_ss + (int64_t)h * D;
+  float qv[E];
+#pragma unroll
+  for (int j = 0; j < E; j++) qv[j] = qp[lane * E + j] * p.scale;
+  const float* kb = p.kc + (int64_t)b * p.c_bs + (int64_t)hk * D;
+  const float* vb = p.vc + (int64_t)b * p.c_bs + (int64_t)hk * D;
+  float mloc = -INFINITY;
+  for (int j = k0 + warp; j < klen; j += NW) {
+    const float* kr = kb + (int64_t)j * p.c_ss + lane * E;
+    float d = 0.f;
+    if constexpr (E == 4) { float4 t = *reinterpret_cast<const float4*>(kr); d = qv[0] * t.x + qv[1] * t.y + qv[2] * t.z + qv[3] * t.w; }
+    else { float2 t = *reinterpret_cast<const float2*>(kr); d = qv[0] * t.x + qv[1] * t.y; }
+    d = warp_sum(d);
+    if (lane == 0) sc[j] = d;
+    mloc = fmaxf(mloc, d);
+  }
+  if (lane == 0) redm[warp] = mloc;
+  __syncthreads();
+  float gm = redm[0];
+#pragma unroll
+  for (int w = 1; w < NW; w++) gm = fmaxf(gm, redm[w]);
+  float sl = 0.f;
+  for (int j = k0 + threadIdx.x; j < klen; j += AD_THREADS) { float e = __expf(sc[j] - gm); sc[j] = e; sl += e; }
+  sl = warp_sum(sl);
+  if (lane == 0) reds[warp] = sl;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; w++) tot += reds[w];
+  float acc[E];
+#pragma unroll
+  for (int j = 0; j < E; j++) acc[j] = 0.f;
+  for (int j = k0 + warp; j < klen; j += NW) {
+    const float pj = sc[j];
+    const float* vr = vb + (int64_t)j * p.c_ss + lane * E;
+    if constexpr (E == 4) { float4 t = *reinterpret_cast<const float4*>(vr); acc[0] = fmaf(pj, t.x, acc[0]); acc[1] = fmaf(pj, t.y, acc[1]); acc[2] = fmaf(pj, t.z, acc[2]); acc[3] = fmaf(pj, t.w, acc[3]); }
+    else { float2 t = *reinterpret_cast<const float2*>(vr); acc[0] = fmaf(pj, t.x, acc[0]); acc[1] = fmaf(pj, t.y, acc[1]); }
+  }
+  __syncthreads();                                  // scores no longer needed: reuse the buffer for the partials
+  float* part = sc;                                 // [NW][D]  (max_k >= NW*D/... guaranteed by the host: smem >= NW*D floats)
+#pragma unroll
+  for (int j = 0; j < E; j++) part[warp * D + lane * E + j] = acc[j];
+  __syncthreads();
+  if (threadIdx.x < D) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; w++) v += part[w * D + threadIdx.x];
+    p.o[(int64_t)b * p.o_bs + (int64_t)s * p.o_ss + (int64_t)h * D + threadIdx.x] = tot > 0.f ? v / tot : 0.f;
+  }
+}
+
+__global__ void swiglu_kernel(const float* x, int64_t x_ld, int64_t rows, int I, int interleaved, float* y, int64_t y_ld) {
+  const int64_t total = rows * I;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / I; const int i = (int)(idx % I);
+    const float g = interleaved ? x[r * x_ld + 2 * i] : x[r * x_ld + i], u = interleaved ? x[r * x_ld + 2 * i + 1] : x[r * x_ld + I + i];
+    y[r * y_ld + i] = g / (1.f + expf(-g)) * u;
+  }
+}
+
+struct EmbedSumParams {
+  const int64_t* codes; int64_t codes_bs; int B, G, dim;
+  const float* const* tables; const int* bins;
+  const float* text; int64_t text_bs, text_ss; int n_text; const float* pad; const int* step_dev; int step_sub;
+  float* out; int64_t out_bs; int* err;
+};
+__global__ void embed_sum_kernel(const EmbedSumParams p) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= p.dim) return;
+  float v = 0.f;
+  if (p.text || p.pad) {
+    const int step = (p.step_dev ? *p.step_dev : 0) - p.step_sub;
+    if (p.text && step >= 0 && step < p.n_text) v = p.text[(int64_t)b * p.text_bs + (int64_t)step * p.text_ss + d];
+    else if (p.pad) v = p.pad[d];
+  }
+  for (int g = 0; g < p.G; g++) {
+    const int64_t c = p.codes[(int64_t)b * p.codes_bs + g];
+    if (c < 0 || c >= p.bins[g]) { if (p.err) *p.err = 1; continue; }
+    v += p.tables[g][c * p.dim + d];
+  }
+  p.out[(int64_t)b * p.out_bs + d] = v;
+}
+
+__global__ void incr_kernel(int* p, int v) { *p += v; }
+
+}  // namespace
+
+extern "C" int32_t b2a_gemv_bf16(const float* x, int64_t x_ld, int32_t M, int32_t K, const void* w_bf16, int64_t w_ld, int32_t N,
+                                 const float* bias, const float* norm_w, float norm_eps, int32_t mode, const float* res,
+                                 int64_t res_ld, float* y, int64_t y_ld, void* stream) {
+  B2A_CHECK_ARG(M >= 1 && M <= 8, "M must be 1..8 (loop larger batches on the host)");
+  B2A_CHECK_ARG(K % 8 == 0 && w_ld % 8 == 0 && x_ld % 4 == 0, "K, w_ld must be multiples of 8 and x_ld of 4 (16-byte loads)");
+  B2A_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)w_bf16 & 15) == 0, "x and w must be 16-byte aligned");
+  B2A_CHECK_ARG(mode == 0 || (mode == 1 && N % 2 == 0 && bias == nullptr), "mode 1 (SwiGLU) needs interleaved gate/up rows and no bias");
+  GemvParams p{x, x_ld, M, K, (const __nv_bfloat16*)w_bf16, w_ld, N, bias, norm_w, norm_eps, mode, res, res_ld, y, y_ld};
+  const int grid = (N + GV_ROWS - 1) / GV_ROWS;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 1) gemv_bf16_kernel<1><<<grid, GV_THREADS, 0, st>>>(p);
+  else if (M == 2) gemv_bf16_kernel<2><<<grid, GV_THREADS, 0, st>>>(p);
+  else if (M <= 4) gemv_bf16_kernel<4><<<grid, GV_THREADS, 0, st>>>(p);
+  else gemv_bf16_kernel<8><<<grid, GV_THREADS, 0, st>>>(p);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_qknorm_rope_cache(const float* qkv, int64_t qkv_bs, int64_t qkv_ss, int32_t B, int32_t S, int32_t Hq,
+                                         int32_t Hkv, int32_t D, const float* q_norm_w, const float* k_norm_w, float eps,
+                                         const int32_t* pos3, const int32_t* base_dev, int32_t base_host, int32_t sec_h,
+                                         int32_t sec_w, float theta, float* q_out, int64_t qo_bs, int64_t qo_ss, float* k_cache,
+                                         float* v_cache, int64_t c_bs, int64_t c_ss, int32_t smax, void* stream) {
+  B2A_CHECK_ARG(D == 64 || D == 128, "head_dim must be 64 or 128");
+  B2A_CHECK_ARG(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "bad shape");
+  QkParams p{qkv, qkv_bs, qkv_ss, B, S, Hq, Hkv, D, q_norm_w, k_norm_w, eps, pos3, base_dev, base_host, sec_h, sec_w, theta,
+             q_out, qo_bs, qo_ss, k_cache, v_cache, c_bs, c_ss, smax};
+  const int64_t warps = (int64_t)B * S * (Hq + 2 * Hkv);
+  const int grid = (int)((warps * 32 + 255) / 256);
+  if (D == 128) qknorm_rope_cache_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else qknorm_rope_cache_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_attn_decode(const float* q, int64_t q_bs, int64_t q_ss, const float* k_cache, const float* v_cache,
+                                   int64_t c_bs, int64_t c_ss, float* out, int64_t o_bs, int64_t o_ss, int32_t B, int32_t S,
+                                   int32_t Hq, int32_t Hkv, int32_t D, float scale, const int32_t* base_dev, int32_t base_host,
+                                   const int32_t* kv_start, int32_t max_k, void* stream) {
+  B2A_CHECK_ARG(D == 64 || D == 128, "head_dim must be 64 or 128");
+  B2A_CHECK_ARG(B > 0 && S > 0 && Hq % Hkv == 0 && max_k > 0 && max_k <= 48 * 1024, "bad shape (max_k <= 49152)");
+  B2A_CHECK_ARG(c_ss % 4 == 0 && c_bs % 4 == 0 && ((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0, "cache rows must be 16-byte aligned");
+  AdParams p{q, q_bs, q_ss, k_cache, v_cache, c_bs, c_ss, out, o_bs, o_ss, B, S, Hq, Hkv, scale, base_dev, base_host, kv_start, max_k};
+  size_t floats = (size_t)max_k;
+  if (floats < (size_t)(AD_THREADS / 32) * D) floats = (size_t)(AD_THREADS / 32) * D;
+  const size_t sm = floats * sizeof(float);
+  dim3 grid(Hq, S, B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 128) {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attn_decode_kernel<128><<<grid, AD_THREADS, sm, st>>>(p);
+  } else {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attn_decode_kernel<64><<<grid, AD_THREADS, sm, st>>>(p);
+  }
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_swiglu(const float* x, int64_t x_ld, int64_t rows, int32_t I, int32_t interleaved, float* y, int64_t y_ld, void* stream) {
+  B2A_CHECK_ARG(rows > 0 && I > 0, "bad shape");
+  int64_t total = rows * I;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  swiglu_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_ld, rows, I, interleaved, y, y_ld);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_embed_sum(const int64_t* codes, int64_t codes_bs, int32_t B, int32_t G, int32_t dim,
+                                 const float* const* tables_dev, const int32_t* bins_dev, const float* text, int64_t text_bs,
+                                 int64_t text_ss, int32_t n_text, const float* pad, const int32_t* step_dev, int32_t step_sub,
+                                 float* out, int64_t out_bs, int32_t* err_flag_dev, void* stream) {
+  B2A_CHECK_ARG(B > 0 && G >= 0 && dim > 0, "bad shape");
+  EmbedSumParams p{codes, codes_bs, B, G, dim, tables_dev, bins_dev, text, text_bs, text_ss, n_text, pad, step_dev, step_sub, out, out_bs, err_flag_dev};
+  dim3 grid((dim + 255) / 256, B);
+  embed_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_incr_i32(int32_t* p, int32_t v, void* stream) {
+  incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p, v);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

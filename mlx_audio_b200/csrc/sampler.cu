@@ -146,7 +146,8 @@ constexpr int SV = 4096;
 struct SampleParams {
   const float* logits; int64_t logits_bs; int V;
   const float* suppress;                  // [V] additive 0/-inf or NULL
-  const uint8_t* seen; int64_t seen_bs;   // [B,V] 1 = token already generated (repetition penalty set) or NULL
+  uint8_t* seen; int64_t seen_bs;         // [B,V] 1 = token already generated (repetition penalty set) or NULL
+  int mark_seen; int64_t out_stride;      // mark_seen: set seen[b][token] after the draw; out[b * out_stride]
   float rep_penalty, temperature; int top_k; float top_p, min_p;
   const float* u;                         // [B] uniforms in [0,1)
   int64_t* out;                           // [B]
@@ -177,7 +178,11 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
       if (tid < s) { if (sv[tid + s] > sv[tid] || (sv[tid + s] == sv[tid] && gi[tid + s] < gi[tid])) { sv[tid] = sv[tid + s]; gi[tid] = gi[tid + s]; } }
       __syncthreads();
     }
-    if (tid == 0) p.out[b] = gi[0] == 0x7fffffff ? 0 : gi[0];
+    if (tid == 0) {
+      const int pick = gi[0] == 0x7fffffff ? 0 : gi[0];
+      p.out[(int64_t)b * p.out_stride] = pick;
+      if (p.mark_seen && p.seen) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
+    }
     return;
   }
   const float inv_t = 1.f / p.temperature;
@@ -248,28 +253,46 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
   float gm = red[0];
   for (int i = 1; i < (int)(blockDim.x >> 5); i++) gm = fmaxf(gm, red[i]);
   __syncthreads();
-  if (tid == 0) {
-    double z = 0.0;
-    for (int v = 0; v < V; v++) if (s_scan[v] > NEG) z += exp((double)(s_scan[v] - gm));
-    double target = (double)p.u[b] * z, run = 0.0;
-    int pick = -1, lastv = 0;
-    for (int v = 0; v < V; v++) {
-      if (s_scan[v] > NEG) { run += exp((double)(s_scan[v] - gm)); lastv = v; if (run > target) { pick = v; break; } }
+  if (tid < 32) {                                                   // warp 0: chunked inverse CDF in index order, double accumulation
+    const int lane = tid, per = (V + 31) / 32, lo = lane * per, hi = min(V, lo + per);
+    double sum = 0.0; int lastlive = -1;
+    for (int v = lo; v < hi; v++) if (s_scan[v] > NEG) { sum += exp((double)(s_scan[v] - gm)); lastlive = v; }
+    double inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const double z = __shfl_sync(0xffffffffu, inc, 31);
+    const double target = (double)p.u[b] * z;
+    int glast = lastlive;
+    for (int o = 16; o > 0; o >>= 1) glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, o));
+    const unsigned ball = __ballot_sync(0xffffffffu, inc > target);
+    int pick = -1;
+    if (ball) {
+      const int L = __ffs(ball) - 1;
+      if (lane == L) {
+        double run = inc - sum;
+        pick = lastlive;
+        for (int v = lo; v < hi; v++) if (s_scan[v] > NEG) { run += exp((double)(s_scan[v] - gm)); if (run > target) { pick = v; break; } }
+      }
+      pick = __shfl_sync(0xffffffffu, pick, L);
+    } else pick = glast;
+    if (lane == 0) {
+      if (pick < 0) pick = 0;
+      p.out[(int64_t)b * p.out_stride] = pick;
+      if (p.mark_seen && p.seen) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
     }
-    p.out[b] = pick >= 0 ? pick : lastv;
   }
 }
 
 }  // namespace
 
 extern "C" int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int32_t V, const float* suppress_mask,
-                                    const uint8_t* seen, int64_t seen_bs, float repetition_penalty, float temperature, int32_t top_k,
-                                    float top_p, float min_p, const float* u, int64_t* out, float* filtered_out, void* stream) {
+                                    uint8_t* seen, int64_t seen_bs, int32_t mark_seen, float repetition_penalty, float temperature,
+                                    int32_t top_k, float top_p, float min_p, const float* u, int64_t* out, int64_t out_stride,
+                                    float* filtered_out, void* stream) {
   B2A_CHECK_ARG(logits && out && B > 0 && V > 0, "bad pointers/shape");
   B2A_CHECK_ARG(temperature <= 0.f || u != nullptr, "a uniform draw per row is required when temperature > 0");
   if (V > SV) { b2a_set_error("b2a_sample_token: vocab %d > %d not supported", V, SV); return B2A_E_UNSUPPORTED; }
   B2A_CHECK_ARG(min_p >= 0.f && min_p <= 1.f, "`min_p` has to be a float in the [0, 1] interval");
-  SampleParams p{logits, logits_bs, V, suppress_mask, seen, seen_bs, repetition_penalty, temperature, top_k, top_p, min_p, u, out, filtered_out};
+  SampleParams p{logits, logits_bs, V, suppress_mask, seen, seen_bs, mark_seen, out_stride < 1 ? 1 : out_stride, repetition_penalty, temperature, top_k, top_p, min_p, u, out, filtered_out};
   sample_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;

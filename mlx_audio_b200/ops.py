@@ -493,15 +493,115 @@ def randn_(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
 
 
 def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, u=None,
-                 suppress_mask=None, seen=None, repetition_penalty: float = 1.0, return_filtered: bool = False):
-    """Fused sampler on logits [B,V] (V <= 4096) -> int64 tokens [B] (and the filtered logits when asked)."""
+                 suppress_mask=None, seen=None, repetition_penalty: float = 1.0, return_filtered: bool = False, mark_seen: bool = False,
+                 out: Optional[torch.Tensor] = None):
+    """Fused sampler on logits [B,V] (V <= 4096) -> int64 tokens [B] (and the filtered logits when asked).  ``out`` may be a
+    strided int64 view (e.g. a column of the [B,16] code matrix)."""
     B, V = logits.shape
     assert logits.stride(1) == 1 and (seen is None or (seen.dtype == torch.uint8 and seen.stride(1) == 1))
-    out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    if out is None:
+        out = torch.empty(B, device=logits.device, dtype=torch.int64)
+    assert out.dtype == torch.int64 and out.dim() == 1 and out.shape[0] == B
     filt = torch.empty(B, V, device=logits.device, dtype=torch.float32) if return_filtered else None
     _call("sampler", _lib.lib().b2a_sample_token, 1, logits.data_ptr(), logits.stride(0), B, V, _p(suppress_mask), _p(seen),
-          0 if seen is None else seen.stride(0), repetition_penalty, temperature, top_k, top_p, min_p, _p(u), out.data_ptr(), _p(filt), _stream())
+          0 if seen is None else seen.stride(0), int(mark_seen), repetition_penalty, temperature, top_k, top_p, min_p, _p(u),
+          out.data_ptr(), out.stride(0) if B > 1 else 1, _p(filt), _stream())
     return (out, filt) if return_filtered else out
+
+
+def gemv(x: torch.Tensor, cw: "ConvW", *, norm_w=None, norm_eps: float = 1e-6, swiglu: bool = False, res=None, out=None) -> torch.Tensor:
+    """Decode-time nn.Linear on x [M, K] (any M; looped in groups of 8) with the bf16 weight rows of ``cw`` ([N, cin_pad]):
+    optional fused RMSNorm prologue, SwiGLU (interleaved gate/up rows) and residual."""
+    assert x.dim() == 2 and x.stride(1) == 1 and cw.K == 1 and cw.w_tc is not None and not cw.f16 and cw.w_tc_lo is None, \
+        "gemv needs a bf16-exact K=1 weight"
+    M, K = x.shape
+    N = cw.cout
+    n_out = N // 2 if swiglu else N
+    if out is None:
+        out = torch.empty(M, n_out, device=x.device, dtype=torch.float32)
+    assert K == cw.cin and out.shape == (M, n_out) and out.stride(1) == 1
+    for m0 in range(0, M, 8):
+        m = min(8, M - m0)
+        r = None if res is None else res[m0:m0 + m]
+        _call("gemv", _lib.lib().b2a_gemv_bf16, 1, x[m0:m0 + m].data_ptr(), x.stride(0), m, K, cw.w_tc.data_ptr(), cw.cin_pad, N,
+              _p(cw.bias), _p(norm_w), norm_eps, int(swiglu), _p(r), 0 if r is None else r.stride(0), out[m0:m0 + m].data_ptr(),
+              out.stride(0), _stream())
+    return out
+
+
+def qknorm_rope_cache(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, k_cache: torch.Tensor, v_cache: torch.Tensor, *,
+                      q_norm=None, k_norm=None, eps: float = 1e-6, pos3=None, base_dev=None, base: int = 0, mrope=(0, 0),
+                      theta: float = 10000.0, q_out=None) -> torch.Tensor:
+    """qkv [B,S,(Hq+2Hkv)D] -> q_out [B,S,Hq*D] (normed + rotated), k/v appended to caches [B,Smax,Hkv*D] at row base+s."""
+    _chk3(qkv, "qkv")
+    B, S, _ = qkv.shape
+    if q_out is None:
+        q_out = torch.empty(B, S, n_heads * head_dim, device=qkv.device, dtype=torch.float32)
+    assert k_cache.shape == v_cache.shape and k_cache.stride() == v_cache.stride() and k_cache.stride(2) == 1
+    assert pos3 is None or (pos3.dtype == torch.int32 and pos3.is_contiguous() and pos3.shape == (3, B, S))
+    _call("rope", _lib.lib().b2a_qknorm_rope_cache, 1, qkv.data_ptr(), qkv.stride(0), qkv.stride(1), B, S, n_heads, n_kv, head_dim,
+          _p(q_norm), _p(k_norm), eps, _p(pos3), _p(base_dev), base, mrope[0], mrope[1], theta, q_out.data_ptr(), q_out.stride(0),
+          q_out.stride(1), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0), k_cache.stride(1), k_cache.shape[1], _stream())
+    return q_out
+
+
+def attn_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, *, scale: float,
+                base_dev=None, base: int = 0, kv_start=None, max_k: Optional[int] = None, out=None) -> torch.Tensor:
+    """Causal GQA attention of q [B,S,Hq*D] against cache rows [kv_start, base+s]; out [B,S,Hq*D]."""
+    _chk3(q, "q")
+    B, S, _ = q.shape
+    if out is None:
+        out = torch.empty(B, S, n_heads * head_dim, device=q.device, dtype=torch.float32)
+    if max_k is None:
+        max_k = k_cache.shape[1] if base_dev is not None else base + S
+    _call("attention", _lib.lib().b2a_attn_decode, 1, q.data_ptr(), q.stride(0), q.stride(1), k_cache.data_ptr(), v_cache.data_ptr(),
+          k_cache.stride(0), k_cache.stride(1), out.data_ptr(), out.stride(0), out.stride(1), B, S, n_heads, n_kv, head_dim, scale,
+          _p(base_dev), base, _p(kv_start), max_k, _stream())
+    return out
+
+
+def swiglu(x: torch.Tensor, out=None, interleaved: bool = False) -> torch.Tensor:
+    """x [..., 2I] (gate | up halves, or interleaved pairs) -> silu(gate) * up [..., I]."""
+    shp = x.shape
+    I = shp[-1] // 2
+    x2 = x.reshape(-1, shp[-1])
+    assert x2.stride(1) == 1
+    if out is None:
+        out = torch.empty(*shp[:-1], I, device=x.device, dtype=torch.float32)
+    o2 = out.reshape(-1, I)
+    _call("other", _lib.lib().b2a_swiglu, 1, x2.data_ptr(), x2.stride(0), x2.shape[0], I, int(interleaved), o2.data_ptr(), o2.stride(0), _stream())
+    return out
+
+
+class EmbedTables:
+    """Device arrays of table pointers / sizes for embed_sum (built once per model)."""
+
+    def __init__(self, tables):
+        self.tables = [t for t in tables]
+        for t in self.tables:
+            assert t.dim() == 2 and t.is_contiguous() and t.dtype == torch.float32 and t.shape[1] == self.tables[0].shape[1]
+        dev = self.tables[0].device
+        self.ptrs = torch.tensor([t.data_ptr() for t in self.tables], dtype=torch.int64, device=dev)
+        self.bins = torch.tensor([t.shape[0] for t in self.tables], dtype=torch.int32, device=dev)
+        self.dim = self.tables[0].shape[1]
+
+
+def embed_sum(codes: torch.Tensor, tabs: EmbedTables, *, text=None, pad=None, step_dev=None, step_sub: int = 0, out=None, err=None) -> torch.Tensor:
+    """out[b] = text-or-pad(b) + sum_g tables[g][codes[b,g]]; codes int64 [B,G] (G <= len(tables))."""
+    assert codes.dtype == torch.int64 and codes.dim() == 2 and codes.stride(1) == 1
+    B, G = codes.shape
+    assert G <= len(tabs.tables)
+    if out is None:
+        out = torch.empty(B, tabs.dim, device=codes.device, dtype=torch.float32)
+    tb, ts, nt = (0, 0, 0) if text is None else (text.stride(0), text.stride(1), text.shape[1])
+    _call("other", _lib.lib().b2a_embed_sum, 1, codes.data_ptr(), codes.stride(0), B, G, tabs.dim, tabs.ptrs.data_ptr(), tabs.bins.data_ptr(),
+          _p(text), tb, ts, nt, _p(pad), _p(step_dev), step_sub, out.data_ptr(), out.stride(0), _p(err), _stream())
+    return out
+
+
+def incr_(p: torch.Tensor, v: int = 1) -> None:
+    assert p.dtype == torch.int32
+    _call("other", _lib.lib().b2a_incr_i32, 1, p.data_ptr(), v, _stream())
 
 
 def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch.Tensor] = None, check=True) -> torch.Tensor:

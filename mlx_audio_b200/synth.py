@@ -355,3 +355,128 @@ def whisper_decoder_weights(dims, seed=1):
     g.P["decoder.token_embedding.weight"][50364:] *= 0.25      # damp timestamp logits (random weights would otherwise let the
     g.P["decoder.token_embedding.weight"] = _f16(g.P["decoder.token_embedding.weight"])   # 1501 timestamps out-vote every text token)
     return g.P
+
+
+# ============================================================================= Qwen3-TTS
+
+def qwen3_talker_weights(cfg, text_vocab=512, seed=11):
+    """Parameter tree of tts/models/qwen3_tts/talker.py:Qwen3TTSTalkerForConditionalGeneration with the checkpoint's ``talker.``
+    prefix; ``cfg`` is the flat dict of oracle/qwen3.py:TALKER.  bf16-exact values.  ``text_vocab`` shrinks the 151 936-row text
+    embedding (prompt assembly only, not on the per-frame path); fan-in scaling keeps the residual stream O(1) through 28 layers
+    and the logits wide enough (std ~ 2) that sampling is not uniform."""
+    g = _Gen(seed)
+    gen = g.g
+    H, I, hd = cfg["hidden_size"], cfg["intermediate_size"], cfg["head_dim"]
+    hq, hk = cfg["num_attention_heads"], cfg["num_key_value_heads"]
+
+    def stack(pre, n_layers, H, I, hq, hk, hd):
+        for i in range(n_layers):
+            L = f"{pre}.layers.{i}"
+            _fan(g, L + ".self_attn.q_proj.weight", hq * hd, H, fan_in=H)
+            _fan(g, L + ".self_attn.k_proj.weight", hk * hd, H, fan_in=H)
+            _fan(g, L + ".self_attn.v_proj.weight", hk * hd, H, fan_in=H)
+            _fan(g, L + ".self_attn.o_proj.weight", H, hq * hd, fan_in=4 * hq * hd)
+            g.P[L + ".self_attn.q_norm.weight"] = _bf16(1.0 + 0.1 * torch.randn(hd, generator=gen))
+            g.P[L + ".self_attn.k_norm.weight"] = _bf16(1.0 + 0.1 * torch.randn(hd, generator=gen))
+            g.P[L + ".input_layernorm.weight"] = _bf16(1.0 + 0.1 * torch.randn(H, generator=gen))
+            g.P[L + ".post_attention_layernorm.weight"] = _bf16(1.0 + 0.1 * torch.randn(H, generator=gen))
+            _fan(g, L + ".mlp.gate_proj.weight", I, H, fan_in=H)
+            _fan(g, L + ".mlp.up_proj.weight", I, H, fan_in=H)
+            _fan(g, L + ".mlp.down_proj.weight", H, I, fan_in=4 * I)
+        g.P[pre + ".norm.weight"] = _bf16(1.0 + 0.1 * torch.randn(H, generator=gen))
+
+    stack("talker.model", cfg["num_hidden_layers"], H, I, hq, hk, hd)
+    g.normal("talker.model.codec_embedding.weight", cfg["vocab_size"], H, std=1.0)
+    g.normal("talker.model.text_embedding.weight", text_vocab, cfg["text_hidden_size"], std=1.0)
+    _fan(g, "talker.text_projection.linear_fc1.weight", cfg["text_hidden_size"], cfg["text_hidden_size"], fan_in=cfg["text_hidden_size"])
+    g.normal("talker.text_projection.linear_fc1.bias", cfg["text_hidden_size"], std=0.05)
+    _fan(g, "talker.text_projection.linear_fc2.weight", H, cfg["text_hidden_size"], fan_in=cfg["text_hidden_size"] / 4)
+    g.normal("talker.text_projection.linear_fc2.bias", H, std=0.05)
+    _fan(g, "talker.codec_head.weight", cfg["vocab_size"], H, fan_in=H / 4)
+    cH, cI = cfg["cp_hidden_size"], cfg["cp_intermediate_size"]
+    stack("talker.code_predictor.model", cfg["cp_num_hidden_layers"], cH, cI, cfg["cp_num_attention_heads"], cfg["cp_num_key_value_heads"],
+          cfg["cp_head_dim"])
+    for k in range(cfg["num_code_groups"] - 1):
+        g.normal(f"talker.code_predictor.model.codec_embedding.{k}.weight", cfg["cp_vocab_size"], H, std=1.0)
+        _fan(g, f"talker.code_predictor.lm_head.{k}.weight", cfg["cp_vocab_size"], cH, fan_in=cH / 4)
+    return g.P
+
+
+def qwen3_tokenizer_weights(cfg, seed=12):
+    """Parameter tree of speech_tokenizer.py:Qwen3TTSSpeechTokenizer (decode side, MLX names after ``sanitize``); ``cfg`` is the
+    flat dict of oracle/qwen3.py:TOKENIZER_DECODER.  bf16-exact values."""
+    g = _Gen(seed)
+    gen = g.g
+    cd, ld, hs = cfg["codebook_dim"], cfg["latent_dim"], cfg["hidden_size"]
+    nsem, nq = cfg["num_semantic_quantizers"], cfg["num_quantizers"]
+    D = "decoder."
+    for name, n in (("rvq_first", nsem), ("rvq_rest", nq - nsem)):
+        for li in range(n):
+            g.normal(f"{D}quantizer.{name}.vq.layers.{li}.codebook.embed.weight", cfg["codebook_size"], cd // 2, std=1.0)
+        _fan(g, f"{D}quantizer.{name}.output_proj.weight", cd, 1, cd // 2, fan_in=(cd // 2) * max(n, 1))
+    _fan(g, D + "pre_conv.conv.weight", ld, 3, cd, fan_in=3 * cd)
+    g.normal(D + "pre_conv.conv.bias", ld, std=0.05)
+    T = D + "pre_transformer"
+    _fan(g, T + ".input_proj.weight", hs, ld, fan_in=ld)
+    g.normal(T + ".input_proj.bias", hs, std=0.05)
+    _fan(g, T + ".output_proj.weight", ld, hs, fan_in=hs)
+    g.normal(T + ".output_proj.bias", ld, std=0.05)
+    nh, hd, I = cfg["num_attention_heads"], cfg["head_dim"], cfg["intermediate_size"]
+    for i in range(cfg["num_hidden_layers"]):
+        L = f"{T}.layers.{i}"
+        for n in "qkv":
+            _fan(g, L + f".self_attn.{n}_proj.weight", nh * hd, hs, fan_in=hs)
+        _fan(g, L + ".self_attn.o_proj.weight", hs, nh * hd, fan_in=nh * hd)
+        _fan(g, L + ".mlp.gate_proj.weight", I, hs, fan_in=hs)
+        _fan(g, L + ".mlp.up_proj.weight", I, hs, fan_in=hs)
+        _fan(g, L + ".mlp.down_proj.weight", hs, I, fan_in=I)
+        g.P[L + ".input_layernorm.weight"] = _bf16(1.0 + 0.1 * torch.randn(hs, generator=gen))
+        g.P[L + ".post_attention_layernorm.weight"] = _bf16(1.0 + 0.1 * torch.randn(hs, generator=gen))
+        g.P[L + ".self_attn_layer_scale.scale"] = _bf16(0.3 + 0.1 * torch.rand(hs, generator=gen))
+        g.P[L + ".mlp_layer_scale.scale"] = _bf16(0.3 + 0.1 * torch.rand(hs, generator=gen))
+    g.P[T + ".norm.weight"] = _bf16(1.0 + 0.1 * torch.randn(hs, generator=gen))
+    for i, f in enumerate(cfg["upsampling_ratios"]):
+        U = f"{D}upsample.{i}"
+        _fan(g, U + ".0.conv.weight", ld, f, ld, fan_in=ld)
+        g.normal(U + ".0.conv.bias", ld, std=0.05)
+        _fan(g, U + ".1.dwconv.conv.weight", ld, 7, 1, fan_in=7)
+        g.normal(U + ".1.dwconv.conv.bias", ld, std=0.05)
+        g.P[U + ".1.norm.weight"] = _bf16(1.0 + 0.1 * torch.randn(ld, generator=gen))
+        g.normal(U + ".1.norm.bias", ld, std=0.05)
+        _fan(g, U + ".1.pwconv1.weight", 4 * ld, ld, fan_in=ld)
+        g.normal(U + ".1.pwconv1.bias", 4 * ld, std=0.05)
+        _fan(g, U + ".1.pwconv2.weight", ld, 4 * ld, fan_in=4 * ld)
+        g.normal(U + ".1.pwconv2.bias", ld, std=0.05)
+        g.P[U + ".1.gamma"] = _bf16(0.3 + 0.1 * torch.rand(ld, generator=gen))
+    dd = cfg["decoder_dim"]
+    _fan(g, D + "decoder.0.conv.weight", dd, 7, ld, fan_in=7 * ld)
+    g.normal(D + "decoder.0.conv.bias", dd, std=0.05)
+    cin = dd
+    for bi, r in enumerate(cfg["upsample_rates"]):
+        cout = cin // 2
+        B_ = f"{D}decoder.{bi + 1}.block"
+        g.P[B_ + ".0.alpha"] = _bf16(0.2 * torch.randn(cin, generator=gen))
+        g.P[B_ + ".0.beta"] = _bf16(0.2 * torch.randn(cin, generator=gen))
+        _fan(g, B_ + ".1.conv.weight", cout, 2 * r, cin, fan_in=2 * cin)
+        g.normal(B_ + ".1.conv.bias", cout, std=0.05)
+        for ui in range(3):
+            U = f"{B_}.{ui + 2}"
+            for a in ("act1", "act2"):
+                g.P[f"{U}.{a}.alpha"] = _bf16(0.2 * torch.randn(cout, generator=gen))
+                g.P[f"{U}.{a}.beta"] = _bf16(0.2 * torch.randn(cout, generator=gen))
+            _fan(g, U + ".conv1.conv.weight", cout, 7, cout, fan_in=7 * cout * 2)
+            g.normal(U + ".conv1.conv.bias", cout, std=0.05)
+            _fan(g, U + ".conv2.conv.weight", cout, 1, cout, fan_in=cout * 4)
+            g.normal(U + ".conv2.conv.bias", cout, std=0.05)
+        cin = cout
+    n_blocks = len(cfg["upsample_rates"])
+    g.P[f"{D}decoder.{n_blocks + 1}.alpha"] = _bf16(0.2 * torch.randn(cin, generator=gen))
+    g.P[f"{D}decoder.{n_blocks + 1}.beta"] = _bf16(0.2 * torch.randn(cin, generator=gen))
+    _fan(g, f"{D}decoder.{n_blocks + 2}.conv.weight", 1, 7, cin, fan_in=7 * cin * 16)
+    g.normal(f"{D}decoder.{n_blocks + 2}.conv.bias", 1, std=0.02)
+    return g.P
+
+
+def qwen3_codes(cfg, t, batch=1, seed=13):
+    """codes [B, 16, T] (first code > 0 so that the valid-length rule of speech_tokenizer.py:1113-1116 keeps every frame)."""
+    return torch.randint(1, cfg["codebook_size"], (batch, cfg["num_quantizers"], t), generator=torch.Generator().manual_seed(seed))

@@ -1,0 +1,239 @@
+"""Qwen3-TTS generation loop on B200 (reference: tts/models/qwen3_tts/qwen3_tts.py).
+
+Covers the base path of ``Model.generate`` (qwen3_tts.py:1122-1575): input assembly from token ids
+(``_prepare_generation_inputs`` :326-484 minus the tokenizer / speaker encoder, which are host / "next" rows), the per-frame
+loop (:1323-1404) with ``_sample_token`` (:805-860), and ``_decode_chunk`` (:1017-1048) through the speech tokenizer.
+
+One frame = talker step + first-codebook sample + 15 code-predictor sub-steps (each with its sampler) + next-input
+embedding sum: ~700 small launches.  They are captured ONCE into a CUDA graph; every scalar that changes between frames
+(KV length, trailing-text index, uniforms, seen-token set, codes) lives in device memory, so the host only replays the
+graph and reads back 16 integers per frame for the EOS test (the reference also syncs once per frame, :1398-1400).
+"""
+from __future__ import annotations
+
+import time
+from typing import Optional
+
+import torch
+
+from .... import ops
+from ..base import GenerationResult
+from .config import ModelConfig
+from .speech_tokenizer import Qwen3TTSSpeechTokenizer
+from .talker import Qwen3TTSTalkerForConditionalGeneration
+
+
+def format_duration(seconds: float) -> str:
+    """qwen3_tts.py:160-165."""
+    hours = int(seconds // 3600)
+    minutes = int((seconds % 3600) // 60)
+    secs = int(seconds % 60)
+    ms = int((seconds % 1) * 1000)
+    return f"{hours:02d}:{minutes:02d}:{secs:02d}.{ms:03d}"
+
+
+class Model:
+    def __init__(self, config: ModelConfig, device="cuda"):
+        self.config = config
+        self.device = torch.device(device)
+        self.talker = Qwen3TTSTalkerForConditionalGeneration(config.talker_config, device)
+        self.speech_tokenizer: Optional[Qwen3TTSSpeechTokenizer] = None
+        self.tokenizer = None
+        self._graph = None
+        self._graph_key = None
+
+    @property
+    def sample_rate(self) -> int:
+        return self.config.sample_rate
+
+    @property
+    def model_type(self) -> str:
+        return self.config.model_type
+
+    def load_weights(self, weights):
+        """``weights`` with the checkpoint's ``talker.`` prefix (sanitized here, qwen3_tts.py:2914-2925)."""
+        self.talker.load_weights(self.talker.sanitize(weights))
+        t = self.talker
+        self._tabs_all = ops.EmbedTables([t.codec_embedding] + t.code_predictor.codec_embedding)
+        self._tab0 = ops.EmbedTables([t.codec_embedding])
+        self._tab_cp = [ops.EmbedTables([e]) for e in t.code_predictor.codec_embedding]
+        return self
+
+    def load_speech_tokenizer(self, speech_tokenizer: Qwen3TTSSpeechTokenizer):
+        self.speech_tokenizer = speech_tokenizer
+
+    # ------------------------------------------------------------------ input assembly
+    @torch.no_grad()
+    def prepare_generation_inputs_from_ids(self, input_ids, language_id: Optional[int] = None, speaker_id=None, speaker_embed=None):
+        """qwen3_tts.py:326-484 after tokenisation: ``input_ids`` = tokenizer.encode("<|im_start|>assistant\\n{text}<|im_end|>\\n
+        <|im_start|>assistant\\n").  Returns (input_embeds [1,P,H], trailing_text_hidden [1,n,H], tts_pad_embed [1,1,H])."""
+        t, cfg, dev = self.talker, self.config.talker_config, self.device
+        ids = torch.as_tensor(input_ids, dtype=torch.int64, device=dev).reshape(-1)
+        text_embed = t.text_projection(ops.gather_rows(t.text_embedding, ids)[None])                          # [1,L,H]
+        tts_ids = torch.tensor([self.config.tts_bos_token_id, self.config.tts_eos_token_id, self.config.tts_pad_token_id], device=dev)
+        tts = t.text_projection(ops.gather_rows(t.text_embedding, tts_ids)[None])
+        tts_bos, tts_eos, tts_pad = tts[:, 0:1], tts[:, 1:2], tts[:, 2:3]
+        if speaker_embed is None and speaker_id is not None:
+            speaker_embed = ops.gather_rows(t.codec_embedding, torch.tensor([int(speaker_id)], device=dev))[None]
+        if language_id is None:
+            prefill = [cfg.codec_nothink_id, cfg.codec_think_bos_id, cfg.codec_think_eos_id]
+        else:
+            prefill = [cfg.codec_think_id, cfg.codec_think_bos_id, int(language_id), cfg.codec_think_eos_id]
+        codec = ops.gather_rows(t.codec_embedding, torch.tensor(prefill, device=dev))[None]
+        suffix = ops.gather_rows(t.codec_embedding, torch.tensor([cfg.codec_pad_id, cfg.codec_bos_id], device=dev))[None]
+        parts = [codec] + ([speaker_embed.reshape(1, 1, -1).float()] if speaker_embed is not None else []) + [suffix]
+        codec = torch.cat(parts, dim=1)
+        role = text_embed[:, :3]
+        combined = torch.cat([tts_pad.expand(1, codec.shape[1] - 2, -1), tts_bos], dim=1) + codec[:, :-1]
+        first_text = text_embed[:, 3:4] + codec[:, -1:]
+        input_embeds = torch.cat([role, combined, first_text], dim=1).contiguous()
+        trailing = torch.cat([text_embed[:, 4:-5], tts_eos], dim=1).contiguous()
+        return input_embeds, trailing, tts_pad.contiguous()
+
+    def _suppress_codec_tokens(self, eos_token_id: int):
+        """qwen3_tts.py:927-933."""
+        cfg = self.config.talker_config
+        return [i for i in range(cfg.vocab_size - 1024, cfg.vocab_size) if i != eos_token_id]
+
+    # ------------------------------------------------------------------ frame loop
+    def _frame(self, x_in: torch.Tensor, sp) -> None:
+        """One pass of the loop body qwen3_tts.py:1323-1398 for every batch row; results land in the state buffers."""
+        t, cp = self.talker, self.talker.code_predictor
+        B = x_in.shape[0]
+        g = self.config.talker_config.num_code_groups
+        logits, hidden = t(x_in, use_device_offset=True)
+        ops.sample_token(logits[:, -1], temperature=sp["temperature"], top_k=sp["top_k"], top_p=sp["top_p"], u=self._u[0],
+                         suppress_mask=self._suppress, seen=self._seen, repetition_penalty=sp["repetition_penalty"], mark_seen=True,
+                         out=self._codes[:, 0])
+        inp0 = self._cp_in0                                                                  # [B,2,H]: (hidden, embed(token 0))
+        ops.copy2d(hidden[:, -1], inp0[:, 0])
+        ops.embed_sum(self._codes[:, 0:1], self._tab0, out=inp0[:, 1], err=self._err)
+        for ci in range(g - 1):
+            if ci == 0:
+                lg = cp(inp0, 0, 0)
+            else:
+                e = ops.embed_sum(self._codes[:, ci:ci + 1], self._tab_cp[ci - 1], out=self._cp_in, err=self._err)
+                lg = cp(e[:, None], ci + 1, ci)
+            ops.sample_token(lg[:, -1], temperature=sp["temperature"], top_k=sp["top_k"], top_p=sp["top_p"], u=self._u[ci + 1],
+                             out=self._codes[:, ci + 1])
+        ops.embed_sum(self._codes, self._tabs_all, text=self._trailing, pad=self._pad, step_dev=t.offset_dev, step_sub=self._prefill_len,
+                      out=self._x_in[:, 0], err=self._err)
+
+    @torch.no_grad()
+    def generate_codes(self, input_embeds, trailing_text_hidden, tts_pad_embed, *, max_tokens: int = 4096, temperature: float = 0.9,
+                       top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, u=None, seed: int = 0,
+                       use_graph: bool = True, stop_on_eos: bool = True) -> torch.Tensor:
+        """The generation loop of Model.generate for B prompts of equal prefill length: returns int64 codes [B, n_frames, 16]
+        (B = 1: frames up to, not including, EOS; B > 1: until every row has hit EOS, rows padded with code 0 after their EOS,
+        the convention of batch_generate / batch_decode).  ``u`` [max_tokens, 16, B] uniforms in [0,1) (drawn from ``seed`` when
+        omitted; parity tests inject them)."""
+        t, cfg, dev = self.talker, self.config.talker_config, self.device
+        x = input_embeds.to(dev).float().contiguous()
+        B, P, H = x.shape
+        g, V = cfg.num_code_groups, cfg.vocab_size
+        eos = cfg.codec_eos_token_id
+        if u is None:
+            gen = torch.Generator(device=dev).manual_seed(seed)
+            u = torch.rand(max_tokens, g, B, device=dev, generator=gen)
+        u = u.to(dev).float().contiguous()
+        sp = {"temperature": float(temperature), "top_k": int(top_k), "top_p": float(top_p), "repetition_penalty": float(repetition_penalty)}
+        t.reset_cache(B, P + max_tokens + 1)
+        self._prefill_len = P
+        self._trailing = trailing_text_hidden.to(dev).float().expand(B, -1, -1).contiguous()
+        self._pad = tts_pad_embed.to(dev).float().reshape(-1).contiguous()
+        self._suppress = torch.zeros(V, device=dev)
+        self._suppress[torch.tensor(self._suppress_codec_tokens(eos), device=dev)] = float("-inf")
+        self._seen = torch.zeros(B, V, dtype=torch.uint8, device=dev)
+        self._codes = torch.zeros(B, g, dtype=torch.int64, device=dev)
+        self._u = torch.zeros(g, B, device=dev)
+        self._x_in = torch.zeros(B, 1, H, device=dev)
+        self._cp_in0 = torch.zeros(B, 2, H, device=dev)
+        self._cp_in = torch.zeros(B, H, device=dev)
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        out = torch.zeros(B, max_tokens, g, dtype=torch.int64, device=dev)
+        done = torch.zeros(B, dtype=torch.bool)
+        n = 0
+        graph = None
+        for step in range(max_tokens):
+            self._u.copy_(u[step])
+            if step == 0:
+                self._frame(x, sp)                                                   # prefill frame (S = P rows), eager
+            elif use_graph:
+                if graph is None:
+                    # warm-up on a side stream is not needed: every kernel has already run once in the prefill frame except
+                    # the S = 1 GEMV variants, which the capture below launches for the first time (lazy module load is done).
+                    torch.cuda.synchronize(dev)
+                    state = (t.offset_dev.clone(), self._seen.clone(), self._codes.clone(), self._x_in.clone())
+                    l0 = ops.LAUNCHES[0]
+                    self._frame(self._x_in, sp)                                      # eager run of the S = 1 path (loads kernels)
+                    self._frame_launches = ops.LAUNCHES[0] - l0
+                    t.offset_dev.copy_(state[0]); self._seen.copy_(state[1]); self._codes.copy_(state[2]); self._x_in.copy_(state[3])
+                    t.offset = P + step - 1
+                    torch.cuda.synchronize(dev)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        self._frame(self._x_in, sp)
+                    t.offset_dev.copy_(state[0]); self._seen.copy_(state[1]); self._codes.copy_(state[2]); self._x_in.copy_(state[3])
+                    t.offset = P + step - 1
+                graph.replay()
+                t.offset = P + step
+                ops.LAUNCHES[0] += self._frame_launches
+            else:
+                l0 = ops.LAUNCHES[0]
+                self._frame(self._x_in, sp)
+                self._frame_launches = ops.LAUNCHES[0] - l0
+            codes_h = self._codes.cpu()                                             # the per-frame sync (EOS test)
+            hit = codes_h[:, 0] == eos
+            if stop_on_eos:
+                done |= hit
+                if bool(done.all()):
+                    break
+                live = ~done
+                out[live.to(dev), n] = self._codes[live.to(dev)]
+            else:
+                out[:, n] = self._codes
+            n += 1
+        if int(self._err.item()) != 0:
+            raise ValueError("generate_codes: a sampled code indexed outside its embedding table")
+        self._graph = graph
+        return out[:, :n]
+
+    # ------------------------------------------------------------------ decode + public generate
+    @torch.no_grad()
+    def _decode_chunk(self, codes: torch.Tensor, chunk_tokens: int = 300) -> torch.Tensor:
+        """qwen3_tts.py:1017-1048: codes [1, T, 16] -> audio [samples], trimmed to the frames whose first code is > 0."""
+        chunks = list(self.speech_tokenizer.streaming_decode(codes, chunk_tokens=chunk_tokens))
+        audio = torch.cat(chunks, dim=-1)[0]
+        valid = int((codes[..., 0] > 0).sum().item()) * self.speech_tokenizer.decode_upsample_rate
+        if 0 < valid < audio.shape[0]:
+            audio = audio[:valid]
+        return audio
+
+    def generate_from_ids(self, input_ids, *, language_id=None, speaker_id=None, temperature: float = 0.9, max_tokens: int = 4096,
+                          top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, seed: int = 0, u=None, **kwargs):
+        """``Model.generate`` (qwen3_tts.py:1122-1575) for one already-tokenised segment; yields one GenerationResult."""
+        if self.speech_tokenizer is None:
+            raise ValueError("Speech tokenizer not loaded")
+        t0 = time.perf_counter()
+        x, trailing, pad = self.prepare_generation_inputs_from_ids(input_ids, language_id, speaker_id)
+        codes = self.generate_codes(x, trailing, pad, max_tokens=max_tokens, temperature=temperature, top_k=top_k, top_p=top_p,
+                                    repetition_penalty=repetition_penalty, seed=seed, u=u)
+        if codes.shape[1] == 0:
+            return
+        audio = self._decode_chunk(codes[:1])
+        torch.cuda.synchronize(self.device)
+        dt = time.perf_counter() - t0
+        samples = int(audio.shape[0])
+        dur = samples / self.sample_rate
+        yield GenerationResult(audio=audio, samples=samples, sample_rate=self.sample_rate, segment_idx=0, token_count=int(codes.shape[1]),
+                               audio_duration=format_duration(dur), real_time_factor=dur / dt if dt > 0 else 0.0,
+                               prompt={"tokens": int(codes.shape[1]), "tokens-per-sec": round(codes.shape[1] / dt, 2) if dt > 0 else 0},
+                               audio_samples={"samples": samples, "samples-per-sec": round(samples / dt, 2) if dt > 0 else 0},
+                               processing_time_seconds=dt, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
+
+    def generate(self, text: str, **kwargs):
+        """Text entry point: needs the HF tokenizer files of the checkpoint (host side, not shipped offline)."""
+        if self.tokenizer is None:
+            raise ValueError("Tokenizer not loaded. Call post_load_hook first.")         # same message as qwen3_tts.py:350-351
+        chat = f"<|im_start|>assistant\n{text}<|im_end|>\n<|im_start|>assistant\n"
+        yield from self.generate_from_ids(self.tokenizer.encode(chat), **kwargs)
