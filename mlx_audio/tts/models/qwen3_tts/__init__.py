@@ -1,0 +1,2 @@
+from mlx_audio_b200.tts.models.qwen3_tts import *  # noqa: F401,F403
+from mlx_audio_b200.tts.models.qwen3_tts import Model, ModelConfig  # noqa: F401

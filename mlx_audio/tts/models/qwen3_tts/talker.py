@@ -1,0 +1,1 @@
+from mlx_audio_b200.tts.models.qwen3_tts.talker import *  # noqa: F401,F403

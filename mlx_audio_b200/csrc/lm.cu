@@ -172,19 +172,29 @@ __global__ void qknorm_rope_cache_kernel(const QkParams p) {
   }
   // rotary: frequency slot i = (lane + 32 j) mod D/2
   float o[E];
-#pragma unroll
-  for (int j = 0; j < E / 2; j++) {
-    const int i = lane + 32 * j;                   // < D/2
+  auto cs_of = [&](int i, float& c, float& sf) {
     int axis = 0;
     if (i % 3 == 1 && i < 3 * p.sec_h) axis = 1; else if (i % 3 == 2 && i < 3 * p.sec_w) axis = 2;
     const int pos = p.pos3 ? p.pos3[((int64_t)axis * p.B + b) * p.S + s] : cpos;
     const double inv = exp2(-(double)(2 * i) / (double)D * log2((double)p.theta));
     double sn, cs;
     sincos((double)pos * inv, &sn, &cs);
-    const float c = (float)cs, sf = (float)sn;
-    const float x1 = v[j], x2 = v[j + E / 2];
-    o[j] = x1 * c - x2 * sf;                        // q*cos + rotate_half(q)*sin, first half: -x2
-    o[j + E / 2] = x2 * c + x1 * sf;
+    c = (float)cs; sf = (float)sn;
+  };
+  if constexpr (E == 1) {                          // D = 32: the partner (i, i + 16) lives in lane ^ 16
+    float c, sf;
+    cs_of(lane & 15, c, sf);
+    const float other = __shfl_xor_sync(0xffffffffu, v[0], 16);
+    o[0] = lane < 16 ? v[0] * c - other * sf : v[0] * c + other * sf;
+  } else {
+#pragma unroll
+    for (int j = 0; j < E / 2; j++) {
+      float c, sf;
+      cs_of(lane + 32 * j, c, sf);
+      const float x1 = v[j], x2 = v[j + E / 2];
+      o[j] = x1 * c - x2 * sf;                      // q*cos + rotate_half(q)*sin, first half: -x2
+      o[j + E / 2] = x2 * c + x1 * sf;
+    }
   }
   if (is_q) {
     float* dst = p.q_out + (int64_t)b * p.qo_bs + (int64_t)s * p.qo_ss + (int64_t)h * D;
@@ -234,7 +244,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AdParams 
     const float* kr = kb + (int64_t)j * p.c_ss + lane * E;
     float d = 0.f;
     if constexpr (E == 4) { float4 t = *reinterpret_cast<const float4*>(kr); d = qv[0] * t.x + qv[1] * t.y + qv[2] * t.z + qv[3] * t.w; }
-    else { float2 t = *reinterpret_cast<const float2*>(kr); d = qv[0] * t.x + qv[1] * t.y; }
+    else if constexpr (E == 2) { float2 t = *reinterpret_cast<const float2*>(kr); d = qv[0] * t.x + qv[1] * t.y; }
+    else d = qv[0] * kr[0];
     d = warp_sum(d);
     if (lane == 0) sc[j] = d;
     mloc = fmaxf(mloc, d);
@@ -259,7 +270,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AdParams 
     const float pj = sc[j];
     const float* vr = vb + (int64_t)j * p.c_ss + lane * E;
     if constexpr (E == 4) { float4 t = *reinterpret_cast<const float4*>(vr); acc[0] = fmaf(pj, t.x, acc[0]); acc[1] = fmaf(pj, t.y, acc[1]); acc[2] = fmaf(pj, t.z, acc[2]); acc[3] = fmaf(pj, t.w, acc[3]); }
-    else { float2 t = *reinterpret_cast<const float2*>(vr); acc[0] = fmaf(pj, t.x, acc[0]); acc[1] = fmaf(pj, t.y, acc[1]); }
+    else if constexpr (E == 2) { float2 t = *reinterpret_cast<const float2*>(vr); acc[0] = fmaf(pj, t.x, acc[0]); acc[1] = fmaf(pj, t.y, acc[1]); }
+    else acc[0] = fmaf(pj, vr[0], acc[0]);
   }
   __syncthreads();                                  // scores no longer needed: reuse the buffer for the partials
   float* part = sc;                                 // [NW][D]  (max_k >= NW*D/... guaranteed by the host: smem >= NW*D floats)
@@ -334,14 +346,15 @@ extern "C" int32_t b2a_qknorm_rope_cache(const float* qkv, int64_t qkv_bs, int64
                                          const int32_t* pos3, const int32_t* base_dev, int32_t base_host, int32_t sec_h,
                                          int32_t sec_w, float theta, float* q_out, int64_t qo_bs, int64_t qo_ss, float* k_cache,
                                          float* v_cache, int64_t c_bs, int64_t c_ss, int32_t smax, void* stream) {
-  B2A_CHECK_ARG(D == 64 || D == 128, "head_dim must be 64 or 128");
+  B2A_CHECK_ARG(D == 32 || D == 64 || D == 128, "head_dim must be 32, 64 or 128");
   B2A_CHECK_ARG(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "bad shape");
   QkParams p{qkv, qkv_bs, qkv_ss, B, S, Hq, Hkv, D, q_norm_w, k_norm_w, eps, pos3, base_dev, base_host, sec_h, sec_w, theta,
              q_out, qo_bs, qo_ss, k_cache, v_cache, c_bs, c_ss, smax};
   const int64_t warps = (int64_t)B * S * (Hq + 2 * Hkv);
   const int grid = (int)((warps * 32 + 255) / 256);
   if (D == 128) qknorm_rope_cache_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  else qknorm_rope_cache_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else if (D == 64) qknorm_rope_cache_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  else qknorm_rope_cache_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
@@ -350,7 +363,7 @@ extern "C" int32_t b2a_attn_decode(const float* q, int64_t q_bs, int64_t q_ss, c
                                    int64_t c_bs, int64_t c_ss, float* out, int64_t o_bs, int64_t o_ss, int32_t B, int32_t S,
                                    int32_t Hq, int32_t Hkv, int32_t D, float scale, const int32_t* base_dev, int32_t base_host,
                                    const int32_t* kv_start, int32_t max_k, void* stream) {
-  B2A_CHECK_ARG(D == 64 || D == 128, "head_dim must be 64 or 128");
+  B2A_CHECK_ARG(D == 32 || D == 64 || D == 128, "head_dim must be 32, 64 or 128");
   B2A_CHECK_ARG(B > 0 && S > 0 && Hq % Hkv == 0 && max_k > 0 && max_k <= 48 * 1024, "bad shape (max_k <= 49152)");
   B2A_CHECK_ARG(c_ss % 4 == 0 && c_bs % 4 == 0 && ((uintptr_t)k_cache & 15) == 0 && ((uintptr_t)v_cache & 15) == 0, "cache rows must be 16-byte aligned");
   AdParams p{q, q_bs, q_ss, k_cache, v_cache, c_bs, c_ss, out, o_bs, o_ss, B, S, Hq, Hkv, scale, base_dev, base_host, kv_start, max_k};
@@ -362,9 +375,12 @@ extern "C" int32_t b2a_attn_decode(const float* q, int64_t q_bs, int64_t q_ss, c
   if (D == 128) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attn_decode_kernel<128><<<grid, AD_THREADS, sm, st>>>(p);
-  } else {
+  } else if (D == 64) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attn_decode_kernel<64><<<grid, AD_THREADS, sm, st>>>(p);
+  } else {
+    if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attn_decode_kernel<32><<<grid, AD_THREADS, sm, st>>>(p);
   }
   B2A_CHECK_LAUNCH();
   return B2A_OK;

@@ -32,15 +32,44 @@ def format_duration(seconds: float) -> str:
     return f"{hours:02d}:{minutes:02d}:{secs:02d}.{ms:03d}"
 
 
+def mel_spectrogram(audio, n_fft: int = 1024, num_mels: int = 128, sample_rate: int = 24000, hop_size: int = 256,
+                    win_size: int = 1024, fmin: float = 0.0, fmax: float = 12000.0, device="cuda") -> torch.Tensor:
+    """qwen3_tts.py:64-120 (speaker-encoder front end): manual reflect pad of (n_fft-hop)/2, STFT (center=False, Hann),
+    sqrt(|X|^2 + 1e-9) @ slaney-mel^T, log(clip(., 1e-5)).  [n] or [B, n] -> [B, frames, num_mels]; the batch is one STFT launch."""
+    from .... import dsp
+    a = torch.as_tensor(audio, dtype=torch.float32, device=device)
+    if a.dim() == 1:
+        a = a[None]
+    pad = (n_fft - hop_size) // 2
+    a = torch.cat([a[:, 1:pad + 1].flip(1), a, a[:, -(pad + 1):-1].flip(1)], dim=1)
+    spec = dsp.stft(a, n_fft=n_fft, hop_length=hop_size, win_length=win_size, window="hann", center=False, pad_mode="reflect", device=device)
+    mag = torch.sqrt(spec.real ** 2 + spec.imag ** 2 + 1e-9)
+    basis = dsp.mel_filters(sample_rate=sample_rate, n_fft=n_fft, n_mels=num_mels, f_min=fmin, f_max=fmax, norm="slaney", mel_scale="slaney")
+    basis = torch.as_tensor(basis, dtype=torch.float32, device=a.device)
+    cw = ops.pack_linear(basis, None, a.device)
+    mel = ops.linear(mag.contiguous(), cw)
+    return torch.log(torch.clamp(mel, min=1e-5))
+
+
 class Model:
     def __init__(self, config: ModelConfig, device="cuda"):
         self.config = config
         self.device = torch.device(device)
         self.talker = Qwen3TTSTalkerForConditionalGeneration(config.talker_config, device)
+        self.speaker_encoder = None          # ECAPA-TDNN voice cloning: SURVEY.md section 8f "next"
         self.speech_tokenizer: Optional[Qwen3TTSSpeechTokenizer] = None
         self.tokenizer = None
+        self.generate_config = None
+        tc = config.talker_config
+        self.supported_speakers = list(tc.spk_id.keys()) if tc.spk_id else []
+        self.supported_languages = ["auto"] + [l for l in (tc.codec_language_id or {}) if "dialect" not in l]
         self._graph = None
-        self._graph_key = None
+
+    def get_supported_speakers(self):
+        return self.supported_speakers
+
+    def get_supported_languages(self):
+        return self.supported_languages
 
     @property
     def sample_rate(self) -> int:
@@ -50,8 +79,9 @@ class Model:
     def model_type(self) -> str:
         return self.config.model_type
 
-    def load_weights(self, weights):
-        """``weights`` with the checkpoint's ``talker.`` prefix (sanitized here, qwen3_tts.py:2914-2925)."""
+    def load_weights(self, weights, strict: bool = True):
+        """``weights`` (dict or list of pairs) with the checkpoint's ``talker.`` prefix (stripped here, talker.py:825-839)."""
+        weights = dict(weights)
         self.talker.load_weights(self.talker.sanitize(weights))
         t = self.talker
         self._tabs_all = ops.EmbedTables([t.codec_embedding] + t.code_predictor.codec_embedding)
@@ -62,9 +92,62 @@ class Model:
     def load_speech_tokenizer(self, speech_tokenizer: Qwen3TTSSpeechTokenizer):
         self.speech_tokenizer = speech_tokenizer
 
+    def load_generate_config(self, generate_config: dict):
+        self.generate_config = generate_config
+
+    def eval(self):
+        return self
+
+    @staticmethod
+    def sanitize(weights):
+        """qwen3_tts.py:2914-2935: drop ``position_ids``; conv weights [out, in, K] -> [out, K, in] unless already MLX-layout."""
+        from .speech_tokenizer import check_array_shape_qwen3
+        out = {}
+        for k, v in weights.items():
+            if "position_ids" in k:
+                continue
+            if ("conv" in k or "speaker_encoder.fc" in k) and "weight" in k and v.dim() == 3:
+                v = v if check_array_shape_qwen3(v) else v.permute(0, 2, 1)
+            out[k] = v
+        return out
+
+    @classmethod
+    def post_load_hook(cls, model: "Model", model_path):
+        """qwen3_tts.py:2818-2911: HF tokenizer (when its files are present), ``speech_tokenizer/`` sub-model, generation config."""
+        import json
+        from pathlib import Path
+        from .config import Qwen3TTSTokenizerConfig, Qwen3TTSTokenizerDecoderConfig, filter_dict_for_dataclass
+        model_path = Path(model_path)
+        try:
+            from transformers import AutoTokenizer
+            model.tokenizer = AutoTokenizer.from_pretrained(str(model_path))
+        except Exception as e:                                           # same behaviour as the reference: warn and continue
+            print(f"Warning: Could not load tokenizer: {e}")
+        st_path = model_path / "speech_tokenizer"
+        if st_path.exists():
+            from safetensors.torch import load_file
+            d = json.load(open(st_path / "config.json"))
+            dec = Qwen3TTSTokenizerDecoderConfig(**filter_dict_for_dataclass(Qwen3TTSTokenizerDecoderConfig, d["decoder_config"])) \
+                if "decoder_config" in d else None
+            tc = Qwen3TTSTokenizerConfig(decoder_config=dec)
+            for k, v in d.items():
+                if k not in ("decoder_config", "encoder_config") and hasattr(tc, k):
+                    setattr(tc, k, v)
+            w = {}
+            for wf in sorted(st_path.glob("*.safetensors")):
+                w.update(load_file(str(wf)))
+            if w:
+                st = Qwen3TTSSpeechTokenizer(tc, model.device).load_weights(Qwen3TTSSpeechTokenizer.sanitize(w))
+                model.load_speech_tokenizer(st)
+        gen = model_path / "generation_config.json"
+        if gen.exists():
+            model.load_generate_config(json.load(open(gen)))
+        return model
+
     # ------------------------------------------------------------------ input assembly
     @torch.no_grad()
-    def prepare_generation_inputs_from_ids(self, input_ids, language_id: Optional[int] = None, speaker_id=None, speaker_embed=None):
+    def prepare_generation_inputs_from_ids(self, input_ids, language_id: Optional[int] = None, speaker_id=None, speaker_embed=None,
+                                           instruct_ids=None):
         """qwen3_tts.py:326-484 after tokenisation: ``input_ids`` = tokenizer.encode("<|im_start|>assistant\\n{text}<|im_end|>\\n
         <|im_start|>assistant\\n").  Returns (input_embeds [1,P,H], trailing_text_hidden [1,n,H], tts_pad_embed [1,1,H])."""
         t, cfg, dev = self.talker, self.config.talker_config, self.device
@@ -86,9 +169,34 @@ class Model:
         role = text_embed[:, :3]
         combined = torch.cat([tts_pad.expand(1, codec.shape[1] - 2, -1), tts_bos], dim=1) + codec[:, :-1]
         first_text = text_embed[:, 3:4] + codec[:, -1:]
-        input_embeds = torch.cat([role, combined, first_text], dim=1).contiguous()
+        parts = [role, combined, first_text]
+        if instruct_ids is not None:                                      # "<|im_start|>user\n{instruct}<|im_end|>\n" (:452-458,473-476)
+            iid = torch.as_tensor(instruct_ids, dtype=torch.int64, device=dev).reshape(-1)
+            parts = [t.text_projection(ops.gather_rows(t.text_embedding, iid)[None])] + parts
+        input_embeds = torch.cat(parts, dim=1).contiguous()
         trailing = torch.cat([text_embed[:, 4:-5], tts_eos], dim=1).contiguous()
         return input_embeds, trailing, tts_pad.contiguous()
+
+    def _prepare_generation_inputs(self, text: str, language: str = "auto", speaker: Optional[str] = None, instruct: Optional[str] = None):
+        """qwen3_tts.py:326-484: tokenise with the chat template, resolve speaker / language / dialect ids from the config."""
+        if self.tokenizer is None:
+            raise ValueError("Tokenizer not loaded. Call post_load_hook first.")
+        cfg = self.config.talker_config
+        ids = self.tokenizer.encode(f"<|im_start|>assistant\n{text}<|im_end|>\n<|im_start|>assistant\n")
+        speaker_id = None
+        if speaker and speaker.lower() in (cfg.spk_id or {}):
+            sid = cfg.spk_id[speaker.lower()]
+            speaker_id = sid[0] if isinstance(sid, (list, tuple)) else sid
+        language_id = None
+        if language.lower() != "auto" and cfg.codec_language_id and language.lower() in cfg.codec_language_id:
+            language_id = cfg.codec_language_id[language.lower()]
+        if language.lower() in ("chinese", "auto") and speaker and speaker.lower() in (cfg.spk_is_dialect or {}) \
+                and cfg.spk_is_dialect[speaker.lower()]:
+            dialect = cfg.spk_is_dialect[speaker.lower()]
+            if dialect in (cfg.codec_language_id or {}):
+                language_id = cfg.codec_language_id[dialect]
+        instruct_ids = self.tokenizer.encode(f"<|im_start|>user\n{instruct}<|im_end|>\n") if instruct else None
+        return self.prepare_generation_inputs_from_ids(ids, language_id, speaker_id, instruct_ids=instruct_ids)
 
     def _suppress_codec_tokens(self, eos_token_id: int):
         """qwen3_tts.py:927-933."""
@@ -231,9 +339,52 @@ class Model:
                                audio_samples={"samples": samples, "samples-per-sec": round(samples / dt, 2) if dt > 0 else 0},
                                processing_time_seconds=dt, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
 
-    def generate(self, text: str, **kwargs):
-        """Text entry point: needs the HF tokenizer files of the checkpoint (host side, not shipped offline)."""
-        if self.tokenizer is None:
-            raise ValueError("Tokenizer not loaded. Call post_load_hook first.")         # same message as qwen3_tts.py:350-351
-        chat = f"<|im_start|>assistant\n{text}<|im_end|>\n<|im_start|>assistant\n"
-        yield from self.generate_from_ids(self.tokenizer.encode(chat), **kwargs)
+    def _generate_segments(self, text, split_pattern, speaker, language, instruct, **gen):
+        if self.speech_tokenizer is None:
+            raise ValueError("Speech tokenizer not loaded")
+        segments = [t for t in (text.split(split_pattern) if split_pattern else [text]) if t.strip()]
+        for idx, seg in enumerate(segments):
+            t0 = time.perf_counter()
+            x, trailing, pad = self._prepare_generation_inputs(seg, language=language, speaker=speaker, instruct=instruct)
+            codes = self.generate_codes(x, trailing, pad, **gen)
+            if codes.shape[1] == 0:
+                continue
+            audio = self._decode_chunk(codes[:1])
+            torch.cuda.synchronize(self.device)
+            dt = time.perf_counter() - t0
+            samples = int(audio.shape[0])
+            dur = samples / self.sample_rate
+            yield GenerationResult(audio=audio, samples=samples, sample_rate=self.sample_rate, segment_idx=idx, token_count=int(codes.shape[1]),
+                                   audio_duration=format_duration(dur), real_time_factor=dur / dt if dt > 0 else 0.0,
+                                   prompt={"tokens": int(codes.shape[1]), "tokens-per-sec": round(codes.shape[1] / dt, 2) if dt > 0 else 0},
+                                   audio_samples={"samples": samples, "samples-per-sec": round(samples / dt, 2) if dt > 0 else 0},
+                                   processing_time_seconds=dt, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
+
+    def generate(self, text: str, voice: Optional[str] = None, instruct: Optional[str] = None, temperature: float = 0.9, speed: float = 1.0,
+                 lang_code: str = "auto", ref_audio=None, ref_text: Optional[str] = None, split_pattern: str = "\n", max_tokens: int = 4096,
+                 verbose: bool = False, stream: bool = False, streaming_interval: float = 2.0, top_k: int = 50, top_p: float = 1.0,
+                 repetition_penalty: float = 1.05, seed: int = 0, **kwargs):
+        """Model.generate (qwen3_tts.py:1122-1575): routes on ``tts_model_type`` exactly as the reference (same errors)."""
+        gen = dict(max_tokens=max_tokens, temperature=temperature, top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty, seed=seed)
+        kind = getattr(self.config, "tts_model_type", "base")
+        if kind == "voice_design":
+            if not instruct:
+                raise ValueError("VoiceDesign model requires 'instruct' to describe the voice "
+                                 "(e.g., 'A cheerful young female voice with high pitch')")
+            yield from self._generate_segments(text, split_pattern, None, lang_code, instruct, **gen)
+            return
+        if kind == "custom_voice":
+            if not voice:
+                raise ValueError(f"CustomVoice model requires 'voice' (speaker name) (e.g., {self.supported_speakers})")
+            if voice.lower() not in [s.lower() for s in self.supported_speakers]:
+                raise ValueError(f"Speaker '{voice}' not supported. Available: {self.supported_speakers}")
+            yield from self._generate_segments(text, split_pattern, voice, lang_code, instruct, **gen)
+            return
+        if self.speech_tokenizer is None:
+            raise ValueError("Speech tokenizer not loaded")
+        if ref_audio is not None and ref_text is not None:
+            raise NotImplementedError("ICL voice cloning needs the speech-tokenizer encoder + speaker encoder (SURVEY.md section 8f 'next')")
+        if voice is not None and voice.lower() not in [s.lower() for s in self.supported_speakers]:
+            raise ValueError(f"Voice '{voice}' is not supported by this Base model. Base models have no built-in preset voices — "
+                             "clone a voice by passing ref_audio and ref_text instead.")
+        yield from self._generate_segments(text, split_pattern, voice, lang_code, None, **gen)

@@ -15,7 +15,7 @@ import torch
 
 from .dsp import STR_TO_WINDOW_FN, ISTFTCache, bartlett, blackman, hamming, hanning, istft, mel_filters, stft  # noqa: F401 (utils.py:31-40 re-exports)
 
-MODEL_REMAPPING = {"tts": {"kokoro": "kokoro"}, "stt": {"whisper": "whisper"}}
+MODEL_REMAPPING = {"tts": {"kokoro": "kokoro", "qwen3_tts": "qwen3_tts"}, "stt": {"whisper": "whisper"}}
 
 
 def get_model_path(path_or_repo: str, **_) -> Path:

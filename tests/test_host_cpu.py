@@ -177,3 +177,52 @@ def test_drop_in_import_surface_and_loader(tmp_path):
     assert model.sample_rate == 24000 and model._w is not None and model.vocab == {"a": 1}
     assert model._w["ups"][0].w.shape == (20, 512, 256)                    # ConvTranspose 512->256 k20 packed [K, Cin, Cout]
     assert all(torch.equal(model.parameters()[k].float(), P[k]) for k in P)  # sanitize inverted the torch layout exactly
+
+
+def test_kvcache_contract():
+    """lm/models/cache.py:104-176: 256-row growth, offset bookkeeping, prefix views, trim."""
+    import torch
+    from mlx_audio.lm.models.cache import KVCache
+    c = KVCache()
+    assert c.empty() and c.offset == 0 and c.nbytes == 0
+    k1, v1 = torch.randn(1, 2, 3, 8), torch.randn(1, 2, 3, 4)
+    k, v = c.update_and_fetch(k1, v1)
+    assert k.shape == (1, 2, 3, 8) and v.shape == (1, 2, 3, 4) and c.keys.shape[2] == 256 and c.offset == 3
+    big = torch.randn(1, 2, 300, 8)
+    k, v = c.update_and_fetch(big, torch.randn(1, 2, 300, 4))
+    assert c.offset == 303 and k.shape[2] == 303 and c.keys.shape[2] == 3 + 512          # prev%step != 0: trimmed to prev, then 2 new blocks
+    assert torch.equal(k[:, :, :3], k1) and torch.equal(k[:, :, 3:], big)
+    assert c.trim(1000) == 303 and c.offset == 0 and c.is_trimmable()
+    c.state = (k1, v1)
+    assert c.offset == 3 and c.size() == 3
+
+
+def test_qwen3_config_and_routing_contract():
+    """tts/tests/test_models.py:2152-2400 (TestQwen3TTSModel) restated for the parts that need no GPU: config parsing, speaker /
+    language lists, shape heuristic of sanitize."""
+    import torch
+    from mlx_audio.tts.models.qwen3_tts.config import ModelConfig, Qwen3TTSTokenizerDecoderConfig
+    from mlx_audio.tts.models.qwen3_tts.speech_tokenizer import Qwen3TTSSpeechTokenizer, check_array_shape_qwen3
+    talker = {"vocab_size": 32, "hidden_size": 64, "intermediate_size": 128, "num_hidden_layers": 1, "num_attention_heads": 2,
+              "num_key_value_heads": 1, "head_dim": 32, "num_code_groups": 4, "text_hidden_size": 64, "text_vocab_size": 100,
+              "codec_eos_token_id": 30, "codec_pad_id": 28, "codec_bos_id": 29, "codec_language_id": {"english": 20, "chinese": 21},
+              "spk_id": {"chelsie": 10, "ethan": 11}, "attention_dropout": 0.0,
+              "code_predictor_config": {"vocab_size": 32, "hidden_size": 64, "intermediate_size": 128, "num_hidden_layers": 1,
+                                        "num_attention_heads": 2, "num_key_value_heads": 1, "head_dim": 32, "num_code_groups": 4}}
+    for kind in ("base", "custom_voice", "voice_design"):
+        cfg = ModelConfig.from_dict({"model_type": "qwen3_tts", "tts_model_type": kind, "tts_model_size": "0b6", "talker_config": talker,
+                                     "speaker_encoder_config": None, "tokenizer_config": None, "sample_rate": 24000})
+        assert cfg.model_type == "qwen3_tts" and cfg.tts_model_type == kind and cfg.sample_rate == 24000
+        assert cfg.talker_config.code_predictor_config.head_dim == 32 and cfg.talker_config.vocab_size == 32
+    d = Qwen3TTSTokenizerDecoderConfig()
+    assert (d.upsample_rates, d.upsampling_ratios, d.num_quantizers, d.codebook_size) == ([8, 5, 4, 3], [2, 2], 16, 2048)
+    assert check_array_shape_qwen3(torch.zeros(8, 3, 16)) and not check_array_shape_qwen3(torch.zeros(8, 16, 3))
+    assert check_array_shape_qwen3(torch.zeros(8, 1, 128)) and not check_array_shape_qwen3(torch.zeros(8, 128, 1))
+    w = {"decoder.pre_conv.conv.weight": torch.zeros(8, 16, 3), "decoder.upsample.0.0.conv.weight": torch.zeros(16, 8, 2),
+         "decoder.quantizer.rvq_first.vq.layers.0._codebook.cluster_usage": torch.tensor([2.0, 0.0]),
+         "decoder.quantizer.rvq_first.vq.layers.0._codebook.embedding_sum": torch.tensor([[2.0, 4.0], [1.0, 1.0]]),
+         "encoder.anything": torch.zeros(1)}
+    s = Qwen3TTSSpeechTokenizer.sanitize(w)
+    assert s["decoder.pre_conv.conv.weight"].shape == (8, 3, 16) and s["decoder.upsample.0.0.conv.weight"].shape == (8, 2, 16)
+    emb = s["decoder.quantizer.rvq_first.vq.layers.0.codebook.embed.weight"]
+    assert emb[0].tolist() == [1.0, 2.0] and abs(float(emb[1, 0]) - 1e5) < 1.0 and "encoder.anything" not in s

@@ -1,6 +1,7 @@
 """Pin the CPU oracle against every known-answer vector the reference's own tests hold
 for the hot path.  Expected values are copied from the cited
 reference tests (data, not code)."""
+import math
 import numpy as np
 import pytest
 
@@ -118,3 +119,91 @@ def test_stft_errors_match_reference_messages():
         O.stft(np.zeros(1000), window="nope")
     with pytest.raises(ValueError, match="Input is too short"):
         O.stft(np.zeros(10), n_fft=400, center=False)
+
+
+# ------------------------------------------------------------------------------------------------ Qwen3-TTS oracle pins
+def _small_tokenizer_cfg():
+    from oracle import qwen3 as Q
+    return dict(Q.TOKENIZER_DECODER, latent_dim=64, codebook_dim=32, codebook_size=64, decoder_dim=48, hidden_size=32, intermediate_size=64,
+                head_dim=16, num_attention_heads=2, num_key_value_heads=2, num_hidden_layers=2)
+
+
+def test_qwen3_interleaved_mrope_pattern():
+    """talker.py:139-184: slot i rotates with the H position iff i%3==1 and i<60, with W iff i%3==2 and i<60, else T
+    (sections [24,20,20] on 64 frequency slots) -- checked against the angle each slot actually receives."""
+    import torch
+    from oracle import qwen3 as Q
+    pos3 = torch.tensor([[[1]], [[10]], [[100]]])
+    cos, sin = Q.mrope_cos_sin(pos3, 128, 1e6, [24, 20, 20])
+    inv = 1.0 / (1e6 ** (torch.arange(0, 128, 2, dtype=torch.float64) / 128))
+    ang = torch.atan2(sin[0, 0, :64], cos[0, 0, :64])
+    for i in range(64):
+        want = 10 if (i % 3 == 1 and i < 60) else (100 if (i % 3 == 2 and i < 60) else 1)
+        a = want * float(inv[i])
+        assert abs(math.remainder(float(ang[i]) - a, 2 * math.pi)) < 1e-9, i
+    assert torch.equal(cos[..., :64], cos[..., 64:])                   # emb = concat(freqs, freqs) (talker.py:220)
+    c2, s2 = Q.mrope_cos_sin(torch.tensor([[7]]), 128, 1e6, [24, 20, 20])
+    c1, s1 = Q.rope_cos_sin(torch.tensor([[7]]), 128, 1e6)
+    assert torch.allclose(c1, c2) and torch.allclose(s1, s2)            # equal positions on the three axes = plain RoPE
+
+
+def test_qwen3_sampler_filters_hand_cases():
+    """lm/sample_utils.py:131-239 on logits whose answer is computable by hand."""
+    import torch
+    from oracle import qwen3 as Q
+    lg = torch.log(torch.tensor([0.1, 0.2, 0.3, 0.4], dtype=torch.float64))
+    assert torch.isinf(Q.apply_top_k(lg, 2)).tolist() == [True, True, False, False]
+    # ascending cumulative probs 0.1, 0.3, 0.6, 1.0: keep those > 1 - top_p
+    assert torch.isinf(Q.apply_top_p(lg, 0.5)).tolist() == [True, True, False, False]
+    assert torch.isinf(Q.apply_top_p(lg, 0.75)).tolist() == [True, False, False, False]
+    assert torch.isinf(Q.apply_min_p(lg, 0.6)).tolist() == [True, True, False, False]     # p < 0.6 * 0.4 removed
+    # inverse CDF in index order: u*1.0 against cumulative 0.1, 0.3, 0.6, 1.0
+    picks = [Q.sample_token(lg, u, temperature=1.0, top_k=0, top_p=1.0, repetition_penalty=1.0) for u in (0.05, 0.25, 0.59, 0.61, 0.999)]
+    assert picks == [0, 1, 2, 3, 3]
+    # sign-aware repetition penalty on the SET of generated ids (qwen3_tts.py:830-842), greedy
+    lg2 = torch.tensor([2.0, 1.9, -1.0, -3.0], dtype=torch.float64)
+    assert Q.sample_token(lg2, 0.0, temperature=0.0, repetition_penalty=1.2, generated_tokens=[0, 0, 0]) == 1     # 2.0/1.2 < 1.9
+    tok, f = Q.sample_token(lg2, 0.0, temperature=0.0, repetition_penalty=2.0, generated_tokens=[2, 7], return_filtered=True)
+    assert tok == 0 and float(f[2]) == -2.0                                    # negative logits are multiplied; id 7 >= V ignored
+    assert Q.sample_token(lg2, 0.0, temperature=0.0, suppress_tokens=[0]) == 1
+
+
+def test_qwen3_vocoder_is_causal_and_1920_per_frame():
+    """speech_tokenizer.py:843-880,932-954: 1920 samples per code frame; every layer is causal, so decoding a prefix gives the
+    prefix of the full decode, and chunked_decode with unlimited left context reproduces the one-shot decode."""
+    import torch
+    from mlx_audio_b200 import synth
+    from oracle import qwen3 as Q
+    cfg = _small_tokenizer_cfg()
+    P = {k: v.double() for k, v in synth.qwen3_tokenizer_weights(cfg, seed=3).items()}
+    codes = synth.qwen3_codes(cfg, 11, batch=2, seed=4)
+    full = Q.tokenizer_decode(P, codes, cfg)
+    assert full.shape == (2, 1, 11 * 1920) and float(full.abs().max()) <= 1.0
+    part = Q.tokenizer_decode(P, codes[..., :7], cfg)
+    assert float((part - full[..., :7 * 1920]).abs().max()) < 1e-12
+    chunked = Q.chunked_decode(P, codes, chunk_size=4, left_context_size=100, cfg=cfg)
+    assert chunked.shape == full.shape and float((chunked - full).abs().max()) < 1e-12
+    wav, lengths = Q.speech_tokenizer_decode(P, codes.transpose(1, 2), cfg)
+    assert wav.shape == (2, 11 * 1920) and lengths.tolist() == [11 * 1920, 11 * 1920]
+    with pytest.raises(ValueError, match="Expected 16 layers of codes"):
+        Q.tokenizer_decode(P, codes[:, :8], cfg)
+
+
+def test_qwen3_frame_loop_contract():
+    """qwen3_tts.py:1323-1404 on a tiny talker: rows are [first code, 15 predictor codes]; first codes never come from the
+    suppressed top-1024 range; greedy decoding is independent of the uniforms; EOS ends the loop without emitting its frame."""
+    import torch
+    from mlx_audio_b200 import synth
+    from oracle import qwen3 as Q
+    cfg = dict(Q.TALKER, num_hidden_layers=1, cp_num_hidden_layers=1)
+    P = {k[len("talker."):]: v.double() for k, v in synth.qwen3_talker_weights(cfg, seed=5).items()}
+    g = torch.Generator().manual_seed(0)
+    x, tr, pad = (torch.randn(1, n, 1024, generator=g, dtype=torch.float64) for n in (6, 2, 1))
+    u = torch.rand(5, 16, generator=g, dtype=torch.float64)
+    codes = Q.generate_codes(P, x, tr, pad, u, 5, cfg=cfg)
+    assert codes.shape == (5, 16) and int(codes[:, 0].max()) < 2048 and int(codes[:, 1:].max()) < 2048
+    g1 = Q.generate_codes(P, x, tr, pad, u, 4, temperature=0.0, cfg=cfg)
+    g2 = Q.generate_codes(P, x, tr, pad, torch.rand(4, 16, dtype=torch.float64), 4, temperature=0.0, cfg=cfg)
+    assert torch.equal(g1, g2)
+    stop = Q.generate_codes(P, x, tr, pad, u, 5, cfg=dict(cfg, codec_eos_token_id=int(codes[2, 0])))
+    assert stop.shape[0] == 2 and torch.equal(stop, codes[:2])
