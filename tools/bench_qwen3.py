@@ -13,6 +13,7 @@ ap.add_argument("--frames", type=int, default=100)
 ap.add_argument("--batches", default="1,8")
 ap.add_argument("--voc-frames", type=int, default=3000)
 ap.add_argument("--which", default="talker,vocoder")
+ap.add_argument("--eager", action="store_true", help="no CUDA graph (for ncu launch lists)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 pk = os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")
@@ -32,11 +33,11 @@ if "talker" in args.which:
     model.config.talker_config.codec_eos_token_id = 3071        # suppressed id: never sampled, the loop runs to max_tokens
     for B in [int(b) for b in args.batches.split(",")]:
         xb = x.expand(B, -1, -1).contiguous()
-        model.generate_codes(xb, trailing, pad, max_tokens=8, seed=1)           # warm-up (loads kernels, captures once)
+        model.generate_codes(xb, trailing, pad, max_tokens=8, seed=1, use_graph=not args.eager)           # warm-up (loads kernels, captures once)
         torch.cuda.synchronize()
         ops.LAUNCHES[0] = 0
         t0 = time.perf_counter()
-        codes = model.generate_codes(xb, trailing, pad, max_tokens=args.frames, seed=2)
+        codes = model.generate_codes(xb, trailing, pad, max_tokens=args.frames, seed=2, use_graph=not args.eager)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         n = codes.shape[1]
