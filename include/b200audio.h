@@ -141,6 +141,11 @@ typedef struct {
   const int32_t* k_len;     /* [B] valid key count or NULL */
 } b2a_attn_t;
 int32_t b2a_attention(const b2a_attn_t* p, void* stream);
+/* Same contract on the tensor cores (tcgen05) for D == 64, H == Hkv, k_len == NULL: S = QK^T and PV as fp16 hi/lo-plane MMAs
+ * (fp32-grade products), online softmax with one thread per query row.  ws: device scratch of b2a_attention_tc_ws_bytes bytes
+ * (fp16 planes of q, k and the transposed v). */
+int64_t b2a_attention_tc_ws_bytes(int32_t B, int32_t H, int32_t Tq, int32_t Tk);
+int32_t b2a_attention_tc(const b2a_attn_t* p, void* ws, void* stream);
 /* in-place rotary embedding on x [B,T,H,D] (token stride ld): traditional != 0 rotates pairs (2i,2i+1)
  * (nn.RoPE(traditional=True), mimi/modules/transformer.py:75-77), else (i, i+D/2) (talker.py:14-18). */
 int32_t b2a_rope(float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t T, int32_t H, int32_t D,

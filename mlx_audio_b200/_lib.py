@@ -59,6 +59,8 @@ PROTOTYPES = {
     "b2a_adain_coeffs": (i32, [c_f, i64, i64, i32, i32, i32, c_f, f32, c_f, c_f, c_f, C.c_void_p]),
     "b2a_layernorm": (i32, [c_f, i64, c_f, i64, c_f, i64, i64, i32, c_f, c_f, c_f, f32, i32, i32, f32, C.c_void_p]),
     "b2a_attention": (i32, [C.POINTER(AttnParams), C.c_void_p]),
+    "b2a_attention_tc_ws_bytes": (i64, [i32, i32, i32, i32]),
+    "b2a_attention_tc": (i32, [C.POINTER(AttnParams), C.c_void_p, C.c_void_p]),
     "b2a_rope": (i32, [c_f, i64, i64, i32, i32, i32, i32, i32, f32, i32, C.c_void_p]),
     "b2a_lstm_bidir": (i32, [c_f, c_f, c_f, i64, i32, i32, i32, C.c_void_p]),
     "b2a_stft": (i32, [c_f, i64, i32, i64, c_f, i32, i32, i32, i64, c_f, c_f, C.c_void_p]),

@@ -154,6 +154,41 @@ struct SampleParams {
   float* filtered;                        // [B,V] optional: the filtered logits the draw is made from (tests)
 };
 
+// categorical draw from the filtered logits lg[0..V) (index order, -inf = removed): inverse CDF with the supplied uniform, done by
+// warp 0 in float64 over 32 contiguous chunks.  gm = max of lg.
+__device__ __forceinline__ void draw_inverse_cdf(const SampleParams& p, const float* lg, int V, int b, float gm) {
+  const float NEG = -INFINITY;
+  const int tid = threadIdx.x;
+  const float* s_scan = lg;
+  if (tid < 32) {
+    const int lane = tid, per = (V + 31) / 32, lo = lane * per, hi = min(V, lo + per);
+    double sum = 0.0; int lastlive = -1;
+    for (int v = lo; v < hi; v++) if (s_scan[v] > NEG) { sum += exp((double)(s_scan[v] - gm)); lastlive = v; }
+    double inc = sum;
+    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    const double z = __shfl_sync(0xffffffffu, inc, 31);
+    const double target = (double)p.u[b] * z;
+    int glast = lastlive;
+    for (int o = 16; o > 0; o >>= 1) glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, o));
+    const unsigned ball = __ballot_sync(0xffffffffu, inc > target);
+    int pick = -1;
+    if (ball) {
+      const int L = __ffs(ball) - 1;
+      if (lane == L) {
+        double run = inc - sum;
+        pick = lastlive;
+        for (int v = lo; v < hi; v++) if (s_scan[v] > NEG) { run += exp((double)(s_scan[v] - gm)); if (run > target) { pick = v; break; } }
+      }
+      pick = __shfl_sync(0xffffffffu, pick, L);
+    } else pick = glast;
+    if (lane == 0) {
+      if (pick < 0) pick = 0;
+      p.out[(int64_t)b * p.out_stride] = pick;
+      if (p.mark_seen && p.seen) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
   __shared__ float sv[SV];
   __shared__ unsigned short si[SV];               // indices < 4096 fit 16 bits (keeps static shared memory under 48 KB)
@@ -188,6 +223,82 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
   const float inv_t = 1.f / p.temperature;
   for (int v = tid; v < SV; v += blockDim.x) { sv[v] = v < V ? base(v) * inv_t : NEG; si[v] = v; }
   __syncthreads();
+  const bool filters_p = (p.top_p > 0.f && p.top_p < 1.f) || p.min_p > 0.f;
+  if (!filters_p) {
+    // ---- fast path (the Qwen3 defaults: top-k only): k-th largest by a 4-pass radix select on order-preserving keys, ties by
+    // lowest index, instead of sorting all V logits.
+    __shared__ unsigned hist[256];
+    __shared__ unsigned sel_prefix, sel_remaining;
+    __shared__ unsigned wcnt[32];
+    auto keyof = [](float x) -> unsigned { unsigned u = __float_as_uint(x); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); };
+    const bool use_k = p.top_k > 0 && p.top_k < V;
+    if (use_k) {
+      if (tid == 0) { sel_prefix = 0u; sel_remaining = (unsigned)p.top_k; }
+      for (int pass = 0; pass < 4; pass++) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) hist[tid] = 0u;
+        __syncthreads();
+        const unsigned pref = sel_prefix, mask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        for (int v = tid; v < V; v += blockDim.x) {
+          const unsigned k = keyof(sv[v]);
+          if ((k & mask) == pref) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {                                              // lane owns bins [255 - 8*lane - 7, 255 - 8*lane] (descending)
+          unsigned c[8], sum = 0u;
+#pragma unroll
+          for (int j = 0; j < 8; j++) { c[j] = hist[255 - (tid * 8 + j)]; sum += c[j]; }
+          unsigned inc = sum;
+          for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += t; }
+          const unsigned rem = sel_remaining;
+          const unsigned ball = __ballot_sync(0xffffffffu, inc >= rem);
+          const int L = __ffs(ball) - 1;                             // first lane whose cumulative count reaches the remaining rank
+          if (tid == L) {
+            unsigned before = inc - sum;
+            for (int j = 0; j < 8; j++) {
+              if (before + c[j] >= rem) { sel_prefix = pref | ((unsigned)(255 - (tid * 8 + j)) << shift); sel_remaining = rem - before; break; }
+              before += c[j];
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // survivors: key > T, plus the first sel_remaining (by index) of the elements with key == T
+    const unsigned T = use_k ? sel_prefix : 0u;
+    const unsigned need_eq = use_k ? sel_remaining : 0xFFFFFFFFu;
+    const int per = (V + (int)blockDim.x - 1) / (int)blockDim.x, lo = tid * per, hi = min(V, lo + per);
+    unsigned eq = 0u;
+    for (int v = lo; v < hi; v++) eq += (use_k && keyof(sv[v]) == T) ? 1u : 0u;
+    unsigned inc = eq;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += t; }
+    if ((tid & 31) == 31) wcnt[tid >> 5] = inc;
+    __syncthreads();
+    unsigned woff = 0u;
+    for (int w = 0; w < (tid >> 5); w++) woff += wcnt[w];
+    unsigned rank = woff + inc - eq;                                 // equal-key elements before this thread's chunk
+    float m2 = NEG;
+    for (int v = lo; v < hi; v++) {
+      float x = sv[v];
+      if (use_k) {
+        const unsigned k = keyof(x);
+        bool keep = k > T;
+        if (k == T) { keep = rank < need_eq; rank++; }
+        if (!keep) x = NEG;
+      }
+      s_scan[v] = x;
+      m2 = fmaxf(m2, x);
+    }
+    m2 = warp_max(m2);
+    if ((tid & 31) == 0) red[tid >> 5] = m2;
+    __syncthreads();
+    float gm = red[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); i++) gm = fmaxf(gm, red[i]);
+    if (p.filtered) for (int v = tid; v < V; v += blockDim.x) p.filtered[(int64_t)b * V + v] = s_scan[v];
+    __syncthreads();
+    draw_inverse_cdf(p, s_scan, V, b, gm);
+    return;
+  }
   // bitonic sort: descending value, ascending index among equals
   for (int k = 2; k <= SV; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -253,33 +364,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
   float gm = red[0];
   for (int i = 1; i < (int)(blockDim.x >> 5); i++) gm = fmaxf(gm, red[i]);
   __syncthreads();
-  if (tid < 32) {                                                   // warp 0: chunked inverse CDF in index order, double accumulation
-    const int lane = tid, per = (V + 31) / 32, lo = lane * per, hi = min(V, lo + per);
-    double sum = 0.0; int lastlive = -1;
-    for (int v = lo; v < hi; v++) if (s_scan[v] > NEG) { sum += exp((double)(s_scan[v] - gm)); lastlive = v; }
-    double inc = sum;
-    for (int o = 1; o < 32; o <<= 1) { double t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    const double z = __shfl_sync(0xffffffffu, inc, 31);
-    const double target = (double)p.u[b] * z;
-    int glast = lastlive;
-    for (int o = 16; o > 0; o >>= 1) glast = max(glast, __shfl_xor_sync(0xffffffffu, glast, o));
-    const unsigned ball = __ballot_sync(0xffffffffu, inc > target);
-    int pick = -1;
-    if (ball) {
-      const int L = __ffs(ball) - 1;
-      if (lane == L) {
-        double run = inc - sum;
-        pick = lastlive;
-        for (int v = lo; v < hi; v++) if (s_scan[v] > NEG) { run += exp((double)(s_scan[v] - gm)); if (run > target) { pick = v; break; } }
-      }
-      pick = __shfl_sync(0xffffffffu, pick, L);
-    } else pick = glast;
-    if (lane == 0) {
-      if (pick < 0) pick = 0;
-      p.out[(int64_t)b * p.out_stride] = pick;
-      if (p.mark_seen && p.seen) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
-    }
-  }
+  draw_inverse_cdf(p, s_scan, V, b, gm);
 }
 
 }  // namespace

@@ -121,6 +121,7 @@ class ConvW:
 # Tensor-core dispatch policy: "off" = CUDA-core fp32 everywhere; "x2" = tcgen05 with (hi, lo) bf16 activation planes
 # (fp32-grade products); "x1" = tcgen05 with a single bf16 plane.
 TC_MODE = [os.environ.get("B2A_TC", "x2")]
+ATTN_MODE = [os.environ.get("B2A_ATTN", "tc")]      # "tc": tcgen05 flash attention for head_dim 64; "cuda": CUDA-core kernel
 TC_MIN_K = 64                          # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
 
 
@@ -390,6 +391,10 @@ def attention(q, k, v, *, n_heads, n_kv_heads=None, scale, causal=False, q_offse
     p.B, p.Tq, p.Tk, p.H, p.Hkv, p.D = B, Tq, k.shape[1], H, Hkv, D
     p.scale, p.causal, p.q_offset, p.window = scale, int(causal), q_offset, window
     p.k_len = _p(k_len)
+    if ATTN_MODE[0] == "tc" and D == 64 and Hkv == H and k_len is None and k.shape[1] >= 64 and out.stride(1) % 4 == 0:
+        ws = torch.empty(_lib.lib().b2a_attention_tc_ws_bytes(B, H, Tq, k.shape[1]), device=q.device, dtype=torch.uint8)
+        _call("attention", _lib.lib().b2a_attention_tc, 4, C.byref(p), ws.data_ptr(), _stream())
+        return out
     _call("attention", _lib.lib().b2a_attention, 1, C.byref(p), _stream())
     return out
 

@@ -61,8 +61,9 @@ class _DecoderStack:
         y = ops.linear(h, cw, res=None if swiglu else res)
         return ops.swiglu(y, interleaved=True) if swiglu else y
 
-    def forward(self, x: torch.Tensor, *, base_dev=None, base: int = 0, pos3=None, kv_start=None) -> torch.Tensor:
-        """x [B,S,H] -> final-normed hidden [B,S,H]; appends S rows to the cache at ``base`` (device scalar or host int)."""
+    def forward(self, x: torch.Tensor, *, base_dev=None, base: int = 0, pos3=None, kv_start=None, final_norm: bool = True) -> torch.Tensor:
+        """x [B,S,H] -> final-normed hidden [B,S,H] (``final_norm=False``: the residual stream, for a consumer that fuses the
+        norm); appends S rows to the cache at ``base`` (device scalar or host int)."""
         B, S, H = x.shape
         x2 = x.reshape(B * S, H)
         hq, hk, hd = self.n_heads, self.n_kv, self.hd
@@ -76,6 +77,8 @@ class _DecoderStack:
             x2 = self._proj(a.view(B * S, hq * hd), lw["o"], res=x2)
             m = self._proj(x2, lw["gu"], norm_w=lw["n2"], swiglu=True)
             x2 = self._proj(m, lw["down"], res=x2)
+        if not final_norm:
+            return x2.view(B, S, H)
         return ops.layernorm(x2, self.norm, None, eps=self.eps, rms=True).view(B, S, H)
 
 
@@ -103,8 +106,8 @@ class Qwen3TTSTalkerCodePredictor:
         B, S, _ = inputs_embeds.shape
         if self.proj is not None:
             inputs_embeds = ops.linear(inputs_embeds, self.proj)
-        h = self.stack.forward(inputs_embeds, base=offset)
-        return self.stack._proj(h.reshape(B * S, -1), self.lm_head[generation_step]).view(B, S, -1)
+        h = self.stack.forward(inputs_embeds, base=offset, final_norm=False)          # final RMSNorm fused into the head GEMV
+        return self.stack._proj(h.reshape(B * S, -1), self.lm_head[generation_step], norm_w=self.stack.norm).view(B, S, -1)
 
 
 class Qwen3TTSTalkerForConditionalGeneration:

@@ -339,3 +339,36 @@ def test_rvq_decode_bit_exact_and_bounds():
     codes[1, 2, 7] = 2048
     with pytest.raises(ValueError):
         ops.rvq_decode(codes, cb)
+
+
+@pytest.mark.parametrize("Tq,Tk,causal,window,q_offset", [(130, 130, False, 0, 0), (1500, 1500, False, 0, 0), (200, 333, False, 0, 0),
+                                                          (325, 325, True, 0, 0), (700, 700, True, 250, 0), (64, 200, True, 0, 136),
+                                                          (1, 70, True, 0, 69)])
+@pytest.mark.parametrize("mode", ["tc", "cuda"])
+def test_attention_tensor_core_vs_cuda_core(Tq, Tk, causal, window, q_offset, mode):
+    """b2a_attention_tc (tcgen05, fp16 hi/lo planes) and b2a_attention (CUDA cores) against float64 SDPA on strided q/k/v views
+    of one fused qkv buffer, ragged tile tails, causal offset (decoder prefill with a cache) and Mimi's sliding window."""
+    from mlx_audio_b200 import ops
+    dev = _dev()
+    B, H, D = 2, 3, 64
+    T = max(Tq, Tk)
+    qkv = _rand(B, T, 3 * H * D, seed=5, scale=1.5)
+    q, k, v = qkv[:, :Tq, :H * D], qkv[:, :Tk, H * D:2 * H * D], qkv[:, :Tk, 2 * H * D:]
+    qh, kh, vh = (t.double().reshape(B, -1, H, D).transpose(1, 2) for t in (q, k, v))
+    mask = None
+    if causal:
+        i, j = torch.arange(Tq)[:, None] + q_offset, torch.arange(Tk)[None, :]
+        ok = j <= i
+        if window:
+            ok = ok & (i - j < window)
+        mask = torch.where(ok, 0.0, -1e9).double()
+    ref = ON.sdpa(qh, kh, vh, 0.125, mask).transpose(1, 2).reshape(B, Tq, H * D)
+    g = qkv.to(dev)
+    old = ops.ATTN_MODE[0]
+    ops.ATTN_MODE[0] = mode
+    try:
+        y = ops.attention(g[:, :Tq, :H * D], g[:, :Tk, H * D:2 * H * D], g[:, :Tk, 2 * H * D:], n_heads=H, scale=0.125, causal=causal,
+                          window=window, q_offset=q_offset)
+    finally:
+        ops.ATTN_MODE[0] = old
+    assert rel_err(y, ref) < 2e-5

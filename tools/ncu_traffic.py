@@ -19,7 +19,8 @@ def main(path, out):
     per = defaultdict(lambda: {"launches": 0, "read": 0.0, "write": 0.0, "ns": 0.0})
     ids = set()
     for r in csv.DictReader(lines):
-        name = re.sub(r"^.*::", "", re.sub(r"[<(].*", "", r["Kernel Name"]))
+        name = r["Kernel Name"].replace("<unnamed>::", "").replace("(anonymous namespace)::", "")
+        name = re.sub(r"^.*::", "", re.sub(r"[<(].*", "", re.sub(r"^void\s+", "", name))).strip()
         m, val = r.get("Metric Name"), float(r["Metric Value"].replace(",", "") or 0)
         if m == "gpu__time_duration.sum":
             per[name]["ns"] += val * {"ns": 1, "us": 1e3, "ms": 1e6}.get(r.get("Metric Unit", "ns"), 1)
