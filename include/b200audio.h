@@ -223,10 +223,12 @@ int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int3
  * b2a_gemv_bf16: y[m, n] = sum_k W[n,k] xn[m,k] (+ bias[n]) (+ res[m,n]) for M <= 8 activation rows -- nn.Linear at decode
  * time (talker.py:284-286,314,335).  W bf16 row-major [N, w_ld].  norm_w != NULL fuses the preceding nn.RMSNorm
  * (talker.py:388,395; x * rsqrt(mean(x^2) + eps) * norm_w).  mode 1 fuses SwiGLU (talker.py:319-321): W rows interleaved
- * (gate_0, up_0, gate_1, ...), y[m, n/2] = silu(gate) * up, y has N/2 columns. */
+ * (gate_0, up_0, gate_1, ...), y[m, n/2] = silu(gate) * up, y has N/2 columns.  prefetch (optional): the NEXT projection's
+ * weights, prefetch_bytes of them are pulled into L2 (prefetch.global.L2) while this kernel runs, so the dependent launch that
+ * follows finds them on chip. */
 int32_t b2a_gemv_bf16(const float* x, int64_t x_ld, int32_t M, int32_t K, const void* w_bf16, int64_t w_ld, int32_t N,
                       const float* bias, const float* norm_w, float norm_eps, int32_t mode, const float* res, int64_t res_ld,
-                      float* y, int64_t y_ld, void* stream);
+                      float* y, int64_t y_ld, const void* prefetch, int64_t prefetch_bytes, void* stream);
 /* TalkerAttention / CodePredictorAttention / DecoderAttention up to the cache update (talker.py:288-307,558-572;
  * speech_tokenizer.py:291-296): qkv [B,S,(Hq+2Hkv) D] -> per-head RMSNorm of q and k (weights [D], NULL = none), rotary
  * embedding in the rotate_half convention, q_out [B,S,Hq,D], k/v appended to the caches [B,Smax,Hkv,D] at row base + s,
@@ -245,6 +247,12 @@ int32_t b2a_attn_decode(const float* q, int64_t q_bs, int64_t q_ss, const float*
                         int64_t c_ss, float* out, int64_t o_bs, int64_t o_ss, int32_t B, int32_t S, int32_t Hq, int32_t Hkv,
                         int32_t D, float scale, const int32_t* base_dev, int32_t base_host, const int32_t* kv_start,
                         int32_t max_k, void* stream);
+/* Single-token decode (S = 1, GQA group of 2): b2a_qknorm_rope_cache + b2a_attn_decode in one launch, one CTA per (kv head, batch)
+ * -- each cache row is read once for both query heads of the group.  qkv [B, (Hq+2Hkv) D]; out [B, Hq*D]; pos3 [3,B] or NULL. */
+int32_t b2a_attn_decode_fused(const float* qkv, int64_t qkv_bs, int32_t B, int32_t Hq, int32_t Hkv, int32_t D, const float* q_norm_w,
+                              const float* k_norm_w, float eps, const int32_t* pos3, const int32_t* base_dev, int32_t base_host,
+                              int32_t sec_h, int32_t sec_w, float theta, float* k_cache, float* v_cache, int64_t c_bs, int64_t c_ss,
+                              int32_t smax, float scale, const int32_t* kv_start, float* out, int64_t o_bs, void* stream);
 /* y[r, i] = silu(gate) * up (talker.py:319-321, speech_tokenizer.py:321-322) for the batched (prefill) path: x [rows, 2I] holds
  * (gate | up) halves, or interleaved (gate_0, up_0, gate_1, ...) pairs -- the row order b2a_gemv_bf16 mode 1 uses. */
 int32_t b2a_swiglu(const float* x, int64_t x_ld, int64_t rows, int32_t I, int32_t interleaved, float* y, int64_t y_ld, void* stream);

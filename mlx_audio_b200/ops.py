@@ -514,9 +514,11 @@ def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, to
     return (out, filt) if return_filtered else out
 
 
-def gemv(x: torch.Tensor, cw: "ConvW", *, norm_w=None, norm_eps: float = 1e-6, swiglu: bool = False, res=None, out=None) -> torch.Tensor:
+def gemv(x: torch.Tensor, cw: "ConvW", *, norm_w=None, norm_eps: float = 1e-6, swiglu: bool = False, res=None, out=None,
+         prefetch: Optional["ConvW"] = None) -> torch.Tensor:
     """Decode-time nn.Linear on x [M, K] (any M; looped in groups of 8) with the bf16 weight rows of ``cw`` ([N, cin_pad]):
-    optional fused RMSNorm prologue, SwiGLU (interleaved gate/up rows) and residual."""
+    optional fused RMSNorm prologue, SwiGLU (interleaved gate/up rows) and residual.  ``prefetch``: the next projection, whose
+    weights are pulled into L2 while this one runs."""
     assert x.dim() == 2 and x.stride(1) == 1 and cw.K == 1 and cw.w_tc is not None and not cw.f16 and cw.w_tc_lo is None, \
         "gemv needs a bf16-exact K=1 weight"
     M, K = x.shape
@@ -525,12 +527,13 @@ def gemv(x: torch.Tensor, cw: "ConvW", *, norm_w=None, norm_eps: float = 1e-6, s
     if out is None:
         out = torch.empty(M, n_out, device=x.device, dtype=torch.float32)
     assert K == cw.cin and out.shape == (M, n_out) and out.stride(1) == 1
+    pf, pf_bytes = (None, 0) if prefetch is None or prefetch.w_tc is None else (prefetch.w_tc.data_ptr(), prefetch.w_tc.numel() * 2)
     for m0 in range(0, M, 8):
         m = min(8, M - m0)
         r = None if res is None else res[m0:m0 + m]
         _call("gemv", _lib.lib().b2a_gemv_bf16, 1, x[m0:m0 + m].data_ptr(), x.stride(0), m, K, cw.w_tc.data_ptr(), cw.cin_pad, N,
               _p(cw.bias), _p(norm_w), norm_eps, int(swiglu), _p(r), 0 if r is None else r.stride(0), out[m0:m0 + m].data_ptr(),
-              out.stride(0), _stream())
+              out.stride(0), pf if m0 == 0 else None, pf_bytes, _stream())
     return out
 
 
@@ -562,6 +565,21 @@ def attn_decode(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, n
     _call("attention", _lib.lib().b2a_attn_decode, 1, q.data_ptr(), q.stride(0), q.stride(1), k_cache.data_ptr(), v_cache.data_ptr(),
           k_cache.stride(0), k_cache.stride(1), out.data_ptr(), out.stride(0), out.stride(1), B, S, n_heads, n_kv, head_dim, scale,
           _p(base_dev), base, _p(kv_start), max_k, _stream())
+    return out
+
+
+def attn_decode_fused(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, k_cache: torch.Tensor, v_cache: torch.Tensor, *, scale: float,
+                      q_norm=None, k_norm=None, eps: float = 1e-6, pos3=None, base_dev=None, base: int = 0, mrope=(0, 0),
+                      theta: float = 10000.0, kv_start=None, out=None) -> torch.Tensor:
+    """Single-token decode step: qkv [B,(Hq+2Hkv)D] -> attention output [B,Hq*D]; k/v appended to the caches at row ``base``."""
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and n_heads == 2 * n_kv and k_cache.stride() == v_cache.stride()
+    B = qkv.shape[0]
+    if out is None:
+        out = torch.empty(B, n_heads * head_dim, device=qkv.device, dtype=torch.float32)
+    assert pos3 is None or (pos3.dtype == torch.int32 and pos3.is_contiguous() and pos3.numel() == 3 * B)
+    _call("attention", _lib.lib().b2a_attn_decode_fused, 1, qkv.data_ptr(), qkv.stride(0), B, n_heads, n_kv, head_dim, _p(q_norm), _p(k_norm),
+          eps, _p(pos3), _p(base_dev), base, mrope[0], mrope[1], theta, k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0),
+          k_cache.stride(1), k_cache.shape[1], scale, _p(kv_start), out.data_ptr(), out.stride(0), _stream())
     return out
 
 

@@ -56,3 +56,31 @@ def resample_audio_array(audio, orig_sample_rate: int, sample_rate: int, axis: i
     h = torch.as_tensor(fir * up, dtype=torch.float64, device=x2.device)
     out = ops.resample_poly(x2, h, up, down, n_pre_pad, n_pre_remove, n_out)
     return out.reshape(*shp[:-1], n_out).movedim(-1, axis)
+
+
+def resample_audio_chunks(chunks, orig_sample_rate: int, sample_rate: int, num_input_frames: int, chunk_duration_seconds: float = 1.0):
+    """resample.py:50-161: time-first chunks -> the whole-buffer ``resample_poly`` result for the first ``num_input_frames``
+    frames.  The reference overlaps chunks with a halo so that each retained region is bit-identical to the one-shot call; here
+    every output sample is an independent fixed-order sum already, so the chunks are gathered (on the device when they are CUDA
+    tensors) and resampled in one launch -- same samples, same edge rule, same errors."""
+    if chunk_duration_seconds <= 0:
+        raise ValueError("chunk_duration_seconds must be positive")
+    try:
+        import torch
+    except ImportError:                                        # pragma: no cover
+        torch = None
+    parts = [c for c in chunks if c.shape[0] > 0]
+    if not parts:
+        return np.empty((0,), dtype=np.float32)
+    cuda = torch is not None and isinstance(parts[0], torch.Tensor) and parts[0].is_cuda
+    num_input_frames = max(0, int(num_input_frames))
+    if num_input_frames == 0:
+        shape = (0, *parts[0].shape[1:])
+        return torch.empty(shape, dtype=torch.float32, device=parts[0].device) if cuda else np.empty(shape, dtype=np.float32)
+    if cuda:
+        whole = torch.cat([p.to(torch.float32) for p in parts], dim=0)[:num_input_frames]
+    else:
+        whole = np.concatenate([np.asarray(p, dtype=np.float32) for p in parts], axis=0)[:num_input_frames]
+    if orig_sample_rate == sample_rate:
+        return whole
+    return resample_audio_array(whole, orig_sample_rate, sample_rate, axis=0)

@@ -11,6 +11,7 @@ CUDA graph (see qwen3_tts.py).  Prefill (S >= 17 rows) runs the same layers on t
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -19,6 +20,8 @@ from .... import ops
 from .config import Qwen3TTSTalkerCodePredictorConfig, Qwen3TTSTalkerConfig
 
 GEMV_MAX_ROWS = 16
+FUSED_DECODE = [os.environ.get("B2A_LM_FUSED", "1") != "0"]       # S = 1: qk-norm + rope + cache append + attention in one launch
+PREFETCH = [os.environ.get("B2A_LM_PREFETCH", "1") != "0"]      # pull the next projection's weights into L2 from the current GEMV
 
 
 def _interleave(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
@@ -54,29 +57,37 @@ class _DecoderStack:
             self.kc = torch.zeros(shape, device=self.device, dtype=torch.float32)
             self.vc = torch.zeros(shape, device=self.device, dtype=torch.float32)
 
-    def _proj(self, x2, cw, norm_w=None, swiglu=False, res=None):
+    def _proj(self, x2, cw, norm_w=None, swiglu=False, res=None, nxt=None):
         if x2.shape[0] <= GEMV_MAX_ROWS:
-            return ops.gemv(x2, cw, norm_w=norm_w, norm_eps=self.eps, swiglu=swiglu, res=res)
+            return ops.gemv(x2, cw, norm_w=norm_w, norm_eps=self.eps, swiglu=swiglu, res=res, prefetch=nxt if PREFETCH[0] else None)
         h = ops.layernorm(x2, norm_w, None, eps=self.eps, rms=True) if norm_w is not None else x2
         y = ops.linear(h, cw, res=None if swiglu else res)
         return ops.swiglu(y, interleaved=True) if swiglu else y
 
-    def forward(self, x: torch.Tensor, *, base_dev=None, base: int = 0, pos3=None, kv_start=None, final_norm: bool = True) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, *, base_dev=None, base: int = 0, pos3=None, kv_start=None, final_norm: bool = True,
+                tail=None) -> torch.Tensor:
         """x [B,S,H] -> final-normed hidden [B,S,H] (``final_norm=False``: the residual stream, for a consumer that fuses the
-        norm); appends S rows to the cache at ``base`` (device scalar or host int)."""
+        norm); appends S rows to the cache at ``base`` (device scalar or host int).  ``tail``: the projection that follows the
+        stack (head), prefetched into L2 by the last layer."""
         B, S, H = x.shape
         x2 = x.reshape(B * S, H)
         hq, hk, hd = self.n_heads, self.n_kv, self.hd
         max_k = self.kc.shape[2] if base_dev is not None else base + S
         for li, lw in enumerate(self.layers):
-            qkv = self._proj(x2, lw["qkv"], norm_w=lw["n1"])
-            q = ops.qknorm_rope_cache(qkv.view(B, S, -1), hq, hk, hd, self.kc[li], self.vc[li], q_norm=lw["qn"], k_norm=lw["kn"],
-                                      eps=self.eps, pos3=pos3, base_dev=base_dev, base=base, mrope=self.mrope, theta=self.theta)
-            a = ops.attn_decode(q, self.kc[li], self.vc[li], hq, hk, hd, scale=hd ** -0.5, base_dev=base_dev, base=base,
-                                kv_start=kv_start, max_k=max_k)
-            x2 = self._proj(a.view(B * S, hq * hd), lw["o"], res=x2)
-            m = self._proj(x2, lw["gu"], norm_w=lw["n2"], swiglu=True)
-            x2 = self._proj(m, lw["down"], res=x2)
+            nxt_qkv = self.layers[li + 1]["qkv"] if li + 1 < len(self.layers) else tail
+            qkv = self._proj(x2, lw["qkv"], norm_w=lw["n1"], nxt=lw["o"])
+            if S == 1 and hq == 2 * hk and hd in (64, 128) and FUSED_DECODE[0]:
+                a = ops.attn_decode_fused(qkv, hq, hk, hd, self.kc[li], self.vc[li], scale=hd ** -0.5, q_norm=lw["qn"], k_norm=lw["kn"],
+                                          eps=self.eps, pos3=pos3, base_dev=base_dev, base=base, mrope=self.mrope, theta=self.theta,
+                                          kv_start=kv_start)
+            else:
+                q = ops.qknorm_rope_cache(qkv.view(B, S, -1), hq, hk, hd, self.kc[li], self.vc[li], q_norm=lw["qn"], k_norm=lw["kn"],
+                                          eps=self.eps, pos3=pos3, base_dev=base_dev, base=base, mrope=self.mrope, theta=self.theta)
+                a = ops.attn_decode(q, self.kc[li], self.vc[li], hq, hk, hd, scale=hd ** -0.5, base_dev=base_dev, base=base,
+                                    kv_start=kv_start, max_k=max_k)
+            x2 = self._proj(a.view(B * S, hq * hd), lw["o"], res=x2, nxt=lw["gu"])
+            m = self._proj(x2, lw["gu"], norm_w=lw["n2"], swiglu=True, nxt=lw["down"])
+            x2 = self._proj(m, lw["down"], res=x2, nxt=nxt_qkv)
         if not final_norm:
             return x2.view(B, S, H)
         return ops.layernorm(x2, self.norm, None, eps=self.eps, rms=True).view(B, S, H)
@@ -106,8 +117,9 @@ class Qwen3TTSTalkerCodePredictor:
         B, S, _ = inputs_embeds.shape
         if self.proj is not None:
             inputs_embeds = ops.linear(inputs_embeds, self.proj)
-        h = self.stack.forward(inputs_embeds, base=offset, final_norm=False)          # final RMSNorm fused into the head GEMV
-        return self.stack._proj(h.reshape(B * S, -1), self.lm_head[generation_step], norm_w=self.stack.norm).view(B, S, -1)
+        head = self.lm_head[generation_step]
+        h = self.stack.forward(inputs_embeds, base=offset, final_norm=False, tail=head)          # final RMSNorm fused into the head GEMV
+        return self.stack._proj(h.reshape(B * S, -1), head, norm_w=self.stack.norm, nxt=self.stack.layers[0]["qkv"]).view(B, S, -1)
 
 
 class Qwen3TTSTalkerForConditionalGeneration:
@@ -168,11 +180,11 @@ class Qwen3TTSTalkerForConditionalGeneration:
                 pos3 = pos3[None].expand(3, -1, -1)
             pos3 = pos3.contiguous()
         if use_device_offset:
-            h = self.stack.forward(inputs_embeds, base_dev=self.offset_dev, pos3=pos3, kv_start=kv_start)
+            h = self.stack.forward(inputs_embeds, base_dev=self.offset_dev, pos3=pos3, kv_start=kv_start, tail=self.codec_head)
             ops.incr_(self.offset_dev, S)
         else:
-            h = self.stack.forward(inputs_embeds, base=self.offset, pos3=pos3, kv_start=kv_start)
+            h = self.stack.forward(inputs_embeds, base=self.offset, pos3=pos3, kv_start=kv_start, tail=self.codec_head)
             ops.incr_(self.offset_dev, S)
         self.offset += S
-        logits = self.stack._proj(h.reshape(B * S, -1), self.codec_head).view(B, S, -1)
+        logits = self.stack._proj(h.reshape(B * S, -1), self.codec_head, nxt=self.code_predictor.stack.layers[0]["qkv"]).view(B, S, -1)
         return logits, h
