@@ -1,5 +1,6 @@
 // Error plumbing + device queries for the C ABI (include/b200audio.h).
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 
 static thread_local char g_err[512] = "";
@@ -15,4 +16,10 @@ extern "C" int32_t b2a_device_sm_count(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
   return n;
+}
+
+bool b2a_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B2A_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }

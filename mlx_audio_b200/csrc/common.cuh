@@ -46,3 +46,22 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor drains; it must
+// not touch the predecessor's outputs (or write anything) before pdl_wait().  Everything independent of the predecessor --
+// weight loads, L2 prefetches, address math -- goes before it.  Inside a CUDA graph the edges become programmatic dependencies.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool b2a_pdl_enabled();      // env B2A_PDL != "0" (api.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t b2a_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = b2a_pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}

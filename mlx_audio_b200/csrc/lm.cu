@@ -46,12 +46,18 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_bf16_kernel(const GemvParams 
 #pragma unroll
     for (int r = 0; r < GV_ROWS; r++) acc[m][r] = 0.f; }
   const int chunks = p.K >> 3;
-  for (int c = tid; c < chunks; c += GV_THREADS) {
-    const int k = c << 3;
-    uint4 wv[GV_ROWS];
+  uint4 wv[GV_ROWS];
+  auto load_w = [&](int c) {
 #pragma unroll
     for (int r = 0; r < GV_ROWS; r++)
-      wv[r] = (n0 + r < p.N) ? __ldcs(reinterpret_cast<const uint4*>(p.w + (int64_t)(n0 + r) * p.w_ld + k)) : make_uint4(0, 0, 0, 0);
+      wv[r] = (n0 + r < p.N && c < chunks) ? __ldcs(reinterpret_cast<const uint4*>(p.w + (int64_t)(n0 + r) * p.w_ld + ((int64_t)c << 3))) : make_uint4(0, 0, 0, 0);
+  };
+  load_w(tid);                                     // weights do not depend on the previous kernel: in flight before the dependency wait
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int c = tid; c < chunks; c += GV_THREADS) {
+    const int k = c << 3;
+    if (c != tid) load_w(c);
     float g[8];
     if (p.norm_w) {
       float4 g0 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k)), g1 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k + 4));
@@ -148,6 +154,8 @@ __global__ void qknorm_rope_cache_kernel(const QkParams p) {
   const int lane = threadIdx.x & 31;
   const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int HT = p.Hq + 2 * p.Hkv;
+  pdl_launch_dependents();
+  pdl_wait();
   if (wid >= (int64_t)p.B * p.S * HT) return;
   const int h = (int)(wid % HT);
   const int s = (int)((wid / HT) % p.S), b = (int)(wid / ((int64_t)HT * p.S));
@@ -234,6 +242,8 @@ __global__ void __launch_bounds__(AD_THREADS) attn_decode_kernel(const AdParams 
   __shared__ float redm[NW], reds[NW];
   const int h = blockIdx.x, s = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int base = p.base_dev ? *p.base_dev : p.base_host;
   int klen = base + s + 1;
   if (klen > p.max_k) klen = p.max_k;
@@ -314,6 +324,8 @@ __global__ void __launch_bounds__(256) attn_decode_fused_kernel(const FdParams p
   __shared__ float redm[G][NW], reds[G][NW];
   const int hk = blockIdx.x, b = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_launch_dependents();
+  pdl_wait();
   const int base = p.base_dev ? *p.base_dev : p.base_host;
   const int klen = min(base + 1, p.smax);
   const int k0 = p.kv_start ? p.kv_start[b] : 0;
@@ -467,6 +479,8 @@ struct EmbedSumParams {
   float* out; int64_t out_bs; int* err;
 };
 __global__ void embed_sum_kernel(const EmbedSumParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= p.dim) return;
@@ -484,7 +498,7 @@ __global__ void embed_sum_kernel(const EmbedSumParams p) {
   p.out[(int64_t)b * p.out_bs + d] = v;
 }
 
-__global__ void incr_kernel(int* p, int v) { *p += v; }
+__global__ void incr_kernel(int* p, int v) { pdl_launch_dependents(); pdl_wait(); *p += v; }
 
 }  // namespace
 
@@ -499,10 +513,10 @@ extern "C" int32_t b2a_gemv_bf16(const float* x, int64_t x_ld, int32_t M, int32_
                (const char*)prefetch, prefetch ? prefetch_bytes : 0};
   const int grid = (N + GV_ROWS - 1) / GV_ROWS;
   cudaStream_t st = (cudaStream_t)stream;
-  if (M == 1) gemv_bf16_kernel<1><<<grid, GV_THREADS, 0, st>>>(p);
-  else if (M == 2) gemv_bf16_kernel<2><<<grid, GV_THREADS, 0, st>>>(p);
-  else if (M <= 4) gemv_bf16_kernel<4><<<grid, GV_THREADS, 0, st>>>(p);
-  else gemv_bf16_kernel<8><<<grid, GV_THREADS, 0, st>>>(p);
+  if (M == 1) b2a_launch_pdl(gemv_bf16_kernel<1>, dim3(grid), dim3(GV_THREADS), 0, st, p);
+  else if (M == 2) b2a_launch_pdl(gemv_bf16_kernel<2>, dim3(grid), dim3(GV_THREADS), 0, st, p);
+  else if (M <= 4) b2a_launch_pdl(gemv_bf16_kernel<4>, dim3(grid), dim3(GV_THREADS), 0, st, p);
+  else b2a_launch_pdl(gemv_bf16_kernel<8>, dim3(grid), dim3(GV_THREADS), 0, st, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
@@ -518,9 +532,9 @@ extern "C" int32_t b2a_qknorm_rope_cache(const float* qkv, int64_t qkv_bs, int64
              q_out, qo_bs, qo_ss, k_cache, v_cache, c_bs, c_ss, smax};
   const int64_t warps = (int64_t)B * S * (Hq + 2 * Hkv);
   const int grid = (int)((warps * 32 + 255) / 256);
-  if (D == 128) qknorm_rope_cache_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  else if (D == 64) qknorm_rope_cache_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-  else qknorm_rope_cache_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  if (D == 128) b2a_launch_pdl(qknorm_rope_cache_kernel<128>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p);
+  else if (D == 64) b2a_launch_pdl(qknorm_rope_cache_kernel<64>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p);
+  else b2a_launch_pdl(qknorm_rope_cache_kernel<32>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
@@ -540,13 +554,13 @@ extern "C" int32_t b2a_attn_decode(const float* q, int64_t q_bs, int64_t q_ss, c
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attn_decode_kernel<128><<<grid, AD_THREADS, sm, st>>>(p);
+    b2a_launch_pdl(attn_decode_kernel<128>, grid, dim3(AD_THREADS), sm, st, p);
   } else if (D == 64) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attn_decode_kernel<64><<<grid, AD_THREADS, sm, st>>>(p);
+    b2a_launch_pdl(attn_decode_kernel<64>, grid, dim3(AD_THREADS), sm, st, p);
   } else {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attn_decode_kernel<32><<<grid, AD_THREADS, sm, st>>>(p);
+    b2a_launch_pdl(attn_decode_kernel<32>, grid, dim3(AD_THREADS), sm, st, p);
   }
   B2A_CHECK_LAUNCH();
   return B2A_OK;
@@ -569,10 +583,10 @@ extern "C" int32_t b2a_attn_decode_fused(const float* qkv, int64_t qkv_bs, int32
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 128) {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_fused_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attn_decode_fused_kernel<128, 2><<<grid, 256, sm, st>>>(p);
+    b2a_launch_pdl(attn_decode_fused_kernel<128, 2>, grid, dim3(256), sm, st, p);
   } else {
     if (sm > 48 * 1024) cudaFuncSetAttribute(attn_decode_fused_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    attn_decode_fused_kernel<64, 2><<<grid, 256, sm, st>>>(p);
+    b2a_launch_pdl(attn_decode_fused_kernel<64, 2>, grid, dim3(256), sm, st, p);
   }
   B2A_CHECK_LAUNCH();
   return B2A_OK;
@@ -594,13 +608,13 @@ extern "C" int32_t b2a_embed_sum(const int64_t* codes, int64_t codes_bs, int32_t
   B2A_CHECK_ARG(B > 0 && G >= 0 && dim > 0, "bad shape");
   EmbedSumParams p{codes, codes_bs, B, G, dim, tables_dev, bins_dev, text, text_bs, text_ss, n_text, pad, step_dev, step_sub, out, out_bs, err_flag_dev};
   dim3 grid((dim + 255) / 256, B);
-  embed_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  b2a_launch_pdl(embed_sum_kernel, grid, dim3(256), 0, (cudaStream_t)stream, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }
 
 extern "C" int32_t b2a_incr_i32(int32_t* p, int32_t v, void* stream) {
-  incr_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p, v);
+  b2a_launch_pdl(incr_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, p, v);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -197,6 +197,8 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
   const int b = blockIdx.x, tid = threadIdx.x, V = p.V;
   const float NEG = -INFINITY;
   const float* lg = p.logits + (int64_t)b * p.logits_bs;
+  pdl_launch_dependents();
+  pdl_wait();
   auto base = [&](int v) -> float {
     float x = lg[v];
     if (p.suppress) x += p.suppress[v];
@@ -378,7 +380,7 @@ extern "C" int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int3
   if (V > SV) { b2a_set_error("b2a_sample_token: vocab %d > %d not supported", V, SV); return B2A_E_UNSUPPORTED; }
   B2A_CHECK_ARG(min_p >= 0.f && min_p <= 1.f, "`min_p` has to be a float in the [0, 1] interval");
   SampleParams p{logits, logits_bs, V, suppress_mask, seen, seen_bs, mark_seen, out_stride < 1 ? 1 : out_stride, repetition_penalty, temperature, top_k, top_p, min_p, u, out, filtered_out};
-  sample_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(p);
+  b2a_launch_pdl(sample_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -55,6 +55,11 @@ class AudioEncoder:
         W = {"conv1": ops.pack_conv(P["encoder.conv1.weight"].float(), P["encoder.conv1.bias"], 1, dev),
              "conv2": ops.pack_conv(P["encoder.conv2.weight"].float(), P["encoder.conv2.bias"], 1, dev),
              "pos": sinusoids(self.dims.n_audio_ctx, d).to(dev)[None].contiguous(), "blocks": []}
+        # conv2 (k3, stride 2, pad 1) as a stride-1 2-tap conv over row PAIRS (space-to-depth): y[l] = W0 x[2l-1] + W1 x[2l] + W2 x[2l+1]
+        # = [0 | W0] . x'[l-1] + [W1 | W2] . x'[l] with x' = x viewed as [B, L/2, 2C] -- a free view, and a shape the tcgen05 conv takes.
+        w2 = P["encoder.conv2.weight"].float()                          # [Cout, 3, Cin]
+        w2p = torch.stack([torch.cat([torch.zeros_like(w2[:, 0]), w2[:, 0]], dim=1), torch.cat([w2[:, 1], w2[:, 2]], dim=1)], dim=1)
+        W["conv2_s2d"] = ops.pack_conv(w2p, P["encoder.conv2.bias"], 1, dev)
         for i in range(self.dims.n_audio_layer):
             L = f"encoder.blocks.{i}"
             wqkv = torch.cat([P[f"{L}.attn.{n}.weight"].float() for n in ("query", "key", "value")], 0)
@@ -73,7 +78,10 @@ class AudioEncoder:
         W, dims = self._w, self.dims
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         x = ops.conv1d(x, W["conv1"], pad_left=1, post_act=ACT["gelu"])
-        x = ops.conv1d(x, W["conv2"], stride=2, pad_left=1, post_act=ACT["gelu"], res=W["pos"])
+        if x.shape[1] % 2 == 0:
+            x = ops.conv1d(x.view(x.shape[0], x.shape[1] // 2, -1), W["conv2_s2d"], pad_left=1, lout=x.shape[1] // 2, post_act=ACT["gelu"], res=W["pos"])
+        else:
+            x = ops.conv1d(x, W["conv2"], stride=2, pad_left=1, post_act=ACT["gelu"], res=W["pos"])
         assert x.shape[1:] == (dims.n_audio_ctx, dims.n_audio_state), "incorrect audio shape"
         d, nh = dims.n_audio_state, dims.n_audio_head
         for blk in W["blocks"]:
