@@ -18,6 +18,7 @@
 // warps 2..5 = epilogue (warp_id % 4 selects the TMEM lane quarter).  One 128 x BN output tile per CTA.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -61,6 +62,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
   return d;
 }
+// start address shifted by whole 128-byte rows inside a swizzled tile: bo_mode 1 also records the row phase in the descriptor's
+// base-offset field (bits 49-51 = (addr >> 7) & 7)
+__device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t saddr, int bo_mode) {
+  uint64_t d = umma_desc_sw128(saddr);
+  if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
@@ -86,6 +94,7 @@ __device__ __noinline__ float act_noinline(float v, int act, float p0) { return 
 struct TcParams {
   int B, L, Lout, Cout, cin_pad, taps, planes, wplanes, BN, stages, f16;
   int Mrows, up_s, up_crop, C;     // transposed-conv mode: N = up_s * C, GEMM row m & column (r, co) -> output row m*up_s + r - up_crop
+  int reuse, R, shift_min, wst, bo_mode;   // A-reuse mode: one (128 + span)-row A tile per K chunk serves every tap (row-shifted descriptors)
   int shift[32];
   const float* bias; int post_act; float post_p0;
   const float* cscale; int64_t cscale_bs;
@@ -115,26 +124,121 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   const int kchunks = p.cin_pad / TK;
   const int iters = p.taps * kchunks;
 
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
-    for (int s = 0; s < p.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(tmem_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  uint32_t tmem_base = 0;
+  if (!p.reuse) {
+    if (warp == 0 && lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+      for (int s = 0; s < p.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+      mbar_init(tmem_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {                                    // TMEM: BN fp32 accumulator columns (power of two >= 32)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tmem_base = *tmem_slot;
+    if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
   }
-  if (warp == 1) {                                    // TMEM: BN fp32 accumulator columns (power of two >= 32)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.BN) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-  if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
 
+  if (p.reuse) {
+    // ================= A-reuse mode =================
+    // smem: [planes] x A super-tile (R rows x 128 B) | [wst] x { W BN*128 B (x wplanes) } | barriers.  For each 64-channel K chunk the
+    // (128 + span)-row activation tile is fetched ONCE; tap t multiplies rows [shift_t - shift_min, +128) of it, addressed by
+    // advancing the shared-memory descriptor by whole 128-byte rows, so the L2 -> SM operand traffic per chunk drops from
+    // taps * (A + W) to A' + taps * W.
+    const int a_rbytes = p.R * 128;
+    const int a_total = a_rbytes * p.planes;
+    const int w_stage = w_bytes * p.wplanes;
+    uint8_t* wbase = smem + a_total;
+    uint64_t* bars = (uint64_t*)(wbase + (size_t)p.wst * w_stage);
+    uint64_t* a_full = bars; uint64_t* a_empty = bars + 1;
+    uint64_t* w_full = bars + 2; uint64_t* w_empty = w_full + p.wst;
+    uint64_t* r_tmem_full = w_empty + p.wst;
+    uint32_t* r_slot = (uint32_t*)(r_tmem_full + 1);
+    if (warp == 0 && lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+      mbar_init(a_full, 1); mbar_init(a_empty, 1);
+      for (int s = 0; s < p.wst; s++) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
+      mbar_init(r_tmem_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(r_slot)), "r"((uint32_t)p.BN) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = *r_slot;
+    if (warp == 0) {
+      if (lane == 0) {                                  // W producer
+        for (int it = 0; it < iters; it++) {
+          const int kc = it / p.taps, tap = it - kc * p.taps;
+          const int s = it % p.wst, ph = (it / p.wst) & 1;
+          mbar_wait(w_empty + s, ph ^ 1);
+          uint8_t* st = wbase + (size_t)s * w_stage;
+          mbar_expect_tx(w_full + s, (uint32_t)w_stage);
+          tma_load_2d(st, &map_w, w_full + s, kc * TK, tap * p.Cout + n0);
+          if (p.wplanes == 2) tma_load_2d(st + w_bytes, &map_wlo, w_full + s, kc * TK, tap * p.Cout + n0);
+        }
+      }
+    } else if (warp == 2) {
+      if (lane == 0) {                                  // A producer: its own warp, so it never shares a scheduler slot with the W ring
+        for (int kc = 0; kc < kchunks; kc++) {
+          mbar_wait(a_empty, (kc & 1) ^ 1);
+          mbar_expect_tx(a_full, (uint32_t)a_total);
+          tma_load_3d(smem, &map_hi, a_full, kc * TK, l0 + p.shift_min, b);
+          if (p.planes == 2) tma_load_3d(smem + a_rbytes, &map_lo, a_full, kc * TK, l0 + p.shift_min, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      const uint32_t fmt = p.f16 ? 0u : 1u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t a0 = smem_u32(smem);
+      for (int kc = 0; kc < kchunks; kc++) {
+        mbar_wait(a_full, kc & 1);
+        for (int tap = 0; tap < p.taps; tap++) {
+          const int it = kc * p.taps + tap;
+          const int s = it % p.wst, ph = (it / p.wst) & 1;
+          mbar_wait(w_full + s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t wst_addr = smem_u32(wbase + (size_t)s * w_stage);
+            const uint32_t rowoff = (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
+            for (int wp = 0; wp < p.wplanes; wp++) {
+              const uint64_t wdesc = umma_desc_sw128(wst_addr + wp * w_bytes);
+              const int npl = wp == 0 ? p.planes : 1;
+              for (int pl = 0; pl < npl; pl++) {
+                const uint64_t adesc = umma_desc_sw128_rows(a0 + pl * a_rbytes + rowoff, p.bo_mode);
+#pragma unroll
+                for (int k = 0; k < TK / UMMA_K; k++)
+                  umma_bf16(tbase, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (it | wp | pl | k) != 0);
+              }
+            }
+            umma_commit(w_empty + s);
+            if (tap == p.taps - 1) umma_commit(a_empty);
+            if (it == iters - 1) umma_commit(r_tmem_full);
+          }
+          __syncwarp();
+        }
+      }
+    }
+    // epilogue warps fall through to the shared epilogue below with these aliases
+    tmem_full = r_tmem_full;
+    tmem_base = tbase;
+  } else
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
@@ -179,7 +283,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       }
       __syncwarp();
     }
-  } else {
+  }
+  if (warp >= 2) {
     // ===== epilogue: TMEM -> registers -> (per-warp shared-memory transpose) -> coalesced global =====
     // tcgen05.ld hands lane i the 32 columns of ROW i; writing that straight out makes every global access touch 32
     // different rows (32 sectors per instruction, latencies exposed one after another: measured 9k cycles per 32-column
@@ -418,16 +523,48 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   const int stage_bytes = TM * 128 * p.planes + p.BN * 128 * p.wplanes;
   // Two CTAs per SM whenever two 2-stage pipelines fit (<= ~113 KB each): one CTA's epilogue then overlaps the other's main
   // loop.  Otherwise one CTA per SM with as many stages as fit.  (Stage 0 doubles as the 17 KB epilogue staging tile.)
+  // Grids that cannot even give every SM one CTA gain nothing from co-residency: they get the deep pipeline instead (the serial
+  // K loop of a decoder conv -- 54 iterations on 32 CTAs -- is then bound by L2 bandwidth, not by TMA latency).
   const int per_cta_2 = 2 * stage_bytes + 1024 + 128;
-  if (2 * per_cta_2 <= 226 * 1024 && 2 * stage_bytes >= 4 * 32 * 33 * 4) p.stages = 2;
+  static int deep_max = -1;
+  if (deep_max < 0) { const char* e = getenv("B2A_TC_DEEP_MAX"); deep_max = e ? atoi(e) : 80; }
+  const int total_ctas = cdiv(p.Mrows, TM) * (Cout / p.BN) * B;
+  if (total_ctas > deep_max && 2 * per_cta_2 <= 226 * 1024 && 2 * stage_bytes >= 4 * 32 * 33 * 4) p.stages = 2;
   else { p.stages = (212 * 1024) / stage_bytes; if (p.stages > 6) p.stages = 6; if (p.stages < 1) p.stages = 1; }
   if ((size_t)p.stages * stage_bytes < 4 * 32 * 33 * 4) { b2a_set_error("b2a_conv1d_tc: tile too small for the epilogue staging"); return B2A_E_UNSUPPORTED; }
   size_t smem = (size_t)p.stages * stage_bytes + 1024 /*align slack*/ + (2 * p.stages + 1) * 8 + 64;
+  // A-reuse mode (multi-tap stride-1 convs whose taps span <= 64 rows): see the kernel.  B2A_TC_REUSE=0 disables it,
+  // B2A_TC_BO=1 selects the descriptor base-offset variant.
+  static int reuse_on = -1, bo_mode = -1;
+  if (reuse_on < 0) { const char* e = getenv("B2A_TC_REUSE"); reuse_on = (e && e[0] == '0') ? 0 : 1; }
+  if (bo_mode < 0) { const char* e = getenv("B2A_TC_BO"); bo_mode = (e && e[0] == '1') ? 1 : 0; }
+  p.reuse = 0; p.R = TM; p.shift_min = 0; p.wst = 0; p.bo_mode = bo_mode;
+  uint32_t a_box_rows = TM;
+  if (reuse_on && !up_stride && taps >= 2) {
+    int smin = p.shift[0], smax = p.shift[0];
+    for (int i = 1; i < taps; i++) { smin = p.shift[i] < smin ? p.shift[i] : smin; smax = p.shift[i] > smax ? p.shift[i] : smax; }
+    const int span = smax - smin;
+    if (span <= 64) {
+      const int R = (TM + span + 7) / 8 * 8;
+      const int a_total = R * 128 * p.planes, w_stage = p.BN * 128 * p.wplanes;
+      int wst = 3;
+      size_t need = (size_t)a_total + (size_t)wst * w_stage;
+      if (2 * (need + 1024 + 256) > 226 * 1024) {                       // one CTA per SM anyway: deepen the weight ring
+        while (wst < 6 && (size_t)a_total + (size_t)(wst + 1) * w_stage + 2048 <= 200 * 1024) wst++;
+        need = (size_t)a_total + (size_t)wst * w_stage;
+      }
+      if (need + 2048 <= 220 * 1024 && a_total >= 4 * 32 * 33 * 4) {
+        p.reuse = 1; p.R = R; p.shift_min = smin; p.wst = wst;
+        a_box_rows = (uint32_t)R;
+        smem = need + 1024 + (2 * wst + 3) * 8 + 64;
+      }
+    }
+  }
 
   CUtensorMap mh, ml, mw, mwl;
   uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
   uint64_t astr[2] = {(uint64_t)cin_pad * 2, (uint64_t)cin_pad * 2 * (uint64_t)L};
-  uint32_t abox[3] = {TK, TM, 1};
+  uint32_t abox[3] = {TK, a_box_rows, 1};
   int e = make_map(&mh, a_hi, 3, adims, astr, abox, p.f16);
   if (!e) e = make_map(&ml, a_lo ? a_lo : a_hi, 3, adims, astr, abox, p.f16);
   uint64_t wdims[2] = {(uint64_t)cin_pad, (uint64_t)taps * Cout};
