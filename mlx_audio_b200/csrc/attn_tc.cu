@@ -5,7 +5,7 @@
 //
 // One CTA = 128 queries of one (batch, head); key tiles of 64.  Per key tile:
 //   S = Q K^T        tcgen05.mma  M128 x N64 x K64, operands fp16 hi/lo planes (3 products: hi*hi, lo*hi, hi*lo -> fp32-grade
-//                    scores), accumulator in TMEM columns [0,64)
+//                    scores), accumulator double-buffered in TMEM columns [0,64) / [128,192): S(t+1) runs under softmax(t)
 //   softmax          thread r of the four softmax warps owns ROW r (tcgen05.ld hands a lane its row), so the online-softmax
 //                    statistics are thread-local: no shuffles, no shared memory; P is written back to shared memory as fp16
 //                    hi/lo planes in the 128-byte-swizzled K-major layout the MMA reads
@@ -133,9 +133,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + OFF_BAR);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4, *s_full = bars + 5,
-           *p_full = bars + 6, *o_full = bars + 7;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4, *s_full = bars + 5 /* [2] */,
+           *p_full = bars + 7, *o_full = bars + 8;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM, bh = blockIdx.y;
 
@@ -152,12 +152,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kh) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vh) : "memory");
     mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(k_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+    mbar_init(s_full, 1); mbar_init(s_full + 1, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -186,23 +186,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     // D = f32, A = B = f16 (format 0), K-major both, N = 64, M = 128
     const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     const uint32_t sb = smem_u32(smem);
-    if (nt > 0) mbar_wait(q_full, 0);
-    for (int t = 0; t < nt; t++) {
+    // S is double-buffered in TMEM (columns [0,64) and [128,192)): S(t+1) = Q K(t+1)^T is issued BEFORE waiting for P(t), so the
+    // score MMA of the next key tile runs underneath the softmax of the current one.
+    auto issue_s = [&](int t) {
       mbar_wait(k_full, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
-        // S = Qh Kh^T + Ql Kh^T + Qh Kl^T
+        const uint32_t d = tmem_base + ((t & 1) ? 128u : 0u);
 #pragma unroll
-        for (int pr = 0; pr < 3; pr++) {
+        for (int pr = 0; pr < 3; pr++) {                       // S = Qh Kh^T + Ql Kh^T + Qh Kl^T
           const uint64_t ad = umma_desc_sw128(sb + (pr == 1 ? OFF_QL : OFF_QH));
           const uint64_t bd = umma_desc_sw128(sb + (pr == 2 ? OFF_KL : OFF_KH));
 #pragma unroll
-          for (int k = 0; k < HD / 16; k++) umma_f16(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (pr | k) != 0);
+          for (int k = 0; k < HD / 16; k++) umma_f16(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (pr | k) != 0);
         }
         umma_commit(k_empty);
-        umma_commit(s_full);
+        umma_commit(s_full + (t & 1));
       }
       __syncwarp();
+    };
+    if (nt > 0) { mbar_wait(q_full, 0); issue_s(0); }
+    for (int t = 0; t < nt; t++) {
+      if (t + 1 < nt) issue_s(t + 1);
       mbar_wait(p_full, t & 1);
       mbar_wait(v_full, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -237,11 +242,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     const int sw = row & 7;
     for (int t = 0; t < nt; t++) {
       const int kt = (t_lo + t) * BN;
-      mbar_wait(s_full, t & 1);
+      mbar_wait(s_full + (t & 1), (t >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       float s[BN];
-      tmem_ld32_nowait(t_s, s);
-      tmem_ld32_nowait(t_s + 32, s + 32);
+      const uint32_t t_sb = t_s + ((t & 1) ? 128u : 0u);
+      tmem_ld32_nowait(t_sb, s);
+      tmem_ld32_nowait(t_sb + 32, s + 32);
       tmem_wait_ld();
       // mask + row max
       int kmax = p.Tk - 1;                                      // last allowed key
@@ -310,7 +316,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

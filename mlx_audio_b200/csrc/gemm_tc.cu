@@ -181,6 +181,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = *r_slot;
+    if (dbg && threadIdx.x == 0) p.dbg[1] = clock64();
     if (warp == 0) {
       if (lane == 0) {                                  // W producer
         for (int it = 0; it < iters; it++) {
@@ -214,6 +215,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
           const int s = it % p.wst, ph = (it / p.wst) & 1;
           mbar_wait(w_full + s, ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (dbg && lane == 0 && it == 0) p.dbg[2] = clock64();
+          if (dbg && lane == 0 && it == iters - 1) p.dbg[3] = clock64();
           if (lane == 0) {
             const uint32_t wst_addr = smem_u32(wbase + (size_t)s * w_stage);
             const uint32_t rowoff = (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
