@@ -36,6 +36,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   const uint32_t addr = smem_u32(bar);
@@ -404,6 +407,216 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// Persistent variant: one CTA per SM walks the output tiles (static round-robin), the accumulator is DOUBLE-BUFFERED in TMEM
+// (2 x BN columns) and eight epilogue warps (two per TMEM lane quarter, splitting the column chunks) drain tile i while the
+// TMA / MMA warps already run tile i+1.  Against the one-tile-per-CTA kernel this removes (a) the wave-quantisation tail
+// (366 tiles on 296 CTA slots = 2 waves), (b) the per-tile prologue (barrier init, TMEM alloc, descriptor prefetch) and
+// (c) the serialisation of main loop and epilogue inside a CTA; with one CTA per SM the operand ring is as deep as shared
+// memory allows.  smem: [stages] x { A planes | W planes } | 8 x 32x33 fp32 transpose tiles | barriers.
+constexpr int PERSIST_THREADS = 320;
+constexpr int PERSIST_STAGING = 8 * 32 * 33 * 4;
+
+__global__ void __launch_bounds__(PERSIST_THREADS, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                       const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wlo, const TcParams p,
+                       int ntm, int ntn, int ntiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a_bytes = TM * 128, w_bytes = p.BN * 128;
+  const int stage_bytes = a_bytes * p.planes + w_bytes * p.wplanes;
+  float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes + PERSIST_STAGING);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;          // [2]
+  uint64_t* tempty = tfull + 2;                // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  const int kchunks = p.cin_pad / TK;
+  const int iters = p.taps * kchunks;
+  const uint32_t tmem_cols = (uint32_t)(2 * p.BN);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
+    for (int s = 0; s < p.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tfull, 1); mbar_init(tfull + 1, 1); mbar_init(tempty, 8); mbar_init(tempty + 1, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: runs ahead across tile boundaries, bounded only by the operand ring =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = tile % ntn, mt = (tile / ntn) % ntm, b = tile / (ntn * ntm);
+        const int l0 = mt * TM, n0 = nt * p.BN;
+        for (int i = 0; i < iters; i++, it++) {
+          const int s = it % p.stages, ph = (it / p.stages) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          const int tap = i / kchunks, kc = i % kchunks;
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          mbar_expect_tx(full + s, (uint32_t)stage_bytes);
+          tma_load_3d(st, &map_hi, full + s, kc * TK, l0 + p.shift[tap], b);
+          if (p.planes == 2) tma_load_3d(st + a_bytes, &map_lo, full + s, kc * TK, l0 + p.shift[tap], b);
+          tma_load_2d(st + (size_t)a_bytes * p.planes, &map_w, full + s, kc * TK, tap * p.Cout + n0);
+          if (p.wplanes == 2) tma_load_2d(st + (size_t)a_bytes * p.planes + w_bytes, &map_wlo, full + s, kc * TK, tap * p.Cout + n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t fmt = p.f16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    uint32_t it = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      mbar_wait(tempty + buf, (use & 1) ^ 1);                 // the epilogue has drained this accumulator (first use: free)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + buf * (uint32_t)p.BN;
+      for (int i = 0; i < iters; i++, it++) {
+        const int s = it % p.stages, ph = (it / p.stages) & 1;
+        mbar_wait(full + s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+          for (int wp = 0; wp < p.wplanes; wp++) {
+            const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes + wp * w_bytes);
+            const int npl = wp == 0 ? p.planes : 1;
+            for (int pl = 0; pl < npl; pl++) {
+              const uint64_t adesc = umma_desc_sw128(st + pl * a_bytes);
+#pragma unroll
+              for (int k = 0; k < TK / UMMA_K; k++)
+                umma_bf16(tacc, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (i | wp | pl | k) != 0);
+            }
+          }
+          umma_commit(empty + s);
+          if (i == iters - 1) umma_commit(tfull + buf);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue (8 warps): quarter = warp % 4 selects the TMEM lanes, sub = (warp - 2) / 4 the 32-column chunks it owns =====
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
+    float* stage = staging + (warp - 2) * (32 * 33);
+    const int mul = p.up_s ? p.up_s : 1;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+      const int nt = tile % ntn, mt = (tile / ntn) % ntm, b = tile / (ntn * ntm);
+      const int l0 = mt * TM, n0 = nt * p.BN;
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      if (!p.up_s) {                                          // pull residual / previous-output rows towards L2 while the MMAs run
+        const int prow = l0 + quarter * 32 + lane;
+        if (prow < p.Lout) {
+          if (p.res) {
+            const float* q = p.res + (int64_t)b * p.res_bs + (int64_t)(p.res_div == 2 ? (prow >> 1) : prow) * p.res_ld + n0;
+            for (int c = sub * 32; c < p.BN; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+          }
+          if (p.accumulate) {
+            const float* q = p.y + (int64_t)b * p.y_bs + (int64_t)prow * p.y_ld + n0;
+            for (int c = sub * 32; c < p.BN; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+          }
+        }
+      }
+      mbar_wait(tfull + buf, use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int mrow0 = l0 + quarter * 32;
+      for (int c0 = sub * 32; c0 < p.BN; c0 += 64) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + buf * (uint32_t)p.BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        if (mrow0 >= p.Mrows) continue;
+#pragma unroll
+        for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+        const int n = n0 + c0 + lane;
+        const int ph = p.up_s ? n / p.C : 0;
+        const int co = n - ph * p.C;
+        const int add = p.up_s ? ph - p.up_crop : 0;
+        const float bias = p.bias ? __ldg(p.bias + co) : 0.f;
+        const float cs = p.cscale ? __ldg(p.cscale + (int64_t)b * p.cscale_bs + co) : 1.f;
+        float* ycol = p.y + (int64_t)b * p.y_bs + co;
+        const float* rcol = p.res ? p.res + (int64_t)b * p.res_bs + co : nullptr;
+        const int row0 = mrow0 * mul + add;
+        const int mvalid = min(32, p.Mrows - mrow0);
+        int i_lo = 0, i_hi = mvalid;
+        if (row0 < 0) i_lo = (-row0 + mul - 1) / mul;
+        if (row0 + (mvalid - 1) * mul >= p.Lout) i_hi = p.Lout > row0 ? (p.Lout - row0 + mul - 1) / mul : 0;
+        const int64_t ystride = (int64_t)mul * p.y_ld;
+        float* yp = ycol + (int64_t)row0 * p.y_ld;
+        const bool half_res = p.res_div == 2;
+        const int odd = row0 & 1;
+        const float* rp = rcol ? rcol + (int64_t)(half_res ? (row0 >> 1) : row0) * p.res_ld : nullptr;
+        const int64_t rstride = (int64_t)mul * p.res_ld;
+        const float osc = p.out_scale;
+        if (i_lo == 0 && i_hi == 32) {
+          float rr[32];
+          if (rp) {
+            if (!half_res) {
+#pragma unroll
+              for (int i = 0; i < 32; i++) rr[i] = __ldg(rp + i * rstride);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++) rr[i] = __ldg(rp + (int64_t)((i + odd) >> 1) * p.res_ld);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) rr[i] = 0.f;
+          }
+          if (p.accumulate) {
+            float oo[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) oo[i] = yp[i * ystride];
+#pragma unroll
+            for (int i = 0; i < 32; i++) rr[i] = rr[i] * osc + oo[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) rr[i] *= osc;
+          }
+          const float cso = cs * osc;
+          if (p.post_act) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) yp[i * ystride] = act_noinline(stage[i * 33 + lane] + bias, p.post_act, p.post_p0) * cso + rr[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) yp[i * ystride] = (stage[i * 33 + lane] + bias) * cso + rr[i];
+          }
+        } else {
+          for (int i = i_lo; i < i_hi; i++) {
+            const int row = row0 + i * mul;
+            float t = stage[i * 33 + lane] + bias;
+            if (p.post_act) t = act_noinline(t, p.post_act, p.post_p0);
+            float rv = rcol ? __ldg(rcol + (int64_t)(half_res ? (row >> 1) : row) * p.res_ld) : 0.f;
+            float o = p.accumulate ? ycol[(int64_t)row * p.y_ld] : 0.f;
+            ycol[(int64_t)row * p.y_ld] = (t * cs + rv) * osc + o;
+          }
+        }
+        __syncwarp();
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + buf);                // 8 arrivals free the accumulator for tile lt + 2
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ---- prologue: fp32 activations -> (hi, lo) bf16 planes with the fused input transform; pad channels are zeroed
 template <typename T> __device__ __forceinline__ T to16(float v);
 template <> __device__ __forceinline__ __nv_bfloat16 to16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
@@ -539,7 +752,7 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   // A-reuse mode (multi-tap stride-1 convs whose taps span <= 64 rows): see the kernel.  B2A_TC_REUSE=0 disables it,
   // B2A_TC_BO=1 selects the descriptor base-offset variant.
   static int reuse_on = -1, bo_mode = -1;
-  if (reuse_on < 0) { const char* e = getenv("B2A_TC_REUSE"); reuse_on = (e && e[0] == '0') ? 0 : 1; }
+  if (reuse_on < 0) { const char* e = getenv("B2A_TC_REUSE"); reuse_on = (e && e[0] == '1') ? 1 : 0; }   // measured slower (single A buffer): opt-in
   if (bo_mode < 0) { const char* e = getenv("B2A_TC_BO"); bo_mode = (e && e[0] == '1') ? 1 : 0; }
   p.reuse = 0; p.R = TM; p.shift_min = 0; p.wst = 0; p.bo_mode = bo_mode;
   uint32_t a_box_rows = TM;
@@ -578,7 +791,31 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   if (e) { b2a_set_error("b2a_conv1d_tc: cuTensorMapEncodeTiled failed (%d)", e); return B2A_E_CUDA; }
 
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  if (!attr) {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  static int persist_on = -1, nsm = 0;
+  if (persist_on < 0) {
+    const char* e = getenv("B2A_TC_PERSIST"); persist_on = (e && e[0] == '0') ? 0 : 1;
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  if (persist_on && !p.reuse && !p.dbg) {
+    int pst = (int)((227 * 1024 - PERSIST_STAGING - 2048) / stage_bytes);
+    if (pst > 6) pst = 6;
+    if (pst >= 2 && 2 * p.BN <= 512) {
+      TcParams q = p;
+      q.stages = pst;
+      const int ntm = cdiv(p.Mrows, TM), ntn = Cout / p.BN, ntiles = ntm * ntn * B;
+      const size_t psm = (size_t)pst * stage_bytes + PERSIST_STAGING + 1024 + (2 * pst + 4) * 8 + 64;
+      const int g = ntiles < nsm ? ntiles : nsm;
+      conv_tc_persist_kernel<<<g, PERSIST_THREADS, psm, (cudaStream_t)stream>>>(mh, ml, mw, mwl, q, ntm, ntn, ntiles);
+      B2A_CHECK_LAUNCH();
+      return B2A_OK;
+    }
+  }
   dim3 grid(cdiv(p.Mrows, TM), Cout / p.BN, B);
   conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mh, ml, mw, mwl, p);
   B2A_CHECK_LAUNCH();
