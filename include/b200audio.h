@@ -210,11 +210,13 @@ int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_bs, const in
  * sign-aware repetition penalty on the `seen` set -> temperature (<= 0: argmax) -> top-k -> top-p -> min-p -> categorical draw
  * by inverse CDF in index order with the caller's uniform u[b] (MLX's PRNG is not reproducible; tests inject u).  V <= 4096.
  * out[b * out_stride] receives the token; mark_seen != 0 also sets seen[b][token] (generated_token_ids.append, :1402).
+ * finished (optional, uint8 [B], in/out) implements the batch loop's bookkeeping (:1880-1887,1923-1929): a finished row emits eos
+ * and is not marked; a row that samples eos becomes finished.
  * filtered_out (optional) receives the filtered, temperature-scaled logits the draw is made from. */
 int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int32_t V, const float* suppress_mask,
                          uint8_t* seen, int64_t seen_bs, int32_t mark_seen, float repetition_penalty, float temperature,
                          int32_t top_k, float top_p, float min_p, const float* u, int64_t* out, int64_t out_stride,
-                         float* filtered_out, void* stream);
+                         float* filtered_out, uint8_t* finished, int32_t eos, void* stream);
 
 /* ---- autoregressive LM step (Qwen3-TTS talker / code predictor, tts/models/qwen3_tts/talker.py) -----------------------
  * All position-dependent scalars may come from device memory (base_dev, step_dev) so that one captured CUDA graph replays
@@ -234,12 +236,13 @@ int32_t b2a_gemv_bf16(const float* x, int64_t x_ld, int32_t M, int32_t K, const 
  * embedding in the rotate_half convention, q_out [B,S,Hq,D], k/v appended to the caches [B,Smax,Hkv,D] at row base + s,
  * base = *base_dev (or base_host when base_dev is NULL).  Rotary position of frequency slot i: pos3[axis,b,s] with the
  * interleaved-MRoPE axis rule of talker.py:139-184 (axis 1 if i%3==1 && i<3*sec_h, axis 2 if i%3==2 && i<3*sec_w, else 0);
- * pos3 NULL = base + s on every axis (sec_h = sec_w = 0 gives the standard RoPE of talker.py:68-113). */
+ * pos3 NULL = base + s on every axis (sec_h = sec_w = 0 gives the standard RoPE of talker.py:68-113), minus pos_shift[b] (clamped at
+ * 0) when pos_shift != NULL: the cumsum(attention_mask) - 1 positions of left-padded batches (talker.py:452-457). */
 int32_t b2a_qknorm_rope_cache(const float* qkv, int64_t qkv_bs, int64_t qkv_ss, int32_t B, int32_t S, int32_t Hq, int32_t Hkv,
                               int32_t D, const float* q_norm_w, const float* k_norm_w, float eps, const int32_t* pos3,
                               const int32_t* base_dev, int32_t base_host, int32_t sec_h, int32_t sec_w, float theta,
                               float* q_out, int64_t qo_bs, int64_t qo_ss, float* k_cache, float* v_cache, int64_t c_bs,
-                              int64_t c_ss, int32_t smax, void* stream);
+                              int64_t c_ss, int32_t smax, const int32_t* pos_shift, void* stream);
 /* mx.fast.scaled_dot_product_attention against the KV cache with GQA (talker.py:309-312): query s attends cache rows
  * [kv_start[b], base + s] (causal inside the new block; kv_start NULL = 0, else the left-padding count of
  * qwen3_tts.py:486-604's batches).  out [B,S,Hq*D].  max_k bounds base + S (shared-memory sizing). */
@@ -258,11 +261,13 @@ int32_t b2a_attn_decode_fused(const float* qkv, int64_t qkv_bs, int32_t B, int32
 int32_t b2a_swiglu(const float* x, int64_t x_ld, int64_t rows, int32_t I, int32_t interleaved, float* y, int64_t y_ld, void* stream);
 /* Next talker input (qwen3_tts.py:1383-1398): out[b] = text(b) + sum_g tables[g][codes[b,g]], text(b) = text[b, step] while
  * step = *step_dev - step_sub < n_text, else pad (tts_pad_embed); text/pad NULL = 0.  tables_dev / bins_dev are DEVICE arrays
- * of G table pointers / table sizes; an out-of-range code sets *err_flag_dev. */
+ * of G table pointers / table sizes; an out-of-range code sets *err_flag_dev.  tidx != NULL selects the batch rule of
+ * _next_batch_input_embeds(pad_when_index_clamped=True) (qwen3_tts.py:993-1015): text row min(tidx[b], n_text-1), replaced by pad
+ * when that is >= n_text-1; afterwards tidx[b] += 1 for rows that are not finished. */
 int32_t b2a_embed_sum(const int64_t* codes, int64_t codes_bs, int32_t B, int32_t G, int32_t dim, const float* const* tables_dev,
                       const int32_t* bins_dev, const float* text, int64_t text_bs, int64_t text_ss, int32_t n_text,
                       const float* pad, const int32_t* step_dev, int32_t step_sub, float* out, int64_t out_bs,
-                      int32_t* err_flag_dev, void* stream);
+                      int32_t* err_flag_dev, int32_t* tidx, const uint8_t* finished, void* stream);
 /* *p += v on the stream (KVCache.offset bookkeeping, lm/models/cache.py:112-155, kept on the device). */
 int32_t b2a_incr_i32(int32_t* p, int32_t v, void* stream);
 

@@ -143,6 +143,7 @@ struct QkParams {
   const float* qn; const float* kn; float eps;     // per-head RMSNorm weights [D] (NULL = no norm)
   const int* pos3; const int* base_dev; int base_host;
   int sec_h, sec_w; float theta;
+  const int* pos_shift;                            // [B] left-padding count: rotary position = max(cache row - pos_shift[b], 0) (qwen3 batches)
   float* q_out; int64_t qo_bs, qo_ss;              // [B,S,Hq,D]
   float* kc; float* vc; int64_t c_bs, c_ss;        // caches [B,Smax,Hkv,D]
   int smax;
@@ -189,7 +190,8 @@ __global__ void qknorm_rope_cache_kernel(const QkParams p) {
   auto cs_of = [&](int i, float& c, float& sf) {
     int axis = 0;
     if (i % 3 == 1 && i < 3 * p.sec_h) axis = 1; else if (i % 3 == 2 && i < 3 * p.sec_w) axis = 2;
-    const int pos = p.pos3 ? p.pos3[((int64_t)axis * p.B + b) * p.S + s] : cpos;
+    int pos = p.pos3 ? p.pos3[((int64_t)axis * p.B + b) * p.S + s] : cpos;
+    if (!p.pos3 && p.pos_shift) { pos -= p.pos_shift[b]; if (pos < 0) pos = 0; }
     const double inv = exp2(-(double)(2 * i) / (double)D * log2((double)p.theta));
     double sn, cs;
     sincos((double)pos * inv, &sn, &cs);
@@ -477,6 +479,7 @@ struct EmbedSumParams {
   const float* const* tables; const int* bins;
   const float* text; int64_t text_bs, text_ss; int n_text; const float* pad; const int* step_dev; int step_sub;
   float* out; int64_t out_bs; int* err;
+  int* tidx; const uint8_t* finished;              // batch loop: per-row trailing index (advanced for unfinished rows), clamp-pad rule
 };
 __global__ void embed_sum_kernel(const EmbedSumParams p) {
   pdl_launch_dependents();
@@ -485,7 +488,14 @@ __global__ void embed_sum_kernel(const EmbedSumParams p) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= p.dim) return;
   float v = 0.f;
-  if (p.text || p.pad) {
+  if (p.tidx) {
+    // _next_batch_input_embeds(pad_when_index_clamped=True) (qwen3_tts.py:993-1015): clamp to n_text-1, and a clamped-or-last index
+    // reads the pad embedding (the last trailing row is never used in batch mode -- reference behaviour, kept)
+    const int idx = p.tidx[b];
+    const int cl = idx < p.n_text - 1 ? idx : p.n_text - 1;
+    if (cl >= p.n_text - 1) v = p.pad ? p.pad[d] : 0.f;
+    else v = p.text[(int64_t)b * p.text_bs + (int64_t)cl * p.text_ss + d];
+  } else if (p.text || p.pad) {
     const int step = (p.step_dev ? *p.step_dev : 0) - p.step_sub;
     if (p.text && step >= 0 && step < p.n_text) v = p.text[(int64_t)b * p.text_bs + (int64_t)step * p.text_ss + d];
     else if (p.pad) v = p.pad[d];
@@ -496,6 +506,15 @@ __global__ void embed_sum_kernel(const EmbedSumParams p) {
     v += p.tables[g][c * p.dim + d];
   }
   p.out[(int64_t)b * p.out_bs + d] = v;
+  // one thread per row advances the trailing index after every reader of this CTA has used it (rows span several CTAs: the index
+  // is read at the top of each; the increment happens in a separate tiny kernel to stay race-free)
+}
+
+__global__ void advance_tidx_kernel(int* tidx, const uint8_t* finished, int B) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && !(finished && finished[b])) tidx[b] += 1;
 }
 
 __global__ void incr_kernel(int* p, int v) { pdl_launch_dependents(); pdl_wait(); *p += v; }
@@ -525,10 +544,10 @@ extern "C" int32_t b2a_qknorm_rope_cache(const float* qkv, int64_t qkv_bs, int64
                                          int32_t Hkv, int32_t D, const float* q_norm_w, const float* k_norm_w, float eps,
                                          const int32_t* pos3, const int32_t* base_dev, int32_t base_host, int32_t sec_h,
                                          int32_t sec_w, float theta, float* q_out, int64_t qo_bs, int64_t qo_ss, float* k_cache,
-                                         float* v_cache, int64_t c_bs, int64_t c_ss, int32_t smax, void* stream) {
+                                         float* v_cache, int64_t c_bs, int64_t c_ss, int32_t smax, const int32_t* pos_shift, void* stream) {
   B2A_CHECK_ARG(D == 32 || D == 64 || D == 128, "head_dim must be 32, 64 or 128");
   B2A_CHECK_ARG(B > 0 && S > 0 && Hq > 0 && Hkv > 0 && Hq % Hkv == 0, "bad shape");
-  QkParams p{qkv, qkv_bs, qkv_ss, B, S, Hq, Hkv, D, q_norm_w, k_norm_w, eps, pos3, base_dev, base_host, sec_h, sec_w, theta,
+  QkParams p{qkv, qkv_bs, qkv_ss, B, S, Hq, Hkv, D, q_norm_w, k_norm_w, eps, pos3, base_dev, base_host, sec_h, sec_w, theta, pos_shift,
              q_out, qo_bs, qo_ss, k_cache, v_cache, c_bs, c_ss, smax};
   const int64_t warps = (int64_t)B * S * (Hq + 2 * Hkv);
   const int grid = (int)((warps * 32 + 255) / 256);
@@ -604,11 +623,14 @@ extern "C" int32_t b2a_swiglu(const float* x, int64_t x_ld, int64_t rows, int32_
 extern "C" int32_t b2a_embed_sum(const int64_t* codes, int64_t codes_bs, int32_t B, int32_t G, int32_t dim,
                                  const float* const* tables_dev, const int32_t* bins_dev, const float* text, int64_t text_bs,
                                  int64_t text_ss, int32_t n_text, const float* pad, const int32_t* step_dev, int32_t step_sub,
-                                 float* out, int64_t out_bs, int32_t* err_flag_dev, void* stream) {
+                                 float* out, int64_t out_bs, int32_t* err_flag_dev, int32_t* tidx, const uint8_t* finished, void* stream) {
   B2A_CHECK_ARG(B > 0 && G >= 0 && dim > 0, "bad shape");
-  EmbedSumParams p{codes, codes_bs, B, G, dim, tables_dev, bins_dev, text, text_bs, text_ss, n_text, pad, step_dev, step_sub, out, out_bs, err_flag_dev};
+  B2A_CHECK_ARG(tidx == nullptr || (text != nullptr && n_text > 0), "per-row trailing indices need the trailing text rows");
+  EmbedSumParams p{codes, codes_bs, B, G, dim, tables_dev, bins_dev, text, text_bs, text_ss, n_text, pad, step_dev, step_sub, out, out_bs, err_flag_dev,
+                   tidx, finished};
   dim3 grid((dim + 255) / 256, B);
   b2a_launch_pdl(embed_sum_kernel, grid, dim3(256), 0, (cudaStream_t)stream, p);
+  if (tidx) b2a_launch_pdl(advance_tidx_kernel, dim3((B + 63) / 64), dim3(64), 0, (cudaStream_t)stream, tidx, finished, (int)B);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -148,6 +148,7 @@ struct SampleParams {
   const float* suppress;                  // [V] additive 0/-inf or NULL
   uint8_t* seen; int64_t seen_bs;         // [B,V] 1 = token already generated (repetition penalty set) or NULL
   int mark_seen; int64_t out_stride;      // mark_seen: set seen[b][token] after the draw; out[b * out_stride]
+  uint8_t* finished; int eos;             // batch loop (qwen3_tts.py:1880-1887): finished rows emit eos; finished |= (token == eos)
   float rep_penalty, temperature; int top_k; float top_p, min_p;
   const float* u;                         // [B] uniforms in [0,1)
   int64_t* out;                           // [B]
@@ -183,8 +184,10 @@ __device__ __forceinline__ void draw_inverse_cdf(const SampleParams& p, const fl
     } else pick = glast;
     if (lane == 0) {
       if (pick < 0) pick = 0;
+      bool live = true;
+      if (p.finished) { if (p.finished[b]) { pick = p.eos; live = false; } else if (pick == p.eos) { p.finished[b] = 1; live = false; } }
       p.out[(int64_t)b * p.out_stride] = pick;
-      if (p.mark_seen && p.seen) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
+      if (p.mark_seen && p.seen && live) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
     }
   }
 }
@@ -216,9 +219,11 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
       __syncthreads();
     }
     if (tid == 0) {
-      const int pick = gi[0] == 0x7fffffff ? 0 : gi[0];
+      int pick = gi[0] == 0x7fffffff ? 0 : gi[0];
+      bool live = true;
+      if (p.finished) { if (p.finished[b]) { pick = p.eos; live = false; } else if (pick == p.eos) { p.finished[b] = 1; live = false; } }
       p.out[(int64_t)b * p.out_stride] = pick;
-      if (p.mark_seen && p.seen) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
+      if (p.mark_seen && p.seen && live) p.seen[(int64_t)b * p.seen_bs + pick] = 1;
     }
     return;
   }
@@ -374,12 +379,12 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleParams p) {
 extern "C" int32_t b2a_sample_token(const float* logits, int64_t logits_bs, int32_t B, int32_t V, const float* suppress_mask,
                                     uint8_t* seen, int64_t seen_bs, int32_t mark_seen, float repetition_penalty, float temperature,
                                     int32_t top_k, float top_p, float min_p, const float* u, int64_t* out, int64_t out_stride,
-                                    float* filtered_out, void* stream) {
+                                    float* filtered_out, uint8_t* finished, int32_t eos, void* stream) {
   B2A_CHECK_ARG(logits && out && B > 0 && V > 0, "bad pointers/shape");
   B2A_CHECK_ARG(temperature <= 0.f || u != nullptr, "a uniform draw per row is required when temperature > 0");
   if (V > SV) { b2a_set_error("b2a_sample_token: vocab %d > %d not supported", V, SV); return B2A_E_UNSUPPORTED; }
   B2A_CHECK_ARG(min_p >= 0.f && min_p <= 1.f, "`min_p` has to be a float in the [0, 1] interval");
-  SampleParams p{logits, logits_bs, V, suppress_mask, seen, seen_bs, mark_seen, out_stride < 1 ? 1 : out_stride, repetition_penalty, temperature, top_k, top_p, min_p, u, out, filtered_out};
+  SampleParams p{logits, logits_bs, V, suppress_mask, seen, seen_bs, mark_seen, out_stride < 1 ? 1 : out_stride, finished, eos, repetition_penalty, temperature, top_k, top_p, min_p, u, out, filtered_out};
   b2a_launch_pdl(sample_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;

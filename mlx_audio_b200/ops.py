@@ -499,7 +499,7 @@ def randn_(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
 
 def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, u=None,
                  suppress_mask=None, seen=None, repetition_penalty: float = 1.0, return_filtered: bool = False, mark_seen: bool = False,
-                 out: Optional[torch.Tensor] = None):
+                 out: Optional[torch.Tensor] = None, finished=None, eos: int = -1):
     """Fused sampler on logits [B,V] (V <= 4096) -> int64 tokens [B] (and the filtered logits when asked).  ``out`` may be a
     strided int64 view (e.g. a column of the [B,16] code matrix)."""
     B, V = logits.shape
@@ -510,7 +510,7 @@ def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, to
     filt = torch.empty(B, V, device=logits.device, dtype=torch.float32) if return_filtered else None
     _call("sampler", _lib.lib().b2a_sample_token, 1, logits.data_ptr(), logits.stride(0), B, V, _p(suppress_mask), _p(seen),
           0 if seen is None else seen.stride(0), int(mark_seen), repetition_penalty, temperature, top_k, top_p, min_p, _p(u),
-          out.data_ptr(), out.stride(0) if B > 1 else 1, _p(filt), _stream())
+          out.data_ptr(), out.stride(0) if B > 1 else 1, _p(filt), _p(finished), eos, _stream())
     return (out, filt) if return_filtered else out
 
 
@@ -539,7 +539,7 @@ def gemv(x: torch.Tensor, cw: "ConvW", *, norm_w=None, norm_eps: float = 1e-6, s
 
 def qknorm_rope_cache(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int, k_cache: torch.Tensor, v_cache: torch.Tensor, *,
                       q_norm=None, k_norm=None, eps: float = 1e-6, pos3=None, base_dev=None, base: int = 0, mrope=(0, 0),
-                      theta: float = 10000.0, q_out=None) -> torch.Tensor:
+                      theta: float = 10000.0, q_out=None, pos_shift=None) -> torch.Tensor:
     """qkv [B,S,(Hq+2Hkv)D] -> q_out [B,S,Hq*D] (normed + rotated), k/v appended to caches [B,Smax,Hkv*D] at row base+s."""
     _chk3(qkv, "qkv")
     B, S, _ = qkv.shape
@@ -549,7 +549,7 @@ def qknorm_rope_cache(qkv: torch.Tensor, n_heads: int, n_kv: int, head_dim: int,
     assert pos3 is None or (pos3.dtype == torch.int32 and pos3.is_contiguous() and pos3.shape == (3, B, S))
     _call("rope", _lib.lib().b2a_qknorm_rope_cache, 1, qkv.data_ptr(), qkv.stride(0), qkv.stride(1), B, S, n_heads, n_kv, head_dim,
           _p(q_norm), _p(k_norm), eps, _p(pos3), _p(base_dev), base, mrope[0], mrope[1], theta, q_out.data_ptr(), q_out.stride(0),
-          q_out.stride(1), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0), k_cache.stride(1), k_cache.shape[1], _stream())
+          q_out.stride(1), k_cache.data_ptr(), v_cache.data_ptr(), k_cache.stride(0), k_cache.stride(1), k_cache.shape[1], _p(pos_shift), _stream())
     return q_out
 
 
@@ -609,7 +609,8 @@ class EmbedTables:
         self.dim = self.tables[0].shape[1]
 
 
-def embed_sum(codes: torch.Tensor, tabs: EmbedTables, *, text=None, pad=None, step_dev=None, step_sub: int = 0, out=None, err=None) -> torch.Tensor:
+def embed_sum(codes: torch.Tensor, tabs: EmbedTables, *, text=None, pad=None, step_dev=None, step_sub: int = 0, out=None, err=None,
+              tidx=None, finished=None) -> torch.Tensor:
     """out[b] = text-or-pad(b) + sum_g tables[g][codes[b,g]]; codes int64 [B,G] (G <= len(tables))."""
     assert codes.dtype == torch.int64 and codes.dim() == 2 and codes.stride(1) == 1
     B, G = codes.shape
@@ -618,7 +619,7 @@ def embed_sum(codes: torch.Tensor, tabs: EmbedTables, *, text=None, pad=None, st
         out = torch.empty(B, tabs.dim, device=codes.device, dtype=torch.float32)
     tb, ts, nt = (0, 0, 0) if text is None else (text.stride(0), text.stride(1), text.shape[1])
     _call("other", _lib.lib().b2a_embed_sum, 1, codes.data_ptr(), codes.stride(0), B, G, tabs.dim, tabs.ptrs.data_ptr(), tabs.bins.data_ptr(),
-          _p(text), tb, ts, nt, _p(pad), _p(step_dev), step_sub, out.data_ptr(), out.stride(0), _p(err), _stream())
+          _p(text), tb, ts, nt, _p(pad), _p(step_dev), step_sub, out.data_ptr(), out.stride(0), _p(err), _p(tidx), _p(finished), _stream())
     return out
 
 

@@ -209,10 +209,10 @@ class Model:
         t, cp = self.talker, self.talker.code_predictor
         B = x_in.shape[0]
         g = self.config.talker_config.num_code_groups
-        logits, hidden = t(x_in, use_device_offset=True)
+        logits, hidden = t(x_in, use_device_offset=True, kv_start=self._kv_start)
         ops.sample_token(logits[:, -1], temperature=sp["temperature"], top_k=sp["top_k"], top_p=sp["top_p"], u=self._u[0],
                          suppress_mask=self._suppress, seen=self._seen, repetition_penalty=sp["repetition_penalty"], mark_seen=True,
-                         out=self._codes[:, 0])
+                         out=self._codes[:, 0], finished=self._finished, eos=sp["eos"])
         inp0 = self._cp_in0                                                                  # [B,2,H]: (hidden, embed(token 0))
         ops.copy2d(hidden[:, -1], inp0[:, 0])
         ops.embed_sum(self._codes[:, 0:1], self._tab0, out=inp0[:, 1], err=self._err)
@@ -224,17 +224,26 @@ class Model:
                 lg = cp(e[:, None], ci + 1, ci)
             ops.sample_token(lg[:, -1], temperature=sp["temperature"], top_k=sp["top_k"], top_p=sp["top_p"], u=self._u[ci + 1],
                              out=self._codes[:, ci + 1])
-        ops.embed_sum(self._codes, self._tabs_all, text=self._trailing, pad=self._pad, step_dev=t.offset_dev, step_sub=self._prefill_len,
-                      out=self._x_in[:, 0], err=self._err)
+        if self._tidx is not None:      # batch rule: per-row trailing index, clamp-pad, advance unfinished rows (qwen3_tts.py:1903-1912)
+            ops.embed_sum(self._codes, self._tabs_all, text=self._trailing, pad=self._pad, out=self._x_in[:, 0], err=self._err,
+                          tidx=self._tidx, finished=self._finished)
+        else:
+            ops.embed_sum(self._codes, self._tabs_all, text=self._trailing, pad=self._pad, step_dev=t.offset_dev, step_sub=self._prefill_len,
+                          out=self._x_in[:, 0], err=self._err)
 
     @torch.no_grad()
     def generate_codes(self, input_embeds, trailing_text_hidden, tts_pad_embed, *, max_tokens: int = 4096, temperature: float = 0.9,
                        top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, u=None, seed: int = 0,
-                       use_graph: bool = True, stop_on_eos: bool = True) -> torch.Tensor:
+                       use_graph: bool = True, stop_on_eos: bool = True, left_padding=None, batch_mode: bool = False):
         """The generation loop of Model.generate for B prompts of equal prefill length: returns int64 codes [B, n_frames, 16]
         (B = 1: frames up to, not including, EOS; B > 1: until every row has hit EOS, rows padded with code 0 after their EOS,
         the convention of batch_generate / batch_decode).  ``u`` [max_tokens, 16, B] uniforms in [0,1) (drawn from ``seed`` when
-        omitted; parity tests inject them)."""
+        omitted; parity tests inject them).
+
+        ``batch_mode`` = the loop of ``batch_generate`` (qwen3_tts.py:1861-1935): ``left_padding`` [B] rows of zero embeddings in front
+        of shorter prompts (masked keys, positions from cumsum(mask) - 1), ``trailing_text_hidden`` [B, n, H] right-padded with the
+        pad embedding, finished rows forced to EOS, per-row trailing indices with the clamp-pad rule; returns (codes [B, n, 16],
+        lengths [B]) with rows zero-padded after their EOS."""
         t, cfg, dev = self.talker, self.config.talker_config, self.device
         x = input_embeds.to(dev).float().contiguous()
         B, P, H = x.shape
@@ -244,10 +253,18 @@ class Model:
             gen = torch.Generator(device=dev).manual_seed(seed)
             u = torch.rand(max_tokens, g, B, device=dev, generator=gen)
         u = u.to(dev).float().contiguous()
-        sp = {"temperature": float(temperature), "top_k": int(top_k), "top_p": float(top_p), "repetition_penalty": float(repetition_penalty)}
+        sp = {"temperature": float(temperature), "top_k": int(top_k), "top_p": float(top_p), "repetition_penalty": float(repetition_penalty),
+              "eos": int(eos)}
+        batch_mode = batch_mode or left_padding is not None
+        self._kv_start = None
+        if left_padding is not None and any(int(v) for v in left_padding):
+            self._kv_start = torch.tensor([int(v) for v in left_padding], dtype=torch.int32, device=dev)
+        self._finished = torch.zeros(B, dtype=torch.uint8, device=dev) if batch_mode else None
+        self._tidx = torch.zeros(B, dtype=torch.int32, device=dev) if batch_mode else None
         t.reset_cache(B, P + max_tokens + 1)
         self._prefill_len = P
-        self._trailing = trailing_text_hidden.to(dev).float().expand(B, -1, -1).contiguous()
+        self._trailing = trailing_text_hidden.to(dev).float().expand(B, -1, -1).contiguous() if trailing_text_hidden.shape[0] != B \
+            else trailing_text_hidden.to(dev).float().contiguous()
         self._pad = tts_pad_embed.to(dev).float().reshape(-1).contiguous()
         self._suppress = torch.zeros(V, device=dev)
         self._suppress[torch.tensor(self._suppress_codec_tokens(eos), device=dev)] = float("-inf")
@@ -259,6 +276,7 @@ class Model:
         self._cp_in = torch.zeros(B, H, device=dev)
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         out = torch.zeros(B, max_tokens, g, dtype=torch.int64, device=dev)
+        lengths = torch.zeros(B, dtype=torch.int64)
         done = torch.zeros(B, dtype=torch.bool)
         n = 0
         graph = None
@@ -271,17 +289,19 @@ class Model:
                     # warm-up on a side stream is not needed: every kernel has already run once in the prefill frame except
                     # the S = 1 GEMV variants, which the capture below launches for the first time (lazy module load is done).
                     torch.cuda.synchronize(dev)
-                    state = (t.offset_dev.clone(), self._seen.clone(), self._codes.clone(), self._x_in.clone())
+                    bufs = [t.offset_dev, self._seen, self._codes, self._x_in] + ([self._finished, self._tidx] if batch_mode else [])
+                    state = [b_.clone() for b_ in bufs]
+                    restore = lambda: [b_.copy_(s_) for b_, s_ in zip(bufs, state)]
                     l0 = ops.LAUNCHES[0]
                     self._frame(self._x_in, sp)                                      # eager run of the S = 1 path (loads kernels)
                     self._frame_launches = ops.LAUNCHES[0] - l0
-                    t.offset_dev.copy_(state[0]); self._seen.copy_(state[1]); self._codes.copy_(state[2]); self._x_in.copy_(state[3])
+                    restore()
                     t.offset = P + step - 1
                     torch.cuda.synchronize(dev)
                     graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(graph):
                         self._frame(self._x_in, sp)
-                    t.offset_dev.copy_(state[0]); self._seen.copy_(state[1]); self._codes.copy_(state[2]); self._x_in.copy_(state[3])
+                    restore()
                     t.offset = P + step - 1
                 graph.replay()
                 t.offset = P + step
@@ -292,7 +312,14 @@ class Model:
                 self._frame_launches = ops.LAUNCHES[0] - l0
             codes_h = self._codes.cpu()                                             # the per-frame sync (EOS test)
             hit = codes_h[:, 0] == eos
-            if stop_on_eos:
+            if batch_mode:
+                fin = self._finished.cpu().bool()
+                if bool(fin.all()):
+                    break
+                live = ~fin
+                out[live.to(dev), n] = self._codes[live.to(dev)]
+                lengths[live] += 1
+            elif stop_on_eos:
                 done |= hit
                 if bool(done.all()):
                     break
@@ -304,7 +331,54 @@ class Model:
         if int(self._err.item()) != 0:
             raise ValueError("generate_codes: a sampled code indexed outside its embedding table")
         self._graph = graph
+        if batch_mode:
+            return out[:, :n], lengths
         return out[:, :n]
+
+    # ------------------------------------------------------------------ batch generation
+    @torch.no_grad()
+    def prepare_batch_inputs_from_ids(self, ids_list, language_id=None, speaker_ids=None, instruct_ids=None):
+        """_prepare_batch_inputs (qwen3_tts.py:486-604) after tokenisation: left-pad the prompts with zero rows, right-pad the trailing
+        text with the pad embedding.  Returns (input_embeds [B,P,H], trailing [B,n,H], tts_pad [1,1,H], left_padding [B])."""
+        per = [self.prepare_generation_inputs_from_ids(ids, language_id, None if speaker_ids is None else speaker_ids[i],
+                                                       instruct_ids=None if instruct_ids is None else instruct_ids[i])
+               for i, ids in enumerate(ids_list)]
+        pad = per[0][2]
+        pmax = max(e.shape[1] for e, _, _ in per)
+        tmax = max(tr.shape[1] for _, tr, _ in per)
+        H = pad.shape[-1]
+        x = torch.zeros(len(per), pmax, H, device=self.device)
+        trailing = pad.reshape(1, 1, H).expand(len(per), tmax, H).clone()
+        left = []
+        for i, (e, tr, _) in enumerate(per):
+            left.append(pmax - e.shape[1])
+            x[i, pmax - e.shape[1]:] = e[0]
+            trailing[i, : tr.shape[1]] = tr[0]
+        return x, trailing, pad, left
+
+    def batch_generate_from_ids(self, ids_list, *, language_id=None, speaker_ids=None, temperature: float = 0.9, max_tokens: int = 4096,
+                                top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, seed: int = 0, u=None, **kwargs):
+        """``Model.batch_generate`` (qwen3_tts.py:1651-2060, non-streaming) for already-tokenised texts: one frame loop for the whole
+        batch, one batched vocoder pass, one BatchGenerationResult per sequence."""
+        from ..base import BatchGenerationResult
+        if self.speech_tokenizer is None:
+            raise ValueError("Speech tokenizer not loaded")
+        t0 = time.perf_counter()
+        x, trailing, pad, left = self.prepare_batch_inputs_from_ids(ids_list, language_id, speaker_ids)
+        codes, lengths = self.generate_codes(x, trailing, pad, max_tokens=max_tokens, temperature=temperature, top_k=top_k, top_p=top_p,
+                                             repetition_penalty=repetition_penalty, seed=seed, u=u, left_padding=left, batch_mode=True)
+        seqs = [codes[b, : int(lengths[b])] for b in range(codes.shape[0])]
+        audios, _ = self.speech_tokenizer.batch_decode([s_ for s_ in seqs if s_.shape[0] > 0])
+        torch.cuda.synchronize(self.device)
+        dt = time.perf_counter() - t0
+        it = iter(audios)
+        for b, s_ in enumerate(seqs):
+            if s_.shape[0] == 0:
+                continue
+            a = next(it)
+            yield BatchGenerationResult(audio=a, sequence_idx=b, samples=int(a.shape[0]), sample_rate=self.sample_rate, token_count=int(s_.shape[0]),
+                                        audio_duration=format_duration(a.shape[0] / self.sample_rate), processing_time_seconds=dt,
+                                        peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9, is_final_chunk=True)
 
     # ------------------------------------------------------------------ decode + public generate
     @torch.no_grad()

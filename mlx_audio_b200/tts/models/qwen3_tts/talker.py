@@ -66,7 +66,7 @@ class _DecoderStack:
         return ops.swiglu(y, interleaved=True) if swiglu else y
 
     def forward(self, x: torch.Tensor, *, base_dev=None, base: int = 0, pos3=None, kv_start=None, final_norm: bool = True,
-                tail=None) -> torch.Tensor:
+                tail=None, pos_shift=None) -> torch.Tensor:
         """x [B,S,H] -> final-normed hidden [B,S,H] (``final_norm=False``: the residual stream, for a consumer that fuses the
         norm); appends S rows to the cache at ``base`` (device scalar or host int).  ``tail``: the projection that follows the
         stack (head), prefetched into L2 by the last layer."""
@@ -77,13 +77,14 @@ class _DecoderStack:
         for li, lw in enumerate(self.layers):
             nxt_qkv = self.layers[li + 1]["qkv"] if li + 1 < len(self.layers) else tail
             qkv = self._proj(x2, lw["qkv"], norm_w=lw["n1"], nxt=lw["o"])
-            if S == 1 and hq == 2 * hk and hd in (64, 128) and FUSED_DECODE[0]:
+            if S == 1 and hq == 2 * hk and hd in (64, 128) and FUSED_DECODE[0] and pos_shift is None:
                 a = ops.attn_decode_fused(qkv, hq, hk, hd, self.kc[li], self.vc[li], scale=hd ** -0.5, q_norm=lw["qn"], k_norm=lw["kn"],
                                           eps=self.eps, pos3=pos3, base_dev=base_dev, base=base, mrope=self.mrope, theta=self.theta,
                                           kv_start=kv_start)
             else:
                 q = ops.qknorm_rope_cache(qkv.view(B, S, -1), hq, hk, hd, self.kc[li], self.vc[li], q_norm=lw["qn"], k_norm=lw["kn"],
-                                          eps=self.eps, pos3=pos3, base_dev=base_dev, base=base, mrope=self.mrope, theta=self.theta)
+                                          eps=self.eps, pos3=pos3, base_dev=base_dev, base=base, mrope=self.mrope, theta=self.theta,
+                                          pos_shift=pos_shift)
                 a = ops.attn_decode(q, self.kc[li], self.vc[li], hq, hk, hd, scale=hd ** -0.5, base_dev=base_dev, base=base,
                                     kv_start=kv_start, max_k=max_k)
             x2 = self._proj(a.view(B * S, hq * hd), lw["o"], res=x2, nxt=lw["gu"])
@@ -172,7 +173,9 @@ class Qwen3TTSTalkerForConditionalGeneration:
         self.offset = 0
 
     def __call__(self, inputs_embeds: torch.Tensor, position_ids=None, kv_start=None, use_device_offset: bool = False):
-        """inputs_embeds [B,S,H] -> (logits [B,S,V], hidden [B,S,H]); appends to the cache (talker.py:799-818)."""
+        """inputs_embeds [B,S,H] -> (logits [B,S,V], hidden [B,S,H]); appends to the cache (talker.py:799-818).  ``kv_start`` int32 [B]
+        = left-padding count per row: the ``attention_mask`` path of talker.py:449-476 (keys before it are masked, rotary positions are
+        cumsum(mask) - 1 = cache row - kv_start, clamped at 0)."""
         B, S, _ = inputs_embeds.shape
         pos3 = None
         if position_ids is not None:
@@ -181,10 +184,12 @@ class Qwen3TTSTalkerForConditionalGeneration:
                 pos3 = pos3[None].expand(3, -1, -1)
             pos3 = pos3.contiguous()
         if use_device_offset:
-            h = self.stack.forward(inputs_embeds, base_dev=self.offset_dev, pos3=pos3, kv_start=kv_start, tail=self.codec_head)
+            h = self.stack.forward(inputs_embeds, base_dev=self.offset_dev, pos3=pos3, kv_start=kv_start, tail=self.codec_head,
+                                   pos_shift=kv_start if pos3 is None else None)
             ops.incr_(self.offset_dev, S)
         else:
-            h = self.stack.forward(inputs_embeds, base=self.offset, pos3=pos3, kv_start=kv_start, tail=self.codec_head)
+            h = self.stack.forward(inputs_embeds, base=self.offset, pos3=pos3, kv_start=kv_start, tail=self.codec_head,
+                                   pos_shift=kv_start if pos3 is None else None)
             ops.incr_(self.offset_dev, S)
         self.offset += S
         logits = self.stack._proj(h.reshape(B * S, -1), self.codec_head, nxt=self.code_predictor.stack.layers[0]["qkv"]).view(B, S, -1)

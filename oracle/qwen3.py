@@ -132,17 +132,27 @@ def cache_offset(caches):
     return 0 if caches is None or "k" not in caches[0] else caches[0]["k"].shape[2]
 
 
-def talker_forward(P, inputs_embeds, caches=None, position_ids=None, cfg=TALKER):
+def talker_forward(P, inputs_embeds, caches=None, position_ids=None, cfg=TALKER, attention_mask=None):
     """Qwen3TTSTalkerForConditionalGeneration.__call__ (talker.py:799-818) over Qwen3TTSTalkerModel.__call__
-    (talker.py:435-496), no attention_mask: inputs_embeds [B,S,1024] -> (logits [B,S,3072], hidden [B,S,1024])."""
+    (talker.py:435-496): inputs_embeds [B,S,1024] -> (logits [B,S,3072], hidden [B,S,1024]).  ``attention_mask`` [B, total_kv] (1 = real
+    token) is the left-padded batch path (:449-476): positions cumsum(mask)-1 clamped at 0, additive -1e9 on padded keys."""
     b, s, _ = inputs_embeds.shape
     off = cache_offset(caches)
+    dt = inputs_embeds.dtype
     if position_ids is None:
-        position_ids = torch.arange(off, off + s)[None, :].expand(b, s)
-    cos, sin = mrope_cos_sin(position_ids, cfg["head_dim"], cfg["rope_theta"], cfg["mrope_section"], inputs_embeds.dtype)
-    mask = causal_mask(s, s, inputs_embeds.dtype) if s > 1 else None      # reference builds [S,S] (prefill starts at offset 0)
-    if mask is not None and off > 0:
-        mask = torch.cat([torch.zeros(s, off, dtype=mask.dtype), mask], dim=1)
+        if attention_mask is not None:
+            pos = torch.clamp(torch.cumsum(attention_mask.to(torch.int64), dim=-1) - 1, min=0)[:, -s:]
+            position_ids = torch.stack([pos, pos, pos], dim=0)
+        else:
+            position_ids = torch.arange(off, off + s)[None, :].expand(b, s)
+    cos, sin = mrope_cos_sin(position_ids, cfg["head_dim"], cfg["rope_theta"], cfg["mrope_section"], dt)
+    if attention_mask is not None:
+        pad = (1 - attention_mask[:, None, None, :].to(dt)) * -1e9            # [B,1,1,total]
+        mask = causal_mask(s, s, dt)[None, None] + pad if s > 1 else pad
+    else:
+        mask = causal_mask(s, s, dt) if s > 1 else None      # reference builds [S,S] (prefill starts at offset 0)
+        if mask is not None and off > 0:
+            mask = torch.cat([torch.zeros(s, off, dtype=mask.dtype), mask], dim=1)
     h = _decoder_stack(P, "model", inputs_embeds, cos, sin, caches, cfg["num_hidden_layers"], cfg["num_attention_heads"],
                        cfg["num_key_value_heads"], cfg["head_dim"], cfg["rms_norm_eps"], mask)
     return N.linear(h, P["codec_head.weight"]), h
@@ -272,6 +282,73 @@ def generate_codes(P, input_embeds, trailing_text_hidden, tts_pad_embed, u, max_
         generated.append(tok)
         out.append(codes)
     return torch.tensor(out, dtype=torch.int64).reshape(-1, g)
+
+
+def generate_codes_batch(P, embeds_list, trailing_list, tts_pad_embed, u, max_tokens, temperature=0.9, top_k=50, top_p=1.0,
+                         repetition_penalty=1.05, cfg=TALKER):
+    """Model.batch_generate's loop (qwen3_tts.py:1861-1935) over _prepare_batch_inputs' padding (:486-604): prompts left-padded with
+    zero rows + attention mask, trailing text right-padded with the pad embedding, finished rows forced to EOS, trailing indices
+    advanced for unfinished rows only, next input through _next_batch_input_embeds(pad_when_index_clamped=True) (:993-1015).
+    ``u`` [max_tokens, 16, B].  Returns a list of int64 code matrices [n_b, 16]."""
+    B = len(embeds_list)
+    g, eos = cfg["num_code_groups"], cfg["codec_eos_token_id"]
+    H = embeds_list[0].shape[-1]
+    dt = embeds_list[0].dtype
+    pmax = max(e.shape[1] for e in embeds_list)
+    tmax = max(t.shape[1] for t in trailing_list)
+    x = torch.zeros(B, pmax, H, dtype=dt)
+    mask = torch.zeros(B, pmax, dtype=dt)
+    trailing = tts_pad_embed.reshape(1, 1, H).expand(B, tmax, H).clone()
+    for i, (e, t) in enumerate(zip(embeds_list, trailing_list)):
+        x[i, pmax - e.shape[1]:] = e[0]
+        mask[i, pmax - e.shape[1]:] = 1
+        trailing[i, : t.shape[1]] = t[0]
+    suppress = [i for i in range(cfg["vocab_size"] - 1024, cfg["vocab_size"]) if i != eos]
+    cache = make_cache(cfg["num_hidden_layers"])
+    gen_ids = [[] for _ in range(B)]
+    out = [[] for _ in range(B)]
+    finished = [False] * B
+    tidx = [0] * B
+    emb0 = P["model.codec_embedding.weight"]
+    amask = mask if B > 1 else None                                       # bs = 1 drops the mask (:1826-1829)
+    for step in range(max_tokens):
+        logits, hidden = talker_forward(P, x, cache, cfg=cfg, attention_mask=amask)
+        toks = []
+        for b in range(B):
+            tk = sample_token(logits[b, -1], u[step, 0, b], temperature, top_k, top_p, repetition_penalty, gen_ids[b] or None, suppress)
+            toks.append(eos if finished[b] else tk)
+        finished = [f or tk == eos for f, tk in zip(finished, toks)]
+        codes = [[tk] for tk in toks]
+        code_cache = make_cache(cfg["cp_num_hidden_layers"])
+        first = torch.tensor(toks)[:, None]
+        for ci in range(g - 1):
+            if ci == 0:
+                inp = torch.cat([hidden[:, -1:, :], emb0[first]], dim=1)
+            else:
+                inp = P[f"code_predictor.model.codec_embedding.{ci - 1}.weight"][torch.tensor([c[-1] for c in codes])[:, None]]
+            cl = code_predictor_forward(P, inp, code_cache, ci, cfg)
+            for b in range(B):
+                codes[b].append(sample_token(cl[b, -1], u[step, ci + 1, b], temperature, top_k, top_p, 1.05, None, None))
+        nxt = []
+        for b in range(B):
+            cl_i = min(tidx[b], tmax - 1)
+            text = tts_pad_embed.reshape(1, H) if cl_i >= tmax - 1 else trailing[b, cl_i: cl_i + 1]
+            ce = emb0[codes[b][0]][None]
+            for i, c in enumerate(codes[b][1:]):
+                ce = ce + P[f"code_predictor.model.codec_embedding.{i}.weight"][c][None]
+            nxt.append(text + ce)
+            if not finished[b]:
+                tidx[b] += 1
+        x = torch.stack(nxt, dim=0)
+        if all(finished):
+            break
+        for b in range(B):
+            if not finished[b]:
+                gen_ids[b].append(toks[b])
+                out[b].append(codes[b])
+        if amask is not None:
+            amask = torch.cat([amask, torch.ones(B, 1, dtype=dt)], dim=1)
+    return [torch.tensor(o, dtype=torch.int64).reshape(-1, g) for o in out]
 
 
 # ------------------------------------------------------------------------------------------------ speech-tokenizer decoder

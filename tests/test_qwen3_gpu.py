@@ -228,3 +228,46 @@ def test_generate_from_ids_end_to_end():
     assert float(r.audio.abs().max()) <= 1.0
     with pytest.raises(ValueError, match="Tokenizer not loaded"):
         next(model.generate("hello"))
+
+
+@pytest.mark.parametrize("use_graph", [True, False])
+def test_batch_generate_codes_left_padded_bit_exact(use_graph):
+    """batch_generate's loop (qwen3_tts.py:1861-1935) with prompts of different lengths: left padding + key masking + cumsum positions,
+    right-padded trailing text with the clamp-pad rule, a row that hits EOS early is frozen at EOS and stops advancing its text."""
+    model, Pt, flat = _talker({"num_hidden_layers": 3, "cp_num_hidden_layers": 2})
+    tc = model.config.talker_config
+    cfg_ids = {k: getattr(tc, k) for k in ("codec_nothink_id", "codec_think_id", "codec_think_bos_id", "codec_think_eos_id", "codec_pad_id", "codec_bos_id")}
+    g = torch.Generator().manual_seed(21)
+    ids_list = [torch.randint(0, 500, (n,), generator=g).tolist() for n in (15, 11, 13)]
+    refs = [Q.prepare_generation_inputs_from_ids(Pt, ids, (501, 502, 500), cfg_ids, language_id=2050) for ids in ids_list]
+    x, trailing, pad, left = model.prepare_batch_inputs_from_ids(ids_list, language_id=2050)
+    assert left == [0, 4, 2] and x.shape[0] == 3 and float(x[1, :4].abs().max()) == 0.0
+    u = torch.rand(9, 16, 3, generator=g)
+    want = Q.generate_codes_batch(Pt, [r[0] for r in refs], [r[1] for r in refs], refs[0][2], u.double(), 9, cfg=flat)
+    codes, lengths = model.generate_codes(x, trailing, pad, max_tokens=9, u=u, left_padding=left, batch_mode=True, use_graph=use_graph)
+    assert lengths.tolist() == [w.shape[0] for w in want] == [9, 9, 9]
+    for b in range(3):
+        assert torch.equal(codes[b, : int(lengths[b])].cpu(), want[b]), b
+    # EOS for row 1 at its 4th frame: it stops there, the others run on
+    eos = int(want[1][3, 0])
+    flat2 = dict(flat, codec_eos_token_id=eos)
+    tc.codec_eos_token_id = eos
+    want2 = Q.generate_codes_batch(Pt, [r[0] for r in refs], [r[1] for r in refs], refs[0][2], u.double(), 9, cfg=flat2)
+    codes2, lengths2 = model.generate_codes(x, trailing, pad, max_tokens=9, u=u, left_padding=left, batch_mode=True, use_graph=use_graph)
+    assert lengths2.tolist() == [w.shape[0] for w in want2] and want2[1].shape[0] <= 3
+    for b in range(3):
+        assert torch.equal(codes2[b, : int(lengths2[b])].cpu(), want2[b]), b
+        assert int(codes2[b, int(lengths2[b]):].abs().sum()) == 0
+
+
+def test_batch_generate_from_ids_results():
+    """BatchGenerationResult contract (tts/models/base.py:89-99): one result per sequence, 1920 samples per generated frame."""
+    model, Pt, flat = _talker({"num_hidden_layers": 2, "cp_num_hidden_layers": 1})
+    st, _, _ = _tokenizer()
+    model.load_speech_tokenizer(st)
+    g = torch.Generator().manual_seed(8)
+    ids_list = [torch.randint(0, 500, (n,), generator=g).tolist() for n in (12, 16)]
+    res = list(model.batch_generate_from_ids(ids_list, max_tokens=4, seed=3))
+    assert [r.sequence_idx for r in res] == [0, 1]
+    for r in res:
+        assert r.sample_rate == 24000 and r.token_count == 4 and r.samples == r.audio.shape[0] == 4 * 1920 and r.is_final_chunk
