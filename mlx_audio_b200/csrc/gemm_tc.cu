@@ -414,7 +414,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
 // (366 tiles on 296 CTA slots = 2 waves), (b) the per-tile prologue (barrier init, TMEM alloc, descriptor prefetch) and
 // (c) the serialisation of main loop and epilogue inside a CTA; with one CTA per SM the operand ring is as deep as shared
 // memory allows.  smem: [stages] x { A planes | W planes } | 8 x 32x33 fp32 transpose tiles | barriers.
-constexpr int PERSIST_THREADS = 320;
+constexpr int PERSIST_THREADS = 352;     // warp 0 TMA (W / classic), warp 1 MMA, warps 2..9 epilogue, warp 10 A-tile producer (reuse mode)
 constexpr int PERSIST_STAGING = 8 * 32 * 33 * 4;
 
 __global__ void __launch_bounds__(PERSIST_THREADS, 1)
@@ -426,12 +426,19 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int a_bytes = TM * 128, w_bytes = p.BN * 128;
   const int stage_bytes = a_bytes * p.planes + w_bytes * p.wplanes;
-  float* staging = reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* full = (uint64_t*)(smem + (size_t)p.stages * stage_bytes + PERSIST_STAGING);
-  uint64_t* empty = full + p.stages;
-  uint64_t* tfull = empty + p.stages;          // [2]
+  // classic: [stages] x {A planes | W planes};  reuse: [2] x A super-tile planes (R rows) | [wst] x W planes.  Then staging, barriers.
+  const int a_rbytes = p.R * 128, a_buf = a_rbytes * p.planes, w_stage = w_bytes * p.wplanes;
+  const size_t ring_bytes = p.reuse ? (size_t)2 * a_buf + (size_t)p.wst * w_stage : (size_t)p.stages * stage_bytes;
+  uint8_t* wbase = smem + (size_t)2 * a_buf;
+  const int nring = p.reuse ? p.wst : p.stages;
+  float* staging = reinterpret_cast<float*>(smem + ring_bytes);
+  uint64_t* full = (uint64_t*)(smem + ring_bytes + PERSIST_STAGING);
+  uint64_t* empty = full + nring;
+  uint64_t* tfull = empty + nring;             // [2]
   uint64_t* tempty = tfull + 2;                // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* a_full = tempty + 2;               // [2] (reuse mode)
+  uint64_t* a_empty = a_full + 2;              // [2]
+  uint32_t* tmem_slot = (uint32_t*)(a_empty + 2);
   const int kchunks = p.cin_pad / TK;
   const int iters = p.taps * kchunks;
   const uint32_t tmem_cols = (uint32_t)(2 * p.BN);
@@ -441,8 +448,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wlo) : "memory");
-    for (int s = 0; s < p.stages; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int s = 0; s < nring; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(tfull, 1); mbar_init(tfull + 1, 1); mbar_init(tempty, 8); mbar_init(tempty + 1, 8);
+    mbar_init(a_full, 1); mbar_init(a_full + 1, 1); mbar_init(a_empty, 1); mbar_init(a_empty + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -455,7 +463,41 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 0 && p.reuse) {
+    // ===== W producer (reuse mode): one weight tile per (K chunk, tap) =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n0 = (tile % ntn) * p.BN;
+        for (int i = 0; i < iters; i++, it++) {
+          const int kc = i / p.taps, tap = i - kc * p.taps;
+          const int s = it % p.wst, ph = (it / p.wst) & 1;
+          mbar_wait(empty + s, ph ^ 1);
+          uint8_t* st = wbase + (size_t)s * w_stage;
+          mbar_expect_tx(full + s, (uint32_t)w_stage);
+          tma_load_2d(st, &map_w, full + s, kc * TK, tap * p.Cout + n0);
+          if (p.wplanes == 2) tma_load_2d(st + w_bytes, &map_wlo, full + s, kc * TK, tap * p.Cout + n0);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===== A producer (reuse mode): one (128 + span)-row activation tile per K chunk, double-buffered =====
+    if (lane == 0 && p.reuse) {
+      uint32_t cg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = (tile / ntn) % ntm, b = tile / (ntn * ntm);
+        const int l0 = mt * TM;
+        for (int kc = 0; kc < kchunks; kc++, cg++) {
+          const uint32_t ab = cg & 1;
+          mbar_wait(a_empty + ab, ((cg >> 1) & 1) ^ 1);
+          uint8_t* dst = smem + (size_t)ab * a_buf;
+          mbar_expect_tx(a_full + ab, (uint32_t)a_buf);
+          tma_load_3d(dst, &map_hi, a_full + ab, kc * TK, l0 + p.shift_min, b);
+          if (p.planes == 2) tma_load_3d(dst + a_rbytes, &map_lo, a_full + ab, kc * TK, l0 + p.shift_min, b);
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===== TMA producer: runs ahead across tile boundaries, bounded only by the operand ring =====
     if (lane == 0) {
       uint32_t it = 0;
@@ -472,6 +514,45 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           if (p.planes == 2) tma_load_3d(st + a_bytes, &map_lo, full + s, kc * TK, l0 + p.shift[tap], b);
           tma_load_2d(st + (size_t)a_bytes * p.planes, &map_w, full + s, kc * TK, tap * p.Cout + n0);
           if (p.wplanes == 2) tma_load_2d(st + (size_t)a_bytes * p.planes + w_bytes, &map_wlo, full + s, kc * TK, tap * p.Cout + n0);
+        }
+      }
+    }
+  } else if (warp == 1 && p.reuse) {
+    // ===== MMA issuer (reuse mode): tap t reads rows [shift_t - shift_min, +128) of the resident A tile =====
+    const uint32_t fmt = p.f16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    const uint32_t a0 = smem_u32(smem);
+    uint32_t it = 0, lt = 0, cg = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      mbar_wait(tempty + buf, (use & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + buf * (uint32_t)p.BN;
+      for (int kc = 0; kc < kchunks; kc++, cg++) {
+        const uint32_t ab = cg & 1;
+        mbar_wait(a_full + ab, (cg >> 1) & 1);
+        for (int tap = 0; tap < p.taps; tap++, it++) {
+          const int s = it % p.wst, ph = (it / p.wst) & 1;
+          mbar_wait(full + s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t wst_addr = smem_u32(wbase + (size_t)s * w_stage);
+            const uint32_t abase = a0 + ab * (uint32_t)a_buf + (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
+            for (int wp = 0; wp < p.wplanes; wp++) {
+              const uint64_t wdesc = umma_desc_sw128(wst_addr + wp * w_bytes);
+              const int npl = wp == 0 ? p.planes : 1;
+              for (int pl = 0; pl < npl; pl++) {
+                const uint64_t adesc = umma_desc_sw128(abase + pl * a_rbytes);
+#pragma unroll
+                for (int k = 0; k < TK / UMMA_K; k++)
+                  umma_bf16(tacc, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (kc | tap | wp | pl | k) != 0);
+              }
+            }
+            umma_commit(empty + s);
+            if (tap == p.taps - 1) umma_commit(a_empty + ab);
+            if (kc == kchunks - 1 && tap == p.taps - 1) umma_commit(tfull + buf);
+          }
+          __syncwarp();
         }
       }
     }
@@ -507,7 +588,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ===== epilogue (8 warps): quarter = warp % 4 selects the TMEM lanes, sub = (warp - 2) / 4 the 32-column chunks it owns =====
     const int quarter = warp & 3, sub = (warp - 2) >> 2;
     float* stage = staging + (warp - 2) * (32 * 33);
@@ -777,6 +858,45 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
     }
   }
 
+  // ---- persistent kernel (default): stage count / A-reuse layout that fit one CTA per SM
+  static int persist_on = -1, preuse_on = -1, nsm = 0;
+  if (persist_on < 0) {
+    const char* e = getenv("B2A_TC_PERSIST"); persist_on = (e && e[0] == '0') ? 0 : 1;
+    const char* r = getenv("B2A_TC_PREUSE"); preuse_on = (r && r[0] == '0') ? 0 : 1;
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+  }
+  bool use_persist = false;
+  TcParams pq = p;
+  size_t psm = 0;
+  if (persist_on && !p.reuse && !p.dbg && 2 * p.BN <= 512) {
+    const size_t budget = (size_t)227 * 1024 - PERSIST_STAGING - 2048;
+    if (preuse_on && !up_stride && taps >= 2) {
+      int smin = p.shift[0], smax = p.shift[0];
+      for (int i = 1; i < taps; i++) { smin = p.shift[i] < smin ? p.shift[i] : smin; smax = p.shift[i] > smax ? p.shift[i] : smax; }
+      const int span = smax - smin;
+      const int R = (TM + span + 7) / 8 * 8;
+      const size_t a2 = (size_t)2 * R * 128 * p.planes, w_stage = (size_t)p.BN * 128 * p.wplanes;
+      if (span <= 64 && a2 + 2 * w_stage <= budget) {
+        int wst = (int)((budget - a2) / w_stage);
+        if (wst > 8) wst = 8;
+        pq.reuse = 1; pq.R = R; pq.shift_min = smin; pq.wst = wst;
+        a_box_rows = (uint32_t)R;
+        psm = a2 + (size_t)wst * w_stage + PERSIST_STAGING + 1024 + (2 * wst + 8) * 8 + 64;
+        use_persist = true;
+      }
+    }
+    if (!use_persist) {
+      int pst = (int)(budget / stage_bytes);
+      if (pst > 6) pst = 6;
+      if (pst >= 2) {
+        pq.stages = pst; pq.reuse = 0; pq.R = TM; pq.wst = 0;
+        psm = (size_t)pst * stage_bytes + PERSIST_STAGING + 1024 + (2 * pst + 8) * 8 + 64;
+        use_persist = true;
+      }
+    }
+  }
+
   CUtensorMap mh, ml, mw, mwl;
   uint64_t adims[3] = {(uint64_t)cin_pad, (uint64_t)L, (uint64_t)B};
   uint64_t astr[2] = {(uint64_t)cin_pad * 2, (uint64_t)cin_pad * 2 * (uint64_t)L};
@@ -796,25 +916,12 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
     cudaFuncSetAttribute(conv_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
-  static int persist_on = -1, nsm = 0;
-  if (persist_on < 0) {
-    const char* e = getenv("B2A_TC_PERSIST"); persist_on = (e && e[0] == '0') ? 0 : 1;
-    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    if (nsm <= 0) nsm = 148;
-  }
-  if (persist_on && !p.reuse && !p.dbg) {
-    int pst = (int)((227 * 1024 - PERSIST_STAGING - 2048) / stage_bytes);
-    if (pst > 6) pst = 6;
-    if (pst >= 2 && 2 * p.BN <= 512) {
-      TcParams q = p;
-      q.stages = pst;
-      const int ntm = cdiv(p.Mrows, TM), ntn = Cout / p.BN, ntiles = ntm * ntn * B;
-      const size_t psm = (size_t)pst * stage_bytes + PERSIST_STAGING + 1024 + (2 * pst + 4) * 8 + 64;
-      const int g = ntiles < nsm ? ntiles : nsm;
-      conv_tc_persist_kernel<<<g, PERSIST_THREADS, psm, (cudaStream_t)stream>>>(mh, ml, mw, mwl, q, ntm, ntn, ntiles);
-      B2A_CHECK_LAUNCH();
-      return B2A_OK;
-    }
+  if (use_persist) {
+    const int ntm = cdiv(p.Mrows, TM), ntn = Cout / p.BN, ntiles = ntm * ntn * B;
+    const int g = ntiles < nsm ? ntiles : nsm;
+    conv_tc_persist_kernel<<<g, PERSIST_THREADS, psm, (cudaStream_t)stream>>>(mh, ml, mw, mwl, pq, ntm, ntn, ntiles);
+    B2A_CHECK_LAUNCH();
+    return B2A_OK;
   }
   dim3 grid(cdiv(p.Mrows, TM), Cout / p.BN, B);
   conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(mh, ml, mw, mwl, p);

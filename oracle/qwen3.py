@@ -478,7 +478,7 @@ def speech_tokenizer_decode(P, audio_codes, cfg=TOKENIZER_DECODER):
     return wav, lengths
 
 
-def prepare_generation_inputs_from_ids(P, input_ids, tts_ids, cfg_ids, language_id=None, speaker_id=None):
+def prepare_generation_inputs_from_ids(P, input_ids, tts_ids, cfg_ids, language_id=None, speaker_id=None, instruct_ids=None):
     """Model._prepare_generation_inputs (qwen3_tts.py:326-484) after tokenisation.  ``tts_ids`` = (bos, eos, pad) text-token ids
     (config.py:218-220); ``cfg_ids`` = dict with codec_nothink_id, codec_think_id, codec_think_bos_id, codec_think_eos_id,
     codec_pad_id, codec_bos_id (config.py:84-92)."""
@@ -501,6 +501,9 @@ def prepare_generation_inputs_from_ids(P, input_ids, tts_ids, cfg_ids, language_
     role = text_embed[:, :3]
     combined = torch.cat([tts_pad.expand(1, codec.shape[1] - 2, -1), tts_bos], dim=1) + codec[:, :-1]
     first_text = text_embed[:, 3:4] + codec[:, -1:]
-    input_embeds = torch.cat([role, combined, first_text], dim=1)
+    parts = [role, combined, first_text]
+    if instruct_ids is not None:                                       # instruct embedding is prepended (qwen3_tts.py:452-458,473-476)
+        parts = [text_projection(te[torch.as_tensor(instruct_ids, dtype=torch.int64).reshape(1, -1)])] + parts
+    input_embeds = torch.cat(parts, dim=1)
     trailing = torch.cat([text_embed[:, 4:-5], tts_eos], dim=1)
     return input_embeds, trailing, tts_pad

@@ -239,9 +239,11 @@ def test_batch_generate_codes_left_padded_bit_exact(use_graph):
     cfg_ids = {k: getattr(tc, k) for k in ("codec_nothink_id", "codec_think_id", "codec_think_bos_id", "codec_think_eos_id", "codec_pad_id", "codec_bos_id")}
     g = torch.Generator().manual_seed(21)
     ids_list = [torch.randint(0, 500, (n,), generator=g).tolist() for n in (15, 11, 13)]
-    refs = [Q.prepare_generation_inputs_from_ids(Pt, ids, (501, 502, 500), cfg_ids, language_id=2050) for ids in ids_list]
-    x, trailing, pad, left = model.prepare_batch_inputs_from_ids(ids_list, language_id=2050)
-    assert left == [0, 4, 2] and x.shape[0] == 3 and float(x[1, :4].abs().max()) == 0.0
+    spk, ins = [2100, None, None], [None, None, [7, 8, 9, 10, 11]]          # a speaker row (+1) and an instruct row (+5): three prefill lengths
+    refs = [Q.prepare_generation_inputs_from_ids(Pt, ids, (501, 502, 500), cfg_ids, language_id=2050, speaker_id=spk[i], instruct_ids=ins[i])
+            for i, ids in enumerate(ids_list)]
+    x, trailing, pad, left = model.prepare_batch_inputs_from_ids(ids_list, language_id=2050, speaker_ids=spk, instruct_ids=ins)
+    assert left == [4, 5, 0] and x.shape[0] == 3 and float(x[1, :5].abs().max()) == 0.0
     u = torch.rand(9, 16, 3, generator=g)
     want = Q.generate_codes_batch(Pt, [r[0] for r in refs], [r[1] for r in refs], refs[0][2], u.double(), 9, cfg=flat)
     codes, lengths = model.generate_codes(x, trailing, pad, max_tokens=9, u=u, left_padding=left, batch_mode=True, use_graph=use_graph)
