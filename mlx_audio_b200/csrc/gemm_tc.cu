@@ -28,6 +28,8 @@ constexpr int TM = 128;            // rows (positions) per CTA tile == UMMA_M
 constexpr int TK = 64;             // bf16 elements per 128-byte swizzle row == K extent of one stage
 constexpr int UMMA_K = 16;
 
+__host__ __device__ __forceinline__ uint32_t pow2_cols(uint32_t n) { uint32_t c = 32; while (c < n) c <<= 1; return c; }   // TMEM allocations are powers of two >= 32
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -140,7 +142,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {                                    // TMEM: BN fp32 accumulator columns (power of two >= 32)
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.BN) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(pow2_cols((uint32_t)p.BN)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -177,7 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(r_slot)), "r"((uint32_t)p.BN) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(r_slot)), "r"(pow2_cols((uint32_t)p.BN)) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -403,7 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
   if (dbg && threadIdx.x == 0) p.dbg[6] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(pow2_cols((uint32_t)p.BN)) : "memory");
   }
 }
 
@@ -441,7 +443,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
   uint32_t* tmem_slot = (uint32_t*)(a_empty + 2);
   const int kchunks = p.cin_pad / TK;
   const int iters = p.taps * kchunks;
-  const uint32_t tmem_cols = (uint32_t)(2 * p.BN);
+  const uint32_t tbuf_stride = pow2_cols((uint32_t)p.BN);      // second accumulator starts on a power-of-two column
+  const uint32_t tmem_cols = 2 * tbuf_stride;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
@@ -527,7 +530,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       const uint32_t buf = lt & 1, use = lt >> 1;
       mbar_wait(tempty + buf, (use & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + buf * (uint32_t)p.BN;
+      const uint32_t tacc = tmem_base + buf * tbuf_stride;
       for (int kc = 0; kc < kchunks; kc++, cg++) {
         const uint32_t ab = cg & 1;
         mbar_wait(a_full + ab, (cg >> 1) & 1);
@@ -565,7 +568,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       const uint32_t buf = lt & 1, use = lt >> 1;
       mbar_wait(tempty + buf, (use & 1) ^ 1);                 // the epilogue has drained this accumulator (first use: free)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + buf * (uint32_t)p.BN;
+      const uint32_t tacc = tmem_base + buf * tbuf_stride;
       for (int i = 0; i < iters; i++, it++) {
         const int s = it % p.stages, ph = (it / p.stages) & 1;
         mbar_wait(full + s, ph);
@@ -616,7 +619,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       const int mrow0 = l0 + quarter * 32;
       for (int c0 = sub * 32; c0 < p.BN; c0 += 64) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + buf * (uint32_t)p.BN + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld32(tmem_base + buf * tbuf_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
         if (mrow0 >= p.Mrows) continue;
 #pragma unroll
         for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
@@ -811,7 +814,18 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
   // N tile: 256 halves the A re-reads per output but only pays once the grid fills the machine; otherwise 128 (more CTAs)
   const int mtiles = cdiv(up_stride ? L + taps - 1 : Lout, TM) * B;
-  p.BN = (Cout % 256 == 0 && mtiles * (Cout / 256) >= 148) ? 256 : ((Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32));
+  // N tile = a divisor of Cout, multiple of 32 (the epilogue's chunk), <= 256 (UMMA N): the largest one that still gives every SM a
+  // tile; when the problem is too small for that, the smallest one >= 64 (more CTAs).  96 / 192 matter: the Qwen3 vocoder's
+  // 96-, 192- and 384-channel blocks would otherwise run as 32-/64-/128-wide tiles and re-read A three times.
+  {
+    int best = 0, smallest = 0;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      if (Cout % bn) continue;
+      if (!best && (int64_t)mtiles * (Cout / bn) >= 148) best = bn;
+      if (bn >= 64 || !smallest) smallest = bn;
+    }
+    p.BN = best ? best : smallest;
+  }
   for (int i = 0; i < taps; i++) p.shift[i] = shifts_host[i];
   p.bias = bias; p.post_act = post_act; p.post_p0 = post_p0; p.cscale = cscale; p.cscale_bs = cscale_bs;
   p.res = res; p.res_bs = res_bs; p.res_ld = res_ld; p.res_div = res_div; p.out_scale = out_scale; p.accumulate = accumulate;

@@ -28,6 +28,9 @@ CASES = [
     (1, 129, 96, 32, 5, 2, 4),
     (1, 5000, 128, 128, 3, 1, 1),
     (1, 3000, 64, 64, 1, 1, 0),
+    (2, 700, 96, 96, 7, 9, 54),          # Qwen3 vocoder block 4: N tile 96, taps spanning 54 rows
+    (1, 40000, 192, 192, 7, 3, 18),      # N tile 192, > 148 tiles: persistent kernel with several tiles per CTA
+    (1, 600, 384, 384, 1, 1, 0),
 ]
 
 
