@@ -814,17 +814,17 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   p.B = B; p.L = L; p.Lout = Lout; p.Cout = Cout; p.cin_pad = cin_pad; p.taps = taps; p.planes = a_lo ? 2 : 1;
   // N tile: 256 halves the A re-reads per output but only pays once the grid fills the machine; otherwise 128 (more CTAs)
   const int mtiles = cdiv(up_stride ? L + taps - 1 : Lout, TM) * B;
-  // N tile = a divisor of Cout, multiple of 32 (the epilogue's chunk), <= 256 (UMMA N): the largest one that still gives every SM a
-  // tile; when the problem is too small for that, the smallest one >= 64 (more CTAs).  96 / 192 matter: the Qwen3 vocoder's
+  // N tile = a divisor of Cout, multiple of 32 (the epilogue's chunk), <= 256 (UMMA N): the largest one >= 128 that still gives every
+  // SM a tile; when the problem is too small for that, the widest one <= 128 (more CTAs; narrower tiles measured slower on Kokoro).  96 / 192 matter: the Qwen3 vocoder's
   // 96-, 192- and 384-channel blocks would otherwise run as 32-/64-/128-wide tiles and re-read A three times.
   {
-    int best = 0, smallest = 0;
+    int best = 0, fallback = 0;
     for (int bn = 256; bn >= 32; bn -= 32) {
       if (Cout % bn) continue;
-      if (!best && (int64_t)mtiles * (Cout / bn) >= 148) best = bn;
-      if (bn >= 64 || !smallest) smallest = bn;
+      if (!best && bn >= 128 && (int64_t)mtiles * (Cout / bn) >= 148) best = bn;   // wide tile that still gives every SM work
+      if (!fallback && bn <= 128) fallback = bn;                                    // else the widest tile <= 128 (more CTAs)
     }
-    p.BN = best ? best : smallest;
+    p.BN = best ? best : fallback;
   }
   for (int i = 0; i < taps; i++) p.shift[i] = shifts_host[i];
   p.bias = bias; p.post_act = post_act; p.post_p0 = post_p0; p.cscale = cscale; p.cscale_bs = cscale_bs;
