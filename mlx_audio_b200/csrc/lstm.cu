@@ -109,7 +109,7 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
   const int gate = r >> 5, unit = r & 31;
   const int grow = gate * LH + rank * UPC + unit;
   __shared__ __align__(16) float hbuf[2][LH];
-  __shared__ float gates[2][4 * UPC];                                // double-buffered: one __syncthreads per step
+  __shared__ float gates[4 * UPC];
   __shared__ __align__(8) uint64_t hbar[2];                         // hbar[i]: "hbuf[i] holds the complete h of a step"
 
   float w[128];
@@ -148,33 +148,25 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
     if (half == 0 && step + 1 < T) xp_next = __ldg(xp_base + (int64_t)(dir == 0 ? t + 1 : t - 1) * 2 * 4 * LH);
     if (step > 0) bar_wait_cluster(smem_addr(&hbar[cur]), ((step - 1) >> 1) & 1);     // h of step-1 complete in hbuf[cur]
     const float* hp = &hbuf[cur][half * 128];
-    // four independent FMA chains (the step is latency-bound: 32 dependent FMAs instead of 64)
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 128; j += 16) {
+    for (int j = 0; j < 128; j += 8) {
       float4 a = *reinterpret_cast<const float4*>(hp + j);
       float4 e = *reinterpret_cast<const float4*>(hp + j + 4);
-      float4 f = *reinterpret_cast<const float4*>(hp + j + 8);
-      float4 g = *reinterpret_cast<const float4*>(hp + j + 12);
       s0 = fmaf(w[j], a.x, s0); s0 = fmaf(w[j + 1], a.y, s0); s0 = fmaf(w[j + 2], a.z, s0); s0 = fmaf(w[j + 3], a.w, s0);
       s1 = fmaf(w[j + 4], e.x, s1); s1 = fmaf(w[j + 5], e.y, s1); s1 = fmaf(w[j + 6], e.z, s1); s1 = fmaf(w[j + 7], e.w, s1);
-      s2 = fmaf(w[j + 8], f.x, s2); s2 = fmaf(w[j + 9], f.y, s2); s2 = fmaf(w[j + 10], f.z, s2); s2 = fmaf(w[j + 11], f.w, s2);
-      s3 = fmaf(w[j + 12], g.x, s3); s3 = fmaf(w[j + 13], g.y, s3); s3 = fmaf(w[j + 14], g.z, s3); s3 = fmaf(w[j + 15], g.w, s3);
     }
-    float s = (s0 + s1) + (s2 + s3);
+    float s = s0 + s1;
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    float* gt = gates[cur];
-    if (half == 0) gt[r] = s + xp_cur;
+    if (half == 0) gates[r] = s + xp_cur;
     __syncthreads();
     if (tid < UPC) {
-      // exp-based sigmoid / tanh on the fast exponential (relative error ~1e-7, far inside the parity budget; the libm tanhf
-      // costs ~4x as many dependent instructions on the critical path of every step)
-      const float gi = 1.f / (1.f + __expf(-gt[tid]));
-      const float gf = 1.f / (1.f + __expf(-gt[UPC + tid]));
-      const float gg = 1.f - 2.f / (__expf(2.f * gt[2 * UPC + tid]) + 1.f);
-      const float go = 1.f / (1.f + __expf(-gt[3 * UPC + tid]));
+      const float gi = 1.f / (1.f + expf(-gates[tid]));
+      const float gf = 1.f / (1.f + expf(-gates[UPC + tid]));
+      const float gg = tanhf(gates[2 * UPC + tid]);
+      const float go = 1.f / (1.f + expf(-gates[3 * UPC + tid]));
       c = fmaf(gf, c, gi * gg);
-      const float hval = go * (1.f - 2.f / (__expf(2.f * c) + 1.f));
+      const float hval = go * tanhf(c);
       out[((int64_t)b * T + t) * out_ld + dir * LH + rank * UPC + tid] = hval;
       const uint32_t off = (uint32_t)((nxt * LH + rank * UPC + tid) * 4);
       if (step + 1 < T) {                                           // the last step has no consumer: no store may outlive the CTA
@@ -183,8 +175,7 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
       }
     }
     xp_cur = xp_next;
-    __syncthreads();              // keeps the 224 non-gate threads parked on the hardware barrier instead of spinning on the mbarrier while
-                                  // the 32 gate threads are on the critical path (without it the step got 10% slower)
+    __syncthreads();                                                // gates[] is rewritten next step
   }
   cluster.sync();                                                   // nobody exits while remote stores may still target it
 }
