@@ -95,7 +95,8 @@ int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B
                       int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                       int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                       int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
-                      int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, void* stream);
+                      int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, double* stats_ws,
+                      int32_t stats_slots, void* stream);
 
 /* profiling aid: CTA (0,0,0) of subsequent b2a_conv1d_tc launches stamps clock64() at its phase boundaries into dbg8[0..6]
  * (entry, setup done, first operands landed, last operands landed, accumulator ready, epilogue done, exit); NULL disables. */
@@ -122,6 +123,11 @@ int32_t b2a_durations_to_index(const float* dur_f, const int64_t* dur_i, int32_t
 int64_t b2a_adain_ws_bytes(int32_t B, int32_t L, int32_t C);
 int32_t b2a_adain_coeffs(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C,
                          const float* gb, float eps, float* scale, float* shift, void* ws, void* stream);
+/* Same coefficients from partial sums a producer already wrote: partials [B][nslots][C][2] float64 (sum, sum of squares per row group).
+ * b2a_conv1d_tc(stats_ws != NULL) emits them from its epilogue -- one slot per 32 output rows (times the up-sampling factor in
+ * transposed mode; stats_slots = ceil(Mrows/128)*4*max(1, up_stride)) -- so AdaIN-conv chains skip the statistics pass over HBM. */
+int32_t b2a_adain_coeffs_from_partials(const double* partials, int32_t nslots, int32_t B, int32_t L, int32_t C, const float* gb,
+                                       float eps, float* scale, float* shift, void* stream);
 /* y[r,:] = LN(x[r,:] + res[r,:]) * w + b, or (1+ada[c])*LN + ada[C+c] when ada != NULL
  * (nn.LayerNorm, modules.py:71-90 AdaLayerNorm). rms != 0 -> RMSNorm (no mean, talker.py:267). */
 int32_t b2a_layernorm(const float* x, int64_t x_ld, const float* res, int64_t res_ld, float* y, int64_t y_ld,

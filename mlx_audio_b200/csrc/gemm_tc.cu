@@ -107,6 +107,7 @@ struct TcParams {
   float out_scale; int accumulate;
   float* y; int64_t y_bs, y_ld;
   long long* dbg;                 // optional: 8 clock64 stamps from CTA (0,0,0) (b2a_conv1d_tc_debug)
+  double* stats; int stats_slots; // optional InstanceNorm partials of the OUTPUT: [B][stats_slots][C][2] = (sum, sum of squares) per 32-row group
 };
 
 // smem: [stages] x { A_hi 16 KB | A_lo 16 KB (planes==2) | W BN*128 B }, then barriers
@@ -620,7 +621,14 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
       for (int c0 = sub * 32; c0 < p.BN; c0 += 64) {
         uint32_t r[32];
         tmem_ld32(tmem_base + buf * tbuf_stride + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, r);
-        if (mrow0 >= p.Mrows) continue;
+        if (mrow0 >= p.Mrows) {                                // rows past the end: their statistics slot is an explicit zero
+          if (p.stats) {
+            const int n_ = n0 + c0 + lane, ph_ = p.up_s ? n_ / p.C : 0;
+            double* w = p.stats + ((((int64_t)b * p.stats_slots + (int64_t)(mt * 4 + quarter) * mul + ph_) * p.C) + (n_ - ph_ * p.C)) * 2;
+            w[0] = 0.0; w[1] = 0.0;
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
         __syncwarp();
@@ -644,6 +652,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         const float* rp = rcol ? rcol + (int64_t)(half_res ? (row0 >> 1) : row0) * p.res_ld : nullptr;
         const int64_t rstride = (int64_t)mul * p.res_ld;
         const float osc = p.out_scale;
+        float st1 = 0.f, st2 = 0.f;                            // InstanceNorm partials of the values written below (this lane's column)
         if (i_lo == 0 && i_hi == 32) {
           float rr[32];
           if (rp) {
@@ -671,10 +680,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
           const float cso = cs * osc;
           if (p.post_act) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) yp[i * ystride] = act_noinline(stage[i * 33 + lane] + bias, p.post_act, p.post_p0) * cso + rr[i];
+            for (int i = 0; i < 32; i++) {
+              const float v = act_noinline(stage[i * 33 + lane] + bias, p.post_act, p.post_p0) * cso + rr[i];
+              yp[i * ystride] = v; st1 += v; st2 = fmaf(v, v, st2);
+            }
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; i++) yp[i * ystride] = (stage[i * 33 + lane] + bias) * cso + rr[i];
+            for (int i = 0; i < 32; i++) {
+              const float v = (stage[i * 33 + lane] + bias) * cso + rr[i];
+              yp[i * ystride] = v; st1 += v; st2 = fmaf(v, v, st2);
+            }
           }
         } else {
           for (int i = i_lo; i < i_hi; i++) {
@@ -683,8 +698,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             if (p.post_act) t = act_noinline(t, p.post_act, p.post_p0);
             float rv = rcol ? __ldg(rcol + (int64_t)(half_res ? (row >> 1) : row) * p.res_ld) : 0.f;
             float o = p.accumulate ? ycol[(int64_t)row * p.y_ld] : 0.f;
-            ycol[(int64_t)row * p.y_ld] = (t * cs + rv) * osc + o;
+            const float v = (t * cs + rv) * osc + o;
+            ycol[(int64_t)row * p.y_ld] = v; st1 += v; st2 = fmaf(v, v, st2);
           }
+        }
+        if (p.stats) {
+          double* w = p.stats + ((((int64_t)b * p.stats_slots + (int64_t)(mt * 4 + quarter) * mul + ph) * p.C) + co) * 2;
+          w[0] = (double)st1; w[1] = (double)st2;
         }
         __syncwarp();
       }
@@ -799,7 +819,8 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
                                  int32_t taps, const int32_t* shifts_host, int32_t Cout, int32_t Lout, const float* bias,
                                  int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                                  int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
-                                 int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, void* stream) {
+                                 int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, double* stats_ws, int32_t stats_slots,
+                                 void* stream) {
   B2A_CHECK_ARG(a_hi && w_bf16 && y && shifts_host, "null pointer");
   B2A_CHECK_ARG(up_stride >= 0 && up_crop >= 0 && (up_stride == 0 || (Cout % up_stride == 0 && (Cout / up_stride) % 32 == 0)),
                 "transposed mode: Cout = up_stride * C with C a multiple of 32");
@@ -831,6 +852,7 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   p.res = res; p.res_bs = res_bs; p.res_ld = res_ld; p.res_div = res_div; p.out_scale = out_scale; p.accumulate = accumulate;
   p.y = y; p.y_bs = y_bs; p.y_ld = y_ld;
   p.dbg = g_dbg;
+  p.stats = stats_ws; p.stats_slots = stats_slots;
   const int stage_bytes = TM * 128 * p.planes + p.BN * 128 * p.wplanes;
   // Two CTAs per SM whenever two 2-stage pipelines fit (<= ~113 KB each): one CTA's epilogue then overlaps the other's main
   // loop.  Otherwise one CTA per SM with as many stages as fit.  (Stage 0 doubles as the 17 KB epilogue staging tile.)
@@ -908,6 +930,14 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
         psm = (size_t)pst * stage_bytes + PERSIST_STAGING + 1024 + (2 * pst + 8) * 8 + 64;
         use_persist = true;
       }
+    }
+  }
+
+  if (stats_ws) {
+    const int need = cdiv(p.Mrows, TM) * 4 * (up_stride ? up_stride : 1);
+    if (!use_persist || stats_slots != need) {
+      b2a_set_error("b2a_conv1d_tc: fused output statistics need the persistent kernel and %d slots (got %d)", need, stats_slots);
+      return B2A_E_UNSUPPORTED;
     }
   }
 

@@ -189,8 +189,10 @@ def pack_linear(w: torch.Tensor, bias=None, device="cuda") -> ConvW:
 
 def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout=None, pad_mode=0,
            pre: Optional[Pre] = None, post_act=0, post_p0=0.0, cscale=None, res=None, res_div=1,
-           out_scale=1.0, out=None, accumulate=False, transpose=False) -> torch.Tensor:
-    """b2a_conv1d_cl / b2a_convtr1d_cl.  For ``transpose`` ``pad_left`` is the left crop of the scatter output."""
+           out_scale=1.0, out=None, accumulate=False, transpose=False, stats=False):
+    """b2a_conv1d_cl / b2a_convtr1d_cl.  For ``transpose`` ``pad_left`` is the left crop of the scatter output.
+    ``stats=True`` returns (y, partials): InstanceNorm partial sums of y from the tensor-core epilogue for ``adain_coeffs(partials=)``,
+    or (y, None) when the layer does not run on that path."""
     _chk3(x, "conv1d x")
     B, L, cin = x.shape
     if cin != cw.cin:
@@ -202,7 +204,7 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
     if _tc_eligible(cw, L, stride, transpose, pad_mode, dilation):
         return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
-                          up_stride=stride if transpose else 0)
+                          up_stride=stride if transpose else 0, stats=stats)
     if out is None:
         out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
     else:
@@ -230,7 +232,7 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     fn = _lib.lib().b2a_convtr1d_cl if transpose else _lib.lib().b2a_conv1d_cl
     _call("conv" if cw.groups == 1 and cw.cin * cw.K >= 64 else "other", fn, 1, C.byref(p), _stream())
-    return out
+    return (out, None) if stats else out
 
 
 def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2, f16: bool = False):
@@ -246,8 +248,11 @@ def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2, f
     return hi, lo
 
 
+TC_STATS = [os.environ.get("B2A_TC_STATS", "1") != "0" and os.environ.get("B2A_TC_PERSIST", "1") != "0"]
+
+
 def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
-               up_stride=0):
+               up_stride=0, stats=False):
     B, L, _ = x.shape
     hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1, cw.f16)
     if out is None:
@@ -268,10 +273,15 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
     if res is not None:
         _chk3(res, "conv1d res")
         r, r_bs, r_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
+    ws, slots = None, 0
+    if stats and TC_STATS[0]:          # InstanceNorm partials of the output straight from the epilogue (persistent kernel only)
+        mrows = (L + taps - 1) if up_stride else lout
+        slots = -(-mrows // 128) * 4 * max(1, up_stride)
+        ws = torch.empty(B, slots, cw.cout, 2, device=x.device, dtype=torch.float64)
     _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, w_tc.data_ptr(), _p(w_lo), taps, shifts, n_total, lout,
           _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
-          out.stride(1), up_stride, pad_left if up_stride else 0, _stream())
-    return out
+          out.stride(1), up_stride, pad_left if up_stride else 0, _p(ws), slots, _stream())
+    return (out, ws) if stats else out
 
 
 def linear(x: torch.Tensor, cw: ConvW, **kw) -> torch.Tensor:
@@ -344,12 +354,18 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5):
-    """InstanceNorm stats of x [B,L,C] folded with AdaIN (gamma|beta) [B,2C] -> (scale, shift) [B,C]."""
+def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5, partials: Optional[torch.Tensor] = None):
+    """InstanceNorm stats of x [B,L,C] folded with AdaIN (gamma|beta) [B,2C] -> (scale, shift) [B,C].  ``partials`` [B,slots,C,2]
+    float64 from ``conv1d(..., stats=True)`` skips the statistics pass over x."""
     _chk3(x, "adain_coeffs x")
     B, L, Cc = x.shape
     scale = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
     shift = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    if partials is not None:
+        assert partials.dtype == torch.float64 and partials.is_contiguous() and partials.shape[0] == B and partials.shape[2] == Cc
+        _call("adain_stats", _lib.lib().b2a_adain_coeffs_from_partials, 1, partials.data_ptr(), partials.shape[1], B, L, Cc, _p(gb), eps,
+              scale.data_ptr(), shift.data_ptr(), _stream())
+        return scale, shift
     ws = _workspace(_lib.lib().b2a_adain_ws_bytes(B, L, Cc), x.device)
     _call("adain_stats", _lib.lib().b2a_adain_coeffs, 2, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
                                            scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream())
