@@ -128,6 +128,14 @@ def test_epilogue_instance_norm_partials(L, Cin, Cout, K, transpose, stride):
     w = _rand(Cout, K, Cin, seed=2, scale=0.05).to(torch.bfloat16).float()
     cw = ops.pack_conv(w, _rand(Cout, seed=3, scale=0.1), 1, dev)
     gb = _rand(2, 2 * Cout, seed=4, scale=0.3).to(dev)
+    old, ops.TC_STATS[0] = ops.TC_STATS[0], True          # opt-in feature (off by default: measured slower end to end)
+    try:
+        _run_stats_case(ops, dev, x, cw, gb, L, Cout, K, transpose, stride)
+    finally:
+        ops.TC_STATS[0] = old
+
+
+def _run_stats_case(ops, dev, x, cw, gb, L, Cout, K, transpose, stride):
     if transpose:
         y, part = ops.conv1d(x.to(dev), cw, stride=stride, pad_left=(K - stride) // 2, transpose=True, stats=True)
     else:
