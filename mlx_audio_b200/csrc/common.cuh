@@ -15,10 +15,20 @@ void b2a_set_error(const char* fmt, ...);
   do { cudaError_t e_ = cudaGetLastError();                        \
        if (e_ != cudaSuccess) { b2a_set_error("%s: %s", __func__, cudaGetErrorString(e_)); return B2A_E_CUDA; } } while (0)
 
+// sin for the Snake activations: two-constant Cody-Waite reduction to [-pi, pi] + the SFU sine (abs error < 5e-7 there), ~6
+// instructions instead of libm's ~40 -- the prologue kernels that apply Snake are otherwise instruction-bound, not HBM-bound.
+__device__ __forceinline__ float b2a_sin(float x) {
+  if (fabsf(x) > 8192.f) return sinf(x);
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);
+  r = fmaf(-k, -1.7484555314695172e-07f, r);
+  return __sinf(r);
+}
+
 __device__ __forceinline__ float b2a_act(float v, int act, float p0, float a, float b) {
   switch (act) {
     case B2A_ACT_LRELU: return v > 0.f ? v : v * p0;
-    case B2A_ACT_SNAKE: { float s = sinf(a * v); return fmaf(b, s * s, v); }
+    case B2A_ACT_SNAKE: { float s = b2a_sin(a * v); return fmaf(b, s * s, v); }
     case B2A_ACT_ELU: return v > 0.f ? v : expm1f(v);
     case B2A_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
     case B2A_ACT_GELU_TANH: { float u = 0.7978845608028654f * (v + 0.044715f * v * v * v); return 0.5f * v * (1.f + tanhf(u)); }

@@ -135,6 +135,139 @@ __global__ void __launch_bounds__(GV_THREADS) gemv_bf16_kernel(const GemvParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Wide variant for 3..8 activation rows (batched decode): the x values a lane needs are loaded ONCE per K chunk and reused for
+// GW_ROWS = 8 weight rows (the narrow kernel re-loads them for every 4 rows, which makes it LSU-bound at M = 8), each warp owns
+// a contiguous quarter of K, partial sums leave the warp through a 62-shuffle reduce-scatter instead of 64 full butterflies.
+constexpr int GW_ROWS = 8;
+
+template <int MT>
+__global__ void __launch_bounds__(GV_THREADS) gemv_bf16_wide_kernel(const GemvParams p) {
+  constexpr int NV = MT * GW_ROWS;                  // partial sums per lane (power of two, >= 32)
+  __shared__ float red[GV_THREADS / 32][NV];
+  __shared__ float ssq[GV_THREADS / 32][MT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * GW_ROWS;
+  if (p.pf) {
+    const int64_t stride = (int64_t)gridDim.x * GV_THREADS * 128;
+    for (int64_t off = ((int64_t)blockIdx.x * GV_THREADS + tid) * 128; off < p.pf_bytes; off += stride)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pf + off));
+  }
+  float acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) acc[i] = 0.f;
+  float sq[MT];
+#pragma unroll
+  for (int m = 0; m < MT; m++) sq[m] = 0.f;
+  const int chunks = p.K >> 3, cw = chunks / (GV_THREADS / 32);          // host guarantees chunks % 4 == 0
+  const int c_begin = warp * cw, c_end = c_begin + cw;
+  uint4 wv[GW_ROWS];
+  auto load_w = [&](int c) {
+#pragma unroll
+    for (int r = 0; r < GW_ROWS; r++)
+      wv[r] = (n0 + r < p.N && c < c_end) ? __ldcs(reinterpret_cast<const uint4*>(p.w + (int64_t)(n0 + r) * p.w_ld + ((int64_t)c << 3))) : make_uint4(0, 0, 0, 0);
+  };
+  load_w(c_begin + lane);
+  pdl_launch_dependents();
+  pdl_wait();
+  for (int c = c_begin + lane; c < c_end; c += 32) {
+    const int k = c << 3;
+    if (c != c_begin + lane) load_w(c);
+    float g[8];
+    if (p.norm_w) {
+      float4 g0 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k)), g1 = __ldg(reinterpret_cast<const float4*>(p.norm_w + k + 4));
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    }
+    float xv[MT][8];
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+      if (m < p.M) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)m * p.x_ld + k));
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.x + (int64_t)m * p.x_ld + k + 4));
+        xv[m][0] = a.x; xv[m][1] = a.y; xv[m][2] = a.z; xv[m][3] = a.w; xv[m][4] = b.x; xv[m][5] = b.y; xv[m][6] = b.z; xv[m][7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) xv[m][j] = 0.f;
+      }
+      if (p.norm_w) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) { sq[m] = fmaf(xv[m][j], xv[m][j], sq[m]); xv[m][j] *= g[j]; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < GW_ROWS; r++) {
+      float wf[8];
+      bf16x8_to_float(wv[r], wf);
+#pragma unroll
+      for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[m * GW_ROWS + r] = fmaf(wf[j], xv[m][j], acc[m * GW_ROWS + r]);
+    }
+  }
+  // reduce-scatter across the warp: after the stage with xor-distance s a lane keeps half of its values (upper half iff lane & s)
+  int base = 0;
+  {
+    int n = NV;
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+      const int half = n >> 1;
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; i++) {
+        if (i < half) {
+          const float send = up ? acc[i] : acc[i + half];
+          const float keep = up ? acc[i + half] : acc[i];
+          acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      if (up) base += half;
+      n = half;
+    }
+  }
+  constexpr int PER = NV / 32;                      // values left per lane
+#pragma unroll
+  for (int i = 0; i < PER; i++) red[warp][base + i] = acc[i];
+  if (p.norm_w) {
+#pragma unroll
+    for (int m = 0; m < MT; m++) { float v = warp_sum(sq[m]); if (lane == 0) ssq[warp][m] = v; }
+  }
+  __syncthreads();
+  if (tid < NV) {
+    const int m = tid / GW_ROWS, r = tid % GW_ROWS, n = n0 + r;
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < GV_THREADS / 32; w++) v += red[w][tid];
+    if (p.norm_w) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < GV_THREADS / 32; w++) sacc += ssq[w][m];
+      v *= rsqrtf(sacc / (float)p.K + p.norm_eps);
+    }
+    if (p.bias && n < p.N) v += __ldg(p.bias + n);
+    red[0][tid] = v;
+  }
+  __syncthreads();
+  if (p.mode == 1) {
+    if (tid < MT * (GW_ROWS / 2)) {
+      const int m = tid / (GW_ROWS / 2), q = tid % (GW_ROWS / 2), n = n0 + 2 * q;
+      if (m < p.M && n + 1 < p.N) {
+        const float gte = red[0][m * GW_ROWS + 2 * q], up = red[0][m * GW_ROWS + 2 * q + 1];
+        float v = gte / (1.f + expf(-gte)) * up;
+        const int no = n >> 1;
+        if (p.res) v += __ldg(p.res + (int64_t)m * p.res_ld + no);
+        p.y[(int64_t)m * p.y_ld + no] = v;
+      }
+    }
+  } else if (tid < NV) {
+    const int m = tid / GW_ROWS, r = tid % GW_ROWS, n = n0 + r;
+    if (m < p.M && n < p.N) {
+      float v = red[0][tid];
+      if (p.res) v += __ldg(p.res + (int64_t)m * p.res_ld + n);
+      p.y[(int64_t)m * p.y_ld + n] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-head RMSNorm of q and k + (multimodal) rotary embedding + KV-cache append.  One warp per (b, s, head); a lane
 // owns elements lane + 32 j, so the rotate_half partner (i, i + D/2) sits in the same lane.
 struct QkParams {
@@ -532,8 +665,14 @@ extern "C" int32_t b2a_gemv_bf16(const float* x, int64_t x_ld, int32_t M, int32_
                (const char*)prefetch, prefetch ? prefetch_bytes : 0};
   const int grid = (N + GV_ROWS - 1) / GV_ROWS;
   cudaStream_t st = (cudaStream_t)stream;
+  static int wide_on = -1;
+  if (wide_on < 0) { const char* e = getenv("B2A_GEMV_WIDE"); wide_on = (e && e[0] == '0') ? 0 : 1; }
+  const bool wide = wide_on && M > 2 && (K >> 3) % (GV_THREADS / 32) == 0;
+  const int gridw = (N + GW_ROWS - 1) / GW_ROWS;
   if (M == 1) b2a_launch_pdl(gemv_bf16_kernel<1>, dim3(grid), dim3(GV_THREADS), 0, st, p);
   else if (M == 2) b2a_launch_pdl(gemv_bf16_kernel<2>, dim3(grid), dim3(GV_THREADS), 0, st, p);
+  else if (wide && M <= 4) b2a_launch_pdl(gemv_bf16_wide_kernel<4>, dim3(gridw), dim3(GV_THREADS), 0, st, p);
+  else if (wide) b2a_launch_pdl(gemv_bf16_wide_kernel<8>, dim3(gridw), dim3(GV_THREADS), 0, st, p);
   else if (M <= 4) b2a_launch_pdl(gemv_bf16_kernel<4>, dim3(grid), dim3(GV_THREADS), 0, st, p);
   else b2a_launch_pdl(gemv_bf16_kernel<8>, dim3(grid), dim3(GV_THREADS), 0, st, p);
   B2A_CHECK_LAUNCH();
