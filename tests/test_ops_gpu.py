@@ -372,3 +372,22 @@ def test_attention_tensor_core_vs_cuda_core(Tq, Tk, causal, window, q_offset, mo
     finally:
         ops.ATTN_MODE[0] = old
     assert rel_err(y, ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,L,Cin,Cout,K,dil,pad_mode", [(2, 1000, 64, 1, 7, 1, 0), (1, 777, 96, 1, 7, 1, 0), (1, 300, 64, 1, 3, 1, 1), (1, 513, 40, 3, 5, 2, 0)])
+def test_conv1d_narrow_output(B, L, Cin, Cout, K, dil, pad_mode):
+    """Waveform heads (Mimi / SNAC / Qwen3 vocoder: C -> 1): the narrow-output kernel with Snake / ELU prologue, bias, clip epilogue."""
+    from mlx_audio_b200 import ops
+    dev = _dev()
+    x, w, bias = _rand(B, L, Cin, seed=1), _rand(Cout, K, Cin, seed=2, scale=0.1), _rand(Cout, seed=3)
+    a = (1 + 0.2 * _rand(Cin, seed=6)).abs() + 0.1
+    xin = x.double() + (1.0 / (a.double() + 1e-9)) * torch.sin(a.double() * x.double()) ** 2
+    padl = (K - 1) * dil                                               # causal
+    if pad_mode == 1:
+        xp = torch.nn.functional.pad(xin.transpose(1, 2), (padl, 0), mode="replicate").transpose(1, 2)
+    else:
+        xp = torch.nn.functional.pad(xin, (0, 0, padl, 0))
+    ref = torch.clamp(ON.conv1d(xp, w.double(), 1, 0, dil, 1, bias.double()), -1.0, 1.0)
+    y = ops.conv1d(x.to(dev), ops.pack_conv(w, bias, 1, dev), dilation=dil, pad_left=padl, lout=L, pad_mode=pad_mode,
+                   pre=ops.Pre(act=ops.ACT["snake"], a=a.to(dev), b=(1.0 / (a + 1e-9)).to(dev)), post_act=ops.ACT["clip1"])
+    assert y.shape == ref.shape and rel_err(y, ref) < 2e-5
