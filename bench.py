@@ -294,14 +294,14 @@ def main():
     alg_bytes = CONV_STACK_MB_PER_AUDIO_S * 1e6 * AUDIO_S_PER_UTT                # per utterance, all conv launches
     achieved = alg_bytes / (conv_ms / 1e3) / 1e9
     traffic = None                                                               # measured DRAM bytes of the same kernels (ncu capture, committed)
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = float(json.load(open(tpath))["conv_stack_bytes_per_step"])
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_kind": peak_kind, "kernel": "dense conv stack: conv_tc_kernel (tcgen05) + prep_bf16_kernel, conv1d_dense/convtr1d_dense (CUDA-core)",
+                "traffic": traffic, "peak_kind": peak_kind, "kernel": "dense conv stack: conv_tc_persist_kernel (tcgen05, persistent) + prep_bf16_kernel, conv1d_dense/convtr1d_dense (CUDA-core)",
                 "launches_per_utterance": n_conv, "kernel_ms_per_utterance": conv_ms, "other_kernels_ms_per_utterance": other_ms,
                 "ms_by_kind": {k: round(v, 3) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
                 "algorithmic_bytes_per_utterance": alg_bytes}
