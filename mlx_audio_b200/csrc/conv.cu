@@ -8,6 +8,7 @@
 namespace {
 
 constexpr int BM = 64;          // output positions per CTA
+constexpr int DW_TL = 128;      // positions per CTA of the staged depthwise kernels
 constexpr int NT = 256;         // threads per CTA
 
 struct Pre {                    // input transform, evaluated while staging x into shared memory
@@ -130,6 +131,68 @@ __global__ void __launch_bounds__(NT) conv1d_dw_kernel(const b2a_conv1d_t p) {
   }
 }
 
+// Vectorised variant (C % 4 == 0, 16-byte aligned rows): a lane owns FOUR consecutive channels, so global loads / stores and the
+// per-tap shared-memory reads are 16 bytes wide (4x fewer LSU instructions than the scalar tile; the SNAC decoder's twelve
+// depthwise layers were LSU-bound at 22 % of HBM bandwidth).  CTA = DW_TL positions x CW channels (CW = 64 or 128).
+template <int KT, int CW>
+__global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t p, int rows) {
+  constexpr int LPR = CW / 4, RPW = 32 / LPR;        // lanes per row, rows per warp-wide access
+  extern __shared__ __align__(16) float smem[];      // [rows][CW]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c4 = (lane % LPR) * 4, rsub = lane / LPR;
+  const int l0 = blockIdx.x * DW_TL, c0 = blockIdx.y * CW, b = blockIdx.z;
+  const int c = c0 + c4;
+  const bool cok = c < p.Cout;                       // C % 4 == 0: the whole quad is in or out
+  const Pre pre = make_pre(p);
+  const int K = KT ? KT : p.K;
+  const float* xb = p.x + (int64_t)b * p.x_bs + c;
+  const int64_t pos0 = (int64_t)l0 - p.pad_left;
+  for (int r = warp * RPW + rsub; r < rows; r += (NT / 32) * RPW) {
+    int64_t pos = pos0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cok) {
+      if (pos < 0 || pos >= p.L) pos = p.pad_mode == 1 ? (pos < 0 ? 0 : (int64_t)p.L - 1) : -1;
+      if (pos >= 0) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(xb + pos * p.x_ld));
+        v.x = pre(t.x, b, c); v.y = pre(t.y, b, c + 1); v.z = pre(t.z, b, c + 2); v.w = pre(t.w, b, c + 3);
+      }
+    }
+    *reinterpret_cast<float4*>(smem + (size_t)r * CW + c4) = v;
+  }
+  float4 w[KT ? KT : 16];
+#pragma unroll
+  for (int k = 0; k < (KT ? KT : 16); k++)
+    w[k] = (cok && k < K) ? __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)k * p.Cout + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cok && p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+  __syncthreads();
+  if (!cok) return;
+  const int d = p.dilation;
+  const bool fast = !p.res && !p.post_cscale && !p.accumulate && !p.post_act && (p.y_ld % 4 == 0) && (p.y_bs % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
+#pragma unroll 2
+  for (int i = warp * RPW + rsub; i < DW_TL; i += (NT / 32) * RPW) {
+    const int l = l0 + i;
+    if (l >= p.Lout) break;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < (KT ? KT : 16); k++) {
+      if (KT || k < K) {
+        const float4 xv = *reinterpret_cast<const float4*>(smem + (size_t)(i + k * d) * CW + c4);
+        acc.x = fmaf(xv.x, w[k].x, acc.x); acc.y = fmaf(xv.y, w[k].y, acc.y); acc.z = fmaf(xv.z, w[k].z, acc.z); acc.w = fmaf(xv.w, w[k].w, acc.w);
+      }
+    }
+    if (fast) {
+      float4 o = make_float4((acc.x + bias4.x) * p.out_scale, (acc.y + bias4.y) * p.out_scale, (acc.z + bias4.z) * p.out_scale,
+                             (acc.w + bias4.w) * p.out_scale);
+      *reinterpret_cast<float4*>(p.y + (int64_t)b * p.y_bs + (int64_t)l * p.y_ld + c) = o;
+    } else {
+      epilogue_store(p, b, l, c, acc.x); epilogue_store(p, b, l, c + 1, acc.y);
+      epilogue_store(p, b, l, c + 2, acc.z); epilogue_store(p, b, l, c + 3, acc.w);
+    }
+  }
+}
+
 // Dense stride-1 conv with a NARROW output (Cout <= 4: the 64->1 / 96->1 waveform heads of Mimi, SNAC and the Qwen3 vocoder).
 // The 64 x BN implicit-GEMM tile wastes 15/16 of its threads there (Mimi head: 14 ms for 4.9 GB of input).  Here a CTA stages
 // NW_TL + (K-1)*dilation transformed input rows once (coalesced, prologue applied once per element), and each thread owns one
@@ -180,7 +243,6 @@ __global__ void __launch_bounds__(NT) conv1d_narrow_kernel(const b2a_conv1d_t p,
 // shared memory, so the transcendental is paid per input element rather than per tap, and every
 // tap is a conflict-free shared-memory read (lane == channel).  Halo rows are shared with the
 // neighbouring CTAs through L2, so HBM sees x once.
-constexpr int DW_TL = 128;
 template <int KT>
 __global__ void __launch_bounds__(NT) conv1d_dw_tiled_kernel(const b2a_conv1d_t p, int rows) {
   extern __shared__ __align__(16) float smem[];      // [rows][32]
@@ -289,17 +351,19 @@ __global__ void __launch_bounds__(NT) convtr1d_dense_kernel(const b2a_conv1d_t p
   }
 }
 
-__global__ void __launch_bounds__(NT) convtr1d_dw_kernel(const b2a_conv1d_t p) {
+// grid (row groups of 16, channel groups of 128, batch): no 64-bit index arithmetic per element (the flat-index version spent
+// its time in four 64-bit divisions per output: 10.6 ms for Mimi's 20 000 x 512 up-sampler)
+constexpr int TRDW_ROWS = 16;
+__global__ void __launch_bounds__(128) convtr1d_dw_kernel(const b2a_conv1d_t p) {
   const Pre pre = make_pre(p);
   const int s = p.stride;
-  const int64_t total = (int64_t)p.B * p.Lout * p.Cout;
-  for (int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * NT) {
-    int c = (int)(idx % p.Cout);
-    int64_t t = idx / p.Cout;
-    int l = (int)(t % p.Lout), b = (int)(t / p.Lout);
-    const float* xb = p.x + (int64_t)b * p.x_bs + c;
-    int q = l + p.pad_left;
-    int r = q % s, ih = q / s;
+  const int c = blockIdx.y * 128 + threadIdx.x, b = blockIdx.z;
+  if (c >= p.Cout) return;
+  const float* xb = p.x + (int64_t)b * p.x_bs + c;
+  const int l_end = min(p.Lout, (int)(blockIdx.x + 1) * TRDW_ROWS);
+  for (int l = blockIdx.x * TRDW_ROWS; l < l_end; l++) {
+    const int q = l + p.pad_left;
+    const int r = q % s, ih = q / s;
     float acc = 0.f;
     for (int k = r, i = ih; k < p.K && i >= 0; k += s, i--) {
       if (i < p.L) acc = fmaf(pre(__ldg(xb + (int64_t)i * p.x_ld), b, c), __ldg(p.w + (int64_t)k * p.Cout + c), acc);
@@ -401,7 +465,29 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
     }
   } else if (p->groups == p->Cin && p->Cin == p->Cout) {
     int rows = DW_TL + (p->K - 1) * p->dilation;
-    if (p->stride == 1 && p->K <= 16 && rows * 32 * 4 <= 96 * 1024 && p->Lout >= DW_TL) {
+    const bool v4 = p->stride == 1 && p->K <= 16 && p->Lout >= DW_TL && p->Cout % 4 == 0 && p->x_ld % 4 == 0 && p->x_bs % 4 == 0 &&
+                    ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->w & 15) == 0 && (!p->bias || ((uintptr_t)p->bias & 15) == 0) &&
+                    (size_t)rows * 128 * 4 <= 160 * 1024;
+    if (v4) {
+      const int CW = p->Cout >= 128 ? 128 : 64;
+      dim3 grid((p->Lout + DW_TL - 1) / DW_TL, (p->Cout + CW - 1) / CW, p->B);
+      const size_t sm = (size_t)rows * CW * sizeof(float);
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr = true;
+      }
+      if (p->K == 7) {
+        if (CW == 128) conv1d_dw_tiled4_kernel<7, 128><<<grid, NT, sm, st>>>(*p, rows);
+        else conv1d_dw_tiled4_kernel<7, 64><<<grid, NT, sm, st>>>(*p, rows);
+      } else {
+        if (CW == 128) conv1d_dw_tiled4_kernel<0, 128><<<grid, NT, sm, st>>>(*p, rows);
+        else conv1d_dw_tiled4_kernel<0, 64><<<grid, NT, sm, st>>>(*p, rows);
+      }
+    } else if (p->stride == 1 && p->K <= 16 && rows * 32 * 4 <= 96 * 1024 && p->Lout >= DW_TL) {
       dim3 grid((p->Lout + DW_TL - 1) / DW_TL, (p->Cout + 31) / 32, p->B);
       size_t sm = (size_t)rows * 32 * sizeof(float);
       if (p->K == 7) {
@@ -441,9 +527,8 @@ extern "C" int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream) {
     dim3 grid(cdiv(p->Lout, BM), cdiv(p->Cout, 64), p->B);
     convtr1d_dense_kernel<<<grid, NT, smem, st>>>(*p, CI, rows, J);
   } else if (p->groups == p->Cin && p->Cin == p->Cout) {
-    int64_t total = (int64_t)p->B * p->Lout * p->Cout;
-    int blocks = (int)((total + NT - 1) / NT); if (blocks > 148 * 32) blocks = 148 * 32;
-    convtr1d_dw_kernel<<<blocks, NT, 0, st>>>(*p);
+    dim3 grid(cdiv(p->Lout, TRDW_ROWS), cdiv(p->Cout, 128), p->B);
+    convtr1d_dw_kernel<<<grid, 128, 0, st>>>(*p);
   } else {
     b2a_set_error("b2a_convtr1d_cl: groups must be 1 or Cin==Cout==groups (got %d)", p->groups);
     return B2A_E_UNSUPPORTED;

@@ -108,7 +108,8 @@ def test_conv1d_strided_views_and_edge_pad():
 
 
 @pytest.mark.parametrize("B,L,C,K,stride,dil,pad", [(1, 100, 96, 7, 1, 1, 3), (2, 64, 33, 7, 1, 9, 27), (1, 50, 8, 4, 2, 1, 1),
-    (2, 700, 64, 7, 1, 9, 27), (1, 515, 33, 7, 1, 3, 9), (1, 300, 40, 5, 1, 2, 4), (1, 129, 512, 7, 1, 1, 3)])
+    (2, 700, 64, 7, 1, 9, 27), (1, 515, 33, 7, 1, 3, 9), (1, 300, 40, 5, 1, 2, 4), (1, 129, 512, 7, 1, 1, 3), (2, 1000, 128, 7, 1, 3, 9),
+    (1, 400, 256, 7, 1, 9, 54), (1, 260, 1024, 7, 1, 1, 6)])
 def test_conv1d_depthwise(B, L, C, K, stride, dil, pad):
     from mlx_audio_b200 import ops
     dev = _dev()
