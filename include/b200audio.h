@@ -71,6 +71,11 @@ typedef struct {
   const float* post_cscale; int64_t post_cscale_bs;    /* [Cout] (bs 0) or [B,Cout] or NULL */
   const float* res; int64_t res_bs; int64_t res_ld; int32_t res_div;
   float out_scale; int32_t accumulate;
+  /* optional: emit the NEXT tensor-core layer's operand instead of y -- act_emit(value) split into bf16 planes hi / lo
+   * [B, Lout, emit_ld] (what b2a_prep_bf16 would produce from y); depthwise stride-1 layers with Cout % 64 == 0 only
+   * (snac/layers.py:208-231: Snake -> depthwise conv -> Snake -> 1x1 conv).  y may be NULL then. */
+  void* emit_hi; void* emit_lo; int64_t emit_ld;
+  int32_t emit_act; float emit_p0; const float* emit_a; const float* emit_b;
 } b2a_conv1d_t;
 
 int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream);

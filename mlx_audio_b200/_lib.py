@@ -27,6 +27,8 @@ class Conv1dParams(C.Structure):
         ("post_cscale", C.c_void_p), ("post_cscale_bs", i64),
         ("res", C.c_void_p), ("res_bs", i64), ("res_ld", i64), ("res_div", i32),
         ("out_scale", f32), ("accumulate", i32),
+        ("emit_hi", C.c_void_p), ("emit_lo", C.c_void_p), ("emit_ld", i64),
+        ("emit_act", i32), ("emit_p0", f32), ("emit_a", C.c_void_p), ("emit_b", C.c_void_p),
     ]
 
 

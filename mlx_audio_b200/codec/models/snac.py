@@ -122,8 +122,16 @@ class SNAC:
                 nz = nz.to(device=dev, dtype=torch.float32).reshape(B, -1).contiguous()
                 y = ops.conv1d(y, blk["noise"], cscale=nz, res=y)                   # x + noise * linear(x)
             for ru in blk["res"]:
-                t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=Pre(act=ACT["snake"], a=ru["s1"][0], b=ru["s1"][1]))
-                y = ops.conv1d(t, ru["c2"], pre=Pre(act=ACT["snake"], a=ru["s2"][0], b=ru["s2"][1]), res=y)
+                s1 = Pre(act=ACT["snake"], a=ru["s1"][0], b=ru["s1"][1])
+                s2 = Pre(act=ACT["snake"], a=ru["s2"][0], b=ru["s2"][1])
+                if ru["c1"].groups > 1 and ru["c2"].w_tc is not None and ops.emit_eligible(ru["c1"], y, y.shape[1], dilation=ru["d"]) \
+                        and ru["c2"].cin_pad == ru["c1"].cout and ru["c2"].cin * ru["c2"].K >= ops.TC_MIN_K:
+                    # depthwise conv writes Snake2(t) as the 1x1 conv's bf16 planes: no fp32 t, no prologue pass
+                    t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=s1, emit=s2)
+                    y = ops.conv1d(t, ru["c2"], res=y)
+                else:
+                    t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=s1)
+                    y = ops.conv1d(t, ru["c2"], pre=s2, res=y)
             x = y
         a, ia = W["out_snake"]
         return ops.conv1d(x, W["out_conv"], pad_left=3, pre=Pre(act=ACT["snake"], a=a, b=ia), post_act=ACT["tanh"])

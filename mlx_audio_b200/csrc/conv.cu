@@ -4,6 +4,7 @@
 // (InstanceNorm/AdaIN apply + Snake/LeakyReLU/ELU), bias, activation, LayerScale/noise gain,
 // residual add, output scale and accumulation, so each conv reads x once and writes y once.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -182,7 +183,20 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
         acc.x = fmaf(xv.x, w[k].x, acc.x); acc.y = fmaf(xv.y, w[k].y, acc.y); acc.z = fmaf(xv.z, w[k].z, acc.z); acc.w = fmaf(xv.w, w[k].w, acc.w);
       }
     }
-    if (fast) {
+    if (p.emit_hi) {                                    // the consumer's prologue + bf16 split, straight from registers
+      float o[4] = {(acc.x + bias4.x) * p.out_scale, (acc.y + bias4.y) * p.out_scale, (acc.z + bias4.z) * p.out_scale, (acc.w + bias4.w) * p.out_scale};
+      __align__(8) __nv_bfloat16 h[4], lw[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        float t = o[q];
+        if (p.emit_act) t = b2a_act(t, p.emit_act, p.emit_p0, p.emit_a ? __ldg(p.emit_a + c + q) : 1.f, p.emit_b ? __ldg(p.emit_b + c + q) : 1.f);
+        h[q] = __float2bfloat16_rn(t);
+        lw[q] = __float2bfloat16_rn(t - __bfloat162float(h[q]));
+      }
+      const int64_t row = (int64_t)b * p.Lout + l;
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.emit_hi) + row * p.emit_ld + c) = *reinterpret_cast<uint2*>(h);
+      if (p.emit_lo) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.emit_lo) + row * p.emit_ld + c) = *reinterpret_cast<uint2*>(lw);
+    } else if (fast) {
       float4 o = make_float4((acc.x + bias4.x) * p.out_scale, (acc.y + bias4.y) * p.out_scale, (acc.z + bias4.z) * p.out_scale,
                              (acc.w + bias4.w) * p.out_scale);
       *reinterpret_cast<float4*>(p.y + (int64_t)b * p.y_bs + (int64_t)l * p.y_ld + c) = o;
@@ -426,7 +440,7 @@ __global__ void durations_to_index_kernel(const float* __restrict__ dur_f, const
 }
 
 int check_common(const b2a_conv1d_t* p) {
-  if (!p || !p->x || !p->w || !p->y) return 1;
+  if (!p || !p->x || !p->w || (!p->y && !p->emit_hi)) return 1;
   if (p->B <= 0 || p->L <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->Lout <= 0) return 2;
   if (p->K <= 0 || p->stride <= 0 || p->dilation <= 0 || p->res_div <= 0) return 3;
   if ((p->pre_scale == nullptr) != (p->pre_shift == nullptr)) return 4;
@@ -439,6 +453,10 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
   int bad = check_common(p);
   if (bad) { b2a_set_error("b2a_conv1d_cl: invalid argument (check %d)", bad); return B2A_E_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (p->emit_hi && !(p->groups == p->Cin && p->Cin == p->Cout)) {
+    b2a_set_error("b2a_conv1d_cl: plane emission is implemented for depthwise layers");
+    return B2A_E_UNSUPPORTED;
+  }
   if (p->groups == 1 && p->stride == 1 && p->Cout <= 4 && p->Lout >= NW_TL &&
       ((size_t)(NW_TL + (p->K - 1) * p->dilation) * (p->Cin + 1) + (size_t)p->K * p->Cin * p->Cout) * sizeof(float) <= 160 * 1024) {
     const int rows = NW_TL + (p->K - 1) * p->dilation;
@@ -468,6 +486,11 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
     const bool v4 = p->stride == 1 && p->K <= 16 && p->Lout >= DW_TL && p->Cout % 4 == 0 && p->x_ld % 4 == 0 && p->x_bs % 4 == 0 &&
                     ((uintptr_t)p->x & 15) == 0 && ((uintptr_t)p->w & 15) == 0 && (!p->bias || ((uintptr_t)p->bias & 15) == 0) &&
                     (size_t)rows * 128 * 4 <= 160 * 1024;
+    if (p->emit_hi && !(v4 && p->Cout % 64 == 0 && p->emit_ld >= p->Cout && p->emit_ld % 4 == 0 && !p->res && !p->post_cscale && !p->accumulate &&
+                        !p->post_act)) {
+      b2a_set_error("b2a_conv1d_cl: plane emission needs the vectorised depthwise path (stride 1, Cout %% 64 == 0, no epilogue extras)");
+      return B2A_E_UNSUPPORTED;
+    }
     if (v4) {
       const int CW = p->Cout >= 128 ? 128 : 64;
       dim3 grid((p->Lout + DW_TL - 1) / DW_TL, (p->Cout + CW - 1) / CW, p->B);
@@ -513,6 +536,7 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
 extern "C" int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream) {
   int bad = check_common(p);
   if (bad) { b2a_set_error("b2a_convtr1d_cl: invalid argument (check %d)", bad); return B2A_E_INVALID; }
+  B2A_CHECK_ARG(p->emit_hi == nullptr && p->y != nullptr, "plane emission is not available for transposed convs");
   B2A_CHECK_ARG(p->dilation == 1, "dilation must be 1");
   B2A_CHECK_ARG(p->pad_left >= 0, "pad_left (crop) must be >= 0");
   cudaStream_t st = (cudaStream_t)stream;

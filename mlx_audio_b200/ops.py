@@ -149,6 +149,18 @@ def _tc_transposed_weights(cw: "ConvW", stride: int):
     return cache[stride]
 
 
+@dataclass
+class Planes:
+    """A tensor-core A operand already split by its producer: bf16 hi / lo planes [B, L, cin_pad] (what prep_bf16 would make)."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    C: int
+
+    @property
+    def shape(self):
+        return (self.hi.shape[0], self.hi.shape[1], self.C)
+
+
 def pack_conv(w_mlx: torch.Tensor, bias=None, groups=1, device="cuda") -> ConvW:
     """MLX-layout conv weight [Cout, K, Cin/g] -> packed [K, Cin/g, Cout]."""
     cout, k, cin_g = w_mlx.shape
@@ -189,10 +201,18 @@ def pack_linear(w: torch.Tensor, bias=None, device="cuda") -> ConvW:
 
 def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout=None, pad_mode=0,
            pre: Optional[Pre] = None, post_act=0, post_p0=0.0, cscale=None, res=None, res_div=1,
-           out_scale=1.0, out=None, accumulate=False, transpose=False, stats=False):
+           out_scale=1.0, out=None, accumulate=False, transpose=False, stats=False, emit: Optional[Pre] = None):
     """b2a_conv1d_cl / b2a_convtr1d_cl.  For ``transpose`` ``pad_left`` is the left crop of the scatter output.
     ``stats=True`` returns (y, partials): InstanceNorm partial sums of y from the tensor-core epilogue for ``adain_coeffs(partials=)``,
     or (y, None) when the layer does not run on that path."""
+    if isinstance(x, Planes):                      # operand already split by its producer (conv1d(..., emit=...)): tensor-core path only
+        B, L, cin = x.shape
+        if cin != cw.cin or pre is not None or not _tc_eligible(cw, L, stride, transpose, pad_mode, dilation) or x.hi.shape[2] != cw.cin_pad:
+            raise ValueError("conv1d: a Planes operand needs a tensor-core-eligible layer with matching channels and no prologue")
+        if lout is None:
+            lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
+        return _conv1d_tc(x, cw, dilation, pad_left, lout, None, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
+                          up_stride=stride if transpose else 0, stats=stats)
     _chk3(x, "conv1d x")
     B, L, cin = x.shape
     if cin != cw.cin:
@@ -205,7 +225,13 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     if _tc_eligible(cw, L, stride, transpose, pad_mode, dilation):
         return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
                           up_stride=stride if transpose else 0, stats=stats)
-    if out is None:
+    planes = None
+    if emit is not None:
+        if not emit_eligible(cw, x, lout, stride, dilation, transpose) or res is not None or cscale is not None or accumulate or post_act or out is not None:
+            raise ValueError("conv1d: emit= needs a stride-1 depthwise layer with Cout % 64 == 0 and no epilogue extras (see ops.emit_eligible)")
+        planes = Planes(torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.bfloat16),
+                        torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.bfloat16) if TC_MODE[0] == "x2" else None, cw.cout)
+    elif out is None:
         out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
     else:
         _chk3(out, "conv1d out")
@@ -215,7 +241,11 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     p.x, p.x_bs, p.x_ld = x.data_ptr(), x.stride(0), x.stride(1)
     p.B, p.L, p.Cin = B, L, cin
     p.w, p.bias = cw.w.data_ptr(), _p(cw.bias)
-    p.y, p.y_bs, p.y_ld = out.data_ptr(), out.stride(0), out.stride(1)
+    if planes is None:
+        p.y, p.y_bs, p.y_ld = out.data_ptr(), out.stride(0), out.stride(1)
+    else:
+        p.emit_hi, p.emit_lo, p.emit_ld = planes.hi.data_ptr(), _p(planes.lo), cw.cout
+        p.emit_act, p.emit_p0, p.emit_a, p.emit_b = emit.act, emit.p0, _p(emit.a), _p(emit.b)
     p.Lout, p.Cout = lout, cw.cout
     p.K, p.stride, p.dilation, p.pad_left, p.groups, p.pad_mode = cw.K, stride, dilation, pad_left, cw.groups, pad_mode
     if pre is not None:
@@ -232,7 +262,16 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     fn = _lib.lib().b2a_convtr1d_cl if transpose else _lib.lib().b2a_conv1d_cl
     _call("conv" if cw.groups == 1 and cw.cin * cw.K >= 64 else "other", fn, 1, C.byref(p), _stream())
+    if planes is not None:
+        return planes
     return (out, None) if stats else out
+
+
+def emit_eligible(cw: "ConvW", x: torch.Tensor, lout: int, stride: int = 1, dilation: int = 1, transpose: bool = False) -> bool:
+    """True when conv1d(x, cw, emit=...) can write the next layer's bf16 planes directly (the vectorised depthwise kernel)."""
+    return (TC_MODE[0] != "off" and not transpose and stride == 1 and cw.groups == cw.cin == cw.cout and cw.cout % 64 == 0 and cw.K <= 16
+            and lout >= 128 and x.stride(1) % 4 == 0 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0
+            and (128 + (cw.K - 1) * dilation) * 128 * 4 <= 160 * 1024)
 
 
 def prep_bf16(x: torch.Tensor, pre: Optional[Pre], cpad: int, planes: int = 2, f16: bool = False):
@@ -256,10 +295,14 @@ TC_STATS = [os.environ.get("B2A_TC_STATS", "0") != "0" and os.environ.get("B2A_T
 
 def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
                up_stride=0, stats=False):
-    B, L, _ = x.shape
-    hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1, cw.f16)
+    if isinstance(x, Planes):
+        B, L, _ = x.shape
+        hi, lo = x.hi, x.lo
+    else:
+        B, L, _ = x.shape
+        hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1, cw.f16)
     if out is None:
-        out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
+        out = torch.empty(B, lout, cw.cout, device=hi.device, dtype=torch.float32)
     else:
         _chk3(out, "conv1d out")
         if out.shape != (B, lout, cw.cout):
@@ -280,7 +323,7 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
     if stats and TC_STATS[0]:          # InstanceNorm partials of the output straight from the epilogue (persistent kernel only)
         mrows = (L + taps - 1) if up_stride else lout
         slots = -(-mrows // 128) * 4 * max(1, up_stride)
-        ws = torch.empty(B, slots, cw.cout, 2, device=x.device, dtype=torch.float64)
+        ws = torch.empty(B, slots, cw.cout, 2, device=hi.device, dtype=torch.float64)
     _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, w_tc.data_ptr(), _p(w_lo), taps, shifts, n_total, lout,
           _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
           out.stride(1), up_stride, pad_left if up_stride else 0, _p(ws), slots, _stream())

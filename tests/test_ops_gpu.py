@@ -392,3 +392,25 @@ def test_conv1d_narrow_output(B, L, Cin, Cout, K, dil, pad_mode):
     y = ops.conv1d(x.to(dev), ops.pack_conv(w, bias, 1, dev), dilation=dil, pad_left=padl, lout=L, pad_mode=pad_mode,
                    pre=ops.Pre(act=ops.ACT["snake"], a=a.to(dev), b=(1.0 / (a + 1e-9)).to(dev)), post_act=ops.ACT["clip1"])
     assert y.shape == ref.shape and rel_err(y, ref) < 2e-5
+
+
+def test_depthwise_conv_emits_next_layers_planes():
+    """conv1d(..., emit=Pre): the vectorised depthwise kernel writes Snake(t) as the next tensor-core layer's bf16 hi/lo planes;
+    they must equal what the separate prologue pass makes from the fp32 output, and the 1x1 conv fed with them the two-kernel result."""
+    from mlx_audio_b200 import ops
+    dev = _dev()
+    B, L, C, K, d = 2, 700, 128, 7, 3
+    x, w, bias = _rand(B, L, C, seed=1).to(dev), _rand(C, K, 1, seed=2, scale=0.3), _rand(C, seed=3)
+    a1 = ((1 + 0.2 * _rand(C, seed=6)).abs() + 0.1).to(dev)
+    a2 = ((1 + 0.2 * _rand(C, seed=7)).abs() + 0.1).to(dev)
+    s1, s2 = ops.Pre(act=ops.ACT["snake"], a=a1, b=1.0 / (a1 + 1e-9)), ops.Pre(act=ops.ACT["snake"], a=a2, b=1.0 / (a2 + 1e-9))
+    dw = ops.pack_conv(w, bias, C, dev)
+    pw = ops.pack_conv(_rand(C, 1, C, seed=8, scale=0.1), _rand(C, seed=9), 1, dev)          # fp32 weights: split planes, as in SNAC
+    assert ops.emit_eligible(dw, x, L, dilation=d)
+    t = ops.conv1d(x, dw, dilation=d, pad_left=3 * d, pre=s1)
+    hi, lo = ops.prep_bf16(t, s2, C, 2, False)
+    pl = ops.conv1d(x, dw, dilation=d, pad_left=3 * d, pre=s1, emit=s2)
+    assert torch.equal(pl.hi, hi) and torch.equal(pl.lo, lo)
+    y_ref = ops.conv1d(t, pw, pre=s2, res=x)
+    y = ops.conv1d(pl, pw, res=x)
+    assert torch.equal(y, y_ref)
