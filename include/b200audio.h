@@ -91,10 +91,7 @@ int32_t b2a_convtr1d_cl(const b2a_conv1d_t* p, void* stream);
  * f16 != 0: planes and weights are IEEE fp16 instead of bf16 (fp16 checkpoints such as Whisper's: weights stay exact).
  * up_stride > 0: TRANSPOSED conv with K = taps * up_stride in polyphase form -- Cout = up_stride * C, W[tap j][r*C + co][ci] =
  * w[k = r + j*up_stride][ci][co], shifts[j] = -j; GEMM row m / column (r, co) lands on output row m*up_stride + r - up_crop
- * (rows outside [0, Lout) dropped), i.e. the GEMM output IS the up-sampled signal, no col2im pass.
- * emit_hi != NULL: the epilogue also writes act_emit(output) (emit_act / emit_p0 / per-channel emit_a, emit_b: the NEXT layer's
- * prologue) as bf16 planes hi / lo [B, Lout, emit_ld] -- the next b2a_conv1d_tc's operand, no b2a_prep_bf16 pass; y may then be NULL
- * (a pure intermediate is never stored in fp32). */
+ * (rows outside [0, Lout) dropped), i.e. the GEMM output IS the up-sampled signal, no col2im pass. */
 int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int32_t cpad,
                       const float* scale, const float* shift, int32_t act, float p0, const float* a, const float* b,
                       void* hi, void* lo, int32_t f16, void* stream);
@@ -104,8 +101,7 @@ int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16, int32_t B
                       int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                       int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
                       int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, double* stats_ws,
-                      int32_t stats_slots, void* emit_hi, void* emit_lo, int64_t emit_ld, int32_t emit_act, float emit_p0,
-                      const float* emit_a, const float* emit_b, void* stream);
+                      int32_t stats_slots, void* stream);
 
 /* profiling aid: CTA (0,0,0) of subsequent b2a_conv1d_tc launches stamps clock64() at its phase boundaries into dbg8[0..6]
  * (entry, setup done, first operands landed, last operands landed, accumulator ready, epilogue done, exit); NULL disables. */

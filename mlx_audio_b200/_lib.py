@@ -52,7 +52,7 @@ PROTOTYPES = {
     "b2a_convtr1d_cl": (i32, [C.POINTER(Conv1dParams), C.c_void_p]),
     "b2a_prep_bf16": (i32, [c_f, i64, i64, i32, i32, i32, i32, c_f, c_f, i32, f32, c_f, c_f, c_f, c_f, i32, C.c_void_p]),
     "b2a_conv1d_tc": (i32, [c_f, c_f, i32, i32, i32, i32, c_f, c_f, i32, C.POINTER(i32), i32, i32, c_f, i32, f32, c_f, i64, c_f, i64, i64, i32, f32, i32,
-                            c_f, i64, i64, i32, i32, c_f, i32, c_f, c_f, i64, i32, f32, c_f, c_f, C.c_void_p]),
+                            c_f, i64, i64, i32, i32, c_f, i32, C.c_void_p]),
     "b2a_conv1d_tc_debug": (i32, [c_f]),
     "b2a_copy2d": (i32, [c_f, i64, c_f, i64, i64, i32, C.c_void_p]),
     "b2a_gather_rows": (i32, [c_f, i64, c_f, c_f, i64, i64, i32, i64, c_f, i64, i64, C.c_void_p]),

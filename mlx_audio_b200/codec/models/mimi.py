@@ -122,17 +122,12 @@ class Mimi:
             m = ops.linear(n2, lw["l1"], post_act=ACT["gelu_tanh"])
             x = ops.linear(m, lw["l2"], cscale=lw["ls2"], res=x)
         elu = Pre(act=ACT["elu"])
-        # each layer's epilogue writes ELU(output) as the next layer's bf16 planes (no fp32 round trip + prologue pass between convs);
-        # fp32 is kept only for the residual input of a block (y) and the final waveform head
-        xp = ops.conv1d(x, W["init"], pad_left=cfg.ksize - 1, lout=x.shape[1], emit=elu, emit_pad=W["dec"][0]["up"].cin_pad, keep=False)
-        for li, lw in enumerate(W["dec"]):
+        x = ops.conv1d(x, W["init"], pad_left=cfg.ksize - 1, lout=x.shape[1])
+        for lw in W["dec"]:
             r = lw["r"]
-            y, yp = ops.conv1d(xp, lw["up"], stride=r, pad_left=0, lout=xp.shape[1] * r, transpose=True, emit=elu, emit_pad=lw["c0"].cin_pad)
-            tp = ops.conv1d(yp, lw["c0"], pad_left=cfg.residual_ksize - 1, lout=y.shape[1], emit=elu, emit_pad=lw["c1"].cin_pad, keep=False)
-            if li + 1 < len(W["dec"]):
-                xp = ops.conv1d(tp, lw["c1"], res=y, emit=elu, emit_pad=W["dec"][li + 1]["up"].cin_pad, keep=False)
-            else:
-                x = ops.conv1d(tp, lw["c1"], res=y)
+            y = ops.conv1d(x, lw["up"], stride=r, pad_left=0, lout=x.shape[1] * r, pre=elu, transpose=True)
+            t = ops.conv1d(y, lw["c0"], pad_left=cfg.residual_ksize - 1, lout=y.shape[1], pre=elu)
+            x = ops.conv1d(t, lw["c1"], pre=elu, res=y)
         pcm = ops.conv1d(x, W["final"], pad_left=cfg.last_ksize - 1, lout=x.shape[1], pre=elu)      # [B, L, 1]
         return pcm.reshape(B, 1, -1)
 

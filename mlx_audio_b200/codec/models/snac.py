@@ -127,7 +127,7 @@ class SNAC:
                 if ru["c1"].groups > 1 and ru["c2"].w_tc is not None and ops.emit_eligible(ru["c1"], y, y.shape[1], dilation=ru["d"]) \
                         and ru["c2"].cin_pad == ru["c1"].cout and ru["c2"].cin * ru["c2"].K >= ops.TC_MIN_K:
                     # depthwise conv writes Snake2(t) as the 1x1 conv's bf16 planes: no fp32 t, no prologue pass
-                    t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=s1, emit=s2, keep=False)
+                    t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=s1, emit=s2)
                     y = ops.conv1d(t, ru["c2"], res=y)
                 else:
                     t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=s1)

@@ -108,8 +108,6 @@ struct TcParams {
   float* y; int64_t y_bs, y_ld;
   long long* dbg;                 // optional: 8 clock64 stamps from CTA (0,0,0) (b2a_conv1d_tc_debug)
   double* stats; int stats_slots; // optional InstanceNorm partials of the OUTPUT: [B][stats_slots][C][2] = (sum, sum of squares) per 32-row group
-  // optional: also (or instead of y, when y == NULL) write act_emit(output) as the NEXT layer's bf16 planes [B, Lout, emit_ld]
-  __nv_bfloat16* emit_hi; __nv_bfloat16* emit_lo; int64_t emit_ld; int emit_act; float emit_p0; const float* emit_a; const float* emit_b;
 };
 
 // smem: [stages] x { A_hi 16 KB | A_lo 16 KB (planes==2) | W BN*128 B }, then barriers
@@ -655,17 +653,6 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
         const int64_t rstride = (int64_t)mul * p.res_ld;
         const float osc = p.out_scale;
         float st1 = 0.f, st2 = 0.f;                            // InstanceNorm partials of the values written below (this lane's column)
-        const float ea = (p.emit_hi && p.emit_a) ? __ldg(p.emit_a + co) : 1.f, eb = (p.emit_hi && p.emit_b) ? __ldg(p.emit_b + co) : 1.f;
-        __nv_bfloat16* eh = p.emit_hi ? p.emit_hi + ((int64_t)b * p.Lout + row0) * p.emit_ld + co : nullptr;
-        __nv_bfloat16* el = p.emit_lo ? p.emit_lo + ((int64_t)b * p.Lout + row0) * p.emit_ld + co : nullptr;
-        const int64_t estride = (int64_t)mul * p.emit_ld;
-        auto emit_one = [&](int i, float v) {
-          float t = p.emit_act ? b2a_act(v, p.emit_act, p.emit_p0, ea, eb) : v;
-          const __nv_bfloat16 h = __float2bfloat16_rn(t);
-          eh[i * estride] = h;
-          if (el) el[i * estride] = __float2bfloat16_rn(t - __bfloat162float(h));
-        };
-        const bool wy = p.y != nullptr;
         if (i_lo == 0 && i_hi == 32) {
           float rr[32];
           if (rp) {
@@ -695,17 +682,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               const float v = act_noinline(stage[i * 33 + lane] + bias, p.post_act, p.post_p0) * cso + rr[i];
-              if (wy) yp[i * ystride] = v;
-              st1 += v; st2 = fmaf(v, v, st2);
-              if (eh) emit_one(i, v);
+              yp[i * ystride] = v; st1 += v; st2 = fmaf(v, v, st2);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) {
               const float v = (stage[i * 33 + lane] + bias) * cso + rr[i];
-              if (wy) yp[i * ystride] = v;
-              st1 += v; st2 = fmaf(v, v, st2);
-              if (eh) emit_one(i, v);
+              yp[i * ystride] = v; st1 += v; st2 = fmaf(v, v, st2);
             }
           }
         } else {
@@ -716,9 +699,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
             float rv = rcol ? __ldg(rcol + (int64_t)(half_res ? (row >> 1) : row) * p.res_ld) : 0.f;
             float o = p.accumulate ? ycol[(int64_t)row * p.y_ld] : 0.f;
             const float v = (t * cs + rv) * osc + o;
-            if (wy) ycol[(int64_t)row * p.y_ld] = v;
-            st1 += v; st2 = fmaf(v, v, st2);
-            if (eh) emit_one(i, v);
+            ycol[(int64_t)row * p.y_ld] = v; st1 += v; st2 = fmaf(v, v, st2);
           }
         }
         if (p.stats) {
@@ -865,10 +846,8 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
                                  int32_t post_act, float post_p0, const float* cscale, int64_t cscale_bs, const float* res,
                                  int64_t res_bs, int64_t res_ld, int32_t res_div, float out_scale, int32_t accumulate, float* y,
                                  int64_t y_bs, int64_t y_ld, int32_t up_stride, int32_t up_crop, double* stats_ws, int32_t stats_slots,
-                                 void* emit_hi, void* emit_lo, int64_t emit_ld, int32_t emit_act, float emit_p0, const float* emit_a,
-                                 const float* emit_b, void* stream) {
-  B2A_CHECK_ARG(a_hi && w_bf16 && (y || emit_hi) && shifts_host, "null pointer");
-  B2A_CHECK_ARG(y || !accumulate, "accumulate needs y");
+                                 void* stream) {
+  B2A_CHECK_ARG(a_hi && w_bf16 && y && shifts_host, "null pointer");
   B2A_CHECK_ARG(up_stride >= 0 && up_crop >= 0 && (up_stride == 0 || (Cout % up_stride == 0 && (Cout / up_stride) % 32 == 0)),
                 "transposed mode: Cout = up_stride * C with C a multiple of 32");
   B2A_CHECK_ARG(B > 0 && L > 0 && Lout > 0 && taps > 0 && taps <= 32 && cin_pad % 64 == 0 && (res_div == 1 || res_div == 2), "bad shape (res_div must be 1 or 2)");
@@ -900,8 +879,6 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
   p.y = y; p.y_bs = y_bs; p.y_ld = y_ld;
   p.dbg = g_dbg;
   p.stats = stats_ws; p.stats_slots = stats_slots;
-  p.emit_hi = (__nv_bfloat16*)emit_hi; p.emit_lo = (__nv_bfloat16*)emit_lo; p.emit_ld = emit_ld; p.emit_act = emit_act; p.emit_p0 = emit_p0;
-  p.emit_a = emit_a; p.emit_b = emit_b;
   const int stage_bytes = TM * 128 * p.planes + p.BN * 128 * p.wplanes;
   // Two CTAs per SM whenever two 2-stage pipelines fit (<= ~113 KB each): one CTA's epilogue then overlaps the other's main
   // loop.  Otherwise one CTA per SM with as many stages as fit.  (Stage 0 doubles as the 17 KB epilogue staging tile.)
@@ -982,10 +959,6 @@ extern "C" int32_t b2a_conv1d_tc(const void* a_hi, const void* a_lo, int32_t f16
     }
   }
 
-  if (emit_hi && (!use_persist || f16)) {
-    b2a_set_error("b2a_conv1d_tc: plane emission needs the persistent bf16 kernel");
-    return B2A_E_UNSUPPORTED;
-  }
   if (stats_ws) {
     const int need = cdiv(p.Mrows, TM) * 4 * (up_stride ? up_stride : 1);
     if (!use_persist || stats_slots != need) {

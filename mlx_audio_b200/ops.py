@@ -201,24 +201,18 @@ def pack_linear(w: torch.Tensor, bias=None, device="cuda") -> ConvW:
 
 def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout=None, pad_mode=0,
            pre: Optional[Pre] = None, post_act=0, post_p0=0.0, cscale=None, res=None, res_div=1,
-           out_scale=1.0, out=None, accumulate=False, transpose=False, stats=False, emit: Optional[Pre] = None, emit_pad: Optional[int] = None,
-           keep: bool = True):
+           out_scale=1.0, out=None, accumulate=False, transpose=False, stats=False, emit: Optional[Pre] = None):
     """b2a_conv1d_cl / b2a_convtr1d_cl.  For ``transpose`` ``pad_left`` is the left crop of the scatter output.
     ``stats=True`` returns (y, partials): InstanceNorm partial sums of y from the tensor-core epilogue for ``adain_coeffs(partials=)``,
-    or (y, None) when the layer does not run on that path.
-    ``emit=Pre(...)`` (the NEXT layer's prologue) additionally returns that layer's operand as ``Planes`` -- written by this layer's
-    epilogue when it runs on the persistent tensor-core kernel (or the vectorised depthwise kernel), by a prologue pass otherwise:
-    ``keep=True`` -> (y, Planes), ``keep=False`` -> Planes only (the fp32 intermediate is then never stored)."""
+    or (y, None) when the layer does not run on that path."""
     if isinstance(x, Planes):                      # operand already split by its producer (conv1d(..., emit=...)): tensor-core path only
         B, L, cin = x.shape
         if cin != cw.cin or pre is not None or not _tc_eligible(cw, L, stride, transpose, pad_mode, dilation) or x.hi.shape[2] != cw.cin_pad:
             raise ValueError("conv1d: a Planes operand needs a tensor-core-eligible layer with matching channels and no prologue")
         if lout is None:
-            lout = (L - 1) * stride + cw.K - 2 * pad_left if transpose else (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
-        te = _tc_emit(emit, cw)
-        r_ = _conv1d_tc(x, cw, dilation, pad_left, lout, None, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
-                        up_stride=stride if transpose else 0, stats=stats, emit=te, emit_pad=emit_pad, keep=keep)
-        return r_ if (emit is None or te is not None) else _emit_fallback(r_, emit, cw, emit_pad, keep)
+            lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
+        return _conv1d_tc(x, cw, dilation, pad_left, lout, None, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
+                          up_stride=stride if transpose else 0, stats=stats)
     _chk3(x, "conv1d x")
     B, L, cin = x.shape
     if cin != cw.cin:
@@ -229,16 +223,8 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
     if _tc_eligible(cw, L, stride, transpose, pad_mode, dilation):
-        if emit is not None and _tc_emit(emit, cw) is None:
-            return _emit_fallback(_conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out,
-                                             accumulate, up_stride=stride if transpose else 0), emit, cw, emit_pad, keep)
         return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
-                          up_stride=stride if transpose else 0, stats=stats, emit=emit, emit_pad=emit_pad, keep=keep)
-    if emit is not None and not (cw.groups > 1 and emit_eligible(cw, x, lout, stride, dilation, transpose) and res is None and cscale is None
-                                 and not accumulate and not post_act and out is None and not keep):
-        y = conv1d(x, cw, stride=stride, dilation=dilation, pad_left=pad_left, lout=lout, pad_mode=pad_mode, pre=pre, post_act=post_act,
-                   post_p0=post_p0, cscale=cscale, res=res, res_div=res_div, out_scale=out_scale, out=out, accumulate=accumulate, transpose=transpose)
-        return _emit_fallback(y, emit, cw, emit_pad, keep)
+                          up_stride=stride if transpose else 0, stats=stats)
     planes = None
     if emit is not None:
         if not emit_eligible(cw, x, lout, stride, dilation, transpose) or res is not None or cscale is not None or accumulate or post_act or out is not None:
@@ -281,21 +267,6 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     return (out, None) if stats else out
 
 
-def _tc_emit(emit, cw):
-    """The tensor-core epilogue emits bf16 planes only (x1 / x2 modes of a bf16 or fp32 checkpoint, persistent kernel on)."""
-    if emit is None or cw.f16 or emit.scale is not None or os.environ.get("B2A_TC_PERSIST", "1") == "0" or os.environ.get("B2A_TC_EMIT", "1") == "0":
-        return None
-    return emit
-
-
-def _emit_fallback(y, emit, cw, emit_pad, keep):
-    """Planes of emit(y) through the separate prologue pass (layers that cannot emit from their epilogue)."""
-    cp = emit_pad or -(-cw.cout // 64) * 64
-    hi, lo = prep_bf16(y, emit, cp, 2 if TC_MODE[0] == "x2" else 1, False)
-    pl = Planes(hi, lo, cw.cout)
-    return (y, pl) if keep else pl
-
-
 def emit_eligible(cw: "ConvW", x: torch.Tensor, lout: int, stride: int = 1, dilation: int = 1, transpose: bool = False) -> bool:
     """True when conv1d(x, cw, emit=...) can write the next layer's bf16 planes directly (the vectorised depthwise kernel)."""
     return (TC_MODE[0] != "off" and not transpose and stride == 1 and cw.groups == cw.cin == cw.cout and cw.cout % 64 == 0 and cw.K <= 16
@@ -323,21 +294,15 @@ TC_STATS = [os.environ.get("B2A_TC_STATS", "0") != "0" and os.environ.get("B2A_T
 
 
 def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
-               up_stride=0, stats=False, emit=None, emit_pad=None, keep=True):
+               up_stride=0, stats=False):
     if isinstance(x, Planes):
         B, L, _ = x.shape
         hi, lo = x.hi, x.lo
     else:
         B, L, _ = x.shape
         hi, lo = prep_bf16(x, pre, cw.cin_pad, 2 if TC_MODE[0] == "x2" else 1, cw.f16)
-    planes = None
-    if emit is not None:                                   # the epilogue writes the next layer's operand (see b2a_conv1d_tc)
-        cp = emit_pad or -(-cw.cout // 64) * 64
-        mk = torch.empty if cp == cw.cout else torch.zeros
-        planes = Planes(mk(B, lout, cp, device=hi.device, dtype=torch.bfloat16),
-                        mk(B, lout, cp, device=hi.device, dtype=torch.bfloat16) if TC_MODE[0] == "x2" else None, cw.cout)
     if out is None:
-        out = torch.empty(B, lout, cw.cout, device=hi.device, dtype=torch.float32) if (keep or planes is None) else None
+        out = torch.empty(B, lout, cw.cout, device=hi.device, dtype=torch.float32)
     else:
         _chk3(out, "conv1d out")
         if out.shape != (B, lout, cw.cout):
@@ -360,13 +325,8 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
         slots = -(-mrows // 128) * 4 * max(1, up_stride)
         ws = torch.empty(B, slots, cw.cout, 2, device=hi.device, dtype=torch.float64)
     _call("conv_tc", _lib.lib().b2a_conv1d_tc, 1, hi.data_ptr(), _p(lo), int(cw.f16), B, L, cw.cin_pad, w_tc.data_ptr(), _p(w_lo), taps, shifts, n_total, lout,
-          _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), _p(out),
-          0 if out is None else out.stride(0), 0 if out is None else out.stride(1), up_stride, pad_left if up_stride else 0, _p(ws), slots,
-          None if planes is None else planes.hi.data_ptr(), None if planes is None else _p(planes.lo), 0 if planes is None else planes.hi.shape[2],
-          0 if emit is None else emit.act, 0.0 if emit is None else emit.p0, None if emit is None else _p(emit.a), None if emit is None else _p(emit.b),
-          _stream())
-    if planes is not None:
-        return (out, planes) if keep else planes
+          _p(cw.bias), post_act, post_p0, cs, cs_bs, r, r_bs, r_ld, res_div, out_scale, int(accumulate), out.data_ptr(), out.stride(0),
+          out.stride(1), up_stride, pad_left if up_stride else 0, _p(ws), slots, _stream())
     return (out, ws) if stats else out
 
 

@@ -134,28 +134,13 @@ class Qwen3TTSSpeechTokenizerDecoder:
         if taps is not None:
             taps["upsample"] = h
         # ---- decoder: conv k7, 4 x (SnakeBeta, ConvT, 3 residual units), SnakeBeta, conv k7 -> 1, clip
-        # Every layer's epilogue writes the NEXT layer's operand (SnakeBeta applied, bf16 hi/lo planes): the chain
-        # conv -> [fp32 store] -> [prologue pass: load, Snake, split, store] -> conv collapses to conv -> conv; fp32 is kept only where a
-        # residual needs it (unit outputs) -- pure intermediates (t, the stem, the SnakeBeta'd block inputs) never reach HBM in fp32.
-        blocks = W["blocks"]
-        wp = ops.conv1d(h, W["init"], pad_left=6, lout=h.shape[1], emit=blocks[0]["snake"], keep=False)
-        w = None
-        for bi, bw in enumerate(blocks):
+        w = ops.conv1d(h, W["init"], pad_left=6, lout=h.shape[1])
+        for bi, bw in enumerate(W["blocks"]):
             r = bw["r"]
-            units = bw["units"]
-            w, wp = ops.conv1d(wp, bw["up"], stride=r, pad_left=0, lout=wp.shape[1] * r, transpose=True, emit=units[0]["s1"], emit_pad=units[0]["c1"].cin_pad)
-            for ui, u in enumerate(units):
-                tp = ops.conv1d(wp, u["c1"], dilation=u["d"], pad_left=6 * u["d"], lout=w.shape[1], emit=u["s2"], emit_pad=u["c2"].cin_pad, keep=False)
-                if ui + 1 < len(units):
-                    nxt, npad = units[ui + 1]["s1"], units[ui + 1]["c1"].cin_pad
-                elif bi + 1 < len(blocks):
-                    nxt, npad = blocks[bi + 1]["snake"], blocks[bi + 1]["up"].cin_pad
-                else:
-                    nxt, npad = None, None
-                if nxt is not None:
-                    w, wp = ops.conv1d(tp, u["c2"], res=w, emit=nxt, emit_pad=npad)
-                else:
-                    w = ops.conv1d(tp, u["c2"], res=w)
+            w = ops.conv1d(w, bw["up"], stride=r, pad_left=0, lout=w.shape[1] * r, pre=bw["snake"], transpose=True)
+            for u in bw["units"]:
+                t = ops.conv1d(w, u["c1"], dilation=u["d"], pad_left=6 * u["d"], lout=w.shape[1], pre=u["s1"])
+                w = ops.conv1d(t, u["c2"], pre=u["s2"], res=w)
             if taps is not None:
                 taps[f"block{bi}"] = w
         wav = ops.conv1d(w, W["out_conv"], pad_left=6, lout=w.shape[1], pre=W["out_snake"], post_act=ACT["clip1"])   # [B, L, 1]

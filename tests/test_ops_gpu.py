@@ -409,7 +409,7 @@ def test_depthwise_conv_emits_next_layers_planes():
     assert ops.emit_eligible(dw, x, L, dilation=d)
     t = ops.conv1d(x, dw, dilation=d, pad_left=3 * d, pre=s1)
     hi, lo = ops.prep_bf16(t, s2, C, 2, False)
-    pl = ops.conv1d(x, dw, dilation=d, pad_left=3 * d, pre=s1, emit=s2, keep=False)
+    pl = ops.conv1d(x, dw, dilation=d, pad_left=3 * d, pre=s1, emit=s2)
     assert torch.equal(pl.hi, hi) and torch.equal(pl.lo, lo)
     y_ref = ops.conv1d(t, pw, pre=s2, res=x)
     y = ops.conv1d(pl, pw, res=x)
