@@ -148,17 +148,44 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
   const int K = KT ? KT : p.K;
   const float* xb = p.x + (int64_t)b * p.x_bs + c;
   const int64_t pos0 = (int64_t)l0 - p.pad_left;
-  for (int r = warp * RPW + rsub; r < rows; r += (NT / 32) * RPW) {
-    int64_t pos = pos0 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (cok) {
+  // per-channel prologue constants in registers (the generic functor re-loads them for every element)
+  float pa[4] = {1.f, 1.f, 1.f, 1.f}, pb[4] = {1.f, 1.f, 1.f, 1.f}, ps[4] = {1.f, 1.f, 1.f, 1.f}, ph[4] = {0.f, 0.f, 0.f, 0.f};
+  if (cok) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (p.pre_a) pa[q] = __ldg(p.pre_a + c + q);
+      if (p.pre_b) pb[q] = __ldg(p.pre_b + c + q);
+      if (p.pre_scale) { ps[q] = __ldg(p.pre_scale + (int64_t)b * p.Cin + c + q); ph[q] = __ldg(p.pre_shift + (int64_t)b * p.Cin + c + q); }
+    }
+  }
+  auto tr = [&](float v, int q) -> float {
+    if (p.pre_scale) v = fmaf(v, ps[q], ph[q]);
+    if (p.pre_act) v = b2a_act(v, p.pre_act, p.pre_p0, pa[q], pb[q]);
+    return v;
+  };
+  // staging: FOUR rows per thread and iteration, all four 16-byte loads in flight before the first is used (one load per
+  // iteration left the CTA waiting a full memory latency twelve times per tile)
+  constexpr int RSTEP = (NT / 32) * RPW;
+  for (int r0 = warp * RPW + rsub; r0 < rows; r0 += 4 * RSTEP) {
+    float4 t[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + u * RSTEP;
+      int64_t pos = pos0 + r;
       if (pos < 0 || pos >= p.L) pos = p.pad_mode == 1 ? (pos < 0 ? 0 : (int64_t)p.L - 1) : -1;
-      if (pos >= 0) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(xb + pos * p.x_ld));
-        v.x = pre(t.x, b, c); v.y = pre(t.y, b, c + 1); v.z = pre(t.z, b, c + 2); v.w = pre(t.w, b, c + 3);
+      ok[u] = cok && r < rows && pos >= 0;
+      t[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(xb + pos * p.x_ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int r = r0 + u * RSTEP;
+      if (r < rows) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok[u]) { v.x = tr(t[u].x, 0); v.y = tr(t[u].y, 1); v.z = tr(t[u].z, 2); v.w = tr(t[u].w, 3); }
+        *reinterpret_cast<float4*>(smem + (size_t)r * CW + c4) = v;
       }
     }
-    *reinterpret_cast<float4*>(smem + (size_t)r * CW + c4) = v;
   }
   float4 w[KT ? KT : 16];
 #pragma unroll
@@ -169,6 +196,11 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
   __syncthreads();
   if (!cok) return;
   const int d = p.dilation;
+  float ea[4] = {1.f, 1.f, 1.f, 1.f}, eb[4] = {1.f, 1.f, 1.f, 1.f};
+  if (p.emit_hi) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) { if (p.emit_a) ea[q] = __ldg(p.emit_a + c + q); if (p.emit_b) eb[q] = __ldg(p.emit_b + c + q); }
+  }
   const bool fast = !p.res && !p.post_cscale && !p.accumulate && !p.post_act && (p.y_ld % 4 == 0) && (p.y_bs % 4 == 0) &&
                     ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0);
 #pragma unroll 2
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         float t = o[q];
-        if (p.emit_act) t = b2a_act(t, p.emit_act, p.emit_p0, p.emit_a ? __ldg(p.emit_a + c + q) : 1.f, p.emit_b ? __ldg(p.emit_b + c + q) : 1.f);
+        if (p.emit_act) t = b2a_act(t, p.emit_act, p.emit_p0, ea[q], eb[q]);
         h[q] = __float2bfloat16_rn(t);
         lw[q] = __float2bfloat16_rn(t - __bfloat162float(h[q]));
       }
