@@ -737,50 +737,38 @@ __global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int6
   const int cp8 = cpad / 8;
   const int64_t total = (int64_t)B * L * cp8;
   const bool vec = (x_ld % 4 == 0) && (x_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  // two index slots per iteration, both loads in flight before either is used (memory-level parallelism: the one-slot loop waited a
-  // full latency per 32 bytes).  (A variant that pinned a channel group per thread to avoid the divisions measured slower.)
-  for (int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += 2 * stride) {
-    int cc0[2], bq[2]; int64_t rq[2]; bool live[2]; float v[2][8];
+  // Measured alternatives that were SLOWER than this plain grid-stride loop (kept out): a channel group pinned per thread with the
+  // constants in registers and no divisions (Whisper prep 5.0 -> 7.7 ms), and two index slots per iteration with both loads in
+  // flight (vocoder prep 24 -> 30 ms: the extra registers cost more occupancy than the second load buys).
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cp8) * 8;
+    const int64_t r = idx / cp8;
+    const int l = (int)(r % L), b = (int)(r / L);
+    const float* xp = x + (int64_t)b * x_bs + (int64_t)l * x_ld + c;
+    float v[8];
+    if (vec && c + 8 <= C) {
+      float4 t0 = __ldg(reinterpret_cast<const float4*>(xp)), t1 = __ldg(reinterpret_cast<const float4*>(xp) + 1);
+      v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    } else {
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int64_t idx = idx0 + u * stride;
-      live[u] = idx < total;
-      const int64_t id = live[u] ? idx : 0;
-      cc0[u] = (int)(id % cp8) * 8;
-      rq[u] = id / cp8;
-      const int l = (int)(rq[u] % L);
-      bq[u] = (int)(rq[u] / L);
-      const float* xp = x + (int64_t)bq[u] * x_bs + (int64_t)l * x_ld + cc0[u];
-      if (live[u] && vec && cc0[u] + 8 <= C) {
-        float4 t0 = __ldg(reinterpret_cast<const float4*>(xp)), t1 = __ldg(reinterpret_cast<const float4*>(xp) + 1);
-        v[u][0] = t0.x; v[u][1] = t0.y; v[u][2] = t0.z; v[u][3] = t0.w; v[u][4] = t1.x; v[u][5] = t1.y; v[u][6] = t1.z; v[u][7] = t1.w;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; q++) v[u][q] = (live[u] && cc0[u] + q < C) ? __ldg(xp + q) : 0.f;
-      }
+      for (int q = 0; q < 8; q++) v[q] = (c + q < C) ? __ldg(xp + q) : 0.f;
     }
+    __align__(16) T16 h[8];
+    __align__(16) T16 lw[8];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      if (!live[u]) continue;
-      const int c = cc0[u], b = bq[u];
-      __align__(16) T16 h[8];
-      __align__(16) T16 lw[8];
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const int cc = c + q;
-        float t = 0.f;
-        if (cc < C) {
-          t = v[u][q];
-          if (scale) t = fmaf(t, __ldg(scale + (int64_t)b * C + cc), __ldg(shift + (int64_t)b * C + cc));
-          if (act) t = b2a_act(t, act, p0, a ? __ldg(a + cc) : 1.f, bb ? __ldg(bb + cc) : 1.f);
-        }
-        h[q] = to16<T16>(t);
-        lw[q] = to16<T16>(t - from16(h[q]));
+    for (int q = 0; q < 8; q++) {
+      const int cc = c + q;
+      float t = 0.f;
+      if (cc < C) {
+        t = v[q];
+        if (scale) t = fmaf(t, __ldg(scale + (int64_t)b * C + cc), __ldg(shift + (int64_t)b * C + cc));
+        if (act) t = b2a_act(t, act, p0, a ? __ldg(a + cc) : 1.f, bb ? __ldg(bb + cc) : 1.f);
       }
-      *reinterpret_cast<uint4*>(hi + rq[u] * cpad + c) = *reinterpret_cast<uint4*>(h);
-      if (lo) *reinterpret_cast<uint4*>(lo + rq[u] * cpad + c) = *reinterpret_cast<uint4*>(lw);
+      h[q] = to16<T16>(t);
+      lw[q] = to16<T16>(t - from16(h[q]));
     }
+    *reinterpret_cast<uint4*>(hi + r * cpad + c) = *reinterpret_cast<uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + r * cpad + c) = *reinterpret_cast<uint4*>(lw);
   }
 }
 
