@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NT) conv1d_dw_kernel(const b2a_conv1d_t p) {
 // Vectorised variant (C % 4 == 0, 16-byte aligned rows): a lane owns FOUR consecutive channels, so global loads / stores and the
 // per-tap shared-memory reads are 16 bytes wide (4x fewer LSU instructions than the scalar tile; the SNAC decoder's twelve
 // depthwise layers were LSU-bound at 22 % of HBM bandwidth).  CTA = DW_TL positions x CW channels (CW = 64 or 128).
-template <int KT, int CW>
+template <int KT, int CW, bool SNAKE>     // SNAKE: prologue (and emitted) activation known to be Snake at compile time (no switch, 3x less code)
 __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t p, int rows) {
   constexpr int LPR = CW / 4, RPW = 32 / LPR;        // lanes per row, rows per warp-wide access
   extern __shared__ __align__(16) float smem[];      // [rows][CW]
@@ -159,9 +159,12 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
     }
   }
   auto tr = [&](float v, int q) -> float {
-    if (p.pre_scale) v = fmaf(v, ps[q], ph[q]);
-    if (p.pre_act) v = b2a_act(v, p.pre_act, p.pre_p0, pa[q], pb[q]);
-    return v;
+    if constexpr (SNAKE) { const float sn = b2a_sin(pa[q] * v); return fmaf(pb[q], sn * sn, v); }
+    else {
+      if (p.pre_scale) v = fmaf(v, ps[q], ph[q]);
+      if (p.pre_act) v = b2a_act(v, p.pre_act, p.pre_p0, pa[q], pb[q]);
+      return v;
+    }
   };
   // staging: FOUR rows per thread and iteration, all four 16-byte loads in flight before the first is used (one load per
   // iteration left the CTA waiting a full memory latency twelve times per tile)
@@ -221,7 +224,8 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         float t = o[q];
-        if (p.emit_act) t = b2a_act(t, p.emit_act, p.emit_p0, ea[q], eb[q]);
+        if constexpr (SNAKE) { const float sn = b2a_sin(ea[q] * t); t = fmaf(eb[q], sn * sn, t); }
+        else if (p.emit_act) t = b2a_act(t, p.emit_act, p.emit_p0, ea[q], eb[q]);
         h[q] = __float2bfloat16_rn(t);
         lw[q] = __float2bfloat16_rn(t - __bfloat162float(h[q]));
       }
@@ -255,13 +259,40 @@ __global__ void __launch_bounds__(NT) conv1d_narrow_kernel(const b2a_conv1d_t p,
   const Pre pre = make_pre(p);
   const float* xb = p.x + (int64_t)b * p.x_bs;
   const int64_t pos0 = (int64_t)l0 - p.pad_left;
-  for (int idx = tid; idx < rows * p.Cin; idx += NT) {
-    const int c = idx % p.Cin, r = idx / p.Cin;
-    const int64_t pos = pos0 + r;
-    float v = 0.f;
-    if (pos >= 0 && pos < p.L) v = pre(__ldg(xb + pos * p.x_ld + c), b, c);
-    else if (p.pad_mode == 1) v = pre(__ldg(xb + (pos < 0 ? 0 : (int64_t)p.L - 1) * p.x_ld + c), b, c);
-    xs[r * ldx + c] = v;
+  const bool v4 = (p.Cin % 4 == 0) && (p.x_ld % 4 == 0) && (p.x_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+  if (v4) {
+    // 16-byte loads, four in flight per thread before the first is consumed (the scalar one-load-per-iteration loop left the CTA
+    // waiting a full memory latency 64 times per tile: 9.7 ms for Mimi's 4.9 GB head instead of ~1 ms)
+    const int q4 = p.Cin >> 2, n4 = rows * q4;
+    for (int i0 = tid; i0 < n4; i0 += 4 * NT) {
+      float4 t[4]; int rr[4], cc[4]; bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + u * NT;
+        rr[u] = i / q4; cc[u] = (i - rr[u] * q4) << 2;
+        int64_t pos = pos0 + rr[u];
+        if (pos < 0 || pos >= p.L) pos = p.pad_mode == 1 ? (pos < 0 ? 0 : (int64_t)p.L - 1) : -1;
+        ok[u] = i < n4 && pos >= 0;
+        t[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(xb + pos * p.x_ld + cc[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (i0 + u * NT < n4) {
+          float* d = xs + rr[u] * ldx + cc[u];
+          if (ok[u]) { d[0] = pre(t[u].x, b, cc[u]); d[1] = pre(t[u].y, b, cc[u] + 1); d[2] = pre(t[u].z, b, cc[u] + 2); d[3] = pre(t[u].w, b, cc[u] + 3); }
+          else { d[0] = 0.f; d[1] = 0.f; d[2] = 0.f; d[3] = 0.f; }
+        }
+      }
+    }
+  } else {
+    for (int idx = tid; idx < rows * p.Cin; idx += NT) {
+      const int c = idx % p.Cin, r = idx / p.Cin;
+      const int64_t pos = pos0 + r;
+      float v = 0.f;
+      if (pos >= 0 && pos < p.L) v = pre(__ldg(xb + pos * p.x_ld + c), b, c);
+      else if (p.pad_mode == 1) v = pre(__ldg(xb + (pos < 0 ? 0 : (int64_t)p.L - 1) * p.x_ld + c), b, c);
+      xs[r * ldx + c] = v;
+    }
   }
   for (int idx = tid; idx < p.K * p.Cin * p.Cout; idx += NT) ws[idx] = __ldg(p.w + idx);
   __syncthreads();
@@ -527,20 +558,26 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
       const int CW = p->Cout >= 128 ? 128 : 64;
       dim3 grid((p->Lout + DW_TL - 1) / DW_TL, (p->Cout + CW - 1) / CW, p->B);
       const size_t sm = (size_t)rows * CW * sizeof(float);
+      const bool snake = p->pre_act == B2A_ACT_SNAKE && !p->pre_scale && (!p->emit_hi || p->emit_act == B2A_ACT_SNAKE);
       static bool attr = false;
       if (!attr) {
-        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<7, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<0, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(conv1d_dw_tiled4_kernel<0, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr = true;
       }
-      if (p->K == 7) {
-        if (CW == 128) conv1d_dw_tiled4_kernel<7, 128><<<grid, NT, sm, st>>>(*p, rows);
-        else conv1d_dw_tiled4_kernel<7, 64><<<grid, NT, sm, st>>>(*p, rows);
+      if (p->K == 7 && snake && (p->emit_hi || true)) {
+        if (CW == 128) conv1d_dw_tiled4_kernel<7, 128, true><<<grid, NT, sm, st>>>(*p, rows);
+        else conv1d_dw_tiled4_kernel<7, 64, true><<<grid, NT, sm, st>>>(*p, rows);
+      } else if (p->K == 7) {
+        if (CW == 128) conv1d_dw_tiled4_kernel<7, 128, false><<<grid, NT, sm, st>>>(*p, rows);
+        else conv1d_dw_tiled4_kernel<7, 64, false><<<grid, NT, sm, st>>>(*p, rows);
       } else {
-        if (CW == 128) conv1d_dw_tiled4_kernel<0, 128><<<grid, NT, sm, st>>>(*p, rows);
-        else conv1d_dw_tiled4_kernel<0, 64><<<grid, NT, sm, st>>>(*p, rows);
+        if (CW == 128) conv1d_dw_tiled4_kernel<0, 128, false><<<grid, NT, sm, st>>>(*p, rows);
+        else conv1d_dw_tiled4_kernel<0, 64, false><<<grid, NT, sm, st>>>(*p, rows);
       }
     } else if (p->stride == 1 && p->K <= 16 && rows * 32 * 4 <= 96 * 1024 && p->Lout >= DW_TL) {
       dim3 grid((p->Lout + DW_TL - 1) / DW_TL, (p->Cout + 31) / 32, p->B);

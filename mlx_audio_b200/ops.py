@@ -122,7 +122,7 @@ class ConvW:
 # (fp32-grade products); "x1" = tcgen05 with a single bf16 plane.
 TC_MODE = [os.environ.get("B2A_TC", "x2")]
 ATTN_MODE = [os.environ.get("B2A_ATTN", "tc")]      # "tc": tcgen05 flash attention for head_dim 64; "cuda": CUDA-core kernel
-TC_MIN_K = 64                          # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
+TC_MIN_K = 32                          # reduction length (Cin*K) below which the layer stays on the CUDA-core kernel
 
 
 def _tc_eligible(cw: "ConvW", L: int, stride: int, transpose: bool, pad_mode: int, dilation: int = 1) -> bool:

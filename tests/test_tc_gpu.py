@@ -31,6 +31,7 @@ CASES = [
     (2, 700, 96, 96, 7, 9, 54),          # Qwen3 vocoder block 4: N tile 96, taps spanning 54 rows
     (1, 40000, 192, 192, 7, 3, 18),      # N tile 192, > 148 tiles: persistent kernel with several tiles per CTA
     (1, 600, 384, 384, 1, 1, 0),
+    (1, 5000, 32, 64, 1, 1, 0),          # Mimi's last residual 1x1 (hidden 32): half of the 64-wide K chunk is zero padding
 ]
 
 
