@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(NT) conv1d_dw_tiled4_kernel(const b2a_conv1d_t
 // output position: K*Cin FMAs against shared memory (row stride Cin+1: conflict-free), weights broadcast from shared memory.
 // HBM-bound by construction: x is read once, y is 1/Cin of it.
 constexpr int NW_TL = 256;
+template <int ACT>      // ACT >= 0: prologue activation fixed at compile time (no AdaIN scale/shift); -1: generic functor
 __global__ void __launch_bounds__(NT) conv1d_narrow_kernel(const b2a_conv1d_t p, int rows) {
   extern __shared__ __align__(16) float smem[];
   const int ldx = p.Cin + 1;
@@ -256,7 +257,14 @@ __global__ void __launch_bounds__(NT) conv1d_narrow_kernel(const b2a_conv1d_t p,
   float* ws = smem + (size_t)rows * ldx;              // [K][Cin][Cout]
   const int tid = threadIdx.x, b = blockIdx.y;
   const int l0 = blockIdx.x * NW_TL;
-  const Pre pre = make_pre(p);
+  const Pre pre_f = make_pre(p);
+  auto pre = [&](float v, int bi, int c) -> float {
+    if constexpr (ACT == B2A_ACT_SNAKE) { const float sn = b2a_sin(__ldg(p.pre_a + c) * v); return fmaf(__ldg(p.pre_b + c), sn * sn, v); }
+    else if constexpr (ACT == B2A_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    else if constexpr (ACT == B2A_ACT_LRELU) return v > 0.f ? v : v * p.pre_p0;
+    else if constexpr (ACT == 0) return v;
+    else return pre_f(v, bi, c);
+  };
   const float* xb = p.x + (int64_t)b * p.x_bs;
   const int64_t pos0 = (int64_t)l0 - p.pad_left;
   const bool v4 = (p.Cin % 4 == 0) && (p.x_ld % 4 == 0) && (p.x_bs % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
@@ -525,9 +533,21 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
     const int rows = NW_TL + (p->K - 1) * p->dilation;
     const size_t sm = ((size_t)rows * (p->Cin + 1) + (size_t)p->K * p->Cin * p->Cout) * sizeof(float);
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv1d_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr = true; }
+    if (!attr) {
+      cudaFuncSetAttribute(conv1d_narrow_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(conv1d_narrow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(conv1d_narrow_kernel<B2A_ACT_SNAKE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(conv1d_narrow_kernel<B2A_ACT_ELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(conv1d_narrow_kernel<B2A_ACT_LRELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      attr = true;
+    }
     dim3 grid(cdiv(p->Lout, NW_TL), p->B);
-    conv1d_narrow_kernel<<<grid, NT, sm, st>>>(*p, rows);
+    if (p->pre_scale) conv1d_narrow_kernel<-1><<<grid, NT, sm, st>>>(*p, rows);
+    else if (p->pre_act == 0) conv1d_narrow_kernel<0><<<grid, NT, sm, st>>>(*p, rows);
+    else if (p->pre_act == B2A_ACT_SNAKE && p->pre_a && p->pre_b) conv1d_narrow_kernel<B2A_ACT_SNAKE><<<grid, NT, sm, st>>>(*p, rows);
+    else if (p->pre_act == B2A_ACT_ELU) conv1d_narrow_kernel<B2A_ACT_ELU><<<grid, NT, sm, st>>>(*p, rows);
+    else if (p->pre_act == B2A_ACT_LRELU) conv1d_narrow_kernel<B2A_ACT_LRELU><<<grid, NT, sm, st>>>(*p, rows);
+    else conv1d_narrow_kernel<-1><<<grid, NT, sm, st>>>(*p, rows);
   } else if (p->groups == 1) {
     const int CI = p->K <= 4 ? 32 : (p->K <= 12 ? 16 : 8);
     const int rows = (BM - 1) * p->stride + (p->K - 1) * p->dilation + 1;
