@@ -60,38 +60,6 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int64_t x_ld, cons
   const int lane = threadIdx.x & 31;
   const float* xp = x + row * x_ld;
   const float* rp = res ? res + row * res_ld : nullptr;
-  float* yp = y + row * y_ld;
-  if (C <= 32 * 32) {
-    // the whole row lives in registers (<= 32 values per lane): ONE pass over global memory instead of three -- these launches sit on
-    // the critical path of the small-T transformers (ALBERT: 24 of them per utterance)
-    float v[32];
-    float s1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const int c = lane + 32 * j;
-      v[j] = c < C ? xp[c] + (rp ? rp[c] : 0.f) : 0.f;
-      s1 += v[j];
-    }
-    s1 = warp_sum(s1);
-    const float mean = rms ? 0.f : s1 / C;
-    float s2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; j++) { const int c = lane + 32 * j; const float d = c < C ? v[j] - mean : 0.f; s2 = fmaf(d, d, s2); }
-    s2 = warp_sum(s2);
-    const float rstd = rsqrtf(s2 / C + eps);
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const int c = lane + 32 * j;
-      if (c < C) {
-        float t = (v[j] - mean) * rstd;
-        if (ada) t = fmaf(1.f + ada[c], t, ada[C + c]);
-        else { if (w) t *= w[c]; if (bb) t += bb[c]; }
-        if (post_act) t = b2a_act(t, post_act, post_p0, 1.f, 1.f);
-        yp[c] = t;
-      }
-    }
-    return;
-  }
   float s1 = 0.f;
   for (int c = lane; c < C; c += 32) { float v = xp[c] + (rp ? rp[c] : 0.f); s1 += v; }
   s1 = warp_sum(s1);
@@ -100,6 +68,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int64_t x_ld, cons
   for (int c = lane; c < C; c += 32) { float v = xp[c] + (rp ? rp[c] : 0.f) - mean; s2 = fmaf(v, v, s2); }
   s2 = warp_sum(s2);
   const float rstd = rsqrtf(s2 / C + eps);
+  float* yp = y + row * y_ld;
   for (int c = lane; c < C; c += 32) {
     float v = (xp[c] + (rp ? rp[c] : 0.f) - mean) * rstd;
     if (ada) v = fmaf(1.f + ada[c], v, ada[C + c]);
