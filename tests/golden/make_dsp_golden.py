@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Golden vectors for the DSP front end produced by the REFERENCE'S OWN code (mlx_audio/dsp.py and
+stt/models/whisper/audio.py:log_mel_spectrogram), executed in the build container with NumPy standing in for the MLX primitives it
+calls (tests/golden/numpy_mlx_shim.py: MLX itself has no wheel here).  What is pinned is therefore the reference's control flow,
+constants, padding / framing / normalisation rules -- the parts a restatement can get wrong -- on top of NumPy's definition of the
+primitives.  /root/reference does not exist on the GPU box: the vectors are committed.
+
+    python tests/golden/make_dsp_golden.py          # needs /root/reference
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import numpy_mlx_shim  # noqa: E402
+
+REF = "/root/reference/mlx_audio"
+
+
+def load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    spec.loader.exec_module(m)
+    return m
+
+
+def main():
+    numpy_mlx_shim.install()
+    dsp = load(os.path.join(REF, "dsp.py"), "ref_dsp")
+    # stubs for audio.py's package imports: `mlx_audio.utils` re-exports dsp (utils.py:31-40), `mlx_audio.stt.utils.load_audio` is unused
+    pkg = types.ModuleType("mlx_audio"); pkg.__path__ = []
+    stt = types.ModuleType("mlx_audio.stt"); stt.__path__ = []
+    stt_utils = types.ModuleType("mlx_audio.stt.utils"); stt_utils.load_audio = lambda *_a, **_k: (_ for _ in ()).throw(RuntimeError("no files"))
+    utils = types.ModuleType("mlx_audio.utils")
+    for n in ("hanning", "mel_filters", "stft"):
+        setattr(utils, n, getattr(dsp, n))
+    sys.modules.update({"mlx_audio": pkg, "mlx_audio.stt": stt, "mlx_audio.stt.utils": stt_utils, "mlx_audio.utils": utils})
+    audio = load(os.path.join(REF, "stt/models/whisper/audio.py"), "ref_whisper_audio")
+
+    out = {}
+    for name in ("hanning", "hamming", "blackman", "bartlett"):
+        for size in (20, 400):
+            out[f"win_{name}_{size}"] = np.asarray(getattr(dsp, name)(size), dtype=np.float32)
+            out[f"win_{name}_{size}_periodic"] = np.asarray(getattr(dsp, name)(size, periodic=True), dtype=np.float32)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(4000).astype(np.float32)
+    for tag, kw in (("whisper", dict(n_fft=400, hop_length=160, window="hann")), ("kokoro", dict(n_fft=20, hop_length=5, window="hann")),
+                    ("const", dict(n_fft=256, hop_length=64, window="hamming", pad_mode="constant")), ("nocenter", dict(n_fft=128, hop_length=32, center=False)),
+                    ("shortwin", dict(n_fft=512, hop_length=128, win_length=400))):
+        s = dsp.stft(numpy_mlx_shim.array(x), **kw)
+        out[f"stft_{tag}_re"], out[f"stft_{tag}_im"] = np.real(s).astype(np.float32), np.imag(s).astype(np.float32)
+    s = dsp.stft(numpy_mlx_shim.array(x), n_fft=256, hop_length=64)
+    # win_length is passed explicitly: the default reads the FRAME count ((x.shape[1] - 1) * 2, dsp.py:465-466), a reference quirk
+    # that only works when frames == n_fft / 2 + 1 (kept in the oracle and the product, pinned in tests/test_oracle_pins.py)
+    for tag, kw in (("default", dict(hop_length=64, win_length=256)), ("len", dict(hop_length=64, win_length=256, length=3900)),
+                    ("norm", dict(hop_length=64, win_length=256, normalized=True))):
+        out[f"istft_{tag}"] = np.asarray(dsp.istft(numpy_mlx_shim.array(np.asarray(s).T), **kw), dtype=np.float32)
+    for tag, kw in (("whisper80", dict(sample_rate=16000, n_fft=400, n_mels=80, norm="slaney", mel_scale=None)),
+                    ("whisper128", dict(sample_rate=16000, n_fft=400, n_mels=128, norm="slaney", mel_scale=None)),
+                    ("qwen3", dict(sample_rate=24000, n_fft=1024, n_mels=128, f_min=0.0, f_max=12000.0, norm="slaney", mel_scale="slaney")),
+                    ("htk", dict(sample_rate=22050, n_fft=512, n_mels=40, norm=None, mel_scale="htk"))):
+        out[f"mel_{tag}"] = np.asarray(dsp.mel_filters(**kw), dtype=np.float32)
+    a = (0.1 * rng.standard_normal(16000)).astype(np.float32)
+    out["logmel_noise"] = np.asarray(audio.log_mel_spectrogram(a, n_mels=80, padding=0), dtype=np.float32)
+    out["logmel_noise_padded"] = np.asarray(audio.log_mel_spectrogram(a[:4000], n_mels=80, padding=8000), dtype=np.float32)
+    sine = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0).astype(np.float32)          # BASELINE config 1
+    out["logmel_sine440"] = np.asarray(audio.log_mel_spectrogram(sine, n_mels=80, padding=0), dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "dsp_golden.npz"), **out)
+    print({k: v.shape for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -233,3 +233,48 @@ def test_resampler_matches_reference_golden_vectors():
             got = resample_audio_chunks(iter(np.array_split(x, 3, axis=0)), osr, tsr, x.shape[0], chunk_duration_seconds=0.05)
             assert got.shape == g[name + "_chunks"].shape and float(np.abs(got - g[name + "_chunks"]).max()) <= 1e-7
             assert float(np.abs(g[name + "_chunks"] - want).max()) <= 1e-7        # the reference's own chunk-invariance
+
+
+def _dsp_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "dsp_golden.npz"))
+
+
+_STFT_CASES = {"whisper": dict(n_fft=400, hop_length=160, window="hann"), "kokoro": dict(n_fft=20, hop_length=5, window="hann"),
+               "const": dict(n_fft=256, hop_length=64, window="hamming", pad_mode="constant"), "nocenter": dict(n_fft=128, hop_length=32, center=False),
+               "shortwin": dict(n_fft=512, hop_length=128, win_length=400)}
+_MEL_CASES = {"whisper80": dict(sample_rate=16000, n_fft=400, n_mels=80, norm="slaney", mel_scale=None),
+              "whisper128": dict(sample_rate=16000, n_fft=400, n_mels=128, norm="slaney", mel_scale=None),
+              "qwen3": dict(sample_rate=24000, n_fft=1024, n_mels=128, f_min=0.0, f_max=12000.0, norm="slaney", mel_scale="slaney"),
+              "htk": dict(sample_rate=22050, n_fft=512, n_mels=40, norm=None, mel_scale="htk")}
+
+
+def test_oracle_dsp_matches_vectors_produced_by_the_reference_code():
+    """tests/golden/dsp_golden.npz = the reference's dsp.py / whisper audio.py RUN here with NumPy standing in for the MLX primitives
+    (tests/golden/make_dsp_golden.py, numpy_mlx_shim.py): windows, five STFT configurations, three iSTFT variants, four mel
+    filterbanks and three log-mel spectrograms (incl. BASELINE config 1's 440 Hz sine) pin the oracle's restatement."""
+    g = _dsp_golden()
+    for name in ("hanning", "hamming", "blackman", "bartlett"):
+        for size in (20, 400):
+            assert np.abs(getattr(O, name)(size) - g[f"win_{name}_{size}"]).max() < 1e-6
+            assert np.abs(getattr(O, name)(size, periodic=True) - g[f"win_{name}_{size}_periodic"]).max() < 1e-6
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(4000).astype(np.float32)
+    for tag, kw in _STFT_CASES.items():
+        s = O.stft(x, **kw)
+        want = g[f"stft_{tag}_re"] + 1j * g[f"stft_{tag}_im"]
+        assert s.shape == want.shape and np.abs(s - want).max() < 2e-4 * max(1.0, float(np.abs(want).max())), tag
+    s = O.stft(x, n_fft=256, hop_length=64)
+    for tag, kw in (("default", dict(hop_length=64, win_length=256)), ("len", dict(hop_length=64, win_length=256, length=3900)),
+                    ("norm", dict(hop_length=64, win_length=256, normalized=True))):
+        y, want = O.istft(s.T, **kw), g[f"istft_{tag}"]
+        ok = np.isfinite(want)                        # the reference divides 0/0 at uncovered edge samples (dsp.py:503-505)
+        assert y.shape == want.shape and np.abs(y[ok] - want[ok]).max() < 2e-5, tag
+    for tag, kw in _MEL_CASES.items():
+        assert np.abs(O.mel_filters(**kw) - g[f"mel_{tag}"]).max() < 2e-6, tag
+    a = (0.1 * rng.standard_normal(16000)).astype(np.float32)
+    assert np.abs(O.whisper_log_mel(a, 80, 0) - g["logmel_noise"]).max() < 2e-4
+    assert np.abs(O.whisper_log_mel(a[:4000], 80, 8000) - g["logmel_noise_padded"]).max() < 2e-4
+    sine = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0).astype(np.float32)
+    d = np.abs(O.whisper_log_mel(sine, 80, 0) - g["logmel_sine440"])
+    assert d.max() < 2e-3 and np.mean(d) < 1e-4          # clamped low-energy bins of a pure tone amplify float32 FFT noise

@@ -108,3 +108,38 @@ def test_whisper_decoder_and_greedy_decode_parity():
     assert tokens == ref_tokens
     assert torch.allclose(lp.cpu().double(), ref_lp, rtol=1e-3, atol=1e-3)
     assert torch.allclose(ns.cpu().double(), ref_ns, rtol=1e-2, atol=1e-30)
+
+
+def test_dsp_frontend_matches_vectors_produced_by_the_reference_code():
+    """The CUDA front end against tests/golden/dsp_golden.npz (the reference's dsp.py / audio.py run with NumPy standing in for MLX,
+    tests/golden/make_dsp_golden.py): STFT configurations, iSTFT variants, mel filterbanks, log-mel incl. BASELINE config 1."""
+    import os
+    import numpy as np
+    from mlx_audio import dsp
+    from mlx_audio.stt.models.whisper.audio import log_mel_spectrogram
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dsp_golden.npz"))
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(4000).astype(np.float32)
+    cases = {"whisper": dict(n_fft=400, hop_length=160, window="hann"), "kokoro": dict(n_fft=20, hop_length=5, window="hann"),
+             "const": dict(n_fft=256, hop_length=64, window="hamming", pad_mode="constant"), "nocenter": dict(n_fft=128, hop_length=32, center=False),
+             "shortwin": dict(n_fft=512, hop_length=128, win_length=400)}
+    for tag, kw in cases.items():
+        s = dsp.stft(x, **kw).cpu().numpy()
+        want = g[f"stft_{tag}_re"] + 1j * g[f"stft_{tag}_im"]
+        assert s.shape == want.shape and np.abs(s - want).max() < 2e-4 * max(1.0, float(np.abs(want).max())), tag
+    s = dsp.stft(x, n_fft=256, hop_length=64)
+    for tag, kw in (("default", dict(hop_length=64, win_length=256)), ("len", dict(hop_length=64, win_length=256, length=3900)),
+                    ("norm", dict(hop_length=64, win_length=256, normalized=True))):
+        y, want = dsp.istft(s.T, **kw).cpu().numpy(), g[f"istft_{tag}"]
+        ok = np.isfinite(want)
+        assert y.shape == want.shape and np.abs(y[ok] - want[ok]).max() < 5e-5, tag
+    for tag, kw in {"whisper80": dict(sample_rate=16000, n_fft=400, n_mels=80, norm="slaney", mel_scale=None),
+                    "qwen3": dict(sample_rate=24000, n_fft=1024, n_mels=128, f_min=0.0, f_max=12000.0, norm="slaney", mel_scale="slaney"),
+                    "htk": dict(sample_rate=22050, n_fft=512, n_mels=40, norm=None, mel_scale="htk")}.items():
+        assert np.abs(np.asarray(torch.as_tensor(dsp.mel_filters(**kw)).cpu()) - g[f"mel_{tag}"]).max() < 2e-6, tag
+    a = (0.1 * rng.standard_normal(16000)).astype(np.float32)
+    assert np.abs(log_mel_spectrogram(a, n_mels=80, padding=0).cpu().numpy() - g["logmel_noise"]).max() < 2e-4
+    assert np.abs(log_mel_spectrogram(a[:4000], n_mels=80, padding=8000).cpu().numpy() - g["logmel_noise_padded"]).max() < 2e-4
+    sine = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0).astype(np.float32)
+    d = np.abs(log_mel_spectrogram(sine, n_mels=80, padding=0).cpu().numpy() - g["logmel_sine440"])
+    assert d.max() < 2e-3 and np.mean(d) < 1e-4
