@@ -3,6 +3,7 @@ for the hot path.  Expected values are copied from the ci
 reference tests (data, not code)."""
 import math
 import numpy as np
+import torch
 import pytest
 
 from oracle import dsp as O
@@ -278,3 +279,32 @@ def test_oracle_dsp_matches_vectors_produced_by_the_reference_code():
     sine = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0).astype(np.float32)
     d = np.abs(O.whisper_log_mel(sine, 80, 0) - g["logmel_sine440"])
     assert d.max() < 2e-3 and np.mean(d) < 1e-4          # clamped low-energy bins of a pure tone amplify float32 FFT noise
+
+
+def _golden(name):
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import synth_params
+    g = np.load(os.path.join(here, name), allow_pickle=False)
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["params"]).items()} if "params" in g.files else None
+    return g, P
+
+
+def test_oracle_whisper_matches_the_reference_model_code():
+    """tests/golden/whisper_golden.npz = the reference's AudioEncoder / TextDecoder classes (whisper.py:338-498) EXECUTED in float64 with
+    NumPy standing in for MLX (tests/golden/make_whisper_golden.py): encoder output, prefill logits, three kv-cache steps."""
+    from oracle import whisper as OW
+    g, P = _golden("whisper_golden.npz")
+    dims = dict(n_mels=80, n_audio_ctx=60, n_audio_state=64, n_audio_head=4, n_audio_layer=2, n_vocab=300, n_text_ctx=32, n_text_state=64,
+                n_text_head=4, n_text_layer=2)
+    assert np.abs(OW.sinusoids(60, 64).numpy() - g["sinusoids"]).max() < 1e-12
+    xa = OW.encoder(P, torch.as_tensor(g["mel"]), dims)
+    assert np.abs(xa.numpy() - g["xa"]).max() < 1e-11
+    lg, cache = OW.decoder_forward(P, torch.as_tensor(g["tokens"]), xa, None, dims)
+    assert np.abs(lg.numpy() - g["logits"]).max() < 1e-11
+    for i in range(g["step_tokens"].shape[1]):
+        lg, cache = OW.decoder_forward(P, torch.as_tensor(g["step_tokens"][:, i:i + 1]), xa, cache, dims)
+        assert np.abs(lg.numpy()[:, 0] - g["step_logits"][:, i]).max() < 1e-11
