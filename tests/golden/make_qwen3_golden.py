@@ -1,0 +1,205 @@
+"""Golden vectors from the REFERENCE'S OWN Qwen3-TTS code (tts/models/qwen3_tts/{talker,speech_tokenizer,qwen3_tts}.py,
+lm/models/cache.py, lm/sample_utils.py) executed in float64 with NumPy standing in for MLX (numpy_mlx_nn.py), at a reduced
+configuration.  Run from the repo root in the build container:  python tests/golden/make_qwen3_golden.py
+->  tests/golden/qwen3_golden.npz
+
+``mx.random.categorical`` is not reproducible outside MLX, so here (as in oracle/qwen3.py and the CUDA sampler) the categorical
+draw is the inverse CDF in index order driven by an injected uniform; everything around the draw is the reference's code."""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import numpy_mlx_nn as shim          # noqa: E402
+import synth_params                  # noqa: E402
+
+REF = "/root/reference/mlx_audio"
+mx, nn = shim.install(precise=True)
+for name, path in (("mlx_audio", REF), ("mlx_audio.lm", f"{REF}/lm"), ("mlx_audio.lm.models", f"{REF}/lm/models"), ("mlx_audio.tts", f"{REF}/tts"),
+                   ("mlx_audio.tts.models", f"{REF}/tts/models"), ("mlx_audio.tts.models.qwen3_tts", f"{REF}/tts/models/qwen3_tts"),
+                   ("mlx_audio.codec", f"{REF}/codec"), ("mlx_audio.codec.models", f"{REF}/codec/models"),
+                   ("mlx_audio.codec.models.mimi", f"{REF}/codec/models/mimi")):
+    shim.stub_package(name, path)
+for stub, names in (("huggingface_hub", ("snapshot_download", "hf_hub_download")),):
+    m = types.ModuleType(stub)
+    for n in names:
+        setattr(m, n, None)
+    sys.modules[stub] = m
+u = types.ModuleType("mlx_audio.utils")
+u.load_audio = None
+import mlx_audio.dsp as _dsp          # noqa: E402
+u.hanning, u.mel_filters, u.stft = _dsp.hanning, _dsp.mel_filters, _dsp.stft
+sys.modules["mlx_audio.utils"] = u
+
+from mlx_audio.tts.models.qwen3_tts import config as C            # noqa: E402
+from mlx_audio.tts.models.qwen3_tts import talker as T            # noqa: E402
+
+CP = dict(vocab_size=80, hidden_size=48, intermediate_size=96, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2, head_dim=16,
+          num_code_groups=4)
+TALKER = dict(vocab_size=1104, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=2,
+              head_dim=16, rope_scaling={"interleaved": True, "mrope_section": [2, 3, 3], "rope_type": "default"}, num_code_groups=4,
+              text_hidden_size=40, text_vocab_size=120, codec_eos_token_id=1000, codec_pad_id=1001, codec_bos_id=1002, codec_think_id=1003,
+              codec_nothink_id=1004, codec_think_bos_id=1005, codec_think_eos_id=1006, codec_language_id={"english": 1010, "german": 1011},
+              spk_id={"amy": 1020, "bob": 1021}, code_predictor_config=CP)
+ORACLE_CFG = {"vocab_size": 1104, "hidden_size": 64, "intermediate_size": 128, "num_hidden_layers": 2, "num_attention_heads": 4,
+              "num_key_value_heads": 2, "head_dim": 16, "rms_norm_eps": 1e-6, "rope_theta": 1000000.0, "mrope_section": [2, 3, 3],
+              "num_code_groups": 4, "codec_eos_token_id": 1000, "text_hidden_size": 40, "cp_vocab_size": 80, "cp_hidden_size": 48,
+              "cp_intermediate_size": 96, "cp_num_hidden_layers": 2, "cp_num_attention_heads": 4, "cp_num_key_value_heads": 2, "cp_head_dim": 16,
+              "cp_rope_theta": 1000000.0}
+
+
+def fill(module, prefix="", rule=lambda name: None):
+    names = [(prefix + n, v.shape, rule(n)) for n, v in shim.flat_parameters(module)]
+    for n, sh, r in names:
+        shim.set_parameter(module, n[len(prefix):], synth_params.value(n, sh, r))
+    return names
+
+
+def talker_cases(out):
+    talker = T.Qwen3TTSTalkerForConditionalGeneration(C.Qwen3TTSTalkerConfig(**TALKER))
+    names = fill(talker)
+    out["talker_params"] = synth_params.manifest(names)
+    rng = np.random.default_rng(31)
+    x = rng.standard_normal((2, 6, 64))
+    cache = talker.make_cache()
+    logits, hidden = talker(mx.array(x), cache=cache)
+    out["t_x"], out["t_logits"], out["t_hidden"] = x, np.asarray(logits), np.asarray(hidden)
+    xs = rng.standard_normal((2, 3, 64))
+    sl = []
+    for i in range(3):
+        lg, hd = talker(mx.array(xs[:, i:i + 1]), cache=cache)
+        sl.append(np.asarray(lg)[:, 0])
+    out["t_step_x"], out["t_step_logits"] = xs, np.stack(sl, 1)
+    # code predictor: 2-token prefill (hidden, code-0 embedding) then single-token steps, one lm_head per generation step
+    cc = talker.code_predictor.make_cache()
+    cx = rng.standard_normal((1, 2, 64))
+    cl, cc, _ = talker.code_predictor(mx.array(cx), cache=cc, generation_step=0)
+    cs = [np.asarray(cl)[:, -1]]
+    cx2 = rng.standard_normal((1, 2, 64))
+    for i in range(2):
+        cl, cc, _ = talker.code_predictor(mx.array(cx2[:, i:i + 1]), cache=cc, generation_step=i + 1)
+        cs.append(np.asarray(cl)[:, -1])
+    out["cp_x"], out["cp_x2"], out["cp_logits"] = cx, cx2, np.stack(cs, 1)
+    return talker
+
+
+TOKDEC = dict(latent_dim=32, codebook_dim=16, codebook_size=80, decoder_dim=48, hidden_size=32, intermediate_size=64, head_dim=8,
+              num_attention_heads=4, num_hidden_layers=2, num_key_value_heads=4, num_quantizers=4, num_semantic_quantizers=1, sliding_window=6,
+              upsample_rates=[8, 5, 4, 3], upsampling_ratios=[2, 2])
+ORACLE_TOK = {"latent_dim": 32, "codebook_dim": 16, "codebook_size": 80, "decoder_dim": 48, "hidden_size": 32, "intermediate_size": 64,
+              "layer_scale_initial_scale": 0.01, "head_dim": 8, "num_attention_heads": 4, "num_hidden_layers": 2, "num_key_value_heads": 4,
+              "num_quantizers": 4, "num_semantic_quantizers": 1, "rms_norm_eps": 1e-5, "rope_theta": 10000.0, "upsample_rates": [8, 5, 4, 3],
+              "upsampling_ratios": [2, 2], "sliding_window": 6}
+
+
+class CharTokenizer:
+    """Stands in for the HF tokenizer: the three chat-template markers are single ids, every other character is one id."""
+    MARK = {"<|im_start|>": 1, "<|im_end|>": 2, "assistant": 3, "user": 4, "\n": 5}
+
+    def __init__(self):
+        self.calls = []
+
+    def encode(self, text):
+        ids, i = [], 0
+        while i < len(text):
+            for m, v in self.MARK.items():
+                if text.startswith(m, i):
+                    ids.append(v)
+                    i += len(m)
+                    break
+            else:
+                ids.append(10 + (ord(text[i]) % 100))
+                i += 1
+        self.calls.append(ids)
+        return ids
+
+
+def tokenizer_cases(out):
+    from mlx_audio.tts.models.qwen3_tts import speech_tokenizer as S
+    tok = S.Qwen3TTSSpeechTokenizer(C.Qwen3TTSTokenizerConfig(decoder_config=C.Qwen3TTSTokenizerDecoderConfig(**TOKDEC)))
+    names = fill(tok, rule=lambda n: "small" if n.endswith((".alpha", ".beta")) else ("scale0.08" if n == "decoder.decoder.6.conv.weight" else None))     # SnakeBeta gains are exp(alpha), exp(beta)
+    out["tok_params"] = synth_params.manifest(names)
+    out["tok_cfg"] = json.dumps(ORACLE_TOK)
+    rng = np.random.default_rng(33)
+    codes = rng.integers(0, 80, size=(2, 4, 9))                    # [B, n_q, T]
+    out["tok_codes"], out["tok_wav"] = codes, np.asarray(tok.decoder(mx.array(codes)))
+    print("clipped fraction", float((np.abs(out["tok_wav"]) >= 1).mean()))
+    out["tok_wav_chunked"] = np.asarray(tok.decoder.chunked_decode(mx.array(codes), chunk_size=4, left_context_size=2))
+    codes_bt = rng.integers(0, 80, size=(2, 7, 4))                 # [B, T, n_q], public decode
+    codes_bt[1, 5:, :] = 0                                         # trailing zero codes shorten the reported length
+    wav, lens = tok.decode(mx.array(codes_bt))
+    out["tok_codes_bt"], out["tok_decode_wav"], out["tok_decode_lens"] = codes_bt, np.asarray(wav), np.asarray(lens)
+    # streaming decoder: two calls of new codes with conv buffers and the transformer kv cache
+    tok.decoder.reset_streaming_state()
+    parts = [np.asarray(tok.decoder.streaming_step(mx.array(codes[:1, :, :5]))), np.asarray(tok.decoder.streaming_step(mx.array(codes[:1, :, 5:])))]
+    tok.decoder.reset_streaming_state()
+    out["tok_stream_wav"] = np.concatenate(parts, axis=-1)
+    return tok
+
+
+def model_cases(out, tok):
+    from mlx_audio.tts.models.qwen3_tts import qwen3_tts as Q
+    cfg = C.ModelConfig(talker_config=dict(TALKER), tts_model_type="custom_voice", tts_pad_token_id=111, tts_bos_token_id=112, tts_eos_token_id=113)
+    model = Q.Model(cfg)
+    names = fill(model.talker)
+    assert synth_params.manifest(names) == out["talker_params"]
+    eos = TALKER["codec_eos_token_id"]
+    gain = float(os.environ.get('EOS_GAIN', '2.0'))
+    w = np.array(model.talker.codec_head.weight)
+    w[eos] *= gain                                                  # makes EOS reachable within a few frames
+    model.talker.codec_head.weight = mx.array(w)
+    model.load_speech_tokenizer(tok)
+    model.tokenizer = CharTokenizer()
+    captured = {}
+    real_decode = tok.decode
+
+    def spy(codes):
+        captured["codes"] = np.asarray(codes)
+        return real_decode(codes)
+    tok.decode = spy
+    out["gen_eos_gain"] = gain
+    cases = [dict(tag="a", text="Hello there, world.", voice="Amy", instruct="calm", lang_code="english", max_tokens=40, seed=int(os.environ.get("SEED_A", "45"))),
+             dict(tag="b", text="Short one", voice="bob", instruct=None, lang_code="auto", max_tokens=6, seed=42, top_p=0.8),
+             dict(tag="c", text="Greedy decoding path", voice="amy", instruct=None, lang_code="german", max_tokens=5, seed=43, temperature=0.0)]
+    for c in cases:
+        g = TALKER["num_code_groups"]
+        us = np.random.default_rng(c["seed"]).random((c["max_tokens"], g))
+        greedy = c.get("temperature", 0.9) <= 0
+        mx.random.queue[:] = [] if greedy else [("categorical", np.array([v])) for v in us.reshape(-1)]
+        model.tokenizer.calls.clear()
+        ie, tr, pad = model._prepare_generation_inputs(c["text"], language=c["lang_code"], speaker=c["voice"], instruct=c["instruct"])
+        text_ids = model.tokenizer.calls[0]
+        instruct_ids = model.tokenizer.calls[1] if c["instruct"] else None
+        captured.clear()
+        res = list(model.generate(text=c["text"], voice=c["voice"], instruct=c["instruct"], lang_code=c["lang_code"], max_tokens=c["max_tokens"],
+                                  temperature=c.get("temperature", 0.9), top_p=c.get("top_p", 1.0)))
+        t = c["tag"]
+        out[f"gen_{t}_meta"] = json.dumps({k: v for k, v in c.items() if k != "seed"} | {"text_ids": text_ids, "instruct_ids": instruct_ids,
+                                                                                         "draws_left": len(mx.random.queue)})
+        out[f"gen_{t}_u"] = us
+        out[f"gen_{t}_input_embeds"], out[f"gen_{t}_trailing"], out[f"gen_{t}_pad"] = np.asarray(ie), np.asarray(tr), np.asarray(pad)
+        out[f"gen_{t}_codes"] = captured["codes"][0]
+        out[f"gen_{t}_audio"] = np.asarray(res[0].audio)
+        print(t, "frames", captured["codes"].shape, "audio", res[0].audio.shape, "draws left", len(mx.random.queue))
+    mx.random.queue[:] = []
+
+
+def main():
+    out = {"cfg": json.dumps(ORACLE_CFG)}
+    talker_cases(out)
+    tok = tokenizer_cases(out)
+    model_cases(out, tok)
+    out.pop("tok_stream_wav", None)
+    for k in list(out):                                              # waveforms are stored as float32 (|x| <= 1: 6e-8 absolute)
+        if k.endswith(("_wav", "_audio", "_wav_chunked")):
+            out[k] = np.asarray(out[k], dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "qwen3_golden.npz"), **out)
+    print({k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

@@ -249,6 +249,14 @@ def build(precise=True):
         return [_w(p) for p in np.split(np.asarray(x), indices_or_sections, axis=axis)]
     core.split = split
 
+    def put_along_axis(a, indices, values, axis=None, **_k):
+        out = np.array(np.asarray(a), copy=True)
+        idx = np.asarray(indices).astype(np.int64)
+        np.put_along_axis(out, idx, np.broadcast_to(np.asarray(values, dtype=out.dtype), idx.shape) if np.ndim(values) else np.asarray(values, dtype=out.dtype), axis)
+        return out.view(array)
+    core.put_along_axis = put_along_axis
+    core.argpartition = lambda a, kth, axis=-1, **_k: np.argpartition(np.asarray(a), kth, axis=axis).astype(np.int32).view(array)
+
     def erf(x):
         from scipy.special import erf as _erf
         return _erf(np.asarray(x)).view(array)
@@ -281,6 +289,21 @@ def build(precise=True):
         return np.asarray(a, dtype=_FLOAT).view(array)
     rnd.normal = lambda shape=(), dtype=None, loc=0.0, scale=1.0, key=None, **_k: _draw("normal", shape) * scale + loc
     rnd.uniform = lambda low=0.0, high=1.0, shape=(), dtype=None, key=None, **_k: _draw("uniform", shape) * (high - low) + low
+    def categorical(logits, axis=-1, shape=None, num_samples=None, key=None, **_k):
+        """Inverse CDF in index order driven by an injected uniform per row (the convention oracle/qwen3.py and the CUDA sampler use)."""
+        lg = np.asarray(logits, dtype=np.float64)
+        assert axis in (-1, lg.ndim - 1) and shape is None and num_samples is None
+        us = np.asarray(_draw("categorical", lg.shape[:-1]), dtype=np.float64).reshape(-1)
+        rows = lg.reshape(-1, lg.shape[-1])
+        out = np.zeros(rows.shape[0], dtype=np.int32)
+        for r in range(rows.shape[0]):
+            w = np.exp(rows[r] - rows[r].max())
+            cum = np.cumsum(w)
+            live = np.nonzero(w > 0)[0]
+            hit = live[cum[live] > us[r] * cum[-1]]
+            out[r] = hit[0] if hit.size else live[-1]
+        return out.reshape(lg.shape[:-1]).view(array)
+    rnd.categorical = categorical
     rnd.seed = lambda *_a, **_k: None
     rnd.key = lambda *_a, **_k: None
     core.random = rnd
@@ -610,6 +633,7 @@ def _build_nn(mx):
     nn.tanh = lambda x: _w(np.tanh(np.asarray(x)))
     nn.sigmoid = mx.sigmoid
     nn.softmax = softmax
+    nn.log_softmax = lambda x, axis=-1: _w(np.asarray(x) - np.max(np.asarray(x), axis=axis, keepdims=True) - np.log(np.sum(np.exp(np.asarray(x) - np.max(np.asarray(x), axis=axis, keepdims=True)), axis=axis, keepdims=True)))
 
     def _act_module(name, fn):
         def __call__(self, x):

@@ -308,3 +308,51 @@ def test_oracle_whisper_matches_the_reference_model_code():
     for i in range(g["step_tokens"].shape[1]):
         lg, cache = OW.decoder_forward(P, torch.as_tensor(g["step_tokens"][:, i:i + 1]), xa, cache, dims)
         assert np.abs(lg.numpy()[:, 0] - g["step_logits"][:, i]).max() < 1e-11
+
+
+def test_oracle_qwen3_matches_the_reference_model_code():
+    """tests/golden/qwen3_golden.npz = the reference's own Qwen3-TTS code (talker.py, speech_tokenizer.py, qwen3_tts.py Model.generate ->
+    generate_custom_voice -> _generate_with_instruct, lm/sample_utils.py, lm/models/cache.py) EXECUTED in float64 at a reduced configuration
+    with NumPy standing in for MLX (tests/golden/make_qwen3_golden.py).  Pins: talker prefill + cached steps (interleaved MRoPE, GQA),
+    code predictor with its per-step heads and small_to_mtp projection, the 12.5 Hz decoder (one-shot, chunked, public decode with lengths),
+    prompt assembly (speaker / language / instruct), and three whole generations -- EOS-terminated sampling with repetition penalty, top-p,
+    and greedy -- whose code matrices must be IDENTICAL and whose waveforms agree to float32 storage precision."""
+    import json
+    from oracle import qwen3 as Q
+    g, _ = _golden("qwen3_golden.npz")
+    import synth_params
+    cfg, tcfg = json.loads(str(g["cfg"])), json.loads(str(g["tok_cfg"]))
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["talker_params"]).items()}
+    PT = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["tok_params"]).items()}
+    cache = Q.make_cache(cfg["num_hidden_layers"])
+    lg, h = Q.talker_forward(P, torch.as_tensor(g["t_x"]), cache, cfg=cfg)
+    assert np.abs(lg.numpy() - g["t_logits"]).max() < 1e-11 and np.abs(h.numpy() - g["t_hidden"]).max() < 1e-11
+    for i in range(g["t_step_x"].shape[1]):
+        lg, _ = Q.talker_forward(P, torch.as_tensor(g["t_step_x"][:, i:i + 1]), cache, cfg=cfg)
+        assert np.abs(lg.numpy()[:, 0] - g["t_step_logits"][:, i]).max() < 1e-11
+    cc = Q.make_cache(cfg["cp_num_hidden_layers"])
+    cl = Q.code_predictor_forward(P, torch.as_tensor(g["cp_x"]), cc, 0, cfg)
+    assert np.abs(cl.numpy()[:, -1] - g["cp_logits"][:, 0]).max() < 1e-11
+    for i in range(2):
+        cl = Q.code_predictor_forward(P, torch.as_tensor(g["cp_x2"][:, i:i + 1]), cc, i + 1, cfg)
+        assert np.abs(cl.numpy()[:, -1] - g["cp_logits"][:, i + 1]).max() < 1e-11
+    wtol = 2e-7                                                         # waveforms are stored as float32 in the fixture
+    assert np.abs(Q.tokenizer_decode(PT, torch.as_tensor(g["tok_codes"]), tcfg).numpy() - g["tok_wav"]).max() < wtol
+    assert np.abs(Q.chunked_decode(PT, torch.as_tensor(g["tok_codes"]), 4, 2, tcfg).numpy() - g["tok_wav_chunked"]).max() < wtol
+    w, ln = Q.speech_tokenizer_decode(PT, torch.as_tensor(g["tok_codes_bt"]), tcfg)
+    assert np.abs(w.numpy() - g["tok_decode_wav"]).max() < wtol and ln.tolist() == g["tok_decode_lens"].tolist()
+    P["codec_head.weight"] = P["codec_head.weight"].clone()
+    P["codec_head.weight"][cfg["codec_eos_token_id"]] *= float(g["gen_eos_gain"])
+    ids = dict(codec_nothink_id=1004, codec_think_id=1003, codec_think_bos_id=1005, codec_think_eos_id=1006, codec_pad_id=1001, codec_bos_id=1002)
+    lang, spk = {"english": 1010, "german": 1011}, {"amy": 1020, "bob": 1021}
+    for t in "abc":
+        m = json.loads(str(g[f"gen_{t}_meta"]))
+        ie, tr, pad = Q.prepare_generation_inputs_from_ids(P, m["text_ids"], (112, 113, 111), ids, lang.get(m["lang_code"]), spk[m["voice"].lower()],
+                                                           m["instruct_ids"])
+        assert np.abs(ie.numpy() - g[f"gen_{t}_input_embeds"]).max() < 1e-12 and np.abs(tr.numpy() - g[f"gen_{t}_trailing"]).max() < 1e-12
+        codes = Q.generate_codes(P, ie, tr, pad, torch.as_tensor(g[f"gen_{t}_u"]), m["max_tokens"], temperature=m.get("temperature", 0.9),
+                                 top_p=m.get("top_p", 1.0), cfg=cfg)
+        assert np.array_equal(codes.numpy(), g[f"gen_{t}_codes"]), t
+        wav, ln = Q.speech_tokenizer_decode(PT, codes[None], tcfg)
+        assert int(ln[0]) == g[f"gen_{t}_audio"].shape[0] and np.abs(wav[0, :int(ln[0])].numpy() - g[f"gen_{t}_audio"]).max() < wtol
+    assert json.loads(str(g["gen_a_meta"]))["draws_left"] > 0           # case a stopped on EOS, not on max_tokens
