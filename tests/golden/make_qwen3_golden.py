@@ -186,6 +186,35 @@ def model_cases(out, tok):
         out[f"gen_{t}_audio"] = np.asarray(res[0].audio)
         print(t, "frames", captured["codes"].shape, "audio", res[0].audio.shape, "draws left", len(mx.random.queue))
     mx.random.queue[:] = []
+    # ---- batch path: Model.batch_generate's own loop (qwen3_tts.py:1800-1935; reached without ICL through stream=True, with a
+    # streaming interval long enough that every sequence is decoded once, at the end) ----
+    texts, voices, instructs = ["First line.", "The second one is longer", "Hi"], ["amy", "bob", "amy"], ["calm and slow", None, "sad"]
+    max_tokens = int(os.environ.get("BATCH_MAX", "12"))
+    g = TALKER["num_code_groups"]
+    ub = np.random.default_rng(int(os.environ.get("SEED_B", "51"))).random((max_tokens, g, len(texts)))
+    mx.random.queue[:] = [("categorical", ub[s, k]) for s in range(max_tokens) for k in range(g)]
+    model.tokenizer.calls.clear()
+    seen = []
+    real_chunked = tok.decoder.chunked_decode
+
+    def spy_chunked(codes, *a, **k):
+        seen.append(np.asarray(codes))
+        return real_chunked(codes, *a, **k)
+    tok.decoder.chunked_decode = spy_chunked
+    res = list(model.batch_generate(texts, voices=voices, instructs=instructs, lang_code="english", max_tokens=max_tokens, stream=True,
+                                    streaming_interval=1e6))
+    del tok.decoder.__dict__["chunked_decode"]
+    calls = list(model.tokenizer.calls)
+    out["batch_meta"] = json.dumps({"texts": texts, "voices": voices, "instructs": instructs, "lang_code": "english", "max_tokens": max_tokens,
+                                    "tokenizer_calls": calls, "draws_left": len(mx.random.queue), "order": [int(r.sequence_idx) for r in res]})
+    out["batch_u"] = ub
+    for r, c in zip(res, seen):
+        b = int(r.sequence_idx)
+        out[f"batch_codes_{b}"] = c[0].T                              # [frames, groups]
+        out[f"batch_audio_{b}"] = np.asarray(r.audio)
+        print("batch row", b, "frames", c.shape[-1], "audio", r.audio.shape)
+    print("batch draws left", len(mx.random.queue), "tokenizer calls", [len(c) for c in calls])
+    mx.random.queue[:] = []
 
 
 def main():
@@ -195,7 +224,7 @@ def main():
     model_cases(out, tok)
     out.pop("tok_stream_wav", None)
     for k in list(out):                                              # waveforms are stored as float32 (|x| <= 1: 6e-8 absolute)
-        if k.endswith(("_wav", "_audio", "_wav_chunked")):
+        if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith("batch_audio_"):
             out[k] = np.asarray(out[k], dtype=np.float32)
     np.savez_compressed(os.path.join(HERE, "qwen3_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})

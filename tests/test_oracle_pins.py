@@ -315,8 +315,8 @@ def test_oracle_qwen3_matches_the_reference_model_code():
     generate_custom_voice -> _generate_with_instruct, lm/sample_utils.py, lm/models/cache.py) EXECUTED in float64 at a reduced configuration
     with NumPy standing in for MLX (tests/golden/make_qwen3_golden.py).  Pins: talker prefill + cached steps (interleaved MRoPE, GQA),
     code predictor with its per-step heads and small_to_mtp projection, the 12.5 Hz decoder (one-shot, chunked, public decode with lengths),
-    prompt assembly (speaker / language / instruct), and three whole generations -- EOS-terminated sampling with repetition penalty, top-p,
-    and greedy -- whose code matrices must be IDENTICAL and whose waveforms agree to float32 storage precision."""
+    prompt assembly (speaker / language / instruct), three whole generations -- EOS-terminated sampling with repetition penalty, top-p,
+    and greedy -- and one left-padded batch of three through Model.batch_generate, whose code matrices must be IDENTICAL and whose waveforms agree to float32 storage precision."""
     import json
     from oracle import qwen3 as Q
     g, _ = _golden("qwen3_golden.npz")
@@ -356,3 +356,17 @@ def test_oracle_qwen3_matches_the_reference_model_code():
         wav, ln = Q.speech_tokenizer_decode(PT, codes[None], tcfg)
         assert int(ln[0]) == g[f"gen_{t}_audio"].shape[0] and np.abs(wav[0, :int(ln[0])].numpy() - g[f"gen_{t}_audio"]).max() < wtol
     assert json.loads(str(g["gen_a_meta"]))["draws_left"] > 0           # case a stopped on EOS, not on max_tokens
+    # Model.batch_generate's own loop (qwen3_tts.py:1800-1935): three prompts of different length (left padding 0 / 18 / 10), one row
+    # reaching EOS six frames before the others stop -> identical code matrices per row
+    m = json.loads(str(g["batch_meta"]))
+    calls, rows = list(m["tokenizer_calls"]), []
+    for v, i in zip(m["voices"], m["instructs"]):
+        tid = calls.pop(0)
+        rows.append(Q.prepare_generation_inputs_from_ids(P, tid, (112, 113, 111), ids, lang[m["lang_code"]], spk[v], calls.pop(0) if i else None))
+    assert len({r[0].shape[1] for r in rows}) == 3
+    got = Q.generate_codes_batch(P, [r[0] for r in rows], [r[1] for r in rows], rows[0][2], torch.as_tensor(g["batch_u"]), m["max_tokens"], cfg=cfg)
+    assert len({int(o.shape[0]) for o in got}) > 1
+    for b, o in enumerate(got):
+        assert np.array_equal(o.numpy(), g[f"batch_codes_{b}"]), b
+        wav, _ = Q.speech_tokenizer_decode(PT, o[None], tcfg)
+        assert np.abs(wav[0].numpy() - g[f"batch_audio_{b}"]).max() < wtol
