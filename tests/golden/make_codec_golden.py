@@ -1,0 +1,112 @@
+"""Golden vectors from the REFERENCE'S OWN codec code (codec/models/snac/*.py, codec/models/mimi/**) executed in float64 with
+NumPy standing in for MLX (numpy_mlx_nn.py), at reduced configurations.  Run from the repo root in the build container:
+python tests/golden/make_codec_golden.py  ->  tests/golden/codec_golden.npz"""
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import numpy_mlx_nn as shim          # noqa: E402
+import synth_params                  # noqa: E402
+
+REF = "/root/reference/mlx_audio"
+mx, nn = shim.install(precise=True)
+for name, path in (("mlx_audio", REF), ("mlx_audio.lm", f"{REF}/lm"), ("mlx_audio.lm.models", f"{REF}/lm/models"), ("mlx_audio.codec", f"{REF}/codec"),
+                   ("mlx_audio.codec.models", f"{REF}/codec/models"), ("mlx_audio.codec.models.snac", f"{REF}/codec/models/snac"),
+                   ("mlx_audio.codec.models.mimi", f"{REF}/codec/models/mimi")):
+    shim.stub_package(name, path)
+hub = types.ModuleType("huggingface_hub")
+hub.snapshot_download = hub.hf_hub_download = None
+sys.modules["huggingface_hub"] = hub
+
+SNAC_CFG = dict(sampling_rate=24000, encoder_dim=8, encoder_rates=[2, 2, 2, 2], latent_dim=None, decoder_dim=64, decoder_rates=[8, 3, 4, 2],
+                attn_window_size=None, codebook_size=64, codebook_dim=4, vq_strides=[4, 2, 1], noise=True, depthwise=True)
+
+
+def fill(module, prefix="", rule=lambda name: None):
+    names = [(prefix + n, v.shape, rule(n)) for n, v in shim.flat_parameters(module)]
+    for n, sh, r in names:
+        shim.set_parameter(module, n[len(prefix):], synth_params.value(n, sh, r))
+    for m in module.modules():                                       # derived buffers (Mimi codebooks: embedding_sum / usage), as the
+        if hasattr(m, "update_in_place"):                            # reference's own weight loader does after assigning parameters
+            m.update_in_place()
+    return names
+
+
+def snac_cases(out):
+    from mlx_audio.codec.models.snac import snac as S
+    model = S.SNAC(**SNAC_CFG)
+    import re
+    last = max(int(m.group(1)) for n, _ in shim.flat_parameters(model) if (m := re.match(r"decoder\.model\.layers\.(\d+)\.weight_g$", n)))
+    names = fill(model, rule=lambda n: "scale0.03" if n == f"decoder.model.layers.{last}.weight_g" else None)   # keeps tanh mostly unsaturated
+    names = [e for e in names if not e[0].startswith("encoder.")]
+    out["snac_params"], out["snac_cfg"] = synth_params.manifest(names), json.dumps(SNAC_CFG)
+    rng = np.random.default_rng(61)
+    t = 5
+    codes = [rng.integers(0, 64, size=(2, t * 4 // s)) for s in SNAC_CFG["vq_strides"]]
+    chans = [SNAC_CFG["decoder_dim"] // 2 ** (i + 1) for i in range(4)]
+    noises = [rng.standard_normal((2, 1, c)) for c in chans]
+    mx.random.strict = True
+    mx.random.queue[:] = [("normal", n) for n in noises]
+    audio = model.decode([mx.array(c) for c in codes])
+    assert not mx.random.queue
+    mx.random.strict = False
+    for i, c in enumerate(codes):
+        out[f"snac_codes_{i}"] = c
+    for i, n in enumerate(noises):
+        out[f"snac_noise_{i}"] = n
+    out["snac_audio"] = np.asarray(audio)
+    print("snac audio", audio.shape, "saturated", float((np.abs(np.asarray(audio)) > 0.999).mean()))
+
+
+MIMI_ORACLE = {"dimension": 32, "nfilters": 4, "ratios": [8, 6, 5, 4], "ksize": 7, "residual_ksize": 3, "last_ksize": 3, "compress": 2, "d_model": 32,
+               "num_heads": 4, "num_layers": 2, "dim_feedforward": 64, "context": 6, "max_period": 10000, "layer_scale": 0.01, "nq": 4, "bins": 64,
+               "qdim": 16, "upsample_stride": 2}
+
+
+def mimi_cases(out):
+    from mlx_audio.codec.models.mimi import mimi as M
+    from mlx_audio.codec.models.mimi.modules import SeanetConfig, TransformerConfig
+    c = MIMI_ORACLE
+    seanet = SeanetConfig(dimension=c["dimension"], channels=1, causal=True, nfilters=c["nfilters"], nresidual_layers=1, ratios=c["ratios"],
+                          ksize=c["ksize"], residual_ksize=c["residual_ksize"], last_ksize=c["last_ksize"], dilation_base=2, pad_mode="constant",
+                          true_skip=True, compress=c["compress"])
+    tr = TransformerConfig(d_model=c["d_model"], num_heads=c["num_heads"], num_layers=c["num_layers"], causal=True, norm_first=True, bias_ff=False,
+                           bias_attn=False, layer_scale=c["layer_scale"], positional_embedding="rope", use_conv_bias=True, gating=False,
+                           norm="layer_norm", context=c["context"], max_period=c["max_period"], max_seq_len=8192, kv_repeat=1,
+                           dim_feedforward=c["dim_feedforward"], conv_layout=True, use_conv_block=False, cross_attention=False, conv_kernel_size=3)
+    cfg = M.MimiConfig(channels=1, sample_rate=24000, frame_rate=12.5, renormalize=True, seanet=seanet, transformer=tr, quantizer_nq=c["nq"],
+                       quantizer_bins=c["bins"], quantizer_dim=c["qdim"])
+    model = M.Mimi(cfg)
+    names = fill(model)
+    names = [e for e in names if not e[0].startswith(("encoder.", "encoder_transformer.", "downsample."))]
+    out["mimi_params"], out["mimi_cfg"] = synth_params.manifest(names), json.dumps(c)
+    rng = np.random.default_rng(62)
+    codes = rng.integers(0, c["bins"], size=(2, c["nq"], 9))
+    pcm = model.decode(mx.array(codes))
+    out["mimi_codes"], out["mimi_pcm"] = codes, np.asarray(pcm)
+    print("mimi pcm", pcm.shape, float(np.abs(np.asarray(pcm)).max()))
+    # streaming: decode_step over two chunks continues the conv buffers and the rotating kv cache
+    model.reset_state()
+    parts = [np.asarray(model.decode_step(mx.array(codes[:, :, :4]))), np.asarray(model.decode_step(mx.array(codes[:, :, 4:])))]
+    out["mimi_pcm_steps"] = np.concatenate(parts, axis=-1)
+    print("mimi step vs full", float(np.abs(out["mimi_pcm_steps"] - out["mimi_pcm"]).max()))
+
+
+def main():
+    out = {}
+    snac_cases(out)
+    mimi_cases(out)
+    out.pop("mimi_pcm_steps")                                        # equal to the one-shot decode (checked above)
+    for k in ("snac_audio", "mimi_pcm"):                             # waveforms stored as float32 (|x| <= 1: 6e-8 absolute)
+        out[k] = np.asarray(out[k], dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "codec_golden.npz"), **out)
+    print({k: getattr(v, "shape", None) for k, v in out.items()})
+
+
+if __name__ == "__main__":
+    main()

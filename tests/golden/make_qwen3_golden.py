@@ -154,6 +154,7 @@ def model_cases(out, tok):
     model.talker.codec_head.weight = mx.array(w)
     model.load_speech_tokenizer(tok)
     model.tokenizer = CharTokenizer()
+    mx.random.strict = True
     captured = {}
     real_decode = tok.decode
 

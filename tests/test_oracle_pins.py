@@ -370,3 +370,25 @@ def test_oracle_qwen3_matches_the_reference_model_code():
         assert np.array_equal(o.numpy(), g[f"batch_codes_{b}"]), b
         wav, _ = Q.speech_tokenizer_decode(PT, o[None], tcfg)
         assert np.abs(wav[0].numpy() - g[f"batch_audio_{b}"]).max() < wtol
+
+
+def test_oracle_codecs_match_the_reference_model_code():
+    """tests/golden/codec_golden.npz = the reference's SNAC.decode (snac/{snac,layers,vq}.py) and Mimi.decode (mimi/mimi.py + modules/) EXECUTED
+    in float64 at reduced configurations with NumPy standing in for MLX (tests/golden/make_codec_golden.py).  SNAC: strides 8/3/4/2 (the
+    output_padding<-groups argument quirk gives 3867 samples for 5 coarse frames), per-channel noise injected.  Mimi: split RVQ with the
+    embedding_sum / cluster_usage codebooks, depthwise transposed-conv upsampling, rope transformer with a 6-step attention context over 18
+    steps, SEANet decoder.  Waveforms are stored as float32 in the fixture, hence 2e-7."""
+    import json
+    from oracle import codec as OC
+    g, _ = _golden("codec_golden.npz")
+    import synth_params
+    cfg = json.loads(str(g["snac_cfg"]))
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["snac_params"]).items()}
+    codes = [torch.as_tensor(g[f"snac_codes_{i}"]).long() for i in range(3)]
+    noises = [torch.as_tensor(g[f"snac_noise_{i}"]) for i in range(4)]
+    y = OC.snac_decode(P, codes, cfg, noises)
+    assert tuple(y.shape) == g["snac_audio"].shape == (2, 3867, 1) and np.abs(y.numpy() - g["snac_audio"]).max() < 2e-7
+    cfg = json.loads(str(g["mimi_cfg"]))
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["mimi_params"]).items()}
+    y = OC.mimi_decode(P, torch.as_tensor(g["mimi_codes"]).long(), cfg)
+    assert tuple(y.shape) == g["mimi_pcm"].shape == (2, 1, 9 * 1920) and np.abs(y.numpy() - g["mimi_pcm"]).max() < 2e-7
