@@ -20,6 +20,7 @@ from . import dsp as D
 from . import nn as N
 
 TAP = None   # set to a dict to capture intermediates (tests only)
+EFFECTIVE_WEIGHTS_BF16 = True   # weight_norm() result rounded to the checkpoint dtype; False = exact arithmetic
 
 
 def _tap(name, value):
@@ -50,6 +51,9 @@ def weight_norm(v, g):
     The reference evaluates this in the checkpoint dtype (bf16) every forward, so the
     effective weight is a bf16 tensor; we evaluate in float32 and round once to bf16
     (DESIGN.md "effective weights")."""
+    if not EFFECTIVE_WEIGHTS_BF16:                  # algorithm pin against the reference code run in float64 (tests/golden)
+        nrm = torch.sqrt((v * v).sum(dim=tuple(range(1, v.ndim)), keepdim=True))
+        return (v / (nrm + 1e-7)) * g
     v32, g32 = v.to(torch.float32), g.to(torch.float32)
     nrm = torch.sqrt((v32 * v32).sum(dim=tuple(range(1, v.ndim)), keepdim=True))
     w = (v32 / (nrm + 1e-7)) * g32

@@ -106,6 +106,18 @@ class array(np.ndarray):
         return array._AtProxy(self)
 
 
+def _red(name):
+    def f(self, axis=None, keepdims=False, **k):
+        if isinstance(axis, list):
+            axis = tuple(axis)
+        return _w(getattr(np.ndarray, name)(self, axis=axis, keepdims=keepdims, **k))
+    return f
+
+
+for _n in ("sum", "mean", "var", "std", "max", "min", "prod"):     # MLX accepts a list of axes
+    setattr(array, _n, _red(_n))
+
+
 def _dt(d):
     if d in (np.float16, np.float32, np.float64, "float16", "float32", "bfloat16") or getattr(d, "__name__", "") == "bfloat16":
         return _FLOAT
@@ -125,6 +137,10 @@ def _w(x):
 def _wrap(fn):
     def f(*a, **k):
         k.pop("stream", None)
+        if isinstance(k.get("axis"), list):
+            k["axis"] = tuple(k["axis"])
+        if isinstance(k.get("axes"), list):
+            k["axes"] = tuple(k["axes"])
         return _w(fn(*a, **k))
     return f
 
@@ -288,6 +304,8 @@ def build(precise=True):
                 raise RuntimeError(f"mx.random.{kind}{tuple(shape)} called with an empty injection queue")
             return np.zeros(shape, dtype=_FLOAT).view(array)         # parameter initialisers: every value is overwritten afterwards
         want, a = rnd.queue.pop(0)
+        if callable(a):
+            a = a(tuple(shape))
         assert want == kind and tuple(a.shape) == tuple(shape), (want, kind, a.shape, shape)
         return np.asarray(a, dtype=_FLOAT).view(array)
     rnd.normal = lambda shape=(), dtype=None, loc=0.0, scale=1.0, key=None, **_k: _draw("normal", shape) * scale + loc

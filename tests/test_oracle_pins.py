@@ -392,3 +392,35 @@ def test_oracle_codecs_match_the_reference_model_code():
     P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["mimi_params"]).items()}
     y = OC.mimi_decode(P, torch.as_tensor(g["mimi_codes"]).long(), cfg)
     assert tuple(y.shape) == g["mimi_pcm"].shape == (2, 1, 9 * 1920) and np.abs(y.numpy() - g["mimi_pcm"]).max() < 2e-7
+
+
+def test_oracle_kokoro_matches_the_reference_model_code():
+    """tests/golden/kokoro_golden.npz = the reference's Kokoro Model.__call__ (kokoro.py:111-177 over modules.py, istftnet.py, interpolate.py,
+    dsp.py) EXECUTED in float64 on the public 82M configuration with NumPy standing in for MLX (tests/golden/make_kokoro_golden.py): ALBERT,
+    duration encoder + LSTMs, duration rounding and alignment, F0/N predictor, text encoder, AdaIN decoder, harmonic source (voiced and
+    unvoiced frames), noise convs, upsampling generator, iSTFT head.  The generator also asserts that the reference module tree and
+    synth.kokoro_weights() name exactly the same 548 parameters.  The oracle runs with exact (unrounded) effective weights here, the one
+    deliberate difference from its default (bf16 checkpoint dtype); the waveform is stored as float32, hence 2e-7."""
+    import json
+    from mlx_audio_b200 import synth
+    from oracle import kokoro as OK
+    g, _ = _golden("kokoro_golden.npz")
+    m = json.loads(str(g["meta"]))
+    cfg = OK.KOKORO_CONFIG
+    P = {k: v.double() for k, v in synth.kokoro_weights(cfg, seed=0).items()}
+    P["predictor.F0_proj.weight"] = P["predictor.F0_proj.weight"] * m["f0_gain"]
+    rng = np.random.default_rng(71)
+    rand_ini = rng.random((1, 9))
+    assert np.array_equal(rand_ini, g["rand_ini"])
+    noise = rng.standard_normal(tuple(int(v) for v in g["noise_shape"])).astype(np.float32).astype(np.float64)
+    OK.EFFECTIVE_WEIGHTS_BF16, OK.TAP = False, {}
+    try:
+        audio, pd = OK.forward(P, torch.as_tensor(g["ids"])[None], torch.as_tensor(g["ref_s"]), cfg, speed=m["speed"], rand_ini=torch.as_tensor(rand_ini),
+                               noise=torch.as_tensor(noise))
+        voiced = float((OK.TAP["F0"] > 10).double().mean())
+    finally:
+        OK.EFFECTIVE_WEIGHTS_BF16, OK.TAP = True, None
+    assert 0.05 < voiced < 0.95                                          # both branches of the harmonic source are exercised
+    assert np.array_equal(pd.numpy(), g["pred_dur"])
+    a, w = audio.numpy().reshape(-1), g["audio"].reshape(-1)
+    assert a.shape == w.shape == (43200,) and np.abs(a - w).max() < 2e-7
