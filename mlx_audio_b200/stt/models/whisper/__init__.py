@@ -1,3 +1,3 @@
-from .whisper import Model, ModelConfig, ModelDimensions
+from .whisper import Model, ModelConfig, ModelDimensions, TokenizerSpec, get_suppress_tokens
 
-__all__ = ["Model", "ModelConfig", "ModelDimensions"]
+__all__ = ["Model", "ModelConfig", "ModelDimensions", "TokenizerSpec", "get_suppress_tokens"]

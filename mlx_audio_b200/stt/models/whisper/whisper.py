@@ -109,10 +109,33 @@ class TokenizerSpec:
     language: int = 50259
     task: int = 50359
     suppress: tuple = ()
+    transcribe: int = 50359
+    translate: int = 50358
+    sot_lm: int = 50360
+    sot_prev: int = 50361
+    non_speech_tokens: Optional[tuple] = None
 
     @property
     def sot_sequence(self):
         return (self.sot, self.language, self.task)
+
+
+def get_suppress_tokens(spec: "TokenizerSpec", suppress_tokens=None) -> tuple:
+    """decoding.py:79-112: the ids the SuppressTokens filter masks.  ``-1`` expands to the tokenizer's non-speech tokens; the
+    transcribe / translate / sot / sot_prev / sot_lm markers and no_speech are always added.  A falsy ``suppress_tokens`` means the
+    filter is not installed at all (decoding.py:489-495) and yields ()."""
+    suppress_tokens = spec.suppress if suppress_tokens is None else suppress_tokens
+    if not suppress_tokens:
+        return ()
+    result = list(suppress_tokens)
+    if -1 in result:
+        if spec.non_speech_tokens is None:
+            raise ValueError("suppress contains -1 but the spec carries no non_speech_tokens (they come from the tokenizer files)")
+        result = [t for t in result if t >= 0] + list(spec.non_speech_tokens)
+    result.extend([spec.transcribe, spec.translate, spec.sot, spec.sot_prev, spec.sot_lm])
+    if spec.no_speech is not None:
+        result.append(spec.no_speech)
+    return tuple(sorted(set(result)))
 
 
 @dataclass
@@ -226,14 +249,15 @@ class Model:
         B = audio_features.shape[0]
         sample_len = sample_len or dims.n_text_ctx // 2
         V = dims.n_vocab
-        init = list(spec.sot_sequence)
+        init = list(spec.sot_sequence) + ([spec.no_timestamps] if without_timestamps else [])   # decoding.py:463-465
         sb = len(init)
         tokens = torch.zeros(B, dims.n_text_ctx + 2, dtype=torch.int64, device=dev)
         tokens[:, :sb] = torch.tensor(init, device=dev)
         neg = float("-inf")
         sup = torch.zeros(V, device=dev)
-        if spec.suppress:
-            sup[list(spec.suppress)] = neg
+        suppress = get_suppress_tokens(spec)
+        if suppress:
+            sup[list(suppress)] = neg
         blank = torch.zeros(V, device=dev)
         blank[list(spec.blank_ids) + [spec.eot]] = neg
         sum_lp = torch.zeros(B, device=dev)
@@ -248,7 +272,7 @@ class Model:
             else:
                 logits = self.decoder(tokens[:, cur - 1:cur], cache)
             not_done.zero_()
-            nxt = ops.whisper_greedy_step(logits, tokens, cur, sb, suppress_mask=sup if spec.suppress else None, blank_mask=blank,
+            nxt = ops.whisper_greedy_step(logits, tokens, cur, sb, suppress_mask=sup if suppress else None, blank_mask=blank,
                                           eot=spec.eot, no_timestamps=spec.no_timestamps, timestamp_begin=spec.timestamp_begin,
                                           max_initial_ts=-1 if max_initial_timestamp_index is None else max_initial_timestamp_index,
                                           without_timestamps=without_timestamps, sum_logprobs=sum_lp, not_done=not_done)

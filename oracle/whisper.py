@@ -62,13 +62,28 @@ class TokenizerSpec:
     """The tokenizer constants the decode loop touches (decoding.py:349-442, whisper.py:46-175).  Defaults are the public
     ids of Whisper's multilingual vocabulary; no tokenizer files are needed for the numeric path."""
     def __init__(self, eot=50257, sot=50258, no_timestamps=50363, timestamp_begin=50364, no_speech=50362, blank_ids=(220,),
-                 language=50259, task=50359):
+                 language=50259, task=50359, transcribe=50359, translate=50358, sot_lm=50360, sot_prev=50361, non_speech_tokens=None):
         self.eot, self.sot, self.no_timestamps, self.timestamp_begin, self.no_speech = eot, sot, no_timestamps, timestamp_begin, no_speech
         self.blank_ids, self.language, self.task = tuple(blank_ids), language, task
+        self.transcribe, self.translate, self.sot_lm, self.sot_prev, self.non_speech_tokens = transcribe, translate, sot_lm, sot_prev, non_speech_tokens
 
     @property
     def sot_sequence(self):
         return (self.sot, self.language, self.task)
+
+
+def get_suppress_tokens(spec, suppress_tokens):
+    """decoding.py:79-112: the ids SuppressTokens masks.  -1 expands to the tokenizer's non-speech tokens; the five task / sot markers and
+    no_speech are ALWAYS added.  (A falsy option means no SuppressTokens filter at all, decoding.py:489-495 -- the caller's check.)"""
+    result = list(suppress_tokens) if suppress_tokens else []
+    if -1 in result:
+        if spec.non_speech_tokens is None:
+            raise ValueError("suppress_tokens contains -1 but the spec carries no non_speech_tokens (they come from the tokenizer files)")
+        result = [t for t in result if t >= 0] + list(spec.non_speech_tokens)
+    result.extend([spec.transcribe, spec.translate, spec.sot, spec.sot_prev, spec.sot_lm])
+    if spec.no_speech is not None:
+        result.append(spec.no_speech)
+    return tuple(sorted(set(result)))
 
 
 def decoder_forward(P, tokens, xa, kv_cache=None, dims=WHISPER_SMALL):
@@ -173,11 +188,12 @@ def greedy_update(tokens, logits, sum_logprobs, eot):
     return tokens, bool((nxt == eot).all()), sum_logprobs
 
 
-def greedy_decode(P, xa, spec, sample_len=16, suppress=(), dims=WHISPER_SMALL, max_initial_timestamp_index=50):
+def greedy_decode(P, xa, spec, sample_len=16, suppress=(), dims=WHISPER_SMALL, max_initial_timestamp_index=50, without_timestamps=False):
     """DecodingTask._main_loop with GreedyDecoder(temperature=0) (decoding.py:588-632) on encoder features xa [B,1500,d].
     Returns (tokens incl. the sot sequence, sum_logprobs, no_speech_probs)."""
     B = xa.shape[0]
-    init = list(spec.sot_sequence)
+    suppress = get_suppress_tokens(spec, suppress) if suppress else ()            # DecodingTask.__init__, decoding.py:489-495
+    init = list(spec.sot_sequence) + ([spec.no_timestamps] if without_timestamps else [])     # sot_sequence_including_notimestamps, :463-465
     tokens = [list(init) for _ in range(B)]
     sample_begin = len(init)
     sum_lp = torch.zeros(B, dtype=xa.dtype)
@@ -188,7 +204,7 @@ def greedy_decode(P, xa, spec, sample_len=16, suppress=(), dims=WHISPER_SMALL, m
         pre, cache = decoder_forward(P, inp, xa, cache, dims)
         if i == 0:
             no_speech = torch.softmax(pre[:, 0], dim=-1)[:, spec.no_speech]          # sot_index = 0
-        logits = apply_filters(pre[:, -1], tokens, spec, sample_begin, suppress, max_initial_timestamp_index)
+        logits = apply_filters(pre[:, -1], tokens, spec, sample_begin, suppress, max_initial_timestamp_index, without_timestamps)
         tokens, completed, sum_lp = greedy_update(tokens, logits, sum_lp, spec.eot)
         if completed or len(tokens[0]) > dims["n_text_ctx"]:
             break

@@ -32,6 +32,67 @@ DIMS = dict(n_mels=80, n_audio_ctx=60, n_audio_state=64, n_audio_head=4, n_audio
             n_text_head=4, n_text_layer=2)
 
 
+class StubTokenizer:
+    """The attributes DecodingTask and its logit filters read (decoding.py:445-507, 349-442), on a 300-entry vocabulary laid out like
+    Whisper's: text < eot < the special block < timestamps."""
+    eot, sot, lang_en, transcribe, translate, sot_lm, sot_prev, no_speech, no_timestamps, timestamp_begin = 200, 201, 202, 203, 204, 205, 206, 207, 208, 209
+    sot_sequence = (201, 202, 203)
+    sot_sequence_including_notimestamps = (201, 202, 203, 208)
+    language = "en"
+
+    def encode(self, text):
+        return [7] if text == " " else [10 + (ord(c) % 150) for c in text]
+
+    def decode(self, tokens):
+        return " ".join(str(t) for t in tokens)
+
+
+def decode_cases(model, mel, out):
+    """DecodingTask._main_loop (decoding.py:588-632) with GreedyDecoder(temperature 0) and the three logit filters, on the encoder
+    features of the model above.  The decoder's last-layer bias of a few timestamp tokens is raised so that the timestamp rules
+    (pairs, text-after-pair, initial-timestamp window, probability-mass rule) all fire within the 14 sampled tokens."""
+    from mlx_audio.stt.models.whisper import decoding as D
+    model.get_tokenizer = lambda language=None, task=None: StubTokenizer()
+    gain = float(os.environ.get("TEXT_GAIN", "3.0"))                 # text rows of the tied embedding: makes text tokens competitive with the
+    w = np.array(model.decoder.token_embedding.weight)              # summed timestamp mass, so that the mass rule fires on some steps only
+    w[:StubTokenizer.eot] *= gain
+    model.decoder.token_embedding.weight = mx.array(w)
+    out["dec_text_gain"] = gain
+    suppress = [3, 4, 5, 250]
+    for tag, opts in (("ts", dict()), ("nots", dict(without_timestamps=True))):
+        options = D.DecodingOptions(language="en", temperature=0.0, sample_len=14, suppress_tokens=suppress, fp16=False, **opts)
+        task = D.DecodingTask(model, options)
+        task.inference.reset()
+        feats = task._get_audio_features(mx.array(mel))
+        tokens = mx.broadcast_to(mx.array(task.initial_tokens), (mel.shape[0], len(task.initial_tokens)))
+        tokens, sum_lp, no_speech = task._main_loop(feats, tokens)
+        out[f"dec_{tag}_tokens"], out[f"dec_{tag}_sum_logprobs"], out[f"dec_{tag}_no_speech"] = np.asarray(tokens), np.asarray(sum_lp), np.asarray(no_speech)
+        print(tag, np.asarray(tokens).tolist(), np.asarray(sum_lp))
+    out["dec_suppress"] = np.asarray(suppress)
+    # the three logit filters and GreedyDecoder.update applied directly to random logits under hand-built token histories
+    tk = StubTokenizer()
+    sb = 3
+    filters = [D.SuppressBlank(tk, sb, 300), D.SuppressTokens(suppress, 300), D.ApplyTimestampRules(tk, sb, 2)]
+    rng = np.random.default_rng(23)
+    T, E = tk.timestamp_begin, tk.eot
+    hist = {"first": [[]] * 3,
+            "mixed": [[11, 12, 13], [11, 12, T + 5], [11, T + 4, T + 5], [T + 1, T + 1, 12], [T + 2, 12, T + 9], [11, 12, E], [T, T, 14], [11, T, T + 30]],
+            "one": [[T + 3], [17], [T]], "two": [[T + 3, T + 3], [17, T + 8], [T + 1, 20]]}
+    for name, rows in hist.items():
+        toks = np.array([[201, 202, 203] + r for r in rows], dtype=np.int32)
+        logits = 3.0 * rng.standard_normal((len(rows), 300))
+        if name == "mixed":
+            logits[0, T:] += 4.0                                     # row 0: timestamp mass beats every text token
+        y = mx.array(logits)
+        for f in filters:
+            y = f.apply(y, mx.array(toks))
+        dec = D.GreedyDecoder(0.0, E)
+        nt, completed, slp = dec.update(mx.array(toks), y, mx.zeros(len(rows)))
+        out[f"filt_{name}_tokens"], out[f"filt_{name}_logits"], out[f"filt_{name}_out"] = toks, logits, np.asarray(y)
+        out[f"filt_{name}_next"], out[f"filt_{name}_sum_logprobs"], out[f"filt_{name}_completed"] = np.asarray(nt), np.asarray(slp), bool(completed)
+    out["dec_max_initial_timestamp_index"] = round(1.0 / (30.0 / DIMS["n_audio_ctx"]))
+
+
 def main():
     model = W.Model(W.ModelDimensions(**DIMS), dtype=mx.float32)
     names = [(n, v.shape) for n, v in shim.flat_parameters(model)]
@@ -50,6 +111,7 @@ def main():
     out = dict(params=synth_params.manifest(names), mel=mel, xa=np.asarray(xa), tokens=tokens, logits=np.asarray(logits),
                cross_qk_last=np.asarray(cross_qk[-1]), step_tokens=step_tokens, step_logits=np.stack(step_logits, 1)[:, :, 0],
                sinusoids=np.asarray(W.sinusoids(60, 64)))
+    decode_cases(model, mel, out)
     np.savez_compressed(os.path.join(HERE, "whisper_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})
 

@@ -79,6 +79,11 @@ class array(np.ndarray):
     def reciprocal(self):
         return 1.0 / self
 
+    def logsumexp(self, axis=None, keepdims=False):
+        m = np.max(np.asarray(self), axis=axis, keepdims=True)
+        r = np.log(np.sum(np.exp(np.asarray(self) - m), axis=axis, keepdims=True)) + m
+        return _w(r if keepdims else np.squeeze(r, axis=axis))
+
     def moveaxis(self, a, b):
         return np.moveaxis(self, a, b)
 
@@ -217,6 +222,8 @@ def build(precise=True):
     core.cpu, core.gpu = "cpu", "gpu"
     core.stream = lambda *_a, **_k: contextlib.nullcontext()
     core.eval = lambda *_a, **_k: None
+    core.async_eval = lambda *_a, **_k: None
+    core.nan = np.nan
     core.clear_cache = lambda *_a, **_k: None
     core.get_peak_memory = lambda: 0
     core.compile = lambda f=None, *a, **k: f if callable(f) else (lambda g: g)

@@ -226,3 +226,15 @@ def test_qwen3_config_and_routing_contract():
     assert s["decoder.pre_conv.conv.weight"].shape == (8, 3, 16) and s["decoder.upsample.0.0.conv.weight"].shape == (8, 2, 16)
     emb = s["decoder.quantizer.rvq_first.vq.layers.0.codebook.embed.weight"]
     assert emb[0].tolist() == [1.0, 2.0] and abs(float(emb[1, 0]) - 1e5) < 1.0 and "encoder.anything" not in s
+
+
+def test_whisper_suppress_token_expansion_follows_the_reference():
+    """decoding.py:79-112 / 489-495: a falsy option installs no SuppressTokens filter; otherwise the transcribe / translate / sot /
+    sot_prev / sot_lm markers and no_speech are always added, and -1 expands to the tokenizer's non-speech tokens."""
+    from mlx_audio.stt.models.whisper.decoding import TokenizerSpec, get_suppress_tokens
+    spec = TokenizerSpec()
+    assert get_suppress_tokens(spec) == () and get_suppress_tokens(spec, []) == ()
+    assert get_suppress_tokens(TokenizerSpec(suppress=(11, 12))) == (11, 12, 50258, 50358, 50359, 50360, 50361, 50362)
+    with pytest.raises(ValueError):
+        get_suppress_tokens(TokenizerSpec(suppress=(-1,)))
+    assert get_suppress_tokens(TokenizerSpec(suppress=(-1, 7), non_speech_tokens=(1, 2))) == (1, 2, 7, 50258, 50358, 50359, 50360, 50361, 50362)

@@ -424,3 +424,35 @@ def test_oracle_kokoro_matches_the_reference_model_code():
     assert np.array_equal(pd.numpy(), g["pred_dur"])
     a, w = audio.numpy().reshape(-1), g["audio"].reshape(-1)
     assert a.shape == w.shape == (43200,) and np.abs(a - w).max() < 2e-7
+
+
+def test_oracle_whisper_decoding_matches_the_reference_decoding_code():
+    """tests/golden/whisper_golden.npz (dec_* / filt_* entries) = the reference's decoding.py EXECUTED through the NumPy MLX stand-in with a
+    stub tokenizer on a 300-entry vocabulary laid out like Whisper's: SuppressBlank, SuppressTokens and ApplyTimestampRules applied to random
+    logits under hand-built token histories (first step, timestamp pairs, text after a pair, EOT rows, the probability-mass rule), then
+    GreedyDecoder.update; and DecodingTask._main_loop for 14 tokens with and without timestamps.  -inf patterns must be identical.
+    This run is what showed that get_suppress_tokens() always adds the task / sot markers and no_speech (decoding.py:100-112)."""
+    from oracle import whisper as OW
+    g, P = _golden("whisper_golden.npz")
+    dims = dict(n_mels=80, n_audio_ctx=60, n_audio_state=64, n_audio_head=4, n_audio_layer=2, n_vocab=300, n_text_ctx=32, n_text_state=64,
+                n_text_head=4, n_text_layer=2)
+    spec = OW.TokenizerSpec(eot=200, sot=201, no_timestamps=208, timestamp_begin=209, no_speech=207, blank_ids=(7,), language=202, task=203,
+                            transcribe=203, translate=204, sot_lm=205, sot_prev=206)
+    sup = g["dec_suppress"].tolist()
+    assert OW.get_suppress_tokens(spec, sup) == (3, 4, 5, 201, 203, 204, 205, 206, 207, 250)
+    for name in ("first", "mixed", "one", "two"):
+        toks = g[f"filt_{name}_tokens"].tolist()
+        y = OW.apply_filters(torch.as_tensor(g[f"filt_{name}_logits"]), toks, spec, 3, sup, max_initial_timestamp_index=2).numpy()
+        want = g[f"filt_{name}_out"]
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isinf(y), np.isinf(want)) and np.abs(y[fin] - want[fin]).max() < 1e-12, name
+        nt, comp, slp = OW.greedy_update(toks, torch.as_tensor(y), torch.zeros(len(toks), dtype=torch.float64), spec.eot)
+        assert np.array_equal(np.array(nt), g[f"filt_{name}_next"]) and comp == bool(g[f"filt_{name}_completed"])
+        assert np.allclose(slp.numpy(), g[f"filt_{name}_sum_logprobs"], rtol=0, atol=1e-12, equal_nan=True)
+    P["decoder.token_embedding.weight"] = P["decoder.token_embedding.weight"].clone()
+    P["decoder.token_embedding.weight"][:200] *= float(g["dec_text_gain"])
+    xa = torch.as_tensor(g["xa"])
+    for tag, wt in (("ts", False), ("nots", True)):
+        tok, slp, ns = OW.greedy_decode(P, xa, spec, sample_len=14, suppress=sup, dims=dims, max_initial_timestamp_index=2, without_timestamps=wt)
+        assert np.array_equal(np.array(tok), g[f"dec_{tag}_tokens"]), tag
+        assert np.abs(slp.numpy() - g[f"dec_{tag}_sum_logprobs"]).max() < 1e-11 and np.abs(ns.numpy() - g[f"dec_{tag}_no_speech"]).max() < 1e-12

@@ -108,6 +108,11 @@ def test_whisper_decoder_and_greedy_decode_parity():
     assert tokens == ref_tokens
     assert torch.allclose(lp.cpu().double(), ref_lp, rtol=1e-3, atol=1e-3)
     assert torch.allclose(ns.cpu().double(), ref_ns, rtol=1e-2, atol=1e-30)
+    # without timestamps the initial sequence carries <|notimestamps|> (decoding.py:463-465) and the timestamp rules are off
+    ref_tokens, ref_lp, _ = OW.greedy_decode(P64, xa.double(), spec, sample_len=6, suppress=(11, 12), dims=dims, without_timestamps=True)
+    tokens, lp, _ = model.greedy_decode(xa, TokenizerSpec(suppress=(11, 12)), sample_len=6, without_timestamps=True)
+    assert tokens == ref_tokens and tokens[0][3] == spec.no_timestamps
+    assert torch.allclose(lp.cpu().double(), ref_lp, rtol=1e-3, atol=1e-3)
 
 
 def test_dsp_frontend_matches_vectors_produced_by_the_reference_code():
