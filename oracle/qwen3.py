@@ -12,7 +12,9 @@ follows the reference literally.
 
 parity: pinned against the reference's own shape/length contracts (tests/test_oracle_pins.py: 1920 samples per frame,
 chunked == unchunked decode on the overlap-free region, interleaved MRoPE index pattern of talker.py:139-184, sampler
-filters vs hand-computed cases of lm/sample_utils.py).  The MLX reference itself cannot run here (no MLX wheel).
+filters vs hand-computed cases of lm/sample_utils.py) AND against the reference's own talker / code predictor / sampler / Model.generate /
+Model.batch_generate / speech-tokenizer code executed through a NumPy stand-in for MLX (tests/golden/make_qwen3_golden.py, qwen3_golden.npz:
+logits 4e-15, code matrices identical).
 """
 from __future__ import annotations
 
