@@ -96,6 +96,73 @@ def snac_decoder(P, z, cfg, noises):
     return torch.tanh(x)
 
 
+def snac_encoder(P, x, cfg):
+    """Encoder (snac/layers.py:133-158) on NLC x [B,n,1] -> [B,T,latent]: k7 conv, per stride {3 residual units, Snake, strided conv
+    k = 2s, padding ceil(s/2)} with channels doubling, final (depthwise) k7 conv.  LocalMHA only when attn_window_size is set (44 kHz)."""
+    if cfg.get("attn_window_size") is not None:
+        raise NotImplementedError("LocalMHA (attn_window_size) is outside the 24 kHz path")
+    pre = "encoder.block.layers"
+    x = snac_wnconv(P, f"{pre}.0", x, padding=3)
+    d, li = cfg["encoder_dim"], 1
+    for stride in cfg["encoder_rates"]:
+        d *= 2
+        groups = d // 2 if cfg["depthwise"] else 1
+        bp = f"{pre}.{li}.block.layers"
+        for bi, dil in enumerate((1, 3, 9)):
+            x = snac_residual_unit(P, f"{bp}.{bi}", x, dil, groups)
+        x = snake_snac(x, P[f"{bp}.3.alpha"].transpose(1, 2))
+        x = snac_wnconv(P, f"{bp}.4", x, stride=stride, padding=math.ceil(stride / 2))
+        li += 1
+    return snac_wnconv(P, f"{pre}.{li}", x, padding=3, groups=d if cfg["depthwise"] else 1)
+
+
+def snac_quantize(P, z, cfg):
+    """ResidualVectorQuantize.__call__ over VectorQuantize.__call__ / decode_latents (snac/vq.py:22-90,93-109) on z [B,D,T]:
+    per level average-pool the residual by the level's stride, project to 8 dims, pick the nearest L2-normalised code
+    (first index on ties), project back, repeat by the stride, subtract from the residual.  -> (z_q [B,D,T], [codes [B,T/stride]])."""
+    zq, residual, codes = 0.0, z, []
+    for i, stride in enumerate(cfg["vq_strides"]):
+        pre = f"quantizer.quantizers.{i}"
+        x = residual.transpose(1, 2)                                                   # NLC
+        if stride > 1:
+            t = (x.shape[1] - stride) // stride + 1
+            x = x[:, : t * stride].reshape(x.shape[0], t, stride, x.shape[2]).sum(dim=2) / stride
+        z_e = snac_wnconv(P, pre + ".in_proj", x)                                      # [B,T',cd]
+        cb = P[pre + ".codebook.weight"]
+        e = z_e.reshape(-1, z_e.shape[-1])
+        en = e / torch.clamp(torch.sqrt((e.abs() ** 2).sum(1, keepdim=True)), min=1e-12)
+        cn = cb / torch.clamp(torch.sqrt((cb.abs() ** 2).sum(1, keepdim=True)), min=1e-12)
+        dist = (en ** 2).sum(1, keepdim=True) - 2 * en @ cn.T + (cn ** 2).sum(1, keepdim=True).T
+        idx = (-dist).argmax(1).reshape(z_e.shape[0], z_e.shape[1])
+        z_qi = z_e + (cb[idx] - z_e)                                                   # straight-through form, kept literally
+        z_qi = snac_wnconv(P, pre + ".out_proj", z_qi).transpose(1, 2)                 # [B,D,T']
+        if stride > 1:
+            z_qi = torch.repeat_interleave(z_qi, stride, dim=2)
+        zq = zq + z_qi
+        residual = residual - z_qi
+        codes.append(idx)
+    return zq, codes
+
+
+def snac_preprocess(audio, cfg):
+    """SNAC.preprocess (snac/snac.py:67-84): right-pad [B,1,n] to a multiple of hop * lcm(vq_strides[, attn window])."""
+    lcm = cfg["vq_strides"][0]
+    for v in cfg["vq_strides"][1:]:
+        lcm = abs(lcm * v) // math.gcd(lcm, v)
+    if cfg.get("attn_window_size"):
+        lcm = abs(lcm * cfg["attn_window_size"]) // math.gcd(lcm, cfg["attn_window_size"])
+    pad_to = math.prod(cfg["encoder_rates"]) * lcm
+    n = audio.shape[-1]
+    return torch.nn.functional.pad(audio, (0, math.ceil(n / pad_to) * pad_to - n))
+
+
+def snac_encode(P, audio, cfg=SNAC_24K):
+    """SNAC.encode (snac/snac.py:95-99): audio [B,1,n] -> list of int64 codes, coarse to fine."""
+    x = snac_preprocess(audio, cfg)
+    z = snac_encoder(P, x.transpose(1, 2), cfg).transpose(1, 2)
+    return snac_quantize(P, z, cfg)[1]
+
+
 def snac_decode(P, codes, cfg=SNAC_24K, noises=None):
     """SNAC.decode (snac/snac.py:101-104): list of codes -> audio [B, T_out, 1]."""
     z = snac_from_codes(P, codes, cfg)
@@ -112,14 +179,14 @@ MIMI_202407 = {   # codec/models/mimi/mimi.py:47-96
 }
 
 
-def mimi_causal_conv(P, pre, x, ksize, stride=1, dilation=1):
-    """StreamableConv1d.__call__ (mimi/modules/conv.py:224-243), causal, constant pad, on NCL x."""
+def mimi_causal_conv(P, pre, x, ksize, stride=1, dilation=1, pad_mode="constant"):
+    """StreamableConv1d.__call__ (mimi/modules/conv.py:224-243), causal, constant (or "edge" = replicate) pad, on NCL x."""
     k_eff = (ksize - 1) * dilation + 1
     pad_total = k_eff - stride
     ln = x.shape[-1]
     nframes = max(ln + pad_total - k_eff, 0) / stride + 1.0
     extra = max(0, (int(math.ceil(nframes)) - 1) * stride + k_eff - pad_total - ln)
-    xp = torch.nn.functional.pad(x, (pad_total, extra))
+    xp = torch.nn.functional.pad(x, (pad_total, extra), mode="replicate" if pad_mode == "edge" else "constant")
     return N.conv1d(xp.transpose(1, 2), P[pre + ".conv.conv.weight"].to(x.dtype), stride, 0, dilation, 1,
                     P.get(pre + ".conv.conv.bias")).transpose(1, 2)
 
@@ -188,6 +255,46 @@ def mimi_seanet_decoder(P, x, cfg):
         y = mimi_causal_conv(P, L + ".residuals.0.block.1", N.elu(y), 1)
         x = y + r
     return mimi_causal_conv(P, pre + ".final_conv1d", N.elu(x), cfg["last_ksize"])
+
+
+def mimi_seanet_encoder(P, x, cfg):
+    """SeanetEncoder.__call__ (seanet.py:194-199) on NCL x [B,1,n]: init conv, per ratio (reversed) {resnet block, ELU, strided conv
+    k = 2r}, ELU, final conv."""
+    pre = "encoder"
+    x = mimi_causal_conv(P, pre + ".init_conv1d", x, cfg["ksize"])
+    for li, ratio in enumerate(reversed(cfg["ratios"])):
+        L = f"{pre}.layers.{li}"
+        y = mimi_causal_conv(P, L + ".residuals.0.block.0", N.elu(x), cfg["residual_ksize"])
+        y = mimi_causal_conv(P, L + ".residuals.0.block.1", N.elu(y), 1)
+        x = mimi_causal_conv(P, L + ".downsample", N.elu(y + x), 2 * ratio, stride=ratio)
+    return mimi_causal_conv(P, pre + ".final_conv1d", N.elu(x), cfg["last_ksize"])
+
+
+def mimi_quantizer_encode(P, x, cfg):
+    """SplitResidualVectorQuantizer.encode (quantization.py:178-185,138-141,90-101,37-45): x [B,512,T] -> int64 codes [B,nq,T].
+    Nearest code = argmin(|e|^2 / 2 - x.e) on the residual, which is then reduced by the chosen embedding."""
+    codes = []
+    for name, nq in (("rvq_first", 1), ("rvq_rest", cfg["nq"] - 1)):
+        if nq <= 0:
+            continue
+        r = N.conv1d(x.transpose(1, 2), P[f"quantizer.{name}.input_proj.weight"].to(x.dtype))          # [B,T,qdim]
+        for li in range(nq):
+            pre = f"quantizer.{name}.vq.layers.{li}.codebook"
+            emb = P[pre + ".embedding_sum"] / torch.clamp(P[pre + ".cluster_usage"], min=1e-5)[:, None]
+            idx = ((emb * emb).sum(-1) / 2 - r @ emb.T).argmin(dim=-1)                                  # [B,T]
+            r = r - emb[idx]
+            codes.append(idx)
+    return torch.stack(codes, dim=1)
+
+
+def mimi_encode(P, pcm, cfg=MIMI_202407):
+    """Mimi.encode (mimi.py:146-153): pcm [B,1,n] -> codes [B,nq,ceil(n/1920)] (SEANet encoder, encoder transformer, stride-2
+    replicate-padded downsampling conv, split RVQ)."""
+    x = mimi_seanet_encoder(P, pcm, cfg)
+    x = mimi_transformer(P, "encoder_transformer", x, cfg)
+    s = cfg["upsample_stride"]
+    x = mimi_causal_conv(P, "downsample.conv", x, 2 * s, stride=s, pad_mode="edge")
+    return mimi_quantizer_encode(P, x, cfg)
 
 
 def mimi_decode(P, codes, cfg=MIMI_202407):

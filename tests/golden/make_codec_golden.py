@@ -43,7 +43,6 @@ def snac_cases(out):
     import re
     last = max(int(m.group(1)) for n, _ in shim.flat_parameters(model) if (m := re.match(r"decoder\.model\.layers\.(\d+)\.weight_g$", n)))
     names = fill(model, rule=lambda n: "scale0.03" if n == f"decoder.model.layers.{last}.weight_g" else None)   # keeps tanh mostly unsaturated
-    names = [e for e in names if not e[0].startswith("encoder.")]
     out["snac_params"], out["snac_cfg"] = synth_params.manifest(names), json.dumps(SNAC_CFG)
     rng = np.random.default_rng(61)
     t = 5
@@ -55,6 +54,13 @@ def snac_cases(out):
     audio = model.decode([mx.array(c) for c in codes])
     assert not mx.random.queue
     mx.random.strict = False
+    # encode side: audio -> three code streams (integer result); 700 samples short of the padding quantum
+    audio_in = 0.5 * rng.standard_normal((2, 1, 3 * 64 - 50))
+    enc = model.encode(mx.array(audio_in))
+    out["snac_enc_audio"] = audio_in
+    for i, c in enumerate(enc):
+        out[f"snac_enc_codes_{i}"] = np.asarray(c)
+    print("snac encode", [np.asarray(c).shape for c in enc])
     for i, c in enumerate(codes):
         out[f"snac_codes_{i}"] = c
     for i, n in enumerate(noises):
@@ -83,13 +89,16 @@ def mimi_cases(out):
                        quantizer_bins=c["bins"], quantizer_dim=c["qdim"])
     model = M.Mimi(cfg)
     names = fill(model)
-    names = [e for e in names if not e[0].startswith(("encoder.", "encoder_transformer.", "downsample."))]
     out["mimi_params"], out["mimi_cfg"] = synth_params.manifest(names), json.dumps(c)
     rng = np.random.default_rng(62)
     codes = rng.integers(0, c["bins"], size=(2, c["nq"], 9))
     pcm = model.decode(mx.array(codes))
     out["mimi_codes"], out["mimi_pcm"] = codes, np.asarray(pcm)
     print("mimi pcm", pcm.shape, float(np.abs(np.asarray(pcm)).max()))
+    # encode side: pcm -> codes (integer result), an input length that is not a multiple of the 1920-sample frame
+    pcm_in = 0.5 * rng.standard_normal((2, 1, 12 * 1920 + 700))
+    out["mimi_enc_pcm"], out["mimi_enc_codes"] = pcm_in, np.asarray(model.encode(mx.array(pcm_in)))
+    print("mimi encode", out["mimi_enc_codes"].shape)
     # streaming: decode_step over two chunks continues the conv buffers and the rotating kv cache
     model.reset_state()
     parts = [np.asarray(model.decode_step(mx.array(codes[:, :, :4]))), np.asarray(model.decode_step(mx.array(codes[:, :, 4:])))]

@@ -377,7 +377,8 @@ def test_oracle_codecs_match_the_reference_model_code():
     in float64 at reduced configurations with NumPy standing in for MLX (tests/golden/make_codec_golden.py).  SNAC: strides 8/3/4/2 (the
     output_padding<-groups argument quirk gives 3867 samples for 5 coarse frames), per-channel noise injected.  Mimi: split RVQ with the
     embedding_sum / cluster_usage codebooks, depthwise transposed-conv upsampling, rope transformer with a 6-step attention context over 18
-    steps, SEANet decoder.  Waveforms are stored as float32 in the fixture, hence 2e-7."""
+    steps, SEANet decoder.  Waveforms are stored as float32 in the fixture, hence 2e-7.  The encode side of both codecs (SEANet / SNAC encoder, residual
+    vector quantisation by nearest code) is pinned too: identical code streams."""
     import json
     from oracle import codec as OC
     g, _ = _golden("codec_golden.npz")
@@ -392,6 +393,15 @@ def test_oracle_codecs_match_the_reference_model_code():
     P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["mimi_params"]).items()}
     y = OC.mimi_decode(P, torch.as_tensor(g["mimi_codes"]).long(), cfg)
     assert tuple(y.shape) == g["mimi_pcm"].shape == (2, 1, 9 * 1920) and np.abs(y.numpy() - g["mimi_pcm"]).max() < 2e-7
+    # encode side (integer results, identical): Mimi.encode on 12 frames + 700 samples, SNAC.encode on a length that needs right padding
+    c = OC.mimi_encode(P, torch.as_tensor(g["mimi_enc_pcm"]), cfg)
+    assert tuple(c.shape) == (2, 4, 13) and np.array_equal(c.numpy(), g["mimi_enc_codes"])
+    cfg = json.loads(str(g["snac_cfg"]))
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["snac_params"]).items()}
+    enc = OC.snac_encode(P, torch.as_tensor(g["snac_enc_audio"]), cfg)
+    assert [tuple(e.shape) for e in enc] == [(2, 3), (2, 6), (2, 12)]
+    for i, e in enumerate(enc):
+        assert np.array_equal(e.numpy(), g[f"snac_enc_codes_{i}"]), i
 
 
 def test_oracle_kokoro_matches_the_reference_model_code():
