@@ -238,3 +238,29 @@ def test_whisper_suppress_token_expansion_follows_the_reference():
     with pytest.raises(ValueError):
         get_suppress_tokens(TokenizerSpec(suppress=(-1,)))
     assert get_suppress_tokens(TokenizerSpec(suppress=(-1, 7), non_speech_tokens=(1, 2))) == (1, 2, 7, 50258, 50358, 50359, 50360, 50361, 50362)
+
+
+def test_kvcache_follows_the_trace_of_the_reference_class():
+    """tests/golden/cache_golden.npz = the reference's lm/models/cache.py:KVCache EXECUTED (NumPy standing in for MLX,
+    tests/golden/make_cache_golden.py) through updates that cross the 256-row growth rule in every way (first block, growth from a
+    non-multiple offset, exact fill), trims, and a state round trip.  The product class must show the same capacity / offset / fetched
+    contents after every operation."""
+    import json
+    import os
+    import numpy as np
+    import torch
+    from mlx_audio.lm.models.cache import KVCache
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "cache_golden.npz"))
+    c = KVCache()
+    for i, rec in enumerate(json.loads(str(g["trace"]))):
+        if rec["op"] == "update":
+            fk, fv = c.update_and_fetch(torch.as_tensor(g[f"k_{i}"]), torch.as_tensor(g[f"v_{i}"]))
+            assert np.array_equal(fk.numpy(), g[f"fk_{i}"]) and np.array_equal(fv.numpy(), g[f"fv_{i}"]), i
+        elif rec["op"] == "trim":
+            assert c.trim(rec["n"]) == rec["trimmed"]
+        else:
+            sk, sv = c.state
+            assert sk.shape[2] == rec["state_len"]
+            c.state = (sk, sv)
+        assert (c.offset, c.keys.shape[2], c.size(), c.empty(), c.is_trimmable()) == (rec["offset"], rec["capacity"], rec["size"], rec["empty"],
+                                                                                      rec["trimmable"]), (i, rec)
