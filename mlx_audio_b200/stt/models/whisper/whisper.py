@@ -226,8 +226,45 @@ class Model:
     def eval(self):
         return self
 
+    _HF_KEY_MAP = (                                                      # whisper.py:562-585; specific patterns before generic ones
+        ("encoder.embed_positions.weight", None),                        # recomputed (sinusoids)
+        ("decoder.embed_positions.weight", "decoder.positional_embedding"),
+        ("encoder.layer_norm.", "encoder.ln_post."), ("decoder.layer_norm.", "decoder.ln."),
+        ("encoder.layers.", "encoder.blocks."), ("decoder.layers.", "decoder.blocks."),
+        (".self_attn_layer_norm.", ".attn_ln."), (".final_layer_norm.", ".mlp_ln."), (".encoder_attn_layer_norm.", ".cross_attn_ln."),
+        (".fc1.", ".mlp1."), (".fc2.", ".mlp2."),
+        (".self_attn.q_proj.", ".attn.query."), (".self_attn.k_proj.", ".attn.key."), (".self_attn.v_proj.", ".attn.value."),
+        (".self_attn.out_proj.", ".attn.out."),
+        (".encoder_attn.q_proj.", ".cross_attn.query."), (".encoder_attn.k_proj.", ".cross_attn.key."),
+        (".encoder_attn.v_proj.", ".cross_attn.value."), (".encoder_attn.out_proj.", ".cross_attn.out."),
+        ("decoder.embed_tokens.", "decoder.token_embedding."),
+    )
+
     def sanitize(self, weights):
-        return {k: v for k, v in weights.items() if "_positional_embedding" not in k}
+        """whisper.py:551-618: a HuggingFace checkpoint (keys under ``model.``) is renamed to the reference's module tree and its conv
+        weights go from (out, in, K) to (out, K, in); an MLX-format checkpoint passes through.  (The dtype cast of the reference happens in
+        ``load_weights`` here.)"""
+        is_hf = any(k.startswith("model.") for k in weights)
+        out = {}
+        for k, v in weights.items():
+            if "_positional_embedding" in k:
+                continue
+            if is_hf:
+                if k.startswith("model."):
+                    k = k[6:]
+                skip = False
+                for old, new in self._HF_KEY_MAP:
+                    if old in k:
+                        if new is None:
+                            skip = True
+                            break
+                        k = k.replace(old, new)
+                if skip:
+                    continue
+                if ("conv1.weight" in k or "conv2.weight" in k) and v.dim() == 3:
+                    v = v.permute(0, 2, 1).contiguous()
+            out[k] = v
+        return out
 
     def load_weights(self, weights, strict=False):
         P = dict(weights)

@@ -1,0 +1,101 @@
+"""Synthetic checkpoints in the layouts the hub ships (HuggingFace / PyTorch names and axis orders), shared by
+make_sanitize_golden.py (which feeds them to the REFERENCE's sanitize functions) and tests/test_host_cpu.py (which feeds the same
+dicts to the product's).  Values come from synth_params.value(name, shape), float32."""
+import numpy as np
+
+import synth_params
+
+WHISPER_DIMS = dict(n_mels=80, n_audio_ctx=60, n_audio_state=64, n_audio_head=4, n_audio_layer=2, n_vocab=300, n_text_ctx=32, n_text_state=64,
+                    n_text_head=4, n_text_layer=2)
+
+
+def _fill(entries):
+    return {n: synth_params.value(n, sh).astype(np.float32) for n, sh in entries}
+
+
+def whisper_hf(d=WHISPER_DIMS):
+    """transformers' WhisperForConditionalGeneration state dict: ``model.`` prefix, (out, in, K) conv weights, no k_proj bias."""
+    e = []
+    a, t = d["n_audio_state"], d["n_text_state"]
+
+    def attn(pre, n):
+        for p in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            e.append((f"{pre}.{p}.weight", (n, n)))
+            if p != "k_proj":
+                e.append((f"{pre}.{p}.bias", (n,)))
+
+    def ln(pre, n):
+        e.extend([(pre + ".weight", (n,)), (pre + ".bias", (n,))])
+    e += [("model.encoder.conv1.weight", (a, d["n_mels"], 3)), ("model.encoder.conv1.bias", (a,)), ("model.encoder.conv2.weight", (a, a, 3)),
+          ("model.encoder.conv2.bias", (a,)), ("model.encoder.embed_positions.weight", (d["n_audio_ctx"], a))]
+    for i in range(d["n_audio_layer"]):
+        L = f"model.encoder.layers.{i}"
+        attn(L + ".self_attn", a)
+        ln(L + ".self_attn_layer_norm", a)
+        e += [(L + ".fc1.weight", (4 * a, a)), (L + ".fc1.bias", (4 * a,)), (L + ".fc2.weight", (a, 4 * a)), (L + ".fc2.bias", (a,))]
+        ln(L + ".final_layer_norm", a)
+    ln("model.encoder.layer_norm", a)
+    e += [("model.decoder.embed_tokens.weight", (d["n_vocab"], t)), ("model.decoder.embed_positions.weight", (d["n_text_ctx"], t))]
+    for i in range(d["n_text_layer"]):
+        L = f"model.decoder.layers.{i}"
+        attn(L + ".self_attn", t)
+        ln(L + ".self_attn_layer_norm", t)
+        attn(L + ".encoder_attn", t)
+        ln(L + ".encoder_attn_layer_norm", t)
+        e += [(L + ".fc1.weight", (4 * t, t)), (L + ".fc1.bias", (4 * t,)), (L + ".fc2.weight", (t, 4 * t)), (L + ".fc2.bias", (t,))]
+        ln(L + ".final_layer_norm", t)
+    ln("model.decoder.layer_norm", t)
+    return _fill(e)
+
+
+def qwen3_model_torch():
+    """Keys of a Qwen3-TTS ``model.safetensors`` that Model.sanitize (qwen3_tts.py:2914-2935) has rules for: position_ids, conv weights in
+    either axis order (the shape heuristic decides), the speaker encoder's 1x1 ``fc``, and plain matrices that must pass through."""
+    return _fill([("talker.model.layers.0.self_attn.q_proj.weight", (64, 32)), ("talker.model.codec_embedding.weight", (50, 32)),
+                  ("talker.rotary.position_ids", (1, 16)), ("speaker_encoder.blocks.0.conv.weight", (48, 40, 5)),
+                  ("speaker_encoder.blocks.1.conv.weight", (48, 3, 96)), ("speaker_encoder.blocks.2.conv.weight", (48, 96, 1)),
+                  ("speaker_encoder.blocks.3.conv.weight", (48, 1, 96)), ("speaker_encoder.blocks.4.conv.weight", (48, 1, 5)),
+                  ("speaker_encoder.blocks.5.conv.weight", (48, 7, 1)), ("speaker_encoder.fc.weight", (32, 96, 1)), ("speaker_encoder.fc.bias", (32,)),
+                  ("speaker_encoder.asp.conv.bias", (48,)), ("talker.code_predictor.lm_head.0.weight", (40, 32))])
+
+
+def qwen3_tokenizer_torch():
+    """Keys of ``speech_tokenizer/model.safetensors`` (decoder half + a few encoder keys, which the decoder-only product must ignore and the
+    reference maps elsewhere): PyTorch conv (out, in, K), transposed conv (in, out, K), codebooks as embedding_sum + cluster_usage."""
+    e = [("decoder.pre_conv.conv.weight", (32, 16, 3)), ("decoder.pre_conv.conv.bias", (32,)),
+         ("decoder.pre_transformer.layers.0.self_attn.q_proj.weight", (32, 32)), ("decoder.pre_transformer.input_proj.weight", (32, 32)),
+         ("decoder.pre_transformer.layers.0.self_attn_layer_scale.scale", (32,)),
+         ("decoder.quantizer.rvq_first.output_proj.weight", (16, 8, 1)), ("decoder.quantizer.rvq_rest.output_proj.weight", (16, 8, 1)),
+         ("decoder.quantizer.rvq_first.vq.layers.0._codebook.embedding_sum", (80, 8)), ("decoder.quantizer.rvq_first.vq.layers.0._codebook.cluster_usage", (80,)),
+         ("decoder.quantizer.rvq_rest.vq.layers.0._codebook.embedding_sum", (80, 8)), ("decoder.quantizer.rvq_rest.vq.layers.0._codebook.cluster_usage", (80,)),
+         ("decoder.quantizer.rvq_rest.vq.layers.1._codebook.embedding_sum", (80, 8)), ("decoder.quantizer.rvq_rest.vq.layers.1._codebook.cluster_usage", (80,)),
+         ("decoder.upsample.0.0.conv.weight", (32, 32, 2)), ("decoder.upsample.0.0.conv.bias", (32,)), ("decoder.upsample.0.1.dwconv.conv.weight", (32, 1, 7)),
+         ("decoder.upsample.0.1.pwconv1.weight", (128, 32)), ("decoder.upsample.0.1.gamma", (32,)),
+         ("decoder.decoder.0.conv.weight", (48, 32, 7)), ("decoder.decoder.1.block.0.alpha", (48,)), ("decoder.decoder.1.block.1.conv.weight", (48, 24, 16)),
+         ("decoder.decoder.1.block.2.conv1.conv.weight", (24, 24, 7)), ("decoder.decoder.1.block.2.conv2.conv.weight", (24, 24, 1)),
+         ("decoder.decoder.2.block.1.conv.weight", (24, 12, 10)), ("decoder.decoder.6.conv.weight", (1, 3, 7)), ("decoder.decoder.6.conv.bias", (1,))]
+    return _fill(e)
+
+
+def kokoro_torch():
+    """Key patterns of the PyTorch Kokoro-82M checkpoint that Model.sanitize (kokoro.py:179-276) and Decoder.sanitize (istftnet.py:999-1011)
+    have rules for: ALBERT position_ids, LayerNorm gamma / beta, torch LSTM names, weight_v in either axis order, the 1x1 F0 / N projections
+    and the generator's noise convs."""
+    return _fill([("bert.embeddings.position_ids", (1, 512)), ("bert.embeddings.word_embeddings.weight", (178, 128)),
+                  ("bert.encoder.albert_layer_groups.0.albert_layers.0.ffn.weight", (64, 32)), ("bert_encoder.weight", (32, 48)), ("bert_encoder.bias", (32,)),
+                  ("text_encoder.embedding.weight", (178, 32)), ("text_encoder.cnn.0.0.weight_v", (32, 32, 5)), ("text_encoder.cnn.0.0.weight_g", (32, 1, 1)),
+                  ("text_encoder.cnn.0.0.bias", (32,)), ("text_encoder.cnn.0.1.gamma", (32,)), ("text_encoder.cnn.0.1.beta", (32,)),
+                  ("text_encoder.lstm.weight_ih_l0", (64, 32)), ("text_encoder.lstm.weight_hh_l0", (64, 16)), ("text_encoder.lstm.bias_ih_l0", (64,)),
+                  ("text_encoder.lstm.bias_hh_l0", (64,)), ("text_encoder.lstm.weight_ih_l0_reverse", (64, 32)),
+                  ("text_encoder.lstm.weight_hh_l0_reverse", (64, 16)), ("text_encoder.lstm.bias_ih_l0_reverse", (64,)),
+                  ("text_encoder.lstm.bias_hh_l0_reverse", (64,)),
+                  ("predictor.lstm.weight_ih_l0", (64, 40)), ("predictor.lstm.bias_hh_l0_reverse", (64,)), ("predictor.text_encoder.lstms.1.fc.weight", (64, 16)),
+                  ("predictor.F0.0.conv1.weight_v", (32, 32, 3)), ("predictor.F0.1.pool.weight_v", (32, 1, 3)), ("predictor.F0.1.conv1x1.weight_v", (16, 32, 1)),
+                  ("predictor.F0_proj.weight", (1, 16, 1)), ("predictor.F0_proj.bias", (1,)), ("predictor.N_proj.weight", (1, 16, 1)),
+                  ("predictor.duration_proj.linear_layer.weight", (50, 32)),
+                  ("decoder.encode.conv1.weight_v", (96, 34, 3)), ("decoder.encode.conv1.weight_g", (96, 1, 1)), ("decoder.asr_res.0.weight_v", (64, 512, 1)),
+                  ("decoder.F0_conv.weight_v", (1, 1, 3)), ("decoder.generator.ups.0.weight_v", (64, 32, 20)), ("decoder.generator.ups.1.weight_v", (32, 12, 16)),
+                  ("decoder.generator.noise_convs.0.weight", (32, 22, 12)), ("decoder.generator.noise_convs.0.bias", (32,)),
+                  ("decoder.generator.noise_convs.1.weight", (16, 22, 1)), ("decoder.generator.resblocks.0.convs1.0.weight_v", (32, 32, 3)),
+                  ("decoder.generator.resblocks.0.alpha1.0", (1, 32, 1)), ("decoder.generator.conv_post.weight_v", (22, 16, 7)),
+                  ("decoder.generator.m_source.l_linear.weight", (1, 9))])

@@ -264,3 +264,36 @@ def test_kvcache_follows_the_trace_of_the_reference_class():
             c.state = (sk, sv)
         assert (c.offset, c.keys.shape[2], c.size(), c.empty(), c.is_trimmable()) == (rec["offset"], rec["capacity"], rec["size"], rec["empty"],
                                                                                       rec["trimmable"]), (i, rec)
+
+
+def test_sanitize_matches_what_the_reference_sanitize_returns():
+    """tests/golden/sanitize_golden.json = key -> (shape, CRC-32 of the float32 bytes) of the dictionaries the REFERENCE's own sanitize
+    functions return for the synthetic hub-layout checkpoints of tests/golden/checkpoint_layouts.py (make_sanitize_golden.py, NumPy standing in
+    for MLX): Whisper from a HuggingFace state dict (whisper.py:551-618), Qwen3-TTS Model.sanitize (qwen3_tts.py:2914-2935), the decoder
+    half of Qwen3TTSSpeechTokenizer.sanitize (speech_tokenizer.py:1220-1447) and Kokoro's Model.sanitize (kokoro.py:179-276).  The product's functions must return the same keys, shapes and
+    values for the same inputs."""
+    import json
+    import os
+    import sys
+    import zlib
+    import numpy as np
+    import torch
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import checkpoint_layouts as L
+    want = json.load(open(os.path.join(here, "sanitize_golden.json")))
+
+    def manifest(d):
+        return {k: [list(v.shape), zlib.crc32(np.ascontiguousarray(v.detach().cpu().float().numpy()).tobytes())] for k, v in d.items()}
+
+    def t(d):
+        return {k: torch.as_tensor(v) for k, v in d.items()}
+    from mlx_audio_b200.stt.models.whisper.whisper import Model as Whisper
+    assert manifest(Whisper.sanitize(Whisper.__new__(Whisper), t(L.whisper_hf()))) == want["whisper_hf"]
+    from mlx_audio.tts.models.qwen3_tts.qwen3_tts import Model as Qwen3
+    from mlx_audio.tts.models.qwen3_tts.speech_tokenizer import Qwen3TTSSpeechTokenizer
+    assert manifest(Qwen3.sanitize(t(L.qwen3_model_torch()))) == want["qwen3_model"]
+    assert manifest(Qwen3TTSSpeechTokenizer.sanitize(t(L.qwen3_tokenizer_torch()))) == want["qwen3_tokenizer_decoder"]
+    from mlx_audio_b200.tts.models.kokoro.kokoro import Model as Kokoro
+    assert manifest(Kokoro.sanitize(Kokoro.__new__(Kokoro), t(L.kokoro_torch()))) == want["kokoro_torch"]
