@@ -59,6 +59,58 @@ class Mimi:
     def reset_state(self):
         """Full-sequence decode keeps no state; present for API parity (mimi.py:138-144)."""
 
+    @staticmethod
+    def sanitize_pytorch_weights(weights: dict) -> dict:
+        """The key / layout mapping of ``Mimi.load_pytorch_weights`` (mimi.py:196-249): kyutai's PyTorch checkpoint names -> the reference's
+        module tree (leading underscores dropped, SEANet ``model.N`` indices -> ``layers.i.{upsample,downsample,residuals.0}``, transformer
+        ``in_proj_weight`` / ``linearN`` renames), conv weights (out, in, K) -> (out, K, in), transposed-conv weights (in, out/g, K) ->
+        (out, K, in/g)."""
+        out = {}
+        for k, v in weights.items():
+            k = ".".join(s.removeprefix("_") for s in k.split("."))
+            if k.startswith("encoder.model."):
+                k = k.replace("encoder.model.", "encoder.")
+            if k.startswith("decoder.model."):
+                k = k.replace("decoder.model.", "decoder.")
+            if k.endswith(".in_proj_weight"):
+                k = k.replace(".in_proj_weight", ".in_proj.weight")
+            if k.endswith(".linear1.weight"):
+                k = k.replace(".linear1.weight", ".gating.linear1.weight")
+            if k.endswith(".linear2.weight"):
+                k = k.replace(".linear2.weight", ".gating.linear2.weight")
+            for li, di in enumerate((2, 5, 8, 11)):
+                k = k.replace(f"decoder.{di}.", f"decoder.layers.{li}.upsample.")
+                k = k.replace(f"decoder.{di + 1}.", f"decoder.layers.{li}.residuals.0.")
+            for li, ei in enumerate((1, 4, 7, 10)):
+                k = k.replace(f"encoder.{ei}.", f"encoder.layers.{li}.residuals.0.")
+                k = k.replace(f"encoder.{ei + 2}.", f"encoder.layers.{li}.downsample.")
+            k = k.replace("decoder.0.", "decoder.init_conv1d.").replace("decoder.14.", "decoder.final_conv1d.")
+            k = k.replace("encoder.0.", "encoder.init_conv1d.").replace("encoder.14.", "encoder.final_conv1d.")
+            k = k.replace(".block.1.", ".block.0.").replace(".block.3.", ".block.1.")
+            if k.endswith((".conv.weight", ".output_proj.weight", ".input_proj.weight")):
+                v = v.transpose(-1, -2)
+            if k.endswith(".convtr.weight"):
+                v = v.permute(0, 2, 1) if (v.dim() == 3 and v.shape[1] == 1) else v.permute(1, 2, 0)
+            out[k] = v.contiguous()
+        return out
+
+    @classmethod
+    def from_pretrained(cls, repo_id, filename: str = "tokenizer-e351c8d8-checkpoint125.safetensors", device="cuda"):
+        """mimi.py:264-275: the 32-codebook 2024-07 configuration from kyutai's checkpoint; ``repo_id`` may be a local directory."""
+        from pathlib import Path
+        f = Path(repo_id) / filename
+        if not f.exists():
+            from huggingface_hub import hf_hub_download
+            f = Path(hf_hub_download(repo_id, filename))
+        return cls(mimi_202407(32), device=device).load_pytorch_weights(f, strict=True)
+
+    def load_pytorch_weights(self, file, strict: bool = True):
+        """mimi.py:192-262: ``file`` = path of kyutai's safetensors checkpoint (or an already loaded dict)."""
+        if not isinstance(file, dict):
+            from safetensors.torch import load_file
+            file = load_file(str(file))
+        return self.load_weights(self.sanitize_pytorch_weights(file), strict=strict)
+
     def load_weights(self, weights, strict=True):
         P, cfg, dev = dict(weights), self.cfg, self.device
         f = lambda t: t.float().to(dev).contiguous()

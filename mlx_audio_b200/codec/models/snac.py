@@ -46,8 +46,26 @@ class SNAC:
         self._w = None
 
     @classmethod
-    def from_config(cls, config: dict, device="cuda"):
+    def from_config(cls, config, device="cuda"):
+        """snac.py:177-182: ``config`` = path of a config.json (as in the reference) or the already parsed dict."""
+        if not isinstance(config, dict):
+            import json
+            with open(config, "r") as f:
+                config = json.load(f)
         return cls(**config, device=device)
+
+    @classmethod
+    def from_pretrained(cls, repo_id, device="cuda", **kwargs):
+        """snac.py:184-199 for a LOCAL snapshot directory (config.json + model.safetensors, already in the module-tree layout); a hub id
+        is resolved through huggingface_hub only when that package can reach it."""
+        from pathlib import Path
+        path = Path(repo_id)
+        if not path.exists():
+            from huggingface_hub import snapshot_download
+            path = Path(snapshot_download(repo_id=repo_id, allow_patterns=["*.safetensors", "*.json"]))
+        from safetensors.torch import load_file
+        model = cls.from_config(path / "config.json", device=device)
+        return model.load_weights(list(load_file(str(path / "model.safetensors")).items()))
 
     @property
     def sample_rate(self):

@@ -99,3 +99,24 @@ def kokoro_torch():
                   ("decoder.generator.noise_convs.1.weight", (16, 22, 1)), ("decoder.generator.resblocks.0.convs1.0.weight_v", (32, 32, 3)),
                   ("decoder.generator.resblocks.0.alpha1.0", (1, 32, 1)), ("decoder.generator.conv_post.weight_v", (22, 16, 7)),
                   ("decoder.generator.m_source.l_linear.weight", (1, 9))])
+
+
+def mimi_torch():
+    """Key patterns of kyutai's PyTorch Mimi checkpoint that Mimi.load_pytorch_weights (mimi.py:192-262) renames / re-lays-out."""
+    e = [("encoder.model.0.conv.conv.weight", (4, 1, 7)), ("encoder.model.0.conv.conv.bias", (4,)), ("encoder.model.1.block.1.conv.conv.weight", (2, 4, 3)),
+         ("encoder.model.1.block.3.conv.conv.weight", (4, 2, 1)), ("encoder.model.3.conv.conv.weight", (8, 4, 8)), ("encoder.model.4.block.1.conv.conv.bias", (4,)),
+         ("encoder.model.6.conv.conv.weight", (16, 8, 10)), ("encoder.model.9.conv.conv.weight", (32, 16, 12)), ("encoder.model.10.block.3.conv.conv.weight", (32, 16, 1)),
+         ("encoder.model.12.conv.conv.weight", (64, 32, 16)), ("encoder.model.14.conv.conv.weight", (32, 64, 3)),
+         ("decoder.model.0.conv.conv.weight", (64, 32, 7)), ("decoder.model.2.convtr.convtr.weight", (64, 32, 16)), ("decoder.model.2.convtr.convtr.bias", (32,)),
+         ("decoder.model.3.block.1.conv.conv.weight", (16, 32, 3)), ("decoder.model.3.block.3.conv.conv.weight", (32, 16, 1)),
+         ("decoder.model.5.convtr.convtr.weight", (32, 16, 12)), ("decoder.model.6.block.1.conv.conv.bias", (8,)), ("decoder.model.8.convtr.convtr.weight", (16, 8, 10)),
+         ("decoder.model.11.convtr.convtr.weight", (8, 4, 8)), ("decoder.model.12.block.3.conv.conv.weight", (4, 2, 1)), ("decoder.model.14.conv.conv.weight", (1, 4, 3)),
+         ("encoder_transformer.transformer.layers.0.self_attn.in_proj_weight", (96, 32)), ("encoder_transformer.transformer.layers.0.self_attn.out_proj.weight", (32, 32)),
+         ("decoder_transformer.transformer.layers.1.self_attn.in_proj_weight", (96, 32)), ("decoder_transformer.transformer.layers.1.linear1.weight", (64, 32)),
+         ("decoder_transformer.transformer.layers.1.linear2.weight", (32, 64)), ("decoder_transformer.transformer.layers.1.norm1.weight", (32,)),
+         ("decoder_transformer.transformer.layers.1.layer_scale_2.scale", (32,)),
+         ("quantizer.rvq_first.input_proj.weight", (16, 32, 1)), ("quantizer.rvq_first.output_proj.weight", (32, 16, 1)),
+         ("quantizer.rvq_first.vq.layers.0._codebook._initialized", (1,)), ("quantizer.rvq_first.vq.layers.0._codebook.embedding_sum", (64, 16)),
+         ("quantizer.rvq_first.vq.layers.0._codebook.cluster_usage", (64,)), ("quantizer.rvq_rest.vq.layers.2._codebook.embedding_sum", (64, 16)),
+         ("quantizer.rvq_rest.output_proj.weight", (32, 16, 1)), ("downsample.conv.conv.conv.weight", (32, 32, 4)), ("upsample.convtr.convtr.convtr.weight", (32, 1, 4))]
+    return _fill(e)

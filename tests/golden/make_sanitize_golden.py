@@ -58,6 +58,23 @@ def main():
     from oracle.kokoro import KOKORO_CONFIG                          # constants only: the public configuration
     km = K.Model(K.ModelConfig(**json.loads(json.dumps(KOKORO_CONFIG)), vocab={}))
     out["kokoro_torch"] = manifest(km.sanitize({k: mx.array(v) for k, v in L.kokoro_torch().items()}))
+    from mlx_audio.codec.models.mimi import mimi as M
+    captured = {}
+
+    class _Loaded:
+        def filter_and_map(self, fn):
+            return None
+
+    class _Mimi(M.Mimi):                                             # only load_pytorch_weights is exercised: no module tree needed
+        def __init__(self):
+            pass
+
+        def load_weights(self, weights, strict=True):
+            captured.update(dict(weights))
+            return _Loaded()
+    mx.load = lambda f: {k: mx.array(v) for k, v in L.mimi_torch().items()}
+    _Mimi().load_pytorch_weights("synthetic")
+    out["mimi_torch"] = manifest(captured)
     for k, v in out.items():
         print(k, len(v))
     json.dump(out, open(os.path.join(HERE, "sanitize_golden.json"), "w"), indent=0, sort_keys=True)

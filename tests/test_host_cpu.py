@@ -270,7 +270,8 @@ def test_sanitize_matches_what_the_reference_sanitize_returns():
     """tests/golden/sanitize_golden.json = key -> (shape, CRC-32 of the float32 bytes) of the dictionaries the REFERENCE's own sanitize
     functions return for the synthetic hub-layout checkpoints of tests/golden/checkpoint_layouts.py (make_sanitize_golden.py, NumPy standing in
     for MLX): Whisper from a HuggingFace state dict (whisper.py:551-618), Qwen3-TTS Model.sanitize (qwen3_tts.py:2914-2935), the decoder
-    half of Qwen3TTSSpeechTokenizer.sanitize (speech_tokenizer.py:1220-1447) and Kokoro's Model.sanitize (kokoro.py:179-276).  The product's functions must return the same keys, shapes and
+    half of Qwen3TTSSpeechTokenizer.sanitize (speech_tokenizer.py:1220-1447) Kokoro's Model.sanitize (kokoro.py:179-276) and the renaming / re-layout of
+    Mimi.load_pytorch_weights (mimi.py:192-262).  The product's functions must return the same keys, shapes and
     values for the same inputs."""
     import json
     import os
@@ -297,3 +298,19 @@ def test_sanitize_matches_what_the_reference_sanitize_returns():
     assert manifest(Qwen3TTSSpeechTokenizer.sanitize(t(L.qwen3_tokenizer_torch()))) == want["qwen3_tokenizer_decoder"]
     from mlx_audio_b200.tts.models.kokoro.kokoro import Model as Kokoro
     assert manifest(Kokoro.sanitize(Kokoro.__new__(Kokoro), t(L.kokoro_torch()))) == want["kokoro_torch"]
+    from mlx_audio_b200.codec.models.mimi import Mimi
+    assert manifest(Mimi.sanitize_pytorch_weights(t(L.mimi_torch()))) == want["mimi_torch"]
+
+
+def test_codec_constructors_accept_what_the_reference_accepts(tmp_path):
+    """SNAC.from_config takes the path of a config.json (snac.py:177-182) as well as a dict; Mimi exposes load_pytorch_weights /
+    from_pretrained (mimi.py:192-275).  Construction only -- no kernels run."""
+    import json
+    from mlx_audio_b200.codec.models.mimi import Mimi
+    from mlx_audio_b200.codec.models.snac import SNAC
+    cfg = dict(sampling_rate=24000, encoder_dim=48, encoder_rates=[2, 4, 8, 8], decoder_dim=1024, decoder_rates=[8, 8, 4, 2], attn_window_size=None,
+               codebook_size=4096, codebook_dim=8, vq_strides=[4, 2, 1], noise=True, depthwise=True)
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    a, b = SNAC.from_config(str(tmp_path / "config.json"), device="cpu"), SNAC.from_config(cfg, device="cpu")
+    assert a.sample_rate == b.sample_rate == 24000 and list(a.vq_strides) == [4, 2, 1]
+    assert callable(Mimi.load_pytorch_weights) and callable(Mimi.from_pretrained) and callable(SNAC.from_pretrained)
