@@ -32,6 +32,20 @@ class ModelDimensions(BaseModelArgs):
     n_text_head: int = 12
     n_text_layer: int = 12
 
+    @classmethod
+    def from_dict(cls, config: dict) -> "ModelDimensions":
+        """whisper.py:293-322: MLX-format keys (n_mels, ...) are filtered to the known fields; a HuggingFace transformers config
+        (d_model / encoder_layers / ...) is mapped, with the reference's large-v3 defaults for absent keys."""
+        config = dict(config)
+        if "d_model" in config or "encoder_layers" in config:
+            return cls(n_mels=config.get("num_mel_bins", 128), n_audio_ctx=config.get("max_source_positions", 1500),
+                       n_audio_state=config.get("d_model", 1280), n_audio_head=config.get("encoder_attention_heads", 20),
+                       n_audio_layer=config.get("encoder_layers", 32), n_vocab=config.get("vocab_size", 51866),
+                       n_text_ctx=config.get("max_target_positions", 448), n_text_state=config.get("d_model", 1280),
+                       n_text_head=config.get("decoder_attention_heads", 20), n_text_layer=config.get("decoder_layers", 32))
+        known = {f.name for f in cls.__dataclass_fields__.values()}
+        return cls(**{k: v for k, v in config.items() if k in known})
+
 
 ModelConfig = ModelDimensions
 

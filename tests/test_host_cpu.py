@@ -314,3 +314,40 @@ def test_codec_constructors_accept_what_the_reference_accepts(tmp_path):
     a, b = SNAC.from_config(str(tmp_path / "config.json"), device="cpu"), SNAC.from_config(cfg, device="cpu")
     assert a.sample_rate == b.sample_rate == 24000 and list(a.vq_strides) == [4, 2, 1]
     assert callable(Mimi.load_pytorch_weights) and callable(Mimi.from_pretrained) and callable(SNAC.from_pretrained)
+
+
+def test_configs_and_result_contracts_match_the_reference_dataclasses():
+    """tests/golden/config_golden.json = what the REFERENCE's own dataclasses parse / declare (make_config_golden.py): Whisper
+    ModelDimensions.from_dict on MLX- and HuggingFace-format configs, Qwen3-TTS ModelConfig.from_dict (nested talker / code predictor /
+    speaker encoder / tokenizer configs, unknown keys dropped, defaults), Kokoro ModelConfig, and the (name, has-default, default) lists of
+    GenerationResult, BatchGenerationResult, DecodingResult."""
+    import dataclasses
+    import json
+    import os
+    import sys
+    here = os.path.join(os.path.dirname(__file__), "golden")
+    if here not in sys.path:
+        sys.path.insert(0, here)
+    import config_cases as C
+    want = json.load(open(os.path.join(here, "config_golden.json")))
+    from mlx_audio.stt.models.whisper import ModelDimensions
+    for k, v in C.WHISPER_CONFIGS.items():
+        assert dataclasses.asdict(ModelDimensions.from_dict(v)) == want["whisper_dims"][k], k
+    from mlx_audio.tts.models.qwen3_tts.config import ModelConfig as Q
+    for k, v in C.QWEN3_CONFIGS.items():
+        got = json.loads(json.dumps(dataclasses.asdict(Q.from_dict(v))))
+        assert got == want["qwen3_config"][k], (k, {f: (got.get(f), want["qwen3_config"][k].get(f)) for f in set(got) | set(want["qwen3_config"][k])
+                                                   if got.get(f) != want["qwen3_config"][k].get(f)})
+    from mlx_audio.tts.models.kokoro import ModelConfig as KC
+    assert json.loads(json.dumps(dataclasses.asdict(KC.from_dict(C.KOKORO_CONFIG_JSON)))) == want["kokoro_config"]
+
+    def fields(cls):
+        out = []
+        for f in dataclasses.fields(cls):
+            d = None if f.default is dataclasses.MISSING else f.default
+            out.append([f.name, f.default is not dataclasses.MISSING or f.default_factory is not dataclasses.MISSING,
+                        d if isinstance(d, (int, float, str, bool, type(None))) else repr(d)])
+        return out
+    from mlx_audio.tts.models.base import BatchGenerationResult, GenerationResult
+    assert fields(GenerationResult) == want["result_fields"]["GenerationResult"]
+    assert fields(BatchGenerationResult) == want["result_fields"]["BatchGenerationResult"]
