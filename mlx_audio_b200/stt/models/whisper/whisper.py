@@ -7,7 +7,7 @@ q|k|v as one GEMM (the key bias is structurally zero), residual adds in the GEMM
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Optional
 
 import torch
@@ -154,12 +154,47 @@ def get_suppress_tokens(spec: "TokenizerSpec", suppress_tokens=None) -> tuple:
 
 @dataclass
 class DecodingResult:
-    """decoding.py:152-162 (numeric fields; text needs the tokenizer files)."""
+    """decoding.py:152-162, field for field."""
     audio_features: torch.Tensor
-    tokens: list
-    avg_logprob: float
-    no_speech_prob: float
-    temperature: float = 0.0
+    language: str
+    language_probs: Optional[dict] = None
+    tokens: list = field(default_factory=list)
+    text: str = ""
+    avg_logprob: float = float("nan")
+    no_speech_prob: float = float("nan")
+    temperature: float = float("nan")
+    compression_ratio: float = float("nan")
+
+
+@dataclass
+class STTOutput:
+    """whisper.py:272-276."""
+    text: str
+    segments: Optional[list] = None
+    language: Optional[str] = None
+
+
+def compression_ratio(text: str) -> float:
+    """decoding.py:19-21."""
+    import zlib
+    b = text.encode("utf-8")
+    return len(b) / len(zlib.compress(b))
+
+
+def results_from_greedy(tokens, sum_logprobs, no_speech_probs, audio_features, spec: "TokenizerSpec", sample_begin: int, language: str = "en",
+                        temperature: float = 0.0, tokenizer=None):
+    """The tail of DecodingTask.run (decoding.py:664-722) for one candidate per audio: GreedyDecoder.finalize appends an EOT, each row is cut
+    to ``[sample_begin, first EOT)``, avg_logprob = sum_logprob / (len(tokens) + 1); text needs a tokenizer (else "", whose compression ratio is 0.0 as the reference computes it)."""
+    out = []
+    for i, row in enumerate(tokens):
+        row = list(row) + [spec.eot]
+        cut = row[sample_begin:]
+        cut = cut[: cut.index(spec.eot)]
+        text = tokenizer.decode(cut).strip() if tokenizer is not None else ""
+        out.append(DecodingResult(audio_features=audio_features[i], language=language, tokens=cut, text=text,
+                                  avg_logprob=float(sum_logprobs[i]) / (len(cut) + 1), no_speech_prob=float(no_speech_probs[i]),
+                                  temperature=temperature, compression_ratio=compression_ratio(text)))
+    return out
 
 
 class TextDecoder:

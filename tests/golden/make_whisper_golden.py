@@ -1,6 +1,7 @@
 """Golden vectors from the REFERENCE'S OWN Whisper model code (stt/models/whisper/whisper.py: AudioEncoder, TextDecoder with
 its kv-cache protocol), executed in float64 with NumPy standing in for MLX (numpy_mlx_nn.py).  Run from the repo root in the
 build container:  python tests/golden/make_whisper_golden.py   ->  tests/golden/whisper_golden.npz"""
+import json
 import os
 import sys
 
@@ -68,6 +69,10 @@ def decode_cases(model, mel, out):
         tokens, sum_lp, no_speech = task._main_loop(feats, tokens)
         out[f"dec_{tag}_tokens"], out[f"dec_{tag}_sum_logprobs"], out[f"dec_{tag}_no_speech"] = np.asarray(tokens), np.asarray(sum_lp), np.asarray(no_speech)
         print(tag, np.asarray(tokens).tolist(), np.asarray(sum_lp))
+        res = task.run(mx.array(mel))                                # the public result objects (decoding.py:634-722)
+        out[f"dec_{tag}_run"] = json.dumps([dict(language=r.language, tokens=[int(t) for t in r.tokens], text=r.text, avg_logprob=float(r.avg_logprob),
+                                                 no_speech_prob=float(r.no_speech_prob), temperature=float(r.temperature),
+                                                 compression_ratio=float(r.compression_ratio)) for r in res])
     out["dec_suppress"] = np.asarray(suppress)
     # the three logit filters and GreedyDecoder.update applied directly to random logits under hand-built token histories
     tk = StubTokenizer()

@@ -351,3 +351,36 @@ def test_configs_and_result_contracts_match_the_reference_dataclasses():
     from mlx_audio.tts.models.base import BatchGenerationResult, GenerationResult
     assert fields(GenerationResult) == want["result_fields"]["GenerationResult"]
     assert fields(BatchGenerationResult) == want["result_fields"]["BatchGenerationResult"]
+    from mlx_audio_b200.stt.models.whisper.whisper import DecodingResult, STTOutput
+    assert [f[0] for f in fields(DecodingResult)] == [f[0] for f in want["result_fields"]["DecodingResult"]]
+    assert [f[:2] for f in fields(DecodingResult)] == [f[:2] for f in want["result_fields"]["DecodingResult"]]
+    assert fields(STTOutput) == want["result_fields"]["STTOutput"]
+
+
+def test_whisper_decoding_results_are_assembled_like_the_reference_run():
+    """tests/golden/whisper_golden.npz holds, next to the raw loop outputs of the reference's DecodingTask._main_loop, the DecodingResult
+    objects its run() builds from them (decoding.py:664-722).  The product's results_from_greedy must build the same objects from the same
+    loop outputs: token lists cut at the first EOT, avg_logprob = sum / (len + 1), text through the tokenizer, compression ratio."""
+    import json
+    import os
+    import numpy as np
+    import torch
+    from mlx_audio.stt.models.whisper.decoding import DecodingResult, TokenizerSpec
+    from mlx_audio_b200.stt.models.whisper.whisper import results_from_greedy
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "whisper_golden.npz"))
+    spec = TokenizerSpec(eot=200, sot=201, no_timestamps=208, timestamp_begin=209, no_speech=207, blank_ids=(7,), language=202, task=203)
+
+    class Tok:
+        def decode(self, tokens):
+            return " ".join(str(t) for t in tokens)
+    for tag, sb in (("ts", 3), ("nots", 4)):
+        want = json.loads(str(g[f"dec_{tag}_run"]))
+        got = results_from_greedy(g[f"dec_{tag}_tokens"].tolist(), g[f"dec_{tag}_sum_logprobs"], g[f"dec_{tag}_no_speech"], torch.as_tensor(g["xa"]),
+                                  spec, sb, tokenizer=Tok())
+        assert len(got) == len(want) == 2 and all(isinstance(r, DecodingResult) for r in got)
+        for r, w in zip(got, want):
+            assert (r.language, r.tokens, r.text, r.temperature) == (w["language"], w["tokens"], w["text"], w["temperature"])
+            assert abs(r.avg_logprob - w["avg_logprob"]) < 1e-12 and abs(r.no_speech_prob - w["no_speech_prob"]) < 1e-15
+            assert abs(r.compression_ratio - w["compression_ratio"]) < 1e-12
+    from mlx_audio_b200.stt.models.whisper.whisper import compression_ratio
+    assert compression_ratio("") == 0.0
