@@ -368,6 +368,23 @@ class Model:
                 break
         return tokens[:, :cur].cpu().tolist(), sum_lp, no_speech
 
+    def decode(self, mel: torch.Tensor, spec: Optional[TokenizerSpec] = None, sample_len: Optional[int] = None,
+               without_timestamps: bool = False, max_initial_timestamp: Optional[float] = 1.0, tokenizer=None, language: str = "en"):
+        """decoding.decode / DecodingTask.run at temperature 0 (decoding.py:634-765): ``mel`` [.., 3000, n_mels] log-mel windows, or encoder
+        features [.., n_audio_ctx, n_audio_state] which skip the encoder (decoding.py:557-565) -> DecodingResult per window (one object for
+        a single window).  Text needs ``tokenizer`` (anything with ``decode(list[int]) -> str``)."""
+        from .audio import CHUNK_LENGTH
+        spec = spec or TokenizerSpec()
+        single = mel.dim() == 2
+        mel = mel[None] if single else mel
+        dims = self.dims
+        feats = mel if tuple(mel.shape[-2:]) == (dims.n_audio_ctx, dims.n_audio_state) else self.encoder(mel)
+        index = round(max_initial_timestamp / (CHUNK_LENGTH / dims.n_audio_ctx)) if max_initial_timestamp else None
+        tokens, sum_lp, no_speech = self.greedy_decode(feats, spec, sample_len, index, without_timestamps)
+        sample_begin = len(spec.sot_sequence) + (1 if without_timestamps else 0)
+        res = results_from_greedy(tokens, sum_lp.cpu().tolist(), no_speech.cpu().tolist(), feats, spec, sample_begin, language, 0.0, tokenizer)
+        return res[0] if single else res
+
     def embed_audio(self, mel):
         return self.encoder(mel)
 

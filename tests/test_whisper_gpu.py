@@ -108,6 +108,12 @@ def test_whisper_decoder_and_greedy_decode_parity():
     assert tokens == ref_tokens
     assert torch.allclose(lp.cpu().double(), ref_lp, rtol=1e-3, atol=1e-3)
     assert torch.allclose(ns.cpu().double(), ref_ns, rtol=1e-2, atol=1e-30)
+    res = model.decode(xa, TokenizerSpec(suppress=(11, 12)), sample_len=10)          # public result objects (decoding.py:634-722)
+    for r, row, s_lp, s_ns in zip(res, ref_tokens, ref_lp.tolist(), ref_ns.tolist()):
+        cut = (row + [spec.eot])[3:]
+        cut = cut[:cut.index(spec.eot)]
+        assert r.tokens == cut and abs(r.avg_logprob - s_lp / (len(cut) + 1)) < 1e-3 and abs(r.no_speech_prob - s_ns) <= 1e-2 * s_ns + 1e-30
+        assert r.temperature == 0.0 and r.language == "en" and r.text == ""
     # without timestamps the initial sequence carries <|notimestamps|> (decoding.py:463-465) and the timestamp rules are off
     ref_tokens, ref_lp, _ = OW.greedy_decode(P64, xa.double(), spec, sample_len=6, suppress=(11, 12), dims=dims, without_timestamps=True)
     tokens, lp, _ = model.greedy_decode(xa, TokenizerSpec(suppress=(11, 12)), sample_len=6, without_timestamps=True)
