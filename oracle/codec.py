@@ -218,22 +218,28 @@ def mimi_quantizer_decode(P, codes, cfg):
     return out
 
 
-def mimi_transformer(P, pre, x, cfg):
-    """ProjectedTransformer / Transformer (transformer.py:63-261) on NCL x (conv_layout), fresh cache (offset 0)."""
+def mimi_transformer(P, pre, x, cfg, rope_traditional=True, full_causal=False):
+    """ProjectedTransformer / Transformer (transformer.py:63-261) on NCL x (conv_layout), fresh cache (offset 0).  ``full_causal``: the
+    caller passes its own causal mask, which replaces the context-window mask (speech_tokenizer.py:1052-1057); ``rope_traditional`` False
+    rotates the half-split pairs (the Qwen3 tokenizer encoder's setting, :1012)."""
     x = x.transpose(1, 2)
     b, t, d = x.shape
     nh = cfg["num_heads"]
     hd = d // nh
     i, j = torch.arange(t)[:, None], torch.arange(t)[None, :]
-    allowed = (j <= i) & (i - j < cfg["context"])
-    mask = torch.where(allowed, 0.0, -1e9).to(x.dtype)
+    if full_causal:
+        mask = torch.where(j <= i, 0.0, float("-inf")).to(x.dtype)
+    else:
+        allowed = (j <= i) & (i - j < cfg["context"])
+        mask = torch.where(allowed, 0.0, -1e9).to(x.dtype)
+    rope = N.rope_traditional if rope_traditional else N.rope_half
     for li in range(cfg["num_layers"]):
         L = f"{pre}.transformer.layers.{li}"
         n1 = N.layer_norm(x, P[L + ".norm1.weight"], P[L + ".norm1.bias"], 1e-5)
         qkv = N.linear(n1, P[L + ".self_attn.in_proj.weight"]).reshape(b, t, 3, nh, hd)
         q, k, v = (qkv[:, :, n].transpose(1, 2) for n in range(3))
-        q = N.rope_traditional(q, 0, cfg["max_period"])
-        k = N.rope_traditional(k, 0, cfg["max_period"])
+        q = rope(q, 0, cfg["max_period"])
+        k = rope(k, 0, cfg["max_period"])
         a = N.sdpa(q, k, v, hd ** -0.5, mask).transpose(1, 2).reshape(b, t, d)
         a = N.linear(a, P[L + ".self_attn.out_proj.weight"])
         x = x + a * P[L + ".layer_scale_1.scale"].to(x.dtype)
@@ -257,10 +263,10 @@ def mimi_seanet_decoder(P, x, cfg):
     return mimi_causal_conv(P, pre + ".final_conv1d", N.elu(x), cfg["last_ksize"])
 
 
-def mimi_seanet_encoder(P, x, cfg):
+def mimi_seanet_encoder(P, x, cfg, root=""):
     """SeanetEncoder.__call__ (seanet.py:194-199) on NCL x [B,1,n]: init conv, per ratio (reversed) {resnet block, ELU, strided conv
     k = 2r}, ELU, final conv."""
-    pre = "encoder"
+    pre = root + "encoder"
     x = mimi_causal_conv(P, pre + ".init_conv1d", x, cfg["ksize"])
     for li, ratio in enumerate(reversed(cfg["ratios"])):
         L = f"{pre}.layers.{li}"
@@ -270,16 +276,16 @@ def mimi_seanet_encoder(P, x, cfg):
     return mimi_causal_conv(P, pre + ".final_conv1d", N.elu(x), cfg["last_ksize"])
 
 
-def mimi_quantizer_encode(P, x, cfg):
+def mimi_quantizer_encode(P, x, cfg, root=""):
     """SplitResidualVectorQuantizer.encode (quantization.py:178-185,138-141,90-101,37-45): x [B,512,T] -> int64 codes [B,nq,T].
     Nearest code = argmin(|e|^2 / 2 - x.e) on the residual, which is then reduced by the chosen embedding."""
     codes = []
     for name, nq in (("rvq_first", 1), ("rvq_rest", cfg["nq"] - 1)):
         if nq <= 0:
             continue
-        r = N.conv1d(x.transpose(1, 2), P[f"quantizer.{name}.input_proj.weight"].to(x.dtype))          # [B,T,qdim]
+        r = N.conv1d(x.transpose(1, 2), P[f"{root}quantizer.{name}.input_proj.weight"].to(x.dtype))    # [B,T,qdim]
         for li in range(nq):
-            pre = f"quantizer.{name}.vq.layers.{li}.codebook"
+            pre = f"{root}quantizer.{name}.vq.layers.{li}.codebook"
             emb = P[pre + ".embedding_sum"] / torch.clamp(P[pre + ".cluster_usage"], min=1e-5)[:, None]
             idx = ((emb * emb).sum(-1) / 2 - r @ emb.T).argmin(dim=-1)                                  # [B,T]
             r = r - emb[idx]

@@ -122,6 +122,17 @@ def rope_traditional(x, offset, base):
     return out.reshape(b, h, t, d)
 
 
+def rope_half(x, offset, base):
+    """nn.RoPE(dims, traditional=False): rotate the pairs (i, i + D/2); x [B,H,T,D]."""
+    b, h, t, d = x.shape
+    pos = torch.arange(offset, offset + t, dtype=x.dtype)
+    inv = torch.exp(-torch.arange(0, d // 2, dtype=x.dtype) * (math.log(base) / (d // 2)))
+    ang = pos[:, None] * inv[None, :]
+    c, s = torch.cos(ang), torch.sin(ang)
+    x1, x2 = x[..., : d // 2], x[..., d // 2:]
+    return torch.cat([x1 * c - x2 * s, x1 * s + x2 * c], dim=-1)
+
+
 def bf16_round(x: torch.Tensor) -> torch.Tensor:
     """Round-to-nearest-even to bfloat16 and back (the precision a bf16 checkpoint stores)."""
     return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)

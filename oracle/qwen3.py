@@ -509,3 +509,122 @@ def prepare_generation_inputs_from_ids(P, input_ids, tts_ids, cfg_ids, language_
     input_embeds = torch.cat(parts, dim=1)
     trailing = torch.cat([text_embed[:, 4:-5], tts_eos], dim=1)
     return input_embeds, trailing, tts_pad
+
+
+# ------------------------------------------------------------------------------------------------ speaker encoder (ECAPA-TDNN)
+SPEAKER_ENCODER = {   # qwen3_tts/config.py:19-30
+    "mel_dim": 128, "enc_dim": 1024, "enc_channels": [512, 512, 512, 512, 1536], "enc_kernel_sizes": [5, 3, 3, 3, 1],
+    "enc_dilations": [1, 2, 3, 4, 1], "enc_attention_channels": 128, "enc_res2net_scale": 8, "enc_se_channels": 128,
+}
+
+
+def _tdnn(P, pre, x, k, dilation):
+    """TimeDelayNetBlock (speaker_encoder.py:30-61) on NCL x: reflect "same" padding, conv, ReLU."""
+    pad = (k - 1) * dilation // 2
+    y = x.transpose(1, 2)
+    if pad > 0:
+        y = torch.cat([y[:, 1:pad + 1].flip(1), y, y[:, -(pad + 1):-1].flip(1)], dim=1)
+    y = N.conv1d(y, P[pre + ".conv.weight"].to(x.dtype), 1, 0, dilation, 1, P[pre + ".conv.bias"])
+    return torch.relu(y.transpose(1, 2))
+
+
+def speaker_encoder(P, mel, cfg=SPEAKER_ENCODER, pre="speaker_encoder"):
+    """Qwen3TTSSpeakerEncoder.__call__ (speaker_encoder.py:206-306): mel [B,T,128] -> embedding [B,enc_dim].  TDNN, three
+    SE-Res2Net blocks (scale 8: chunk i is convolved after adding the previous chunk's output), concatenation of their outputs,
+    TDNN, attentive statistics pooling (weighted mean | std), 1x1 projection."""
+    ch, ks, dl, sc = cfg["enc_channels"], cfg["enc_kernel_sizes"], cfg["enc_dilations"], cfg["enc_res2net_scale"]
+    x = _tdnn(P, f"{pre}.blocks.0", mel.transpose(1, 2), ks[0], dl[0])
+    feats = []
+    for i in range(1, len(ch) - 1):
+        B_ = f"{pre}.blocks.{i}"
+        r = x
+        y = _tdnn(P, B_ + ".tdnn1", x, 1, 1)
+        outs, prev = [], None
+        for j, c in enumerate(torch.chunk(y, sc, dim=1)):                               # Res2NetBlock (:64-104)
+            prev = c if j == 0 else _tdnn(P, f"{B_}.res2net_block.blocks.{j - 1}", c if j == 1 else c + prev, ks[i], dl[i])
+            outs.append(prev)
+        y = _tdnn(P, B_ + ".tdnn2", torch.cat(outs, dim=1), 1, 1)
+        se = y.mean(dim=2, keepdim=True).transpose(1, 2)                                 # SqueezeExcitationBlock (:107-138)
+        se = torch.relu(N.conv1d(se, P[B_ + ".se_block.conv1.weight"].to(y.dtype), bias=P[B_ + ".se_block.conv1.bias"]))
+        se = torch.sigmoid(N.conv1d(se, P[B_ + ".se_block.conv2.weight"].to(y.dtype), bias=P[B_ + ".se_block.conv2.bias"])).transpose(1, 2)
+        x = y * se + r
+        feats.append(x)
+    x = _tdnn(P, pre + ".mfa", torch.cat(feats, dim=1), ks[-1], dl[-1])
+    eps = 1e-12                                                                          # AttentiveStatisticsPooling (:171-203)
+    mean = x.mean(dim=2, keepdim=True)
+    std = torch.sqrt(x.var(dim=2, unbiased=False, keepdim=True) + eps)
+    a = torch.cat([x, mean.expand_as(x), std.expand_as(x)], dim=1)
+    a = torch.tanh(_tdnn(P, pre + ".asp.tdnn", a, 1, 1))
+    a = N.conv1d(a.transpose(1, 2), P[pre + ".asp.conv.weight"].to(x.dtype), bias=P[pre + ".asp.conv.bias"]).transpose(1, 2)
+    a = torch.softmax(a, dim=2)
+    mean = (a * x).sum(dim=2, keepdim=True)
+    std = torch.sqrt(torch.clamp((a * (x - mean) ** 2).sum(dim=2, keepdim=True), min=eps))
+    pooled = torch.cat([mean, std], dim=1).transpose(1, 2)
+    return N.conv1d(pooled, P[pre + ".fc.weight"].to(x.dtype), bias=P[pre + ".fc.bias"])[:, 0]
+
+
+# ------------------------------------------------------------------------------------------------ speech-tokenizer encoder (ICL)
+TOKENIZER_ENCODER = {   # qwen3_tts/config.py:136-173 in oracle/codec.py's Mimi vocabulary
+    "dimension": 512, "nfilters": 64, "ratios": [8, 6, 5, 4], "ksize": 7, "residual_ksize": 3, "last_ksize": 3, "compress": 2, "d_model": 512,
+    "num_heads": 8, "num_layers": 8, "dim_feedforward": 2048, "context": 250, "max_period": 10000, "layer_scale": 0.01, "nq": 32, "bins": 2048,
+    "qdim": 256, "upsample_stride": 2, "valid_num_quantizers": 16,
+}
+
+
+def tokenizer_encode(P, audio, cfg=TOKENIZER_ENCODER, root="encoder_model."):
+    """Qwen3TTSSpeechTokenizerEncoder.encode (speech_tokenizer.py:1037-1058): audio [B,1,n] -> codes [B,16,ceil(n/1920)].  Mimi's SEANet
+    encoder and split RVQ, with a FULL causal mask (no context window) and half-split RoPE in the transformer; only the first 16 of the
+    32 code books are kept."""
+    from . import codec as OC
+    x = OC.mimi_seanet_encoder(P, audio, cfg, root)
+    x = OC.mimi_transformer(P, root + "encoder_transformer", x, cfg, rope_traditional=False, full_causal=True)
+    s = cfg["upsample_stride"]
+    x = OC.mimi_causal_conv(P, root + "downsample.conv", x, 2 * s, stride=s, pad_mode="edge")
+    return OC.mimi_quantizer_encode(P, x, cfg, root)[:, : cfg["valid_num_quantizers"]]
+
+
+# ------------------------------------------------------------------------------------------------ ICL voice cloning
+def prepare_icl_generation_inputs_from_ids(P, target_ids, ref_ids, ref_codes, tts_ids, cfg_ids, language_id=None, speaker_embed=None, cfg=TALKER):
+    """Model._prepare_icl_generation_inputs (qwen3_tts.py:606-803) after tokenisation and reference encoding.  ``target_ids`` = ids of
+    "<|im_start|>assistant\n{text}<|im_end|>\n<|im_start|>assistant\n", ``ref_ids`` = ids of "<|im_start|>assistant\n{ref_text}<|im_end|>\n",
+    ``ref_codes`` [1, G, T_ref] from the speech-tokenizer encoder, ``speaker_embed`` [1, hidden] (x-vector) or None.
+    -> (input_embeds, trailing_text_hidden = the pad embedding, tts_pad_embed)."""
+    def text_projection(x):
+        h = torch.nn.functional.silu(N.linear(x, P["text_projection.linear_fc1.weight"], P["text_projection.linear_fc1.bias"]))
+        return N.linear(h, P["text_projection.linear_fc2.weight"], P["text_projection.linear_fc2.bias"])
+    te, ce = P["model.text_embedding.weight"], P["model.codec_embedding.weight"]
+    target = torch.as_tensor(target_ids, dtype=torch.int64).reshape(1, -1)
+    ref = torch.as_tensor(ref_ids, dtype=torch.int64).reshape(1, -1)
+    text_ids, ref_text_ids = target[:, 3:-5], ref[:, 3:-2]
+    tts = text_projection(te[torch.tensor([list(tts_ids)])])
+    tts_bos, tts_eos, tts_pad = tts[:, 0:1], tts[:, 1:2], tts[:, 2:3]
+    text_embed = torch.cat([text_projection(te[torch.cat([ref_text_ids, text_ids], dim=1)]), tts_eos], dim=1)
+    codes = torch.as_tensor(ref_codes, dtype=torch.int64)
+    rc = ce[codes[:, 0]]
+    for i in range(cfg["num_code_groups"] - 1):
+        rc = rc + P[f"code_predictor.model.codec_embedding.{i}.weight"][codes[:, i + 1]]
+    codec_icl = torch.cat([ce[torch.tensor([[cfg_ids["codec_bos_id"]]])], rc], dim=1)
+    icl = torch.cat([text_embed + ce[torch.tensor([[cfg_ids["codec_pad_id"]]])], codec_icl + tts_pad], dim=1)   # all text, then all codec
+    if language_id is None:
+        prefill = [cfg_ids["codec_nothink_id"], cfg_ids["codec_think_bos_id"], cfg_ids["codec_think_eos_id"]]
+    else:
+        prefill = [cfg_ids["codec_think_id"], cfg_ids["codec_think_bos_id"], language_id, cfg_ids["codec_think_eos_id"]]
+    parts = [ce[torch.tensor([prefill])]] + ([speaker_embed.reshape(1, 1, -1)] if speaker_embed is not None else []) \
+        + [ce[torch.tensor([[cfg_ids["codec_pad_id"], cfg_ids["codec_bos_id"]]])]]
+    prefix = torch.cat(parts, dim=1)
+    combined = torch.cat([tts_pad.expand(1, prefix.shape[1] - 2, -1), tts_bos], dim=1) + prefix[:, :-1]
+    return torch.cat([text_projection(te[target[:, :3]]), combined, icl], dim=1), tts_pad, tts_pad
+
+
+def decode_icl_generated_codes(PT, gen_codes, ref_codes, cfg=TOKENIZER_DECODER):
+    """Model._decode_icl_generated_codes (qwen3_tts.py:1085-1112): decode [reference codes | generated codes] together, keep the valid
+    length, cut the reference's share ``int(ref_len / total_len * n_samples)`` off the front."""
+    ref_t = torch.as_tensor(ref_codes, dtype=torch.int64).transpose(1, 2)
+    full = torch.cat([ref_t, gen_codes[None]], dim=1)
+    wav, lengths = speech_tokenizer_decode(PT, full, cfg)
+    audio = wav[0]
+    valid = int(lengths[0])
+    if 0 < valid < audio.shape[0]:
+        audio = audio[:valid]
+    cut = int(ref_t.shape[1] / max(full.shape[1], 1) * audio.shape[0])
+    return audio[cut:] if 0 < cut < audio.shape[0] else audio

@@ -56,6 +56,9 @@ def fill(module, prefix="", rule=lambda name: None):
     names = [(prefix + n, v.shape, rule(n)) for n, v in shim.flat_parameters(module)]
     for n, sh, r in names:
         shim.set_parameter(module, n[len(prefix):], synth_params.value(n, sh, r))
+    for m in module.modules():                                       # Mimi codebooks keep a derived embedding table
+        if hasattr(m, "update_in_place"):
+            m.update_in_place()
     return names
 
 
@@ -96,6 +99,13 @@ ORACLE_TOK = {"latent_dim": 32, "codebook_dim": 16, "codebook_size": 80, "decode
               "upsampling_ratios": [2, 2], "sliding_window": 6}
 
 
+TOKENC = dict(hidden_size=32, num_filters=4, upsampling_ratios=[8, 6, 5, 4], intermediate_size=64, num_attention_heads=4, num_key_value_heads=4,
+              num_hidden_layers=2, sliding_window=6, codebook_dim=16, codebook_size=64, num_quantizers=20, head_dim=8)
+ORACLE_TOKENC = {"dimension": 32, "nfilters": 4, "ratios": [8, 6, 5, 4], "ksize": 7, "residual_ksize": 3, "last_ksize": 3, "compress": 2, "d_model": 32,
+                 "num_heads": 4, "num_layers": 2, "dim_feedforward": 64, "context": 6, "max_period": 10000, "layer_scale": 0.01, "nq": 20, "bins": 64,
+                 "qdim": 16, "upsample_stride": 2, "valid_num_quantizers": 16}
+
+
 class CharTokenizer:
     """Stands in for the HF tokenizer: the three chat-template markers are single ids, every other character is one id."""
     MARK = {"<|im_start|>": 1, "<|im_end|>": 2, "assistant": 3, "user": 4, "\n": 5}
@@ -120,10 +130,12 @@ class CharTokenizer:
 
 def tokenizer_cases(out):
     from mlx_audio.tts.models.qwen3_tts import speech_tokenizer as S
-    tok = S.Qwen3TTSSpeechTokenizer(C.Qwen3TTSTokenizerConfig(decoder_config=C.Qwen3TTSTokenizerDecoderConfig(**TOKDEC)))
+    tok = S.Qwen3TTSSpeechTokenizer(C.Qwen3TTSTokenizerConfig(decoder_config=C.Qwen3TTSTokenizerDecoderConfig(**TOKDEC),
+                                                              encoder_config=C.Qwen3TTSTokenizerEncoderConfig(**TOKENC)))
     names = fill(tok, rule=lambda n: "small" if n.endswith((".alpha", ".beta")) else ("scale0.08" if n == "decoder.decoder.6.conv.weight" else None))     # SnakeBeta gains are exp(alpha), exp(beta)
     out["tok_params"] = synth_params.manifest(names)
     out["tok_cfg"] = json.dumps(ORACLE_TOK)
+    out["tok_enc_cfg"] = json.dumps(ORACLE_TOKENC)
     rng = np.random.default_rng(33)
     codes = rng.integers(0, 80, size=(2, 4, 9))                    # [B, n_q, T]
     out["tok_codes"], out["tok_wav"] = codes, np.asarray(tok.decoder(mx.array(codes)))
@@ -133,6 +145,10 @@ def tokenizer_cases(out):
     codes_bt[1, 5:, :] = 0                                         # trailing zero codes shorten the reported length
     wav, lens = tok.decode(mx.array(codes_bt))
     out["tok_codes_bt"], out["tok_decode_wav"], out["tok_decode_lens"] = codes_bt, np.asarray(wav), np.asarray(lens)
+    # encoder (ICL voice cloning): audio -> the first 16 of 20 code books, 5 frames + 300 samples
+    audio = 0.4 * np.random.default_rng(133).standard_normal((2, 1, 5 * 1920 + 300))      # regenerated by the test from the seed
+    out["tok_enc_codes"] = np.asarray(tok.encode(mx.array(audio)))
+    print("tokenizer encode", out["tok_enc_codes"].shape)
     # streaming decoder: two calls of new codes with conv buffers and the transformer kv cache
     tok.decoder.reset_streaming_state()
     parts = [np.asarray(tok.decoder.streaming_step(mx.array(codes[:1, :, :5]))), np.asarray(tok.decoder.streaming_step(mx.array(codes[:1, :, 5:])))]
@@ -218,14 +234,83 @@ def model_cases(out, tok):
     mx.random.queue[:] = []
 
 
+SPK = dict(mel_dim=128, enc_dim=64, enc_channels=[32, 32, 32, 32, 96], enc_kernel_sizes=[5, 3, 3, 3, 1], enc_dilations=[1, 2, 3, 4, 1],
+           enc_attention_channels=16, enc_res2net_scale=4, enc_se_channels=16)
+
+
+def speaker_cases(out):
+    """ECAPA-TDNN speaker encoder on the reference's own 24 kHz mel front end (qwen3_tts.py:64-121, speaker_encoder.py)."""
+    from mlx_audio.tts.models.qwen3_tts import qwen3_tts as Q
+    from mlx_audio.tts.models.qwen3_tts import speaker_encoder as SE
+    enc = SE.Qwen3TTSSpeakerEncoder(C.Qwen3TTSSpeakerEncoderConfig(**SPK))
+    names = fill(enc, prefix="speaker_encoder.")
+    out["spk_params"], out["spk_cfg"] = synth_params.manifest(names), json.dumps(SPK)
+    audio = 0.3 * np.random.default_rng(135).standard_normal((2, 9000))                       # regenerated by the test from the seed
+    mel = Q.mel_spectrogram(mx.array(audio))
+    emb = enc(mel)
+    out["spk_mel"], out["spk_embedding"] = np.asarray(mel), np.asarray(emb)
+    print("speaker", np.asarray(mel).shape, np.asarray(emb).shape)
+    return enc
+
+
+def icl_cases(out, tok_full):
+    """Voice cloning: Model.generate(text, ref_audio, ref_text) on a base model -> _generate_icl (qwen3_tts.py:2200-2510): reference audio
+    through the speech-tokenizer encoder and the ECAPA speaker encoder, in-context prompt, the frame loop with repetition penalty 1.5,
+    joint decode of [reference | generated] codes with the reference's share cut off."""
+    from mlx_audio.tts.models.qwen3_tts import qwen3_tts as Q
+    from mlx_audio.tts.models.qwen3_tts import speech_tokenizer as S
+    Q.load_audio = lambda a, sample_rate=None: a
+    mx.random.strict = False                                         # parameter initialisers draw while the modules are built
+    enc4 = dict(TOKENC, num_quantizers=4)                            # the encoder must emit as many code books as the talker predicts
+    tok = S.Qwen3TTSSpeechTokenizer(C.Qwen3TTSTokenizerConfig(decoder_config=C.Qwen3TTSTokenizerDecoderConfig(**TOKDEC),
+                                                              encoder_config=C.Qwen3TTSTokenizerEncoderConfig(**enc4)))
+    fill(tok, rule=lambda n: "small" if n.endswith((".alpha", ".beta")) else ("scale0.08" if n == "decoder.decoder.6.conv.weight" else None))
+    cfg = C.ModelConfig(talker_config=dict(TALKER), speaker_encoder_config=dict(SPK), tts_model_type="base", tts_pad_token_id=111,
+                        tts_bos_token_id=112, tts_eos_token_id=113)
+    model = Q.Model(cfg)
+    fill(model.talker)
+    fill(model.speaker_encoder, prefix="speaker_encoder.")
+    eos, gain = TALKER["codec_eos_token_id"], float(out["gen_eos_gain"])
+    w = np.array(model.talker.codec_head.weight)
+    w[eos] *= gain
+    model.talker.codec_head.weight = mx.array(w)
+    model.load_speech_tokenizer(tok)
+    model.tokenizer = CharTokenizer()
+    mx.random.strict = True
+    for tag, seed in (("a", 46), ("b", 48)):                         # a: runs to max_tokens and contains a zero first code (shorter valid length); b: EOS
+        rng = np.random.default_rng(seed)
+        ref_audio = 0.3 * rng.standard_normal(3 * 1920 + 500)
+        max_tokens, g = 10, TALKER["num_code_groups"]
+        us = rng.random((max_tokens, g))
+        model.tokenizer.calls.clear()
+        model._icl_cache.clear()
+        ie, tr, pad, ref_codes = model._prepare_icl_generation_inputs("Clone me.", mx.array(ref_audio), "Reference words", language="german")
+        calls = list(model.tokenizer.calls)
+        model._icl_cache.clear()
+        mx.random.queue[:] = [("categorical", np.array([v])) for v in us.reshape(-1)]
+        res = list(model.generate(text="Clone me.", ref_audio=mx.array(ref_audio), ref_text="Reference words", lang_code="german", max_tokens=max_tokens))
+        out[f"icl_{tag}_meta"] = json.dumps({"text": "Clone me.", "ref_text": "Reference words", "lang_code": "german", "max_tokens": max_tokens,
+                                             "ref_ids": calls[0], "target_ids": calls[1], "draws_left": len(mx.random.queue), "enc_nq": 4,
+                                             "repetition_penalty": 1.5, "token_count": int(res[0].token_count), "seed": seed})
+        out[f"icl_{tag}_ref_codes"] = np.asarray(ref_codes)            # ref_audio and u: default_rng(seed) replayed by the test
+        out[f"icl_{tag}_input_embeds"], out[f"icl_{tag}_audio"] = np.asarray(ie), np.asarray(res[0].audio)
+        out[f"icl_{tag}_speaker_embed"] = np.asarray(model.extract_speaker_embedding(mx.array(ref_audio)))
+        print("icl", tag, "ref codes", np.asarray(ref_codes).shape, "prompt", np.asarray(ie).shape, "audio", res[0].audio.shape, "tokens", res[0].token_count,
+              "draws left", len(mx.random.queue))
+    mx.random.queue[:] = []
+    mx.random.strict = False
+
+
 def main():
     out = {"cfg": json.dumps(ORACLE_CFG)}
     talker_cases(out)
+    speaker_cases(out)
     tok = tokenizer_cases(out)
     model_cases(out, tok)
+    icl_cases(out, tok)
     out.pop("tok_stream_wav", None)
     for k in list(out):                                              # waveforms are stored as float32 (|x| <= 1: 6e-8 absolute)
-        if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith("batch_audio_"):
+        if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith("batch_audio_"):   # (inputs are named *_pcm_in and stay float64)
             out[k] = np.asarray(out[k], dtype=np.float32)
     np.savez_compressed(os.path.join(HERE, "qwen3_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})

@@ -466,3 +466,45 @@ def test_oracle_whisper_decoding_matches_the_reference_decoding_code():
         tok, slp, ns = OW.greedy_decode(P, xa, spec, sample_len=14, suppress=sup, dims=dims, max_initial_timestamp_index=2, without_timestamps=wt)
         assert np.array_equal(np.array(tok), g[f"dec_{tag}_tokens"]), tag
         assert np.abs(slp.numpy() - g[f"dec_{tag}_sum_logprobs"]).max() < 1e-11 and np.abs(ns.numpy() - g[f"dec_{tag}_no_speech"]).max() < 1e-12
+
+
+def test_oracle_qwen3_voice_cloning_matches_the_reference_model_code():
+    """qwen3_golden.npz, voice-cloning entries = the reference's own code EXECUTED (make_qwen3_golden.py): the ECAPA-TDNN speaker encoder on
+    the 24 kHz mel front end (speaker_encoder.py, qwen3_tts.py:64-121,285-324), the speech-tokenizer ENCODER (speech_tokenizer.py:957-1058:
+    Mimi SEANet encoder, full-causal half-split-RoPE transformer, replicate-padded stride-2 conv, split RVQ, first 16 of 20 code books) and
+    two whole ``Model.generate(text, ref_audio, ref_text)`` runs on a base model (-> _generate_icl, qwen3_tts.py:2200-2510): in-context prompt,
+    frame loop with repetition penalty 1.5, joint decode of [reference | generated] codes with the reference's share cut off -- one run
+    reaching EOS, one whose first-code-book zero shortens the valid length (the ``codes > 0`` rule of speech_tokenizer.py:1113-1116)."""
+    import json
+    from oracle import dsp as D
+    from oracle import qwen3 as Q
+    g, _ = _golden("qwen3_golden.npz")
+    import synth_params
+    cfg, tcfg, ecfg, scfg = (json.loads(str(g[k])) for k in ("cfg", "tok_cfg", "tok_enc_cfg", "spk_cfg"))
+    P, PT, PS = ({k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g[n]).items()} for n in ("talker_params", "tok_params", "spk_params"))
+    audio = 0.4 * np.random.default_rng(133).standard_normal((2, 1, 5 * 1920 + 300))
+    codes = Q.tokenizer_encode(PT, torch.as_tensor(audio), ecfg)
+    assert tuple(codes.shape) == (2, 16, 6) and np.array_equal(codes.numpy(), g["tok_enc_codes"])
+    spk_audio = 0.3 * np.random.default_rng(135).standard_normal((2, 9000))
+    assert np.abs(np.asarray(D.qwen3_mel_spectrogram(spk_audio)) - g["spk_mel"]).max() < 5e-5     # the oracle's filterbank emulates float32
+    assert np.abs(Q.speaker_encoder(PS, torch.as_tensor(g["spk_mel"]), scfg).numpy() - g["spk_embedding"]).max() < 1e-12
+    P["codec_head.weight"] = P["codec_head.weight"].clone()
+    P["codec_head.weight"][cfg["codec_eos_token_id"]] *= float(g["gen_eos_gain"])
+    ids = dict(codec_nothink_id=1004, codec_think_id=1003, codec_think_bos_id=1005, codec_think_eos_id=1006, codec_pad_id=1001, codec_bos_id=1002)
+    lengths = []
+    for t in "ab":
+        m = json.loads(str(g[f"icl_{t}_meta"]))
+        rng = np.random.default_rng(m["seed"])
+        ref_audio, us = 0.3 * rng.standard_normal(3 * 1920 + 500), rng.random((m["max_tokens"], 4))
+        rc = Q.tokenizer_encode(PT, torch.as_tensor(ref_audio)[None, None], dict(ecfg, nq=m["enc_nq"]))
+        assert np.array_equal(rc.numpy(), g[f"icl_{t}_ref_codes"])
+        se = Q.speaker_encoder(PS, torch.as_tensor(np.asarray(D.qwen3_mel_spectrogram(ref_audio))).double(), scfg)
+        assert np.abs(se.numpy() - g[f"icl_{t}_speaker_embed"]).max() < 1e-5
+        ie, tr, pad = Q.prepare_icl_generation_inputs_from_ids(P, m["target_ids"], m["ref_ids"], rc, (112, 113, 111), ids, 1011,
+                                                               torch.as_tensor(g[f"icl_{t}_speaker_embed"]), cfg)
+        assert np.abs(ie.numpy() - g[f"icl_{t}_input_embeds"]).max() < 1e-12
+        gen = Q.generate_codes(P, ie, tr, pad, torch.as_tensor(us), m["max_tokens"], repetition_penalty=m["repetition_penalty"], cfg=cfg)
+        wav = Q.decode_icl_generated_codes(PT, gen, rc, tcfg).numpy()
+        assert gen.shape[0] == m["token_count"] and wav.shape == g[f"icl_{t}_audio"].shape and np.abs(wav - g[f"icl_{t}_audio"]).max() < 2e-7
+        lengths.append(wav.shape[0])
+    assert lengths == [17829, 7680]
