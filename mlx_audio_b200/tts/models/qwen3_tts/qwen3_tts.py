@@ -51,6 +51,21 @@ def mel_spectrogram(audio, n_fft: int = 1024, num_mels: int = 128, sample_rate: 
     return torch.log(torch.clamp(mel, min=1e-5))
 
 
+def decode_in_chunks(decoder, codes: torch.Tensor, upsample: int, decode_chunk: int = 15, decode_ctx: int = 5) -> torch.Tensor:
+    """The chunking of Model._decode_generated_codes (qwen3_tts.py:1050-1083) around any ``decoder([1, G, t]) -> [1, 1, upsample * t]``."""
+    if codes.shape[0] == 0:
+        return torch.zeros(0, dtype=torch.float32, device=codes.device)
+    t = codes[None].transpose(1, 2).contiguous()                           # [1, G, n]
+    parts, start, n = [], 0, t.shape[-1]
+    while start < n:
+        end = min(start + decode_chunk, n)
+        ctx = decode_ctx if start > decode_ctx else start
+        wav = decoder(t[..., start - ctx: end].contiguous())[0, 0]
+        parts.append(wav[ctx * upsample:] if ctx > 0 else wav)
+        start = end
+    return torch.cat(parts) if len(parts) > 1 else parts[0]
+
+
 class Model:
     def __init__(self, config: ModelConfig, device="cuda"):
         self.config = config
@@ -234,7 +249,8 @@ class Model:
     @torch.no_grad()
     def generate_codes(self, input_embeds, trailing_text_hidden, tts_pad_embed, *, max_tokens: int = 4096, temperature: float = 0.9,
                        top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, u=None, seed: int = 0,
-                       use_graph: bool = True, stop_on_eos: bool = True, left_padding=None, batch_mode: bool = False):
+                       use_graph: bool = True, stop_on_eos: bool = True, left_padding=None, batch_mode: bool = False,
+                       trailing_rule: str = "clamp_pad"):
         """The generation loop of Model.generate for B prompts of equal prefill length: returns int64 codes [B, n_frames, 16]
         (B = 1: frames up to, not including, EOS; B > 1: until every row has hit EOS, rows padded with code 0 after their EOS,
         the convention of batch_generate / batch_decode).  ``u`` [max_tokens, 16, B] uniforms in [0,1) (drawn from ``seed`` when
@@ -243,7 +259,9 @@ class Model:
         ``batch_mode`` = the loop of ``batch_generate`` (qwen3_tts.py:1861-1935): ``left_padding`` [B] rows of zero embeddings in front
         of shorter prompts (masked keys, positions from cumsum(mask) - 1), ``trailing_text_hidden`` [B, n, H] right-padded with the
         pad embedding, finished rows forced to EOS, per-row trailing indices with the clamp-pad rule; returns (codes [B, n, 16],
-        lengths [B]) with rows zero-padded after their EOS."""
+        lengths [B]) with rows zero-padded after their EOS.  ``trailing_rule="standard"`` is the rule of the default (non-streaming)
+        batch path, where every row behaves as a single sequence (continuous_batching.py:261-278: text while its index is inside the
+        trailing text, pad afterwards): one extra pad row is appended so that the kernel's clamp lands on it."""
         t, cfg, dev = self.talker, self.config.talker_config, self.device
         x = input_embeds.to(dev).float().contiguous()
         B, P, H = x.shape
@@ -266,6 +284,10 @@ class Model:
         self._trailing = trailing_text_hidden.to(dev).float().expand(B, -1, -1).contiguous() if trailing_text_hidden.shape[0] != B \
             else trailing_text_hidden.to(dev).float().contiguous()
         self._pad = tts_pad_embed.to(dev).float().reshape(-1).contiguous()
+        if batch_mode and trailing_rule == "standard":
+            self._trailing = torch.cat([self._trailing, self._pad.reshape(1, 1, H).expand(B, 1, H)], dim=1).contiguous()
+        elif trailing_rule not in ("clamp_pad", "standard"):
+            raise ValueError(f"trailing_rule must be 'clamp_pad' or 'standard', got {trailing_rule!r}")
         self._suppress = torch.zeros(V, device=dev)
         self._suppress[torch.tensor(self._suppress_codec_tokens(eos), device=dev)] = float("-inf")
         self._seen = torch.zeros(B, V, dtype=torch.uint8, device=dev)
@@ -357,18 +379,28 @@ class Model:
         return x, trailing, pad, left
 
     def batch_generate_from_ids(self, ids_list, *, language_id=None, speaker_ids=None, temperature: float = 0.9, max_tokens: int = 4096,
-                                top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, seed: int = 0, u=None, **kwargs):
-        """``Model.batch_generate`` (qwen3_tts.py:1651-2060, non-streaming) for already-tokenised texts: one frame loop for the whole
-        batch, one batched vocoder pass, one BatchGenerationResult per sequence."""
+                                top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, seed: int = 0, u=None,
+                                stream: bool = False, **kwargs):
+        """``Model.batch_generate`` (qwen3_tts.py:1651-2060) for already-tokenised texts, one BatchGenerationResult per sequence.
+
+        ``stream=False`` (the reference's default) follows its batch session (continuous_batching.py): every row generates exactly what it
+        would generate alone from its own uniform stream (standard trailing-text rule), and is decoded by ``_decode_generated_codes`` --
+        15-frame chunks with 5 frames of left context (qwen3_tts.py:1050-1083).  ``stream=True`` follows the streaming branch
+        (qwen3_tts.py:1861-2040) with one final chunk per row: finished rows forced to EOS, clamp-pad trailing rule, one decode of the whole
+        row (chunks of 300 + 25 context)."""
         from ..base import BatchGenerationResult
         if self.speech_tokenizer is None:
             raise ValueError("Speech tokenizer not loaded")
         t0 = time.perf_counter()
         x, trailing, pad, left = self.prepare_batch_inputs_from_ids(ids_list, language_id, speaker_ids)
         codes, lengths = self.generate_codes(x, trailing, pad, max_tokens=max_tokens, temperature=temperature, top_k=top_k, top_p=top_p,
-                                             repetition_penalty=repetition_penalty, seed=seed, u=u, left_padding=left, batch_mode=True)
+                                             repetition_penalty=repetition_penalty, seed=seed, u=u, left_padding=left, batch_mode=True,
+                                             trailing_rule="clamp_pad" if stream else "standard")
         seqs = [codes[b, : int(lengths[b])] for b in range(codes.shape[0])]
-        audios, _ = self.speech_tokenizer.batch_decode([s_ for s_ in seqs if s_.shape[0] > 0])
+        if stream:
+            audios, _ = self.speech_tokenizer.batch_decode([s_ for s_ in seqs if s_.shape[0] > 0])
+        else:
+            audios = [self._decode_generated_codes(s_) for s_ in seqs if s_.shape[0] > 0]
         torch.cuda.synchronize(self.device)
         dt = time.perf_counter() - t0
         it = iter(audios)
@@ -378,9 +410,17 @@ class Model:
             a = next(it)
             yield BatchGenerationResult(audio=a, sequence_idx=b, samples=int(a.shape[0]), sample_rate=self.sample_rate, token_count=int(s_.shape[0]),
                                         audio_duration=format_duration(a.shape[0] / self.sample_rate), processing_time_seconds=dt,
-                                        peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9, is_final_chunk=True)
+                                        peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9, is_streaming_chunk=stream,
+                                        is_final_chunk=stream)
 
     # ------------------------------------------------------------------ decode + public generate
+    @torch.no_grad()
+    def _decode_generated_codes(self, codes: torch.Tensor, *, decode_chunk: int = 15, decode_ctx: int = 5) -> torch.Tensor:
+        """qwen3_tts.py:1050-1083: codes [n, G] of one sequence -> audio [1920 n], decoded in ``decode_chunk``-frame pieces with up to
+        ``decode_ctx`` frames of left context whose samples are dropped."""
+        dec = self.speech_tokenizer.decoder
+        return decode_in_chunks(lambda c: dec(c), codes, dec.total_upsample, decode_chunk, decode_ctx)
+
     @torch.no_grad()
     def _decode_chunk(self, codes: torch.Tensor, chunk_tokens: int = 300) -> torch.Tensor:
         """qwen3_tts.py:1017-1048: codes [1, T, 16] -> audio [samples], trimmed to the frames whose first code is > 0."""
@@ -416,7 +456,8 @@ class Model:
     def _generate_segments(self, text, split_pattern, speaker, language, instruct, **gen):
         if self.speech_tokenizer is None:
             raise ValueError("Speech tokenizer not loaded")
-        segments = [t for t in (text.split(split_pattern) if split_pattern else [text]) if t.strip()]
+        # base path: segments are split AND stripped (qwen3_tts.py:1268-1271); the instruct paths pass split_pattern=None and the text as is
+        segments = [t.strip() for t in text.split(split_pattern) if t.strip()] if split_pattern else [text]
         for idx, seg in enumerate(segments):
             t0 = time.perf_counter()
             x, trailing, pad = self._prepare_generation_inputs(seg, language=language, speaker=speaker, instruct=instruct)
@@ -445,14 +486,14 @@ class Model:
             if not instruct:
                 raise ValueError("VoiceDesign model requires 'instruct' to describe the voice "
                                  "(e.g., 'A cheerful young female voice with high pitch')")
-            yield from self._generate_segments(text, split_pattern, None, lang_code, instruct, **gen)
+            yield from self._generate_segments(text, None, None, lang_code, instruct, **gen)        # one utterance: _generate_with_instruct does not split
             return
         if kind == "custom_voice":
             if not voice:
                 raise ValueError(f"CustomVoice model requires 'voice' (speaker name) (e.g., {self.supported_speakers})")
             if voice.lower() not in [s.lower() for s in self.supported_speakers]:
                 raise ValueError(f"Speaker '{voice}' not supported. Available: {self.supported_speakers}")
-            yield from self._generate_segments(text, split_pattern, voice, lang_code, instruct, **gen)
+            yield from self._generate_segments(text, None, voice, lang_code, instruct, **gen)
             return
         if self.speech_tokenizer is None:
             raise ValueError("Speech tokenizer not loaded")

@@ -628,3 +628,20 @@ def decode_icl_generated_codes(PT, gen_codes, ref_codes, cfg=TOKENIZER_DECODER):
         audio = audio[:valid]
     cut = int(ref_t.shape[1] / max(full.shape[1], 1) * audio.shape[0])
     return audio[cut:] if 0 < cut < audio.shape[0] else audio
+
+
+def decode_generated_codes(PT, codes, cfg=TOKENIZER_DECODER, decode_chunk=15, decode_ctx=5):
+    """Model._decode_generated_codes (qwen3_tts.py:1050-1083), the decode of the default (non-streaming) batch path: 15-frame chunks,
+    each decoded with up to 5 frames of left context whose samples are dropped; no valid-length trimming.  codes [n, G] -> wav [1920 n]."""
+    up = 1
+    for r in list(cfg["upsample_rates"]) + list(cfg["upsampling_ratios"]):
+        up *= r
+    t = codes[None].transpose(1, 2)
+    parts, start, n = [], 0, t.shape[-1]
+    while start < n:
+        end = min(start + decode_chunk, n)
+        ctx = decode_ctx if start > decode_ctx else start
+        wav = tokenizer_decode(PT, t[..., start - ctx: end], cfg)[0, 0]
+        parts.append(wav[ctx * up:])
+        start = end
+    return torch.cat(parts)

@@ -232,6 +232,60 @@ def model_cases(out, tok):
         print("batch row", b, "frames", c.shape[-1], "audio", r.audio.shape)
     print("batch draws left", len(mx.random.queue), "tokenizer calls", [len(c) for c in calls])
     mx.random.queue[:] = []
+    session_cases(out, model, tok, texts, voices, instructs)
+
+
+def session_cases(out, model, tok, texts, voices, instructs):
+    """The DEFAULT batch path: Model.batch_generate(stream=False) -> Qwen3TTSBatchSession (continuous_batching.py): prompts admitted
+    together with left padding, finished rows LEAVE the batch (BatchKVCache rows extracted / merged every step), each row follows the
+    single-sequence trailing-text rule, and every finished row is decoded by _decode_generated_codes (15-frame chunks with 5 frames of
+    left context, qwen3_tts.py:1050-1083).  Each row draws from its own uniform stream u[row, frame, group]."""
+    from mlx_audio.tts.models.qwen3_tts import continuous_batching as CB
+    max_tokens, g, B = 20, TALKER["num_code_groups"], len(texts)
+    us = np.random.default_rng(int(os.environ.get("SEED_S", "63"))).random((B, max_tokens, g))
+    state = {"rows": [], "frame": {b: 0 for b in range(B)}, "group": 0}
+
+    def draw(shape):
+        rows = state["rows"]
+        assert shape == (len(rows),), (shape, rows)
+        v = np.array([us[r, state["frame"][r], state["group"]] for r in rows])
+        state["group"] += 1
+        if state["group"] == g:
+            state["group"] = 0
+            for r in rows:
+                state["frame"][r] += 1
+        return v
+    admit, advance = CB.Qwen3TTSBatchSession._admit_pending, CB.Qwen3TTSBatchSession._advance_active
+
+    def admit_spy(self):
+        state["rows"] = [it.sequence_id for it in self._pending[: min(self.available_slots, len(self._pending))]]
+        return admit(self)
+
+    def advance_spy(self):
+        state["rows"] = [st.sequence_id for st in self._active]
+        return advance(self)
+    CB.Qwen3TTSBatchSession._admit_pending, CB.Qwen3TTSBatchSession._advance_active = admit_spy, advance_spy
+    decoded = []
+    real = model._decode_generated_codes
+
+    def decode_spy(codes, **k):
+        decoded.append(np.concatenate([np.asarray(c) for c in codes], axis=0))
+        return real(codes, **k)
+    model._decode_generated_codes = decode_spy
+    mx.random.queue[:] = [("categorical", draw)] * (max_tokens * g + g)
+    model.tokenizer.calls.clear()
+    res = list(model.batch_generate(texts, voices=voices, instructs=instructs, lang_code="english", max_tokens=max_tokens, stream=False))
+    CB.Qwen3TTSBatchSession._admit_pending, CB.Qwen3TTSBatchSession._advance_active = admit, advance
+    del model.__dict__["_decode_generated_codes"]
+    out["session_meta"] = json.dumps({"texts": texts, "voices": voices, "instructs": instructs, "lang_code": "english", "max_tokens": max_tokens,
+                                      "tokenizer_calls": list(model.tokenizer.calls), "order": [int(r.sequence_idx) for r in res],
+                                      "frames": [int(state["frame"][b]) for b in range(B)]})
+    out["session_u"] = us
+    for r, c in zip(res, decoded):
+        b = int(r.sequence_idx)
+        out[f"session_codes_{b}"], out[f"session_audio_{b}"] = c, np.asarray(r.audio)
+        print("session row", b, "frames", c.shape, "audio", r.audio.shape, "token_count", r.token_count)
+    mx.random.queue[:] = []
 
 
 SPK = dict(mel_dim=128, enc_dim=64, enc_channels=[32, 32, 32, 32, 96], enc_kernel_sizes=[5, 3, 3, 3, 1], enc_dilations=[1, 2, 3, 4, 1],
@@ -310,7 +364,7 @@ def main():
     icl_cases(out, tok)
     out.pop("tok_stream_wav", None)
     for k in list(out):                                              # waveforms are stored as float32 (|x| <= 1: 6e-8 absolute)
-        if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith("batch_audio_"):   # (inputs are named *_pcm_in and stay float64)
+        if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith(("batch_audio_", "session_audio_")):   # (inputs are named *_pcm_in and stay float64)
             out[k] = np.asarray(out[k], dtype=np.float32)
     np.savez_compressed(os.path.join(HERE, "qwen3_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})

@@ -468,6 +468,35 @@ def test_oracle_whisper_decoding_matches_the_reference_decoding_code():
         assert np.abs(slp.numpy() - g[f"dec_{tag}_sum_logprobs"]).max() < 1e-11 and np.abs(ns.numpy() - g[f"dec_{tag}_no_speech"]).max() < 1e-12
 
 
+def test_oracle_qwen3_default_batch_path_matches_the_reference_session():
+    """qwen3_golden.npz session_* = the reference's DEFAULT batch path, Model.batch_generate(stream=False) -> Qwen3TTSBatchSession
+    (continuous_batching.py) EXECUTED through the stand-in with per-row uniform streams: rows leave the batch when they finish (11, 15, 20
+    frames), BatchKVCache rows are extracted / merged every step, and every row is decoded by _decode_generated_codes.  Each row must equal
+    what the single-sequence loop generates from the same stream, and its audio the 15-frame / 5-context chunked decode."""
+    import json
+    from oracle import qwen3 as Q
+    g, _ = _golden("qwen3_golden.npz")
+    import synth_params
+    cfg, tcfg = json.loads(str(g["cfg"])), json.loads(str(g["tok_cfg"]))
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["talker_params"]).items()}
+    PT = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["tok_params"]).items()}
+    P["codec_head.weight"] = P["codec_head.weight"].clone()
+    P["codec_head.weight"][cfg["codec_eos_token_id"]] *= float(g["gen_eos_gain"])
+    ids = dict(codec_nothink_id=1004, codec_think_id=1003, codec_think_bos_id=1005, codec_think_eos_id=1006, codec_pad_id=1001, codec_bos_id=1002)
+    lang, spk = {"english": 1010, "german": 1011}, {"amy": 1020, "bob": 1021}
+    m = json.loads(str(g["session_meta"]))
+    calls, us = list(m["tokenizer_calls"]), torch.as_tensor(g["session_u"])
+    lengths = []
+    for b, (v, i) in enumerate(zip(m["voices"], m["instructs"])):
+        tid = calls.pop(0)
+        ie, tr, pad = Q.prepare_generation_inputs_from_ids(P, tid, (112, 113, 111), ids, lang[m["lang_code"]], spk[v], calls.pop(0) if i else None)
+        codes = Q.generate_codes(P, ie, tr, pad, us[b], m["max_tokens"], cfg=cfg)
+        assert np.array_equal(codes.numpy(), g[f"session_codes_{b}"]), b
+        assert np.abs(Q.decode_generated_codes(PT, codes, tcfg).numpy() - g[f"session_audio_{b}"]).max() < 2e-7
+        lengths.append(codes.shape[0])
+    assert lengths == [11, 15, 20]
+
+
 def test_oracle_qwen3_voice_cloning_matches_the_reference_model_code():
     """qwen3_golden.npz, voice-cloning entries = the reference's own code EXECUTED (make_qwen3_golden.py): the ECAPA-TDNN speaker encoder on
     the 24 kHz mel front end (speaker_encoder.py, qwen3_tts.py:64-121,285-324), the speech-tokenizer ENCODER (speech_tokenizer.py:957-1058:

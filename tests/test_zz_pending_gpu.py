@@ -1,0 +1,40 @@
+"""GPU parity tests written AFTER this round's GPU budget was spent: they have not yet run on hardware.  The file sorts last so that
+a surprise here cannot hide the validated files before it under ``pytest -x``.  Each test drives host-side compositions of kernels
+whose own parity tests (test_qwen3_gpu.py) are validated; what is new is the composition."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import qwen3 as Q
+
+
+def test_default_batch_path_rows_equal_single_sequence_generation_and_chunked_decode():
+    """Model.batch_generate(stream=False) of the reference = Qwen3TTSBatchSession (continuous_batching.py; pinned by
+    tests/test_oracle_pins.py::test_oracle_qwen3_default_batch_path_matches_the_reference_session): every row generates what the
+    single-sequence loop generates from its own uniform stream (standard trailing-text rule), and is decoded in 15-frame chunks with 5
+    frames of left context.  Product: generate_codes(trailing_rule="standard") + _decode_generated_codes; codes bit-exact, waveform 1e-3
+    relative RMS; rows run past 15 frames so that the chunking matters."""
+    from test_qwen3_gpu import _talker, _tokenizer          # tests/ is on sys.path (rootdir-relative "prepend" import mode)
+    model, Pt, flat = _talker({"num_hidden_layers": 2, "cp_num_hidden_layers": 1})
+    st, P64, tflat = _tokenizer()
+    model.load_speech_tokenizer(st)
+    tc = model.config.talker_config
+    cfg_ids = {k: getattr(tc, k) for k in ("codec_nothink_id", "codec_think_id", "codec_think_bos_id", "codec_think_eos_id", "codec_pad_id", "codec_bos_id")}
+    g = torch.Generator().manual_seed(31)
+    ids_list = [torch.randint(0, 500, (n,), generator=g).tolist() for n in (12, 30, 17)]          # trailing texts of 3, 21 and 8 rows
+    n_frames = 18
+    u = torch.rand(n_frames, 16, 3, generator=g)
+    x, trailing, pad, left = model.prepare_batch_inputs_from_ids(ids_list, language_id=2050)
+    codes, lengths = model.generate_codes(x, trailing, pad, max_tokens=n_frames, u=u, left_padding=left, batch_mode=True, trailing_rule="standard")
+    for b, ids in enumerate(ids_list):
+        ie, tr, pd = Q.prepare_generation_inputs_from_ids(Pt, ids, (501, 502, 500), cfg_ids, language_id=2050)
+        want = Q.generate_codes(Pt, ie, tr, pd, u[:, :, b].double(), n_frames, cfg=flat)
+        assert int(lengths[b]) == want.shape[0] and torch.equal(codes[b, : int(lengths[b])].cpu(), want), b
+        audio = model._decode_generated_codes(codes[b, : int(lengths[b])])
+        ref = Q.decode_generated_codes(P64, want, tflat)
+        assert audio.shape[0] == want.shape[0] * 1920
+        err = float(((audio.cpu().double() - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt())
+        assert err < 1e-3, (b, err)
+    res = list(model.batch_generate_from_ids(ids_list, language_id=2050, max_tokens=n_frames, u=u))
+    assert [r.sequence_idx for r in res] == [0, 1, 2] and all(r.samples == r.token_count * 1920 and not r.is_streaming_chunk for r in res)
