@@ -272,4 +272,7 @@ def test_batch_generate_from_ids_results():
     res = list(model.batch_generate_from_ids(ids_list, max_tokens=4, seed=3))
     assert [r.sequence_idx for r in res] == [0, 1]
     for r in res:
-        assert r.sample_rate == 24000 and r.token_count == 4 and r.samples == r.audio.shape[0] == 4 * 1920 and r.is_final_chunk
+        assert r.sample_rate == 24000 and r.token_count == 4 and r.samples == r.audio.shape[0] == 4 * 1920
+        assert not r.is_streaming_chunk and not r.is_final_chunk         # the default path's events carry neither flag (continuous_batching.py:326-344)
+    res = list(model.batch_generate_from_ids(ids_list, max_tokens=4, seed=3, stream=True))
+    assert [r.sequence_idx for r in res] == [0, 1] and all(r.is_streaming_chunk and r.is_final_chunk and r.samples == 4 * 1920 for r in res)
