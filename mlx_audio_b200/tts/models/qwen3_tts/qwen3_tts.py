@@ -51,21 +51,6 @@ def mel_spectrogram(audio, n_fft: int = 1024, num_mels: int = 128, sample_rate: 
     return torch.log(torch.clamp(mel, min=1e-5))
 
 
-def decode_in_chunks(decoder, codes: torch.Tensor, upsample: int, decode_chunk: int = 15, decode_ctx: int = 5) -> torch.Tensor:
-    """The chunking of Model._decode_generated_codes (qwen3_tts.py:1050-1083) around any ``decoder([1, G, t]) -> [1, 1, upsample * t]``."""
-    if codes.shape[0] == 0:
-        return torch.zeros(0, dtype=torch.float32, device=codes.device)
-    t = codes[None].transpose(1, 2).contiguous()                           # [1, G, n]
-    parts, start, n = [], 0, t.shape[-1]
-    while start < n:
-        end = min(start + decode_chunk, n)
-        ctx = decode_ctx if start > decode_ctx else start
-        wav = decoder(t[..., start - ctx: end].contiguous())[0, 0]
-        parts.append(wav[ctx * upsample:] if ctx > 0 else wav)
-        start = end
-    return torch.cat(parts) if len(parts) > 1 else parts[0]
-
-
 class Model:
     def __init__(self, config: ModelConfig, device="cuda"):
         self.config = config
@@ -418,8 +403,11 @@ class Model:
     def _decode_generated_codes(self, codes: torch.Tensor, *, decode_chunk: int = 15, decode_ctx: int = 5) -> torch.Tensor:
         """qwen3_tts.py:1050-1083: codes [n, G] of one sequence -> audio [1920 n], decoded in ``decode_chunk``-frame pieces with up to
         ``decode_ctx`` frames of left context whose samples are dropped."""
-        dec = self.speech_tokenizer.decoder
-        return decode_in_chunks(lambda c: dec(c), codes, dec.total_upsample, decode_chunk, decode_ctx)
+        if codes.shape[0] == 0:
+            return torch.zeros(0, dtype=torch.float32, device=self.device)
+        # the reference's loop is chunked_decode's loop with (15, 5) in place of (300, 25): same chunk boundaries, same "context only
+        # when start > context" rule, context samples dropped (speech_tokenizer.py:932-954 vs qwen3_tts.py:1066-1078)
+        return self.speech_tokenizer.decoder.chunked_decode(codes[None].transpose(1, 2), chunk_size=decode_chunk, left_context_size=decode_ctx)[0, 0]
 
     @torch.no_grad()
     def _decode_chunk(self, codes: torch.Tensor, chunk_tokens: int = 300) -> torch.Tensor:

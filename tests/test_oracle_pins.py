@@ -493,8 +493,12 @@ def test_oracle_qwen3_default_batch_path_matches_the_reference_session():
         codes = Q.generate_codes(P, ie, tr, pad, us[b], m["max_tokens"], cfg=cfg)
         assert np.array_equal(codes.numpy(), g[f"session_codes_{b}"]), b
         assert np.abs(Q.decode_generated_codes(PT, codes, tcfg).numpy() - g[f"session_audio_{b}"]).max() < 2e-7
+        # the same audio is chunked_decode with (15, 5) in place of (300, 25) -- which is how the product computes it
+        assert np.abs(Q.chunked_decode(PT, codes.T[None], 15, 5, tcfg)[0, 0].numpy() - g[f"session_audio_{b}"]).max() < 2e-7
         lengths.append(codes.shape[0])
     assert lengths == [11, 15, 20]
+    one_shot = Q.tokenizer_decode(PT, torch.as_tensor(g["session_codes_2"]).long().T[None], tcfg)[0, 0]
+    assert np.abs(one_shot.numpy() - g["session_audio_2"]).max() > 0.1          # ... and NOT a one-shot decode of the 20-frame row
 
 
 def test_oracle_qwen3_voice_cloning_matches_the_reference_model_code():
