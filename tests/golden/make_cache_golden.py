@@ -41,7 +41,7 @@ def main():
                    trimmable=bool(c.is_trimmable()))
         trace.append(rec)
         print(rec)
-    np.savez_compressed(os.path.join(HERE, "cache_golden.npz"), trace=json.dumps(trace), **out)
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "cache_golden.npz"), trace=json.dumps(trace), **out)
 
 
 if __name__ == "__main__":

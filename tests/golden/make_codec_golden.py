@@ -113,7 +113,7 @@ def main():
     out.pop("mimi_pcm_steps")                                        # equal to the one-shot decode (checked above)
     for k in ("snac_audio", "mimi_pcm"):                             # waveforms stored as float32 (|x| <= 1: 6e-8 absolute)
         out[k] = np.asarray(out[k], dtype=np.float32)
-    np.savez_compressed(os.path.join(HERE, "codec_golden.npz"), **out)
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "codec_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})
 
 

@@ -54,7 +54,7 @@ def main():
     from mlx_audio.stt.models.whisper import decoding as D
     out["result_fields"] = {"GenerationResult": fields(TB.GenerationResult), "BatchGenerationResult": fields(TB.BatchGenerationResult),
                             "DecodingResult": fields(D.DecodingResult), "STTOutput": fields(W.STTOutput), "DecodingOptions": fields(D.DecodingOptions)}
-    json.dump(out, open(os.path.join(HERE, "config_golden.json"), "w"), indent=1, sort_keys=True)
+    json.dump(out, open(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "config_golden.json"), "w"), indent=1, sort_keys=True)
     print({k: (list(v) if isinstance(v, dict) else type(v)) for k, v in out.items()})
 
 

@@ -70,7 +70,7 @@ def main():
     out["logmel_noise_padded"] = np.asarray(audio.log_mel_spectrogram(a[:4000], n_mels=80, padding=8000), dtype=np.float32)
     sine = np.sin(2 * np.pi * 440.0 * np.arange(16000) / 16000.0).astype(np.float32)          # BASELINE config 1
     out["logmel_sine440"] = np.asarray(audio.log_mel_spectrogram(sine, n_mels=80, padding=0), dtype=np.float32)
-    np.savez_compressed(os.path.join(HERE, "dsp_golden.npz"), **out)
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "dsp_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 
 

@@ -87,7 +87,7 @@ def main():
     assert not mx.random.queue
     audio, pred_dur = np.asarray(res.audio), np.asarray(res.pred_dur)
     print("pred_dur", pred_dur.tolist(), "audio", audio.shape, float(np.abs(audio).max()))
-    np.savez_compressed(os.path.join(HERE, "kokoro_golden.npz"), ids=ids, ref_s=np.asarray(ref_s, dtype=np.float64), rand_ini=rand_ini,
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "kokoro_golden.npz"), ids=ids, ref_s=np.asarray(ref_s, dtype=np.float64), rand_ini=rand_ini,
                         noise_shape=np.asarray(draws["noise"].shape), pred_dur=pred_dur, audio=audio.astype(np.float32),
                         meta=json.dumps({"n_phonemes": n_ph, "weights": "synth.kokoro_weights(KOKORO_CONFIG, seed=0)", "f0_gain": f0_gain, "noise": "np.random.default_rng(71): .random((1, 9)) then .standard_normal(noise_shape).astype(float32)", "speed": float(os.environ.get("SPEED", "4.0"))}))
 

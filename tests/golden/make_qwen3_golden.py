@@ -366,7 +366,7 @@ def main():
     for k in list(out):                                              # waveforms are stored as float32 (|x| <= 1: 6e-8 absolute)
         if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith(("batch_audio_", "session_audio_")):   # (inputs are named *_pcm_in and stay float64)
             out[k] = np.asarray(out[k], dtype=np.float32)
-    np.savez_compressed(os.path.join(HERE, "qwen3_golden.npz"), **out)
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "qwen3_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})
 
 

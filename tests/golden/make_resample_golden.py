@@ -33,7 +33,7 @@ def main():
         if axis == 0 or x.ndim == 1:                                      # resample_audio_chunks is time-first (resample.py:50-161)
             chunks = np.array_split(x, 3, axis=0)
             out[name + "_chunks"] = np.asarray(ref.resample_audio_chunks(iter(chunks), osr, tsr, x.shape[0], chunk_duration_seconds=0.05))
-    np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), "resample_golden.npz"), **out)
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", os.path.dirname(os.path.abspath(__file__))), "resample_golden.npz"), **out)
     print({k: (v.shape, str(v.dtype)) for k, v in out.items()})
 
 

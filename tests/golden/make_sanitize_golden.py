@@ -77,7 +77,7 @@ def main():
     out["mimi_torch"] = manifest(captured)
     for k, v in out.items():
         print(k, len(v))
-    json.dump(out, open(os.path.join(HERE, "sanitize_golden.json"), "w"), indent=0, sort_keys=True)
+    json.dump(out, open(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "sanitize_golden.json"), "w"), indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":

@@ -117,7 +117,7 @@ def main():
                cross_qk_last=np.asarray(cross_qk[-1]), step_tokens=step_tokens, step_logits=np.stack(step_logits, 1)[:, :, 0],
                sinusoids=np.asarray(W.sinusoids(60, 64)))
     decode_cases(model, mel, out)
-    np.savez_compressed(os.path.join(HERE, "whisper_golden.npz"), **out)
+    np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "whisper_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})
 
 

@@ -1,0 +1,41 @@
+"""The committed fixtures under tests/golden/ are outputs of the reference's own source.  Where that source is present (the build
+container: /root/reference), every generator is re-run into a scratch directory and its output compared with the committed file --
+so a fixture can never drift from the code that is supposed to have produced it.  Skipped elsewhere (the GPU box has no /root/reference)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+GENERATORS = {"make_cache_golden.py": "cache_golden.npz", "make_codec_golden.py": "codec_golden.npz", "make_config_golden.py": "config_golden.json",
+              "make_dsp_golden.py": "dsp_golden.npz", "make_kokoro_golden.py": "kokoro_golden.npz", "make_qwen3_golden.py": "qwen3_golden.npz",
+              "make_resample_golden.py": "resample_golden.npz", "make_sanitize_golden.py": "sanitize_golden.json",
+              "make_whisper_golden.py": "whisper_golden.npz"}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/mlx_audio"), reason="the reference source is only present in the build container")
+@pytest.mark.parametrize("generator", sorted(GENERATORS))
+def test_fixture_is_what_the_reference_code_produces(generator, tmp_path):
+    env = dict(os.environ, GOLDEN_OUT=str(tmp_path), OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(HERE, generator)], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    name = GENERATORS[generator]
+    if name.endswith(".json"):
+        assert json.load(open(tmp_path / name)) == json.load(open(os.path.join(HERE, name)))
+        return
+    new, old = np.load(tmp_path / name), np.load(os.path.join(HERE, name))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        a, b = new[k], old[k]
+        assert a.dtype == b.dtype and a.shape == b.shape, k
+        if a.dtype.kind in "fc":
+            fin = np.isfinite(b)
+            assert np.array_equal(np.isfinite(a), fin) and np.array_equal(a[~fin], b[~fin], equal_nan=True), k
+            scale = max(1.0, float(np.abs(b[fin]).max())) if fin.any() else 1.0
+            assert np.abs(a[fin] - b[fin]).max(initial=0.0) <= 1e-12 * scale, k
+        else:
+            assert np.array_equal(a, b), k
