@@ -77,8 +77,11 @@ def snac_decoder(P, z, cfg, noises):
     pre = "decoder.model.layers"
     li = 0
     c = z.shape[-1]
-    x = snac_wnconv(P, f"{pre}.{li}", z, padding=3, groups=c); li += 1               # depthwise k7
-    x = snac_wnconv(P, f"{pre}.{li}", x); li += 1                                     # pointwise
+    if cfg["depthwise"]:
+        x = snac_wnconv(P, f"{pre}.{li}", z, padding=3, groups=c); li += 1           # depthwise k7
+        x = snac_wnconv(P, f"{pre}.{li}", x); li += 1                                 # pointwise
+    else:
+        x = snac_wnconv(P, f"{pre}.{li}", z, padding=3); li += 1                      # one dense k7 conv (layers.py:187-188)
     ch = cfg["decoder_dim"]
     for i, stride in enumerate(cfg["decoder_rates"]):
         bp = f"{pre}.{li}.block.layers"; li += 1

@@ -453,8 +453,9 @@ def tokenizer_decode(P, codes, cfg=TOKENIZER_DECODER, taps=None):
             w = causal_conv(P, U + ".conv2.conv", y, 1) + w
         if taps is not None:
             taps[f"block{bi}"] = w
-    w = snake_beta(w, P["decoder.decoder.5.alpha"], P["decoder.decoder.5.beta"])
-    w = causal_conv(P, "decoder.decoder.6.conv", w, 7)
+    last = len(cfg["upsample_rates"]) + 1                                 # [0] initial conv, [1..n] blocks, [n+1] snake, [n+2] output conv
+    w = snake_beta(w, P[f"decoder.decoder.{last}.alpha"], P[f"decoder.decoder.{last}.beta"])
+    w = causal_conv(P, f"decoder.decoder.{last + 1}.conv", w, 7)
     return torch.clamp(w.transpose(1, 2), -1.0, 1.0)
 
 

@@ -92,5 +92,48 @@ def main():
                         meta=json.dumps({"n_phonemes": n_ph, "weights": "synth.kokoro_weights(KOKORO_CONFIG, seed=0)", "f0_gain": f0_gain, "noise": "np.random.default_rng(71): .random((1, 9)) then .standard_normal(noise_shape).astype(float32)", "speed": float(os.environ.get("SPEED", "4.0"))}))
 
 
+def live(n):
+    """--live N: N random utterances (length, speed, style vector, weight seed, F0 scale) through the reference Model.__call__ and the
+    oracle's forward; durations identical, waveform 1e-9."""
+    import torch
+    from oracle import kokoro as OK
+    OK.EFFECTIVE_WEIGHTS_BF16 = False
+    cfg = json.loads(json.dumps(KOKORO_CONFIG))
+    vocab = {chr(0x100 + i): i for i in range(cfg["n_token"])}
+    model = K.Model(K.ModelConfig(**cfg, vocab=vocab))
+    model.eval()
+    worst = 0.0
+    for seed in range(n):
+        rng = np.random.default_rng(4000 + seed)
+        P = synth.kokoro_weights(cfg, seed=int(rng.integers(1, 100)))
+        P["predictor.F0_proj.weight"] = P["predictor.F0_proj.weight"] * float(rng.uniform(200, 900))
+        for k, v in P.items():
+            shim.set_parameter(model, k, v.double().numpy())
+        n_ph, speed = int(rng.integers(3, 14)), float(rng.uniform(3.0, 7.0))
+        ids = rng.integers(1, cfg["n_token"], size=n_ph)
+        ref_s = rng.standard_normal((1, 256))
+        rand_ini = rng.random((1, 9))
+        draws = {}
+
+        def noise(shape):
+            draws["noise"] = rng.standard_normal(shape)
+            return draws["noise"]
+        mx.random.strict = True
+        mx.random.queue[:] = [("uniform", rand_ini), ("normal", noise), ("normal", lambda shape: np.zeros(shape))]
+        res = model("".join(chr(0x100 + int(i)) for i in ids), mx.array(ref_s), speed=speed, return_output=True)
+        mx.random.strict = False
+        audio, pd = OK.forward({k: v.double() for k, v in P.items()}, torch.as_tensor(np.concatenate([[0], ids, [0]]))[None], torch.as_tensor(ref_s), cfg,
+                               speed=speed, rand_ini=torch.as_tensor(rand_ini), noise=torch.as_tensor(draws["noise"]))
+        assert np.array_equal(pd.numpy(), np.asarray(res.pred_dur)), (pd, res.pred_dur)
+        err = float(np.abs(audio.numpy().reshape(-1) - np.asarray(res.audio).reshape(-1)).max())
+        worst = max(worst, err)
+        print("kokoro phonemes", n_ph, "speed", round(speed, 2), "durations", np.asarray(res.pred_dur).tolist(), "samples", np.asarray(res.audio).size, "err", err)
+    assert worst < 1e-9, worst
+    print("LIVE OK", worst)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--live":
+        live(int(sys.argv[2]))
+    else:
+        main()

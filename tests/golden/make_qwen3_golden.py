@@ -370,5 +370,84 @@ def main():
     print({k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def live(n):
+    """--live N: N random configurations of the talker / code predictor / tokenizer decoder, reference classes vs oracle/qwen3.py."""
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import qwen3 as OQ
+    from mlx_audio.tts.models.qwen3_tts import speech_tokenizer as S
+    worst = 0.0
+    for seed in range(n):
+        rng = np.random.default_rng(2000 + seed)
+        kv = int(rng.choice([1, 2]))
+        heads = kv * int(rng.choice([1, 2, 4]))
+        hd = int(rng.choice([8, 16, 32]))
+        half = hd // 2
+        a = int(rng.integers(1, half - 1))
+        b = int(rng.integers(1, half - a))
+        sec = [a, b, half - a - b]
+        hidden, cph = int(rng.choice([32, 48])), int(rng.choice([24, 32]))
+        g = int(rng.integers(2, 6))
+        cp = dict(vocab_size=int(rng.integers(20, 60)), hidden_size=cph, intermediate_size=2 * cph, num_hidden_layers=int(rng.integers(1, 3)),
+                  num_attention_heads=heads, num_key_value_heads=kv, head_dim=hd, num_code_groups=g)
+        tk = dict(vocab_size=int(rng.integers(1100, 1200)), hidden_size=hidden, intermediate_size=2 * hidden, num_hidden_layers=int(rng.integers(1, 4)),
+                  num_attention_heads=heads, num_key_value_heads=kv, head_dim=hd,
+                  rope_scaling={"interleaved": True, "mrope_section": sec, "rope_type": "default"}, num_code_groups=g, text_hidden_size=24,
+                  text_vocab_size=40, code_predictor_config=cp)
+        oc = {"vocab_size": tk["vocab_size"], "hidden_size": hidden, "intermediate_size": 2 * hidden, "num_hidden_layers": tk["num_hidden_layers"],
+              "num_attention_heads": heads, "num_key_value_heads": kv, "head_dim": hd, "rms_norm_eps": 1e-6, "rope_theta": 1000000.0,
+              "mrope_section": sec, "num_code_groups": g, "codec_eos_token_id": 2150, "text_hidden_size": 24, "cp_vocab_size": cp["vocab_size"],
+              "cp_hidden_size": cph, "cp_intermediate_size": 2 * cph, "cp_num_hidden_layers": cp["num_hidden_layers"], "cp_num_attention_heads": heads,
+              "cp_num_key_value_heads": kv, "cp_head_dim": hd, "cp_rope_theta": 1000000.0}
+        talker = T.Qwen3TTSTalkerForConditionalGeneration(C.Qwen3TTSTalkerConfig(**tk))
+        P = {k: torch.as_tensor(synth_params.value(k, sh, r)) for k, sh, r in fill(talker)}
+        bsz, s0 = int(rng.integers(1, 4)), int(rng.integers(2, 9))
+        x = rng.standard_normal((bsz, s0, hidden))
+        cache, ocache = talker.make_cache(), OQ.make_cache(oc["num_hidden_layers"])
+        lg, _ = talker(mx.array(x), cache=cache)
+        olg, _ = OQ.talker_forward(P, torch.as_tensor(x), ocache, cfg=oc)
+        errs = [np.abs(np.asarray(lg) - olg.numpy()).max()]
+        for _ in range(2):
+            x1 = rng.standard_normal((bsz, 1, hidden))
+            lg, _ = talker(mx.array(x1), cache=cache)
+            olg, _ = OQ.talker_forward(P, torch.as_tensor(x1), ocache, cfg=oc)
+            errs.append(np.abs(np.asarray(lg) - olg.numpy()).max())
+        cc, occ = talker.code_predictor.make_cache(), OQ.make_cache(oc["cp_num_hidden_layers"])
+        cx = rng.standard_normal((bsz, 2, hidden))
+        cl, cc, _ = talker.code_predictor(mx.array(cx), cache=cc, generation_step=0)
+        errs.append(np.abs(np.asarray(cl) - OQ.code_predictor_forward(P, torch.as_tensor(cx), occ, 0, oc).numpy()).max())
+        for st in range(1, g - 1):
+            c1 = rng.standard_normal((bsz, 1, hidden))
+            cl, cc, _ = talker.code_predictor(mx.array(c1), cache=cc, generation_step=st)
+            errs.append(np.abs(np.asarray(cl) - OQ.code_predictor_forward(P, torch.as_tensor(c1), occ, st, oc).numpy()).max())
+        # tokenizer decoder with other strides
+        ups = [int(v) for v in rng.choice([2, 3, 4, 5], size=int(rng.integers(2, 4)))]
+        rat = [int(v) for v in rng.choice([2, 3], size=int(rng.integers(1, 3)))]
+        dh = int(rng.choice([1, 2, 4]))
+        dd = 8 * 2 ** len(ups)
+        nq = int(rng.integers(2, 6))
+        td = dict(latent_dim=24, codebook_dim=8, codebook_size=32, decoder_dim=dd, hidden_size=dh * 8, intermediate_size=32, head_dim=8,
+                  num_attention_heads=dh, num_hidden_layers=int(rng.integers(1, 3)), num_key_value_heads=dh, num_quantizers=nq,
+                  num_semantic_quantizers=1, upsample_rates=ups, upsampling_ratios=rat)
+        otd = {"latent_dim": 24, "codebook_dim": 8, "codebook_size": 32, "decoder_dim": dd, "hidden_size": dh * 8, "intermediate_size": 32,
+               "layer_scale_initial_scale": 0.01, "head_dim": 8, "num_attention_heads": dh, "num_hidden_layers": td["num_hidden_layers"],
+               "num_key_value_heads": dh, "num_quantizers": nq, "num_semantic_quantizers": 1, "rms_norm_eps": 1e-5, "rope_theta": 10000.0,
+               "upsample_rates": ups, "upsampling_ratios": rat}
+        tok = S.Qwen3TTSSpeechTokenizer(C.Qwen3TTSTokenizerConfig(decoder_config=C.Qwen3TTSTokenizerDecoderConfig(**td)))
+        PT = {k: torch.as_tensor(synth_params.value(k, sh, r)) for k, sh, r in fill(tok, rule=lambda nm: "small" if nm.endswith((".alpha", ".beta")) else None)}
+        codes = rng.integers(0, 32, size=(2, nq, int(rng.integers(2, 7))))
+        wav = np.asarray(tok.decoder(mx.array(codes)))
+        owav = OQ.tokenizer_decode(PT, torch.as_tensor(codes), otd).numpy()
+        assert wav.shape == owav.shape, (wav.shape, owav.shape)
+        errs.append(np.abs(wav - owav).max())
+        worst = max(worst, float(max(errs)))
+        print("qwen3 heads", heads, "kv", kv, "hd", hd, "mrope", sec, "groups", g, "| tokenizer ups", ups, rat, "nq", nq, "max err", float(max(errs)))
+    assert worst < 1e-9, worst
+    print("LIVE OK", worst)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--live":
+        live(int(sys.argv[2]))
+    else:
+        main()

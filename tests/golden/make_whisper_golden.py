@@ -121,5 +121,46 @@ def main():
     print({k: getattr(v, "shape", None) for k, v in out.items()})
 
 
+def live(n):
+    """--live N: N random configurations, reference classes vs oracle/whisper.py, no fixture involved (tests/test_golden_reproducible.py)."""
+    import torch
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import whisper as OW
+    worst = 0.0
+    for seed in range(n):
+        rng = np.random.default_rng(1000 + seed)
+        heads = int(rng.choice([1, 2, 4]))
+        state = heads * int(rng.choice([8, 16]))
+        d = dict(n_mels=int(rng.choice([16, 80])), n_audio_ctx=int(rng.integers(5, 40)), n_audio_state=state, n_audio_head=heads,
+                 n_audio_layer=int(rng.integers(1, 4)), n_vocab=int(rng.integers(50, 200)), n_text_ctx=int(rng.integers(8, 24)), n_text_state=state,
+                 n_text_head=heads, n_text_layer=int(rng.integers(1, 4)))
+        model = W.Model(W.ModelDimensions(**d), dtype=mx.float32)
+        names = [(k, v.shape) for k, v in shim.flat_parameters(model)]
+        for k, sh in names:
+            shim.set_parameter(model, k, synth_params.value(k, sh))
+        P = {k: torch.as_tensor(synth_params.value(k, sh)) for k, sh in names}
+        b = int(rng.integers(1, 4))
+        mel = rng.standard_normal((b, 2 * d["n_audio_ctx"], d["n_mels"]))
+        xa = model.encoder(mx.array(mel))
+        oxa = OW.encoder(P, torch.as_tensor(mel), d)
+        nt = int(rng.integers(1, d["n_text_ctx"] - 3))
+        toks = rng.integers(0, d["n_vocab"], size=(b, nt))
+        lg, kv, _ = model.decoder(mx.array(toks), xa)
+        olg, cache = OW.decoder_forward(P, torch.as_tensor(toks), oxa, None, d)
+        errs = [np.abs(np.asarray(xa) - oxa.numpy()).max(), np.abs(np.asarray(lg) - olg.numpy()).max()]
+        for _ in range(2):
+            t1 = rng.integers(0, d["n_vocab"], size=(b, 1))
+            lg, kv, _ = model.decoder(mx.array(t1), xa, kv_cache=kv)
+            olg, cache = OW.decoder_forward(P, torch.as_tensor(t1), oxa, cache, d)
+            errs.append(np.abs(np.asarray(lg) - olg.numpy()).max())
+        worst = max(worst, float(max(errs)))
+        print("whisper", d, "max err", float(max(errs)))
+    assert worst < 1e-10, worst
+    print("LIVE OK", worst)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--live":
+        live(int(sys.argv[2]))
+    else:
+        main()
