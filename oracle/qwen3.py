@@ -424,8 +424,13 @@ def convnext(P, pre, x):
     return x + P[pre + ".gamma"].to(x.dtype) * h
 
 
-def tokenizer_decode(P, codes, cfg=TOKENIZER_DECODER, taps=None):
-    """Qwen3TTSSpeechTokenizerDecoder.__call__ (speech_tokenizer.py:843-880): codes [B,16,T] -> wav [B,1,1920 T]."""
+def tokenizer_decode(P, codes, cfg=TOKENIZER_DECODER, taps=None, stream_boundaries=()):
+    """Qwen3TTSSpeechTokenizerDecoder.__call__ (speech_tokenizer.py:843-880): codes [B,16,T] -> wav [B,1,1920 T].
+
+    ``stream_boundaries`` (frame indices where a new ``streaming_step`` call began) turns this into the concatenated output of the
+    incremental decoder (speech_tokenizer.py:889-930).  Every buffered layer of that path is exact, with one exception that is kept:
+    DecoderBlockUpsample.step (:645-656) overlap-adds the transposed-conv tail of the previous call INCLUDING its bias, so the bias is
+    counted twice over the first ``kernel - stride`` (= stride) output samples after each boundary."""
     if codes.shape[1] != cfg["num_quantizers"]:
         raise ValueError(f"Expected {cfg['num_quantizers']} layers of codes, got {codes.shape[1]}")
     h = quantizer_decode(P, codes, cfg)
@@ -444,7 +449,14 @@ def tokenizer_decode(P, codes, cfg=TOKENIZER_DECODER, taps=None):
     for bi, r in enumerate(cfg["upsample_rates"]):
         B_ = f"decoder.decoder.{bi + 1}.block"
         w = snake_beta(w, P[B_ + ".0.alpha"], P[B_ + ".0.beta"])
+        frames_in = w.shape[1]                                                        # NLC
         w = causal_convtr(P, B_ + ".1.conv", w, 2 * r, r)
+        if stream_boundaries and (B_ + ".1.conv.bias") in P:
+            per_frame = frames_in // codes.shape[-1]                                  # this block's input samples per code frame
+            w = w.clone()
+            for f in stream_boundaries:
+                pos = f * per_frame * r
+                w[:, pos: pos + r, :] += P[B_ + ".1.conv.bias"].to(w.dtype)[None, None, :]
         for ui, d in enumerate((1, 3, 9)):
             U = f"{B_}.{ui + 2}"
             y = snake_beta(w, P[U + ".act1.alpha"], P[U + ".act1.beta"])

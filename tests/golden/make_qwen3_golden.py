@@ -362,7 +362,6 @@ def main():
     tok = tokenizer_cases(out)
     model_cases(out, tok)
     icl_cases(out, tok)
-    out.pop("tok_stream_wav", None)
     for k in list(out):                                              # waveforms are stored as float32 (|x| <= 1: 6e-8 absolute)
         if k.endswith(("_wav", "_audio", "_wav_chunked")) or k.startswith(("batch_audio_", "session_audio_")):   # (inputs are named *_pcm_in and stay float64)
             out[k] = np.asarray(out[k], dtype=np.float32)

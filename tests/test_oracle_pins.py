@@ -341,6 +341,11 @@ def test_oracle_qwen3_matches_the_reference_model_code():
     assert np.abs(Q.chunked_decode(PT, torch.as_tensor(g["tok_codes"]), 4, 2, tcfg).numpy() - g["tok_wav_chunked"]).max() < wtol
     w, ln = Q.speech_tokenizer_decode(PT, torch.as_tensor(g["tok_codes_bt"]), tcfg)
     assert np.abs(w.numpy() - g["tok_decode_wav"]).max() < wtol and ln.tolist() == g["tok_decode_lens"].tolist()
+    # the incremental decoder (streaming_step, speech_tokenizer.py:889-930) fed 5 + 4 frames: exact everywhere except that the transposed-conv
+    # bias is overlap-added twice after the boundary -- restated by the oracle, and clearly not the one-shot decode
+    first = torch.as_tensor(g["tok_codes"][:1])
+    assert np.abs(Q.tokenizer_decode(PT, first, tcfg, stream_boundaries=(5,)).numpy() - g["tok_stream_wav"]).max() < wtol
+    assert np.abs(Q.tokenizer_decode(PT, first, tcfg).numpy() - g["tok_stream_wav"]).max() > 0.1
     P["codec_head.weight"] = P["codec_head.weight"].clone()
     P["codec_head.weight"][cfg["codec_eos_token_id"]] *= float(g["gen_eos_gain"])
     ids = dict(codec_nothink_id=1004, codec_think_id=1003, codec_think_bos_id=1005, codec_think_eos_id=1006, codec_pad_id=1001, codec_bos_id=1002)
