@@ -47,6 +47,7 @@ class Mimi:
         self.cfg = cfg
         self.device = torch.device(device)
         self._w = None
+        self._stream_codes = None
 
     @property
     def frame_rate(self):
@@ -57,7 +58,23 @@ class Mimi:
         return self.cfg.sample_rate
 
     def reset_state(self):
-        """Full-sequence decode keeps no state; present for API parity (mimi.py:138-144)."""
+        """mimi.py:138-144: forget the streaming state."""
+        self._stream_codes = None
+
+    @torch.no_grad()
+    def decode_step(self, xs: torch.Tensor) -> torch.Tensor:
+        """mimi.py:171-176: the next ``T_new`` code frames [B, nq, T_new] -> their 1920 T_new samples.  In the reference the incremental
+        path (conv buffers, overlap-add with the bias handled, rotating KV cache) returns exactly the corresponding slice of a one-shot
+        decode (7e-16 when its own code is run, tests/golden/make_codec_golden.py); here the codes seen so far are kept and re-decoded --
+        the same samples, with the cost of a full decode per call (a 10 000-frame decode is 34 ms).  ``reset_state()`` / ``decode()`` start a
+        new stream, as they do in the reference."""
+        xs = xs.to(device=self.device, dtype=torch.int64)
+        prev = getattr(self, "_stream_codes", None)
+        codes = xs if prev is None else torch.cat([prev, xs], dim=-1)
+        pcm = self.decode(codes)
+        self._stream_codes = codes
+        hop = pcm.shape[-1] // codes.shape[-1]
+        return pcm[..., (codes.shape[-1] - xs.shape[-1]) * hop:]
 
     @staticmethod
     def sanitize_pytorch_weights(weights: dict) -> dict:
@@ -152,6 +169,7 @@ class Mimi:
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """codes int64 [B, nq, T] -> pcm [B, 1, 1920 T]."""
         W, cfg, dev = self._w, self.cfg, self.device
+        self._stream_codes = None                                       # decode() resets the streaming state (mimi.py:156-158)
         codes = codes.to(device=dev, dtype=torch.int64).contiguous()
         B, nq, T = codes.shape
         q = ops.rvq_decode(codes[:, :1], W["cb_first"])

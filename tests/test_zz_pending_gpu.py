@@ -38,3 +38,22 @@ def test_default_batch_path_rows_equal_single_sequence_generation_and_chunked_de
         assert err < 1e-3, (b, err)
     res = list(model.batch_generate_from_ids(ids_list, language_id=2050, max_tokens=n_frames, u=u))
     assert [r.sequence_idx for r in res] == [0, 1, 2] and all(r.samples == r.token_count * 1920 and not r.is_streaming_chunk for r in res)
+
+
+def test_mimi_decode_step_returns_the_slices_of_a_one_shot_decode():
+    """Mimi.decode_step (mimi.py:171-176): in the reference the incremental path equals the one-shot decode (checked on the reference's own
+    code, tests/golden/make_codec_golden.py); the product re-decodes the codes seen so far, so the chunks are the slices."""
+    from mlx_audio_b200 import synth
+    from mlx_audio_b200.codec import Mimi, mimi_202407
+    from oracle import codec as OC
+    m = Mimi(mimi_202407(32), device="cuda:0").load_weights(synth.mimi_weights(OC.MIMI_202407))
+    codes = synth.mimi_codes(OC.MIMI_202407, 12, batch=2)
+    full = m.decode(codes)
+    m.reset_state()
+    parts = [m.decode_step(codes[:, :, :5]), m.decode_step(codes[:, :, 5:6]), m.decode_step(codes[:, :, 6:])]
+    assert [p.shape[-1] for p in parts] == [5 * 1920, 1920, 6 * 1920]
+    got = torch.cat(parts, dim=-1)
+    assert torch.equal(parts[2], full[..., 6 * 1920:])                   # the same full decode
+    assert float((got - full).abs().max()) <= 1e-4 * max(1.0, float(full.abs().max()))      # shorter decodes: same maths, other tile shapes
+    m.decode(codes[:, :, :3])                                            # decode() starts a new stream
+    assert m.decode_step(codes[:, :, :2]).shape[-1] == 2 * 1920
