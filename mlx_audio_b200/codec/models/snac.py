@@ -154,5 +154,23 @@ class SNAC:
         a, ia = W["out_snake"]
         return ops.conv1d(x, W["out_conv"], pad_left=3, pre=Pre(act=ACT["snake"], a=a, b=ia), post_act=ACT["tanh"])
 
+    def decode_stream(self, codes: List[torch.Tensor], prev_codes: Optional[List[torch.Tensor]] = None, context_frames: int = 8, noises=None):
+        """snac.py:106-162, literally: the first call decodes ``codes``; later calls prepend ``max(1, context_frames // stride_l)`` frames of
+        context per level and decode the combination.  Kept quirk: the reference trims the context with ``full_audio[..., n:]`` on an audio
+        tensor whose LAST axis is the channel ([B, T, 1]), so nothing is trimmed and the context's audio is returned again.
+        -> (audio [B, T, 1], new context)."""
+        new_context = [c[:, -context_frames:] if c.shape[1] > context_frames else c for c in codes]
+        if prev_codes is None:
+            return self.decode(codes, noises=noises), new_context
+        combined = []
+        for stride, prev, new in zip(self.vq_strides, prev_codes, codes):
+            keep = max(1, context_frames // stride)
+            prev = prev[:, -keep:] if prev.shape[1] > keep else prev
+            combined.append(torch.cat([prev.to(new.device), new], dim=1))
+        full_audio = self.decode(combined, noises=noises)
+        context_samples = context_frames * self.hop_length
+        audio = full_audio[..., context_samples:] if full_audio.shape[-1] > context_samples else full_audio
+        return audio, new_context
+
     def encode(self, audio_data):
         raise NotImplementedError("SNAC.encode is the 'next' row 2 of SURVEY.md section 8f (codec encode side)")

@@ -173,6 +173,22 @@ def snac_decode(P, codes, cfg=SNAC_24K, noises=None):
         noises = [torch.zeros(1, 1, 1, dtype=z.dtype)] * len(cfg["decoder_rates"])
     return snac_decoder(P, z.transpose(1, 2), cfg, noises)
 
+def snac_decode_stream(P, codes, prev_codes=None, context_frames=8, cfg=SNAC_24K, noises=None):
+    """SNAC.decode_stream (snac/snac.py:106-162), literally -- including the ``[..., context_samples:]`` slice that acts on the channel
+    axis of the [B, T, 1] audio and therefore trims nothing.  -> (audio, new context)."""
+    new_context = [c[:, -context_frames:] if c.shape[1] > context_frames else c for c in codes]
+    if prev_codes is None:
+        return snac_decode(P, codes, cfg, noises), new_context
+    combined = []
+    for stride, prev, new in zip(cfg["vq_strides"], prev_codes, codes):
+        keep = max(1, context_frames // stride)
+        prev = prev[:, -keep:] if prev.shape[1] > keep else prev
+        combined.append(torch.cat([prev, new], dim=1))
+    full = snac_decode(P, combined, cfg, noises)
+    n = context_frames * math.prod(cfg["encoder_rates"])
+    return (full[..., n:] if full.shape[-1] > n else full), new_context
+
+
 # ============================================================================= Mimi
 
 MIMI_202407 = {   # codec/models/mimi/mimi.py:47-96

@@ -61,6 +61,22 @@ def snac_cases(out):
     for i, c in enumerate(enc):
         out[f"snac_enc_codes_{i}"] = np.asarray(c)
     print("snac encode", [np.asarray(c).shape for c in enc])
+    # decode_stream: a first call and a second call that prepends context (two decodes = eight noise draws)
+    c1 = [rng.integers(0, 64, size=(2, 12 // s_)) for s_ in SNAC_CFG["vq_strides"]]
+    c2 = [rng.integers(0, 64, size=(2, 8 // s_)) for s_ in SNAC_CFG["vq_strides"]]
+    zs = [rng.standard_normal((2, 1, c)) for c in chans] + [rng.standard_normal((2, 1, c)) for c in chans]
+    mx.random.strict = True
+    mx.random.queue[:] = [("normal", z) for z in zs]
+    a1, ctx = model.decode_stream([mx.array(c) for c in c1])
+    a2, ctx2 = model.decode_stream([mx.array(c) for c in c2], prev_codes=ctx, context_frames=8)
+    assert not mx.random.queue
+    mx.random.strict = False
+    for i in range(3):
+        out[f"snac_stream_c1_{i}"], out[f"snac_stream_c2_{i}"], out[f"snac_stream_ctx_{i}"] = c1[i], c2[i], np.asarray(ctx2[i])
+    for i, z in enumerate(zs):
+        out[f"snac_stream_noise_{i}"] = z
+    out["snac_stream_audio1"], out["snac_stream_audio2"] = np.asarray(a1), np.asarray(a2)
+    print("snac decode_stream", np.asarray(a1).shape, np.asarray(a2).shape, [np.asarray(c).shape for c in ctx2])
     for i, c in enumerate(codes):
         out[f"snac_codes_{i}"] = c
     for i, n in enumerate(noises):
@@ -111,7 +127,7 @@ def main():
     snac_cases(out)
     mimi_cases(out)
     out.pop("mimi_pcm_steps")                                        # equal to the one-shot decode (checked above)
-    for k in ("snac_audio", "mimi_pcm"):                             # waveforms stored as float32 (|x| <= 1: 6e-8 absolute)
+    for k in ("snac_audio", "mimi_pcm", "snac_stream_audio1", "snac_stream_audio2"):                             # waveforms stored as float32 (|x| <= 1: 6e-8 absolute)
         out[k] = np.asarray(out[k], dtype=np.float32)
     np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "codec_golden.npz"), **out)
     print({k: getattr(v, "shape", None) for k, v in out.items()})

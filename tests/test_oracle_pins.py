@@ -398,6 +398,17 @@ def test_oracle_codecs_match_the_reference_model_code():
     P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["mimi_params"]).items()}
     y = OC.mimi_decode(P, torch.as_tensor(g["mimi_codes"]).long(), cfg)
     assert tuple(y.shape) == g["mimi_pcm"].shape == (2, 1, 9 * 1920) and np.abs(y.numpy() - g["mimi_pcm"]).max() < 2e-7
+    # SNAC.decode_stream (snac.py:106-162): a first call, then a call that prepends 2 / 4 / 8 context frames per level; the reference's
+    # context trim slices the channel axis of the [B, T, 1] audio, so the second call returns context + new audio (3099 samples) -- kept
+    scfg = json.loads(str(g["snac_cfg"]))
+    PS = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["snac_params"]).items()}
+    c1, c2 = ([torch.as_tensor(g[f"snac_stream_c{j}_{i}"]).long() for i in range(3)] for j in (1, 2))
+    zs = [torch.as_tensor(g[f"snac_stream_noise_{i}"]) for i in range(8)]
+    a1, ctx = OC.snac_decode_stream(PS, c1, None, 8, scfg, zs[:4])
+    a2, ctx2 = OC.snac_decode_stream(PS, c2, ctx, 8, scfg, zs[4:])
+    assert tuple(a1.shape) == (2, 2331, 1) and tuple(a2.shape) == (2, 3099, 1)
+    assert np.abs(a1.numpy() - g["snac_stream_audio1"]).max() < 2e-7 and np.abs(a2.numpy() - g["snac_stream_audio2"]).max() < 2e-7
+    assert all(np.array_equal(c.numpy(), g[f"snac_stream_ctx_{i}"]) for i, c in enumerate(ctx2))
     # encode side (integer results, identical): Mimi.encode on 12 frames + 700 samples, SNAC.encode on a length that needs right padding
     c = OC.mimi_encode(P, torch.as_tensor(g["mimi_enc_pcm"]), cfg)
     assert tuple(c.shape) == (2, 4, 13) and np.array_equal(c.numpy(), g["mimi_enc_codes"])

@@ -56,3 +56,24 @@ def test_mimi_decode_step_returns_the_slices_of_a_one_shot_decode():
     assert float((got - full).abs().max()) <= 1e-4 * max(1.0, float(full.abs().max()))      # shorter decodes: same maths, other tile shapes
     m.decode(codes[:, :, :3])                                            # decode() starts a new stream
     assert m.decode_step(codes[:, :, :2]).shape[-1] == 2 * 1920
+
+
+def test_snac_decode_stream_follows_the_reference_function():
+    """SNAC.decode_stream (snac.py:106-162; the oracle's restatement is pinned to the reference's own run incl. the untrimmed-context
+    quirk): product vs oracle on the 24 kHz configuration, two calls."""
+    from mlx_audio_b200 import synth
+    from mlx_audio_b200.codec import SNAC
+    from oracle import codec as OC
+    P = synth.snac_weights(OC.SNAC_24K)
+    model = SNAC.from_config(OC.SNAC_24K, device="cuda:0").load_weights(P)
+    P64 = {k: v.double() for k, v in P.items()}
+    c1, c2 = synth.snac_codes(OC.SNAC_24K, 24, 1, seed=6), synth.snac_codes(OC.SNAC_24K, 16, 1, seed=8)
+    n1, n2 = synth.snac_noises(OC.SNAC_24K, 1, seed=7), synth.snac_noises(OC.SNAC_24K, 1, seed=9)
+    a1, ctx = model.decode_stream(c1, noises=n1)
+    a2, ctx2 = model.decode_stream(c2, prev_codes=ctx, context_frames=8, noises=n2)
+    r1, rctx = OC.snac_decode_stream(P64, c1, None, 8, OC.SNAC_24K, [n.double() for n in n1])
+    r2, rctx2 = OC.snac_decode_stream(P64, c2, rctx, 8, OC.SNAC_24K, [n.double() for n in n2])
+    assert a1.shape == r1.shape and a2.shape == r2.shape and a2.shape[1] > a1.shape[1] * 16 // 24      # context audio is returned again
+    for a, r in ((a1, r1), (a2, r2)):
+        assert float(((a.cpu().double() - r) ** 2).mean().sqrt() / (r ** 2).mean().sqrt()) < 1e-3
+    assert all(torch.equal(c.cpu(), rc) for c, rc in zip(ctx2, rctx2))
