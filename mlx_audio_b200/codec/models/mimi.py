@@ -203,3 +203,21 @@ class Mimi:
 
     def encode(self, xs):
         raise NotImplementedError("Mimi.encode is the 'next' row 2 of SURVEY.md section 8f (codec encode side)")
+
+
+class MimiStreamingDecoder:
+    """mimi.py:278-320: keeps the codec's streaming state across calls.  The reference decodes frame by frame with ``decode_step``; since
+    every step returns the matching slice of a one-shot decode, a block of frames is decoded here with a single ``decode_step``."""
+
+    def __init__(self, mimi: Mimi) -> None:
+        self._mimi = mimi
+        self.reset()
+
+    def reset(self) -> None:
+        self._mimi.reset_state()
+
+    def decode_frames(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens [B, C, T] or [C, T] -> waveform [B, 1, 1920 T] for these frames (continuing the stream)."""
+        if tokens.dim() == 2:
+            tokens = tokens[None]
+        return self._mimi.decode_step(tokens)

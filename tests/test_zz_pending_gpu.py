@@ -56,6 +56,10 @@ def test_mimi_decode_step_returns_the_slices_of_a_one_shot_decode():
     assert float((got - full).abs().max()) <= 1e-4 * max(1.0, float(full.abs().max()))      # shorter decodes: same maths, other tile shapes
     m.decode(codes[:, :, :3])                                            # decode() starts a new stream
     assert m.decode_step(codes[:, :, :2]).shape[-1] == 2 * 1920
+    from mlx_audio.codec import MimiStreamingDecoder
+    sd = MimiStreamingDecoder(m)
+    blocks = torch.cat([sd.decode_frames(codes[:, :, :7]), sd.decode_frames(codes[:, :, 7:])], dim=-1)
+    assert float((blocks - full).abs().max()) <= 1e-4 * max(1.0, float(full.abs().max()))
 
 
 def test_snac_decode_stream_follows_the_reference_function():
