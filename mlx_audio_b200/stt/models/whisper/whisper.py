@@ -254,6 +254,8 @@ class TextDecoder:
             m = ops.linear(h, blk["mlp1"], post_act=ACT["gelu"])
             x = ops.linear(m, blk["mlp2"], res=x)
         cache["offset"] = off + n
+        if not last_only:                                                     # every position: Model.logits / __call__ (whisper.py:623-631)
+            return ops.linear(ops.layernorm(x.contiguous(), *W["ln"]), W["logits"])
         rows = x[:, -1:] if not also_first else torch.cat([x[:, -1:], x[:, :1]], 1)
         hl = ops.layernorm(rows.contiguous(), *W["ln"])
         logits = ops.linear(hl, W["logits"])                                  # tied embedding (whisper.py:498)
@@ -387,6 +389,23 @@ class Model:
 
     def embed_audio(self, mel):
         return self.encoder(mel)
+
+    def logits(self, tokens: torch.Tensor, audio_features: torch.Tensor) -> torch.Tensor:
+        """whisper.py:623-624: logits [B, n, n_vocab] of every position of ``tokens`` [B, n] given encoder features."""
+        tokens = tokens.to(device=self.device, dtype=torch.int64)
+        return self.decoder(tokens, self.decoder.new_cache(audio_features.to(self.device)), last_only=False)
+
+    def __call__(self, mel: torch.Tensor, tokens: torch.Tensor) -> torch.Tensor:
+        """whisper.py:630-631."""
+        return self.logits(tokens, self.encoder(mel))
+
+    @property
+    def is_multilingual(self) -> bool:
+        return self.dims.n_vocab >= 51865                                    # whisper.py:633-635
+
+    @property
+    def num_languages(self) -> int:
+        return self.dims.n_vocab - 51765 - int(self.is_multilingual)         # whisper.py:637-639
 
     def encode_audio(self, audio: torch.Tensor) -> torch.Tensor:
         """BASELINE config 3: audio [B, 480000] -> log-mel (reference's +30 s zero pad, first 3000 frames) -> encoder."""

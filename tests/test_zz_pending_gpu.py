@@ -81,3 +81,21 @@ def test_snac_decode_stream_follows_the_reference_function():
     for a, r in ((a1, r1), (a2, r2)):
         assert float(((a.cpu().double() - r) ** 2).mean().sqrt() / (r ** 2).mean().sqrt()) < 1e-3
     assert all(torch.equal(c.cpu(), rc) for c, rc in zip(ctx2, rctx2))
+
+
+def test_whisper_logits_of_every_position():
+    """Model.logits(tokens, audio_features) (whisper.py:623-624): all positions, vs the float64 oracle (1e-3 relative to the logit scale)."""
+    from mlx_audio_b200 import synth
+    from mlx_audio_b200.stt.models.whisper import Model, ModelDimensions
+    from oracle import whisper as OW
+    dims = dict(OW.WHISPER_SMALL)
+    dims["n_text_layer"] = 2
+    P = synth.whisper_decoder_weights(dims)
+    model = Model(ModelDimensions.from_dict(dims), device="cuda:0").load_weights(P)
+    xa = torch.randn(2, 1500, 768, generator=torch.Generator().manual_seed(0))
+    tokens = torch.randint(0, dims["n_vocab"], (2, 9), generator=torch.Generator().manual_seed(1))
+    want, _ = OW.decoder_forward({k: v.double() for k, v in P.items()}, tokens, xa.double(), None, dims)
+    got = model.logits(tokens, xa)
+    assert got.shape == want.shape == (2, 9, dims["n_vocab"])
+    assert float((got.double().cpu() - want).abs().max() / want.abs().max()) < 1e-3
+    assert model.is_multilingual and model.num_languages == 99
