@@ -74,5 +74,55 @@ def main():
     print({k: v.shape for k, v in out.items()})
 
 
+def live(n):
+    """--live N: random STFT / iSTFT / mel-filterbank / log-mel configurations, the reference's dsp.py (float32, NumPy standing in for MLX)
+    vs oracle/dsp.py side by side."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import dsp as O
+    numpy_mlx_shim.install()
+    dsp = load(os.path.join(REF, "dsp.py"), "ref_dsp_live")
+    worst = {"stft": 0.0, "istft": 0.0, "mel": 0.0, "window": 0.0}
+    for seed in range(n):
+        rng = np.random.default_rng(5000 + seed)
+        n_fft = int(rng.choice([16, 20, 64, 128, 400, 512]))
+        hop = int(rng.integers(max(1, n_fft // 8), n_fft // 2 + 1))
+        win_length = int(rng.choice([n_fft, max(4, n_fft - int(rng.integers(0, n_fft // 2)))]))
+        window = str(rng.choice(["hann", "hamming", "blackman", "bartlett"]))
+        center = bool(rng.integers(0, 2))
+        pad_mode = str(rng.choice(["reflect", "constant"]))
+        x = rng.standard_normal(int(rng.integers(2 * n_fft, 6 * n_fft))).astype(np.float32)
+        kw = dict(n_fft=n_fft, hop_length=hop, win_length=win_length, window=window, center=center, pad_mode=pad_mode)
+        a, b = np.asarray(dsp.stft(numpy_mlx_shim.array(x), **kw)), O.stft(x, **kw)
+        assert a.shape == b.shape, (kw, a.shape, b.shape)
+        worst["stft"] = max(worst["stft"], float(np.abs(a - b).max() / max(1.0, np.abs(b).max())))
+        for size in (int(rng.integers(3, 40)),):
+            for name in ("hanning", "hamming", "blackman", "bartlett"):
+                for periodic in (False, True):
+                    wa, wb = np.asarray(getattr(dsp, name)(size, periodic=periodic)), getattr(O, name)(size, periodic=periodic)
+                    worst["window"] = max(worst["window"], float(np.abs(wa - wb).max()))
+        # iSTFT of a centred reflect STFT with a full-length window (the combination the reference's own callers use)
+        nf = int(rng.choice([16, 64, 256]))
+        hp = nf // int(rng.choice([2, 4]))
+        y = rng.standard_normal(6 * nf).astype(np.float32)
+        spec = np.asarray(dsp.stft(numpy_mlx_shim.array(y), n_fft=nf, hop_length=hp))
+        norm = bool(rng.integers(0, 2))
+        ia = np.asarray(dsp.istft(numpy_mlx_shim.array(spec.T), hop_length=hp, win_length=nf, normalized=norm))
+        ib = O.istft(spec.T, hop_length=hp, win_length=nf, normalized=norm)
+        ok = np.isfinite(ia)
+        assert ia.shape == ib.shape
+        worst["istft"] = max(worst["istft"], float(np.abs(ia[ok] - ib[ok]).max()))
+        sr = int(rng.choice([16000, 22050, 24000, 44100]))
+        mk = dict(sample_rate=sr, n_fft=int(rng.choice([256, 400, 1024])), n_mels=int(rng.choice([20, 40, 80, 128])), f_min=float(rng.choice([0.0, 50.0])),
+                  f_max=float(rng.choice([sr / 2, sr / 2 - 1000.0])), norm=[None, "slaney"][int(rng.integers(0, 2))], mel_scale=str(rng.choice(["htk", "slaney"])))
+        worst["mel"] = max(worst["mel"], float(np.abs(np.asarray(dsp.mel_filters(**mk)) - O.mel_filters(**mk)).max()))
+        print("dsp", kw, "| istft", nf, hp, norm, "| mel", mk["sample_rate"], mk["n_mels"], mk["norm"], mk["mel_scale"])
+    print(worst)
+    assert worst["stft"] < 2e-4 and worst["istft"] < 5e-5 and worst["mel"] < 5e-6 and worst["window"] < 1e-6, worst
+    print("LIVE OK", worst)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 2 and sys.argv[1] == "--live":
+        live(int(sys.argv[2]))
+    else:
+        main()

@@ -42,7 +42,7 @@ def test_fixture_is_what_the_reference_code_produces(generator, tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/mlx_audio"), reason="the reference source is only present in the build container")
-@pytest.mark.parametrize("generator,n", [("make_whisper_golden.py", 4), ("make_qwen3_golden.py", 4), ("make_codec_golden.py", 5), ("make_kokoro_golden.py", 2)])
+@pytest.mark.parametrize("generator,n", [("make_dsp_golden.py", 12), ("make_whisper_golden.py", 4), ("make_qwen3_golden.py", 4), ("make_codec_golden.py", 5), ("make_kokoro_golden.py", 2)])
 def test_oracle_agrees_with_the_reference_code_on_random_configurations(generator, n):
     """Beyond the committed fixtures: ``--live N`` draws N random configurations (head counts, GQA ratios, MRoPE sections, code-book counts,
     stride lists, depthwise / noise switches, attention contexts, kernel sizes; for Kokoro random utterances, styles, speeds and weight
