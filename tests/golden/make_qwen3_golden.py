@@ -441,6 +441,30 @@ def live(n):
         errs.append(np.abs(wav - owav).max())
         worst = max(worst, float(max(errs)))
         print("qwen3 heads", heads, "kv", kv, "hd", hd, "mrope", sec, "groups", g, "| tokenizer ups", ups, rat, "nq", nq, "max err", float(max(errs)))
+    # sampler chain (qwen3_tts.py:805-860 over lm/sample_utils.py): random logits and settings, the same injected uniform on both sides
+    from mlx_audio.tts.models.qwen3_tts import qwen3_tts as QM
+    m = QM.Model.__new__(QM.Model)
+    mx.random.strict = True
+    n_cases = 60 * n
+    for case in range(n_cases):
+        rng = np.random.default_rng(9000 + case)
+        V = int(rng.integers(8, 300))
+        logits = rng.standard_normal(V) * float(rng.choice([0.5, 2.0, 6.0]))
+        kw = dict(temperature=float(rng.choice([0.0, 0.3, 0.9, 1.0, 1.7])), top_k=int(rng.choice([0, 1, 5, 50, 400])),
+                  top_p=float(rng.choice([1.0, 0.95, 0.7, 0.2])), repetition_penalty=float(rng.choice([1.0, 1.05, 1.5])),
+                  min_p=float(rng.choice([0.0, 0.0, 0.05, 0.3])))
+        gen = [int(v) for v in rng.integers(0, V + 20, size=int(rng.integers(0, 8)))] or None
+        sup = [int(v) for v in rng.choice(V, size=int(rng.integers(0, max(1, V // 4))), replace=False)] or None
+        if sup is not None and len(sup) >= V:
+            sup = sup[: V - 1]
+        u = float(rng.random())
+        mx.random.queue[:] = [("categorical", np.array([u]))]
+        tok = int(np.asarray(m._sample_token(mx.array(logits[None, None, :]), generated_tokens=gen, suppress_tokens=sup, **kw))[0, 0])
+        mx.random.queue[:] = []
+        want = OQ.sample_token(torch.as_tensor(logits), u, kw["temperature"], kw["top_k"], kw["top_p"], kw["repetition_penalty"], gen, sup, kw["min_p"])
+        assert tok == want, (case, kw, tok, want)
+    mx.random.strict = False
+    print("sampler cases identical:", n_cases)
     assert worst < 1e-9, worst
     print("LIVE OK", worst)
 
