@@ -155,6 +155,36 @@ def live(n):
             errs.append(np.abs(np.asarray(lg) - olg.numpy()).max())
         worst = max(worst, float(max(errs)))
         print("whisper", d, "max err", float(max(errs)))
+    # logit filters + greedy update on random logits under random token histories (decoding.py:307-442)
+    from mlx_audio.stt.models.whisper import decoding as D
+    tk = StubTokenizer()
+    spec = OW.TokenizerSpec(eot=200, sot=201, no_timestamps=208, timestamp_begin=209, no_speech=207, blank_ids=(7,), language=202, task=203,
+                            transcribe=203, translate=204, sot_lm=205, sot_prev=206)
+    T, E = tk.timestamp_begin, tk.eot
+    cases = 40 * n
+    for case in range(cases):
+        rng = np.random.default_rng(7000 + case)
+        B, L = int(rng.integers(1, 5)), int(rng.integers(0, 7))
+        pool = np.concatenate([rng.integers(0, E, size=20), rng.integers(T, 300, size=20), [E, T, T + 1]])
+        hist = rng.choice(pool, size=(B, L))
+        toks = np.concatenate([np.tile([201, 202, 203], (B, 1)), hist], axis=1).astype(np.int32)
+        logits = rng.standard_normal((B, 300)) * float(rng.choice([0.5, 3.0]))
+        if rng.random() < 0.4:
+            logits[:, T:] += float(rng.uniform(1, 6))
+        sup = sorted(set(int(v) for v in rng.integers(0, 300, size=int(rng.integers(0, 6)))))
+        mi = [None, 0, 2, 30][int(rng.integers(0, 4))]
+        filters = [D.SuppressBlank(tk, 3, 300)] + ([D.SuppressTokens(sup, 300)] if sup else []) + [D.ApplyTimestampRules(tk, 3, mi)]
+        y = mx.array(logits)
+        for f in filters:
+            y = f.apply(y, mx.array(toks))
+        want = OW.apply_filters(torch.as_tensor(logits), toks.tolist(), spec, 3, sup, max_initial_timestamp_index=mi).numpy()
+        y = np.asarray(y)
+        fin = np.isfinite(y)
+        assert np.array_equal(fin, np.isfinite(want)) and (not fin.any() or np.abs(y[fin] - want[fin]).max() < 1e-12), (case, toks.tolist(), sup, mi)
+        nt, comp, slp = D.GreedyDecoder(0.0, E).update(mx.array(toks), mx.array(y), mx.zeros(B))
+        ont, ocomp, oslp = OW.greedy_update(toks.tolist(), torch.as_tensor(want), torch.zeros(B, dtype=torch.float64), E)
+        assert np.array_equal(np.asarray(nt), np.array(ont)) and bool(comp) == ocomp and np.allclose(np.asarray(slp), oslp.numpy(), rtol=0, atol=1e-12, equal_nan=True), case
+    print("filter / greedy cases identical:", cases)
     assert worst < 1e-10, worst
     print("LIVE OK", worst)
 
