@@ -384,3 +384,35 @@ def test_whisper_decoding_results_are_assembled_like_the_reference_run():
             assert abs(r.compression_ratio - w["compression_ratio"]) < 1e-12
     from mlx_audio_b200.stt.models.whisper.whisper import compression_ratio
     assert compression_ratio("") == 0.0
+
+
+def test_product_never_touches_the_oracle_or_the_reference():
+    """The oracle is test infrastructure: no module of the product (mlx_audio_b200/, the mlx_audio/ shim, the C sources) may import, open or
+    mention-by-path ``oracle/`` or ``/root/reference``, and importing every product module must not pull ``oracle`` into sys.modules."""
+    import importlib
+    import os
+    import pkgutil
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|/root/reference|oracle/_ref|importlib[^\n]*oracle", re.M)
+    offenders = []
+    for base in ("mlx_audio_b200", "mlx_audio"):
+        for dp, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    if pat.search(open(os.path.join(dp, f), errors="ignore").read()):
+                        offenders.append(os.path.join(dp, f))
+    assert not offenders, offenders
+    code = ("import importlib, pkgutil, sys\n"
+            "for root in ('mlx_audio_b200', 'mlx_audio'):\n"
+            "    pkg = importlib.import_module(root)\n"
+            "    for m in pkgutil.walk_packages(pkg.__path__, root + '.'):\n"
+            "        if m.name.endswith(('.build', 'libb200audio')):\n"
+            "            continue\n"
+            "        importlib.import_module(m.name)\n"
+            "assert not any(k == 'oracle' or k.startswith('oracle.') for k in sys.modules), 'oracle imported'\n"
+            "print('clean')\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-1500:]
