@@ -116,7 +116,29 @@ def live(n):
                   f_max=float(rng.choice([sr / 2, sr / 2 - 1000.0])), norm=[None, "slaney"][int(rng.integers(0, 2))], mel_scale=str(rng.choice(["htk", "slaney"])))
         worst["mel"] = max(worst["mel"], float(np.abs(np.asarray(dsp.mel_filters(**mk)) - O.mel_filters(**mk)).max()))
         print("dsp", kw, "| istft", nf, hp, norm, "| mel", mk["sample_rate"], mk["n_mels"], mk["norm"], mk["mel_scale"])
+    # interpolate (tts/models/interpolate.py): nearest / linear, align_corners on / off / None, up- and down-scaling incl. the 300x of Kokoro's source
+    sys.path.insert(0, HERE)
+    import numpy_mlx_nn as nn_shim
+    core64, _ = nn_shim.install(precise=True)
+    interp = load(os.path.join(REF, "tts", "models", "interpolate.py"), "ref_interpolate_live")
+    worst["interp"] = 0.0
+    for seed in range(6 * n):
+        rng = np.random.default_rng(6000 + seed)
+        x = rng.standard_normal((int(rng.integers(1, 3)), int(rng.integers(1, 4)), int(rng.integers(2, 700))))
+        mode = str(rng.choice(["nearest", "linear"]))
+        ac = [None, False, True][int(rng.integers(0, 3))] if mode == "linear" else None
+        if rng.random() < 0.5:
+            kw = dict(scale_factor=float(rng.choice([2.0, 0.5, 1 / 3, 3.0, 300.0, 1 / 300, 1.7])))
+        else:
+            kw = dict(size=int(rng.integers(1, 900)))
+        if x.shape[-1] * kw.get("scale_factor", 1.0) > 40000:
+            x = x[..., :100]
+        a = np.asarray(interp.interpolate(core64.array(x), mode=mode, align_corners=ac, **kw))
+        b = O.interpolate(x, mode=mode, align_corners=ac, **kw)
+        assert a.shape == np.asarray(b).shape, (x.shape, kw, mode, ac, a.shape, np.asarray(b).shape)
+        worst["interp"] = max(worst["interp"], float(np.abs(a - np.asarray(b)).max()))
     print(worst)
+    assert worst["interp"] < 1e-12, worst
     assert worst["stft"] < 2e-4 and worst["istft"] < 5e-5 and worst["mel"] < 5e-6 and worst["window"] < 1e-6, worst
     print("LIVE OK", worst)
 
