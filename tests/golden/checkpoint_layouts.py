@@ -120,3 +120,73 @@ def mimi_torch():
          ("quantizer.rvq_first.vq.layers.0._codebook.cluster_usage", (64,)), ("quantizer.rvq_rest.vq.layers.2._codebook.embedding_sum", (64, 16)),
          ("quantizer.rvq_rest.output_proj.weight", (32, 16, 1)), ("downsample.conv.conv.conv.weight", (32, 32, 4)), ("upsample.convtr.convtr.convtr.weight", (32, 1, 4))]
     return _fill(e)
+
+
+HF_MIMI_SMALL = dict(hidden_size=32, num_filters=4, upsampling_ratios=[8, 6, 5, 4], intermediate_size=64, num_attention_heads=4, num_key_value_heads=4,
+                     head_dim=8, num_hidden_layers=2, codebook_size=64, codebook_dim=16, vector_quantization_hidden_dimension=16, num_quantizers=6,
+                     num_semantic_quantizers=1, sliding_window=250, upsample_groups=32)
+ORACLE_MIMI_SMALL = {"dimension": 32, "nfilters": 4, "ratios": [8, 6, 5, 4], "ksize": 7, "residual_ksize": 3, "last_ksize": 3, "compress": 2, "d_model": 32,
+                     "num_heads": 4, "num_layers": 2, "dim_feedforward": 64, "context": 250, "max_period": 10000, "layer_scale": 0.01, "nq": 6, "bins": 64,
+                     "qdim": 16, "upsample_stride": 2, "valid_num_quantizers": 16}
+
+
+def qwen3_tokenizer_encoder_hf():
+    """The ENCODER half of ``speech_tokenizer/model.safetensors``: transformers' MimiModel state-dict names under an ``encoder.`` prefix
+    (speech_tokenizer.py:1253-1388 maps them onto Mimi modules).  Names and shapes come from a small transformers MimiModel."""
+    import transformers
+    m = transformers.MimiModel(transformers.MimiConfig(**HF_MIMI_SMALL))
+    keep = ("encoder.", "encoder_transformer.", "downsample.", "quantizer.")
+    return _fill([("encoder." + k, tuple(v.shape)) for k, v in m.state_dict().items() if k.startswith(keep)])
+
+
+def map_hf_mimi_encoder(weights):
+    """The encoder branch of Qwen3TTSSpeechTokenizer.sanitize (speech_tokenizer.py:1253-1415), restated for tests: SEANet layer indices ->
+    init / residual / downsample / final convs, q/k/v -> one in_proj, (out, in, K) -> (out, K, in), code books kept as sum + usage."""
+    import re
+    conv_map = {0: "encoder_model.encoder.init_conv1d", 3: "encoder_model.encoder.layers.0.downsample", 6: "encoder_model.encoder.layers.1.downsample",
+                9: "encoder_model.encoder.layers.2.downsample", 12: "encoder_model.encoder.layers.3.downsample", 14: "encoder_model.encoder.final_conv1d"}
+    res_map, blk_map = {1: 0, 4: 1, 7: 2, 10: 3}, {1: 0, 3: 1}
+    tr = {"self_attn.o_proj.weight": "self_attn.out_proj.weight", "mlp.fc1.weight": "gating.linear1.weight", "mlp.fc2.weight": "gating.linear2.weight",
+          "input_layernorm.weight": "norm1.weight", "input_layernorm.bias": "norm1.bias", "post_attention_layernorm.weight": "norm2.weight",
+          "post_attention_layernorm.bias": "norm2.bias", "self_attn_layer_scale.scale": "layer_scale_1.scale", "mlp_layer_scale.scale": "layer_scale_2.scale"}
+    out, qkv = {}, {}
+    sw = lambda v: v.swapaxes(-1, -2) if v.ndim == 3 else v                                     # noqa: E731
+    for k, v in weights.items():
+        if not k.startswith("encoder."):
+            continue
+        parts = k.split(".")
+        if k.startswith("encoder.encoder.layers."):
+            n = int(parts[3])
+            if "block" in k:
+                if n not in res_map or int(parts[5]) not in blk_map:
+                    continue
+                base, suffix = f"encoder_model.encoder.layers.{res_map[n]}.residuals.0.block.{blk_map[int(parts[5])]}", ".".join(parts[6:])
+            else:
+                if n not in conv_map:
+                    continue
+                base, suffix = conv_map[n], ".".join(parts[4:])
+            out[f"{base}.conv.{suffix}"] = sw(v) if "weight" in suffix else v
+        elif k.startswith("encoder.encoder_transformer.layers."):
+            li, rest = int(parts[3]), ".".join(parts[4:])
+            pre = f"encoder_model.encoder_transformer.transformer.layers.{li}."
+            m = re.match(r"self_attn\.([qkv])_proj\.weight", rest)
+            if m:
+                qkv.setdefault(li, {})[m.group(1)] = v
+            elif rest in tr:
+                out[pre + tr[rest]] = v
+        elif k.startswith("encoder.downsample."):
+            suffix = k.replace("encoder.downsample.", "")
+            out[f"encoder_model.downsample.conv.conv.{suffix}"] = sw(v) if "weight" in suffix else v
+        elif k.startswith("encoder.quantizer."):
+            rest = k.replace("encoder.quantizer.", "")
+            which = "rvq_first" if "semantic_residual_vector_quantizer" in rest else "rvq_rest"
+            m = re.search(r"layers\.(\d+)\.codebook\.(cluster_usage|embed_sum)", rest)
+            if m:
+                out[f"encoder_model.quantizer.{which}.vq.layers.{m.group(1)}.codebook.{'embedding_sum' if m.group(2) == 'embed_sum' else 'cluster_usage'}"] = v
+            elif "input_proj.weight" in rest or "output_proj.weight" in rest:
+                out[f"encoder_model.quantizer.{which}.{'input_proj' if 'input_proj' in rest else 'output_proj'}.weight"] = sw(v)
+    for li, d in qkv.items():
+        if len(d) == 3:
+            cat = __import__("numpy").concatenate if not hasattr(d["q"], "dim") else __import__("torch").cat
+            out[f"encoder_model.encoder_transformer.transformer.layers.{li}.self_attn.in_proj.weight"] = cat([d["q"], d["k"], d["v"]], 0)
+    return out

@@ -15,6 +15,7 @@ sys.path.insert(0, HERE)
 import numpy_mlx_nn as shim          # noqa: E402
 import checkpoint_layouts as L      # noqa: E402
 
+ENC_HF = L.qwen3_tokenizer_encoder_hf()        # needs the real transformers / huggingface_hub: taken before the stand-ins are installed
 REF = "/root/reference/mlx_audio"
 mx, nn = shim.install(precise=True)
 for name, path in (("mlx_audio", REF), ("mlx_audio.lm", f"{REF}/lm"), ("mlx_audio.lm.models", f"{REF}/lm/models"), ("mlx_audio.tts", f"{REF}/tts"),
@@ -53,6 +54,8 @@ def main():
     out["qwen3_model"] = manifest(Q.Model.sanitize({k: mx.array(v) for k, v in L.qwen3_model_torch().items()}))
     full = S.Qwen3TTSSpeechTokenizer.sanitize({k: mx.array(v) for k, v in L.qwen3_tokenizer_torch().items()})
     out["qwen3_tokenizer_decoder"] = manifest({k: v for k, v in full.items() if not k.startswith("encoder_model.")})
+    enc = S.Qwen3TTSSpeechTokenizer.sanitize({k: mx.array(v) for k, v in ENC_HF.items()})
+    out["qwen3_tokenizer_encoder"] = manifest(enc)
     from mlx_audio.tts.models.kokoro import kokoro as K
     sys.path.insert(0, ROOT)
     from oracle.kokoro import KOKORO_CONFIG                          # constants only: the public configuration

@@ -46,3 +46,26 @@ def test_whisper_oracle_and_sanitize_agree_with_the_transformers_implementation(
     xa = OW.encoder(P, mel, d)
     lg, _ = OW.decoder_forward(P, toks, xa, None, d)
     assert float((enc - xa).abs().max()) < 1e-12 and float((logits - lg).abs().max()) < 1e-12
+
+
+def test_speech_tokenizer_encoder_oracle_agrees_with_the_transformers_mimi_encoder():
+    """The Qwen3-TTS speech-tokenizer ENCODER is transformers' Mimi encoder re-hosted on the reference's Mimi modules (speech_tokenizer.py:957-1058,
+    1253-1415).  A transformers MimiModel filled with the synthetic weights -> ``encode(audio)``; the same weights through the restated key mapping
+    (equal to the reference's own ``sanitize``: sanitize_golden.json) -> the oracle's ``tokenizer_encode``.  The code streams must be IDENTICAL: SEANet
+    encoder, half-split RoPE, replicate-padded stride-2 conv and the residual nearest-code search all mean what the oracle says they mean."""
+    import json
+    import zlib
+    import checkpoint_layouts as L
+    from oracle import qwen3 as Q
+    W = L.qwen3_tokenizer_encoder_hf()
+    mapped = L.map_hf_mimi_encoder(W)
+    want = json.load(open(os.path.join(HERE, "sanitize_golden.json")))["qwen3_tokenizer_encoder"]
+    assert {k: [list(v.shape), zlib.crc32(np.ascontiguousarray(v, dtype=np.float32).tobytes())] for k, v in mapped.items()} == want
+    hf = transformers.MimiModel(transformers.MimiConfig(**L.HF_MIMI_SMALL)).double().eval()
+    missing, unexpected = hf.load_state_dict({k[len("encoder."):]: torch.as_tensor(v).double() for k, v in W.items()}, strict=False)
+    assert not unexpected and all(k.startswith(("decoder", "upsample")) for k in missing)
+    P = {k: torch.as_tensor(np.asarray(v)).double() for k, v in mapped.items()}
+    audio = torch.as_tensor(0.4 * np.random.default_rng(3).standard_normal((2, 1, 7 * 1920 + 500)))
+    with torch.no_grad():
+        codes = hf.encode(audio).audio_codes
+    assert tuple(codes.shape) == (2, 6, 8) and torch.equal(codes, Q.tokenizer_encode(P, audio, L.ORACLE_MIMI_SMALL))
