@@ -69,3 +69,36 @@ def test_speech_tokenizer_encoder_oracle_agrees_with_the_transformers_mimi_encod
     with torch.no_grad():
         codes = hf.encode(audio).audio_codes
     assert tuple(codes.shape) == (2, 6, 8) and torch.equal(codes, Q.tokenizer_encode(P, audio, L.ORACLE_MIMI_SMALL))
+
+
+def test_reference_talker_outputs_agree_with_the_transformers_qwen3_decoder():
+    """qwen3_golden.npz holds what the REFERENCE's talker and code predictor computed (make_qwen3_golden.py).  With the three MRoPE position axes
+    equal -- the only case text-to-speech uses -- interleaved MRoPE is ordinary RoPE, and the talker is a Qwen3 decoder stack: transformers' Qwen3Model
+    with the same weights (identical parameter names) must reproduce the reference's hidden states and logits.  5e-6: transformers builds its rotary
+    table in float32."""
+    import json
+    import synth_params
+    g = np.load(os.path.join(HERE, "qwen3_golden.npz"))
+    cfg = json.loads(str(g["cfg"]))
+    P = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["talker_params"]).items()}
+
+    def stack(prefix, layers, hidden, inter, vocab):
+        hc = transformers.Qwen3Config(vocab_size=vocab, hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
+                                      num_attention_heads=cfg["num_attention_heads"], num_key_value_heads=cfg["num_key_value_heads"], head_dim=cfg["head_dim"],
+                                      rms_norm_eps=cfg["rms_norm_eps"], rope_theta=cfg["rope_theta"], max_position_embeddings=256, attention_bias=False,
+                                      tie_word_embeddings=False, use_sliding_window=False, attention_dropout=0.0)
+        m = transformers.Qwen3Model(hc).double().eval()
+        sd = {k: P[prefix + k] for k in m.state_dict() if prefix + k in P}
+        sd["embed_tokens.weight"] = torch.zeros(vocab, hidden, dtype=torch.float64)                      # unused: inputs_embeds are given
+        assert not m.load_state_dict(sd, strict=True).missing_keys
+        return m
+    talker = stack("model.", cfg["num_hidden_layers"], cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"])
+    with torch.no_grad():
+        h = talker(inputs_embeds=torch.as_tensor(g["t_x"])).last_hidden_state
+    assert float((h - torch.as_tensor(g["t_hidden"])).abs().max()) < 5e-6
+    assert float((h @ P["codec_head.weight"].T - torch.as_tensor(g["t_logits"])).abs().max()) < 5e-6
+    cp = stack("code_predictor.model.", cfg["cp_num_hidden_layers"], cfg["cp_hidden_size"], cfg["cp_intermediate_size"], cfg["cp_vocab_size"])
+    x = torch.as_tensor(g["cp_x"]) @ P["code_predictor.small_to_mtp_projection.weight"].T + P["code_predictor.small_to_mtp_projection.bias"]
+    with torch.no_grad():
+        hc_ = cp(inputs_embeds=x).last_hidden_state
+    assert float((hc_[:, -1] @ P["code_predictor.lm_head.0.weight"].T - torch.as_tensor(g["cp_logits"][:, 0])).abs().max()) < 5e-6
