@@ -190,3 +190,54 @@ def map_hf_mimi_encoder(weights):
             cat = __import__("numpy").concatenate if not hasattr(d["q"], "dim") else __import__("torch").cat
             out[f"encoder_model.encoder_transformer.transformer.layers.{li}.self_attn.in_proj.weight"] = cat([d["q"], d["k"], d["v"]], 0)
     return out
+
+
+def map_hf_mimi_decoder(sd, heads, head_dim):
+    """transformers MimiModel (decode side) -> the reference's Mimi module tree (codec/models/mimi), for the independent cross-check of the
+    oracle's ``mimi_decode``.  The reference's Mimi rotates interleaved pairs (nn.RoPE(traditional=True), kyutai's convention) while
+    transformers rotates half-split pairs of permuted projections: q / k rows are re-interleaved per head so that both compute the same
+    attention.  torch tensors in, torch tensors out."""
+    import re
+    import torch
+
+    def interleave(w):
+        w = w.reshape(heads, head_dim, -1)
+        out = torch.empty_like(w)
+        out[:, 0::2], out[:, 1::2] = w[:, : head_dim // 2], w[:, head_dim // 2:]
+        return out.reshape(heads * head_dim, -1)
+    tr = {"self_attn.o_proj.weight": "self_attn.out_proj.weight", "mlp.fc1.weight": "gating.linear1.weight", "mlp.fc2.weight": "gating.linear2.weight",
+          "input_layernorm.weight": "norm1.weight", "input_layernorm.bias": "norm1.bias", "post_attention_layernorm.weight": "norm2.weight",
+          "post_attention_layernorm.bias": "norm2.bias", "self_attn_layer_scale.scale": "layer_scale_1.scale", "mlp_layer_scale.scale": "layer_scale_2.scale"}
+    P, qkv = {}, {}
+    sw = lambda v: v.transpose(-1, -2) if v.dim() == 3 else v                                  # noqa: E731
+    for k, v in sd.items():
+        p = k.split(".")
+        if k.startswith("decoder.layers."):
+            n = int(p[2])
+            if n == 0:
+                P["decoder.init_conv1d.conv.conv." + p[-1]] = sw(v)
+            elif n == 14:
+                P["decoder.final_conv1d.conv.conv." + p[-1]] = sw(v)
+            elif n in (2, 5, 8, 11):
+                P[f"decoder.layers.{(n - 2) // 3}.upsample.convtr.convtr." + p[-1]] = v.permute(1, 2, 0) if v.dim() == 3 else v
+            else:
+                P[f"decoder.layers.{(n - 3) // 3}.residuals.0.block.{ {1: 0, 3: 1}[int(p[4])] }.conv.conv." + p[-1]] = sw(v)
+        elif k.startswith("decoder_transformer.layers."):
+            li, rest = int(p[2]), ".".join(p[3:])
+            m = re.match(r"self_attn\.([qkv])_proj\.weight", rest)
+            if m:
+                qkv.setdefault(li, {})[m.group(1)] = v
+            elif rest in tr:
+                P[f"decoder_transformer.transformer.layers.{li}." + tr[rest]] = v
+        elif k == "upsample.conv.weight":
+            P["upsample.convtr.convtr.convtr.weight"] = v.permute(0, 2, 1)
+        elif k.startswith("quantizer."):
+            which = "rvq_first" if "semantic" in k else "rvq_rest"
+            m = re.search(r"layers\.(\d+)\.codebook\.(cluster_usage|embed_sum)", k)
+            if m:
+                P[f"quantizer.{which}.vq.layers.{m.group(1)}.codebook." + ("embedding_sum" if m.group(2) == "embed_sum" else "cluster_usage")] = v
+            elif "output_proj.weight" in k:
+                P[f"quantizer.{which}.output_proj.weight"] = sw(v)
+    for li, d in qkv.items():
+        P[f"decoder_transformer.transformer.layers.{li}.self_attn.in_proj.weight"] = torch.cat([interleave(d["q"]), interleave(d["k"]), d["v"]], 0)
+    return P

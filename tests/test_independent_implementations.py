@@ -102,3 +102,25 @@ def test_reference_talker_outputs_agree_with_the_transformers_qwen3_decoder():
     with torch.no_grad():
         hc_ = cp(inputs_embeds=x).last_hidden_state
     assert float((hc_[:, -1] @ P["code_predictor.lm_head.0.weight"].T - torch.as_tensor(g["cp_logits"][:, 0])).abs().max()) < 5e-6
+
+
+def test_mimi_decode_oracle_agrees_with_the_transformers_mimi_decoder():
+    """transformers' MimiModel.decode vs the oracle's ``mimi_decode`` on the same synthetic weights (keys mapped onto the reference's module tree,
+    q / k rows re-interleaved because the reference rotates interleaved pairs where transformers rotates half-split pairs).  2e-7 with the tanh GELU
+    the reference's MLP uses (``nn.gelu_approx``, transformer.py:141); with transformers' default exact GELU the two differ by ~1e-4 -- the size of the
+    reference's own departure from the original model, noted here, not corrected."""
+    import checkpoint_layouts as L
+    import synth_params
+    from oracle import codec as OC
+    codes = torch.as_tensor(np.random.default_rng(1).integers(0, 64, size=(2, 6, 9)))
+    err = {}
+    for act in ("gelu_pytorch_tanh", "gelu"):
+        hf = transformers.MimiModel(transformers.MimiConfig(**L.HF_MIMI_SMALL, hidden_act=act)).double().eval()
+        sd = {k: torch.as_tensor(synth_params.value(k, tuple(v.shape))).double() for k, v in hf.state_dict().items()}
+        hf.load_state_dict(sd)
+        with torch.no_grad():
+            a = hf.decode(codes).audio_values
+        o = OC.mimi_decode(L.map_hf_mimi_decoder(sd, heads=4, head_dim=8), codes, dict(L.ORACLE_MIMI_SMALL))
+        assert a.shape == o.shape == (2, 1, 9 * 1920)
+        err[act] = float((a - o).abs().max())
+    assert err["gelu_pytorch_tanh"] < 2e-7 and 1e-6 < err["gelu"] < 1e-2, err
