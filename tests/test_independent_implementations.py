@@ -124,3 +124,20 @@ def test_mimi_decode_oracle_agrees_with_the_transformers_mimi_decoder():
         assert a.shape == o.shape == (2, 1, 9 * 1920)
         err[act] = float((a - o).abs().max())
     assert err["gelu_pytorch_tanh"] < 2e-7 and 1e-6 < err["gelu"] < 1e-2, err
+
+
+def test_stft_oracle_agrees_with_torch_stft_where_the_reference_does():
+    """torch.stft vs the oracle's ``stft`` (symmetric Hann, centred, reflect / constant padding): 1e-13 whenever the window fills the frame.
+    With win_length < n_fft they differ BY DESIGN: the reference zero-pads the window on the right (dsp.py:399-403, pinned by dsp_golden.npz
+    "shortwin"), torch and librosa centre it."""
+    from oracle import dsp as O
+    x = np.random.default_rng(2).standard_normal(4000)
+    for n_fft, hop in ((400, 160), (20, 5), (256, 64), (1024, 256)):
+        for pad_mode in ("reflect", "constant"):
+            w = torch.as_tensor(O.hanning(n_fft, periodic=False))
+            t = torch.stft(torch.as_tensor(x), n_fft, hop, n_fft, window=w, center=True, pad_mode=pad_mode, return_complex=True).T.numpy()
+            o = O.stft(x, n_fft=n_fft, hop_length=hop, window="hann", center=True, pad_mode=pad_mode)
+            assert t.shape == o.shape and np.abs(t - o).max() < 1e-12
+    w = torch.as_tensor(O.hanning(400, periodic=False))
+    t = torch.stft(torch.as_tensor(x), 512, 128, 400, window=w, center=True, pad_mode="reflect", return_complex=True).T.numpy()
+    assert np.abs(t - O.stft(x, n_fft=512, hop_length=128, win_length=400)).max() > 1.0
