@@ -141,3 +141,35 @@ def test_stft_oracle_agrees_with_torch_stft_where_the_reference_does():
     w = torch.as_tensor(O.hanning(400, periodic=False))
     t = torch.stft(torch.as_tensor(x), 512, 128, 400, window=w, center=True, pad_mode="reflect", return_complex=True).T.numpy()
     assert np.abs(t - O.stft(x, n_fft=512, hop_length=128, win_length=400)).max() > 1.0
+
+
+def test_kokoro_albert_and_lstm_oracles_agree_with_transformers_and_torch():
+    """Kokoro's text side against two independent implementations on the synthetic 82M weights: transformers' AlbertModel (same parameter names as
+    the reference's CustomAlbert; exact GELU as the reference uses -- the original PL-BERT default "gelu_new" would differ by ~1e-3) and
+    torch.nn.LSTM (the reference's hand-written bidirectional LSTM, modules.py:93-285, follows PyTorch's gate order and double bias)."""
+    from mlx_audio_b200 import synth
+    from oracle import kokoro as OK
+    cfg, pb = OK.KOKORO_CONFIG, OK.KOKORO_CONFIG["plbert"]
+    P = {k: v.double() for k, v in synth.kokoro_weights(cfg, seed=0).items()}
+    ac = transformers.AlbertConfig(vocab_size=cfg["n_token"], embedding_size=128, hidden_size=pb["hidden_size"], num_hidden_layers=pb["num_hidden_layers"],
+                                   num_attention_heads=pb["num_attention_heads"], intermediate_size=pb["intermediate_size"],
+                                   max_position_embeddings=pb["max_position_embeddings"], hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+                                   hidden_act="gelu", num_hidden_groups=1, inner_group_num=1, type_vocab_size=2)
+    hf = transformers.AlbertModel(ac).double().eval()
+    assert not hf.load_state_dict({k: P["bert." + k] for k in hf.state_dict()}, strict=True).missing_keys
+    ids = torch.as_tensor(np.random.default_rng(0).integers(1, cfg["n_token"], size=(1, 17)))
+    with torch.no_grad():
+        h = hf(input_ids=ids, attention_mask=torch.ones_like(ids)).last_hidden_state
+    assert float((h - OK.albert(P, ids, torch.ones_like(ids), pb)).abs().max()) < 1e-12
+    pre = "predictor.lstm"
+    hid, inp = P[pre + ".Wh_forward"].shape[1], P[pre + ".Wx_forward"].shape[1]
+    lstm = torch.nn.LSTM(inp, hid, batch_first=True, bidirectional=True).double()
+    with torch.no_grad():
+        for d, suffix in (("forward", ""), ("backward", "_reverse")):
+            getattr(lstm, "weight_ih_l0" + suffix).copy_(P[f"{pre}.Wx_{d}"])
+            getattr(lstm, "weight_hh_l0" + suffix).copy_(P[f"{pre}.Wh_{d}"])
+            getattr(lstm, "bias_ih_l0" + suffix).copy_(P[f"{pre}.bias_ih_{d}"])
+            getattr(lstm, "bias_hh_l0" + suffix).copy_(P[f"{pre}.bias_hh_{d}"])
+        x = torch.as_tensor(np.random.default_rng(1).standard_normal((2, 23, inp)))
+        want, _ = lstm(x)
+    assert float((want - OK.lstm_bi(P, pre, x)).abs().max()) < 1e-12
