@@ -173,3 +173,27 @@ def test_kokoro_albert_and_lstm_oracles_agree_with_transformers_and_torch():
         x = torch.as_tensor(np.random.default_rng(1).standard_normal((2, 23, inp)))
         want, _ = lstm(x)
     assert float((want - OK.lstm_bi(P, pre, x)).abs().max()) < 1e-12
+
+
+def test_interpolate_and_istft_oracles_agree_with_torch():
+    """torch.nn.functional.interpolate (nearest / linear, align_corners on and off, up- and down-scaling incl. Kokoro's x300 and /300) and torch.istft
+    (window-squared normalisation = the reference's ``normalized=True``) against the oracle's restatements of tts/models/interpolate.py and
+    dsp.py:436-513."""
+    import torch.nn.functional as F
+    from oracle import dsp as O
+    rng = np.random.default_rng(0)
+    for length, kw in ((50, dict(scale_factor=2.0)), (300, dict(scale_factor=1 / 3)), (7, dict(size=20)), (40, dict(size=13)), (10, dict(scale_factor=300.0)),
+                       (3000, dict(scale_factor=1 / 300))):
+        x = rng.standard_normal((2, 3, length))
+        for mode, ac in (("nearest", None), ("linear", False), ("linear", True)):
+            t = F.interpolate(torch.as_tensor(x), mode=mode, align_corners=ac, **kw).numpy()
+            o = np.asarray(O.interpolate(x, mode=mode, align_corners=ac, **kw))
+            assert t.shape == o.shape and np.abs(t - o).max() < 1e-12, (length, kw, mode, ac)
+    y = rng.standard_normal(2048)
+    for n_fft, hop in ((256, 64), (64, 16)):
+        w = torch.as_tensor(O.hanning(n_fft, periodic=True))
+        spec = torch.stft(torch.as_tensor(y), n_fft, hop, n_fft, window=w, center=True, pad_mode="reflect", return_complex=True)
+        t = torch.istft(spec, n_fft, hop, n_fft, window=w, center=True).numpy()
+        o = O.istft(spec.numpy(), hop_length=hop, win_length=n_fft, window=w.numpy(), center=True, normalized=True)
+        n = min(t.shape[0], o.shape[0])
+        assert abs(t.shape[0] - o.shape[0]) <= hop and np.abs(t[:n] - o[:n]).max() < 1e-10
