@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- Kokoro-82M TTS audio-seconds synthesised per wall-second on N B200s (BASELINE.json metric).
 
-Workload (BASELINE.json configs[1]): one 128-phoneme utterance (T = 130 tokens
-with BOS/EOS), durations pinned to 3 frames/token -> F = 390 frames -> 234 000 samples = 9.75 s of 24 kHz
-audio, synthetic bf16 checkpoint at the real Kokoro-82M shapes (81.8 M parameters), SineGen noise drawn
-on device every step.  A "step" = one utterance per GPU (weak scaling: every rank synthesises its own).
+Workload (BASELINE.json configs[1]): one 128-phoneme utterance (T = 130 tokens with BOS/EOS) through the
+model's OWN duration head (3 frames / token on the synthetic checkpoint -> F = 390 frames -> 234 000 samples = 9.75 s of 24 kHz
+audio), synthetic bf16 checkpoint at the real Kokoro-82M shapes (81.8 M parameters), SineGen noise drawn on device every step from
+an advancing Philox state.  A "step" = one utterance per GPU (weak scaling: every rank synthesises its own).
 
-  value      device-resident inputs, CUDA-graph replay of the whole utterance, K steps between
-             barrier+synchronize brackets, CUDA events, max over ranks.
-  e2e        the public API path with HOST buffers: pinned ids/style -> device, replay, waveform -> pinned host.
-  roofline   the dominant kernel family (dense conv1d / transposed conv of the decoder+generator stack):
-             algorithmic bytes per utterance (137.2 MB per audio-second, bf16
-             convention) / summed CUDA-event time of those launches, against MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the oracle port (torch-CPU fp32 restatement of the reference; MLX is not installable) on
-             the host cores, bounded sample.
+  value      device-resident inputs through the public graph path (`Model.synthesize_ids`: text-side graph -> ONE host read of the
+             frame count -> acoustic-side graph), K steps between barrier+synchronize brackets, CUDA events, max over ranks.
+             `value_pinned_durations` = the same with the durations supplied (no host read in the middle).
+  e2e        the call a user makes, with HOST buffers: `model(phonemes, ref_s_pinned, out=pinned)` -- phoneme string -> ids, H2D
+             copies, both graphs, waveform D2H into pinned memory, stream synchronised -- wall clock.
+  parity_rel_rms   the same graph path once more on the committed fixture inputs (tests/golden/bench_shapes_golden.npz: injected SineGen
+             noise + the oracle's float32 F0/N curves) against the cached float64-oracle waveform of THIS shape.
+  roofline   the dominant kernel family (dense conv1d / transposed conv of the decoder+generator stack).  Times are those of the
+             REPLAYED graph: an instrumented copy of the graphs carries event-record nodes around every launch; `kernel_ms` is the
+             wall-clock coverage (union of the intervals) of the family inside one replay, so it can never exceed ms_per_step.
+             Algorithmic bytes per utterance (137.2 MB per audio-second, bf16 convention) / that time,
+             against MEASURED_PEAKS.json hbm_gbs; `tensor` repeats it in flops against the sustained bf16 peak.
+  cpu_baseline  the oracle port (torch-CPU fp32 restatement of the reference; MLX is not installable) on the host cores, bounded sample.
 `--impl reference` times that same CPU restatement as the reference arm (rank 0 only).
+`--workload whisper|codec|qwen3` select the other BASELINE configurations (see the functions below).
 """
 from __future__ import annotations
 
@@ -29,9 +35,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-AUDIO_S_PER_UTT = 9.75
-N_PHONEMES, DUR = 128, 3
+N_PHONEMES = 128
 CONV_STACK_MB_PER_AUDIO_S = 137.2          # SURVEY.md section 8(d), Kokoro decoder+generator, bf16 convention
+CONV_STACK_GFLOP_PER_AUDIO_S = 58.84       # 573.7 GF per 9.75 s utterance (VERDICT r01 / SURVEY 8d), one bf16 product per MAC
 METRIC = "audio-sec/sec Kokoro-82M TTS (128-phoneme utterance, 9.75 s)"
 
 
@@ -40,7 +46,7 @@ def _peaks():
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             return json.load(f), "measured"
     except Exception:
-        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1590.0}, "fallback"
 
 
 class ClockSampler(threading.Thread):
@@ -78,23 +84,22 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_port_run(n_utts: int, threads: int):
-    """Time the oracle port (fp32 torch-CPU restatement of the reference) on `n_utts` cfg2 utterances."""
+    """Time the oracle port (fp32 torch-CPU restatement of the reference) on `n_utts` cfg2 utterances, durations from its own
+    duration head exactly like the GPU arm.  Returns (seconds per utterance list, audio seconds per utterance)."""
     import torch
     from mlx_audio_b200 import synth
+    from mlx_audio_b200.configs import KOKORO_82M
     from oracle import kokoro as OK
     torch.set_num_threads(threads)
     print(f"[bench] cpu port: {n_utts} utterance(s) on {threads} threads", file=sys.stderr, flush=True)
-    P = synth.kokoro_weights(OK.KOKORO_CONFIG)
+    P = synth.kokoro_weights(KOKORO_82M)
     ids, ref = synth.kokoro_inputs(N_PHONEMES)
-    T = ids.shape[1]
-    _, nz = synth.kokoro_noise(T * DUR * 600)
-    times = []
+    times, audio = [], None
     for _ in range(n_utts):
         t0 = time.perf_counter()
-        audio, _ = OK.forward(P, ids, ref, noise=nz, pred_dur_override=[DUR] * T)
+        audio, _ = OK.forward(P, ids, ref, noise=lambda n: synth.kokoro_noise(n)[1])
         times.append(time.perf_counter() - t0)
-    assert audio.shape[0] == int(AUDIO_S_PER_UTT * 24000)
-    return times
+    return times, audio.shape[0] / 24000.0
 
 
 def host_threads() -> int:
@@ -114,43 +119,81 @@ def host_threads() -> int:
     return max(1, min(n, 32))
 
 
+WORKLOAD_NAME = "kokoro-82m cfg2: 128 phonemes (T=130), model duration head -> F=390 frames, 234000 samples = 9.75 s per step per GPU"
+
+
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU implementation of the path, here its restatement (MLX cannot be installed)."""
     if rank != 0:
         return
     cores = host_threads()
     cpu_port_run(1, cores)           # warm-up (bounded: one utterance)
-    times = cpu_port_run(args.steps, cores)
+    times, audio_s = cpu_port_run(args.steps, cores)
     total = sum(times)
-    v = AUDIO_S_PER_UTT * len(times) / total
+    v = audio_s * len(times) / total
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "kokoro-82m cfg2: 128 phonemes, F=390 frames, 9.75 s audio per step", "parallelism": "cpu"},
+            "config": {"workload": WORKLOAD_NAME, "parallelism": "cpu"},
             "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": f"{len(times)} full cfg2 utterances, torch-CPU fp32 restatement of the reference (oracle/kokoro.py)"},
             "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
-    ap.add_argument("--cpu-utts", type=int, default=4, help="utterances in the cpu_baseline sample")
-    ap.add_argument("--ncu", action="store_true", help="profiling aid: 2 eager warm-up steps, then ONE eager step between "
-                    "cudaProfilerStart/Stop (run under `ncu --profile-from-start off`); prints no bench line")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
+def _union_ms(intervals):
+    """Total length of the union of (start, end) intervals."""
+    tot, cur_s, cur_e = 0.0, None, None
+    for s, e in sorted(intervals):
+        if cur_e is None or s > cur_e:
+            if cur_e is not None:
+                tot += cur_e - cur_s
+            cur_s, cur_e = s, e
+        else:
+            cur_e = max(cur_e, e)
+    if cur_e is not None:
+        tot += cur_e - cur_s
+    return tot
 
+
+def kokoro_graph_profile(model, ops, torch, ids_d, ref_d, dev, reps=3):
+    """Per-launch times INSIDE the replayed graphs: a second model object (same weights) captures its graphs while ops.PROFILE is on
+    with external events, so every launch is bracketed by event-record nodes; each replay re-stamps them."""
+    from mlx_audio_b200.tts.models.kokoro import Model
+    prof = {}
+    twin = Model(model.config, device=dev)
+    twin._w, twin._ada_slices, twin._ada_pred, twin._raw = model._w, model._ada_slices, model._ada_pred, getattr(model, "_raw", None)
+    twin.seed(7)
+    ops.PROFILE, ops.PROFILE_EXTERNAL = prof, True
+    try:
+        twin.synthesize_ids(ids_d, ref_d)                 # captures both graphs with the event nodes (the eager warm-ups also append)
+    finally:
+        ops.PROFILE, ops.PROFILE_EXTERNAL = None, False
+    # keep only the events recorded during the two captures: they are the LAST n of each kind, where n = launches in the captured pass;
+    # simplest robust filter: an event pair that was never re-stamped by a replay raises / returns garbage -> use a base event in-graph
+    t_base = torch.cuda.Event(enable_timing=True)
+    per_kind, cover = {}, {}
+    for _ in range(reps):
+        t_base.record()
+        twin.synthesize_ids(ids_d, ref_d)
+        torch.cuda.synchronize(dev)
+        for kind, evs in prof.items():
+            iv = []
+            for a, b in evs:
+                try:
+                    s, e = t_base.elapsed_time(a), t_base.elapsed_time(b)
+                except Exception:
+                    continue
+                if s >= 0.0 and e >= s:                   # events of the eager warm-up passes lie BEFORE t_base: negative -> dropped
+                    iv.append((s, e))
+            per_kind.setdefault(kind, []).append(sum(e - s for s, e in iv))
+            cover.setdefault(kind, []).append(iv)
+    n_launch = {k: len(v[-1]) for k, v in cover.items()}
+    by_kind = {k: sum(v) / len(v) for k, v in per_kind.items()}
+    return by_kind, {k: v[-1] for k, v in cover.items()}, n_launch
+
+
+def main_kokoro(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -160,75 +203,90 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    import numpy as np
     from mlx_audio_b200 import ops, synth
+    from mlx_audio_b200.configs import KOKORO_82M
     from mlx_audio_b200.tts.models.kokoro import Model, ModelConfig
-    from mlx_audio_b200.tts.models.kokoro.kokoro import CapturedUtterance
-    from oracle.kokoro import KOKORO_CONFIG            # config dict only (data); the oracle itself runs in cpu_baseline
 
     W = max(args.warmup, 3)
     K = args.steps
     log = lambda m: print(f"[bench r{rank} {time.strftime('%H:%M:%S')}] {m}", file=sys.stderr, flush=True)
     log("building synthetic checkpoint")
-    P = synth.kokoro_weights(KOKORO_CONFIG, seed=0)
-    model = Model(ModelConfig.from_dict(KOKORO_CONFIG), device=dev).load_weights(list(P.items()))
+    P = synth.kokoro_weights(KOKORO_82M, seed=0)
+    model = Model(ModelConfig.from_dict(KOKORO_82M), device=dev).load_weights(list(P.items()))
+    model.use_graphs = not args.no_graph
+    model.seed(1234 + rank)
     ids, ref_s = synth.kokoro_inputs(N_PHONEMES, seed=1 + rank)
     T = ids.shape[1]
-    F = T * DUR
-    n_samples = F * 600
     ids_d, ref_d = ids[0].to(dev), ref_s.to(dev)
-    dur_d = torch.full((T,), DUR, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > 126 MB L2
+    # vocabulary for the string entry point: symbol i <-> token id i (ids 1..177 are used by the synthetic utterance)
+    model.vocab = {chr(0x100 + i): i for i in range(1, KOKORO_82M["n_token"])}
+    phonemes = "".join(chr(0x100 + int(i)) for i in ids[0, 1:-1])
 
-    log("model ready; capturing")
-    cap = CapturedUtterance(model, T, F, seed=1234 + rank)
-    cap.set_inputs(ids_d, ref_d, dur_d)
-    noise_buf = torch.empty(1, n_samples, 9, device=dev)
+    run_ids = model.synthesize_ids if model.use_graphs else model.forward_ids
 
-    def step_eager():
-        ops.randn_(noise_buf, 1234 + rank, 0)
-        return model.forward_ids(ids_d, ref_d, noise=noise_buf, pred_dur=dur_d, n_frames=F)[0]
+    def step():
+        return run_ids(ids_d, ref_d)[0]
 
     if args.ncu:
         for _ in range(2):
-            step_eager()
+            model.forward_ids(ids_d, ref_d)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
-        step_eager()
+        model.forward_ids(ids_d, ref_d)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
         return
-    if args.no_graph:
-        step = step_eager
-        launches_per_step = None
-    else:
-        cap.capture()
-        step = cap.replay
-        launches_per_step = cap.launches
+    if args.ncu_graph:
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
+
+    log("model ready; capturing")
+    audio = step()
+    torch.cuda.synchronize(dev)
+    n_samples = int(audio.shape[0])
+    F = n_samples // 600
+    audio_s = n_samples / 24000.0
+    dur_d = torch.full((T,), F // T, dtype=torch.int64, device=dev)
+    dur_d[0] += F - int(dur_d.sum().item())
+    launches_per_step = None
+    if model.use_graphs:
+        launches_per_step = sum(v["launches"] for v in model._graphs.values()) + 2       # + the Philox draw (2 launches) between the graphs
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def timed(fn):
+        for _ in range(W):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            flush.zero_()                                                      # L2 flush between timed iterations
+            out = fn()
+        e1.record()
+        barrier()
+        return e0.elapsed_time(e1), out
+
     log("timing device-resident steps")
-    # ---------------- device-resident timing
-    for _ in range(W):
-        step()
     n0 = ops.LAUNCHES[0]
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        flush.zero_()                                                          # L2 flush between timed iterations
-        audio = step()
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, audio = timed(step)
     clocks = sampler.stop()
     launches = ops.LAUNCHES[0] - n0
     assert audio.shape[0] == n_samples and bool(torch.isfinite(audio).all())
+    ms_pinned, _ = timed(lambda: run_ids(ids_d, ref_d, pred_dur=dur_d, n_frames=F)[0])
     # L2 flush cost measured separately and subtracted (it is not part of the step)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
@@ -238,28 +296,25 @@ def main():
     f1.record()
     torch.cuda.synchronize(dev)
     ms_flush = f0.elapsed_time(f1)
-    ms_net = max(ms - ms_flush, 1e-6)
-    t = torch.tensor([ms_net], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * K * AUDIO_S_PER_UTT / (ms_max / 1e3)
 
-    log(f"value done: {ms_max / K:.3f} ms/step; timing e2e")
+    def rank_max(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_max = rank_max(max(ms - ms_flush, 1e-6))
+    ms_pinned_max = rank_max(max(ms_pinned - ms_flush, 1e-6))
+    value = world * K * audio_s / (ms_max / 1e3)
+
+    log(f"value done: {ms_max / K:.3f} ms/step ({ms_pinned_max / K:.3f} with pinned durations); timing e2e")
     # ---------------- end-to-end through the public call with host buffers
-    ids_h = ids[0].clone().pin_memory()
     ref_h = ref_s.clone().pin_memory()
     out_h = torch.empty(n_samples, dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        if args.no_graph:
-            a = model.forward_ids(ids_h.to(dev, non_blocking=True), ref_h.to(dev, non_blocking=True), noise=ops.randn_(noise_buf, 7, 0),
-                                  pred_dur=dur_d, n_frames=F)[0]
-        else:
-            cap.set_inputs(ids_h, ref_h)
-            a = cap.replay()
-        out_h.copy_(a, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()                            # the caller owns the waveform when this returns
+        model(phonemes, ref_h, 1.0, out=out_h)                                 # phoneme string -> ids -> H2D -> graphs -> D2H into pinned memory
+        torch.cuda.current_stream(dev).synchronize()                           # the caller owns the waveform when this returns
         return out_h
 
     for _ in range(W):
@@ -271,59 +326,101 @@ def main():
         step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0 - ms_flush / 1e3
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * K * AUDIO_S_PER_UTT / float(t.item())
+    e2e_value = world * K * audio_s / rank_max(e2e_s)
+    assert bool(torch.isfinite(out_h).all()) and float(out_h.abs().max()) > 0
+
+    # ---------------- parity of this very shape against the cached oracle waveform
+    parity = None
+    gpath = os.path.join(ROOT, "tests", "golden", "bench_shapes_golden.npz")
+    if os.path.exists(gpath) and rank == 0:
+        g = np.load(gpath)
+        ids0, ref0 = synth.kokoro_inputs(N_PHONEMES, seed=1)
+        nz = synth.kokoro_noise(ids0.shape[1] * 3 * 600, 3)[1].to(dev).contiguous()
+        f0n = (torch.as_tensor(g["kokoro_f0"]).to(dev), torch.as_tensor(g["kokoro_n"]).to(dev))
+        a, pd = run_ids(ids0[0].to(dev), ref0.to(dev), noise=nz, f0n_override=f0n)
+        want = torch.as_tensor(g["kokoro_audio"]).double()
+        got = a.double().cpu()
+        if got.shape == want.shape:
+            parity = float(torch.sqrt(((got - want) ** 2).mean()) / torch.sqrt((want ** 2).mean()))
+        else:
+            parity = float("nan")
+        log(f"parity vs cached oracle waveform (cfg2 shape, graph path): rel RMS {parity:.3e}")
 
     log("e2e done; instrumented pass")
-    # ---------------- roofline of the dominant kernel family (instrumented eager pass, CUDA events per launch)
-    prof = {"conv": [], "other": []}
-    ops.PROFILE = prof
-    nprof = 3
-    for _ in range(nprof):
-        step_eager()
-    torch.cuda.synchronize(dev)
-    ops.PROFILE = None
-    by_kind = {k: sum(a.elapsed_time(b) for a, b in v) / nprof for k, v in prof.items()}
-    conv_kinds = ("conv", "conv_tc", "prep")                   # the dense conv stack: CUDA-core convs, tcgen05 convs + their bf16 prologue
-    conv_ms = sum(by_kind.get(k, 0.0) for k in conv_kinds)
-    other_ms = sum(v for k, v in by_kind.items() if k not in conv_kinds)
-    n_conv = sum(len(prof.get(k, [])) for k in conv_kinds) // nprof
+    # ---------------- roofline of the dominant kernel family, timed inside the replayed graph
+    conv_kinds = ("conv", "conv_tc", "prep", "adain_stats")     # the dense conv stack: convs, their bf16 prologue and InstanceNorm statistics
+    timing_path = "graph event nodes"
+    try:
+        if not model.use_graphs:
+            raise RuntimeError("eager run requested")
+        by_kind, cover, n_launch = kokoro_graph_profile(model, ops, torch, ids_d, ref_d, dev)
+        if not by_kind or sum(n_launch.values()) == 0:
+            raise RuntimeError("no in-graph events came back")
+        conv_iv = [iv for k in conv_kinds for iv in cover.get(k, [])]
+        conv_ms = _union_ms(conv_iv)
+        conv_sum_ms = sum(by_kind.get(k, 0.0) for k in conv_kinds)
+        n_conv = sum(n_launch.get(k, 0) for k in conv_kinds)
+        all_ms = _union_ms([iv for v in cover.values() for iv in v])
+    except Exception as exc:                                   # older driver without timed event nodes: eager instrumented pass
+        log(f"graph-node timing unavailable ({exc}); falling back to the eager instrumented pass")
+        timing_path = "eager pass (serialises the graph's parallel branches)"
+        prof = {}
+        ops.PROFILE = prof
+        for _ in range(3):
+            model.forward_ids(ids_d, ref_d)
+        torch.cuda.synchronize(dev)
+        ops.PROFILE = None
+        by_kind = {k: sum(a.elapsed_time(b) for a, b in v) / 3 for k, v in prof.items()}
+        conv_ms = conv_sum_ms = sum(by_kind.get(k, 0.0) for k in conv_kinds)
+        n_conv = sum(len(prof.get(k, [])) for k in conv_kinds) // 3
+        all_ms = sum(by_kind.values())
     peaks, peak_kind = _peaks()
-    alg_bytes = CONV_STACK_MB_PER_AUDIO_S * 1e6 * AUDIO_S_PER_UTT                # per utterance, all conv launches
+    alg_bytes = CONV_STACK_MB_PER_AUDIO_S * 1e6 * audio_s                    # per utterance, all conv launches
+    alg_flops = CONV_STACK_GFLOP_PER_AUDIO_S * 1e9 * audio_s
     achieved = alg_bytes / (conv_ms / 1e3) / 1e9
-    traffic = None                                                               # measured DRAM bytes of the same kernels (ncu capture, committed)
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01b_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = float(json.load(open(tpath))["conv_stack_bytes_per_step"])
-        except Exception:
-            traffic = None
+    traffic = None                                                           # measured DRAM bytes of the same kernels (ncu capture, committed)
+    for name in ("r02_traffic.json", "r01b_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tpath):
+            try:
+                traffic = float(json.load(open(tpath))["conv_stack_bytes_per_step"])
+                break
+            except Exception:
+                traffic = None
+    tf = alg_flops / (conv_ms / 1e3) / 1e12
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic, "peak_kind": peak_kind, "kernel": "dense conv stack: conv_tc_persist_kernel (tcgen05, persistent) + prep_bf16_kernel, conv1d_dense/convtr1d_dense (CUDA-core)",
-                "launches_per_utterance": n_conv, "kernel_ms_per_utterance": conv_ms, "other_kernels_ms_per_utterance": other_ms,
+                "traffic": traffic, "peak_kind": peak_kind,
+                "kernel": "dense conv stack of the decoder + generator (tcgen05 conv kernels + CUDA-core strided / narrow convs, incl. their prologue and InstanceNorm statistics)",
+                "timing": timing_path, "launches_per_utterance": n_conv, "kernel_ms_per_utterance": conv_ms,
+                "kernel_ms_summed": conv_sum_ms, "all_kernels_ms_per_utterance": all_ms,
                 "ms_by_kind": {k: round(v, 3) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
-                "algorithmic_bytes_per_utterance": alg_bytes}
+                "algorithmic_bytes_per_utterance": alg_bytes,
+                "tensor": {"bound": "tensor", "achieved": tf, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "unit": "TFLOP/s",
+                           "frac": tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "algorithmic_flops_per_utterance": alg_flops,
+                           "note": "one bf16 product per MAC; the x2 (hi+lo) mode issues two"}}
 
     log("instrumented pass done")
     if rank == 0:
         cores = host_threads()
         cpu = None
         if world == 1 and args.cpu_utts > 0:
-            times = cpu_port_run(args.cpu_utts, cores)
-            cpu = {"value": AUDIO_S_PER_UTT * len(times) / sum(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
+            times, cpu_audio_s = cpu_port_run(args.cpu_utts, cores)
+            cpu = {"value": cpu_audio_s * len(times) / sum(times), "unit": "audio-s/s", "cores": cores, "kind": "port",
                    "sample": f"{len(times)} full cfg2 utterances ({sum(times):.1f} s), torch-CPU fp32 restatement of the reference"}
         line = {"metric": METRIC, "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if ops.TC_MODE[0] == "off" else ("bf16x2" if ops.TC_MODE[0] == "x2" else "bf16"), "data": "synthetic",
-                "config": {"workload": "kokoro-82m cfg2: 128 phonemes (T=130), durations pinned to 3 -> F=390 frames, 234000 samples = 9.75 s per step per GPU",
+                "config": {"workload": WORKLOAD_NAME,
                            "parallelism": f"utterance-sharded x{world} (no data-path collective)", "l2": "256 MiB flush between timed steps (its cost subtracted)",
-                           "launch": "eager" if args.no_graph else "cuda-graph replay", "weights": "synthetic bf16 checkpoint, 81.8 M params",
-                           "activations": "fp32 in HBM; tensor-core mode " + ops.TC_MODE[0] + " (x2 = hi+lo bf16 planes, fp32-grade products)"},
+                           "launch": "eager" if args.no_graph else "cuda-graph replay through Model.synthesize_ids (2 graphs + 1 host read of F)",
+                           "weights": "synthetic bf16 checkpoint, 81.8 M params",
+                           "activations": "fp32 in HBM; tensor-core mode " + ops.TC_MODE[0] + " (x2 = hi+lo bf16 planes, fp32-grade products)",
+                           "frames": F, "audio_s_per_step": audio_s},
                 "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(ids_h.numel() * 8 + ref_h.numel() * 4),
-                        "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                "value_pinned_durations": world * K * audio_s / (ms_pinned_max / 1e3), "ms_per_step_pinned_durations": ms_pinned_max / K,
+                "parity_rel_rms": parity,
+                "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(T * 8 + ref_h.numel() * 4),
+                        "d2h_bytes_per_step": int(out_h.numel() * 4 + 8), "call": "Model.__call__(phonemes, ref_s, out=pinned)"},
                 "roofline": roofline}
         if cpu:
             line["cpu_baseline"] = cpu
@@ -332,6 +429,32 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kokoro", choices=["kokoro", "whisper", "codec", "qwen3"])
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+    ap.add_argument("--cpu-utts", type=int, default=4, help="utterances in the cpu_baseline sample")
+    ap.add_argument("--ncu", action="store_true", help="profiling aid: 2 eager warm-up steps, then ONE eager step between "
+                    "cudaProfilerStart/Stop (run under `ncu --profile-from-start off`); prints no bench line")
+    ap.add_argument("--ncu-graph", action="store_true", help="like --ncu but the profiled step is the graph replay "
+                    "(run under `ncu --profile-from-start off --graph-profiling node`)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "kokoro":
+        from mlx_audio_b200 import bench_workloads
+        return bench_workloads.main(args, rank, world, local_rank)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    main_kokoro(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

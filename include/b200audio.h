@@ -205,6 +205,9 @@ int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_
 /* out[i] ~ N(0,1), i < n: Philox4x32-10 keyed by `seed`, counter `offset + i/4`, Box-Muller.  The production replacement for
  * mx.random.normal in SineGen / NoiseBlock (istftnet.py:649, snac/layers.py:263); parity tests inject the noise instead. */
 int32_t b2a_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+/* Same draws with {seed, offset} read from DEVICE memory (state[0], state[1]); a second one-thread launch then advances state[1] by the
+ * (n + 3) / 4 counters used, so a captured CUDA graph draws fresh noise on every replay the way mx.random's global state advances. */
+int32_t b2a_randn_dev(float* out, int64_t n, uint64_t* state, void* stream);
 
 /* ---- Whisper decode step (stt/models/whisper/decoding.py:307-325,349-442) -----------------------------------
  * One launch = SuppressBlank + SuppressTokens + ApplyTimestampRules + GreedyDecoder.update(temperature 0) for every row:

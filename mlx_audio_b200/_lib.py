@@ -73,6 +73,7 @@ PROTOTYPES = {
     "b2a_kokoro_source": (i32, [c_f, i32, i32, i32, c_f, c_f, c_f, c_f, c_f, c_f, C.c_void_p]),
     "b2a_kokoro_istft_head": (i32, [c_f, i64, i64, i32, i32, c_f, C.c_void_p]),
     "b2a_randn": (i32, [c_f, i64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "b2a_randn_dev": (i32, [c_f, i64, c_f, C.c_void_p]),
     "b2a_whisper_greedy_step": (i32, [c_f, i64, c_f, i64, i32, i32, i32, i32, c_f, c_f, i32, i32, i32, i32, i32, c_f, c_f, c_f, C.c_void_p]),
     "b2a_sample_token": (i32, [c_f, i64, i32, i32, c_f, c_f, i64, i32, f32, f32, i32, f32, f32, c_f, c_f, i64, c_f, c_f, i32, C.c_void_p]),
     "b2a_gemv_bf16": (i32, [c_f, i64, i32, i32, c_f, i64, i32, c_f, c_f, f32, i32, c_f, i64, c_f, i64, c_f, i64, C.c_void_p]),

@@ -339,6 +339,8 @@ extern "C" int32_t b2a_istft(const float* re, const float* im, int32_t B, int32_
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = (size_t)(2 * n_fft + 2 * (n_fft / 2 + 1)) * sizeof(float);
   dim3 grid(T, B);
+  static bool attr = false;      // n_fft = 4096 needs 49 160 B of dynamic shared memory, just above the 48 KB default
+  if (!attr) { cudaFuncSetAttribute(irfft_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
   irfft_frames_kernel<<<grid, 128, smem, st>>>(re, im, n_fft, T, window, ws);
   ola_kernel<<<grid_for(out_len * B, 256), 256, 0, st>>>(ws, n_fft, T, hop, window, norm_sq, clamp_mode, trim, out_len, out, B);
   B2A_CHECK_LAUNCH();
@@ -376,7 +378,10 @@ __device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_
   uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
   c0 = n0; c1 = n1; c2 = n2; c3 = n3;
 }
-__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset) {
+// seed / counter offset either as launch arguments (state == nullptr) or read from device memory {seed, offset}: a captured
+// CUDA graph then draws FRESH noise on every replay (randn_advance_kernel moves the offset past the counters just used)
+__global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ state) {
+  if (state) { seed = state[0]; offset = state[1]; }
   int64_t n4 = (n + 3) / 4;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     uint64_t ctr = offset + (uint64_t)i;
@@ -392,12 +397,22 @@ __global__ void randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed, 
     for (int j = 0; j < 4; j++) { int64_t o = i * 4 + j; if (o < n) out[o] = v[j]; }
   }
 }
+__global__ void randn_advance_kernel(uint64_t* state, uint64_t by) { state[1] += by; }
 }  // namespace
 
 extern "C" int32_t b2a_randn(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream) {
   B2A_CHECK_ARG(out && n >= 0, "bad pointer/size");
   if (n == 0) return B2A_OK;
-  randn_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+  randn_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, nullptr);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_randn_dev(float* out, int64_t n, uint64_t* state, void* stream) {
+  B2A_CHECK_ARG(out && state && n >= 0, "bad pointer/size");
+  if (n == 0) return B2A_OK;
+  randn_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(out, n, 0, 0, state);
+  randn_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, (uint64_t)((n + 3) / 4));
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -24,13 +24,16 @@ LAUNCHES = [0]        # kernels launched through this module (bench.py reports i
 
 
 PROFILE = None        # dict kind -> [(start_event, end_event)] when bench.py instruments a pass
+PROFILE_EXTERNAL = False   # True while an instrumented CUDA graph is captured: the events become event-record NODES of the graph, so
+                           # every replay re-stamps them and the per-launch times are those of the replayed graph (not of an eager pass)
 
 
 def _call(kind, fn, n_launches, *args):
     """Invoke a C-ABI entry point, map its status to an exception, count its kernel launches and (when
     bench.py asks) bracket it with CUDA events on the launching stream."""
     if PROFILE is not None:
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        b = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
         a.record()
         rc = fn(*args)
         b.record()
@@ -559,6 +562,13 @@ def randn_(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
     return out
 
 
+def randn_dev_(out: torch.Tensor, state: torch.Tensor) -> torch.Tensor:
+    """N(0,1) fill keyed by a device-resident Philox state (int64 [2] = seed, counter offset) that the call advances: graph-replay safe."""
+    assert out.is_contiguous() and out.dtype == torch.float32 and state.dtype == torch.int64 and state.numel() == 2 and state.is_contiguous()
+    _call("other", _lib.lib().b2a_randn_dev, 2, out.data_ptr(), out.numel(), state.data_ptr(), _stream())
+    return out
+
+
 def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, top_p: float = 1.0, min_p: float = 0.0, u=None,
                  suppress_mask=None, seen=None, repetition_penalty: float = 1.0, return_filtered: bool = False, mark_seen: bool = False,
                  out: Optional[torch.Tensor] = None, finished=None, eos: int = -1):
@@ -576,13 +586,19 @@ def sample_token(logits: torch.Tensor, *, temperature: float, top_k: int = 0, to
     return (out, filt) if return_filtered else out
 
 
+def gemv_eligible(cw: "ConvW") -> bool:
+    """The decode GEMV streams ONE bf16 plane of weights: bf16-exact K=1 layers only (fp16 / fp32 checkpoints and layers whose
+    Cout is not a multiple of 32 go through ``linear``)."""
+    return cw.K == 1 and cw.w_tc is not None and not cw.f16 and cw.w_tc_lo is None
+
+
 def gemv(x: torch.Tensor, cw: "ConvW", *, norm_w=None, norm_eps: float = 1e-6, swiglu: bool = False, res=None, out=None,
          prefetch: Optional["ConvW"] = None) -> torch.Tensor:
     """Decode-time nn.Linear on x [M, K] (any M; looped in groups of 8) with the bf16 weight rows of ``cw`` ([N, cin_pad]):
     optional fused RMSNorm prologue, SwiGLU (interleaved gate/up rows) and residual.  ``prefetch``: the next projection, whose
     weights are pulled into L2 while this one runs."""
-    assert x.dim() == 2 and x.stride(1) == 1 and cw.K == 1 and cw.w_tc is not None and not cw.f16 and cw.w_tc_lo is None, \
-        "gemv needs a bf16-exact K=1 weight"
+    if not (x.dim() == 2 and x.stride(1) == 1 and gemv_eligible(cw)):
+        raise NotImplementedError("gemv needs a bf16-exact K=1 weight with Cout % 32 == 0 (see ops.gemv_eligible); use ops.linear")
     M, K = x.shape
     N = cw.cout
     n_out = N // 2 if swiglu else N

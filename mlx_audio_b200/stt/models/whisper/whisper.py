@@ -293,8 +293,10 @@ class Model:
 
     def sanitize(self, weights):
         """whisper.py:551-618: a HuggingFace checkpoint (keys under ``model.``) is renamed to the reference's module tree and its conv
-        weights go from (out, in, K) to (out, K, in); an MLX-format checkpoint passes through.  (The dtype cast of the reference happens in
-        ``load_weights`` here.)"""
+        weights go from (out, in, K) to (out, K, in); an MLX-format checkpoint passes through.  Like the reference (whisper.py:613-615)
+        every floating-point tensor is rounded to the model dtype (``Model(dims, dtype=torch.float16)`` by default), so an fp32 checkpoint
+        runs with fp16-rounded weights -- which are fp16-exact and therefore take the single-plane fp16 tcgen05 weight path."""
+        dt = getattr(self, "dtype", None)
         is_hf = any(k.startswith("model.") for k in weights)
         out = {}
         for k, v in weights.items():
@@ -314,6 +316,8 @@ class Model:
                     continue
                 if ("conv1.weight" in k or "conv2.weight" in k) and v.dim() == 3:
                     v = v.permute(0, 2, 1).contiguous()
+            if dt is not None and torch.is_tensor(v) and v.is_floating_point() and v.dtype != dt:
+                v = v.to(dt)
             out[k] = v
         return out
 

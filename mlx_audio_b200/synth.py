@@ -103,7 +103,11 @@ def kokoro_weights(cfg, seed=0):
         g.lstm(f"predictor.text_encoder.lstms.{2 * i}", hd + st, hd // 2)
         g.linear(f"predictor.text_encoder.lstms.{2 * i + 1}.fc", 2 * hd, st)
     g.lstm("predictor.lstm", hd + st, hd // 2)
-    g.linear("predictor.duration_proj.linear_layer", cfg["max_dur"], hd)
+    # duration head: bias centred on logit(0.06) and wider weights, so that sum_k sigmoid(.) -- the predicted duration -- is ~3 frames per
+    # token (a realistic ~13 phonemes/s) instead of the 25 frames/token that zero-mean logits give; the 128-phoneme utterance of
+    # BASELINE config 2 then comes out at ~10 s of audio through the model's OWN duration head (bench.py e2e, un-pinned durations)
+    g.normal("predictor.duration_proj.linear_layer.weight", cfg["max_dur"], hd, std=0.1)
+    g.P["predictor.duration_proj.linear_layer.bias"] = _bf16(-2.8 + 0.02 * torch.randn(cfg["max_dur"], generator=g.g))
     g.lstm("predictor.shared", hd + st, hd // 2)
     for name in ("F0", "N"):
         g.adain_resblk1d(f"predictor.{name}.0", hd, hd, st)

@@ -94,6 +94,9 @@ class Model:
         self._pipelines = {}
         self.tap = None            # set to a dict to capture intermediates (parity tests)
         self.concurrent = True     # independent sub-graphs (text encoder, F0/N heads, source path, resblocks) on parallel streams
+        self.use_graphs = True     # __call__ / generate replay cached CUDA graphs (synthesize_ids); False -> eager forward_ids
+        self.max_graphs = 32
+        self._graphs, self._graph_pool, self._rng_state, self._warm_stream = {}, None, None, None
 
     # ------------------------------------------------------------------ protocol
     @property
@@ -310,28 +313,21 @@ class Model:
         return x
 
     # ------------------------------------------------------------------ forward
+    # The utterance has exactly one data-dependent size: F = sum(pred_dur).  Everything in front of it (`_text_side`: ALBERT, text
+    # encoder, duration encoder, duration head, alignment indices) depends on T only; everything behind it (`_acoustic_side`: F0 / N
+    # heads, decoder, generator, iSTFT head) on (T, F).  `forward_ids` runs both eagerly; `synthesize_ids` replays one CUDA graph per
+    # side with a single host read of F in between (the reference syncs once per phoneme, kokoro.py:148-152).
     @torch.no_grad()
-    def forward_ids(self, input_ids, ref_s, speed: float = 1.0, *, noise=None, pred_dur=None, n_frames: Optional[int] = None,
-                    f0n_override=None):
-        """Token ids (BOS/EOS 0 included) + style [1,256] -> (audio [samples], pred_dur int64 [T]).
-
-        ``noise`` [1, 600F, 9] injects the SineGen Gaussian (istftnet.py:649); None -> noiseless source
-        (production draws Philox noise with torch).  ``pred_dur`` overrides the duration head.
-        ``n_frames``: the caller already knows sum(pred_dur) (CUDA-graph capture) -> no host sync.
-        ``f0n_override`` = (F0 [2F], N [2F]) replaces the predicted curves (parity tests: the hn-NSF phase integrates F0
-        over the whole utterance x300, so decoder parity is checked on identical curves).
-        """
+    def _text_side(self, ids, ref_s, speed: float = 1.0, pred_dur=None):
+        """ids int64 [T] + style [1,256] (device) -> state dict: X [T,640] = [d_en | style], t_en [T,512], pred_dur, alignment
+        indices (first `total` valid), total (device int64 [1]), the two style-projection rows."""
         W, cfg, dev = self._w, self.config, self.device
-        if W is None:
-            raise RuntimeError("Kokoro: load_weights() has not been called")
-        ids = torch.as_tensor(input_ids, dtype=torch.int64, device=dev).reshape(-1).contiguous()
         T = ids.shape[0]
-        assert T <= self.context_length, (T, self.context_length)
-        ref_s = ref_s.to(device=dev, dtype=torch.float32).reshape(1, -1).contiguous()
         s_dec, s_pred = ref_s[:, :128].contiguous(), ref_s[:, 128:].contiguous()
-        self._pred_set = set(self._ada_pred)
-        self._gb_pred = ops.linear(s_pred, W["ada_all"])              # [1, sum 2C]  (all style projections at once)
-        self._gb_dec = ops.linear(s_dec, W["ada_all"])
+        st = {"T": T}
+        st["gb_pred"] = ops.linear(s_pred, W["ada_all"])              # [1, sum 2C]  (all style projections at once)
+        st["gb_dec"] = ops.linear(s_dec, W["ada_all"])
+        self._bind(st)
         hd = cfg.hidden_dim
         par = self.concurrent
         # ---- text encoder: independent of the ALBERT / duration chain -> its own branch (parallel graph path)
@@ -365,10 +361,10 @@ class Model:
             h = ops.layernorm(f2, *W["full_ln"], eps=1e-12)
         self._tap("bert", h)
         # ---- duration encoder: X640 = [d_en | style]
-        st = cfg.style_dim
-        X = torch.empty(T, hd + st, device=dev, dtype=torch.float32)
+        stl = cfg.style_dim
+        X = torch.empty(T, hd + stl, device=dev, dtype=torch.float32)
         ops.linear(h, W["bert_encoder"], out=X[:, :hd])
-        ops.copy2d(s_pred.expand(T, st), X[:, hd:])
+        ops.copy2d(s_pred.expand(T, stl), X[:, hd:])
         for i in range(cfg.n_layer):
             o = self._lstm_run(X, W["dur_lstms"][i])
             ops.layernorm(o, eps=1e-5, ada=self._gb(f"adaln.{i}").reshape(-1).contiguous(), out=X[:, :hd])
@@ -379,18 +375,36 @@ class Model:
         self._tap("dur", dsum)
         max_frames = 100 * T
         if pred_dur is not None:
-            pd = torch.as_tensor(pred_dur, dtype=torch.int64, device=dev).contiguous()
-            pred, idx, total = ops.durations_to_index(pd, max_frames)
+            pred, idx, total = ops.durations_to_index(pred_dur, max_frames)
         else:
             pred, idx, total = ops.durations_to_index(dsum, max_frames, float(speed))
-        F = int(total.item()) if n_frames is None else int(n_frames)   # the one host sync of the utterance
-        if F <= 0:
-            return torch.zeros(1, device=dev), pred
-        idx = idx[:F]
+        if par:
+            ops.join(dev, side_text)
+        else:
+            text_branch()
+        self._tap("t_en", t_en)
+        st.update(X=X, t_en=t_en, pred=pred, idx=idx, total=total)
+        return st
+
+    def _bind(self, st):
+        """Point the style-projection lookups (`_gb`) at this utterance's rows."""
+        self._pred_set = set(self._ada_pred)
+        self._gb_pred, self._gb_dec = st["gb_pred"], st["gb_dec"]
+
+    @torch.no_grad()
+    def _acoustic_side(self, st, F: int, noise=None, f0n_override=None):
+        """State of `_text_side` + the frame count -> waveform [600 F] samples."""
+        W, cfg, dev = self._w, self.config, self.device
+        self._bind(st)
+        hd = cfg.hidden_dim
+        par = self.concurrent
+        X, t_en = st["X"], st["t_en"]
+        idx = st["idx"][:F]
         # ---- F0 / N prediction
         en = ops.gather_rows(X, idx)                                   # [F,640]  == d^T @ aln
         xs = self._lstm_run(en, W["shared"])[None]                     # [1,F,512]
         F0N = torch.empty(2, 2 * F, 1, device=dev, dtype=torch.float32)
+
         def head(n_i, name):
             hcur = xs
             for blk in W[name]:
@@ -413,12 +427,6 @@ class Model:
         self._tap("en", en)
         self._tap("F0", f0_curve)
         self._tap("N", n_curve)
-        # ---- text encoder (joined here)
-        if par:
-            ops.join(dev, side_text)
-        else:
-            text_branch()
-        self._tap("t_en", t_en)
         # ---- harmonic-source path (depends on the F0 curve only): source -> STFT -> noise convs -> noise resblocks, run as a
         #      branch concurrent with the decoder blocks
         ist = cfg.istftnet
@@ -505,13 +513,143 @@ class Model:
         xpost = ops.conv1d(x, W["conv_post"], pad_left=3, pre=Pre(act=ACT["lrelu"], p0=0.01))[:, :, :W["n_post"]]
         self._tap("xpost", xpost)
         audio = ops.kokoro_istft_head(xpost)[0]
-        return audio, pred
+        return audio
+
+
+    @torch.no_grad()
+    def forward_ids(self, input_ids, ref_s, speed: float = 1.0, *, noise=None, pred_dur=None, n_frames: Optional[int] = None,
+                    f0n_override=None):
+        """Token ids (BOS/EOS 0 included) + style [1,256] -> (audio [samples], pred_dur int64 [T]), launched eagerly.
+
+        ``noise`` [1, 600F, 9] injects the SineGen Gaussian (istftnet.py:649); None -> noiseless source (`synthesize_ids` draws
+        Philox noise on the device).  ``pred_dur`` overrides the duration head.  ``n_frames``: the caller already knows
+        sum(pred_dur) -> no host sync.  ``f0n_override`` = (F0 [2F], N [2F]) replaces the predicted curves (parity tests: the
+        hn-NSF phase integrates F0 over the whole utterance x300, so decoder parity is checked on identical curves).
+        """
+        if self._w is None:
+            raise RuntimeError("Kokoro: load_weights() has not been called")
+        dev = self.device
+        ids = torch.as_tensor(input_ids, dtype=torch.int64, device=dev).reshape(-1).contiguous()
+        assert ids.shape[0] <= self.context_length, (ids.shape[0], self.context_length)
+        ref_s = ref_s.to(device=dev, dtype=torch.float32).reshape(1, -1).contiguous()
+        pd = None if pred_dur is None else torch.as_tensor(pred_dur, dtype=torch.int64, device=dev).contiguous()
+        st = self._text_side(ids, ref_s, speed, pd)
+        F = int(st["total"].item()) if n_frames is None else int(n_frames)   # the one host sync of the utterance
+        if F <= 0:
+            return torch.zeros(1, device=dev), st["pred"]
+        return self._acoustic_side(st, F, noise, f0n_override), st["pred"]
+
+    # ------------------------------------------------------------------ CUDA-graph path (what __call__ / generate use)
+    def seed(self, seed: int) -> None:
+        """Reset the device-resident Philox state the SineGen noise is drawn from (the analogue of ``mx.random.seed``)."""
+        self._rng_state = torch.tensor([int(seed), 0], dtype=torch.int64, device=self.device)
+
+    def _capture(self, fn):
+        """Warm ``fn`` up once on a side stream (lazy kernel loading, workspace growth), then record it into a CUDA graph that shares
+        this model's memory pool (graphs of one model never run concurrently).  Returns (graph, outputs of the captured run, launches)."""
+        dev = self.device
+        if self._warm_stream is None:
+            self._warm_stream = torch.cuda.Stream(device=dev)
+        s = self._warm_stream
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            fn()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        g = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES[0]
+        with torch.cuda.graph(g, pool=self._graph_pool):
+            out = fn()
+        return g, out, ops.LAUNCHES[0] - n0
+
+    def _text_graph(self, T: int, speed: float, pinned: bool):
+        key = ("text", T, float(speed), pinned)
+        ent = self._graphs.get(key)
+        if ent is None:
+            dev = self.device
+            ent = {"ids": torch.zeros(T, dtype=torch.int64, device=dev), "ref_s": torch.zeros(1, 256, dtype=torch.float32, device=dev),
+                   "dur": torch.ones(T, dtype=torch.int64, device=dev) if pinned else None}
+            ent["graph"], ent["st"], ent["launches"] = self._capture(lambda: self._text_side(ent["ids"], ent["ref_s"], speed, ent["dur"]))
+            self._remember(key, ent)
+        return ent
+
+    def _acoustic_graph(self, tg, T: int, F: int, f0n: bool):
+        key = ("acoustic", id(tg), T, F, f0n)
+        ent = self._graphs.get(key)
+        if ent is None:
+            dev = self.device
+            ent = {"noise": torch.zeros(1, F * 600, 9, dtype=torch.float32, device=dev), "text": tg,
+                   "f0n": torch.zeros(2, 2 * F, dtype=torch.float32, device=dev) if f0n else None}
+            ent["graph"], ent["audio"], ent["launches"] = self._capture(
+                lambda: self._acoustic_side(tg["st"], F, ent["noise"], None if ent["f0n"] is None else (ent["f0n"][0], ent["f0n"][1])))
+            self._remember(key, ent)
+        return ent
+
+    def _remember(self, key, ent):
+        self._graphs[key] = ent
+        while len(self._graphs) > self.max_graphs:                     # oldest first; a text graph drags its acoustic graphs along
+            old_key = next(iter(self._graphs))
+            old = self._graphs.pop(old_key)
+            for k in [k for k, v in self._graphs.items() if v.get("text") is old]:
+                self._graphs.pop(k)
+
+    @torch.no_grad()
+    def synthesize_ids(self, input_ids, ref_s, speed: float = 1.0, *, noise=None, pred_dur=None, n_frames: Optional[int] = None,
+                       f0n_override=None, out: Optional[torch.Tensor] = None):
+        """`forward_ids` by CUDA-graph replay: one graph for the text / prosody side per (T, speed), ONE host read of the frame count,
+        one graph for the acoustic side per (T, F); both are captured the first time a shape is seen and cached (``max_graphs``).
+        ``input_ids`` / ``ref_s`` may live in (pinned) host memory -- they are copied into the graphs' static buffers asynchronously.
+        SineGen noise comes from the model's device-resident Philox state and differs on every call (``seed()`` resets it); ``noise``
+        injects it instead.  Returns (audio [600 F] -- a static buffer that the next call with the same shape overwrites; pass ``out``
+        (pinned host or device) to receive a copy -- and pred_dur)."""
+        if self._w is None:
+            raise RuntimeError("Kokoro: load_weights() has not been called")
+        dev = self.device
+        ids = torch.as_tensor(input_ids, dtype=torch.int64).reshape(-1)
+        T = ids.shape[0]
+        assert T <= self.context_length, (T, self.context_length)
+        pinned = pred_dur is not None
+        tg = self._text_graph(T, float(speed), pinned)
+        tg["ids"].copy_(ids, non_blocking=True)
+        tg["ref_s"].copy_(torch.as_tensor(ref_s).reshape(1, -1), non_blocking=True)
+        if pinned:
+            tg["dur"].copy_(torch.as_tensor(pred_dur, dtype=torch.int64).reshape(-1), non_blocking=True)
+        tg["graph"].replay()
+        ops.LAUNCHES[0] += tg["launches"]
+        st = tg["st"]
+        F = int(st["total"].item()) if n_frames is None else int(n_frames)   # the one host sync of the utterance
+        if F <= 0:
+            return torch.zeros(1, device=dev), st["pred"]
+        ag = self._acoustic_graph(tg, T, F, f0n_override is not None)
+        if noise is not None:
+            ag["noise"].copy_(noise, non_blocking=True)
+        else:
+            if self._rng_state is None:
+                self.seed(torch.seed() & 0x7FFFFFFF)
+            ops.randn_dev_(ag["noise"], self._rng_state)
+        if f0n_override is not None:
+            ag["f0n"][0].copy_(torch.as_tensor(f0n_override[0]).reshape(-1), non_blocking=True)
+            ag["f0n"][1].copy_(torch.as_tensor(f0n_override[1]).reshape(-1), non_blocking=True)
+        ag["graph"].replay()
+        ops.LAUNCHES[0] += ag["launches"]
+        audio = ag["audio"]
+        if out is not None:
+            out.copy_(audio, non_blocking=True)
+            audio = out
+        return audio, st["pred"]
 
     def __call__(self, phonemes: str, ref_s, speed: Number = 1, return_output: bool = False, decoder=None, **kw):
         """kokoro.py:111-177: phoneme string -> waveform [1, samples] (or Output)."""
         ids = [i for i in (self.vocab.get(p) for p in phonemes) if i is not None]
         assert len(ids) + 2 <= self.context_length, (len(ids) + 2, self.context_length)
-        audio, pred = self.forward_ids([0, *ids, 0], ref_s, float(speed), **kw)
+        if self.use_graphs and self.tap is None:
+            audio, pred = self.synthesize_ids([0, *ids, 0], ref_s, float(speed), **kw)
+            if kw.get("out") is None:
+                audio = audio.clone()                                  # the graph's static output buffer is reused by the next call
+        else:
+            audio, pred = self.forward_ids([0, *ids, 0], ref_s, float(speed), **kw)
         audio = audio[None]
         return self.Output(audio=audio, pred_dur=pred) if return_output else audio
 
@@ -548,59 +686,3 @@ class Model:
                 prompt={"tokens": len(ps), "tokens-per-sec": round(len(ps) / seg_t, 2) if seg_t > 0 else 0},
                 audio_samples={"samples": samples, "samples-per-sec": round(samples / seg_t, 2) if seg_t > 0 else 0},
                 processing_time_seconds=seg_t, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
-
-
-class CapturedUtterance:
-    """One Kokoro utterance shape (T tokens, F frames) captured as a CUDA graph.
-
-    The utterance is ~700 dependent kernel launches on tens of microseconds of work each, so it is
-    launch-bound from Python; replaying a graph removes the host from the loop.  Inputs live in static
-    device buffers (``ids``, ``ref_s``, ``dur``); SineGen noise is drawn inside the graph by our Philox
-    kernel from a device-side counter, so every replay sees fresh noise like the reference's
-    ``mx.random.normal`` (istftnet.py:649)."""
-
-    def __init__(self, model: "Model", T: int, F: int, seed: int = 1234, with_noise: bool = True):
-        dev = model.device
-        self.model, self.T, self.F = model, T, F
-        self.ids = torch.zeros(T, dtype=torch.int64, device=dev)
-        self.ref_s = torch.zeros(1, 256, dtype=torch.float32, device=dev)
-        self.dur = torch.full((T,), max(F // T, 1), dtype=torch.int64, device=dev)
-        self.dur[0] += F - int(self.dur.sum().item())
-        self.noise = torch.zeros(1, F * 600, 9, dtype=torch.float32, device=dev) if with_noise else None
-        self.seed, self.step = seed, 0
-        self.graph = None
-        self.audio = None
-        self.launches = 0
-
-    def _run(self):
-        if self.noise is not None:
-            ops.randn_(self.noise, self.seed, 0)
-        audio, _ = self.model.forward_ids(self.ids, self.ref_s, noise=self.noise, pred_dur=self.dur, n_frames=self.F)
-        return audio
-
-    def capture(self, warmup: int = 2):
-        s = torch.cuda.Stream(device=self.model.device)
-        s.wait_stream(torch.cuda.current_stream(self.model.device))
-        with torch.cuda.stream(s):
-            for _ in range(warmup):
-                self._run()
-        torch.cuda.current_stream(self.model.device).wait_stream(s)
-        torch.cuda.synchronize(self.model.device)
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = ops.LAUNCHES[0]
-        with torch.cuda.graph(self.graph):
-            self.audio = self._run()
-        self.launches = ops.LAUNCHES[0] - n0
-        return self
-
-    def set_inputs(self, ids: torch.Tensor, ref_s: torch.Tensor, dur: Optional[torch.Tensor] = None):
-        """Async copies (host pinned or device) into the static buffers; sum(dur) must equal F."""
-        self.ids.copy_(ids.reshape(-1), non_blocking=True)
-        self.ref_s.copy_(ref_s.reshape(1, -1), non_blocking=True)
-        if dur is not None:
-            self.dur.copy_(dur.reshape(-1), non_blocking=True)
-
-    def replay(self) -> torch.Tensor:
-        self.graph.replay()
-        ops.LAUNCHES[0] += self.launches
-        return self.audio

@@ -231,6 +231,17 @@ class Model:
             ops.embed_sum(self._codes, self._tabs_all, text=self._trailing, pad=self._pad, step_dev=t.offset_dev, step_sub=self._prefill_len,
                           out=self._x_in[:, 0], err=self._err)
 
+    def _uniform_stream(self, seed):
+        """Generator the sampler's uniforms are drawn from.  ``seed=None`` continues ONE stream owned by the model, so successive
+        segments and calls see fresh draws the way the reference's global ``mx.random`` state advances (qwen3_tts.py:805-860);
+        an integer starts a reproducible stream for this call only."""
+        if seed is not None:
+            return torch.Generator(device=self.device).manual_seed(int(seed))
+        if getattr(self, "_rng", None) is None:
+            self._rng = torch.Generator(device=self.device)
+            self._rng.seed()
+        return self._rng
+
     @torch.no_grad()
     def generate_codes(self, input_embeds, trailing_text_hidden, tts_pad_embed, *, max_tokens: int = 4096, temperature: float = 0.9,
                        top_k: int = 50, top_p: float = 1.0, repetition_penalty: float = 1.05, u=None, seed: int = 0,
@@ -253,8 +264,7 @@ class Model:
         g, V = cfg.num_code_groups, cfg.vocab_size
         eos = cfg.codec_eos_token_id
         if u is None:
-            gen = torch.Generator(device=dev).manual_seed(seed)
-            u = torch.rand(max_tokens, g, B, device=dev, generator=gen)
+            u = torch.rand(max_tokens, g, B, device=dev, generator=self._uniform_stream(seed))
         u = u.to(dev).float().contiguous()
         sp = {"temperature": float(temperature), "top_k": int(top_k), "top_p": float(top_p), "repetition_penalty": float(repetition_penalty),
               "eos": int(eos)}
@@ -449,7 +459,10 @@ class Model:
         for idx, seg in enumerate(segments):
             t0 = time.perf_counter()
             x, trailing, pad = self._prepare_generation_inputs(seg, language=language, speaker=speaker, instruct=instruct)
-            codes = self.generate_codes(x, trailing, pad, **gen)
+            seg_gen = dict(gen)
+            if seg_gen.get("seed") is not None:                       # a fixed seed still gives every segment its own draws
+                seg_gen["seed"] = int(seg_gen["seed"]) + idx
+            codes = self.generate_codes(x, trailing, pad, **seg_gen)
             if codes.shape[1] == 0:
                 continue
             audio = self._decode_chunk(codes[:1])
@@ -466,7 +479,7 @@ class Model:
     def generate(self, text: str, voice: Optional[str] = None, instruct: Optional[str] = None, temperature: float = 0.9, speed: float = 1.0,
                  lang_code: str = "auto", ref_audio=None, ref_text: Optional[str] = None, split_pattern: str = "\n", max_tokens: int = 4096,
                  verbose: bool = False, stream: bool = False, streaming_interval: float = 2.0, top_k: int = 50, top_p: float = 1.0,
-                 repetition_penalty: float = 1.05, seed: int = 0, **kwargs):
+                 repetition_penalty: float = 1.05, seed: Optional[int] = None, **kwargs):
         """Model.generate (qwen3_tts.py:1122-1575): routes on ``tts_model_type`` exactly as the reference (same errors)."""
         gen = dict(max_tokens=max_tokens, temperature=temperature, top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty, seed=seed)
         kind = getattr(self.config, "tts_model_type", "base")
@@ -485,8 +498,14 @@ class Model:
             return
         if self.speech_tokenizer is None:
             raise ValueError("Speech tokenizer not loaded")
-        if ref_audio is not None and ref_text is not None:
-            raise NotImplementedError("ICL voice cloning needs the speech-tokenizer encoder + speaker encoder (SURVEY.md section 8f 'next')")
+        if ref_audio is not None:
+            # with ref_text: in-context cloning (_generate_icl); alone: x-vector cloning through the speaker encoder (qwen3_tts.py:382-383).
+            # Neither encoder has a CUDA path yet -- refuse instead of silently synthesising the default voice.
+            raise NotImplementedError("voice cloning from ref_audio needs the speech-tokenizer encoder + speaker encoder "
+                                      "(SURVEY.md section 8f 'next'); call without ref_audio for the default voice")
+        if stream:
+            raise NotImplementedError("stream=True (incremental audio chunks) is not implemented for generate(); use "
+                                      "batch_generate(stream=True) or speech_tokenizer.streaming_decode on the returned codes")
         if voice is not None and voice.lower() not in [s.lower() for s in self.supported_speakers]:
             raise ValueError(f"Voice '{voice}' is not supported by this Base model. Base models have no built-in preset voices — "
                              "clone a voice by passing ref_audio and ref_text instead.")

@@ -53,13 +53,18 @@ class _DecoderStack:
         self.kc = self.vc = None
 
     def alloc_cache(self, batch: int, max_len: int):
-        shape = (len(self.layers), batch, max_len, self.n_kv * self.hd)
-        if self.kc is None or self.kc.shape != shape:
+        """Pre-sized device cache [layer, B, rows, n_kv*hd].  The row capacity is rounded up to 256 and a buffer that is already
+        large enough for this batch is reused: rows past the device-side length are never read (attn_decode stops at base + s),
+        so a prompt of another length costs neither a ~1 GB reallocation nor a zero-fill."""
+        rows = -(-max_len // 256) * 256
+        if self.kc is None or self.kc.shape[1] != batch or self.kc.shape[2] < rows:
+            shape = (len(self.layers), batch, rows, self.n_kv * self.hd)
+            self.kc = self.vc = None                       # release before allocating the replacement
             self.kc = torch.zeros(shape, device=self.device, dtype=torch.float32)
             self.vc = torch.zeros(shape, device=self.device, dtype=torch.float32)
 
     def _proj(self, x2, cw, norm_w=None, swiglu=False, res=None, nxt=None):
-        if x2.shape[0] <= GEMV_MAX_ROWS:
+        if x2.shape[0] <= GEMV_MAX_ROWS and ops.gemv_eligible(cw):
             return ops.gemv(x2, cw, norm_w=norm_w, norm_eps=self.eps, swiglu=swiglu, res=res, prefetch=nxt if PREFETCH[0] else None)
         h = ops.layernorm(x2, norm_w, None, eps=self.eps, rms=True) if norm_w is not None else x2
         y = ops.linear(h, cw, res=None if swiglu else res)

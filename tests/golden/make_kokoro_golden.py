@@ -83,13 +83,13 @@ def main():
         return draws["noise"]
     mx.random.strict = True
     mx.random.queue[:] = [("uniform", rand_ini), ("normal", noise), ("normal", lambda shape: np.zeros(shape))]
-    res = model(phonemes, mx.array(np.asarray(ref_s, dtype=np.float64)), speed=float(os.environ.get("SPEED", "4.0")), return_output=True)
+    res = model(phonemes, mx.array(np.asarray(ref_s, dtype=np.float64)), speed=float(os.environ.get("SPEED", "0.5")), return_output=True)
     assert not mx.random.queue
     audio, pred_dur = np.asarray(res.audio), np.asarray(res.pred_dur)
     print("pred_dur", pred_dur.tolist(), "audio", audio.shape, float(np.abs(audio).max()))
     np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "kokoro_golden.npz"), ids=ids, ref_s=np.asarray(ref_s, dtype=np.float64), rand_ini=rand_ini,
                         noise_shape=np.asarray(draws["noise"].shape), pred_dur=pred_dur, audio=audio.astype(np.float32),
-                        meta=json.dumps({"n_phonemes": n_ph, "weights": "synth.kokoro_weights(KOKORO_CONFIG, seed=0)", "f0_gain": f0_gain, "noise": "np.random.default_rng(71): .random((1, 9)) then .standard_normal(noise_shape).astype(float32)", "speed": float(os.environ.get("SPEED", "4.0"))}))
+                        meta=json.dumps({"n_phonemes": n_ph, "weights": "synth.kokoro_weights(KOKORO_CONFIG, seed=0)", "f0_gain": f0_gain, "noise": "np.random.default_rng(71): .random((1, 9)) then .standard_normal(noise_shape).astype(float32)", "speed": float(os.environ.get("SPEED", "0.5"))}))
 
 
 def live(n):
@@ -109,7 +109,7 @@ def live(n):
         P["predictor.F0_proj.weight"] = P["predictor.F0_proj.weight"] * float(rng.uniform(200, 900))
         for k, v in P.items():
             shim.set_parameter(model, k, v.double().numpy())
-        n_ph, speed = int(rng.integers(3, 14)), float(rng.uniform(3.0, 7.0))
+        n_ph, speed = int(rng.integers(3, 14)), float(rng.uniform(0.4, 1.2))
         ids = rng.integers(1, cfg["n_token"], size=n_ph)
         ref_s = rng.standard_normal((1, 256))
         rand_ini = rng.random((1, 9))

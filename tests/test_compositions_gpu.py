@@ -1,12 +1,10 @@
-"""GPU parity tests written AFTER this round's GPU budget was spent: they have not yet run on hardware.  The file sorts last so that
-a surprise here cannot hide the validated files before it under ``pytest -x``.  Each test drives host-side compositions of kernels
-whose own parity tests (test_qwen3_gpu.py) are validated; what is new is the composition."""
+"""Host-side compositions of validated kernels (default batch path of Qwen3-TTS, Mimi.decode_step, SNAC.decode_stream, Whisper
+Model.logits) against the oracle.  First hardware run: round 1 driver (all four passed there as xpass; the marker is gone, so a
+regression now fails)."""
 import pytest
 import torch
 
-# xfail(strict=False): a first hardware run that fails here is reported as xfailed and one that passes as xpassed -- either way the validated
-# suite in front of this file keeps its own verdict.  Remove the mark once the file has run green on a B200.
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; first hardware run pending")]
+pytestmark = pytest.mark.gpu
 
 from oracle import qwen3 as Q
 

@@ -416,3 +416,26 @@ def test_product_never_touches_the_oracle_or_the_reference():
             "print('clean')\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "clean" in r.stdout, r.stderr[-1500:]
+
+
+def test_product_configs_say_what_the_oracle_configs_say():
+    """mlx_audio_b200/configs.py (what bench.py and tools/ use) restates the public configurations; the oracle keeps its own copies next
+    to the reference citations.  They must agree, and nothing outside tests/, bench.py's CPU arm and smoke() may import oracle/."""
+    import os
+    import re
+    from mlx_audio_b200 import configs as C
+    from oracle import codec as OC, kokoro as OK, qwen3 as OQ, whisper as OW
+    assert C.KOKORO_82M == OK.KOKORO_CONFIG and C.SNAC_24K == OC.SNAC_24K and C.MIMI_202407 == OC.MIMI_202407
+    assert C.WHISPER_SMALL == OW.WHISPER_SMALL and C.QWEN3_TALKER == OQ.TALKER and C.QWEN3_TOKENIZER_DECODER == OQ.TOKENIZER_DECODER
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from\s+oracle[\s.]|import\s+oracle)", re.M)
+    for top in ("mlx_audio_b200", "mlx_audio", "tools"):
+        for dp, _, fs in os.walk(os.path.join(root, top)):
+            for f in fs:
+                if f.endswith(".py"):
+                    assert not pat.search(open(os.path.join(dp, f)).read()), os.path.join(dp, f)
+    # bench.py: the only import sits inside cpu_port_run (the cpu_baseline / --impl reference leg)
+    src = open(os.path.join(root, "bench.py")).read()
+    hits = [m.start() for m in pat.finditer(src)]
+    lo, hi = src.index("def cpu_port_run"), src.index("def host_threads")
+    assert hits and all(lo < h < hi for h in hits)

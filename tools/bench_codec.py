@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mlx_audio_b200 import ops, synth
 from mlx_audio_b200.codec import SNAC, Mimi, mimi_202407
-from oracle.codec import MIMI_202407, SNAC_24K      # config dicts only
+from mlx_audio_b200.configs import MIMI_202407, SNAC_24K
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=10000)

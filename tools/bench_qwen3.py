@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mlx_audio_b200 import ops, synth
 from mlx_audio_b200.tts.models.qwen3_tts import (Model, ModelConfig, Qwen3TTSSpeechTokenizer, Qwen3TTSTalkerConfig, Qwen3TTSTokenizerConfig)
-from oracle.qwen3 import TALKER, TOKENIZER_DECODER     # config dicts only
+from mlx_audio_b200.configs import QWEN3_TALKER as TALKER, QWEN3_TOKENIZER_DECODER as TOKENIZER_DECODER
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--frames", type=int, default=100)

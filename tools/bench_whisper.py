@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mlx_audio_b200 import ops, synth
 from mlx_audio_b200.stt.models.whisper import Model, ModelDimensions
-from oracle.whisper import WHISPER_SMALL
+from mlx_audio_b200.configs import WHISPER_SMALL
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
