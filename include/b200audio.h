@@ -133,6 +133,11 @@ int32_t b2a_adain_coeffs(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, 
  * transposed mode; stats_slots = ceil(Mrows/128)*4*max(1, up_stride)) -- so AdaIN-conv chains skip the statistics pass over HBM. */
 int32_t b2a_adain_coeffs_from_partials(const double* partials, int32_t nslots, int32_t B, int32_t L, int32_t C, const float* gb,
                                        float eps, float* scale, float* shift, void* stream);
+/* (sum, sumsq) over L of every channel of x [B, L, C], ADDED to n_dst (1..4) float64 accumulators laid out [B][.][2]; dst[i] points at
+ * the first channel's pair, dst_bs[i] doubles separate batches.  This is the statistics format b2a_conv1d_fused consumes (pre_mode 2)
+ * and produces (stats_out); the stand-alone kernel covers tensors no fused conv produced (LSTM outputs, concatenated side channels). */
+int32_t b2a_channel_stats(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, double* const* dst,
+                          const int64_t* dst_bs, int32_t n_dst, void* stream);
 /* y[r,:] = LN(x[r,:] + res[r,:]) * w + b, or (1+ada[c])*LN + ada[C+c] when ada != NULL
  * (nn.LayerNorm, modules.py:71-90 AdaLayerNorm). rms != 0 -> RMSNorm (no mean, talker.py:267). */
 int32_t b2a_layernorm(const float* x, int64_t x_ld, const float* res, int64_t res_ld, float* y, int64_t y_ld,
@@ -201,6 +206,34 @@ int32_t b2a_kokoro_source(const float* f0, int32_t B, int32_t n_frames, int32_t 
 /* x [B, T, 22] = conv_post output -> audio [B, (T-1)*5] : exp / sin heads, cos/sin, 20-point inverse rFFT, periodic Hann,
  * overlap-add, / sum(w^2), trim 10 samples each side (phase in [-1,1] so mlx_unwrap is the identity). */
 int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t T, float* audio, void* stream);
+
+/* ---- fused dense conv1d / nn.Linear / polyphase ConvTranspose1d on tcgen05 (csrc/conv_fused.cu) ------------------------------
+ * One launch = [InstanceNorm / AdaIN coefficients from the producer's (sum, sumsq)] + input activation + bf16/fp16 hi(+lo) split +
+ * sum over taps of row-shifted GEMMs + bias / activation / channel scale / residual / scale / accumulate (+ polyphase scatter) +
+ * (sum, sumsq) of the output for the NEXT layer's InstanceNorm.  Replaces, per layer, the call sites of mx.conv1d / conv_transpose1d /
+ * nn.Linear TOGETHER WITH the elementwise chain in front of them: AdaIN1d + Snake / LeakyReLU in AdaINResBlock1 and AdainResBlk1d
+ * (tts/models/kokoro/istftnet.py:216-396, 853-933), the generator's ups / conv_post (:725-835), ALBERT's Linear layers
+ * (tts/models/kokoro/modules.py:434-645).  Up to B2A_CONVF_MAX_PROBLEMS independent problems share one persistent grid (the three
+ * parallel resblocks of a generator stage).  x: fp32 [B, L, Cin] (16-byte aligned, row stride % 4 == 0); optional x1 / x2 (same
+ * strides) are added to x first (the resblock average of the previous stage), then * in_scale.  Weights as for b2a_conv1d_tc:
+ * 16-bit [taps][N][cin_pad] (+ optional lo plane).  y: fp32 [B, Lout, C].  pre_mode 0: no affine; 1: x*scale[b,c]+shift[b,c];
+ * 2: scale/shift derived in-kernel from pre_stats [B, Cin, 2] = (sum, sumsq) over L (biased variance, eps) and gamma|beta rows
+ * pre_gb [B, 2 Cin] (NULL: plain InstanceNorm).  stats_out [B, C, 2] float64 is ADDED to (zero it before the launch).
+ * ws: zero-initialised scratch (>= 16 MiB recommended) for split-K partial tiles; NULL disables K splitting. */
+#define B2A_CONVF_MAX_PROBLEMS 4
+typedef struct {
+  const float* x; const float* x1; const float* x2; int64_t x_bs, x_ld; float in_scale;
+  int32_t B, L, Cin;
+  int32_t pre_mode; const float* pre_scale; const float* pre_shift; const double* pre_stats; const float* pre_gb; int64_t pre_gb_bs; float pre_eps;
+  int32_t pre_act; float pre_p0; const float* pre_a; const float* pre_b;
+  const void* w_hi; const void* w_lo; int32_t cin_pad, taps, N; int32_t shifts[32];
+  int32_t Lout; const float* bias; int32_t post_act; float post_p0; const float* cscale; int64_t cscale_bs;
+  const float* res; int64_t res_bs, res_ld; int32_t res_div; float out_scale; int32_t accumulate;
+  float* y; int64_t y_bs, y_ld;
+  int32_t up_stride, up_crop;
+  double* stats_out;
+} b2a_convf_t;
+int32_t b2a_conv1d_fused(const b2a_convf_t* problems, int32_t n_problems, int32_t planes, int32_t f16, void* ws, int64_t ws_bytes, void* stream);
 
 /* out[i] ~ N(0,1), i < n: Philox4x32-10 keyed by `seed`, counter `offset + i/4`, Box-Muller.  The production replacement for
  * mx.random.normal in SineGen / NoiseBlock (istftnet.py:649, snac/layers.py:263); parity tests inject the noise instead. */

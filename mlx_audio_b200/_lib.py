@@ -43,6 +43,23 @@ class AttnParams(C.Structure):
     ]
 
 
+class ConvFParams(C.Structure):
+    """Mirror of b2a_convf_t (one problem of a fused tcgen05 conv launch)."""
+    _fields_ = [
+        ("x", C.c_void_p), ("x1", C.c_void_p), ("x2", C.c_void_p), ("x_bs", i64), ("x_ld", i64), ("in_scale", f32),
+        ("B", i32), ("L", i32), ("Cin", i32),
+        ("pre_mode", i32), ("pre_scale", C.c_void_p), ("pre_shift", C.c_void_p), ("pre_stats", C.c_void_p), ("pre_gb", C.c_void_p),
+        ("pre_gb_bs", i64), ("pre_eps", f32),
+        ("pre_act", i32), ("pre_p0", f32), ("pre_a", C.c_void_p), ("pre_b", C.c_void_p),
+        ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("cin_pad", i32), ("taps", i32), ("N", i32), ("shifts", i32 * 32),
+        ("Lout", i32), ("bias", C.c_void_p), ("post_act", i32), ("post_p0", f32), ("cscale", C.c_void_p), ("cscale_bs", i64),
+        ("res", C.c_void_p), ("res_bs", i64), ("res_ld", i64), ("res_div", i32), ("out_scale", f32), ("accumulate", i32),
+        ("y", C.c_void_p), ("y_bs", i64), ("y_ld", i64),
+        ("up_stride", i32), ("up_crop", i32),
+        ("stats_out", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/b200audio.h declares
 PROTOTYPES = {
     "b2a_last_error": (C.c_char_p, []),
@@ -54,12 +71,14 @@ PROTOTYPES = {
     "b2a_conv1d_tc": (i32, [c_f, c_f, i32, i32, i32, i32, c_f, c_f, i32, C.POINTER(i32), i32, i32, c_f, i32, f32, c_f, i64, c_f, i64, i64, i32, f32, i32,
                             c_f, i64, i64, i32, i32, c_f, i32, C.c_void_p]),
     "b2a_conv1d_tc_debug": (i32, [c_f]),
+    "b2a_conv1d_fused": (i32, [C.POINTER(ConvFParams), i32, i32, i32, c_f, i64, C.c_void_p]),
     "b2a_copy2d": (i32, [c_f, i64, c_f, i64, i64, i32, C.c_void_p]),
     "b2a_gather_rows": (i32, [c_f, i64, c_f, c_f, i64, i64, i32, i64, c_f, i64, i64, C.c_void_p]),
     "b2a_durations_to_index": (i32, [c_f, c_f, i32, f32, c_f, c_f, i64, c_f, C.c_void_p]),
     "b2a_adain_ws_bytes": (i64, [i32, i32, i32]),
     "b2a_adain_coeffs": (i32, [c_f, i64, i64, i32, i32, i32, c_f, f32, c_f, c_f, c_f, C.c_void_p]),
     "b2a_adain_coeffs_from_partials": (i32, [c_f, i32, i32, i32, i32, c_f, f32, c_f, c_f, C.c_void_p]),
+    "b2a_channel_stats": (i32, [c_f, i64, i64, i32, i32, i32, C.POINTER(C.c_void_p), C.POINTER(i64), i32, C.c_void_p]),
     "b2a_layernorm": (i32, [c_f, i64, c_f, i64, c_f, i64, i64, i32, c_f, c_f, c_f, f32, i32, i32, f32, C.c_void_p]),
     "b2a_attention": (i32, [C.POINTER(AttnParams), C.c_void_p]),
     "b2a_attention_tc_ws_bytes": (i64, [i32, i32, i32, i32]),

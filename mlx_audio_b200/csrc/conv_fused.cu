@@ -1,0 +1,605 @@
+// Fused dense conv1d / linear / polyphase transposed conv for sm_100a (include/b200audio.h: b2a_conv1d_fused).
+//
+// Round 1 ran every tensor-core layer as FOUR launches: InstanceNorm statistics (2 kernels), a prologue pass that re-read the fp32
+// activations, applied AdaIN / Snake / LeakyReLU and wrote them back to HBM as bf16 (hi, lo) planes, and the tcgen05 GEMM that
+// read those planes once per tap.  This kernel does all of it in ONE launch and reads the activations ONCE:
+//
+//   converter warps (8)  fp32 activations (global, coalesced float4) -> [AdaIN scale/shift from the producer's (sum, sumsq)] ->
+//                        Snake / LeakyReLU / ELU -> bf16 (or fp16) hi + lo planes written straight into the 128B-swizzled shared-memory
+//                        tile the MMA consumes.  One (128 + span)-row tile per 64-channel K chunk serves EVERY tap: tap t multiplies
+//                        rows [shift_t - shift_min, +128) of it through a row-shifted UMMA descriptor.  Rows outside [0, L) are
+//                        written as zeros = the convolution's zero padding.  Double-buffered.
+//   TMA warp             weight tiles [BN x 64] per (K chunk, tap) through a ring of mbarrier stages.
+//   MMA warp             tcgen05.mma kind::f16, M128 x BN x K16, fp32 accumulator double-buffered in TMEM.
+//   epilogue warps (8)   tcgen05.ld -> per-warp smem transpose -> coalesced rows; bias / activation / channel scale / residual /
+//                        out_scale / accumulate / polyphase scatter fused; per-channel (sum, sumsq) of what was written is reduced in
+//                        shared memory and added to a float64 accumulator in global memory -- the NEXT layer's AdaIN statistics.
+//
+// Grouped launches: up to 4 independent problems (e.g. the three parallel AdaINResBlock1 branches of a generator stage, kernel sizes
+// 3 / 7 / 11) share one persistent grid; tiles are ordered heaviest problem first.  Small-M problems can split K across CTAs
+// (partial accumulators in a global workspace, the last CTA to arrive reduces and runs the epilogue).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+using namespace tc;
+
+namespace {
+
+constexpr int TM = 128;
+constexpr int TK = 64;
+constexpr int UMMA_K = 16;
+constexpr int MAXG = B2A_CONVF_MAX_PROBLEMS;
+constexpr int NCONV = 8;                       // converter warps
+constexpr int NEPI = 8;                        // epilogue warps
+constexpr int W_CONV0 = 2, W_EPI0 = 2 + NCONV;
+constexpr int THREADS = (2 + NCONV + NEPI) * 32;          // 576
+constexpr int STAGING = NEPI * 32 * 33 * 4;               // per-warp 32x33 fp32 transpose tiles
+constexpr int SACC = 2 * 256 * 4;                         // per-tile (sum, sumsq) accumulators, up to 256 columns
+
+struct FProb {
+  const float* x; const float* x1; const float* x2; int64_t x_bs, x_ld; float in_scale;
+  int B, L, Cin, cin_pad;
+  int pre_mode;                                // 0 none, 1 scale/shift [B,Cin], 2 statistics (sum, sumsq) [B,Cin,2] (+ gamma|beta [B,2Cin])
+  const float* pre_scale; const float* pre_shift;
+  const double* pre_stats; const float* pre_gb; int64_t pre_gb_bs; float pre_eps, pre_invL;
+  int pre_act; float pre_p0; const float* pre_a; const float* pre_b;
+  int taps, wplanes, BN, ntn, ntm, Ntot, R, shift_min, ksplit, kper;
+  int shift[32];
+  int Lout, Mrows, up_s, up_crop, C;
+  const float* bias; int post_act; float post_p0; const float* cscale; int64_t cscale_bs;
+  const float* res; int64_t res_bs, res_ld; int res_div; float out_scale; int accumulate;
+  float* y; int64_t y_bs, y_ld;
+  double* stats_out;
+  float* ws; int* counters;                    // split-K workspace [tile][ksplit][128*BN] and arrival counters [tile]
+  int tile_begin;
+};
+
+struct FParams {
+  int G, ntiles, planes, f16, wst, w_stage, a_plane, tmem_stride;
+  FProb pr[MAXG];
+};
+
+struct TileRef { int g, b, mt, nt, ks; };
+
+__device__ __forceinline__ TileRef decode_tile(const FParams& p, int tile) {
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < MAXG; i++) if (i < p.G && tile >= p.pr[i].tile_begin) g = i;
+  const FProb& P = p.pr[g];
+  int local = tile - P.tile_begin;
+  TileRef t;
+  t.g = g;
+  t.ks = local % P.ksplit; local /= P.ksplit;
+  t.nt = local % P.ntn; local /= P.ntn;
+  t.mt = local % P.ntm; t.b = local / P.ntm;
+  return t;
+}
+
+template <typename T> __device__ __forceinline__ T cvt16(float v);
+template <> __device__ __forceinline__ __nv_bfloat16 cvt16<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half cvt16<__half>(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float back16(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float back16(__half v) { return __half2float(v); }
+
+__device__ __noinline__ float act_slow(float v, int act, float p0) { return b2a_act(v, act, p0, 1.f, 1.f); }
+
+// One float4 (4 channels of one row) -> transformed hi / lo 16-bit quads at the swizzled position of row r, 8-byte slot c4.
+template <typename T16>
+__device__ __forceinline__ void convert_store(float4 v, bool valid, const float sc[4], const float sh[4], const float aa[4], const float bb[4],
+                                              const bool chok[4], int act, float p0, uint8_t* hi, uint8_t* lo, int r, int c4) {
+  float t[4] = {v.x, v.y, v.z, v.w};
+  __align__(8) T16 h[4];
+  __align__(8) T16 l[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    float u = 0.f;
+    if (valid && chok[q]) {
+      u = fmaf(t[q], sc[q], sh[q]);
+      if (act == B2A_ACT_SNAKE) { const float s = b2a_sin(aa[q] * u); u = fmaf(bb[q], s * s, u); }
+      else if (act == B2A_ACT_LRELU) u = u > 0.f ? u : u * p0;
+      else if (act == B2A_ACT_ELU) u = u > 0.f ? u : expm1f(u);
+      else if (act) u = act_slow(u, act, p0);
+    }
+    h[q] = cvt16<T16>(u);
+    l[q] = cvt16<T16>(u - back16(h[q]));
+  }
+  const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
+  *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap mw1,
+                  const __grid_constant__ CUtensorMap mw2, const __grid_constant__ CUtensorMap mw3,
+                  const __grid_constant__ CUtensorMap ml0, const __grid_constant__ CUtensorMap ml1,
+                  const __grid_constant__ CUtensorMap ml2, const __grid_constant__ CUtensorMap ml3) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // layout: [2] x A buffer (planes x a_plane bytes) | [wst] x W stage | staging | sacc | barriers
+  const int a_buf = p.a_plane * p.planes;
+  uint8_t* wbase = smem + (size_t)2 * a_buf;
+  float* staging = reinterpret_cast<float*>(wbase + (size_t)p.wst * p.w_stage);
+  float* sacc = staging + STAGING / 4;
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sacc) + SACC);
+  uint64_t* empty = full + p.wst;
+  uint64_t* tfull = empty + p.wst;           // [2]
+  uint64_t* tempty = tfull + 2;              // [2]
+  uint64_t* a_full = tempty + 2;             // [2]
+  uint64_t* a_empty = a_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+  int* flag_slot = reinterpret_cast<int*>(tmem_slot + 1);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.wst; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(tfull, 1); mbar_init(tfull + 1, 1); mbar_init(tempty, NEPI); mbar_init(tempty + 1, NEPI);
+    mbar_init(a_full, NCONV); mbar_init(a_full + 1, NCONV); mbar_init(a_empty, 1); mbar_init(a_empty + 1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  const uint32_t tmem_cols = 2u * (uint32_t)p.tmem_stride;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();        // the next kernel may start its own prologue / weight loads as SMs free up; it waits for us before reading
+
+  if (warp == 0) {
+    // ===== weight producer: independent of the previous kernel's output, so it starts before the programmatic-dependency wait =====
+    if (lane == 0) {
+      const CUtensorMap* mws[MAXG] = {&mw0, &mw1, &mw2, &mw3};
+      const CUtensorMap* mls[MAXG] = {&ml0, &ml1, &ml2, &ml3};
+      for (int g = 0; g < p.G; g++) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(mws[g]) : "memory");
+        if (p.pr[g].wplanes == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(mls[g]) : "memory");
+      }
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+        const TileRef t = decode_tile(p, tile);
+        const FProb& P = p.pr[t.g];
+        const int n0 = t.nt * P.BN;
+        const int kchunks = P.cin_pad / TK;
+        const int kc0 = t.ks * P.kper, kc1 = min(kchunks, kc0 + P.kper);
+        const uint32_t wb = (uint32_t)P.BN * 128u;
+        for (int kc = kc0; kc < kc1; kc++) {
+          for (int tap = 0; tap < P.taps; tap++, it++) {
+            const int s = it % p.wst, ph = (it / p.wst) & 1;
+            mbar_wait(empty + s, ph ^ 1);
+            uint8_t* st = wbase + (size_t)s * p.w_stage;
+            mbar_expect_tx(full + s, wb * (uint32_t)P.wplanes);
+            tma_load_2d(st, mws[t.g], full + s, kc * TK, tap * P.Ntot + n0);
+            if (P.wplanes == 2) tma_load_2d(st + wb, mls[t.g], full + s, kc * TK, tap * P.Ntot + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t fmt = p.f16 ? 0u : 1u;
+    const uint32_t a0 = smem_u32(smem);
+    uint32_t it = 0, lt = 0, cg = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
+      const TileRef t = decode_tile(p, tile);
+      const FProb& P = p.pr[t.g];
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(P.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const int kchunks = P.cin_pad / TK;
+      const int kc0 = t.ks * P.kper, kc1 = min(kchunks, kc0 + P.kper);
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      const uint32_t wb = (uint32_t)P.BN * 128u;
+      mbar_wait(tempty + buf, (use & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + buf * (uint32_t)p.tmem_stride;
+      for (int kc = kc0; kc < kc1; kc++, cg++) {
+        const uint32_t ab = cg & 1;
+        mbar_wait(a_full + ab, (cg >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int tap = 0; tap < P.taps; tap++, it++) {
+          const int s = it % p.wst, ph = (it / p.wst) & 1;
+          mbar_wait(full + s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0) {
+            const uint32_t wst_addr = smem_u32(wbase + (size_t)s * p.w_stage);
+            const uint32_t abase = a0 + ab * (uint32_t)a_buf + (uint32_t)(P.shift[tap] - P.shift_min) * 128u;
+            for (int wp = 0; wp < P.wplanes; wp++) {
+              const uint64_t wdesc = umma_desc_sw128(wst_addr + wp * wb);
+              const int npl = wp == 0 ? p.planes : 1;            // products kept: a_hi*w_hi, a_lo*w_hi, a_hi*w_lo
+              for (int pl = 0; pl < npl; pl++) {
+                const uint64_t adesc = umma_desc_sw128(abase + pl * (uint32_t)p.a_plane);
+#pragma unroll
+                for (int k = 0; k < TK / UMMA_K; k++)
+                  umma_f16(tacc, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, ((kc - kc0) | tap | wp | pl | k) != 0);
+              }
+            }
+            umma_commit(empty + s);
+            if (tap == P.taps - 1) umma_commit(a_empty + ab);
+            if (kc == kc1 - 1 && tap == P.taps - 1) umma_commit(tfull + buf);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < W_EPI0) {
+    // ===== converter warps: fp32 activations -> transformed 16-bit planes in the swizzled A tile =====
+    pdl_wait();
+    const int t256 = (warp - W_CONV0) * 32 + lane;
+    const int c4 = t256 & 15;                       // float4 slot inside the 64-channel chunk (fixed per thread: constants stay in registers)
+    const int r0 = t256 >> 4;                       // first row of this thread (stride 16)
+    uint32_t cg = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const TileRef t = decode_tile(p, tile);
+      const FProb& P = p.pr[t.g];
+      const int kchunks = P.cin_pad / TK;
+      const int kc0 = t.ks * P.kper, kc1 = min(kchunks, kc0 + P.kper);
+      const int lbase = t.mt * TM + P.shift_min;
+      const float* xb = P.x + (int64_t)t.b * P.x_bs;
+      const float* xb1 = P.x1 ? P.x1 + (int64_t)t.b * P.x_bs : nullptr;
+      const float* xb2 = P.x2 ? P.x2 + (int64_t)t.b * P.x_bs : nullptr;
+      const int R = P.R;
+      for (int kc = kc0; kc < kc1; kc++, cg++) {
+        const uint32_t ab = cg & 1;
+        const int ch = kc * TK + c4 * 4;
+        float sc[4], sh[4], aa[4], bb[4];
+        bool chok[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int c = ch + q;
+          chok[q] = c < P.Cin;
+          sc[q] = P.in_scale; sh[q] = 0.f; aa[q] = 1.f; bb[q] = 1.f;
+          if (chok[q]) {
+            if (P.pre_mode == 1) {
+              const float s_ = __ldg(P.pre_scale + (int64_t)t.b * P.Cin + c);
+              sh[q] = __ldg(P.pre_shift + (int64_t)t.b * P.Cin + c);
+              sc[q] = s_ * P.in_scale;
+            } else if (P.pre_mode == 2) {
+              const double* w = P.pre_stats + ((int64_t)t.b * P.Cin + c) * 2;
+              const double mean = w[0] * (double)P.pre_invL;
+              double var = w[1] * (double)P.pre_invL - mean * mean;
+              if (var < 0) var = 0;
+              const double rstd = 1.0 / sqrt(var + (double)P.pre_eps);
+              double g_ = 1.0, be = 0.0;
+              if (P.pre_gb) { g_ = 1.0 + (double)__ldg(P.pre_gb + (int64_t)t.b * P.pre_gb_bs + c); be = (double)__ldg(P.pre_gb + (int64_t)t.b * P.pre_gb_bs + P.Cin + c); }
+              const double s_ = g_ * rstd;
+              sc[q] = (float)s_ * P.in_scale;
+              sh[q] = (float)(be - s_ * mean);
+            }
+            if (P.pre_a) aa[q] = __ldg(P.pre_a + c);
+            if (P.pre_b) bb[q] = __ldg(P.pre_b + c);
+          }
+        }
+        const bool anych = ch < P.Cin;
+        mbar_wait(a_empty + ab, ((cg >> 1) & 1) ^ 1);
+        uint8_t* hi = smem + (size_t)ab * a_buf;
+        uint8_t* lo = p.planes == 2 ? hi + p.a_plane : nullptr;
+        // rows r0, r0+16, ...: four loads in flight per thread
+        for (int r = r0; r < R; r += 64) {
+          float4 v[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int rr = r + u * 16;
+            const int l = lbase + rr;
+            ok[u] = rr < R && l >= 0 && l < P.L && anych;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[u]) {
+              const int64_t off = (int64_t)l * P.x_ld + ch;
+              v[u] = __ldg(reinterpret_cast<const float4*>(xb + off));
+              if (xb1) { const float4 w = __ldg(reinterpret_cast<const float4*>(xb1 + off)); v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w; }
+              if (xb2) { const float4 w = __ldg(reinterpret_cast<const float4*>(xb2 + off)); v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w; }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int rr = r + u * 16;
+            if (rr < R) {
+              if (p.f16) convert_store<__half>(v[u], ok[u], sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo, rr, c4);
+              else convert_store<__nv_bfloat16>(v[u], ok[u], sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo, rr, c4);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + ab);
+      }
+    }
+  } else {
+    // ===== epilogue warps =====
+    pdl_wait();
+    const int ew = warp - W_EPI0;                    // 0..7
+    const int quarter = warp & 3, sub = ew >> 2;     // TMEM lane quarter is warp % 4 (hardware rule); sub splits the 32-column chunks
+    const int et = ew * 32 + lane;                   // 0..255 inside the epilogue group
+    float* stage = staging + ew * (32 * 33);
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
+      const TileRef t = decode_tile(p, tile);
+      const FProb& P = p.pr[t.g];
+      const int mul = P.up_s ? P.up_s : 1;
+      const int l0 = t.mt * TM, n0 = t.nt * P.BN, b = t.b;
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      const bool do_stats = P.stats_out != nullptr;
+      if (do_stats) {
+        for (int i = et; i < 2 * P.BN; i += NEPI * 32) sacc[i] = 0.f;
+        bar_sync(1, NEPI * 32);
+      }
+      mbar_wait(tfull + buf, use & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int mrow0 = l0 + quarter * 32;
+      const uint32_t tcol = tmem_base + buf * (uint32_t)p.tmem_stride + ((uint32_t)(quarter * 32) << 16);
+      bool last_split = true;
+      if (P.ksplit > 1) {
+        // ---- split-K: park this CTA's partial accumulator, then only the last CTA to arrive for the tile carries on
+        const int tid = ((b * P.ntm + t.mt) * P.ntn + t.nt);
+        float* mine = P.ws + ((int64_t)tid * P.ksplit + t.ks) * (TM * P.BN) + (int64_t)(quarter * 32 + lane) * P.BN;
+        for (int c0 = sub * 32; c0 < P.BN; c0 += 64) {
+          uint32_t r[32];
+          tmem_ld32(tcol + (uint32_t)c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(mine + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        }
+        __threadfence();
+        bar_sync(2, NEPI * 32);
+        if (et == 0) {
+          const int prev = atomicAdd(P.counters + tid, 1);
+          const int last = prev == P.ksplit - 1;
+          if (last) P.counters[tid] = 0;              // re-arm for the next launch that reuses this workspace
+          *flag_slot = last;
+        }
+        bar_sync(2, NEPI * 32);
+        last_split = *flag_slot != 0;
+        if (last_split) __threadfence();
+      }
+      if (last_split) {
+        for (int c0 = sub * 32; c0 < P.BN; c0 += 64) {
+          uint32_t r[32];
+          if (P.ksplit > 1) {
+            const int tid = ((b * P.ntm + t.mt) * P.ntn + t.nt);
+            const float* base = P.ws + (int64_t)tid * P.ksplit * (TM * P.BN) + (int64_t)(quarter * 32 + lane) * P.BN + c0;
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = 0.f;
+            for (int s = 0; s < P.ksplit; s++) {       // fixed order -> deterministic sum
+              const float* q = base + (int64_t)s * (TM * P.BN);
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(q + j));
+                acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j++) r[j] = __float_as_uint(acc[j]);
+          } else {
+            tmem_ld32(tcol + (uint32_t)c0, r);
+          }
+          const int n = n0 + c0 + lane;
+          const int ph = P.up_s ? n / P.C : 0;
+          const int co = n - ph * P.C;
+          float st1 = 0.f, st2 = 0.f;
+          if (mrow0 < P.Mrows) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
+            __syncwarp();
+            const int add = P.up_s ? ph - P.up_crop : 0;
+            const float bias = P.bias ? __ldg(P.bias + co) : 0.f;
+            const float cs = P.cscale ? __ldg(P.cscale + (int64_t)b * P.cscale_bs + co) : 1.f;
+            float* ycol = P.y + (int64_t)b * P.y_bs + co;
+            const float* rcol = P.res ? P.res + (int64_t)b * P.res_bs + co : nullptr;
+            const int row0 = mrow0 * mul + add;
+            const int mvalid = min(32, P.Mrows - mrow0);
+            int i_lo = 0, i_hi = mvalid;
+            if (row0 < 0) i_lo = (-row0 + mul - 1) / mul;
+            if (row0 + (mvalid - 1) * mul >= P.Lout) i_hi = P.Lout > row0 ? (P.Lout - row0 + mul - 1) / mul : 0;
+            const int64_t ystride = (int64_t)mul * P.y_ld;
+            float* yp = ycol + (int64_t)row0 * P.y_ld;
+            const bool half_res = P.res_div == 2;
+            const int odd = row0 & 1;
+            const float* rp = rcol ? rcol + (int64_t)(half_res ? (row0 >> 1) : row0) * P.res_ld : nullptr;
+            const int64_t rstride = (int64_t)mul * P.res_ld;
+            const float osc = P.out_scale, cso = cs * P.out_scale;
+            if (i_lo == 0 && i_hi == 32) {
+#pragma unroll
+              for (int hh = 0; hh < 2; hh++) {          // two halves of 16 rows: all loads of a half are issued before its stores
+                float rr[16];
+                if (rp) {
+                  if (!half_res) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) rr[i] = __ldg(rp + (hh * 16 + i) * rstride);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) rr[i] = __ldg(rp + (int64_t)((hh * 16 + i + odd) >> 1) * P.res_ld);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; i++) rr[i] = 0.f;
+                }
+                if (P.accumulate) {
+#pragma unroll
+                  for (int i = 0; i < 16; i++) rr[i] = rr[i] * osc + yp[(hh * 16 + i) * ystride];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; i++) rr[i] *= osc;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                  float a = stage[(hh * 16 + i) * 33 + lane] + bias;
+                  if (P.post_act) a = act_slow(a, P.post_act, P.post_p0);
+                  const float v = fmaf(a, cso, rr[i]);
+                  yp[(hh * 16 + i) * ystride] = v; st1 += v; st2 = fmaf(v, v, st2);
+                }
+              }
+            } else {
+              for (int i = i_lo; i < i_hi; i++) {
+                const int row = row0 + i * mul;
+                float a = stage[i * 33 + lane] + bias;
+                if (P.post_act) a = act_slow(a, P.post_act, P.post_p0);
+                const float rv = rcol ? __ldg(rcol + (int64_t)(half_res ? (row >> 1) : row) * P.res_ld) : 0.f;
+                const float o = P.accumulate ? ycol[(int64_t)row * P.y_ld] : 0.f;
+                const float v = (a * cs + rv) * osc + o;
+                ycol[(int64_t)row * P.y_ld] = v; st1 += v; st2 = fmaf(v, v, st2);
+              }
+            }
+            __syncwarp();
+          }
+          if (do_stats) { atomicAdd(sacc + c0 + lane, st1); atomicAdd(sacc + P.BN + c0 + lane, st2); }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty + buf);                // 8 arrivals free the accumulator for tile lt + 2
+      if (do_stats) {
+        bar_sync(1, NEPI * 32);
+        if (last_split) {
+          const int co0 = P.up_s ? (n0 % P.C) : n0;
+          for (int i = et; i < 2 * P.BN; i += NEPI * 32) {
+            const int which = i >= P.BN, col = i - which * P.BN;
+            atomicAdd(P.stats_out + ((int64_t)b * P.C + co0 + col) * 2 + which, (double)sacc[i]);
+          }
+        }
+        bar_sync(1, NEPI * 32);
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_enc = nullptr;
+
+int get_enc() {
+  if (g_enc) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+  g_enc = (EncodeTiledFn)fn;
+  return 0;
+}
+
+int make_wmap(CUtensorMap* m, const void* base, uint64_t cin_pad, uint64_t rows, uint32_t bn, int f16) {
+  cuuint64_t gd[2] = {cin_pad, rows};
+  cuuint64_t gs[1] = {cin_pad * 2};
+  cuuint32_t bx[2] = {TK, bn};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace
+
+extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t planes, int32_t f16, void* ws, int64_t ws_bytes, void* stream) {
+  B2A_CHECK_ARG(pr && n >= 1 && n <= MAXG && (planes == 1 || planes == 2), "1..4 problems, planes 1 or 2");
+  if (get_enc() != 0) { b2a_set_error("b2a_conv1d_fused: cuTensorMapEncodeTiled entry point not found"); return B2A_E_CUDA; }
+  static int nsm = 0, pdl = -1, ksplit_on = -1;
+  if (!nsm) {
+    int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    if (nsm <= 0) nsm = 148;
+    const char* e = getenv("B2A_FUSED_PDL"); pdl = (e && e[0] == '0') ? 0 : 1;
+    const char* k = getenv("B2A_FUSED_KSPLIT"); ksplit_on = (k && k[0] == '0') ? 0 : 1;
+  }
+  FParams p;
+  p.G = n; p.planes = planes; p.f16 = f16 ? 1 : 0;
+  // heaviest problem first (cost per tile ~ taps * K chunks): sort indices
+  int order[MAXG];
+  double cost[MAXG];
+  for (int i = 0; i < n; i++) { order[i] = i; cost[i] = (double)pr[i].taps * pr[i].cin_pad; }
+  for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (cost[order[j]] > cost[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
+  int maxR = 0, maxBN = 0, maxWst = 0, tiles_total = 0;
+  int64_t base_tiles = 0;
+  for (int gi = 0; gi < n; gi++) {
+    const b2a_convf_t& q = pr[order[gi]];
+    B2A_CHECK_ARG(q.x && q.w_hi && q.y && q.B > 0 && q.L > 0 && q.Lout > 0 && q.Cin > 0 && q.taps > 0 && q.taps <= 32 && q.cin_pad % 64 == 0 && q.cin_pad >= q.Cin,
+                  "bad pointers / shape");
+    B2A_CHECK_ARG(q.N % 32 == 0 && q.y_ld % 4 == 0 && (q.res == nullptr || q.res_ld % 4 == 0) && (q.res_div == 1 || q.res_div == 2), "N % 32, row strides % 4, res_div 1|2");
+    B2A_CHECK_ARG(q.x_ld % 4 == 0 && q.x_bs % 4 == 0 && ((uintptr_t)q.x & 15) == 0 && q.x_ld >= ((q.Cin + 3) & ~3), "x must be 16-byte aligned with row stride % 4 == 0 and >= ceil4(Cin)");
+    B2A_CHECK_ARG((q.x1 == nullptr || ((uintptr_t)q.x1 & 15) == 0) && (q.x2 == nullptr || ((uintptr_t)q.x2 & 15) == 0), "x1 / x2 alignment");
+    B2A_CHECK_ARG(q.up_stride >= 0 && (q.up_stride == 0 || (q.N % q.up_stride == 0 && (q.N / q.up_stride) % 32 == 0)), "transposed mode: N = up_stride * C, C % 32 == 0");
+    B2A_CHECK_ARG(q.pre_mode >= 0 && q.pre_mode <= 2 && (q.pre_mode != 1 || (q.pre_scale && q.pre_shift)) && (q.pre_mode != 2 || q.pre_stats), "prologue mode / pointers");
+    FProb& P = p.pr[gi];
+    P.x = q.x; P.x1 = q.x1; P.x2 = q.x2; P.x_bs = q.x_bs; P.x_ld = q.x_ld; P.in_scale = q.in_scale;
+    P.B = q.B; P.L = q.L; P.Cin = q.Cin; P.cin_pad = q.cin_pad;
+    P.pre_mode = q.pre_mode; P.pre_scale = q.pre_scale; P.pre_shift = q.pre_shift; P.pre_stats = q.pre_stats; P.pre_gb = q.pre_gb;
+    P.pre_gb_bs = q.pre_gb_bs; P.pre_eps = q.pre_eps; P.pre_invL = 1.0f / (float)q.L;
+    P.pre_act = q.pre_act; P.pre_p0 = q.pre_p0; P.pre_a = q.pre_a; P.pre_b = q.pre_b;
+    P.taps = q.taps; P.wplanes = q.w_lo ? 2 : 1; P.Ntot = q.N;
+    int smin = q.shifts[0], smax = q.shifts[0];
+    for (int i = 0; i < q.taps; i++) { P.shift[i] = q.shifts[i]; smin = q.shifts[i] < smin ? q.shifts[i] : smin; smax = q.shifts[i] > smax ? q.shifts[i] : smax; }
+    if (smax - smin > 64) { b2a_set_error("b2a_conv1d_fused: taps span %d rows (> 64)", smax - smin); return B2A_E_UNSUPPORTED; }
+    P.shift_min = smin; P.R = (TM + (smax - smin) + 7) / 8 * 8;
+    P.up_s = q.up_stride; P.up_crop = q.up_crop; P.C = q.up_stride ? q.N / q.up_stride : q.N;
+    P.Lout = q.Lout; P.Mrows = q.up_stride ? q.L + q.taps - 1 : q.Lout;
+    P.ntm = cdiv(P.Mrows, TM);
+    // N tile: the widest divisor of N (multiple of 32, <= 128) -- in polyphase mode also a divisor of C so that a tile stays inside one phase
+    int bn = 0;
+    for (int c = 128; c >= 32; c -= 32) if (q.N % c == 0 && P.C % c == 0) { bn = c; break; }
+    P.BN = bn; P.ntn = q.N / bn;
+    base_tiles = (int64_t)P.ntm * P.ntn * q.B;
+    // split K across CTAs when the problem alone cannot give every SM a tile (single-problem launches only)
+    const int kchunks = q.cin_pad / TK;
+    P.ksplit = 1;
+    if (ksplit_on && n == 1 && base_tiles * 2 <= nsm && kchunks >= 4 && ws) {
+      int ks = (int)(nsm / base_tiles);
+      if (ks > 8) ks = 8;
+      if (ks > kchunks / 2) ks = kchunks / 2;
+      if (ks >= 2) P.ksplit = ks;
+    }
+    P.kper = cdiv(kchunks, P.ksplit);
+    P.ksplit = cdiv(kchunks, P.kper);                     // no empty splits
+    P.bias = q.bias; P.post_act = q.post_act; P.post_p0 = q.post_p0; P.cscale = q.cscale; P.cscale_bs = q.cscale_bs;
+    P.res = q.res; P.res_bs = q.res_bs; P.res_ld = q.res_ld; P.res_div = q.res_div; P.out_scale = q.out_scale; P.accumulate = q.accumulate;
+    P.y = q.y; P.y_bs = q.y_bs; P.y_ld = q.y_ld; P.stats_out = q.stats_out;
+    P.ws = nullptr; P.counters = nullptr;
+    if (P.ksplit > 1) {
+      const int64_t need = base_tiles * P.ksplit * (TM * P.BN) * 4 + base_tiles * 4 + 256;
+      if (need > ws_bytes) { P.ksplit = 1; P.kper = kchunks; }
+      else { P.counters = (int*)ws; P.ws = (float*)((uint8_t*)ws + ((base_tiles * 4 + 255) / 256) * 256); }
+    }
+    P.tile_begin = tiles_total;
+    tiles_total += (int)(base_tiles * P.ksplit);
+    maxR = P.R > maxR ? P.R : maxR; maxBN = P.BN > maxBN ? P.BN : maxBN;
+    const int wsz = P.BN * 128 * P.wplanes;
+    maxWst = wsz > maxWst ? wsz : maxWst;
+  }
+  p.ntiles = tiles_total;
+  p.a_plane = maxR * 128;
+  p.w_stage = maxWst;
+  p.tmem_stride = (int)(maxBN <= 32 ? 32 : maxBN <= 64 ? 64 : maxBN <= 128 ? 128 : 256);
+  const size_t fixed = (size_t)2 * p.a_plane * planes + STAGING + SACC + 1024 /*align*/ + 512 /*barriers*/;
+  int wst = (int)(((size_t)227 * 1024 - fixed) / p.w_stage);
+  if (wst > 8) wst = 8;
+  if (wst < 2) { b2a_set_error("b2a_conv1d_fused: shared memory cannot hold two weight stages (R %d, BN %d)", maxR, maxBN); return B2A_E_UNSUPPORTED; }
+  p.wst = wst;
+  const size_t smem = fixed + (size_t)wst * p.w_stage;
+
+  CUtensorMap mw[MAXG], ml[MAXG];
+  for (int gi = 0; gi < MAXG; gi++) {
+    const b2a_convf_t& q = pr[order[gi < n ? gi : 0]];
+    const FProb& P = p.pr[gi < n ? gi : 0];
+    int e = make_wmap(&mw[gi], q.w_hi, (uint64_t)q.cin_pad, (uint64_t)q.taps * q.N, (uint32_t)P.BN, p.f16);
+    if (!e) e = make_wmap(&ml[gi], q.w_lo ? q.w_lo : q.w_hi, (uint64_t)q.cin_pad, (uint64_t)q.taps * q.N, (uint32_t)P.BN, p.f16);
+    if (e) { b2a_set_error("b2a_conv1d_fused: cuTensorMapEncodeTiled failed (%d)", e); return B2A_E_CUDA; }
+  }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  const int grid = tiles_total < nsm ? tiles_total : nsm;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, conv_fused_kernel, p, mw[0], mw[1], mw[2], mw[3], ml[0], ml[1], ml[2], ml[3]);
+  if (err != cudaSuccess) { b2a_set_error("b2a_conv1d_fused: launch failed: %s", cudaGetErrorString(err)); return B2A_E_CUDA; }
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}

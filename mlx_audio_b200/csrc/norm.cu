@@ -30,6 +30,31 @@ __global__ void adain_partial_kernel(const float* __restrict__ x, int64_t x_bs, 
   }
 }
 
+// (sum, sumsq) of every channel ADDED to up to four float64 accumulators [B][.][2] (each pointer already offset to its first channel,
+// `dst_bs` doubles between batches): the statistics format the fused conv's epilogue produces and its prologue consumes.
+__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int L, int C, double* d0, double* d1,
+                                     double* d2, double* d3, int64_t bs0, int64_t bs1, int64_t bs2, int64_t bs3) {
+  __shared__ double s1[8][33], s2[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, chunk = blockIdx.y, b = blockIdx.z;
+  const int r0 = chunk * ROWS_PER_CHUNK, r1 = min(L, r0 + ROWS_PER_CHUNK);
+  double a1 = 0.0, a2 = 0.0;
+  if (c < C) {
+    const float* xp = x + (int64_t)b * x_bs + c;
+    for (int r = r0 + threadIdx.y; r < r1; r += 8) { double v = (double)__ldg(xp + (int64_t)r * x_ld); a1 += v; a2 = fma(v, v, a2); }
+  }
+  s1[threadIdx.y][threadIdx.x] = a1; s2[threadIdx.y][threadIdx.x] = a2;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    double t1 = 0, t2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+    if (d0) { atomicAdd(d0 + (int64_t)b * bs0 + 2 * c, t1); atomicAdd(d0 + (int64_t)b * bs0 + 2 * c + 1, t2); }
+    if (d1) { atomicAdd(d1 + (int64_t)b * bs1 + 2 * c, t1); atomicAdd(d1 + (int64_t)b * bs1 + 2 * c + 1, t2); }
+    if (d2) { atomicAdd(d2 + (int64_t)b * bs2 + 2 * c, t1); atomicAdd(d2 + (int64_t)b * bs2 + 2 * c + 1, t2); }
+    if (d3) { atomicAdd(d3 + (int64_t)b * bs3 + 2 * c, t1); atomicAdd(d3 + (int64_t)b * bs3 + 2 * c + 1, t2); }
+  }
+}
+
 // one warp per (b, c): lanes stride the chunk partials (a serial walk over ~200 chunks per thread cost 20 us per call)
 __global__ void adain_final_kernel(const double* __restrict__ ws, int nchunk, int L, int C, const float* __restrict__ gb,
                                    float eps, float* __restrict__ scale, float* __restrict__ shift, int B) {
@@ -101,6 +126,18 @@ extern "C" int32_t b2a_adain_coeffs_from_partials(const double* partials, int32_
                                                   float eps, float* scale, float* shift, void* stream) {
   B2A_CHECK_ARG(partials && scale && shift && B > 0 && L > 0 && C > 0 && nslots > 0, "bad pointers/shape");
   adain_final_kernel<<<cdiv((int64_t)B * C, 8), 256, 0, (cudaStream_t)stream>>>(partials, nslots, L, C, gb, eps, scale, shift, B);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_channel_stats(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, double* const* dst,
+                                     const int64_t* dst_bs, int32_t n_dst, void* stream) {
+  B2A_CHECK_ARG(x && dst && dst_bs && B > 0 && L > 0 && C > 0 && n_dst >= 1 && n_dst <= 4, "bad pointers/shape (1..4 destinations)");
+  double* d[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t bs[4] = {0, 0, 0, 0};
+  for (int i = 0; i < n_dst; i++) { B2A_CHECK_ARG(dst[i], "null destination"); d[i] = dst[i]; bs[i] = dst_bs[i]; }
+  dim3 grid(cdiv(C, 32), cdiv(L, ROWS_PER_CHUNK), B), block(32, 8);
+  channel_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, L, C, d[0], d[1], d[2], d[3], bs[0], bs[1], bs[2], bs[3]);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

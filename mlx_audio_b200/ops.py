@@ -15,7 +15,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import AttnParams, Conv1dParams
+from ._lib import AttnParams, Conv1dParams, ConvFParams
 
 ACT = {"none": 0, "lrelu": 1, "snake": 2, "elu": 3, "gelu": 4, "gelu_tanh": 5, "tanh": 6, "sigmoid": 7,
        "silu": 8, "clip1": 9}
@@ -225,6 +225,11 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L - 1) * stride + cw.K - 2 * pad_left
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
+    if emit is None and fused_eligible(x, cw, stride, dilation, transpose, pad_mode):
+        y = conv_fused(FusedProblem(x, cw, stride=stride, dilation=dilation, pad_left=pad_left, lout=lout, pre=pre, post_act=post_act,
+                                    post_p0=post_p0, cscale=cscale, res=res, res_div=res_div, out_scale=out_scale, out=out,
+                                    accumulate=accumulate, transpose=transpose))[0]
+        return (y, None) if stats else y
     if _tc_eligible(cw, L, stride, transpose, pad_mode, dilation):
         return _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, res, res_div, out_scale, out, accumulate,
                           up_stride=stride if transpose else 0, stats=stats)
@@ -333,6 +338,138 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
     return (out, ws) if stats else out
 
 
+
+# ---------------------------------------------------------------------------------------------------------------- fused tcgen05 conv
+# One launch per layer (or per GROUP of independent layers): InstanceNorm / AdaIN coefficients from the producer's (sum, sumsq), the
+# input activation, the 16-bit hi/lo split, the tap-summed GEMM, the epilogue and the output's (sum, sumsq) -- csrc/conv_fused.cu.
+FUSED = [os.environ.get("B2A_FUSED", "1") != "0"]
+FUSED_WS_BYTES = 16 << 20
+_FUSED_WS = {}
+
+
+@dataclass
+class PreStats:
+    """Input transform whose scale/shift the kernel derives itself: InstanceNorm over L from ``stats`` [B, C, 2] float64 (sum, sumsq) as
+    accumulated by the producing layer, folded with AdaIN's (1 + gamma) / beta rows ``gb`` [B, 2C] (None: plain InstanceNorm); then
+    the activation."""
+    stats: torch.Tensor
+    gb: Optional[torch.Tensor] = None
+    eps: float = 1e-5
+    act: int = 0
+    p0: float = 0.0
+    a: Optional[torch.Tensor] = None
+    b: Optional[torch.Tensor] = None
+
+
+def new_stats(B: int, Cc: int, device) -> torch.Tensor:
+    """Zeroed (sum, sumsq) accumulator for ``FusedProblem(..., stats_out=)``."""
+    return torch.zeros(B, Cc, 2, device=device, dtype=torch.float64)
+
+
+def fused_eligible(x, cw: "ConvW", stride: int = 1, dilation: int = 1, transpose: bool = False, pad_mode: int = 0) -> bool:
+    """Dense layers the fused kernel takes: tensor-core weights, stride 1 (or a polyphase transposed conv), taps spanning <= 64 rows,
+    16-byte aligned fp32 rows."""
+    if not FUSED[0] or TC_MODE[0] == "off" or cw.w_tc is None or pad_mode != 0 or cw.cout % 32 != 0 or cw.groups != 1 or isinstance(x, Planes):
+        return False
+    if x.dtype != torch.float32 or x.dim() != 3 or x.stride(2) != 1 or x.stride(1) % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
+        return False
+    if x.stride(1) < -(-x.shape[2] // 4) * 4:
+        return False
+    if transpose:
+        return dilation == 1 and cw.K % stride == 0 and cw.K // stride <= 32 and cw.cin * (cw.K // stride) >= TC_MIN_K
+    return stride == 1 and cw.K <= 32 and (cw.K - 1) * dilation <= 64 and cw.cin * cw.K >= TC_MIN_K
+
+
+class FusedProblem:
+    """One problem of a fused launch: the filled C struct, its output tensor and the tensors it points into (kept alive)."""
+
+    def __init__(self, x, cw: "ConvW", *, stride=1, dilation=1, pad_left=0, lout=None, pre=None, x_add=(), in_scale=1.0, post_act=0, post_p0=0.0,
+                 cscale=None, res=None, res_div=1, out_scale=1.0, out=None, accumulate=False, transpose=False, stats_out=None):
+        _chk3(x, "conv_fused x")
+        B, L, cin = x.shape
+        if cin != cw.cin:
+            raise ValueError(f"conv_fused: input has {cin} channels, weight expects {cw.cin}")
+        if lout is None:
+            lout = (L - 1) * stride + cw.K - 2 * pad_left if transpose else (L + 2 * pad_left - dilation * (cw.K - 1) - 1) + 1
+        if out is None:
+            out = torch.empty(B, lout, cw.cout, device=x.device, dtype=torch.float32)
+        else:
+            _chk3(out, "conv_fused out")
+            if out.shape != (B, lout, cw.cout):
+                raise ValueError(f"conv_fused: out has shape {tuple(out.shape)}, expected {(B, lout, cw.cout)}")
+        p = ConvFParams()
+        p.x, p.x_bs, p.x_ld, p.in_scale = x.data_ptr(), x.stride(0), x.stride(1), float(in_scale)
+        keep = [x, out, cw]
+        for i, xa in enumerate(x_add):
+            if xa.shape != x.shape or xa.stride() != x.stride() or xa.dtype != torch.float32:
+                raise ValueError("conv_fused: x_add tensors must have x's shape and strides")
+            setattr(p, "x1" if i == 0 else "x2", xa.data_ptr())
+            keep.append(xa)
+        p.B, p.L, p.Cin = B, L, cin
+        if isinstance(pre, PreStats):
+            if pre.stats.dtype != torch.float64 or tuple(pre.stats.shape) != (B, cin, 2) or not pre.stats.is_contiguous():
+                raise ValueError("conv_fused: stats must be a contiguous float64 [B, Cin, 2] tensor")
+            p.pre_mode, p.pre_stats, p.pre_eps = 2, pre.stats.data_ptr(), float(pre.eps)
+            if pre.gb is not None:
+                if pre.gb.shape[-1] != 2 * cin or pre.gb.stride(-1) != 1:
+                    raise ValueError("conv_fused: gb must be [B, 2*Cin] rows (gamma | beta)")
+                p.pre_gb, p.pre_gb_bs = pre.gb.data_ptr(), (pre.gb.stride(0) if pre.gb.dim() == 2 and pre.gb.shape[0] == B and B > 1 else 0)
+            keep += [pre.stats, pre.gb]
+        elif pre is not None and pre.scale is not None:
+            p.pre_mode, p.pre_scale, p.pre_shift = 1, pre.scale.data_ptr(), pre.shift.data_ptr()
+            keep += [pre.scale, pre.shift]
+        if pre is not None:
+            p.pre_act, p.pre_p0, p.pre_a, p.pre_b = pre.act, float(pre.p0), _p(pre.a), _p(pre.b)
+            keep += [pre.a, pre.b]
+        if transpose:
+            taps, n_total = cw.K // stride, stride * cw.cout
+            w_tc, w_lo = _tc_transposed_weights(cw, stride)
+            shifts = [-j for j in range(taps)]
+            p.up_stride, p.up_crop = stride, pad_left
+        else:
+            taps, n_total, w_tc, w_lo = cw.K, cw.cout, cw.w_tc, cw.w_tc_lo
+            shifts = [k * dilation - pad_left for k in range(taps)]
+        p.w_hi, p.w_lo, p.cin_pad, p.taps, p.N = w_tc.data_ptr(), _p(w_lo), cw.cin_pad, taps, n_total
+        for i, sft in enumerate(shifts):
+            p.shifts[i] = sft
+        p.Lout, p.bias, p.post_act, p.post_p0 = lout, _p(cw.bias), post_act, float(post_p0)
+        if cscale is not None:
+            p.cscale, p.cscale_bs = cscale.data_ptr(), (cscale.stride(0) if cscale.dim() == 2 else 0)
+            keep.append(cscale)
+        if res is not None:
+            _chk3(res, "conv_fused res")
+            p.res, p.res_bs, p.res_ld = res.data_ptr(), (res.stride(0) if res.shape[0] == B else 0), res.stride(1)
+            keep.append(res)
+        p.res_div, p.out_scale, p.accumulate = res_div, float(out_scale), int(accumulate)
+        p.y, p.y_bs, p.y_ld = out.data_ptr(), out.stride(0), out.stride(1)
+        if stats_out is not None:
+            if stats_out.dtype != torch.float64 or tuple(stats_out.shape) != (B, cw.cout, 2) or not stats_out.is_contiguous():
+                raise ValueError("conv_fused: stats_out must be a contiguous float64 [B, Cout, 2] tensor")
+            p.stats_out = stats_out.data_ptr()
+            keep.append(stats_out)
+        self.p, self.out, self.keep, self.f16 = p, out, keep, cw.f16
+
+
+def conv_fused(problems) -> list:
+    """Launch 1..4 independent fused conv problems on one persistent grid; returns their outputs."""
+    if isinstance(problems, FusedProblem):
+        problems = [problems]
+    n = len(problems)
+    if not 1 <= n <= 4:
+        raise ValueError("conv_fused: 1..4 problems per launch")
+    f16 = problems[0].f16
+    if any(pr.f16 != f16 for pr in problems):
+        raise ValueError("conv_fused: all problems of a launch must use the same 16-bit operand type")
+    arr = (ConvFParams * n)(*[pr.p for pr in problems])
+    dev = problems[0].out.device
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    ws = _FUSED_WS.get(key)
+    if ws is None:
+        ws = _FUSED_WS[key] = torch.zeros(FUSED_WS_BYTES, device=dev, dtype=torch.uint8)      # split-K partial tiles + (self-resetting) counters
+    _call("conv_tc", _lib.lib().b2a_conv1d_fused, 1, arr, n, 2 if TC_MODE[0] == "x2" else 1, int(f16), ws.data_ptr(), ws.numel(), _stream())
+    return [pr.out for pr in problems]
+
+
 def linear(x: torch.Tensor, cw: ConvW, **kw) -> torch.Tensor:
     """nn.Linear on [..., in] via the K=1 conv; accepts [rows, in] or [B, L, in]."""
     if x.dim() == 2:
@@ -418,6 +555,31 @@ def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5, partials
     ws = _workspace(_lib.lib().b2a_adain_ws_bytes(B, L, Cc), x.device)
     _call("adain_stats", _lib.lib().b2a_adain_coeffs, 2, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, _p(gb), eps,
                                            scale.data_ptr(), shift.data_ptr(), ws.data_ptr(), _stream())
+    return scale, shift
+
+
+def channel_stats(x: torch.Tensor, dsts) -> None:
+    """Add (sum, sumsq) over L of x [B, L, C] to each float64 accumulator in ``dsts`` (views [B, C, 2] of possibly wider [B, C', 2] buffers)."""
+    _chk3(x, "channel_stats x")
+    B, L, Cc = x.shape
+    if isinstance(dsts, torch.Tensor):
+        dsts = [dsts]
+    n = len(dsts)
+    for d in dsts:
+        assert d.dtype == torch.float64 and tuple(d.shape) == (B, Cc, 2) and d.stride(2) == 1 and d.stride(1) == 2
+    ptrs = (C.c_void_p * n)(*[d.data_ptr() for d in dsts])
+    bss = (C.c_int64 * n)(*[d.stride(0) for d in dsts])
+    _call("adain_stats", _lib.lib().b2a_channel_stats, 1, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, ptrs, bss, n, _stream())
+
+
+def coeffs_from_stats(stats: torch.Tensor, L: int, gb: Optional[torch.Tensor], eps=1e-5):
+    """(sum, sumsq) [B, C, 2] float64 -> AdaIN (scale, shift) [B, C] float32 for consumers outside the fused conv (depthwise layers)."""
+    B, Cc, _ = stats.shape
+    assert stats.dtype == torch.float64 and stats.is_contiguous()
+    scale = torch.empty(B, Cc, device=stats.device, dtype=torch.float32)
+    shift = torch.empty(B, Cc, device=stats.device, dtype=torch.float32)
+    _call("adain_stats", _lib.lib().b2a_adain_coeffs_from_partials, 1, stats.data_ptr(), 1, B, L, Cc, _p(gb), eps, scale.data_ptr(),
+          shift.data_ptr(), _stream())
     return scale, shift
 
 

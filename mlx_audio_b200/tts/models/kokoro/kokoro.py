@@ -97,6 +97,7 @@ class Model:
         self.use_graphs = True     # __call__ / generate replay cached CUDA graphs (synthesize_ids); False -> eager forward_ids
         self.max_graphs = 32
         self._graphs, self._graph_pool, self._rng_state, self._warm_stream = {}, None, None, None
+        self._stats_pool = None
 
     # ------------------------------------------------------------------ protocol
     @property
@@ -312,6 +313,193 @@ class Model:
                 x, xpart = ops.conv1d(xt, blk["c2"][j], pad_left=(k - 1) // 2, pre=Pre(s2, h2, ACT["snake"], 0.0, a, ia), res=x, stats=True)
         return x
 
+
+    # ------------------------------------------------------------------ fused acoustic side (one launch per layer GROUP)
+    # Every dense conv below is ONE launch of csrc/conv_fused.cu that also applies the AdaIN + Snake / LeakyReLU in front of it (from the
+    # (sum, sumsq) its producer accumulated) and accumulates the (sum, sumsq) of its own output for the next AdaIN.  Layers that are
+    # independent of each other -- the F0 and N heads, a block's conv1 and its 1x1 shortcut, the three parallel AdaINResBlock1 branches of
+    # a generator stage (kernel sizes 3 / 7 / 11) -- share one persistent grid.
+    def _stats(self, C: int) -> torch.Tensor:
+        if self._stats_pool is not None:                               # buffers reserved up front for a concurrent branch
+            t = self._stats_pool.pop(0)
+            assert t.shape[1] == C
+            return t
+        off = self._arena_off
+        self._arena_off += 2 * C
+        assert self._arena_off <= self._arena.numel()
+        return self._arena[off:off + 2 * C].view(1, C, 2)
+
+    def _resblk1d_group(self, xs, sxs, blks, outs=None, sos=None):
+        """AdainResBlk1d (istftnet.py:853-933) for n parallel blocks of identical structure: xs[i] [1,L,Cin] with statistics sxs[i]
+        -> outs[i] [1, L or 2L, Cout] (statistics of the outputs added to sos[i] when given)."""
+        n = len(blks)
+        outs = outs or [None] * n
+        sos = sos or [None] * n
+        up = blks[0]["up"]
+        L = xs[0].shape[1]
+        lrelu = ACT["lrelu"]
+        s1 = [self._stats(b["conv1"].cout) for b in blks]
+        first = []
+        if up:
+            rs = []
+            for x, sx, b in zip(xs, sxs, blks):
+                sc, sh = ops.coeffs_from_stats(sx, L, self._gb(b["name"] + ".norm1"))
+                rs.append(ops.conv1d(x, b["pool"], stride=2, pad_left=1, lout=2 * L, pre=Pre(sc, sh, lrelu, 0.2), transpose=True))
+            first = [ops.FusedProblem(r, b["conv1"], pad_left=1, stats_out=st) for r, b, st in zip(rs, blks, s1)]
+        else:
+            first = [ops.FusedProblem(x, b["conv1"], pad_left=1, pre=ops.PreStats(sx, self._gb(b["name"] + ".norm1"), 1e-5, lrelu, 0.2), stats_out=st)
+                     for x, sx, b, st in zip(xs, sxs, blks, s1)]
+        shortcut = [ops.FusedProblem(x, b["sc"]) for x, b in zip(xs, blks) if "sc" in b]
+        res = ops.conv_fused(first + shortcut) if len(first) + len(shortcut) <= 4 else ops.conv_fused(first) + ops.conv_fused(shortcut)
+        r1 = res[:n]
+        scs = res[n:] if shortcut else xs
+        second = [ops.FusedProblem(r, b["conv2"], pad_left=1, pre=ops.PreStats(st, self._gb(b["name"] + ".norm2"), 1e-5, lrelu, 0.2), res=sc,
+                                   res_div=2 if up else 1, out_scale=1.0 / math.sqrt(2.0), out=o, stats_out=so)
+                  for r, b, st, sc, o, so in zip(r1, blks, s1, scs, outs, sos)]
+        return ops.conv_fused(second)
+
+    def _resblock1_group(self, xs, sxs, blks, outs=None):
+        """AdaINResBlock1 (istftnet.py:341-396) for n parallel blocks (different kernel sizes) -> n outputs."""
+        n = len(blks)
+        outs = outs or [None] * n
+        cur, scur = list(xs), list(sxs)
+        for j in range(3):
+            last = j == 2
+            st1 = [self._stats(b["c1"][j].cout) for b in blks]
+            c1 = [ops.FusedProblem(x, b["c1"][j], dilation=b["dils"][j], pad_left=(b["k"] * b["dils"][j] - b["dils"][j]) // 2,
+                                   pre=ops.PreStats(sx, self._gb(f"{b['name']}.adain1.{j}"), 1e-5, ACT["snake"], 0.0, *b["a1"][j]), stats_out=st)
+                  for x, sx, b, st in zip(cur, scur, blks, st1)]
+            xt = ops.conv_fused(c1)
+            snew = [None if last else self._stats(b["c2"][j].cout) for b in blks]
+            c2 = [ops.FusedProblem(t, b["c2"][j], pad_left=(b["k"] - 1) // 2,
+                                   pre=ops.PreStats(st, self._gb(f"{b['name']}.adain2.{j}"), 1e-5, ACT["snake"], 0.0, *b["a2"][j]), res=x,
+                                   out=outs[i] if last else None, stats_out=sn)
+                  for i, (t, st, x, b, sn) in enumerate(zip(xt, st1, cur, blks, snew))]
+            cur, scur = ops.conv_fused(c2), snew
+        return cur
+
+    @torch.no_grad()
+    def _acoustic_side_fused(self, st, F: int, noise=None, f0n_override=None):
+        W, cfg, dev = self._w, self.config, self.device
+        self._bind(st)
+        hd = cfg.hidden_dim
+        par = self.concurrent
+        X, t_en = st["X"], st["t_en"]
+        idx = st["idx"][:F]
+        self._arena = torch.zeros(1 << 17, device=dev, dtype=torch.float64)          # every (sum, sumsq) accumulator of the utterance: one memset
+        self._arena_off = 0
+        # ---- F0 / N prediction: the two heads run as 2-problem groups
+        en = ops.gather_rows(X, idx)                                   # [F,640]  == d^T @ aln
+        xs = self._lstm_run(en, W["shared"])[None]                     # [1,F,512]
+        sxs = self._stats(xs.shape[2])
+        ops.channel_stats(xs, sxs)
+        F0N = torch.empty(2, 2 * F, 1, device=dev, dtype=torch.float32)
+        hcur, scur = [xs, xs], [sxs, sxs]
+        for bi in range(3):
+            blks = [W["F0"][bi], W["N"][bi]]
+            sos = [self._stats(b["conv2"].cout) for b in blks] if bi < 2 else None
+            hcur = self._resblk1d_group(hcur, scur, blks, sos=sos)
+            scur = sos
+        ops.conv1d(hcur[0], W["F0_proj"], out=F0N[0:1])
+        ops.conv1d(hcur[1], W["N_proj"], out=F0N[1:2])
+        if f0n_override is not None:
+            F0N[0, :, 0].copy_(torch.as_tensor(f0n_override[0]).to(device=dev, dtype=torch.float32).reshape(-1))
+            F0N[1, :, 0].copy_(torch.as_tensor(f0n_override[1]).to(device=dev, dtype=torch.float32).reshape(-1))
+        f0_curve, n_curve = F0N[0:1], F0N[1:2]                         # [1,2F,1]
+        self._tap("en", en)
+        self._tap("F0", f0_curve)
+        self._tap("N", n_curve)
+        # ---- harmonic-source path: its own branch (concurrent with the decoder blocks)
+        ist = cfg.istftnet
+        rates, ks = ist["upsample_rates"], ist["upsample_kernel_sizes"]
+        nk = len(ist["resblock_kernel_sizes"])
+        n_har = 120 * F + 1
+        xsrcs = []
+        for i in range(len(rates)):
+            sf0 = math.prod(rates[i + 1:]) if i + 1 < len(rates) else 1
+            Li = (n_har + 2 * ((sf0 + 1) // 2) - (2 * sf0 - 1) - 1) // sf0 + 1 if sf0 > 1 else n_har
+            xsrcs.append(torch.empty(1, Li, W["noise_convs"][i].cout, device=dev, dtype=torch.float32))
+        src_stats = [self._stats(W["noise_convs"][i].cout) for i in range(len(rates))]
+        src_arena = [[self._stats(W["noise_convs"][i].cout) for _ in range(5)] for i in range(len(rates))]   # reserved up front: the branch runs concurrently
+
+        def source_branch():
+            har = ops.kokoro_source(f0_curve.reshape(1, 2 * F), noise, *W["src_lin"])      # [1,120F+1,22]
+            self._tap("har", har)
+            for i in range(len(rates)):
+                if i + 1 < len(rates):
+                    sf0 = math.prod(rates[i + 1:])
+                    t = ops.conv1d(har, W["noise_convs"][i], stride=sf0, pad_left=(sf0 + 1) // 2)
+                else:
+                    t = ops.conv1d(har, W["noise_convs"][i])
+                ops.channel_stats(t, src_stats[i])
+                pool, self._stats_pool = self._stats_pool, list(src_arena[i])
+                try:
+                    self._resblock1_group([t], [src_stats[i]], [W["noise_res"][i]], outs=[xsrcs[i]])
+                finally:
+                    self._stats_pool = pool
+
+        if par:
+            side_src = ops.fork(dev, 1)
+            with torch.cuda.stream(side_src[0]):
+                source_branch()
+        # ---- decoder
+        b514 = torch.empty(1, F, hd + 4, device=dev, dtype=torch.float32)[:, :, :hd + 2]     # row stride padded to a multiple of 4 floats
+        ops.gather_rows(t_en, idx, out=b514[0, :, :hd])                # asr = t_en @ aln
+        ops.conv1d(f0_curve, W["F0_conv"], stride=2, pad_left=1, out=b514[:, :, hd:hd + 1])
+        ops.conv1d(n_curve, W["N_conv"], stride=2, pad_left=1, out=b514[:, :, hd + 1:hd + 2])
+        bufs = [torch.empty(1, F, 1024 + 64 + 4, device=dev, dtype=torch.float32)[:, :, :1024 + 64 + 2] for _ in range(2)]
+        ops.conv1d(b514[:, :, :hd], W["asr_res"], out=bufs[0][:, :, 1024:1088])
+        ops.copy2d(b514[0, :, hd:], bufs[0][0, :, 1088:])
+        ops.copy2d(bufs[0][0, :, 1024:], bufs[1][0, :, 1024:])
+        s514 = self._stats(hd + 2)
+        ops.channel_stats(b514, s514)
+        nblk = len(W["decode"])
+        sbuf = [self._stats(1024 + 64 + 2) for _ in range(nblk)]       # statistics of each decode block's input [conv out | asr_res | F0 | N]
+        ops.channel_stats(bufs[0][:, :, 1024:], [sb[:, 1024:] for sb in sbuf])      # the side channels are the same for every block
+        self._resblk1d_group([b514], [s514], [W["encode"]], outs=[bufs[0][:, :, :1024]], sos=[sbuf[0][:, :1024]])
+        self._tap("dec_encode", bufs[0][:, :, :1024])
+        cur = 0
+        x = None
+        for i, blk in enumerate(W["decode"]):
+            if blk["up"]:
+                x = self._resblk1d_group([bufs[cur]], [sbuf[i]], [blk])[0]              # [1,2F,512]
+            else:
+                self._resblk1d_group([bufs[cur]], [sbuf[i]], [blk], outs=[bufs[1 - cur][:, :, :1024]], sos=[sbuf[i + 1][:, :1024]])
+                cur = 1 - cur
+        self._tap("dec_out", x)
+        if par:
+            ops.join(dev, side_src)
+        else:
+            source_branch()
+        # ---- generator: per stage one polyphase transposed conv + six grouped launches (3 dilations x (c1, c2)) of nk problems each
+        x_add, in_scale = (), 1.0
+        for i, (u, kk) in enumerate(zip(rates, ks)):
+            last = i == len(rates) - 1
+            xsrc = xsrcs[i]
+            L = x.shape[1]
+            lout = (L - 1) * u + kk - 2 * ((kk - u) // 2)
+            cout = W["ups"][i].cout
+            sy = self._stats(cout)
+            pre = Pre(act=ACT["lrelu"], p0=0.1)
+            if last:                                                   # "ReflectionPad1d((1,0))" is a zero pad on the left
+                y = torch.empty(1, lout + 1, cout, device=dev, dtype=torch.float32)
+                ops.copy2d(xsrc[0, :1], y[0, :1])
+                ops.channel_stats(y[:, :1], sy)                        # row 0 never passes through the conv's epilogue
+                ops.conv_fused(ops.FusedProblem(x, W["ups"][i], stride=u, pad_left=(kk - u) // 2, pre=pre, transpose=True, res=xsrc[:, 1:],
+                                                out=y[:, 1:], x_add=x_add, in_scale=in_scale, stats_out=sy))
+            else:
+                y = ops.conv_fused(ops.FusedProblem(x, W["ups"][i], stride=u, pad_left=(kk - u) // 2, pre=pre, transpose=True, res=xsrc,
+                                                    x_add=x_add, in_scale=in_scale, stats_out=sy))[0]
+            blks = [W["resblocks"][i * nk + j] for j in range(nk)]
+            outs = self._resblock1_group([y] * nk, [sy] * nk, blks)
+            x, x_add, in_scale = outs[0], tuple(outs[1:]), 1.0 / nk    # the average of the nk branches is folded into the consumer's load
+            if self.tap is not None:
+                self._tap(f"gen_stage{i}", sum(outs) / nk)
+        xpost = ops.conv_fused(ops.FusedProblem(x, W["conv_post"], pad_left=3, pre=Pre(act=ACT["lrelu"], p0=0.01), x_add=x_add,
+                                                in_scale=in_scale))[0][:, :, :W["n_post"]]
+        self._tap("xpost", xpost)
+        return ops.kokoro_istft_head(xpost)[0]
+
     # ------------------------------------------------------------------ forward
     # The utterance has exactly one data-dependent size: F = sum(pred_dur).  Everything in front of it (`_text_side`: ALBERT, text
     # encoder, duration encoder, duration head, alignment indices) depends on T only; everything behind it (`_acoustic_side`: F0 / N
@@ -394,6 +582,8 @@ class Model:
     @torch.no_grad()
     def _acoustic_side(self, st, F: int, noise=None, f0n_override=None):
         """State of `_text_side` + the frame count -> waveform [600 F] samples."""
+        if ops.FUSED[0] and ops.TC_MODE[0] != "off":
+            return self._acoustic_side_fused(st, F, noise, f0n_override)
         W, cfg, dev = self._w, self.config, self.device
         self._bind(st)
         hd = cfg.hidden_dim
