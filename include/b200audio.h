@@ -133,11 +133,14 @@ int32_t b2a_adain_coeffs(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, 
  * transposed mode; stats_slots = ceil(Mrows/128)*4*max(1, up_stride)) -- so AdaIN-conv chains skip the statistics pass over HBM. */
 int32_t b2a_adain_coeffs_from_partials(const double* partials, int32_t nslots, int32_t B, int32_t L, int32_t C, const float* gb,
                                        float eps, float* scale, float* shift, void* stream);
-/* (sum, sumsq) over L of every channel of x [B, L, C], ADDED to n_dst (1..4) float64 accumulators laid out [B][.][2]; dst[i] points at
- * the first channel's pair, dst_bs[i] doubles separate batches.  This is the statistics format b2a_conv1d_fused consumes (pre_mode 2)
+/* (sum, sumsq) over L of every channel of x [B, L, C], ADDED to n_dst (1..4) binned accumulators laid out [B][.][2][4] int64; dst[i] points
+ * at the first channel's bins, dst_bs[i] int64 elements separate batches.  This is the statistics format b2a_conv1d_fused consumes (pre_mode 2)
  * and produces (stats_out); the stand-alone kernel covers tensors no fused conv produced (LSTM outputs, concatenated side channels). */
-int32_t b2a_channel_stats(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, double* const* dst,
+int32_t b2a_channel_stats(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int64_t* const* dst,
                           const int64_t* dst_bs, int32_t n_dst, void* stream);
+/* AdaIN (scale, shift) [B, C] from binned statistics [B, C, 2, 4] (for consumers outside the fused conv: depthwise layers). */
+int32_t b2a_coeffs_from_stats(const int64_t* stats, int32_t B, int32_t L, int32_t C, const float* gb, float eps, float* scale, float* shift,
+                              void* stream);
 /* y[r,:] = LN(x[r,:] + res[r,:]) * w + b, or (1+ada[c])*LN + ada[C+c] when ada != NULL
  * (nn.LayerNorm, modules.py:71-90 AdaLayerNorm). rms != 0 -> RMSNorm (no mean, talker.py:267). */
 int32_t b2a_layernorm(const float* x, int64_t x_ld, const float* res, int64_t res_ld, float* y, int64_t y_ld,
@@ -217,22 +220,25 @@ int32_t b2a_kokoro_istft_head(const float* x, int64_t x_bs, int64_t x_ld, int32_
  * parallel resblocks of a generator stage).  x: fp32 [B, L, Cin] (16-byte aligned, row stride % 4 == 0); optional x1 / x2 (same
  * strides) are added to x first (the resblock average of the previous stage), then * in_scale.  Weights as for b2a_conv1d_tc:
  * 16-bit [taps][N][cin_pad] (+ optional lo plane).  y: fp32 [B, Lout, C].  pre_mode 0: no affine; 1: x*scale[b,c]+shift[b,c];
- * 2: scale/shift derived in-kernel from pre_stats [B, Cin, 2] = (sum, sumsq) over L (biased variance, eps) and gamma|beta rows
- * pre_gb [B, 2 Cin] (NULL: plain InstanceNorm).  stats_out [B, C, 2] float64 is ADDED to (zero it before the launch).
+ * 2: scale/shift derived in-kernel from pre_stats [B, Cin, 2, 4] = (sum, sumsq) over L (biased variance, eps) and gamma|beta rows
+ * pre_gb [B, 2 Cin] (NULL: plain InstanceNorm).  stats_out [B, C, 2, 4] is ADDED to (zero it before the launch).  A statistic is four
+ * int64 bins counting multiples of 2^(-100 + 40 k): integer atomics make the accumulation order-independent, so results are
+ * bit-reproducible across runs and between eager launches and graph replays (csrc/common.cuh: repro_add / repro_value).
  * ws: zero-initialised scratch (>= 16 MiB recommended) for split-K partial tiles; NULL disables K splitting. */
 #define B2A_CONVF_MAX_PROBLEMS 4
 typedef struct {
   const float* x; const float* x1; const float* x2; int64_t x_bs, x_ld; float in_scale;
   int32_t B, L, Cin;
-  int32_t pre_mode; const float* pre_scale; const float* pre_shift; const double* pre_stats; const float* pre_gb; int64_t pre_gb_bs; float pre_eps;
+  int32_t pre_mode; const float* pre_scale; const float* pre_shift; const int64_t* pre_stats; const float* pre_gb; int64_t pre_gb_bs; float pre_eps;
   int32_t pre_act; float pre_p0; const float* pre_a; const float* pre_b;
   const void* w_hi; const void* w_lo; int32_t cin_pad, taps, N; int32_t shifts[32];
   int32_t Lout; const float* bias; int32_t post_act; float post_p0; const float* cscale; int64_t cscale_bs;
   const float* res; int64_t res_bs, res_ld; int32_t res_div; float out_scale; int32_t accumulate;
   float* y; int64_t y_bs, y_ld;
   int32_t up_stride, up_crop;
-  double* stats_out;
+  int64_t* stats_out;
 } b2a_convf_t;
+int32_t b2a_conv1d_fused_debug(void* stamps /* device uint64 [grid][16] or NULL: phase time stamps of the next launches */);
 int32_t b2a_conv1d_fused(const b2a_convf_t* problems, int32_t n_problems, int32_t planes, int32_t f16, void* ws, int64_t ws_bytes, void* stream);
 
 /* out[i] ~ N(0,1), i < n: Philox4x32-10 keyed by `seed`, counter `offset + i/4`, Box-Muller.  The production replacement for
@@ -246,12 +252,15 @@ int32_t b2a_randn_dev(float* out, int64_t n, uint64_t* state, void* stream);
  * One launch = SuppressBlank + SuppressTokens + ApplyTimestampRules + GreedyDecoder.update(temperature 0) for every row:
  * next_out[b] = argmax of the filtered logits (eot once a row has ended), sum_logprobs[b] += its log-probability while the row
  * is live, *not_done += 1 per row whose next token is not eot.  tokens [B, >= cur_len] is the device-resident history
- * (no per-step tolist()); suppress_mask / blank_mask are additive 0/-inf vectors [V] (NULL = none); max_initial_ts < 0 = off. */
+ * (no per-step tolist()); suppress_mask / blank_mask are additive 0/-inf vectors [V] (NULL = none); max_initial_ts < 0 = off.
+ * temperature > 0 (the fallback temperatures of whisper.py:957-995): the next token is a categorical draw from softmax(filtered / temperature)
+ * -- inverse CDF in index order driven by u[b] in [0,1) -- and the log-probability bookkeeping uses the un-tempered logits, as
+ * GreedyDecoder.update does (decoding.py:307-325). */
 int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_bs, const int64_t* tokens, int64_t tokens_bs,
                                 int32_t B, int32_t cur_len, int32_t sample_begin, int32_t V, const float* suppress_mask,
                                 const float* blank_mask, int32_t eot, int32_t no_timestamps, int32_t timestamp_begin,
                                 int32_t max_initial_ts, int32_t without_timestamps, int64_t* next_out,
-                                float* sum_logprobs, int32_t* not_done, void* stream);
+                                float* sum_logprobs, int32_t* not_done, float temperature, const float* u, void* stream);
 
 /* Fused LM sampler (tts/models/qwen3_tts/qwen3_tts.py:805-860 over lm/sample_utils.py:131-239,279): additive suppress mask ->
  * sign-aware repetition penalty on the `seen` set -> temperature (<= 0: argmax) -> top-k -> top-p -> min-p -> categorical draw

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "b2a_conv1d_tc": (i32, [c_f, c_f, i32, i32, i32, i32, c_f, c_f, i32, C.POINTER(i32), i32, i32, c_f, i32, f32, c_f, i64, c_f, i64, i64, i32, f32, i32,
                             c_f, i64, i64, i32, i32, c_f, i32, C.c_void_p]),
     "b2a_conv1d_tc_debug": (i32, [c_f]),
+    "b2a_conv1d_fused_debug": (i32, [c_f]),
     "b2a_conv1d_fused": (i32, [C.POINTER(ConvFParams), i32, i32, i32, c_f, i64, C.c_void_p]),
     "b2a_copy2d": (i32, [c_f, i64, c_f, i64, i64, i32, C.c_void_p]),
     "b2a_gather_rows": (i32, [c_f, i64, c_f, c_f, i64, i64, i32, i64, c_f, i64, i64, C.c_void_p]),
@@ -79,6 +80,7 @@ PROTOTYPES = {
     "b2a_adain_coeffs": (i32, [c_f, i64, i64, i32, i32, i32, c_f, f32, c_f, c_f, c_f, C.c_void_p]),
     "b2a_adain_coeffs_from_partials": (i32, [c_f, i32, i32, i32, i32, c_f, f32, c_f, c_f, C.c_void_p]),
     "b2a_channel_stats": (i32, [c_f, i64, i64, i32, i32, i32, C.POINTER(C.c_void_p), C.POINTER(i64), i32, C.c_void_p]),
+    "b2a_coeffs_from_stats": (i32, [c_f, i32, i32, i32, c_f, f32, c_f, c_f, C.c_void_p]),
     "b2a_layernorm": (i32, [c_f, i64, c_f, i64, c_f, i64, i64, i32, c_f, c_f, c_f, f32, i32, i32, f32, C.c_void_p]),
     "b2a_attention": (i32, [C.POINTER(AttnParams), C.c_void_p]),
     "b2a_attention_tc_ws_bytes": (i64, [i32, i32, i32, i32]),
@@ -93,7 +95,7 @@ PROTOTYPES = {
     "b2a_kokoro_istft_head": (i32, [c_f, i64, i64, i32, i32, c_f, C.c_void_p]),
     "b2a_randn": (i32, [c_f, i64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "b2a_randn_dev": (i32, [c_f, i64, c_f, C.c_void_p]),
-    "b2a_whisper_greedy_step": (i32, [c_f, i64, c_f, i64, i32, i32, i32, i32, c_f, c_f, i32, i32, i32, i32, i32, c_f, c_f, c_f, C.c_void_p]),
+    "b2a_whisper_greedy_step": (i32, [c_f, i64, c_f, i64, i32, i32, i32, i32, c_f, c_f, i32, i32, i32, i32, i32, c_f, c_f, c_f, f32, c_f, C.c_void_p]),
     "b2a_sample_token": (i32, [c_f, i64, i32, i32, c_f, c_f, i64, i32, f32, f32, i32, f32, f32, c_f, c_f, i64, c_f, c_f, i32, C.c_void_p]),
     "b2a_gemv_bf16": (i32, [c_f, i64, i32, i32, c_f, i64, i32, c_f, c_f, f32, i32, c_f, i64, c_f, i64, c_f, i64, C.c_void_p]),
     "b2a_qknorm_rope_cache": (i32, [c_f, i64, i64, i32, i32, i32, i32, i32, c_f, c_f, f32, c_f, c_f, i32, i32, i32, f32, c_f, i64, i64,

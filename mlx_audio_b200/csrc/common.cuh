@@ -57,6 +57,41 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- reproducible (order-independent) accumulation of statistics --------------------------------------------------------------
+// InstanceNorm (sum, sumsq) accumulators are added to by many CTAs in whatever order they finish.  Floating-point atomics would make
+// the result depend on that order (graph replay != eager launch, run != run); so an accumulator is B2A_NBIN int64 bins, bin k counting
+// multiples of 2^(B2A_BIN0 + 40 k).  An fp32 addend (24 significant bits) is split EXACTLY over the two bins it straddles and added with
+// integer atomics -- associative, hence bit-reproducible -- and 23 bits of headroom per bin allow ~8 M addends.  Range 2^-100 .. 2^83;
+// smaller parts are dropped, non-finite addends are ignored.
+#define B2A_NBIN 4
+#define B2A_BIN0 (-100)
+#define B2A_BIN_BITS 40
+__device__ __forceinline__ void repro_add(long long* bins, float v) {
+  if (v == 0.f || !isfinite(v)) return;
+  int e;
+  frexpf(v, &e);                                       // |v| in [2^(e-1), 2^e)
+  int k = (e - 1 - B2A_BIN0) / B2A_BIN_BITS;
+  k = (e - 1) < B2A_BIN0 ? 0 : (k > B2A_NBIN - 1 ? B2A_NBIN - 1 : k);
+  const double d = ldexp((double)v, -(B2A_BIN0 + B2A_BIN_BITS * k));
+  const long long hi = (long long)d;                   // truncation; |d| < 2^63 inside the supported range
+  atomicAdd(reinterpret_cast<unsigned long long*>(bins + k), (unsigned long long)hi);
+  if (k > 0) {
+    const long long lo = (long long)rint((d - (double)hi) * 1099511627776.0);     // exact: the addend's LSB is >= one unit of bin k-1
+    if (lo) atomicAdd(reinterpret_cast<unsigned long long*>(bins + k - 1), (unsigned long long)lo);
+  }
+}
+__device__ __forceinline__ void repro_add_d(long long* bins, double v) {   // float64 addend as two fp32 pieces (48 significant bits)
+  const float h = (float)v;
+  repro_add(bins, h);
+  repro_add(bins, (float)(v - (double)h));
+}
+__device__ __forceinline__ double repro_value(const long long* bins) {
+  double t = 0.0;
+#pragma unroll
+  for (int k = B2A_NBIN - 1; k >= 0; k--) t += (double)bins[k] * ldexp(1.0, B2A_BIN0 + B2A_BIN_BITS * k);
+  return t;
+}
+
 // ---- programmatic dependent launch (PDL): a kernel launched with the attribute may start while its predecessor drains; it must
 // not touch the predecessor's outputs (or write anything) before pdl_wait().  Everything independent of the predecessor --
 // weight loads, L2 prefetches, address math -- goes before it.  Inside a CUDA graph the edges become programmatic dependencies.

@@ -30,10 +30,10 @@ __global__ void adain_partial_kernel(const float* __restrict__ x, int64_t x_bs, 
   }
 }
 
-// (sum, sumsq) of every channel ADDED to up to four float64 accumulators [B][.][2] (each pointer already offset to its first channel,
-// `dst_bs` doubles between batches): the statistics format the fused conv's epilogue produces and its prologue consumes.
-__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int L, int C, double* d0, double* d1,
-                                     double* d2, double* d3, int64_t bs0, int64_t bs1, int64_t bs2, int64_t bs3) {
+// (sum, sumsq) of every channel ADDED to up to four binned accumulators [B][.][2][B2A_NBIN] (each pointer already offset to its first
+// channel, `bs` int64 elements between batches): the statistics format the fused conv's epilogue produces and its prologue consumes.
+__global__ void channel_stats_kernel(const float* __restrict__ x, int64_t x_bs, int64_t x_ld, int L, int C, long long* d0, long long* d1,
+                                     long long* d2, long long* d3, int64_t bs0, int64_t bs1, int64_t bs2, int64_t bs3) {
   __shared__ double s1[8][33], s2[8][33];
   const int c = blockIdx.x * 32 + threadIdx.x, chunk = blockIdx.y, b = blockIdx.z;
   const int r0 = chunk * ROWS_PER_CHUNK, r1 = min(L, r0 + ROWS_PER_CHUNK);
@@ -48,11 +48,28 @@ __global__ void channel_stats_kernel(const float* __restrict__ x, int64_t x_bs, 
     double t1 = 0, t2 = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
-    if (d0) { atomicAdd(d0 + (int64_t)b * bs0 + 2 * c, t1); atomicAdd(d0 + (int64_t)b * bs0 + 2 * c + 1, t2); }
-    if (d1) { atomicAdd(d1 + (int64_t)b * bs1 + 2 * c, t1); atomicAdd(d1 + (int64_t)b * bs1 + 2 * c + 1, t2); }
-    if (d2) { atomicAdd(d2 + (int64_t)b * bs2 + 2 * c, t1); atomicAdd(d2 + (int64_t)b * bs2 + 2 * c + 1, t2); }
-    if (d3) { atomicAdd(d3 + (int64_t)b * bs3 + 2 * c, t1); atomicAdd(d3 + (int64_t)b * bs3 + 2 * c + 1, t2); }
+    long long* ds[4] = {d0, d1, d2, d3};
+    const int64_t bss[4] = {bs0, bs1, bs2, bs3};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      if (ds[i]) { long long* w = ds[i] + (int64_t)b * bss[i] + (int64_t)c * 2 * B2A_NBIN; repro_add_d(w, t1); repro_add_d(w + B2A_NBIN, t2); }
   }
+}
+
+__global__ void coeffs_from_stats_kernel(const long long* __restrict__ st, int L, int C, const float* __restrict__ gb, float eps,
+                                         float* __restrict__ scale, float* __restrict__ shift, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i % C;
+  const long long* w = st + (int64_t)i * 2 * B2A_NBIN;
+  double mean = repro_value(w) / L, var = repro_value(w + B2A_NBIN) / L - mean * mean;
+  if (var < 0) var = 0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  double g = 1.0, be = 0.0;
+  if (gb) { g = 1.0 + (double)gb[(int64_t)b * 2 * C + c]; be = (double)gb[(int64_t)b * 2 * C + C + c]; }
+  const double sc = g * rstd;
+  scale[i] = (float)sc;
+  shift[i] = (float)(be - sc * mean);
 }
 
 // one warp per (b, c): lanes stride the chunk partials (a serial walk over ~200 chunks per thread cost 20 us per call)
@@ -130,14 +147,22 @@ extern "C" int32_t b2a_adain_coeffs_from_partials(const double* partials, int32_
   return B2A_OK;
 }
 
-extern "C" int32_t b2a_channel_stats(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, double* const* dst,
+extern "C" int32_t b2a_channel_stats(const float* x, int64_t x_bs, int64_t x_ld, int32_t B, int32_t L, int32_t C, int64_t* const* dst,
                                      const int64_t* dst_bs, int32_t n_dst, void* stream) {
   B2A_CHECK_ARG(x && dst && dst_bs && B > 0 && L > 0 && C > 0 && n_dst >= 1 && n_dst <= 4, "bad pointers/shape (1..4 destinations)");
-  double* d[4] = {nullptr, nullptr, nullptr, nullptr};
+  long long* d[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t bs[4] = {0, 0, 0, 0};
-  for (int i = 0; i < n_dst; i++) { B2A_CHECK_ARG(dst[i], "null destination"); d[i] = dst[i]; bs[i] = dst_bs[i]; }
+  for (int i = 0; i < n_dst; i++) { B2A_CHECK_ARG(dst[i], "null destination"); d[i] = (long long*)dst[i]; bs[i] = dst_bs[i]; }
   dim3 grid(cdiv(C, 32), cdiv(L, ROWS_PER_CHUNK), B), block(32, 8);
   channel_stats_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, x_bs, x_ld, L, C, d[0], d[1], d[2], d[3], bs[0], bs[1], bs[2], bs[3]);
+  B2A_CHECK_LAUNCH();
+  return B2A_OK;
+}
+
+extern "C" int32_t b2a_coeffs_from_stats(const int64_t* stats, int32_t B, int32_t L, int32_t C, const float* gb, float eps, float* scale,
+                                         float* shift, void* stream) {
+  B2A_CHECK_ARG(stats && scale && shift && B > 0 && L > 0 && C > 0, "bad pointers/shape");
+  coeffs_from_stats_kernel<<<cdiv((int64_t)B * C, 256), 256, 0, (cudaStream_t)stream>>>((const long long*)stats, L, C, gb, eps, scale, shift, B);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
 }

@@ -15,6 +15,8 @@ struct GreedyParams {
   int64_t* next_out;                            // [B]
   float* sum_logprobs;                          // [B] in/out
   int* not_done;                                // [1] incremented when a row's next token is not eot
+  float temperature; const float* u;            // temperature > 0: categorical draw from softmax(filtered / temperature) by inverse CDF in
+                                                // index order, driven by u[b] in [0,1) (decoding.py:295-316)
 };
 
 __device__ __forceinline__ float block_max(float v, float* sh) {
@@ -106,9 +108,45 @@ __global__ void whisper_greedy_kernel(const GreedyParams p) {
     }
   se = block_sum(se, sh);
   __syncthreads();
+  __shared__ double s_scan[512];
+  __shared__ int s_pick, s_lastlive;
+  float picked_logit = gmax;
+  if (p.temperature > 0.f && gmax > NEG) {
+    // categorical draw: every thread owns a contiguous index range; float64 range sums, block scan, then the owning thread walks its range
+    auto fin = [&](int v) -> float { return (rule_masked(v) || (text_masked && v < tb)) ? NEG : pre(v); };
+    const int per = (p.V + nt - 1) / nt, lo = tid * per, hi = min(p.V, lo + per);
+    const double inv_t = 1.0 / (double)p.temperature;
+    double mine = 0.0; int lastlive = -1;
+    for (int v = lo; v < hi; v++) { const float x = fin(v); if (x > NEG) { mine += exp((double)(x - gmax) * inv_t); lastlive = v; } }
+    if (tid == 0) { s_pick = -1; s_lastlive = -1; }
+    s_scan[tid] = mine;
+    __syncthreads();
+    for (int o = 1; o < nt; o <<= 1) {                     // Hillis-Steele inclusive scan over the nt range sums
+      const double t = tid >= o ? s_scan[tid - o] : 0.0;
+      __syncthreads();
+      s_scan[tid] += t;
+      __syncthreads();
+    }
+    const double z = s_scan[nt - 1], target = (double)p.u[b] * z;
+    atomicMax(&s_lastlive, lastlive);
+    const double incl = s_scan[tid], excl = incl - mine;
+    if (incl > target && !(excl > target)) {               // the first range whose inclusive sum passes the target
+      double run = excl; int pick = lastlive;
+      for (int v = lo; v < hi; v++) { const float x = fin(v); if (x > NEG) { run += exp((double)(x - gmax) * inv_t); if (run > target) { pick = v; break; } } }
+      s_pick = pick;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int pick = s_pick >= 0 ? s_pick : max(s_lastlive, 0);
+      s_best = (unsigned long long)(unsigned)pick;
+      s_scan[0] = (double)fin(pick);
+    }
+    __syncthreads();
+    picked_logit = (float)s_scan[0];
+  }
   if (tid == 0) {
     int nxt = (int)s_best;
-    const float cur_lp = gmax > NEG ? -logf(se) : NAN;             // logit[nxt] - logsumexp = gmax - (gmax + log se)
+    const float cur_lp = gmax > NEG ? (picked_logit - gmax) - logf(se) : NAN;   // logit[nxt] - logsumexp (argmax: logit[nxt] = gmax)
     const bool was_eot = tk[p.cur_len - 1] == p.eot;
     if (!was_eot) p.sum_logprobs[b] += cur_lp;
     if (was_eot) nxt = p.eot;
@@ -123,11 +161,12 @@ extern "C" int32_t b2a_whisper_greedy_step(const float* logits, int64_t logits_b
                                            int32_t B, int32_t cur_len, int32_t sample_begin, int32_t V, const float* suppress_mask,
                                            const float* blank_mask, int32_t eot, int32_t no_timestamps, int32_t timestamp_begin,
                                            int32_t max_initial_ts, int32_t without_timestamps, int64_t* next_out,
-                                           float* sum_logprobs, int32_t* not_done, void* stream) {
+                                           float* sum_logprobs, int32_t* not_done, float temperature, const float* u, void* stream) {
   B2A_CHECK_ARG(logits && tokens && next_out && sum_logprobs && not_done, "null pointer");
+  B2A_CHECK_ARG(temperature >= 0.f && (temperature == 0.f || u), "temperature > 0 needs one uniform per row");
   B2A_CHECK_ARG(B > 0 && V > 0 && cur_len >= sample_begin && cur_len >= 1 && timestamp_begin > 0 && timestamp_begin <= V, "bad shape");
   GreedyParams p{logits, logits_bs, tokens, tokens_bs, cur_len, sample_begin, V, suppress_mask, blank_mask, eot, no_timestamps,
-                 timestamp_begin, max_initial_ts, without_timestamps, next_out, sum_logprobs, not_done};
+                 timestamp_begin, max_initial_ts, without_timestamps, next_out, sum_logprobs, not_done, temperature, u};
   whisper_greedy_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(p);
   B2A_CHECK_LAUNCH();
   return B2A_OK;

@@ -349,8 +349,8 @@ _FUSED_WS = {}
 
 @dataclass
 class PreStats:
-    """Input transform whose scale/shift the kernel derives itself: InstanceNorm over L from ``stats`` [B, C, 2] float64 (sum, sumsq) as
-    accumulated by the producing layer, folded with AdaIN's (1 + gamma) / beta rows ``gb`` [B, 2C] (None: plain InstanceNorm); then
+    """Input transform whose scale/shift the kernel derives itself: InstanceNorm over L from ``stats`` [B, C, 2, 4] int64 (binned sum, sumsq:
+    ``new_stats`` / ``stats_value``) as accumulated by the producing layer, folded with AdaIN's (1 + gamma) / beta rows ``gb`` [B, 2C] (None: plain InstanceNorm); then
     the activation."""
     stats: torch.Tensor
     gb: Optional[torch.Tensor] = None
@@ -361,9 +361,22 @@ class PreStats:
     b: Optional[torch.Tensor] = None
 
 
+STAT_BINS, STAT_BIN0, STAT_BIN_BITS = 4, -100, 40          # csrc/common.cuh: B2A_NBIN, B2A_BIN0, B2A_BIN_BITS
+
+
 def new_stats(B: int, Cc: int, device) -> torch.Tensor:
-    """Zeroed (sum, sumsq) accumulator for ``FusedProblem(..., stats_out=)``."""
-    return torch.zeros(B, Cc, 2, device=device, dtype=torch.float64)
+    """Zeroed (sum, sumsq) accumulator for ``FusedProblem(..., stats_out=)``: [B, C, 2, 4] int64 bins (multiples of 2^(-100 + 40 k)); integer
+    atomics make the accumulation independent of the order in which CTAs arrive -> bit-reproducible statistics."""
+    return torch.zeros(B, Cc, 2, STAT_BINS, device=device, dtype=torch.int64)
+
+
+def stats_value(stats: torch.Tensor) -> torch.Tensor:
+    """Binned accumulator [..., 4] int64 -> float64 values [...] (what repro_value computes on the device)."""
+    w = torch.tensor([2.0 ** (STAT_BIN0 + STAT_BIN_BITS * k) for k in range(STAT_BINS)], dtype=torch.float64, device=stats.device)
+    t = torch.zeros(stats.shape[:-1], dtype=torch.float64, device=stats.device)
+    for k in range(STAT_BINS - 1, -1, -1):
+        t = t + stats[..., k].double() * w[k]
+    return t
 
 
 def fused_eligible(x, cw: "ConvW", stride: int = 1, dilation: int = 1, transpose: bool = False, pad_mode: int = 0) -> bool:
@@ -407,8 +420,8 @@ class FusedProblem:
             keep.append(xa)
         p.B, p.L, p.Cin = B, L, cin
         if isinstance(pre, PreStats):
-            if pre.stats.dtype != torch.float64 or tuple(pre.stats.shape) != (B, cin, 2) or not pre.stats.is_contiguous():
-                raise ValueError("conv_fused: stats must be a contiguous float64 [B, Cin, 2] tensor")
+            if pre.stats.dtype != torch.int64 or tuple(pre.stats.shape) != (B, cin, 2, STAT_BINS) or not pre.stats.is_contiguous():
+                raise ValueError("conv_fused: stats must be a contiguous int64 [B, Cin, 2, 4] tensor (ops.new_stats)")
             p.pre_mode, p.pre_stats, p.pre_eps = 2, pre.stats.data_ptr(), float(pre.eps)
             if pre.gb is not None:
                 if pre.gb.shape[-1] != 2 * cin or pre.gb.stride(-1) != 1:
@@ -443,8 +456,8 @@ class FusedProblem:
         p.res_div, p.out_scale, p.accumulate = res_div, float(out_scale), int(accumulate)
         p.y, p.y_bs, p.y_ld = out.data_ptr(), out.stride(0), out.stride(1)
         if stats_out is not None:
-            if stats_out.dtype != torch.float64 or tuple(stats_out.shape) != (B, cw.cout, 2) or not stats_out.is_contiguous():
-                raise ValueError("conv_fused: stats_out must be a contiguous float64 [B, Cout, 2] tensor")
+            if stats_out.dtype != torch.int64 or tuple(stats_out.shape) != (B, cw.cout, 2, STAT_BINS) or not stats_out.is_contiguous():
+                raise ValueError("conv_fused: stats_out must be a contiguous int64 [B, Cout, 2, 4] tensor (ops.new_stats)")
             p.stats_out = stats_out.data_ptr()
             keep.append(stats_out)
         self.p, self.out, self.keep, self.f16 = p, out, keep, cw.f16
@@ -504,14 +517,16 @@ def gather_rows(src: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor
 
 def whisper_greedy_step(logits: torch.Tensor, tokens: torch.Tensor, cur_len: int, sample_begin: int, *, suppress_mask, blank_mask,
                         eot: int, no_timestamps: int, timestamp_begin: int, max_initial_ts: int, without_timestamps: bool,
-                        sum_logprobs: torch.Tensor, not_done: torch.Tensor) -> torch.Tensor:
-    """Fused logit filters + greedy update (decoding.py:307-325,349-442).  logits [B,V] fp32, tokens [B, >=cur_len] int64."""
+                        sum_logprobs: torch.Tensor, not_done: torch.Tensor, temperature: float = 0.0, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused logit filters + greedy / categorical update (decoding.py:295-325,349-442).  logits [B,V] fp32, tokens [B, >=cur_len] int64;
+    ``temperature`` > 0 draws from softmax(filtered / temperature) with one uniform per row ``u`` [B]."""
     B, V = logits.shape
     assert logits.stride(1) == 1 and tokens.dtype == torch.int64 and tokens.stride(1) == 1
+    assert u is None or (u.dtype == torch.float32 and u.is_contiguous() and u.numel() == B)
     nxt = torch.empty(B, device=logits.device, dtype=torch.int64)
     _call("sampler", _lib.lib().b2a_whisper_greedy_step, 1, logits.data_ptr(), logits.stride(0), tokens.data_ptr(), tokens.stride(0), B, cur_len,
           sample_begin, V, _p(suppress_mask), _p(blank_mask), eot, no_timestamps, timestamp_begin, max_initial_ts, int(without_timestamps),
-          nxt.data_ptr(), sum_logprobs.data_ptr(), not_done.data_ptr(), _stream())
+          nxt.data_ptr(), sum_logprobs.data_ptr(), not_done.data_ptr(), float(temperature), _p(u), _stream())
     return nxt
 
 
@@ -559,27 +574,26 @@ def adain_coeffs(x: torch.Tensor, gb: Optional[torch.Tensor], eps=1e-5, partials
 
 
 def channel_stats(x: torch.Tensor, dsts) -> None:
-    """Add (sum, sumsq) over L of x [B, L, C] to each float64 accumulator in ``dsts`` (views [B, C, 2] of possibly wider [B, C', 2] buffers)."""
+    """Add (sum, sumsq) over L of x [B, L, C] to each binned accumulator in ``dsts`` (views [B, C, 2, 4] of possibly wider [B, C', 2, 4] buffers)."""
     _chk3(x, "channel_stats x")
     B, L, Cc = x.shape
     if isinstance(dsts, torch.Tensor):
         dsts = [dsts]
     n = len(dsts)
     for d in dsts:
-        assert d.dtype == torch.float64 and tuple(d.shape) == (B, Cc, 2) and d.stride(2) == 1 and d.stride(1) == 2
+        assert d.dtype == torch.int64 and tuple(d.shape) == (B, Cc, 2, STAT_BINS) and d.stride(3) == 1 and d.stride(2) == STAT_BINS and d.stride(1) == 2 * STAT_BINS
     ptrs = (C.c_void_p * n)(*[d.data_ptr() for d in dsts])
     bss = (C.c_int64 * n)(*[d.stride(0) for d in dsts])
     _call("adain_stats", _lib.lib().b2a_channel_stats, 1, x.data_ptr(), x.stride(0), x.stride(1), B, L, Cc, ptrs, bss, n, _stream())
 
 
 def coeffs_from_stats(stats: torch.Tensor, L: int, gb: Optional[torch.Tensor], eps=1e-5):
-    """(sum, sumsq) [B, C, 2] float64 -> AdaIN (scale, shift) [B, C] float32 for consumers outside the fused conv (depthwise layers)."""
-    B, Cc, _ = stats.shape
-    assert stats.dtype == torch.float64 and stats.is_contiguous()
+    """Binned (sum, sumsq) [B, C, 2, 4] -> AdaIN (scale, shift) [B, C] float32 for consumers outside the fused conv (depthwise layers)."""
+    B, Cc = stats.shape[:2]
+    assert stats.dtype == torch.int64 and stats.is_contiguous() and tuple(stats.shape[2:]) == (2, STAT_BINS)
     scale = torch.empty(B, Cc, device=stats.device, dtype=torch.float32)
     shift = torch.empty(B, Cc, device=stats.device, dtype=torch.float32)
-    _call("adain_stats", _lib.lib().b2a_adain_coeffs_from_partials, 1, stats.data_ptr(), 1, B, L, Cc, _p(gb), eps, scale.data_ptr(),
-          shift.data_ptr(), _stream())
+    _call("adain_stats", _lib.lib().b2a_coeffs_from_stats, 1, stats.data_ptr(), B, L, Cc, _p(gb), eps, scale.data_ptr(), shift.data_ptr(), _stream())
     return scale, shift
 
 

@@ -232,8 +232,12 @@ class TextDecoder:
                 "cross": [ops.linear(xa, blk["ckv"]) for blk in W["blocks"]]}
 
     @torch.no_grad()
-    def __call__(self, tokens: torch.Tensor, cache: dict, last_only: bool = True, also_first: bool = False):
-        """tokens int64 [B,n] -> logits [B,V] of the last position (and of position 0 when ``also_first``)."""
+    def __call__(self, tokens: torch.Tensor, cache: dict, last_only: bool = True, also_first: bool = False, also_at: Optional[int] = None):
+        """tokens int64 [B,n] -> logits [B,V] of the last position (and of position ``also_at`` -- 0 when ``also_first`` -- for the
+        no-speech probability at the sot token, decoding.py:610-612)."""
+        if also_first and also_at is None:
+            also_at = 0
+        also_first = also_at is not None
         W, dims = self._w, self.dims
         d, nh = dims.n_text_state, dims.n_text_head
         B, n = tokens.shape
@@ -256,7 +260,7 @@ class TextDecoder:
         cache["offset"] = off + n
         if not last_only:                                                     # every position: Model.logits / __call__ (whisper.py:623-631)
             return ops.linear(ops.layernorm(x.contiguous(), *W["ln"]), W["logits"])
-        rows = x[:, -1:] if not also_first else torch.cat([x[:, -1:], x[:, :1]], 1)
+        rows = x[:, -1:] if not also_first else torch.cat([x[:, -1:], x[:, also_at:also_at + 1]], 1)
         hl = ops.layernorm(rows.contiguous(), *W["ln"])
         logits = ops.linear(hl, W["logits"])                                  # tied embedding (whisper.py:498)
         return (logits[:, 0], logits[:, 1]) if also_first else logits[:, 0]
@@ -331,18 +335,28 @@ class Model:
 
     @torch.no_grad()
     def greedy_decode(self, audio_features: torch.Tensor, spec: Optional[TokenizerSpec] = None, sample_len: Optional[int] = None,
-                      max_initial_timestamp_index: Optional[int] = 50, without_timestamps: bool = False):
-        """DecodingTask.run with GreedyDecoder(temperature=0) (decoding.py:588-722) on encoder features [B,1500,d]:
-        the whole step -- logit filters, argmax, log-prob bookkeeping -- is one fused kernel on the device-resident token
-        history; the only host read per step is the `completed` flag (the reference also syncs on it, decoding.py:625).
-        Returns (tokens list per row incl. the sot sequence, sum_logprobs [B], no_speech_probs [B])."""
+                      max_initial_timestamp_index: Optional[int] = 50, without_timestamps: bool = False, *, temperature: float = 0.0,
+                      uniforms=None, prompt=None):
+        """DecodingTask.run's sampling loop with GreedyDecoder (decoding.py:295-325, 588-632) on encoder features [B,1500,d]: the whole step
+        -- logit filters, argmax or categorical draw, log-prob bookkeeping -- is one fused kernel on the device-resident token history; the
+        only host read per step is the `completed` flag (the reference also syncs on it, decoding.py:625).
+
+        ``temperature`` > 0 samples from softmax(filtered / temperature); ``uniforms`` [steps, B] in [0,1) drives the draws (inverse CDF in
+        index order; parity tests inject it, otherwise drawn on the device).  ``prompt`` = previous-context token ids: the initial tokens
+        become [sot_prev] + prompt[-(n_text_ctx // 2 - 1):] + sot sequence (decoding.py:538-549).
+        Returns (tokens list per row incl. the initial tokens, sum_logprobs [B], no_speech_probs [B]); ``self.last_sample_begin`` holds the
+        index of the first sampled position."""
         spec = spec or TokenizerSpec()
         dims, dev = self.dims, self.device
         B = audio_features.shape[0]
         sample_len = sample_len or dims.n_text_ctx // 2
         V = dims.n_vocab
         init = list(spec.sot_sequence) + ([spec.no_timestamps] if without_timestamps else [])   # decoding.py:463-465
+        if prompt:
+            init = [spec.sot_prev] + [int(t) for t in prompt][-(dims.n_text_ctx // 2 - 1):] + init
         sb = len(init)
+        sot_index = init.index(spec.sot)
+        self.last_sample_begin = sb
         tokens = torch.zeros(B, dims.n_text_ctx + 2, dtype=torch.int64, device=dev)
         tokens[:, :sb] = torch.tensor(init, device=dev)
         neg = float("-inf")
@@ -357,9 +371,17 @@ class Model:
         cache = self.decoder.new_cache(audio_features)
         cur = sb
         no_speech = None
+        temperature = float(temperature)
+        if temperature > 0:
+            if uniforms is None:
+                if getattr(self, "_rng", None) is None:
+                    self._rng = torch.Generator(device=dev)
+                    self._rng.seed()
+                uniforms = torch.rand(sample_len, B, device=dev, generator=self._rng)
+            uniforms = torch.as_tensor(uniforms, dtype=torch.float32).to(dev).reshape(-1, B).contiguous()
         for i in range(sample_len):
             if i == 0:
-                logits, first = self.decoder(tokens[:, :cur], cache, also_first=True)
+                logits, first = self.decoder(tokens[:, :cur], cache, also_at=sot_index)
                 no_speech = torch.softmax(first, dim=-1)[:, spec.no_speech]            # one-off, not on the per-step path
             else:
                 logits = self.decoder(tokens[:, cur - 1:cur], cache)
@@ -367,7 +389,8 @@ class Model:
             nxt = ops.whisper_greedy_step(logits, tokens, cur, sb, suppress_mask=sup if suppress else None, blank_mask=blank,
                                           eot=spec.eot, no_timestamps=spec.no_timestamps, timestamp_begin=spec.timestamp_begin,
                                           max_initial_ts=-1 if max_initial_timestamp_index is None else max_initial_timestamp_index,
-                                          without_timestamps=without_timestamps, sum_logprobs=sum_lp, not_done=not_done)
+                                          without_timestamps=without_timestamps, sum_logprobs=sum_lp, not_done=not_done,
+                                          temperature=temperature, u=uniforms[i] if temperature > 0 else None)
             tokens[:, cur] = nxt
             cur += 1
             if int(not_done.item()) == 0 or cur > dims.n_text_ctx:
@@ -375,10 +398,11 @@ class Model:
         return tokens[:, :cur].cpu().tolist(), sum_lp, no_speech
 
     def decode(self, mel: torch.Tensor, spec: Optional[TokenizerSpec] = None, sample_len: Optional[int] = None,
-               without_timestamps: bool = False, max_initial_timestamp: Optional[float] = 1.0, tokenizer=None, language: str = "en"):
-        """decoding.decode / DecodingTask.run at temperature 0 (decoding.py:634-765): ``mel`` [.., 3000, n_mels] log-mel windows, or encoder
-        features [.., n_audio_ctx, n_audio_state] which skip the encoder (decoding.py:557-565) -> DecodingResult per window (one object for
-        a single window).  Text needs ``tokenizer`` (anything with ``decode(list[int]) -> str``)."""
+               without_timestamps: bool = False, max_initial_timestamp: Optional[float] = 1.0, tokenizer=None, language: str = "en", *,
+               temperature: float = 0.0, uniforms=None, prompt=None):
+        """decoding.decode / DecodingTask.run (decoding.py:634-765): ``mel`` [.., 3000, n_mels] log-mel windows, or encoder features
+        [.., n_audio_ctx, n_audio_state] which skip the encoder (decoding.py:557-565) -> DecodingResult per window (one object for a single
+        window).  Text needs ``tokenizer`` (anything with ``decode(list[int]) -> str``)."""
         from .audio import CHUNK_LENGTH
         spec = spec or TokenizerSpec()
         single = mel.dim() == 2
@@ -386,9 +410,10 @@ class Model:
         dims = self.dims
         feats = mel if tuple(mel.shape[-2:]) == (dims.n_audio_ctx, dims.n_audio_state) else self.encoder(mel)
         index = round(max_initial_timestamp / (CHUNK_LENGTH / dims.n_audio_ctx)) if max_initial_timestamp else None
-        tokens, sum_lp, no_speech = self.greedy_decode(feats, spec, sample_len, index, without_timestamps)
-        sample_begin = len(spec.sot_sequence) + (1 if without_timestamps else 0)
-        res = results_from_greedy(tokens, sum_lp.cpu().tolist(), no_speech.cpu().tolist(), feats, spec, sample_begin, language, 0.0, tokenizer)
+        tokens, sum_lp, no_speech = self.greedy_decode(feats, spec, sample_len, index, without_timestamps, temperature=temperature,
+                                                       uniforms=uniforms, prompt=prompt)
+        res = results_from_greedy(tokens, sum_lp.cpu().tolist(), no_speech.cpu().tolist(), feats, spec, self.last_sample_begin, language,
+                                  float(temperature), tokenizer)
         return res[0] if single else res
 
     def embed_audio(self, mel):
@@ -417,6 +442,27 @@ class Model:
         mel = log_mel_spectrogram(audio, self.dims.n_mels, padding=N_SAMPLES, device=self.device)
         return self.encoder(mel[:, :N_FRAMES])
 
+    def detect_language(self, mel: torch.Tensor, spec: Optional[TokenizerSpec] = None):
+        """decoding.detect_language (decoding.py:20-77): one decoder pass on [sot], softmax over the language tokens only.
+        Returns (language token ids [n], list of {code: probability})."""
+        from .transcribe import LANGUAGE_CODES
+        spec = spec or TokenizerSpec()
+        single = mel.dim() == 2
+        mel = mel[None] if single else mel
+        feats = mel if tuple(mel.shape[-2:]) == (self.dims.n_audio_ctx, self.dims.n_audio_state) else self.encoder(mel)
+        n = feats.shape[0]
+        x = torch.full((n, 1), spec.sot, dtype=torch.int64, device=self.device)
+        logits = self.logits(x, feats)[:, 0]
+        ids = list(range(spec.sot + 1, spec.sot + 1 + self.num_languages))
+        sub = logits[:, ids].double()
+        probs = torch.softmax(sub, dim=-1).cpu()
+        toks = torch.tensor(ids)[sub.argmax(dim=-1).cpu()]
+        dicts = [{c: float(probs[i, j]) for j, c in enumerate(LANGUAGE_CODES[: len(ids)])} for i in range(n)]
+        return (toks[0], dicts[0]) if single else (toks, dicts)
+
     def generate(self, audio, **kw):
-        raise NotImplementedError("text in/out needs the tokenizer files (not available offline); the numeric path is "
-                                  "encode_audio(audio) -> greedy_decode(features, TokenizerSpec(...))")
+        """Model.generate (whisper.py:799-1318): 30-second windows with the seek rule, temperature fallback, previous-text conditioning.
+        See ``transcribe.transcribe`` for the arguments; ``tokenizer`` (``decode(list[int]) -> str``, ``encode``) is needed for text, token
+        ids are always returned in the segments."""
+        from .transcribe import transcribe
+        return transcribe(self, audio, **kw)

@@ -324,10 +324,11 @@ class Model:
             t = self._stats_pool.pop(0)
             assert t.shape[1] == C
             return t
+        n = 2 * ops.STAT_BINS * C
         off = self._arena_off
-        self._arena_off += 2 * C
+        self._arena_off += n
         assert self._arena_off <= self._arena.numel()
-        return self._arena[off:off + 2 * C].view(1, C, 2)
+        return self._arena[off:off + n].view(1, C, 2, ops.STAT_BINS)
 
     def _resblk1d_group(self, xs, sxs, blks, outs=None, sos=None):
         """AdainResBlk1d (istftnet.py:853-933) for n parallel blocks of identical structure: xs[i] [1,L,Cin] with statistics sxs[i]
@@ -344,7 +345,9 @@ class Model:
             rs = []
             for x, sx, b in zip(xs, sxs, blks):
                 sc, sh = ops.coeffs_from_stats(sx, L, self._gb(b["name"] + ".norm1"))
-                rs.append(ops.conv1d(x, b["pool"], stride=2, pad_left=1, lout=2 * L, pre=Pre(sc, sh, lrelu, 0.2), transpose=True))
+                cpad = -(-x.shape[2] // 4) * 4                         # row stride padded to 16 bytes: the fused conv loads float4 chunks
+                r = torch.empty(1, 2 * L, cpad, device=x.device, dtype=torch.float32)[:, :, :x.shape[2]]
+                rs.append(ops.conv1d(x, b["pool"], stride=2, pad_left=1, lout=2 * L, pre=Pre(sc, sh, lrelu, 0.2), transpose=True, out=r))
             first = [ops.FusedProblem(r, b["conv1"], pad_left=1, stats_out=st) for r, b, st in zip(rs, blks, s1)]
         else:
             first = [ops.FusedProblem(x, b["conv1"], pad_left=1, pre=ops.PreStats(sx, self._gb(b["name"] + ".norm1"), 1e-5, lrelu, 0.2), stats_out=st)
@@ -386,7 +389,7 @@ class Model:
         par = self.concurrent
         X, t_en = st["X"], st["t_en"]
         idx = st["idx"][:F]
-        self._arena = torch.zeros(1 << 17, device=dev, dtype=torch.float64)          # every (sum, sumsq) accumulator of the utterance: one memset
+        self._arena = torch.zeros(1 << 19, device=dev, dtype=torch.int64)            # every (sum, sumsq) accumulator of the utterance: one memset
         self._arena_off = 0
         # ---- F0 / N prediction: the two heads run as 2-problem groups
         en = ops.gather_rows(X, idx)                                   # [F,640]  == d^T @ aln

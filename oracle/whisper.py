@@ -209,3 +209,167 @@ def greedy_decode(P, xa, spec, sample_len=16, suppress=(), dims=WHISPER_SMALL, m
         if completed or len(tokens[0]) > dims["n_text_ctx"]:
             break
     return tokens, sum_lp, no_speech
+
+
+# ------------------------------------------------------------------------------------------------ sampling + long-form loop
+def sample_update(tokens, logits, sum_logprobs, eot, temperature, u):
+    """GreedyDecoder.update at temperature > 0 (decoding.py:295-325): categorical draw from softmax(logits / temperature) -- defined, as
+    everywhere in this repository, as the inverse CDF in index order driven by one uniform ``u[b]`` per row (MLX's PRNG is not
+    reproducible) -- while the log-probability bookkeeping uses the un-tempered logits."""
+    B = logits.shape[0]
+    nxt = []
+    u = torch.as_tensor(u, dtype=torch.float64).reshape(-1).expand(B) if torch.as_tensor(u).numel() == 1 else torch.as_tensor(u, dtype=torch.float64).reshape(-1)
+    for b in range(B):
+        row = logits[b].double() / float(temperature)
+        w = torch.exp(row - row.max())
+        cum = torch.cumsum(w, 0)
+        live = torch.nonzero(w > 0).reshape(-1)
+        hit = live[cum[live] > float(u[b]) * float(cum[-1])]
+        nxt.append(int(hit[0]) if hit.numel() else int(live[-1]))
+    nxt = torch.tensor(nxt)
+    logprobs = logits - torch.logsumexp(logits, dim=-1, keepdim=True)
+    cur = logprobs[torch.arange(B), nxt]
+    last = torch.tensor([t[-1] for t in tokens])
+    sum_logprobs = sum_logprobs + cur * (last != eot)
+    nxt = torch.where(last == eot, torch.full_like(nxt, eot), nxt)
+    tokens = [t + [int(n)] for t, n in zip(tokens, nxt)]
+    return tokens, bool((nxt == eot).all()), sum_logprobs
+
+
+def compression_ratio(text):
+    """decoding.py:19-21."""
+    import zlib
+    b = text.encode("utf-8")
+    return len(b) / len(zlib.compress(b))
+
+
+def decode_window(P, xa, spec, dims, *, temperature=0.0, uniforms=None, prompt=(), sample_len=None, suppress=(), max_initial_timestamp_index=50,
+                  without_timestamps=False, tokenizer=None):
+    """DecodingTask.run for one window (decoding.py:445-722): initial tokens incl. the previous-text prompt, the sampling loop, the
+    result fields.  xa [1, n_audio_ctx, d] encoder features.  Returns a dict with the DecodingResult fields."""
+    n_ctx = dims["n_text_ctx"]
+    sample_len = sample_len or n_ctx // 2
+    sup = get_suppress_tokens(spec, suppress) if suppress else ()
+    init = list(spec.sot_sequence) + ([spec.no_timestamps] if without_timestamps else [])
+    if prompt:
+        init = [spec.sot_prev] + list(prompt)[-(n_ctx // 2 - 1):] + init
+    sb, sot_index = len(init), init.index(spec.sot)
+    tokens = [list(init)]
+    sum_lp = torch.zeros(1, dtype=xa.dtype)
+    cache, no_speech = None, None
+    for i in range(sample_len):
+        inp = torch.tensor(tokens if i == 0 else [[t[-1]] for t in tokens])
+        pre, cache = decoder_forward(P, inp, xa, cache, dims)
+        if i == 0:
+            no_speech = torch.softmax(pre[:, sot_index], dim=-1)[:, spec.no_speech]
+        logits = apply_filters(pre[:, -1], tokens, spec, sb, sup, max_initial_timestamp_index, without_timestamps)
+        if temperature == 0:
+            tokens, completed, sum_lp = greedy_update(tokens, logits, sum_lp, spec.eot)
+        else:
+            tokens, completed, sum_lp = sample_update(tokens, logits, sum_lp, spec.eot, temperature, uniforms[i])
+        if completed or len(tokens[0]) > n_ctx:
+            break
+    row = tokens[0] + [spec.eot]                              # GreedyDecoder.finalize
+    cut = row[sb:]
+    cut = cut[: cut.index(spec.eot)]
+    text = tokenizer.decode(cut).strip() if tokenizer is not None else ""
+    return {"tokens": cut, "text": text, "avg_logprob": float(sum_lp[0]) / (len(cut) + 1), "no_speech_prob": float(no_speech[0]),
+            "temperature": float(temperature), "compression_ratio": compression_ratio(text)}
+
+
+def transcribe(P, mel, spec, dims, tokenizer, *, temperatures=(0.0, 0.2, 0.4, 0.6, 0.8, 1.0), compression_ratio_threshold=2.4,
+               logprob_threshold=-1.0, no_speech_threshold=0.6, condition_on_previous_text=True, initial_prompt_tokens=(), return_timestamps=True,
+               clip_timestamps=(0.0,), suppress=(), sample_len=None, uniforms=None, n_frames=3000, hop=160, sr=16000):
+    """Model.generate's window loop (whisper.py:934-1318) on a log-mel spectrogram ``mel`` [frames + n_frames, n_mels] (already padded by
+    one window of zeros, _prepare_audio :748-775).  ``uniforms(k)`` returns the per-step uniforms of the k-th decode call made at a
+    temperature > 0.  Returns (text, segments)."""
+    content_frames = mel.shape[0] - n_frames
+    fps = sr // hop
+    points = [round(ts * fps) for ts in clip_timestamps] or [0]
+    if len(points) % 2 == 1:
+        points.append(content_frames)
+    else:
+        points[-1] = min(content_frames, points[-1])
+    clips = list(zip(points[::2], points[1::2]))
+    input_stride = n_frames // dims["n_audio_ctx"]
+    time_precision = input_stride * hop / sr
+    tb, eot = spec.timestamp_begin, spec.eot
+    precision = 30.0 / dims["n_audio_ctx"]
+    mi = round(1.0 / precision)
+    all_tokens = list(initial_prompt_tokens)
+    all_segments, prompt_reset_since, hot_calls = [], 0, [0]
+
+    def with_fallback(segment):
+        xa = encoder(P, segment[None], dims)
+        res = None
+        for t in temperatures:
+            u = None
+            if t > 0:
+                u = uniforms(hot_calls[0])
+                hot_calls[0] += 1
+            res = decode_window(P, xa, spec, dims, temperature=t, uniforms=u, prompt=all_tokens[prompt_reset_since:], sample_len=sample_len,
+                                suppress=suppress, max_initial_timestamp_index=mi, without_timestamps=not return_timestamps, tokenizer=tokenizer)
+            bad = False
+            if compression_ratio_threshold is not None and res["compression_ratio"] > compression_ratio_threshold:
+                bad = True
+            if logprob_threshold is not None and res["avg_logprob"] < logprob_threshold:
+                bad = True
+            if no_speech_threshold is not None and res["no_speech_prob"] > no_speech_threshold:
+                bad = False
+            if not bad:
+                break
+        return res
+
+    seek = clips[0][0]
+    for _, clip_end in clips:
+        while seek < clip_end:
+            time_offset = float(seek * hop / sr)
+            segment_size = min(n_frames, content_frames - seek, clip_end - seek)
+            seg = mel[seek:seek + segment_size]
+            if seg.shape[0] < n_frames:
+                seg = torch.cat([seg, torch.zeros(n_frames - seg.shape[0], seg.shape[1], dtype=seg.dtype)], 0)
+            res = with_fallback(seg)
+            tokens = res["tokens"]
+            if no_speech_threshold is not None:
+                skip = res["no_speech_prob"] > no_speech_threshold
+                if logprob_threshold is not None and res["avg_logprob"] > logprob_threshold:
+                    skip = False
+                if skip:
+                    seek += segment_size
+                    continue
+            cur = []
+
+            def mk(start, end, toks):
+                return {"seek": seek, "start": float(start), "end": float(end), "text": tokenizer.decode([t for t in toks if t < eot]), "tokens": list(toks),
+                        "temperature": res["temperature"], "avg_logprob": res["avg_logprob"], "compression_ratio": res["compression_ratio"],
+                        "no_speech_prob": res["no_speech_prob"]}
+            is_ts = [t >= tb for t in tokens]
+            single = is_ts[-2:] == [False, True]
+            cons = [i + 1 for i in range(len(tokens) - 1) if is_ts[i] and is_ts[i + 1]]
+            if cons:
+                if single:
+                    cons.append(len(tokens))
+                last = 0
+                for c in cons:
+                    sl = tokens[last:c]
+                    cur.append(mk(time_offset + (sl[0] - tb) * time_precision, time_offset + (sl[-1] - tb) * time_precision, sl))
+                    last = c
+                if single:
+                    seek += segment_size
+                else:
+                    seek += (tokens[last - 1] - tb) * input_stride
+            else:
+                duration = segment_size * hop / sr
+                stamps = [t for t in tokens if t >= tb]
+                if stamps and stamps[-1] != tb:
+                    duration = (stamps[-1] - tb) * time_precision
+                cur.append(mk(time_offset, time_offset + duration, tokens))
+                seek += segment_size
+            for sg in cur:
+                if sg["start"] == sg["end"] or sg["text"].strip() == "":
+                    sg["text"], sg["tokens"], sg["words"] = "", [], []
+            all_segments.extend({"id": i, **sg} for i, sg in enumerate(cur, start=len(all_segments)))
+            all_tokens.extend(t for sg in cur for t in sg["tokens"])
+            if not condition_on_previous_text or res["temperature"] > 0.5:
+                prompt_reset_since = len(all_tokens)
+    return tokenizer.decode(all_tokens[len(initial_prompt_tokens):]), all_segments

@@ -98,6 +98,89 @@ def decode_cases(model, mel, out):
     out["dec_max_initial_timestamp_index"] = round(1.0 / (30.0 / DIMS["n_audio_ctx"]))
 
 
+GEN_DIMS = dict(n_mels=80, n_audio_ctx=1500, n_audio_state=32, n_audio_head=2, n_audio_layer=1, n_vocab=300, n_text_ctx=48, n_text_state=32,
+                n_text_head=2, n_text_layer=2)
+
+
+def generate_case(out):
+    """Model.generate (whisper.py:799-1318) on 75 s of synthetic audio: three 30-second windows through decode_with_fallback (temperatures
+    0 / 0.4 / 0.8 / 1.0), the no-speech skip, segment cutting at consecutive timestamp tokens, the seek rule, previous-text conditioning with
+    the prompt reset after a hot window.  The model is tiny (one encoder layer of width 32) but keeps n_audio_ctx = 1500 so that the
+    reference's hard-coded 3000-frame windows fit.  Categorical draws: D.categorical is replaced by the inverse-CDF draw of the stand-in fed
+    from a table U[k, step], k = index of the decode call among those made at a temperature > 0 (one table row per call, so the
+    reference's extra discarded step after completion does not shift later draws)."""
+    from mlx_audio.stt.models.whisper import decoding as D
+    sys.modules["mlx_audio.stt.utils"].merge_hotwords = lambda prompt, hotwords: prompt
+    model = W.Model(W.ModelDimensions(**GEN_DIMS), dtype=mx.float32)
+    names = [(n, v.shape) for n, v in shim.flat_parameters(model)]
+    for n, sh in names:
+        shim.set_parameter(model, n, synth_params.value(n, sh))
+    model.get_tokenizer = lambda language=None, task=None: StubTokenizer()
+    gain = 3.0
+    w0 = np.array(model.decoder.token_embedding.weight)
+
+    def set_gain(gv):
+        w = w0.copy()
+        w[:StubTokenizer.eot] *= gv
+        model.decoder.token_embedding.weight = mx.array(w)
+    set_gain(gain)
+    rng = np.random.default_rng(33)
+    sr = 16000
+    t = np.arange(75 * sr) / sr
+    audio = (0.2 * np.sin(2 * np.pi * 220 * t) * (1 + np.sin(2 * np.pi * 0.3 * t)) + 0.05 * rng.standard_normal(t.shape)).astype(np.float32)
+    audio[int(31 * sr):int(58 * sr)] *= 1e-3                      # a quiet stretch
+    U = rng.random((64, GEN_DIMS["n_text_ctx"] // 2 + 4))
+    state = {"call": -1, "step": 0, "temps": []}
+    run0 = D.DecodingTask.run
+
+    def run(self, mel):
+        state["temps"].append(float(self.options.temperature))
+        if self.options.temperature > 0:
+            state["call"] += 1
+            state["step"] = 0
+        return run0(self, mel)
+
+    def cat(logits, temp):
+        u = U[state["call"], state["step"]]
+        state["step"] += 1
+        mx.random.queue.append(("categorical", np.full(np.asarray(logits).shape[:-1], u)))
+        return mx.random.categorical(logits / temp)
+    D.DecodingTask.run, D.categorical = run, cat
+    mx.random.strict = True
+    cases = {"default": dict(temperature=(0.0, 0.4, 0.8, 1.0), logprob_threshold=-4.6, compression_ratio_threshold=2.4, no_speech_threshold=0.6),
+             "nocond": dict(temperature=(0.0, 0.5), logprob_threshold=-4.3, condition_on_previous_text=False, no_speech_threshold=None,
+                            initial_prompt_tokens=[11, 12, 13]),
+             "nots": dict(temperature=0.0, return_timestamps=False, clip_timestamps="5,40"),
+             # weaker text rows: the timestamp-mass rule fires after some text, which closes timestamp PAIRS -> segments cut at the pairs and
+             # seek moves to the last closed timestamp instead of by a whole window
+             "pairs": dict(temperature=(0.0, 0.6), logprob_threshold=-5.2, no_speech_threshold=None, clip_timestamps="0,9",
+                           text_gain=float(os.environ.get("GEN_GAIN2", "1.6")))}
+    try:
+        for tag, kw in cases.items():
+            state.update(call=-1, step=0, temps=[])
+            kw = dict(kw)
+            set_gain(kw.pop("text_gain", gain))
+            prompt_tokens = kw.pop("initial_prompt_tokens", None)
+            if prompt_tokens is not None:                           # the stub tokenizer's encode() ignores the text and returns these ids
+                StubTokenizer.encode = lambda self, text, _p=prompt_tokens: list(_p)
+                kw["initial_prompt"] = "x"
+            res = model.generate(mx.array(audio), language="en", verbose=None, suppress_tokens=[3, 4, 5, 250], sample_len=14, fp16=False, **kw)
+            segs = [{k: (v if not isinstance(v, (np.floating, np.integer)) else v.item()) for k, v in sg.items()} for sg in res.segments]
+            for sg in segs:
+                sg["tokens"] = [int(t_) for t_ in sg["tokens"]]
+                sg.pop("words", None)
+            out[f"gen_{tag}"] = json.dumps(dict(text=res.text, language=res.language, segments=segs, temps=state["temps"]))
+            print(tag, "decode calls", len(state["temps"]), "hot", sum(t_ > 0 for t_ in state["temps"]), "segments", len(segs),
+                  [(s_["seek"], round(s_["start"], 2), round(s_["end"], 2), len(s_["tokens"])) for s_ in segs[:8]])
+    finally:
+        D.DecodingTask.run = run0
+        mx.random.strict = False
+    out["gen_audio_head"], out["gen_U"], out["gen_text_gain"] = audio[:16], U, gain      # the audio is rebuilt from the formula above (seed 33)
+    out["gen_pairs_gain"] = float(os.environ.get("GEN_GAIN2", "1.6"))
+    out["gen_params"] = synth_params.manifest(names)
+    out["gen_suppress"] = np.asarray([3, 4, 5, 250])
+
+
 def main():
     model = W.Model(W.ModelDimensions(**DIMS), dtype=mx.float32)
     names = [(n, v.shape) for n, v in shim.flat_parameters(model)]
@@ -117,8 +200,9 @@ def main():
                cross_qk_last=np.asarray(cross_qk[-1]), step_tokens=step_tokens, step_logits=np.stack(step_logits, 1)[:, :, 0],
                sinusoids=np.asarray(W.sinusoids(60, 64)))
     decode_cases(model, mel, out)
+    generate_case(out)
     np.savez_compressed(os.path.join(os.environ.get("GOLDEN_OUT", HERE), "whisper_golden.npz"), **out)
-    print({k: getattr(v, "shape", None) for k, v in out.items()})
+    print(len(out), "entries")
 
 
 def live(n):

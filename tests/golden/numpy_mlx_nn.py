@@ -67,6 +67,9 @@ class array(np.ndarray):
     def rsqrt(self):
         return 1.0 / np.sqrt(self)
 
+    def log10(self):
+        return np.log10(self).view(array)
+
     def abs(self):
         return np.abs(self)
 

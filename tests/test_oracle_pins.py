@@ -557,3 +557,78 @@ def test_oracle_qwen3_voice_cloning_matches_the_reference_model_code():
         assert gen.shape[0] == m["token_count"] and wav.shape == g[f"icl_{t}_audio"].shape and np.abs(wav - g[f"icl_{t}_audio"]).max() < 2e-7
         lengths.append(wav.shape[0])
     assert lengths == [17829, 7680]
+
+
+WHISPER_GEN_DIMS = dict(n_mels=80, n_audio_ctx=1500, n_audio_state=32, n_audio_head=2, n_audio_layer=1, n_vocab=300, n_text_ctx=48, n_text_state=32,
+                        n_text_head=2, n_text_layer=2)
+
+
+def whisper_generate_audio():
+    """The 75-second synthetic recording of tests/golden/make_whisper_golden.py:generate_case, rebuilt from its formula (seed 33), and the
+    uniform table that follows it in the same random stream."""
+    rng = np.random.default_rng(33)
+    sr = 16000
+    t = np.arange(75 * sr) / sr
+    audio = (0.2 * np.sin(2 * np.pi * 220 * t) * (1 + np.sin(2 * np.pi * 0.3 * t)) + 0.05 * rng.standard_normal(t.shape)).astype(np.float32)
+    audio[int(31 * sr):int(58 * sr)] *= 1e-3
+    U = rng.random((64, WHISPER_GEN_DIMS["n_text_ctx"] // 2 + 4))
+    return audio, U
+
+
+class WhisperStubTokenizer:
+    """decode / encode of the stub tokenizer the reference ran with (make_whisper_golden.py:StubTokenizer)."""
+
+    def __init__(self, prompt=None):
+        self.prompt = prompt
+
+    def decode(self, tokens):
+        return " ".join(str(int(t)) for t in tokens)
+
+    def encode(self, text):
+        return list(self.prompt) if self.prompt is not None else []
+
+
+WHISPER_GEN_CASES = {
+    "default": dict(temperatures=(0.0, 0.4, 0.8, 1.0), logprob_threshold=-4.6, compression_ratio_threshold=2.4, no_speech_threshold=0.6),
+    "nocond": dict(temperatures=(0.0, 0.5), logprob_threshold=-4.3, condition_on_previous_text=False, no_speech_threshold=None, initial_prompt_tokens=(11, 12, 13)),
+    "nots": dict(temperatures=(0.0,), return_timestamps=False, clip_timestamps=(5.0, 40.0)),
+    "pairs": dict(temperatures=(0.0, 0.6), logprob_threshold=-5.2, no_speech_threshold=None, clip_timestamps=(0.0, 9.0)),
+}
+
+
+def _segments_match(got, want, tol=1e-6):
+    assert len(got) == len(want), (len(got), len(want))
+    for a, b in zip(got, want):
+        assert a["tokens"] == b["tokens"] and a["seek"] == b["seek"] and a["text"] == b["text"] and a["id"] == b["id"], (a, b)
+        for k in ("start", "end", "temperature", "avg_logprob", "compression_ratio", "no_speech_prob"):
+            assert abs(a[k] - b[k]) <= tol * max(1.0, abs(b[k])), (k, a[k], b[k])
+
+
+def test_oracle_whisper_generate_matches_the_reference_generate():
+    """whisper_golden.npz gen_* = the reference's Model.generate (whisper.py:799-1318) EXECUTED through the NumPy stand-in on 75 s of
+    synthetic audio with a stub tokenizer: log-mel front end, three to a dozen 30-second windows, decode_with_fallback over several
+    temperatures (categorical draws injected per decode call), the no-speech skip, segment cutting at timestamp pairs, the seek rule, prompt
+    conditioning and its reset after a hot window, clip_timestamps, return_timestamps=False.  The oracle's transcribe() must return the same
+    segments: token ids, seek positions and temperatures identical, times and scores to 1e-6 (the reference builds its window and filterbank in float32)."""
+    import json
+    from oracle import dsp as OD
+    from oracle import whisper as OW
+    g, _ = _golden("whisper_golden.npz")
+    import synth_params
+    P0 = {k: torch.as_tensor(v) for k, v in synth_params.from_manifest(g["gen_params"]).items()}
+    audio, U = whisper_generate_audio()
+    assert np.array_equal(audio[:16], g["gen_audio_head"]) and np.array_equal(U, g["gen_U"])
+    mel = torch.as_tensor(OD.whisper_log_mel(audio, 80, padding=480000))
+    spec = OW.TokenizerSpec(eot=200, sot=201, no_timestamps=208, timestamp_begin=209, no_speech=207, blank_ids=(7,), language=202, task=203,
+                            transcribe=203, translate=204, sot_lm=205, sot_prev=206)
+    for tag, kw in WHISPER_GEN_CASES.items():
+        want = json.loads(str(g[f"gen_{tag}"]))
+        kw = dict(kw)
+        P = dict(P0)
+        P["decoder.token_embedding.weight"] = P0["decoder.token_embedding.weight"].clone()
+        P["decoder.token_embedding.weight"][:200] *= float(g["gen_pairs_gain"] if tag == "pairs" else g["gen_text_gain"])
+        prompt = kw.pop("initial_prompt_tokens", ())
+        text, segs = OW.transcribe(P, mel, spec, WHISPER_GEN_DIMS, WhisperStubTokenizer(), initial_prompt_tokens=prompt,
+                                   suppress=g["gen_suppress"].tolist(), sample_len=14, uniforms=lambda k: U[k], **kw)
+        _segments_match(segs, want["segments"])
+        assert text == want["text"], tag

@@ -18,6 +18,16 @@ def rel_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+@pytest.fixture(params=["gemm_tc", "fused"])
+def path(request):
+    """Every dense-conv case runs through both tensor-core kernels: round 1's prologue pass + conv_tc_persist_kernel (csrc/gemm_tc.cu) and
+    the fused kernel that converts the activations on the fly (csrc/conv_fused.cu)."""
+    from mlx_audio_b200 import ops
+    old, ops.FUSED[0] = ops.FUSED[0], request.param == "fused"
+    yield request.param
+    ops.FUSED[0] = old
+
+
 CASES = [
     # B, L, Cin, Cout, K, dil, pad
     (1, 300, 128, 128, 7, 3, 9),
@@ -37,7 +47,7 @@ CASES = [
 
 @pytest.mark.parametrize("mode,tol", [("x2", 2e-5), ("x1", 4e-3)])
 @pytest.mark.parametrize("case", CASES)
-def test_conv1d_tc(case, mode, tol):
+def test_conv1d_tc(case, mode, tol, path):
     from mlx_audio_b200 import ops
     B, L, Cin, Cout, K, dil, pad = case
     dev = torch.device("cuda:0")
@@ -70,7 +80,7 @@ def test_conv1d_tc(case, mode, tol):
         assert rel_err(y, y_cc.double()) < 2e-5
 
 
-def test_conv1d_tc_epilogue_variants():
+def test_conv1d_tc_epilogue_variants(path):
     from mlx_audio_b200 import ops
     dev = torch.device("cuda:0")
     x = _rand(2, 200, 128, seed=1)
@@ -94,7 +104,7 @@ def test_conv1d_tc_epilogue_variants():
 
 @pytest.mark.parametrize("B,L,Cin,Cout,K,stride,pad,opad", [(1, 780, 512, 256, 20, 10, 5, 0), (1, 500, 256, 128, 12, 6, 3, 0),
                                                              (2, 300, 128, 64, 16, 8, 4, 1), (1, 257, 64, 32, 4, 2, 1, 1), (1, 100, 256, 128, 8, 4, 0, 0)])
-def test_convtr1d_tc_polyphase(B, L, Cin, Cout, K, stride, pad, opad):
+def test_convtr1d_tc_polyphase(B, L, Cin, Cout, K, stride, pad, opad, path):
     """Transposed conv on the tensor-core path (K = 2*stride, polyphase: the GEMM output is the up-sampled signal)."""
     from mlx_audio_b200 import ops
     dev = torch.device("cuda:0")
@@ -130,10 +140,11 @@ def test_epilogue_instance_norm_partials(L, Cin, Cout, K, transpose, stride):
     cw = ops.pack_conv(w, _rand(Cout, seed=3, scale=0.1), 1, dev)
     gb = _rand(2, 2 * Cout, seed=4, scale=0.3).to(dev)
     old, ops.TC_STATS[0] = ops.TC_STATS[0], True          # opt-in feature (off by default: measured slower end to end)
+    oldf, ops.FUSED[0] = ops.FUSED[0], False              # this is gemm_tc.cu's epilogue; the fused kernel's statistics: test_fused_gpu.py
     try:
         _run_stats_case(ops, dev, x, cw, gb, L, Cout, K, transpose, stride)
     finally:
-        ops.TC_STATS[0] = old
+        ops.TC_STATS[0], ops.FUSED[0] = old, oldf
 
 
 def _run_stats_case(ops, dev, x, cw, gb, L, Cout, K, transpose, stride):
