@@ -449,7 +449,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload != "kokoro":
-        from mlx_audio_b200 import bench_workloads
+        import bench_workloads
         return bench_workloads.main(args, rank, world, local_rank)
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -333,6 +333,13 @@ int32_t b2a_incr_i32(int32_t* p, int32_t v, void* stream);
  * is out of range (checked on device, reported via *err_flag_dev != 0). */
 int32_t b2a_rvq_decode(const int64_t* codes, int64_t codes_bs, int64_t codes_qs, int32_t B, int32_t nq, int64_t T,
                        const float* codebooks, int32_t bins, int32_t dim, float* out, int64_t out_ld, int32_t* err_flag_dev, void* stream);
+/* Residual-VQ ENCODE: codes[row, q] = nearest entry of codebooks[q] to the row's residual, q = 0 .. nq-1, the residual shrinking by the
+ * chosen entry after every level (mimi/modules/quantization.py:37-45, 90-101; speech_tokenizer.py:957-1058 uses the same quantizer).
+ * x [rows, dim] fp32 (row stride x_ld); codebooks [nq, bins, dim]; c2 [nq, bins] float64: mode 0 (Euclidean) |e|^2 / 2, score = c2 - x.e;
+ * mode 1 (SNAC, snac/vq.py:56-73: one level, L2-normalised rows -- codebooks must hold the NORMALISED table) |en|^2, score = |xn|^2 - 2 xn.en
+ * + c2.  Scores accumulate in float64; ties -> lowest index.  codes int64, element (row, q) at row * codes_row_stride + q * codes_level_stride. */
+int32_t b2a_rvq_encode(const float* x, int64_t x_ld, int64_t rows, int32_t dim, const float* codebooks, const double* c2, int32_t bins,
+                       int32_t nq, int32_t mode, int64_t* codes, int64_t codes_row_stride, int64_t codes_level_stride, void* stream);
 /* SNAC from_codes (snac/vq.py:111-131): z[b,t,:] = sum_l ( W_l @ E_l[codes_l[b, t / stride_l]] + bias_l ),
  * codes_l int64 [B, T/stride_l]; E_l [bins, cd]; W_l [cd][dim] (packed, K=1); out [B,T,dim]. */
 int32_t b2a_snac_from_codes(const int64_t* const* codes_host_ptrs, const int32_t* strides_host, int32_t n_levels,

@@ -76,6 +76,27 @@ class Mimi:
         hop = pcm.shape[-1] // codes.shape[-1]
         return pcm[..., (codes.shape[-1] - xs.shape[-1]) * hop:]
 
+    @property
+    def span_halo(self) -> int:
+        """Left context (code frames) that makes a span decode exact: the stack is causal; each of the transformer's layers looks back
+        ``context`` positions (at ``upsample_stride`` positions per frame), so the receptive field of the stack is num_layers * context
+        positions, plus a few frames for the causal convolutions either side of it."""
+        c = self.cfg
+        return -(-(c.num_layers * c.context) // c.upsample_stride) + 16
+
+    @torch.no_grad()
+    def decode_span(self, codes: torch.Tensor, start: int, end: int, halo=None) -> torch.Tensor:
+        """Samples of code frames [start, end) -- equal to that slice of ``decode(codes)`` -- from the frames themselves plus ``halo``
+        frames of left context (one stream sharded across GPUs).  Returns [B, 1, (end - start) * 1920]."""
+        halo = self.span_halo if halo is None else halo
+        T = codes.shape[-1]
+        if not 0 <= start < end <= T:
+            raise ValueError(f"decode_span: need 0 <= start < end <= {T}")
+        rs = max(0, start - halo)
+        pcm = self.decode(codes[:, :, rs:end])
+        hop = pcm.shape[-1] // (end - rs)
+        return pcm[..., (start - rs) * hop:]
+
     @staticmethod
     def sanitize_pytorch_weights(weights: dict) -> dict:
         """The key / layout mapping of ``Mimi.load_pytorch_weights`` (mimi.py:196-249): kyutai's PyTorch checkpoint names -> the reference's

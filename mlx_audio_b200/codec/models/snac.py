@@ -154,6 +154,28 @@ class SNAC:
         a, ia = W["out_snake"]
         return ops.conv1d(x, W["out_conv"], pad_left=3, pre=Pre(act=ACT["snake"], a=a, b=ia), post_act=ACT["tanh"])
 
+    # halo (in finest-level frames) that makes a span decode EXACT: first conv +-3, per block the transposed conv (+-1) and three residual
+    # units of kernel 7 with dilations 1 / 3 / 9 (+-39 samples at that block's rate: 39/8 + 39/64 + ... < 6 frames), last conv +-3/512.
+    SPAN_HALO = 16
+
+    @torch.no_grad()
+    def decode_span(self, codes: List[torch.Tensor], start: int, end: int, noises: Optional[List[torch.Tensor]] = None, halo: int = SPAN_HALO):
+        """Audio of the finest-level frames [start, end) of a stream, decoded from those frames plus ``halo`` frames on each side: the decoder
+        is convolutional, so this equals the corresponding slice of ``decode(codes)`` (one stream sharded across
+        GPUs; the per-channel NoiseBlock draws ``noises`` must be the same on every shard).  ``start`` / ``end`` / ``halo`` are multiples of
+        the coarsest code stride.  Returns [B, (end - start) * hop (+ the decoder's 75-sample tail when ``end`` is the stream's end), 1]."""
+        top = max(self.vq_strides)
+        T = codes[-1].shape[1] * self.vq_strides[-1]
+        if start % top or (end % top and end != T) or halo % top or not 0 <= start < end <= T:
+            raise ValueError(f"decode_span: start / end / halo must be multiples of {top} inside [0, {T}]")
+        rs, re = max(0, start - halo), min(T, end + halo)
+        part = [c[:, rs // st: -(-re // st)] for c, st in zip(codes, self.vq_strides)]
+        y = self.decode(part, noises=noises)
+        hop = math.prod(self.decoder_rates)
+        lo = (start - rs) * hop
+        hi = y.shape[1] if end == T else lo + (end - start) * hop
+        return y[:, lo:hi]
+
     def decode_stream(self, codes: List[torch.Tensor], prev_codes: Optional[List[torch.Tensor]] = None, context_frames: int = 8, noises=None):
         """snac.py:106-162, literally: the first call decodes ``codes``; later calls prepend ``max(1, context_frames // stride_l)`` frames of
         context per level and decode the combination.  Kept quirk: the reference trims the context with ``full_audio[..., n:]`` on an audio

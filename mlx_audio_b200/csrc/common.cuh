@@ -25,6 +25,17 @@ __device__ __forceinline__ float b2a_sin(float x) {
   return __sinf(r);
 }
 
+// The same without the libm fall-back for huge arguments (its Payne-Hanek slow path is ~500 instructions of code per call site, which
+// made the fused conv's converter loop instruction-cache-bound): three-constant Cody-Waite, accurate to ~1e-6 for |x| < 1e5 -- the Snake
+// argument is alpha x a normalised activation, orders of magnitude below that; beyond it the result degrades gracefully (stays in [-1, 1]).
+__device__ __forceinline__ float b2a_sin_fast(float x) {
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.28125f, x);                                   // 2 pi = 6.28125 + 1.9353071795864769e-3 (split so that k * C1 is exact)
+  r = fmaf(-k, 1.9353071693331003e-3f, r);
+  r = fmaf(-k, 1.0253331169063645e-11f, r);
+  return __sinf(r);
+}
+
 __device__ __forceinline__ float b2a_act(float v, int act, float p0, float a, float b) {
   switch (act) {
     case B2A_ACT_LRELU: return v > 0.f ? v : v * p0;

@@ -86,9 +86,13 @@ __device__ __forceinline__ float back16(__nv_bfloat16 v) { return __bfloat162flo
 __device__ __forceinline__ float back16(__half v) { return __half2float(v); }
 
 __device__ __noinline__ float act_slow(float v, int act, float p0) { return b2a_act(v, act, p0, 1.f, 1.f); }
+__device__ __noinline__ float act_slow2(float v, int act, float p0, float a, float b) { return b2a_act(v, act, p0, a, b); }
 
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// accumulate the nanoseconds a role spends inside a wait (debug runs only): slots 16.. of the CTA's row
+#define TIMED_WAIT(p, acc, stmt) do { if ((p).dbg) { const unsigned long long t0_ = gtime(); stmt; acc += gtime() - t0_; } else { stmt; } } while (0)
 __device__ __forceinline__ void stamp(const FParams& p, int slot) {
-  if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 16 + slot] = t; }
+  if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 32 + slot] = t; }
 }
 
 // One float4 (4 channels of one row) -> transformed hi / lo 16-bit quads at the swizzled position of row r, 8-byte slot c4.
@@ -104,11 +108,11 @@ __device__ __forceinline__ void convert_store(float4 v, bool valid, const float 
     float u = 0.f;
     if (valid && chok[q]) {
       u = fmaf(t[q], sc[q], sh[q]);
-      if constexpr (ACT == B2A_ACT_SNAKE) { const float s = b2a_sin(aa[q] * u); u = fmaf(bb[q], s * s, u); }
+      if constexpr (ACT == B2A_ACT_SNAKE) { const float s = b2a_sin_fast(aa[q] * u); u = fmaf(bb[q], s * s, u); }
       else if constexpr (ACT == B2A_ACT_LRELU) u = u > 0.f ? u : u * p0;
       else if constexpr (ACT == B2A_ACT_ELU) u = u > 0.f ? u : expm1f(u);
       else if constexpr (ACT == 0) { }
-      else if (act) u = b2a_act(u, act, p0, aa[q], bb[q]);
+      else if (act) u = act_slow2(u, act, p0, aa[q], bb[q]);
     }
     h[q] = cvt16<T16>(u);
     l[q] = cvt16<T16>(u - back16(h[q]));
@@ -118,31 +122,32 @@ __device__ __forceinline__ void convert_store(float4 v, bool valid, const float 
   if (lo) *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
 }
 
-// One K chunk of the A tile: rows r0, r0 + 16, ... of 4 channels; six independent 16-byte loads in flight per thread.
-template <typename T16, int ACT>
+// One K chunk of the A tile: rows r0, r0 + 16, ... of 4 channels.  ALL loads of a batch are issued before anything consumes them: a
+// consumer placed between two loads -- even a predicated-off one, e.g. the optional x1 / x2 adds -- waits on the scoreboard of the
+// load in front of it and serialises the batch into one L2 round trip per row (measured: 2-10 us per K chunk instead of < 1 us).
+// NADD = number of extra input tensors summed into x (0, 1 or 2); U = rows in flight per thread.
+template <typename T16, int ACT, int NADD, int U>
 __device__ __forceinline__ void convert_chunk(const float* __restrict__ xb, const float* __restrict__ xb1, const float* __restrict__ xb2, int64_t x_ld,
                                               int L, int lbase, int ch, int c4, int r0, int R, bool anych, const float sc[4], const float sh[4],
                                               const float aa[4], const float bb[4], const bool chok[4], int act, float p0, uint8_t* hi, uint8_t* lo) {
-  constexpr int U = 6;
   for (int r = r0; r < R; r += 16 * U) {
-    float4 v[U];
+    float4 v[U], w1[NADD > 0 ? U : 1], w2[NADD > 1 ? U : 1];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int rr = r + u * 16;
       const int l = lbase + rr;
       ok[u] = rr < R && l >= 0 && l < L && anych;
-      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ok[u]) {
-        const int64_t off = (int64_t)l * x_ld + ch;
-        v[u] = __ldg(reinterpret_cast<const float4*>(xb + off));
-        if (xb1) { const float4 w = __ldg(reinterpret_cast<const float4*>(xb1 + off)); v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w; }
-        if (xb2) { const float4 w = __ldg(reinterpret_cast<const float4*>(xb2 + off)); v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w; }
-      }
+      const int64_t off = ok[u] ? (int64_t)l * x_ld + ch : 0;     // masked rows read row 0 of the chunk (always valid memory), result discarded
+      v[u] = __ldg(reinterpret_cast<const float4*>(xb + off));
+      if constexpr (NADD > 0) w1[u] = __ldg(reinterpret_cast<const float4*>(xb1 + off));
+      if constexpr (NADD > 1) w2[u] = __ldg(reinterpret_cast<const float4*>(xb2 + off));
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int rr = r + u * 16;
+      if constexpr (NADD > 0) { v[u].x += w1[u].x; v[u].y += w1[u].y; v[u].z += w1[u].z; v[u].w += w1[u].w; }
+      if constexpr (NADD > 1) { v[u].x += w2[u].x; v[u].y += w2[u].y; v[u].z += w2[u].z; v[u].w += w2[u].w; }
       if (rr < R) convert_store<T16, ACT>(v[u], ok[u], sc, sh, aa, bb, chok, act, p0, hi, lo, rr, c4);
     }
   }
@@ -241,6 +246,7 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
     const uint32_t fmt = p.f16 ? 0u : 1u;
     const uint32_t a0 = smem_u32(smem);
     uint32_t it = 0, lt = 0, cg = 0;
+    unsigned long long w_tempty = 0, w_afull = 0, w_wfull = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
@@ -249,16 +255,16 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
       const int kc0 = t.ks * P.kper, kc1 = min(kchunks, kc0 + P.kper);
       const uint32_t buf = lt & 1, use = lt >> 1;
       const uint32_t wb = (uint32_t)P.BN * 128u;
-      mbar_wait(tempty + buf, (use & 1) ^ 1);
+      TIMED_WAIT(p, w_tempty, mbar_wait(tempty + buf, (use & 1) ^ 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.tmem_stride;
       for (int kc = kc0; kc < kc1; kc++, cg++) {
         const uint32_t ab = cg & 1;
-        mbar_wait(a_full + ab, (cg >> 1) & 1);
+        TIMED_WAIT(p, w_afull, mbar_wait(a_full + ab, (cg >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int tap = 0; tap < P.taps; tap++, it++) {
           const int s = it % p.wst, ph = (it / p.wst) & 1;
-          mbar_wait(full + s, ph);
+          TIMED_WAIT(p, w_wfull, mbar_wait(full + s, ph));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (lane == 0 && it == 0) stamp(p, 4);
           if (lane == 0) {
@@ -282,6 +288,7 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
         }
       }
     }
+    if (p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 16] = w_tempty; p.dbg[(size_t)blockIdx.x * 32 + 17] = w_afull; p.dbg[(size_t)blockIdx.x * 32 + 18] = w_wfull; }
   } else if (warp < W_EPI0) {
     // ===== converter warps: fp32 activations -> transformed 16-bit planes in the swizzled A tile =====
     pdl_wait();
@@ -291,6 +298,7 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
     const int r0 = t256 >> 4;                       // first row of this thread (stride 16)
     uint32_t cg = 0;
     int cur_key = -1;
+    unsigned long long w_aempty = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
@@ -335,16 +343,22 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
           }
         }
         const bool anych = ch < P.Cin;
-        mbar_wait(a_empty + ab, ((cg >> 1) & 1) ^ 1);
+        TIMED_WAIT(p, w_aempty, mbar_wait(a_empty + ab, ((cg >> 1) & 1) ^ 1));
         uint8_t* hi = smem + (size_t)ab * a_buf;
         uint8_t* lo = p.planes == 2 ? hi + p.a_plane : nullptr;
-#define B2A_CONVERT(T, A) convert_chunk<T, A>(xb, xb1, xb2, P.x_ld, P.L, lbase, ch, c4, r0, R, anych, sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo)
-        if (p.f16) { if (P.pre_act == 0) B2A_CONVERT(__half, 0); else B2A_CONVERT(__half, -1); }
-        else if (P.pre_act == 0) B2A_CONVERT(__nv_bfloat16, 0);
-        else if (P.pre_act == B2A_ACT_SNAKE) B2A_CONVERT(__nv_bfloat16, B2A_ACT_SNAKE);
-        else if (P.pre_act == B2A_ACT_LRELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_LRELU);
-        else if (P.pre_act == B2A_ACT_ELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_ELU);
-        else B2A_CONVERT(__nv_bfloat16, -1);
+#define B2A_CONVERT(T, A, N, UU) convert_chunk<T, A, N, UU>(xb, xb1, xb2, P.x_ld, P.L, lbase, chs, c4, r0, R, anych, sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo)
+        const int chs = anych ? ch : 0;                    // chunks wholly past Cin (never with a valid weight column) still index valid memory
+        // specialised bodies for the hot cases only (each instantiation is ~1-2 K instructions): single input x {none, Snake, LeakyReLU, ELU};
+        // summed inputs (the folded branch average) and fp16 operands with an activation take the runtime-switch body
+        if (p.f16) { if (xb1 == nullptr && P.pre_act == 0) B2A_CONVERT(__half, 0, 0, 6); else if (xb2) B2A_CONVERT(__half, -1, 2, 3);
+                     else if (xb1) B2A_CONVERT(__half, -1, 1, 4); else B2A_CONVERT(__half, -1, 0, 6); }
+        else if (xb2) B2A_CONVERT(__nv_bfloat16, -1, 2, 3);
+        else if (xb1) B2A_CONVERT(__nv_bfloat16, -1, 1, 4);
+        else if (P.pre_act == 0) B2A_CONVERT(__nv_bfloat16, 0, 0, 9);
+        else if (P.pre_act == B2A_ACT_SNAKE) B2A_CONVERT(__nv_bfloat16, B2A_ACT_SNAKE, 0, 9);
+        else if (P.pre_act == B2A_ACT_LRELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_LRELU, 0, 9);
+        else if (P.pre_act == B2A_ACT_ELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_ELU, 0, 6);
+        else B2A_CONVERT(__nv_bfloat16, -1, 0, 6);
 #undef B2A_CONVERT
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
         __syncwarp();
@@ -352,6 +366,7 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
         if (warp == W_CONV0 && lane == 0) { if (cg == 0) stamp(p, 6); stamp(p, 7); }
       }
     }
+    if (p.dbg && warp == W_CONV0 && lane == 0) p.dbg[(size_t)blockIdx.x * 32 + 19] = w_aempty;
   } else {
     // ===== epilogue warps =====
     pdl_wait();
@@ -360,6 +375,7 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
     const int et = ew * 32 + lane;                   // 0..255 inside the epilogue group
     float* stage = staging + ew * (32 * 33);
     uint32_t lt = 0;
+    unsigned long long w_tfull = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
@@ -367,22 +383,39 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
       const int l0 = t.mt * TM, n0 = t.nt * P.BN, b = t.b;
       const uint32_t buf = lt & 1, use = lt >> 1;
       const bool do_stats = P.stats_out != nullptr;
-      mbar_wait(tfull + buf, use & 1);
+      if (!P.up_s && P.ksplit == 1) {                           // pull this warp's residual / previous-output rows towards L2 while the MMAs run
+        const int prow = l0 + quarter * 32 + lane;
+        if (prow < P.Lout) {
+          if (P.res) {
+            const float* q = P.res + (int64_t)b * P.res_bs + (int64_t)(P.res_div == 2 ? (prow >> 1) : prow) * P.res_ld + n0;
+            for (int c = sub * 32; c < P.BN; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+          }
+          if (P.accumulate) {
+            const float* q = P.y + (int64_t)b * P.y_bs + (int64_t)prow * P.y_ld + n0;
+            for (int c = sub * 32; c < P.BN; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+          }
+        }
+      }
+      TIMED_WAIT(p, w_tfull, mbar_wait(tfull + buf, use & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (et == 0 && lt == 0) stamp(p, 8);
       const int mrow0 = l0 + quarter * 32;
       const uint32_t tcol = tmem_base + buf * (uint32_t)p.tmem_stride + ((uint32_t)(quarter * 32) << 16);
       bool last_split = true;
       if (P.ksplit > 1) {
-        // ---- split-K: park this CTA's partial accumulator, then only the last CTA to arrive for the tile carries on
+        // ---- split-K: park this CTA's partial accumulator (through the transpose tile: whole 128-byte row segments), then only the
+        // last CTA to arrive for the tile carries on
         const int tid = ((b * P.ntm + t.mt) * P.ntn + t.nt);
-        float* mine = P.ws + ((int64_t)tid * P.ksplit + t.ks) * (TM * P.BN) + (int64_t)(quarter * 32 + lane) * P.BN;
+        float* mine = P.ws + ((int64_t)tid * P.ksplit + t.ks) * (TM * P.BN) + (int64_t)(quarter * 32) * P.BN;
         for (int c0 = sub * 32; c0 < P.BN; c0 += 64) {
           uint32_t r[32];
           tmem_ld32(tcol + (uint32_t)c0, r);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(mine + c0 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+#pragma unroll 8
+          for (int i = 0; i < 32; i++) mine[(int64_t)i * P.BN + c0 + lane] = stage[i * 33 + lane];
+          __syncwarp();
         }
         __threadfence();
         bar_sync(2, NEPI * 32);
@@ -399,37 +432,48 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
       }
       if (last_split) {
         for (int c0 = sub * 32; c0 < P.BN; c0 += 64) {
-          uint32_t r[32];
           if (P.ksplit > 1) {
+            // fixed-order sum of the partial tiles, read row by row (lane = column: coalesced, and already the layout the stores below want)
             const int tid = ((b * P.ntm + t.mt) * P.ntn + t.nt);
-            const float* base = P.ws + (int64_t)tid * P.ksplit * (TM * P.BN) + (int64_t)(quarter * 32 + lane) * P.BN + c0;
-            float acc[32];
+            const float* base = P.ws + (int64_t)tid * P.ksplit * (TM * P.BN) + (int64_t)(quarter * 32) * P.BN + c0 + lane;
+            for (int i0 = 0; i0 < 32; i0 += 8) {
+              float acc[8];
 #pragma unroll
-            for (int j = 0; j < 32; j++) acc[j] = 0.f;
-            for (int s = 0; s < P.ksplit; s++) {       // fixed order -> deterministic sum
-              const float* q = base + (int64_t)s * (TM * P.BN);
+              for (int i = 0; i < 8; i++) acc[i] = 0.f;
+              for (int s = 0; s < P.ksplit; s++) {
+                const float* q = base + (int64_t)s * (TM * P.BN) + (int64_t)i0 * P.BN;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 v = __ldcg(reinterpret_cast<const float4*>(q + j));
-                acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+                for (int i = 0; i < 8; i++) acc[i] += __ldcg(q + (int64_t)i * P.BN);
               }
-            }
 #pragma unroll
-            for (int j = 0; j < 32; j++) r[j] = __float_as_uint(acc[j]);
+              for (int i = 0; i < 8; i++) stage[(i0 + i) * 33 + lane] = acc[i];
+            }
+            __syncwarp();
           } else {
+            uint32_t r[32];
             tmem_ld32(tcol + (uint32_t)c0, r);
+            if (mrow0 < P.Mrows) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
+            }
+            __syncwarp();
           }
-          const int n = n0 + c0 + lane;
+          // Vectorised write-out: lane = (row sub-index rsub = lane / 8, four consecutive columns c4 = 4 (lane % 8)); one instruction moves
+          // four output rows x 128 bytes, and all eight residual / previous-output loads of the chunk are in flight together (the scalar
+          // version needed four dependent 16-load batches per warp and tile: ~10 us per tile, the kernel's bottleneck).
+          const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+          const int n = n0 + c0 + c4;
           const int ph = P.up_s ? n / P.C : 0;
           const int co = n - ph * P.C;
-          float st1 = 0.f, st2 = 0.f;
+          float st1[4] = {0.f, 0.f, 0.f, 0.f}, st2[4] = {0.f, 0.f, 0.f, 0.f};
           if (mrow0 < P.Mrows) {
-#pragma unroll
-            for (int j = 0; j < 32; j++) stage[lane * 33 + j] = __uint_as_float(r[j]);
-            __syncwarp();
             const int add = P.up_s ? ph - P.up_crop : 0;
-            const float bias = P.bias ? __ldg(P.bias + co) : 0.f;
-            const float cs = P.cscale ? __ldg(P.cscale + (int64_t)b * P.cscale_bs + co) : 1.f;
+            float bias[4], cso[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              bias[q] = P.bias ? __ldg(P.bias + co + q) : 0.f;
+              cso[q] = (P.cscale ? __ldg(P.cscale + (int64_t)b * P.cscale_bs + co + q) : 1.f) * P.out_scale;
+            }
             float* ycol = P.y + (int64_t)b * P.y_bs + co;
             const float* rcol = P.res ? P.res + (int64_t)b * P.res_bs + co : nullptr;
             const int row0 = mrow0 * mul + add;
@@ -437,58 +481,62 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
             int i_lo = 0, i_hi = mvalid;
             if (row0 < 0) i_lo = (-row0 + mul - 1) / mul;
             if (row0 + (mvalid - 1) * mul >= P.Lout) i_hi = P.Lout > row0 ? (P.Lout - row0 + mul - 1) / mul : 0;
-            const int64_t ystride = (int64_t)mul * P.y_ld;
-            float* yp = ycol + (int64_t)row0 * P.y_ld;
             const bool half_res = P.res_div == 2;
-            const int odd = row0 & 1;
-            const float* rp = rcol ? rcol + (int64_t)(half_res ? (row0 >> 1) : row0) * P.res_ld : nullptr;
-            const int64_t rstride = (int64_t)mul * P.res_ld;
-            const float osc = P.out_scale, cso = cs * P.out_scale;
-            if (i_lo == 0 && i_hi == 32) {
+            const float osc = P.out_scale;
+            float4 rr[8];
+            bool okr[8];
 #pragma unroll
-              for (int hh = 0; hh < 2; hh++) {          // two halves of 16 rows: all loads of a half are issued before its stores
-                float rr[16];
-                if (rp) {
-                  if (!half_res) {
+            for (int i = 0; i < 8; i++) {                                  // the chunk's residual (+ previous output) rows: one batch of loads
+              const int ti = 4 * i + rsub;                                 // tile row 0..31
+              const int row = row0 + ti * mul;
+              okr[i] = ti >= i_lo && ti < i_hi;
+              rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (okr[i]) {
+                if (rcol) rr[i] = __ldg(reinterpret_cast<const float4*>(rcol + (int64_t)(half_res ? (row >> 1) : row) * P.res_ld));
+              }
+            }
+            if (P.accumulate) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) rr[i] = __ldg(rp + (hh * 16 + i) * rstride);
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) rr[i] = __ldg(rp + (int64_t)((hh * 16 + i + odd) >> 1) * P.res_ld);
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; i++) rr[i] = 0.f;
-                }
-                if (P.accumulate) {
-#pragma unroll
-                  for (int i = 0; i < 16; i++) rr[i] = rr[i] * osc + yp[(hh * 16 + i) * ystride];
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 16; i++) rr[i] *= osc;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                  float a = stage[(hh * 16 + i) * 33 + lane] + bias;
-                  if (P.post_act) a = act_slow(a, P.post_act, P.post_p0);
-                  const float v = fmaf(a, cso, rr[i]);
-                  yp[(hh * 16 + i) * ystride] = v; st1 += v; st2 = fmaf(v, v, st2);
+              for (int i = 0; i < 8; i++) {
+                if (okr[i]) {
+                  const float4 o = *reinterpret_cast<const float4*>(ycol + (int64_t)(row0 + (4 * i + rsub) * mul) * P.y_ld);
+                  rr[i].x = fmaf(rr[i].x, osc, o.x); rr[i].y = fmaf(rr[i].y, osc, o.y); rr[i].z = fmaf(rr[i].z, osc, o.z); rr[i].w = fmaf(rr[i].w, osc, o.w);
                 }
               }
             } else {
-              for (int i = i_lo; i < i_hi; i++) {
-                const int row = row0 + i * mul;
-                float a = stage[i * 33 + lane] + bias;
-                if (P.post_act) a = act_slow(a, P.post_act, P.post_p0);
-                const float rv = rcol ? __ldg(rcol + (int64_t)(half_res ? (row >> 1) : row) * P.res_ld) : 0.f;
-                const float o = P.accumulate ? ycol[(int64_t)row * P.y_ld] : 0.f;
-                const float v = (a * cs + rv) * osc + o;
-                ycol[(int64_t)row * P.y_ld] = v; st1 += v; st2 = fmaf(v, v, st2);
+#pragma unroll
+              for (int i = 0; i < 8; i++) { rr[i].x *= osc; rr[i].y *= osc; rr[i].z *= osc; rr[i].w *= osc; }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int ti = 4 * i + rsub;
+              if (okr[i]) {
+                const float* sp = stage + ti * 33 + c4;                   // stride 33: the four scalar reads of a quarter-warp hit 32 distinct banks
+                float a[4] = {sp[0] + bias[0], sp[1] + bias[1], sp[2] + bias[2], sp[3] + bias[3]};
+                if (P.post_act) {
+#pragma unroll
+                  for (int q = 0; q < 4; q++) a[q] = act_slow(a[q], P.post_act, P.post_p0);
+                }
+                float4 v;
+                v.x = fmaf(a[0], cso[0], rr[i].x); v.y = fmaf(a[1], cso[1], rr[i].y); v.z = fmaf(a[2], cso[2], rr[i].z); v.w = fmaf(a[3], cso[3], rr[i].w);
+                *reinterpret_cast<float4*>(ycol + (int64_t)(row0 + ti * mul) * P.y_ld) = v;
+                st1[0] += v.x; st1[1] += v.y; st1[2] += v.z; st1[3] += v.w;
+                st2[0] = fmaf(v.x, v.x, st2[0]); st2[1] = fmaf(v.y, v.y, st2[1]); st2[2] = fmaf(v.z, v.z, st2[2]); st2[3] = fmaf(v.w, v.w, st2[3]);
               }
             }
             __syncwarp();
           }
-          if (do_stats) { sacc[(quarter * 2 + 0) * 128 + c0 + lane] = st1; sacc[(quarter * 2 + 1) * 128 + c0 + lane] = st2; }   // one writer per slot
+          if (do_stats) {                                                  // fixed-order reduction over the four row sub-indices, then one writer per slot
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              st1[q] += __shfl_xor_sync(0xffffffffu, st1[q], 8); st1[q] += __shfl_xor_sync(0xffffffffu, st1[q], 16);
+              st2[q] += __shfl_xor_sync(0xffffffffu, st2[q], 8); st2[q] += __shfl_xor_sync(0xffffffffu, st2[q], 16);
+            }
+            if (rsub == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; q++) { sacc[(quarter * 2 + 0) * 128 + c0 + c4 + q] = st1[q]; sacc[(quarter * 2 + 1) * 128 + c0 + c4 + q] = st2[q]; }
+            }
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -509,6 +557,7 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
         bar_sync(1, NEPI * 32);
       }
     }
+    if (p.dbg && et == 0) p.dbg[(size_t)blockIdx.x * 32 + 20] = w_tfull;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (threadIdx.x == 0) stamp(p, 12);
@@ -574,6 +623,7 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
     B2A_CHECK_ARG(q.x && q.w_hi && q.y && q.B > 0 && q.L > 0 && q.Lout > 0 && q.Cin > 0 && q.taps > 0 && q.taps <= 32 && q.cin_pad % 64 == 0 && q.cin_pad >= q.Cin,
                   "bad pointers / shape");
     B2A_CHECK_ARG(q.N % 32 == 0 && q.y_ld % 4 == 0 && (q.res == nullptr || q.res_ld % 4 == 0) && (q.res_div == 1 || q.res_div == 2), "N % 32, row strides % 4, res_div 1|2");
+    B2A_CHECK_ARG(((uintptr_t)q.y & 15) == 0 && q.y_bs % 4 == 0 && (q.res == nullptr || (((uintptr_t)q.res & 15) == 0 && q.res_bs % 4 == 0)), "y / res must be 16-byte aligned");
     B2A_CHECK_ARG(q.x_ld % 4 == 0 && q.x_bs % 4 == 0 && ((uintptr_t)q.x & 15) == 0 && q.x_ld >= ((q.Cin + 3) & ~3), "x must be 16-byte aligned with row stride % 4 == 0 and >= ceil4(Cin)");
     B2A_CHECK_ARG((q.x1 == nullptr || ((uintptr_t)q.x1 & 15) == 0) && (q.x2 == nullptr || ((uintptr_t)q.x2 & 15) == 0), "x1 / x2 alignment");
     B2A_CHECK_ARG(q.up_stride >= 0 && (q.up_stride == 0 || (q.N % q.up_stride == 0 && (q.N / q.up_stride) % 32 == 0)), "transposed mode: N = up_stride * C, C % 32 == 0");
@@ -613,9 +663,12 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
     P.y = q.y; P.y_bs = q.y_bs; P.y_ld = q.y_ld; P.stats_out = (long long*)q.stats_out;
     P.ws = nullptr; P.counters = nullptr;
     if (P.ksplit > 1) {
-      const int64_t need = base_tiles * P.ksplit * (TM * P.BN) * 4 + base_tiles * 4 + 256;
-      if (need > ws_bytes) { P.ksplit = 1; P.kper = kchunks; }
-      else { P.counters = (int*)ws; P.ws = (float*)((uint8_t*)ws + ((base_tiles * 4 + 255) / 256) * 256); }
+      // workspace layout: [4 KB of arrival counters (one per output tile; a split launch has < 148 of them)] [partial tiles].  The counter region
+      // has a FIXED size: were it sized per launch, the partial tiles of a launch with fewer tiles would overwrite counters that a later launch
+      // with more tiles expects to be zero (they are self-resetting, never re-zeroed).
+      const int64_t need = 4096 + base_tiles * P.ksplit * (TM * P.BN) * 4;
+      if (need > ws_bytes || base_tiles > 1024) { P.ksplit = 1; P.kper = kchunks; }
+      else { P.counters = (int*)ws; P.ws = (float*)((uint8_t*)ws + 4096); }
     }
     P.tile_begin = tiles_total;
     tiles_total += (int)(base_tiles * P.ksplit);

@@ -225,7 +225,7 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L - 1) * stride + cw.K - 2 * pad_left
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
-    if emit is None and fused_eligible(x, cw, stride, dilation, transpose, pad_mode):
+    if emit is None and fused_eligible(x, cw, stride, dilation, transpose, pad_mode, out, res):
         y = conv_fused(FusedProblem(x, cw, stride=stride, dilation=dilation, pad_left=pad_left, lout=lout, pre=pre, post_act=post_act,
                                     post_p0=post_p0, cscale=cscale, res=res, res_div=res_div, out_scale=out_scale, out=out,
                                     accumulate=accumulate, transpose=transpose))[0]
@@ -379,14 +379,18 @@ def stats_value(stats: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def fused_eligible(x, cw: "ConvW", stride: int = 1, dilation: int = 1, transpose: bool = False, pad_mode: int = 0) -> bool:
+def _al16(t: Optional[torch.Tensor]) -> bool:
+    return t is None or (t.data_ptr() % 16 == 0 and t.stride(1) % 4 == 0 and t.stride(0) % 4 == 0)
+
+
+def fused_eligible(x, cw: "ConvW", stride: int = 1, dilation: int = 1, transpose: bool = False, pad_mode: int = 0, out=None, res=None) -> bool:
     """Dense layers the fused kernel takes: tensor-core weights, stride 1 (or a polyphase transposed conv), taps spanning <= 64 rows,
     16-byte aligned fp32 rows."""
     if not FUSED[0] or TC_MODE[0] == "off" or cw.w_tc is None or pad_mode != 0 or cw.cout % 32 != 0 or cw.groups != 1 or isinstance(x, Planes):
         return False
     if x.dtype != torch.float32 or x.dim() != 3 or x.stride(2) != 1 or x.stride(1) % 4 or x.stride(0) % 4 or x.data_ptr() % 16:
         return False
-    if x.stride(1) < -(-x.shape[2] // 4) * 4:
+    if x.stride(1) < -(-x.shape[2] // 4) * 4 or not _al16(out) or not _al16(res):
         return False
     if transpose:
         return dilation == 1 and cw.K % stride == 0 and cw.K // stride <= 32 and cw.cin * (cw.K // stride) >= TC_MIN_K
@@ -894,6 +898,20 @@ def rvq_decode(codes: torch.Tensor, codebooks: torch.Tensor, out: Optional[torch
                                          dim, out.data_ptr(), out.stride(1), err.data_ptr(), _stream())
     if check and int(err.item()) != 0:
         raise ValueError(f"rvq_decode: code index out of range [0, {bins})")
+    return out
+
+
+def rvq_encode(x: torch.Tensor, codebooks: torch.Tensor, c2: torch.Tensor, *, mode: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Nearest-code search with the residual loop: x [R, D] fp32 rows, codebooks [nq, bins, D], c2 [nq, bins] float64 (|e|^2 / 2, or |en|^2 for
+    ``mode=1`` = SNAC's single-level cosine search on an L2-normalised table) -> int64 codes [R, nq] (or ``out``, any strides)."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32 and codebooks.is_contiguous() and c2.dtype == torch.float64 and c2.is_contiguous()
+    R, D = x.shape
+    nq, bins, _ = codebooks.shape
+    if out is None:
+        out = torch.empty(R, nq, device=x.device, dtype=torch.int64)
+    assert out.shape == (R, nq) and out.dtype == torch.int64
+    _call("rvq", _lib.lib().b2a_rvq_encode, 1, x.data_ptr(), x.stride(0), R, D, codebooks.data_ptr(), c2.data_ptr(), bins, nq, mode, out.data_ptr(),
+          out.stride(0), out.stride(1), _stream())
     return out
 
 

@@ -67,3 +67,27 @@ def gather_waveforms(local: List[torch.Tensor], local_ids: List[int], n_total: i
             if i >= 0:
                 out[i] = b[j, :n].clone()
     return out
+
+
+def decode_stream_sharded(model, codes, *, noises=None, dst: int = 0):
+    """One long code stream decoded by all ranks: rank r decodes its contiguous span of frames (+ the halo that makes it exact,
+    ``model.decode_span``) and rank ``dst`` receives the stitched waveform through one trailing all_gather (`gather_waveforms`); no
+    collective inside the decode.  ``codes``: Mimi ``[B, nq, T]`` or SNAC's list of per-level code tensors (every rank holds the
+    stream: it is a few hundred KB).  Returns the waveform on ``dst`` (None elsewhere); with one rank this is ``decode_span(0, T)``."""
+    rank, ws = world()
+    snac = isinstance(codes, (list, tuple))
+    if snac:
+        T = codes[-1].shape[1] * model.vq_strides[-1]
+        mult = max(model.vq_strides)
+    else:
+        T, mult = codes.shape[-1], 1
+    _, _, cs, ce = shard_span(T, rank, ws, multiple=mult)
+    if ce > cs:
+        y = model.decode_span(codes, cs, ce, noises=noises) if snac else model.decode_span(codes, cs, ce)
+        piece = (y[0, :, 0] if snac else y[0, 0]).contiguous()
+    else:
+        piece = torch.zeros(0, device=model.device)
+    parts = gather_waveforms([piece], [rank], ws, dst=dst)
+    if parts is None:
+        return None
+    return torch.cat([p for p in parts if p is not None and p.numel()])

@@ -96,6 +96,7 @@ class Model:
         self.concurrent = True     # independent sub-graphs (text encoder, F0/N heads, source path, resblocks) on parallel streams
         self.use_graphs = True     # __call__ / generate replay cached CUDA graphs (synthesize_ids); False -> eager forward_ids
         self.max_graphs = 32
+        self.share_graph_pool = True
         self._graphs, self._graph_pool, self._rng_state, self._warm_stream = {}, None, None, None
         self._stats_pool = None
 
@@ -749,11 +750,11 @@ class Model:
             fn()
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        if self._graph_pool is None:
+        if self._graph_pool is None and self.share_graph_pool:
             self._graph_pool = torch.cuda.graph_pool_handle()
         g = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES[0]
-        with torch.cuda.graph(g, pool=self._graph_pool):
+        with torch.cuda.graph(g, pool=self._graph_pool if self.share_graph_pool else None):
             out = fn()
         return g, out, ops.LAUNCHES[0] - n0
 
@@ -846,36 +847,55 @@ class Model:
         audio = audio[None]
         return self.Output(audio=audio, pred_dur=pred) if return_output else audio
 
-    # ------------------------------------------------------------------ generate (kokoro.py:293-370)
+    # ------------------------------------------------------------------ generate (kokoro.py:278-370)
+    def _get_pipeline(self, lang_code: str, **kw):
+        from .pipeline import KokoroPipeline
+        if lang_code not in self._pipelines:
+            self._pipelines[lang_code] = KokoroPipeline(lang_code, self, self.repo_id, **kw)
+        return self._pipelines[lang_code]
+
+    def _result(self, audio, seg_idx, n_tokens, seg_t):
+        samples = audio.shape[1]
+        dur = samples / self.sample_rate
+        return GenerationResult(
+            audio=audio[0], samples=samples, sample_rate=self.sample_rate, segment_idx=seg_idx, token_count=n_tokens,
+            audio_duration=f"{int(dur // 3600):02d}:{int(dur // 60) % 60:02d}:{int(dur % 60):02d}.{int((dur % 1) * 1000):03d}",
+            real_time_factor=round(seg_t / dur, 2) if dur > 0 else 0,
+            prompt={"tokens": n_tokens, "tokens-per-sec": round(n_tokens / seg_t, 2) if seg_t > 0 else 0},
+            audio_samples={"samples": samples, "samples-per-sec": round(samples / seg_t, 2) if seg_t > 0 else 0},
+            processing_time_seconds=seg_t, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
+
     def generate(self, text: str, voice=None, speed: float = 1.0, lang_code: str = "a", split_pattern: str = r"\n+", **kwargs):
-        """Generator of GenerationResult.  G2P (misaki) is host-side and outside the hot path; when it is
-        unavailable pass ``phonemes=...`` and ``ref_s=...`` (or a voice pack tensor [N,1,256] as ``voice``)."""
+        """Generator of GenerationResult (kokoro.py:293-370).  Text goes through the pipeline (pipeline.py): G2P -- the optional ``misaki``
+        package, or ``g2p=callable`` -- then <= 510-phoneme chunks, one graph-replayed model call per chunk, ``voice`` = the name of a pack
+        under ``voices_dir=`` / a file path / several names averaged / a tensor ``[510, 1, 256]``.  Without G2P pass ``phonemes=`` (a string
+        or a list of strings, each <= 510) and either a voice pack or a fixed style row ``ref_s=`` [1, 256]."""
         phonemes = kwargs.pop("phonemes", None)
         ref_s = kwargs.pop("ref_s", None)
-        if phonemes is None:
-            try:
-                from misaki import en  # noqa: F401
-            except ImportError as e:
-                raise ImportError("Kokoro G2P needs `misaki` (pip install misaki[en]); or call generate(text, phonemes=..., ref_s=...)") from e
-            raise NotImplementedError("misaki G2P bridge is host-side glue outside the accelerated path")
-        segments = phonemes if isinstance(phonemes, (list, tuple)) else [phonemes]
+        pipe_kw = {k: kwargs.pop(k) for k in ("g2p", "voices_dir") if k in kwargs}
         start = time.time()
-        for seg_idx, ps in enumerate(segments):
-            rs = ref_s
-            if rs is None:
-                if not isinstance(voice, torch.Tensor):
-                    raise ValueError("pass ref_s [1,256] or a voice pack tensor [N,1,256] as `voice`")
-                rs = voice[len(ps) - 1]                                # pipeline.py:303
-            audio = self(ps, rs, speed)
+        if phonemes is not None:
+            from .pipeline import MAX_PHONEMES
+            pack = None
+            if ref_s is None:
+                if voice is None:
+                    raise ValueError("pass ref_s [1,256] or a voice (pack tensor [N,1,256], file path or name) with phonemes=")
+                pack = self._get_pipeline(lang_code, **pipe_kw).load_voice(voice)
+            for seg_idx, ps in enumerate(phonemes if isinstance(phonemes, (list, tuple)) else [phonemes]):
+                if len(ps) > MAX_PHONEMES:
+                    raise ValueError(f"Phoneme string too long: {len(ps)} > {MAX_PHONEMES}")
+                audio = self(ps, ref_s if ref_s is not None else pack[len(ps) - 1], speed)          # pipeline.py:303
+                torch.cuda.synchronize(self.device)
+                now = time.time()
+                seg_t, start = now - start, now
+                yield self._result(audio, seg_idx, len(ps), seg_t)
+            return
+        pipeline = self._get_pipeline(lang_code, **pipe_kw)
+        if voice is None:
+            voice = "af_heart"
+        for seg_idx, (_gs, ps, audio) in enumerate(pipeline(text, voice=voice, speed=speed, split_pattern=split_pattern)):
             torch.cuda.synchronize(self.device)
             now = time.time()
             seg_t, start = now - start, now
-            samples = audio.shape[1]
-            dur = samples / self.sample_rate
-            yield GenerationResult(
-                audio=audio[0], samples=samples, sample_rate=self.sample_rate, segment_idx=seg_idx, token_count=len(ps),
-                audio_duration=f"{int(dur // 3600):02d}:{int(dur // 60) % 60:02d}:{int(dur % 60):02d}.{int((dur % 1) * 1000):03d}",
-                real_time_factor=round(seg_t / dur, 2) if dur > 0 else 0,
-                prompt={"tokens": len(ps), "tokens-per-sec": round(len(ps) / seg_t, 2) if seg_t > 0 else 0},
-                audio_samples={"samples": samples, "samples-per-sec": round(samples / seg_t, 2) if seg_t > 0 else 0},
-                processing_time_seconds=seg_t, peak_memory_usage=torch.cuda.max_memory_allocated(self.device) / 1e9)
+            assert audio is not None and audio.shape[1] > 0, "No audio generated"
+            yield self._result(audio, seg_idx, len(ps) if ps is not None else 0, seg_t)

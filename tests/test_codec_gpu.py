@@ -70,3 +70,41 @@ def test_mimi_reference_length_pin_and_prefix_causality(mimi):
     assert y.shape == (1, 1, 120960)
     y2 = model.decode(codes[:, :, :40])
     assert torch.allclose(y2, y[:, :, : 40 * 1920], atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("parts", [2, 3])
+def test_snac_span_decodes_stitch_to_the_one_shot_decode(snac, parts):
+    """SURVEY.md section 8e (config 5): one stream sharded by contiguous frame spans with a 16-frame halo per side; the per-channel
+    NoiseBlock draws are shared.  The stitched waveform equals the one-shot decode (different tile positions only: <= 1e-5 of full scale)."""
+    from mlx_audio_b200.parallel import shard_span
+    model, _ = snac
+    T = 236
+    codes = synth.snac_codes(OC.SNAC_24K, T)
+    noises = synth.snac_noises(OC.SNAC_24K)
+    full = model.decode(codes, noises=noises)
+    pieces = []
+    for r in range(parts):
+        _, _, cs, ce = shard_span(T, r, parts, multiple=max(model.vq_strides))
+        if ce > cs:
+            pieces.append(model.decode_span(codes, cs, ce, noises=noises))
+    got = torch.cat(pieces, dim=1)
+    assert got.shape == full.shape == (1, 120907, 1)
+    assert float((got - full).abs().max()) <= 1e-5
+    with pytest.raises(ValueError):
+        model.decode_span(codes, 2, 40, noises=noises)
+
+
+def test_mimi_span_decodes_stitch_to_the_one_shot_decode(mimi):
+    """Mimi is causal: a span needs LEFT context only -- num_layers x context transformer positions plus the convolutions (span_halo).  With
+    a too-short halo the result differs, which is what makes the exact halo worth stating."""
+    model, _ = mimi
+    T = 2400
+    codes = synth.mimi_codes(OC.MIMI_202407, T)
+    full = model.decode(codes)
+    assert model.span_halo == 8 * 250 // 2 + 16
+    a = model.decode_span(codes, 0, 1200)
+    b = model.decode_span(codes, 1200, 2400)
+    got = torch.cat([a, b], dim=-1)
+    assert got.shape == full.shape and float((got - full).abs().max()) <= 1e-5 * max(1.0, float(full.abs().max()))
+    short = model.decode_span(codes, 1200, 2400, halo=40)
+    assert float((short - full[..., 1200 * 1920:]).abs().max()) > 1e-4 * float(full.abs().max())

@@ -19,7 +19,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "b200audio.h")).read()
     declared = set(re.findall(r"\b(b2a_\w+)\s*\(", header))
-    declared -= {"b2a_conv1d_t", "b2a_attn_t"}
+    declared -= {"b2a_conv1d_t", "b2a_attn_t", "b2a_convf_t"}
     assert declared, "no declarations parsed"
     assert declared == set(_lib.PROTOTYPES), f"header vs ctypes prototypes differ: {declared ^ set(_lib.PROTOTYPES)}"
     for name in declared:
@@ -36,15 +36,17 @@ def test_ctypes_struct_matches_c_layout(tmp_path):
         #include <stddef.h>
         #include "b200audio.h"
         int main(void) {
-          printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2a_conv1d_t), offsetof(b2a_conv1d_t, pre_scale), offsetof(b2a_conv1d_t, res),
-                 offsetof(b2a_conv1d_t, accumulate), sizeof(b2a_attn_t), offsetof(b2a_attn_t, k_len));
+          printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(b2a_conv1d_t), offsetof(b2a_conv1d_t, pre_scale), offsetof(b2a_conv1d_t, res),
+                 offsetof(b2a_conv1d_t, accumulate), sizeof(b2a_attn_t), offsetof(b2a_attn_t, k_len),
+                 sizeof(b2a_convf_t), offsetof(b2a_convf_t, shifts), offsetof(b2a_convf_t, res), offsetof(b2a_convf_t, stats_out));
           return 0; }'''))
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    C, A = _lib.Conv1dParams, _lib.AttnParams
+    C, A, Fz = _lib.Conv1dParams, _lib.AttnParams, _lib.ConvFParams
     import ctypes
-    assert got == [ctypes.sizeof(C), C.pre_scale.offset, C.res.offset, C.accumulate.offset, ctypes.sizeof(A), A.k_len.offset]
+    assert got == [ctypes.sizeof(C), C.pre_scale.offset, C.res.offset, C.accumulate.offset, ctypes.sizeof(A), A.k_len.offset,
+                   ctypes.sizeof(Fz), Fz.shifts.offset, Fz.res.offset, Fz.stats_out.offset]
 
 
 def test_missing_library_fails_loudly(monkeypatch):
@@ -125,7 +127,7 @@ def test_shard_units_and_spans():
 GLOO_WORKER = r'''
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
-from mlx_audio_b200.parallel import gather_waveforms, shard_units, world
+from mlx_audio_b200.parallel import decode_stream_sharded, gather_waveforms, shard_units, world
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
 rank, ws = world()
 lengths = [300, 100, 250, 50, 120]
@@ -137,6 +139,30 @@ if rank == 0:
     print("GATHER_OK", mine)
 else:
     assert out is None
+
+
+class FakeSnac:                      # stands in for the GPU codec: 3 code levels, hop 4, sample value = global sample index
+    vq_strides, device = [4, 2, 1], torch.device("cpu")
+    def decode_span(self, codes, start, end, noises=None):
+        assert start % 4 == 0
+        n = (end - start) * 4 + (3 if end == codes[-1].shape[1] else 0)
+        return (torch.arange(n, dtype=torch.float32) + start * 4).reshape(1, n, 1)
+
+
+class FakeMimi:
+    device = torch.device("cpu")
+    def decode_span(self, codes, start, end):
+        return (torch.arange((end - start) * 5, dtype=torch.float32) + start * 5).reshape(1, 1, -1)
+
+
+T = 44
+y = decode_stream_sharded(FakeSnac(), [torch.zeros(1, T // 4), torch.zeros(1, T // 2), torch.zeros(1, T)])
+z = decode_stream_sharded(FakeMimi(), torch.zeros(1, 8, 31, dtype=torch.int64))
+if rank == 0:
+    assert torch.equal(y, torch.arange(T * 4 + 3, dtype=torch.float32)) and torch.equal(z, torch.arange(31 * 5, dtype=torch.float32))
+    print("STREAM_OK")
+else:
+    assert y is None and z is None
 dist.barrier(); dist.destroy_process_group()
 '''
 
@@ -149,7 +175,7 @@ def test_gloo_world2_sharding_and_trailing_gather(tmp_path):
              for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
-    assert "GATHER_OK" in outs[0]
+    assert "GATHER_OK" in outs[0] and "STREAM_OK" in outs[0]
 
 
 def test_drop_in_import_surface_and_loader(tmp_path):
@@ -439,3 +465,89 @@ def test_product_configs_say_what_the_oracle_configs_say():
     hits = [m.start() for m in pat.finditer(src)]
     lo, hi = src.index("def cpu_port_run"), src.index("def host_threads")
     assert hits and all(lo < h < hi for h in hits)
+    # bench_workloads.py (the other BASELINE configurations): oracle imports only inside the *_cpu functions (cpu_baseline / reference arm)
+    src = open(os.path.join(root, "bench_workloads.py")).read()
+    spans = [(m.start(), src.find("\ndef ", m.start() + 1)) for m in re.finditer(r"^def _\w+_cpu\(", src, re.M)]
+    hits = [m.start() for m in pat.finditer(src)]
+    assert hits and all(any(a < h < (b if b > 0 else len(src)) for a, b in spans) for h in hits)
+
+
+def test_kokoro_pipeline_chunking_follows_the_reference_pipeline():
+    """tests/golden/pipeline_golden.json = the reference's KokoroPipeline.en_tokenize / waterfall_last / join_timestamps and the sentence
+    chunking of its non-English branch EXECUTED on synthetic token lists (make_pipeline_golden.py).  The product's chunk_tokens /
+    join_timestamps / chunk_text must cut at the same places, and the model is called once per chunk with the voice row picked by the
+    phoneme count (pipeline.py:296-303)."""
+    import json
+    import torch
+    from mlx_audio_b200.tts.models.kokoro import pipeline as PL
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "pipeline_golden.json")))
+
+    class Tok:
+        def __init__(self, text, phonemes, whitespace):
+            self.text, self.phonemes, self.whitespace, self.start_ts, self.end_ts = text, phonemes, whitespace, None, None
+    for case in g["chunk_cases"]:
+        toks = [Tok(*s) for s in case["tokens"]]
+        got = [[gs, ps, len(tks)] for gs, ps, tks in PL.chunk_tokens(toks)]
+        assert got == case["chunks"] and all(len(c[1]) <= 510 for c in got)
+    for case in g["timestamp_cases"]:
+        toks = [Tok(*s) for s in case["tokens"]]
+        PL.join_timestamps(toks, torch.tensor(case["pred_dur"]))
+        assert [[t.start_ts, t.end_ts] for t in toks] == case["stamps"]
+    for case in g["text_chunks"]:
+        assert [c for c in PL.chunk_text(case["text"]) if c.strip()] == case["chunks"]
+    # one model call per chunk; voice = comma-separated packs averaged; style row = pack[len(phonemes) - 1]
+    calls = []
+
+    class FakeModel:
+        def __call__(self, ps, ref_s, speed, return_output=False):
+            calls.append((ps, ref_s.clone(), speed))
+            return type("O", (), {"audio": torch.zeros(1, 600 * len(ps)), "pred_dur": torch.ones(len(ps) + 2, dtype=torch.int64)})()
+    va, vb = torch.arange(510 * 256, dtype=torch.float32).reshape(510, 1, 256), torch.ones(510, 1, 256)
+    pipe = PL.KokoroPipeline("en-us", FakeModel(), g2p=lambda text: ("", [Tok(*s) for s in g["chunk_cases"][1]["tokens"]]))
+    pipe.voices = {"af_a": va, "af_b": vb}
+    res = list(pipe("ignored", voice="af_a,af_b", speed=1.25))
+    assert [r.phonemes for r in res] == [c[1] for c in g["chunk_cases"][1]["chunks"]] and len(calls) == len(res)
+    for (ps, ref_s, speed), r in zip(calls, res):
+        assert torch.equal(ref_s, ((va + vb) / 2)[len(ps) - 1]) and speed == 1.25 and r.text_index == 0 and r.audio.shape[1] == 600 * len(ps)
+    assert any(t.start_ts is not None for t in res[0].tokens)
+    with pytest.raises(ValueError, match="Specify a voice"):
+        list(pipe("x"))
+    with pytest.raises(ValueError, match="too long"):
+        list(pipe.generate_from_tokens("a" * 511, voice="af_a"))
+    assert [r.phonemes for r in pipe.generate_from_tokens("abc", voice=va)] == ["abc"]
+    with pytest.raises(ImportError, match="misaki"):
+        PL.KokoroPipeline("a", FakeModel()).g2p
+
+
+def test_torch_library_ops_are_registered_with_fake_implementations():
+    """north_star / SURVEY.md section 8b: the C-ABI entry points are surfaced as torch custom ops (namespace b200audio) with
+    ``register_fake``, so they trace without a GPU; on CPU tensors they refuse to run (no CPU fallback)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from mlx_audio_b200 import torch_ops
+    for name in torch_ops.OPS:
+        assert hasattr(torch.ops.b200audio, name), name
+    with FakeTensorMode():
+        x = torch.empty(2, 100, 64, device="cuda")
+        w = torch.empty(128, 7, 64, device="cuda")
+        assert torch.ops.b200audio.conv1d_cl(x, w, None, 1, 3, 9, 1, False, 2, 0.0, 0).shape == (2, 100, 128)
+        wt = torch.empty(32, 16, 64, device="cuda")
+        assert torch.ops.b200audio.conv1d_cl(x, wt, None, 8, 1, 4, 1, True, 1, 0.1, 0).shape == (2, 800, 32)
+        assert torch.ops.b200audio.linear(x, torch.empty(256, 64, device="cuda"), None, 4).shape == (2, 100, 256)
+        q = torch.empty(1, 130, 768, device="cuda")
+        assert torch.ops.b200audio.attention(q, q, q, 12, 0.125, False, 0).shape == q.shape
+        assert torch.ops.b200audio.lstm_bidir(torch.empty(1, 130, 2048, device="cuda"), torch.empty(2, 1024, 256, device="cuda")).shape == (1, 130, 512)
+        assert torch.ops.b200audio.layernorm(q, None, None, 1e-5, False).shape == q.shape
+        assert torch.ops.b200audio.whisper_logmel(torch.empty(32, 480000, device="cuda"), 80, 480000).shape == (32, 6000, 80)
+        codes = torch.empty(1, 32, 63, dtype=torch.int64, device="cuda")
+        assert torch.ops.b200audio.rvq_decode(codes, torch.empty(32, 2048, 256, device="cuda")).shape == (1, 63, 256)
+        enc = torch.ops.b200audio.rvq_encode(torch.empty(63, 256, device="cuda"), torch.empty(32, 2048, 256, device="cuda"),
+                                             torch.empty(32, 2048, dtype=torch.float64, device="cuda"), 0)
+        assert enc.shape == (63, 32) and enc.dtype == torch.int64
+        re, im = torch.ops.b200audio.stft(torch.empty(1, 16000, device="cuda"), torch.empty(400, device="cuda"), 400, 160, 1)
+        assert re.shape == im.shape == (1, 101, 201)
+        assert torch.ops.b200audio.kokoro_istft_head(torch.empty(1, 46801, 22, device="cuda")).shape == (1, 234000)
+        tok = torch.ops.b200audio.sample_token(torch.empty(8, 3072, device="cuda"), torch.empty(8, device="cuda"), 0.9, 50, 1.0, 0.0)
+        assert tok.shape == (8,) and tok.dtype == torch.int64
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        torch.ops.b200audio.layernorm(torch.zeros(2, 8), None, None, 1e-5, False)

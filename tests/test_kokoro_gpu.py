@@ -203,3 +203,28 @@ def test_kokoro_free_running_error_is_the_conditioning_of_the_harmonic_source(se
           f"of that size moves by {[f'{d:.2e}' for d in devs]}")
     assert delta < TOL_TEXT
     assert free < 10 * max(devs) + 1e-3, (free, devs)
+
+
+def test_kokoro_generate_text_path_with_a_g2p_callable_and_a_voice_pack(setup):
+    """Model.generate(text, voice=...) (kokoro.py:293-370 over pipeline.py): G2P tokens -> <= 510-phoneme chunks -> one graph-replayed call
+    per chunk with the style row voice[len(phonemes) - 1].  misaki is not in this image, so the G2P is a callable; the voice is a pack tensor."""
+    model, _, _ = setup
+    model.vocab = {chr(97 + i): i + 1 for i in range(26)}
+    model.vocab[" "] = 27
+
+    class Tok:
+        def __init__(self, text, phonemes, whitespace):
+            self.text, self.phonemes, self.whitespace = text, phonemes, whitespace
+
+    def g2p(text):
+        toks = [Tok(w, w, " ") for w in text.split()]
+        return "", toks
+    pack = torch.randn(510, 1, 256, generator=torch.Generator().manual_seed(4))
+    model._pipelines = {}
+    res = list(model.generate("hello brave new world\nsecond line here", voice=pack, g2p=g2p))
+    assert len(res) == 2 and [r.token_count for r in res] == [len("hello brave new world"), len("second line here")]
+    ps = "hello brave new world"
+    want = model(ps, pack[len(ps) - 1], 1.0, noise=None)
+    assert res[0].samples == want.shape[1] and res[0].sample_rate == 24000 and res[0].audio.dim() == 1
+    with pytest.raises(ValueError, match="too long"):
+        list(model.generate("x", phonemes="a" * 600, ref_s=pack[0]))

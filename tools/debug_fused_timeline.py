@@ -9,11 +9,16 @@ import torch
 from mlx_audio_b200 import ops, _lib
 
 dev = "cuda:0"
+ops.TC_MODE[0] = os.environ.get("TC", "x2")
+ONLY = os.environ.get("ONLY")
+print("tensor-core mode", ops.TC_MODE[0])
 def w(cout, k, cin, seed):
     return (torch.randn(cout, k, cin, generator=torch.Generator().manual_seed(seed)) * 0.05).to(torch.bfloat16).float()
 
 def run(name, probs_fn, reps=3):
-    stamps = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+    if ONLY and ONLY not in name:
+        return
+    stamps = torch.zeros(148, 32, dtype=torch.int64, device=dev)
     for _ in range(reps):
         ops.conv_fused(probs_fn())
     torch.cuda.synchronize()
@@ -30,7 +35,9 @@ def run(name, probs_fn, reps=3):
     print(f"== {name}: event {e0.elapsed_time(e1)*1e3:.1f} us, CTAs {int(live.sum())}")
     for c in sorted(set([0, int(live.sum()) // 2, int(live.sum()) - 1])):
         print(f"  cta {c}: " + " ".join(f"{i}:{rel[c, i]:.1f}" for i in range(14)))
-    last = torch.nan_to_num(rel[live], nan=0.0).max(dim=1).values
+    waits = s[live][:, 16:21].float().mean(dim=0) / 1e3
+    print(f"  mean wait us per CTA: MMA on tempty {waits[0]:.1f}, MMA on A {waits[1]:.1f}, MMA on W {waits[2]:.1f}; converter on a_empty {waits[3]:.1f}; epilogue on tfull {waits[4]:.1f}")
+    last = torch.nan_to_num(rel[live][:, :14], nan=0.0).max(dim=1).values
     print(f"  CTA end times: min {float(last.min()):.1f} median {float(last.median()):.1f} max {float(last.max()):.1f} us")
 
 x130 = torch.randn(1, 130, 2048, device=dev)
@@ -53,3 +60,13 @@ run("generator stage 1 group + stats in/out", lambda: [ops.FusedProblem(xs, cw, 
 xd = torch.randn(1, 390, 1092, device=dev)[:, :, :1090]
 cwd = ops.pack_conv(w(1024, 3, 1090, 5), None, 1, dev)
 run("decoder conv 390 x 1090 -> 1024 k3 (split-K)", lambda: [ops.FusedProblem(xd, cwd, pad_left=1)])
+
+# ---- is a row-shifted (tap) A descriptor slower than an aligned one?  Same MMA count per tile, one tile per CTA, no activation, no residual
+xa = torch.randn(1, 148 * 128, 1024, device=dev)
+cwa = ops.pack_conv(w(128, 1, 1024, 31), None, 1, dev)
+run("mma probe: k=1 (aligned A), 16 K chunks = 128 MMAs per tile", lambda: [ops.FusedProblem(xa, cwa)])
+xb = torch.randn(1, 148 * 128, 320, device=dev)
+cwb = ops.pack_conv(w(128, 3, 320, 32), None, 1, dev)
+run("mma probe: k=3 (row-shifted A), 5 K chunks x 3 taps = 120 MMAs per tile", lambda: [ops.FusedProblem(xb, cwb, pad_left=1)])
+cwc = ops.pack_conv(w(128, 3, 320, 33), None, 1, dev)
+run("mma probe: k=3 dilation 8 (shifts -8, 0, +8: multiples of the 8-row swizzle atom)", lambda: [ops.FusedProblem(xb, cwc, pad_left=8, dilation=8)])
