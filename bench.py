@@ -303,6 +303,21 @@ def main_kokoro(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # where the step goes: the two graphs timed separately (same buffers, no flush in between)
+    side_ms = {}
+    if model.use_graphs:
+        tgs = [v for k, v in model._graphs.items() if k[0] == "text" and not k[3]]
+        ags = [v for k, v in model._graphs.items() if k[0] == "acoustic" and v["text"] is (tgs[0] if tgs else None) and not k[4]]
+        if tgs and ags:
+            for name, g in (("text_side", tgs[0]["graph"]), ("acoustic_side", ags[0]["graph"])):
+                torch.cuda.synchronize(dev)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    g.replay()
+                b.record()
+                torch.cuda.synchronize(dev)
+                side_ms[name] = a.elapsed_time(b) / 10
     ms_max = rank_max(max(ms - ms_flush, 1e-6))
     ms_pinned_max = rank_max(max(ms_pinned - ms_flush, 1e-6))
     value = world * K * audio_s / (ms_max / 1e3)
@@ -418,7 +433,7 @@ def main_kokoro(args, rank, world, local_rank):
                            "frames": F, "audio_s_per_step": audio_s},
                 "clocks": clocks, "gpu_launches": launches,
                 "value_pinned_durations": world * K * audio_s / (ms_pinned_max / 1e3), "ms_per_step_pinned_durations": ms_pinned_max / K,
-                "parity_rel_rms": parity,
+                "parity_rel_rms": parity, "ms_by_side": {k: round(v, 3) for k, v in side_ms.items()},
                 "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(T * 8 + ref_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel() * 4 + 8), "call": "Model.__call__(phonemes, ref_s, out=pinned)"},
                 "roofline": roofline}

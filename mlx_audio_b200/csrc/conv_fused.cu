@@ -30,11 +30,11 @@ constexpr int TM = 128;
 constexpr int TK = 64;
 constexpr int UMMA_K = 16;
 constexpr int MAXG = B2A_CONVF_MAX_PROBLEMS;
-constexpr int NCONV = 8;                       // converter warps
-constexpr int NEPI = 8;                        // epilogue warps
-constexpr int W_CONV0 = 2, W_EPI0 = 2 + NCONV;
-constexpr int THREADS = (2 + NCONV + NEPI) * 32;          // 576
-constexpr int STAGING = NEPI * 32 * 33 * 4;               // per-warp 32x33 fp32 transpose tiles
+constexpr int NWORK = 16;                      // worker warps: every one converts A chunks AND runs epilogues (see the kernel's worker section)
+constexpr int W_WORK0 = 2;
+constexpr int THREADS = (2 + NWORK) * 32;                 // 576
+constexpr int RSTRIDE = NWORK * 32 / 16;                  // rows between a worker thread's consecutive A-tile rows (16 float4 slots per 64-channel row)
+constexpr int STAGING = NWORK * 32 * 33 * 4;              // per-warp 32x33 fp32 transpose tiles
 constexpr int SACC = 4 * 2 * 128 * 4;                     // per-tile (sum, sumsq) partials: [TMEM lane quarter][which][column <= 128]
 constexpr int CT_MAX = 1280;                              // channels of the per-CTA (scale, shift) table of the input transform
 constexpr int CTAB = 2 * CT_MAX * 4;
@@ -59,7 +59,10 @@ struct FProb {
 
 struct FParams {
   int G, ntiles, planes, f16, wst, w_stage, a_plane, tmem_stride;
-  unsigned long long* dbg;                     // optional [gridDim][16] globaltimer stamps (b2a_conv1d_fused_debug)
+  unsigned long long* dbg;                     // optional [gridDim][32] globaltimer stamps (b2a_conv1d_fused_debug)
+  int dbg_flags;                               // experiments (env B2A_FUSED_DBGFLAGS): 1 = converter skips the global loads, 2 = skips the smem stores,
+                                               // 4 = skips fence.proxy.async, 16 = workers skip the conversion, 32 = skip the epilogue body;
+                                               // results are then garbage -- timing only
   FProb pr[MAXG];
 };
 
@@ -89,8 +92,9 @@ __device__ __noinline__ float act_slow(float v, int act, float p0) { return b2a_
 __device__ __noinline__ float act_slow2(float v, int act, float p0, float a, float b) { return b2a_act(v, act, p0, a, b); }
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// accumulate the nanoseconds a role spends inside a wait (debug runs only): slots 16.. of the CTA's row
-#define TIMED_WAIT(p, acc, stmt) do { if ((p).dbg) { const unsigned long long t0_ = gtime(); stmt; acc += gtime() - t0_; } else { stmt; } } while (0)
+// accumulate the SM cycles a role spends inside a wait (debug runs only): slots 16.. of the CTA's row.  clock64, not %globaltimer: the
+// global timer read costs ~1 us on this part and, placed around every wait, it WAS the timeline (measured: same kernel 2x slower).
+#define TIMED_WAIT(p, acc, stmt) do { if ((p).dbg) { const long long t0_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
 __device__ __forceinline__ void stamp(const FParams& p, int slot) {
   if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 32 + slot] = t; }
 }
@@ -99,7 +103,7 @@ __device__ __forceinline__ void stamp(const FParams& p, int slot) {
 // ACT >= 0: the activation is a compile-time constant (round 1 measured the inlined runtime switch instruction-cache- and branch-bound); -1: runtime.
 template <typename T16, int ACT>
 __device__ __forceinline__ void convert_store(float4 v, bool valid, const float sc[4], const float sh[4], const float aa[4], const float bb[4],
-                                              const bool chok[4], int act, float p0, uint8_t* hi, uint8_t* lo, int r, int c4) {
+                                              const bool chok[4], int act, float p0, uint8_t* hi, uint8_t* lo, int r, int c4, bool do_store = true) {
   float t[4] = {v.x, v.y, v.z, v.w};
   __align__(8) T16 h[4];
   __align__(8) T16 l[4];
@@ -118,37 +122,43 @@ __device__ __forceinline__ void convert_store(float4 v, bool valid, const float 
     l[q] = cvt16<T16>(u - back16(h[q]));
   }
   const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)c4 >> 1) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)c4 & 1u) << 3);
-  *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
-  if (lo) *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+  if (do_store) {
+    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<uint2*>(h);
+    if (lo) *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<uint2*>(l);
+  } else if (reinterpret_cast<uint2*>(h)->x == 0x12345678u && reinterpret_cast<uint2*>(l)->y == 0x9abcdef0u) {
+    hi[0] = 1;                                                             // timing experiment: keep the conversion alive without the stores
+  }
 }
 
-// One K chunk of the A tile: rows r0, r0 + 16, ... of 4 channels.  ALL loads of a batch are issued before anything consumes them: a
+// One K chunk of the A tile: rows r0, r0 + RSTRIDE, ... of 4 channels.  ALL loads of a batch are issued before anything consumes them: a
 // consumer placed between two loads -- even a predicated-off one, e.g. the optional x1 / x2 adds -- waits on the scoreboard of the
 // load in front of it and serialises the batch into one L2 round trip per row (measured: 2-10 us per K chunk instead of < 1 us).
 // NADD = number of extra input tensors summed into x (0, 1 or 2); U = rows in flight per thread.
 template <typename T16, int ACT, int NADD, int U>
 __device__ __forceinline__ void convert_chunk(const float* __restrict__ xb, const float* __restrict__ xb1, const float* __restrict__ xb2, int64_t x_ld,
                                               int L, int lbase, int ch, int c4, int r0, int R, bool anych, const float sc[4], const float sh[4],
-                                              const float aa[4], const float bb[4], const bool chok[4], int act, float p0, uint8_t* hi, uint8_t* lo) {
-  for (int r = r0; r < R; r += 16 * U) {
+                                              const float aa[4], const float bb[4], const bool chok[4], int act, float p0, uint8_t* hi, uint8_t* lo,
+                                              int flags = 0) {
+  for (int r = r0; r < R; r += RSTRIDE * U) {
     float4 v[U], w1[NADD > 0 ? U : 1], w2[NADD > 1 ? U : 1];
     bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int rr = r + u * 16;
+      const int rr = r + u * RSTRIDE;
       const int l = lbase + rr;
       ok[u] = rr < R && l >= 0 && l < L && anych;
       const int64_t off = ok[u] ? (int64_t)l * x_ld + ch : 0;     // masked rows read row 0 of the chunk (always valid memory), result discarded
+      if (flags & 1) v[u] = make_float4((float)rr, 1.f, 2.f, 3.f); else
       v[u] = __ldg(reinterpret_cast<const float4*>(xb + off));
       if constexpr (NADD > 0) w1[u] = __ldg(reinterpret_cast<const float4*>(xb1 + off));
       if constexpr (NADD > 1) w2[u] = __ldg(reinterpret_cast<const float4*>(xb2 + off));
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const int rr = r + u * 16;
+      const int rr = r + u * RSTRIDE;
       if constexpr (NADD > 0) { v[u].x += w1[u].x; v[u].y += w1[u].y; v[u].z += w1[u].z; v[u].w += w1[u].w; }
       if constexpr (NADD > 1) { v[u].x += w2[u].x; v[u].y += w2[u].y; v[u].z += w2[u].z; v[u].w += w2[u].w; }
-      if (rr < R) convert_store<T16, ACT>(v[u], ok[u], sc, sh, aa, bb, chok, act, p0, hi, lo, rr, c4);
+      if (rr < R) convert_store<T16, ACT>(v[u], ok[u], sc, sh, aa, bb, chok, act, p0, hi, lo, rr, c4, !(flags & 2));
     }
   }
 }
@@ -169,13 +179,25 @@ __device__ __forceinline__ void stats_coeffs(const FProb& P, int b, int c, float
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
-conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap mw1,
+conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap mw1,
                   const __grid_constant__ CUtensorMap mw2, const __grid_constant__ CUtensorMap mw3,
                   const __grid_constant__ CUtensorMap ml0, const __grid_constant__ CUtensorMap ml1,
                   const __grid_constant__ CUtensorMap ml2, const __grid_constant__ CUtensorMap ml3) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The problem table is indexed by the tile's problem id at run time.  Reading it from the kernel-parameter (constant) bank costs a
+  // dependent, dynamically indexed LDC per field -- hundreds of cycles each once 18 warps thrash the constant cache -- and those loads sat
+  // inside every role's inner loop (measured: the MMA issuer spent ~1.5 us per K chunk issuing 8 MMAs).  One cooperative copy into shared
+  // memory at kernel start makes every later access a ~30-cycle LDS.
+  __shared__ __align__(16) FParams sparams;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&gp);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sparams);
+    for (int i = threadIdx.x; i < (int)(sizeof(FParams) / 4); i += THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const FParams& p = sparams;
   if (threadIdx.x == 0) stamp(p, 0);
   // layout: [2] x A buffer (planes x a_plane bytes) | [wst] x W stage | staging | sacc | coefficient table | barriers
   const int a_buf = p.a_plane * p.planes;
@@ -194,8 +216,8 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.wst; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(tfull, 1); mbar_init(tfull + 1, 1); mbar_init(tempty, NEPI); mbar_init(tempty + 1, NEPI);
-    mbar_init(a_full, NCONV); mbar_init(a_full + 1, NCONV); mbar_init(a_empty, 1); mbar_init(a_empty + 1, 1);
+    mbar_init(tfull, 1); mbar_init(tfull + 1, 1); mbar_init(tempty, NWORK); mbar_init(tempty + 1, NWORK);
+    mbar_init(a_full, NWORK); mbar_init(a_full + 1, NWORK); mbar_init(a_empty, 1); mbar_init(a_empty + 1, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -220,7 +242,9 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
         asm volatile("prefetch.tensormap [%0];" ::"l"(mws[g]) : "memory");
         if (p.pr[g].wplanes == 2) asm volatile("prefetch.tensormap [%0];" ::"l"(mls[g]) : "memory");
       }
-      uint32_t it = 0;
+      int s = 0; uint32_t ph = 0;
+      unsigned long long w_pempty = 0;
+      const long long pt0 = clock64();
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const TileRef t = decode_tile(p, tile);
         const FProb& P = p.pr[t.g];
@@ -229,24 +253,33 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
         const int kc0 = t.ks * P.kper, kc1 = min(kchunks, kc0 + P.kper);
         const uint32_t wb = (uint32_t)P.BN * 128u;
         for (int kc = kc0; kc < kc1; kc++) {
-          for (int tap = 0; tap < P.taps; tap++, it++) {
-            const int s = it % p.wst, ph = (it / p.wst) & 1;
-            mbar_wait(empty + s, ph ^ 1);
+          for (int tap = 0; tap < P.taps; tap++) {
+            TIMED_WAIT(p, w_pempty, mbar_wait(empty + s, ph ^ 1));
             uint8_t* st = wbase + (size_t)s * p.w_stage;
-            if (it == 0) stamp(p, 2);
             mbar_expect_tx(full + s, wb * (uint32_t)P.wplanes);
             tma_load_2d(st, mws[t.g], full + s, kc * TK, tap * P.Ntot + n0);
             if (P.wplanes == 2) tma_load_2d(st + wb, mls[t.g], full + s, kc * TK, tap * P.Ntot + n0);
+            if (++s == p.wst) { s = 0; ph ^= 1; }
           }
         }
       }
+      if (p.dbg) { p.dbg[(size_t)blockIdx.x * 32 + 21] = (unsigned long long)(clock64() - pt0); p.dbg[(size_t)blockIdx.x * 32 + 22] = w_pempty; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+    // The whole warp runs this loop in lock step and one elected lane issues (elect.sync inside the asm blocks).  The first version
+    // wrapped the issue in `if (lane == 0)`: ptxas then guards every UTCHMMA operand with its own ELECT + R2UR.BROADCAST sequence,
+    // and together with the ring-slot division and per-MMA descriptor rebuilds one tap step (8 MMAs, 0.27 us of tensor time) cost
+    // ~500 dynamic instructions = 1.1 us of a lone warp's issue time -- the kernel's real bottleneck (profiles/r02: the skeleton with
+    // no loads, no MMAs and no epilogue ran at 80 % of the full kernel's time).
     const uint32_t fmt = p.f16 ? 0u : 1u;
-    const uint32_t a0 = smem_u32(smem);
-    uint32_t it = 0, lt = 0, cg = 0;
+    const uint32_t a0 = smem_u32(smem), w0 = smem_u32(wbase);
+    const uint32_t wst = (uint32_t)p.wst, w_stage = (uint32_t)p.w_stage, a_plane = (uint32_t)p.a_plane;
+    const bool two_a = p.planes == 2;
+    const uint64_t dhi = umma_desc_sw128(0);                       // descriptor bits above the 14-bit start-address field
+    uint32_t s = 0, ph = 0, lt = 0, cg = 0;
     unsigned long long w_tempty = 0, w_afull = 0, w_wfull = 0;
+    const long long mt0 = clock64();
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
@@ -255,51 +288,77 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
       const int kc0 = t.ks * P.kper, kc1 = min(kchunks, kc0 + P.kper);
       const uint32_t buf = lt & 1, use = lt >> 1;
       const uint32_t wb = (uint32_t)P.BN * 128u;
+      const int taps = P.taps, smin = P.shift_min;
+      const bool two_w = P.wplanes == 2;
       TIMED_WAIT(p, w_tempty, mbar_wait(tempty + buf, (use & 1) ^ 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + buf * (uint32_t)p.tmem_stride;
+      uint32_t accum = 0;                                            // the tile's first MMA overwrites the accumulator
       for (int kc = kc0; kc < kc1; kc++, cg++) {
         const uint32_t ab = cg & 1;
         TIMED_WAIT(p, w_afull, mbar_wait(a_full + ab, (cg >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int tap = 0; tap < P.taps; tap++, it++) {
-          const int s = it % p.wst, ph = (it / p.wst) & 1;
+        const uint32_t abase = a0 + ab * (uint32_t)a_buf;
+        for (int tap = 0; tap < taps; tap++) {
           TIMED_WAIT(p, w_wfull, mbar_wait(full + s, ph));
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (lane == 0 && it == 0) stamp(p, 4);
-          if (lane == 0) {
-            const uint32_t wst_addr = smem_u32(wbase + (size_t)s * p.w_stage);
-            const uint32_t abase = a0 + ab * (uint32_t)a_buf + (uint32_t)(P.shift[tap] - P.shift_min) * 128u;
-            for (int wp = 0; wp < P.wplanes; wp++) {
-              const uint64_t wdesc = umma_desc_sw128(wst_addr + wp * wb);
-              const int npl = wp == 0 ? p.planes : 1;            // products kept: a_hi*w_hi, a_lo*w_hi, a_hi*w_lo
-              for (int pl = 0; pl < npl; pl++) {
-                const uint64_t adesc = umma_desc_sw128(abase + pl * (uint32_t)p.a_plane);
-#pragma unroll
-                for (int k = 0; k < TK / UMMA_K; k++)
-                  umma_f16(tacc, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, ((kc - kc0) | tap | wp | pl | k) != 0);
-              }
-            }
-            umma_commit(empty + s);
-            if (tap == P.taps - 1) umma_commit(a_empty + ab);
-            if (kc == kc1 - 1 && tap == P.taps - 1) { umma_commit(tfull + buf); if (lt == 0) stamp(p, 5); }
+          const uint32_t wa = w0 + s * w_stage;
+          const uint32_t aa = abase + (uint32_t)(P.shift[tap] - smin) * 128u;
+          const uint64_t wd = dhi | (uint64_t)(wa >> 4), ad = dhi | (uint64_t)(aa >> 4);
+          umma_f16_x4(tacc, ad, wd, idesc, accum);                                               // a_hi * w_hi
+          accum = 1;
+          if (two_a) umma_f16_x4(tacc, dhi | (uint64_t)((aa + a_plane) >> 4), wd, idesc, 1u);      // a_lo * w_hi
+          if (two_w) umma_f16_x4(tacc, ad, dhi | (uint64_t)((wa + wb) >> 4), idesc, 1u);           // a_hi * w_lo
+          umma_commit_elect(empty + s);
+          if (tap == taps - 1) {
+            umma_commit_elect(a_empty + ab);
+            if (kc == kc1 - 1) umma_commit_elect(tfull + buf);
           }
-          __syncwarp();
+          if (++s == wst) { s = 0; ph ^= 1; }
         }
       }
     }
-    if (p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 16] = w_tempty; p.dbg[(size_t)blockIdx.x * 32 + 17] = w_afull; p.dbg[(size_t)blockIdx.x * 32 + 18] = w_wfull; }
-  } else if (warp < W_EPI0) {
-    // ===== converter warps: fp32 activations -> transformed 16-bit planes in the swizzled A tile =====
+    if (p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 23] = (unsigned long long)(clock64() - mt0); p.dbg[(size_t)blockIdx.x * 32 + 16] = w_tempty; p.dbg[(size_t)blockIdx.x * 32 + 17] = w_afull; p.dbg[(size_t)blockIdx.x * 32 + 18] = w_wfull; }
+  } else {
+    // ===== worker warps (16): A-tile conversion AND epilogue =====
+    // The first version of this kernel split the roles (8 converter + 8 epilogue warps).  Its profile on the Kokoro layers: the converter
+    // was the bottleneck everywhere (~5 us per K chunk, issue-latency bound with two warps per scheduler) while the epilogue warps
+    // idled ~70 % of the time, and the two big loops evicted each other from the instruction caches (a third of the stall samples
+    // were no_inst).  Now every worker runs the same loop at the same time, at twice the width:
+    //     C(0) C(1) E(0) C(2) E(1) ... E(last)        C = convert all K chunks of a tile, E = epilogue of a tile
+    // MMA(t) needs the TMEM buffer E(t-2) frees, and E(t-2) precedes C(t) in this order: no deadlock.  E(t) runs after C(t+1), by when
+    // the MMAs of tile t have normally retired, so the workers rarely wait on tfull.
     pdl_wait();
-    if (warp == W_CONV0 && lane == 0) stamp(p, 3);
-    const int t256 = (warp - W_CONV0) * 32 + lane;
-    const int c4 = t256 & 15;                       // float4 slot inside the 64-channel chunk (fixed per thread: constants stay in registers)
-    const int r0 = t256 >> 4;                       // first row of this thread (stride 16)
+    if (warp == W_WORK0 && lane == 0) stamp(p, 3);
+    const int ww = warp - W_WORK0;                   // 0..15
+    const int wt = ww * 32 + lane;                   // 0..511
+    const int c4 = wt & 15;                          // float4 slot inside the 64-channel chunk (fixed per thread: constants stay in registers)
+    const int r0 = wt >> 4;                          // first A-tile row of this thread (stride RSTRIDE)
+    const int quarter = warp & 3, sub = ww >> 2;     // TMEM lane quarter is warp % 4 (hardware rule); sub picks the 32-column chunk
+    const int et = wt;
+    float* stage = staging + ww * (32 * 33);
     uint32_t cg = 0;
     int cur_key = -1;
-    unsigned long long w_aempty = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    unsigned long long w_aempty = 0, w_tfull = 0;
+
+    auto convert_tile = [&](const int tile) {
+      {
+        const TileRef t = decode_tile(p, tile);
+        const FProb& P = p.pr[t.g];
+        const int l0 = t.mt * TM, n0 = t.nt * P.BN, b = t.b;
+        if (!P.up_s && P.ksplit == 1) {                           // pull this warp's residual / previous-output rows towards L2 while the MMAs run
+          const int prow = l0 + quarter * 32 + lane;
+          if (prow < P.Lout) {
+            if (P.res) {
+              const float* q = P.res + (int64_t)b * P.res_bs + (int64_t)(P.res_div == 2 ? (prow >> 1) : prow) * P.res_ld + n0;
+              for (int c = sub * 32; c < P.BN; c += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+            }
+            if (P.accumulate) {
+              const float* q = P.y + (int64_t)b * P.y_bs + (int64_t)prow * P.y_ld + n0;
+              for (int c = sub * 32; c < P.BN; c += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+            }
+          }
+        }
+      }
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
       const int kchunks = P.cin_pad / TK;
@@ -309,19 +368,19 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
       const float* xb1 = P.x1 ? P.x1 + (int64_t)t.b * P.x_bs : nullptr;
       const float* xb2 = P.x2 ? P.x2 + (int64_t)t.b * P.x_bs : nullptr;
       const int R = P.R;
-      // (scale, shift) of every input channel: computed once per (problem, batch) by the 256 converter threads -- the float64 statistics
+      // (scale, shift) of every input channel: computed once per (problem, batch) by the 512 worker threads -- the float64 statistics
       // arithmetic costs ~150 double-precision operations per channel, far too much to repeat in every K chunk of every tile
       const bool tabled = P.pre_mode != 0 && P.Cin <= CT_MAX;
       const int key = (t.g << 16) | t.b;
       if (tabled && key != cur_key) {
-        bar_sync(3, NCONV * 32);                       // nobody still reads the previous table
-        for (int c = t256; c < P.Cin; c += NCONV * 32) {
+        bar_sync(3, NWORK * 32);                       // nobody still reads the previous table
+        for (int c = wt; c < P.Cin; c += NWORK * 32) {
           float sc_ = P.in_scale, sh_ = 0.f;
           if (P.pre_mode == 1) { sc_ = __ldg(P.pre_scale + (int64_t)t.b * P.Cin + c) * P.in_scale; sh_ = __ldg(P.pre_shift + (int64_t)t.b * P.Cin + c); }
           else stats_coeffs(P, t.b, c, sc_, sh_);
           ctab[c] = sc_; ctab[CT_MAX + c] = sh_;
         }
-        bar_sync(3, NCONV * 32);
+        bar_sync(3, NWORK * 32);
         cur_key = key;
       }
       for (int kc = kc0; kc < kc1; kc++, cg++) {
@@ -346,68 +405,47 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
         TIMED_WAIT(p, w_aempty, mbar_wait(a_empty + ab, ((cg >> 1) & 1) ^ 1));
         uint8_t* hi = smem + (size_t)ab * a_buf;
         uint8_t* lo = p.planes == 2 ? hi + p.a_plane : nullptr;
-#define B2A_CONVERT(T, A, N, UU) convert_chunk<T, A, N, UU>(xb, xb1, xb2, P.x_ld, P.L, lbase, chs, c4, r0, R, anych, sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo)
+#define B2A_CONVERT(T, A, N, UU) convert_chunk<T, A, N, UU>(xb, xb1, xb2, P.x_ld, P.L, lbase, chs, c4, r0, R, anych, sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo, p.dbg_flags)
         const int chs = anych ? ch : 0;                    // chunks wholly past Cin (never with a valid weight column) still index valid memory
         // specialised bodies for the hot cases only (each instantiation is ~1-2 K instructions): single input x {none, Snake, LeakyReLU, ELU};
         // summed inputs (the folded branch average) and fp16 operands with an activation take the runtime-switch body
-        if (p.f16) { if (xb1 == nullptr && P.pre_act == 0) B2A_CONVERT(__half, 0, 0, 6); else if (xb2) B2A_CONVERT(__half, -1, 2, 3);
-                     else if (xb1) B2A_CONVERT(__half, -1, 1, 4); else B2A_CONVERT(__half, -1, 0, 6); }
-        else if (xb2) B2A_CONVERT(__nv_bfloat16, -1, 2, 3);
-        else if (xb1) B2A_CONVERT(__nv_bfloat16, -1, 1, 4);
-        else if (P.pre_act == 0) B2A_CONVERT(__nv_bfloat16, 0, 0, 9);
-        else if (P.pre_act == B2A_ACT_SNAKE) B2A_CONVERT(__nv_bfloat16, B2A_ACT_SNAKE, 0, 9);
-        else if (P.pre_act == B2A_ACT_LRELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_LRELU, 0, 9);
-        else if (P.pre_act == B2A_ACT_ELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_ELU, 0, 6);
-        else B2A_CONVERT(__nv_bfloat16, -1, 0, 6);
+        if (p.dbg_flags & 16) { }
+        else if (p.f16) { if (xb1 == nullptr && P.pre_act == 0) B2A_CONVERT(__half, 0, 0, 5); else if (xb2) B2A_CONVERT(__half, -1, 2, 2);
+                     else if (xb1) B2A_CONVERT(__half, -1, 1, 3); else B2A_CONVERT(__half, -1, 0, 3); }
+        else if (xb2) B2A_CONVERT(__nv_bfloat16, -1, 2, 2);
+        else if (xb1) B2A_CONVERT(__nv_bfloat16, -1, 1, 3);
+        else if (P.pre_act == 0) B2A_CONVERT(__nv_bfloat16, 0, 0, 5);
+        else if (P.pre_act == B2A_ACT_SNAKE) B2A_CONVERT(__nv_bfloat16, B2A_ACT_SNAKE, 0, 5);
+        else if (P.pre_act == B2A_ACT_LRELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_LRELU, 0, 5);
+        else if (P.pre_act == B2A_ACT_ELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_ELU, 0, 3);
+        else B2A_CONVERT(__nv_bfloat16, -1, 0, 3);
 #undef B2A_CONVERT
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
+        if (!(p.dbg_flags & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + ab);
-        if (warp == W_CONV0 && lane == 0) { if (cg == 0) stamp(p, 6); stamp(p, 7); }
+        if (warp == W_WORK0 && lane == 0) { if (cg == 0) stamp(p, 6); stamp(p, 7); }
       }
-    }
-    if (p.dbg && warp == W_CONV0 && lane == 0) p.dbg[(size_t)blockIdx.x * 32 + 19] = w_aempty;
-  } else {
-    // ===== epilogue warps =====
-    pdl_wait();
-    const int ew = warp - W_EPI0;                    // 0..7
-    const int quarter = warp & 3, sub = ew >> 2;     // TMEM lane quarter is warp % 4 (hardware rule); sub splits the 32-column chunks
-    const int et = ew * 32 + lane;                   // 0..255 inside the epilogue group
-    float* stage = staging + ew * (32 * 33);
-    uint32_t lt = 0;
-    unsigned long long w_tfull = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
+    };
+
+    auto epilogue_tile = [&](const int tile, const uint32_t lt) {
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
       const int mul = P.up_s ? P.up_s : 1;
       const int l0 = t.mt * TM, n0 = t.nt * P.BN, b = t.b;
       const uint32_t buf = lt & 1, use = lt >> 1;
       const bool do_stats = P.stats_out != nullptr;
-      if (!P.up_s && P.ksplit == 1) {                           // pull this warp's residual / previous-output rows towards L2 while the MMAs run
-        const int prow = l0 + quarter * 32 + lane;
-        if (prow < P.Lout) {
-          if (P.res) {
-            const float* q = P.res + (int64_t)b * P.res_bs + (int64_t)(P.res_div == 2 ? (prow >> 1) : prow) * P.res_ld + n0;
-            for (int c = sub * 32; c < P.BN; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
-          }
-          if (P.accumulate) {
-            const float* q = P.y + (int64_t)b * P.y_bs + (int64_t)prow * P.y_ld + n0;
-            for (int c = sub * 32; c < P.BN; c += 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
-          }
-        }
-      }
       TIMED_WAIT(p, w_tfull, mbar_wait(tfull + buf, use & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (et == 0 && lt == 0) stamp(p, 8);
       const int mrow0 = l0 + quarter * 32;
       const uint32_t tcol = tmem_base + buf * (uint32_t)p.tmem_stride + ((uint32_t)(quarter * 32) << 16);
-      bool last_split = true;
+      bool last_split = !(p.dbg_flags & 32);
       if (P.ksplit > 1) {
         // ---- split-K: park this CTA's partial accumulator (through the transpose tile: whole 128-byte row segments), then only the
         // last CTA to arrive for the tile carries on
         const int tid = ((b * P.ntm + t.mt) * P.ntn + t.nt);
         float* mine = P.ws + ((int64_t)tid * P.ksplit + t.ks) * (TM * P.BN) + (int64_t)(quarter * 32) * P.BN;
-        for (int c0 = sub * 32; c0 < P.BN; c0 += 64) {
+        for (int c0 = sub * 32; c0 < P.BN; c0 += 128) {
           uint32_t r[32];
           tmem_ld32(tcol + (uint32_t)c0, r);
 #pragma unroll
@@ -418,20 +456,20 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
           __syncwarp();
         }
         __threadfence();
-        bar_sync(2, NEPI * 32);
+        bar_sync(2, NWORK * 32);
         if (et == 0) {
           const int prev = atomicAdd(P.counters + tid, 1);
           const int last = prev == P.ksplit - 1;
           if (last) P.counters[tid] = 0;              // re-arm for the next launch that reuses this workspace
           *flag_slot = last;
         }
-        bar_sync(2, NEPI * 32);
+        bar_sync(2, NWORK * 32);
         last_split = *flag_slot != 0;
         if (last_split) __threadfence();
         if (et == 0 && lt == 0) stamp(p, 9);
       }
       if (last_split) {
-        for (int c0 = sub * 32; c0 < P.BN; c0 += 64) {
+        for (int c0 = sub * 32; c0 < P.BN; c0 += 128) {
           if (P.ksplit > 1) {
             // fixed-order sum of the partial tiles, read row by row (lane = column: coalesced, and already the layout the stores below want)
             const int tid = ((b * P.ntm + t.mt) * P.ntn + t.nt);
@@ -542,22 +580,36 @@ conv_fused_kernel(const __grid_constant__ FParams p, const __grid_constant__ CUt
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (et == 0) { if (lt == 0) stamp(p, 10); stamp(p, 11); }
-      if (lane == 0) mbar_arrive(tempty + buf);                // 8 arrivals free the accumulator for tile lt + 2
+      if (lane == 0) mbar_arrive(tempty + buf);                // 16 arrivals free the accumulator for tile lt + 2
       if (do_stats) {
-        bar_sync(1, NEPI * 32);
+        bar_sync(1, NWORK * 32);
         if (last_split) {
           const int co0 = P.up_s ? (n0 % P.C) : n0;
-          for (int i = et; i < 2 * P.BN; i += NEPI * 32) {
+          for (int i = et; i < 2 * P.BN; i += NWORK * 32) {
             const int which = i >= P.BN, col = i - which * P.BN;
             const float v = ((sacc[(0 * 2 + which) * 128 + col] + sacc[(1 * 2 + which) * 128 + col]) + sacc[(2 * 2 + which) * 128 + col]) +
                             sacc[(3 * 2 + which) * 128 + col];                      // fixed order over the four lane quarters
             repro_add(P.stats_out + (((int64_t)b * P.C + co0 + col) * 2 + which) * B2A_NBIN, v);
           }
         }
-        bar_sync(1, NEPI * 32);
+        bar_sync(1, NWORK * 32);
       }
+    };
+
+    int prev = -1;
+    uint32_t nt_done = 0;
+    long long cyc_c = 0, cyc_e = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      const long long c0_ = clock64();
+      convert_tile(tile);
+      const long long c1_ = clock64();
+      if (prev >= 0) { epilogue_tile(prev, nt_done); nt_done++; }
+      cyc_c += c1_ - c0_; cyc_e += clock64() - c1_;
+      prev = tile;
     }
-    if (p.dbg && et == 0) p.dbg[(size_t)blockIdx.x * 32 + 20] = w_tfull;
+    { const long long c1_ = clock64(); if (prev >= 0) epilogue_tile(prev, nt_done); cyc_e += clock64() - c1_; }
+    if (p.dbg && warp == W_WORK0 && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 24] = (unsigned long long)cyc_c; p.dbg[(size_t)blockIdx.x * 32 + 25] = (unsigned long long)cyc_e; }
+    if (p.dbg && warp == W_WORK0 && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 19] = w_aempty; p.dbg[(size_t)blockIdx.x * 32 + 20] = w_tfull; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (threadIdx.x == 0) stamp(p, 12);
@@ -611,6 +663,7 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
   }
   FParams p;
   p.G = n; p.planes = planes; p.f16 = f16 ? 1 : 0; p.dbg = g_fdbg;
+  { static int flags = -1; if (flags < 0) { const char* e = getenv("B2A_FUSED_DBGFLAGS"); flags = e ? atoi(e) : 0; } p.dbg_flags = flags; }
   // heaviest problem first (cost per tile ~ taps * K chunks): sort indices
   int order[MAXG];
   double cost[MAXG];
@@ -680,8 +733,9 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
   p.a_plane = maxR * 128;
   p.w_stage = maxWst;
   p.tmem_stride = (int)(maxBN <= 32 ? 32 : maxBN <= 64 ? 64 : maxBN <= 128 ? 128 : 256);
+  const size_t DYN_SMEM_MAX = (size_t)227 * 1024 - ((sizeof(FParams) + 1023) & ~(size_t)1023);   // the kernel keeps a static shared copy of FParams
   const size_t fixed = (size_t)2 * p.a_plane * planes + STAGING + SACC + CTAB + 1024 /*align*/ + 512 /*barriers*/;
-  int wst = (int)(((size_t)227 * 1024 - fixed) / p.w_stage);
+  int wst = (int)((DYN_SMEM_MAX - fixed) / p.w_stage);   // the kernel keeps a static shared copy of FParams
   if (wst > 8) wst = 8;
   if (wst < 2) { b2a_set_error("b2a_conv1d_fused: shared memory cannot hold two weight stages (R %d, BN %d)", maxR, maxBN); return B2A_E_UNSUPPORTED; }
   p.wst = wst;
@@ -696,7 +750,14 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
     if (e) { b2a_set_error("b2a_conv1d_fused: cuTensorMapEncodeTiled failed (%d)", e); return B2A_E_CUDA; }
   }
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM_MAX) != cudaSuccess) {
+      cudaGetLastError();
+      b2a_set_error("b2a_conv1d_fused: cannot raise the dynamic shared-memory limit to %d bytes", (int)DYN_SMEM_MAX);
+      return B2A_E_CUDA;
+    }
+    attr = true;
+  }
   const int grid = tiles_total < nsm ? tiles_total : nsm;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;

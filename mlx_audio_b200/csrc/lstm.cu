@@ -47,25 +47,29 @@ lstm_bidir_kernel(const float* __restrict__ xproj, const float* __restrict__ wh,
     float xp_next = 0.f;                                            // prefetch next step's input projection
     if (half == 0 && step + 1 < T) xp_next = __ldg(xp_base + (int64_t)(dir == 0 ? t + 1 : t - 1) * 2 * 4 * LH);
     const float* hp = &hbuf[cur][half * 128];
-    float s0 = 0.f, s1 = 0.f;
+    // eight independent accumulators: the recurrence is a latency chain (16-deep FMA chains instead of 64-deep)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
 #pragma unroll
     for (int j = 0; j < 128; j += 8) {
       float4 a = *reinterpret_cast<const float4*>(hp + j);
       float4 e = *reinterpret_cast<const float4*>(hp + j + 4);
-      s0 = fmaf(w[j], a.x, s0); s0 = fmaf(w[j + 1], a.y, s0); s0 = fmaf(w[j + 2], a.z, s0); s0 = fmaf(w[j + 3], a.w, s0);
-      s1 = fmaf(w[j + 4], e.x, s1); s1 = fmaf(w[j + 5], e.y, s1); s1 = fmaf(w[j + 6], e.z, s1); s1 = fmaf(w[j + 7], e.w, s1);
+      s0 = fmaf(w[j], a.x, s0); s1 = fmaf(w[j + 1], a.y, s1); s2 = fmaf(w[j + 2], a.z, s2); s3 = fmaf(w[j + 3], a.w, s3);
+      s4 = fmaf(w[j + 4], e.x, s4); s5 = fmaf(w[j + 5], e.y, s5); s6 = fmaf(w[j + 6], e.z, s6); s7 = fmaf(w[j + 7], e.w, s7);
     }
-    float s = s0 + s1;
+    float s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (half == 0) gates[r] = s + xp_cur;
+    float* gbuf = gates + cur * (4 * UPC);                           // double-buffered: no second block barrier per step
+    if (half == 0) gbuf[r] = s + xp_cur;
     __syncthreads();
     if (tid < UPC) {
-      const float gi = 1.f / (1.f + expf(-gates[tid]));
-      const float gf = 1.f / (1.f + expf(-gates[UPC + tid]));
-      const float gg = tanhf(gates[2 * UPC + tid]);
-      const float go = 1.f / (1.f + expf(-gates[3 * UPC + tid]));
+      // sigmoid / tanh through the SFU exponential (abs error ~1e-7: far inside the 1e-4 stage tolerance); libm's expf / tanhf cost
+      // ~150 cycles each on the recurrence's critical path
+      const float gi = 1.f / (1.f + __expf(-gbuf[tid]));
+      const float gf = 1.f / (1.f + __expf(-gbuf[UPC + tid]));
+      const float gg = 1.f - 2.f / (1.f + __expf(2.f * gbuf[2 * UPC + tid]));
+      const float go = 1.f / (1.f + __expf(-gbuf[3 * UPC + tid]));
       c = fmaf(gf, c, gi * gg);
-      const float hval = go * tanhf(c);
+      const float hval = go * (1.f - 2.f / (1.f + __expf(2.f * c)));
       out[((int64_t)b * T + t) * out_ld + dir * LH + rank * UPC + tid] = hval;
 #pragma unroll
       for (int rr = 0; rr < NCTA; rr++) {
@@ -109,7 +113,7 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
   const int gate = r >> 5, unit = r & 31;
   const int grow = gate * LH + rank * UPC + unit;
   __shared__ __align__(16) float hbuf[2][LH];
-  __shared__ float gates[4 * UPC];
+  __shared__ float gates[2 * 4 * UPC];
   __shared__ __align__(8) uint64_t hbar[2];                         // hbar[i]: "hbuf[i] holds the complete h of a step"
 
   float w[128];
@@ -148,25 +152,29 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
     if (half == 0 && step + 1 < T) xp_next = __ldg(xp_base + (int64_t)(dir == 0 ? t + 1 : t - 1) * 2 * 4 * LH);
     if (step > 0) bar_wait_cluster(smem_addr(&hbar[cur]), ((step - 1) >> 1) & 1);     // h of step-1 complete in hbuf[cur]
     const float* hp = &hbuf[cur][half * 128];
-    float s0 = 0.f, s1 = 0.f;
+    // eight independent accumulators: the recurrence is a latency chain (16-deep FMA chains instead of 64-deep)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
 #pragma unroll
     for (int j = 0; j < 128; j += 8) {
       float4 a = *reinterpret_cast<const float4*>(hp + j);
       float4 e = *reinterpret_cast<const float4*>(hp + j + 4);
-      s0 = fmaf(w[j], a.x, s0); s0 = fmaf(w[j + 1], a.y, s0); s0 = fmaf(w[j + 2], a.z, s0); s0 = fmaf(w[j + 3], a.w, s0);
-      s1 = fmaf(w[j + 4], e.x, s1); s1 = fmaf(w[j + 5], e.y, s1); s1 = fmaf(w[j + 6], e.z, s1); s1 = fmaf(w[j + 7], e.w, s1);
+      s0 = fmaf(w[j], a.x, s0); s1 = fmaf(w[j + 1], a.y, s1); s2 = fmaf(w[j + 2], a.z, s2); s3 = fmaf(w[j + 3], a.w, s3);
+      s4 = fmaf(w[j + 4], e.x, s4); s5 = fmaf(w[j + 5], e.y, s5); s6 = fmaf(w[j + 6], e.z, s6); s7 = fmaf(w[j + 7], e.w, s7);
     }
-    float s = s0 + s1;
+    float s = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
     s += __shfl_xor_sync(0xffffffffu, s, 1);
-    if (half == 0) gates[r] = s + xp_cur;
+    float* gbuf = gates + cur * (4 * UPC);                           // double-buffered: no second block barrier per step
+    if (half == 0) gbuf[r] = s + xp_cur;
     __syncthreads();
     if (tid < UPC) {
-      const float gi = 1.f / (1.f + expf(-gates[tid]));
-      const float gf = 1.f / (1.f + expf(-gates[UPC + tid]));
-      const float gg = tanhf(gates[2 * UPC + tid]);
-      const float go = 1.f / (1.f + expf(-gates[3 * UPC + tid]));
+      // sigmoid / tanh through the SFU exponential (abs error ~1e-7: far inside the 1e-4 stage tolerance); libm's expf / tanhf cost
+      // ~150 cycles each on the recurrence's critical path
+      const float gi = 1.f / (1.f + __expf(-gbuf[tid]));
+      const float gf = 1.f / (1.f + __expf(-gbuf[UPC + tid]));
+      const float gg = 1.f - 2.f / (1.f + __expf(2.f * gbuf[2 * UPC + tid]));
+      const float go = 1.f / (1.f + __expf(-gbuf[3 * UPC + tid]));
       c = fmaf(gf, c, gi * gg);
-      const float hval = go * tanhf(c);
+      const float hval = go * (1.f - 2.f / (1.f + __expf(2.f * c)));
       out[((int64_t)b * T + t) * out_ld + dir * LH + rank * UPC + tid] = hval;
       const uint32_t off = (uint32_t)((nxt * LH + rank * UPC + tid) * 4);
       if (step + 1 < T) {                                           // the last step has no consumer: no store may outlive the CTA
@@ -174,8 +182,7 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
         for (int q = 0; q < NCTA; q++) st_async_f32(rh[q] + off, hval, rb[q] + (uint32_t)(nxt * 8));
       }
     }
-    xp_cur = xp_next;
-    __syncthreads();                                                // gates[] is rewritten next step
+    xp_cur = xp_next;                                               // gates[] of the next step live in the other half: no barrier here
   }
   cluster.sync();                                                   // nobody exits while remote stores may still target it
 }

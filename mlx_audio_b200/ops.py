@@ -225,7 +225,10 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
             lout = (L - 1) * stride + cw.K - 2 * pad_left
         else:
             lout = (L + 2 * pad_left - dilation * (cw.K - 1) - 1) // stride + 1
-    if emit is None and fused_eligible(x, cw, stride, dilation, transpose, pad_mode, out, res):
+    # Tiny GEMMs (a few rows: ALBERT at T = 130, decode-time prefills) are latency chains, not throughput problems: the fused kernel's
+    # converter -> MMA -> split-K fix-up chain measured 30-40 us per launch there against ~14 us for the pre-split planes + TMA pipeline.
+    small_gemm = SMALL_GEMM_SPLIT_PATH[0] and cw.K == 1 and B * L <= 256 and _tc_eligible(cw, L, stride, transpose, pad_mode, dilation)
+    if emit is None and not small_gemm and fused_eligible(x, cw, stride, dilation, transpose, pad_mode, out, res):
         y = conv_fused(FusedProblem(x, cw, stride=stride, dilation=dilation, pad_left=pad_left, lout=lout, pre=pre, post_act=post_act,
                                     post_p0=post_p0, cscale=cscale, res=res, res_div=res_div, out_scale=out_scale, out=out,
                                     accumulate=accumulate, transpose=transpose))[0]
@@ -343,6 +346,7 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
 # One launch per layer (or per GROUP of independent layers): InstanceNorm / AdaIN coefficients from the producer's (sum, sumsq), the
 # input activation, the 16-bit hi/lo split, the tap-summed GEMM, the epilogue and the output's (sum, sumsq) -- csrc/conv_fused.cu.
 FUSED = [os.environ.get("B2A_FUSED", "1") != "0"]
+SMALL_GEMM_SPLIT_PATH = [os.environ.get("B2A_SMALL_GEMM_SPLIT", "1") != "0"]
 FUSED_WS_BYTES = 16 << 20
 _FUSED_WS = {}
 
