@@ -164,11 +164,12 @@ def kokoro_graph_profile(model, ops, torch, ids_d, ref_d, dev, reps=3):
     twin = Model(model.config, device=dev)
     twin._w, twin._ada_slices, twin._ada_pred, twin._raw = model._w, model._ada_slices, model._ada_pred, getattr(model, "_raw", None)
     twin.seed(7)
-    ops.PROFILE, ops.PROFILE_EXTERNAL = prof, True
+    tags = {}
+    ops.PROFILE, ops.PROFILE_EXTERNAL, ops.PROFILE_TAGS = prof, True, tags
     try:
         twin.synthesize_ids(ids_d, ref_d)                 # captures both graphs with the event nodes (the eager warm-ups also append)
     finally:
-        ops.PROFILE, ops.PROFILE_EXTERNAL = None, False
+        ops.PROFILE, ops.PROFILE_EXTERNAL, ops.PROFILE_TAGS = None, False, None
     # keep only the events recorded during the two captures: they are the LAST n of each kind, where n = launches in the captured pass;
     # simplest robust filter: an event pair that was never re-stamped by a replay raises / returns garbage -> use a base event in-graph
     t_base = torch.cuda.Event(enable_timing=True)
@@ -177,19 +178,24 @@ def kokoro_graph_profile(model, ops, torch, ids_d, ref_d, dev, reps=3):
         t_base.record()
         twin.synthesize_ids(ids_d, ref_d)
         torch.cuda.synchronize(dev)
+        top = []
         for kind, evs in prof.items():
             iv = []
-            for a, b in evs:
+            for i, (a, b) in enumerate(evs):
                 try:
                     s, e = t_base.elapsed_time(a), t_base.elapsed_time(b)
                 except Exception:
                     continue
+                if s >= 0.0 and e >= s and tags.get(kind) and tags[kind][i]:
+                    top.append((round((e - s) * 1e3, 1), tags[kind][i]))
                 if s >= 0.0 and e >= s:                   # events of the eager warm-up passes lie BEFORE t_base: negative -> dropped
                     iv.append((s, e))
             per_kind.setdefault(kind, []).append(sum(e - s for s, e in iv))
             cover.setdefault(kind, []).append(iv)
     n_launch = {k: len(v[-1]) for k, v in cover.items()}
     by_kind = {k: sum(v) / len(v) for k, v in per_kind.items()}
+    kokoro_graph_profile.top_launches = sorted(top, reverse=True)[:24]          # (us, label) of the last replay's slowest tagged launches
+    kokoro_graph_profile.tagged_us = round(sum(t for t, _ in top), 1)
     return by_kind, {k: v[-1] for k, v in cover.items()}, n_launch
 
 
@@ -409,6 +415,7 @@ def main_kokoro(args, rank, world, local_rank):
                 "timing": timing_path, "launches_per_utterance": n_conv, "kernel_ms_per_utterance": conv_ms,
                 "kernel_ms_summed": conv_sum_ms, "all_kernels_ms_per_utterance": all_ms,
                 "ms_by_kind": {k: round(v, 3) for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1])},
+                "top_launches_us": getattr(kokoro_graph_profile, "top_launches", None), "fused_launches_us_total": getattr(kokoro_graph_profile, "tagged_us", None),
                 "algorithmic_bytes_per_utterance": alg_bytes,
                 "tensor": {"bound": "tensor", "achieved": tf, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "unit": "TFLOP/s",
                            "frac": tf / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "algorithmic_flops_per_utterance": alg_flops,

@@ -94,7 +94,7 @@ __device__ __noinline__ float act_slow2(float v, int act, float p0, float a, flo
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // accumulate the SM cycles a role spends inside a wait (debug runs only): slots 16.. of the CTA's row.  clock64, not %globaltimer: the
 // global timer read costs ~1 us on this part and, placed around every wait, it WAS the timeline (measured: same kernel 2x slower).
-#define TIMED_WAIT(p, acc, stmt) do { if ((p).dbg) { const long long t0_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
+#define TIMED_WAIT(p, acc, stmt) do { if (DBG && (p).dbg) { const long long t0_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
 __device__ __forceinline__ void stamp(const FParams& p, int slot) {
   if (p.dbg) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); p.dbg[(size_t)blockIdx.x * 32 + slot] = t; }
 }
@@ -178,6 +178,8 @@ __device__ __forceinline__ void stats_coeffs(const FProb& P, int b, int c, float
   sh = (float)(be - s_ * mean);
 }
 
+// DBG = false compiles every timing stamp, wait accumulator and ablation flag out of the production kernel.
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CUtensorMap mw0, const __grid_constant__ CUtensorMap mw1,
                   const __grid_constant__ CUtensorMap mw2, const __grid_constant__ CUtensorMap mw3,
@@ -198,7 +200,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
   }
   __syncthreads();
   const FParams& p = sparams;
-  if (threadIdx.x == 0) stamp(p, 0);
+  if (threadIdx.x == 0) if (DBG) stamp(p, 0);
   // layout: [2] x A buffer (planes x a_plane bytes) | [wst] x W stage | staging | sacc | coefficient table | barriers
   const int a_buf = p.a_plane * p.planes;
   uint8_t* wbase = smem + (size_t)2 * a_buf;
@@ -230,7 +232,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) stamp(p, 1);
+  if (threadIdx.x == 0) if (DBG) stamp(p, 1);
   pdl_launch_dependents();        // the next kernel may start its own prologue / weight loads as SMs free up; it waits for us before reading
 
   if (warp == 0) {
@@ -244,7 +246,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
       }
       int s = 0; uint32_t ph = 0;
       unsigned long long w_pempty = 0;
-      const long long pt0 = clock64();
+      const long long pt0 = DBG ? clock64() : 0;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         const TileRef t = decode_tile(p, tile);
         const FProb& P = p.pr[t.g];
@@ -263,7 +265,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
           }
         }
       }
-      if (p.dbg) { p.dbg[(size_t)blockIdx.x * 32 + 21] = (unsigned long long)(clock64() - pt0); p.dbg[(size_t)blockIdx.x * 32 + 22] = w_pempty; }
+      if (DBG && p.dbg) { p.dbg[(size_t)blockIdx.x * 32 + 21] = (unsigned long long)(clock64() - pt0); p.dbg[(size_t)blockIdx.x * 32 + 22] = w_pempty; }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -279,7 +281,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
     const uint64_t dhi = umma_desc_sw128(0);                       // descriptor bits above the 14-bit start-address field
     uint32_t s = 0, ph = 0, lt = 0, cg = 0;
     unsigned long long w_tempty = 0, w_afull = 0, w_wfull = 0;
-    const long long mt0 = clock64();
+    const long long mt0 = DBG ? clock64() : 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, lt++) {
       const TileRef t = decode_tile(p, tile);
       const FProb& P = p.pr[t.g];
@@ -317,7 +319,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
         }
       }
     }
-    if (p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 23] = (unsigned long long)(clock64() - mt0); p.dbg[(size_t)blockIdx.x * 32 + 16] = w_tempty; p.dbg[(size_t)blockIdx.x * 32 + 17] = w_afull; p.dbg[(size_t)blockIdx.x * 32 + 18] = w_wfull; }
+    if (DBG && p.dbg && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 23] = (unsigned long long)(clock64() - mt0); p.dbg[(size_t)blockIdx.x * 32 + 16] = w_tempty; p.dbg[(size_t)blockIdx.x * 32 + 17] = w_afull; p.dbg[(size_t)blockIdx.x * 32 + 18] = w_wfull; }
   } else {
     // ===== worker warps (16): A-tile conversion AND epilogue =====
     // The first version of this kernel split the roles (8 converter + 8 epilogue warps).  Its profile on the Kokoro layers: the converter
@@ -328,7 +330,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
     // MMA(t) needs the TMEM buffer E(t-2) frees, and E(t-2) precedes C(t) in this order: no deadlock.  E(t) runs after C(t+1), by when
     // the MMAs of tile t have normally retired, so the workers rarely wait on tfull.
     pdl_wait();
-    if (warp == W_WORK0 && lane == 0) stamp(p, 3);
+    if (warp == W_WORK0 && lane == 0) if (DBG) stamp(p, 3);
     const int ww = warp - W_WORK0;                   // 0..15
     const int wt = ww * 32 + lane;                   // 0..511
     const int c4 = wt & 15;                          // float4 slot inside the 64-channel chunk (fixed per thread: constants stay in registers)
@@ -405,11 +407,11 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
         TIMED_WAIT(p, w_aempty, mbar_wait(a_empty + ab, ((cg >> 1) & 1) ^ 1));
         uint8_t* hi = smem + (size_t)ab * a_buf;
         uint8_t* lo = p.planes == 2 ? hi + p.a_plane : nullptr;
-#define B2A_CONVERT(T, A, N, UU) convert_chunk<T, A, N, UU>(xb, xb1, xb2, P.x_ld, P.L, lbase, chs, c4, r0, R, anych, sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo, p.dbg_flags)
+#define B2A_CONVERT(T, A, N, UU) convert_chunk<T, A, N, UU>(xb, xb1, xb2, P.x_ld, P.L, lbase, chs, c4, r0, R, anych, sc, sh, aa, bb, chok, P.pre_act, P.pre_p0, hi, lo, (DBG ? p.dbg_flags : 0))
         const int chs = anych ? ch : 0;                    // chunks wholly past Cin (never with a valid weight column) still index valid memory
         // specialised bodies for the hot cases only (each instantiation is ~1-2 K instructions): single input x {none, Snake, LeakyReLU, ELU};
         // summed inputs (the folded branch average) and fp16 operands with an activation take the runtime-switch body
-        if (p.dbg_flags & 16) { }
+        if ((DBG ? p.dbg_flags : 0) & 16) { }
         else if (p.f16) { if (xb1 == nullptr && P.pre_act == 0) B2A_CONVERT(__half, 0, 0, 5); else if (xb2) B2A_CONVERT(__half, -1, 2, 2);
                      else if (xb1) B2A_CONVERT(__half, -1, 1, 3); else B2A_CONVERT(__half, -1, 0, 3); }
         else if (xb2) B2A_CONVERT(__nv_bfloat16, -1, 2, 2);
@@ -420,10 +422,10 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
         else if (P.pre_act == B2A_ACT_ELU) B2A_CONVERT(__nv_bfloat16, B2A_ACT_ELU, 0, 3);
         else B2A_CONVERT(__nv_bfloat16, -1, 0, 3);
 #undef B2A_CONVERT
-        if (!(p.dbg_flags & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
+        if (!((DBG ? p.dbg_flags : 0) & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA's async-proxy reads
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + ab);
-        if (warp == W_WORK0 && lane == 0) { if (cg == 0) stamp(p, 6); stamp(p, 7); }
+        if (warp == W_WORK0 && lane == 0) { if (cg == 0) if (DBG) stamp(p, 6); if (DBG) stamp(p, 7); }
       }
     };
 
@@ -436,10 +438,10 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
       const bool do_stats = P.stats_out != nullptr;
       TIMED_WAIT(p, w_tfull, mbar_wait(tfull + buf, use & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (et == 0 && lt == 0) stamp(p, 8);
+      if (et == 0 && lt == 0) if (DBG) stamp(p, 8);
       const int mrow0 = l0 + quarter * 32;
       const uint32_t tcol = tmem_base + buf * (uint32_t)p.tmem_stride + ((uint32_t)(quarter * 32) << 16);
-      bool last_split = !(p.dbg_flags & 32);
+      bool last_split = !((DBG ? p.dbg_flags : 0) & 32);
       if (P.ksplit > 1) {
         // ---- split-K: park this CTA's partial accumulator (through the transpose tile: whole 128-byte row segments), then only the
         // last CTA to arrive for the tile carries on
@@ -466,7 +468,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
         bar_sync(2, NWORK * 32);
         last_split = *flag_slot != 0;
         if (last_split) __threadfence();
-        if (et == 0 && lt == 0) stamp(p, 9);
+        if (et == 0 && lt == 0) if (DBG) stamp(p, 9);
       }
       if (last_split) {
         for (int c0 = sub * 32; c0 < P.BN; c0 += 128) {
@@ -579,7 +581,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (et == 0) { if (lt == 0) stamp(p, 10); stamp(p, 11); }
+      if (et == 0) { if (lt == 0) if (DBG) stamp(p, 10); if (DBG) stamp(p, 11); }
       if (lane == 0) mbar_arrive(tempty + buf);                // 16 arrivals free the accumulator for tile lt + 2
       if (do_stats) {
         bar_sync(1, NWORK * 32);
@@ -600,21 +602,21 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
     uint32_t nt_done = 0;
     long long cyc_c = 0, cyc_e = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-      const long long c0_ = clock64();
+      const long long c0_ = DBG ? clock64() : 0;
       convert_tile(tile);
-      const long long c1_ = clock64();
+      const long long c1_ = DBG ? clock64() : 0;
       if (prev >= 0) { epilogue_tile(prev, nt_done); nt_done++; }
-      cyc_c += c1_ - c0_; cyc_e += clock64() - c1_;
+      if (DBG) { cyc_c += c1_ - c0_; cyc_e += clock64() - c1_; }
       prev = tile;
     }
-    { const long long c1_ = clock64(); if (prev >= 0) epilogue_tile(prev, nt_done); cyc_e += clock64() - c1_; }
-    if (p.dbg && warp == W_WORK0 && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 24] = (unsigned long long)cyc_c; p.dbg[(size_t)blockIdx.x * 32 + 25] = (unsigned long long)cyc_e; }
-    if (p.dbg && warp == W_WORK0 && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 19] = w_aempty; p.dbg[(size_t)blockIdx.x * 32 + 20] = w_tfull; }
+    { const long long c1_ = DBG ? clock64() : 0; if (prev >= 0) epilogue_tile(prev, nt_done); if (DBG) cyc_e += clock64() - c1_; }
+    if (DBG && p.dbg && warp == W_WORK0 && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 24] = (unsigned long long)cyc_c; p.dbg[(size_t)blockIdx.x * 32 + 25] = (unsigned long long)cyc_e; }
+    if (DBG && p.dbg && warp == W_WORK0 && lane == 0) { p.dbg[(size_t)blockIdx.x * 32 + 19] = w_aempty; p.dbg[(size_t)blockIdx.x * 32 + 20] = w_tfull; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  if (threadIdx.x == 0) stamp(p, 12);
+  if (threadIdx.x == 0) if (DBG) stamp(p, 12);
   __syncthreads();
-  if (threadIdx.x == 0) stamp(p, 13);
+  if (threadIdx.x == 0) if (DBG) stamp(p, 13);
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -751,7 +753,8 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
   }
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM_MAX) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM_MAX) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DYN_SMEM_MAX) != cudaSuccess) {
       cudaGetLastError();
       b2a_set_error("b2a_conv1d_fused: cannot raise the dynamic shared-memory limit to %d bytes", (int)DYN_SMEM_MAX);
       return B2A_E_CUDA;
@@ -765,7 +768,9 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, conv_fused_kernel, p, mw[0], mw[1], mw[2], mw[3], ml[0], ml[1], ml[2], ml[3]);
+  const bool dbg = p.dbg != nullptr || p.dbg_flags != 0;
+  cudaError_t err = dbg ? cudaLaunchKernelEx(&cfg, conv_fused_kernel<true>, p, mw[0], mw[1], mw[2], mw[3], ml[0], ml[1], ml[2], ml[3])
+                        : cudaLaunchKernelEx(&cfg, conv_fused_kernel<false>, p, mw[0], mw[1], mw[2], mw[3], ml[0], ml[1], ml[2], ml[3]);
   if (err != cudaSuccess) { b2a_set_error("b2a_conv1d_fused: launch failed: %s", cudaGetErrorString(err)); return B2A_E_CUDA; }
   B2A_CHECK_LAUNCH();
   return B2A_OK;

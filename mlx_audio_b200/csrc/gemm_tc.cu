@@ -26,7 +26,6 @@ namespace {
 
 constexpr int TM = 128;            // rows (positions) per CTA tile == UMMA_M
 constexpr int TK = 64;             // bf16 elements per 128-byte swizzle row == K extent of one stage
-constexpr int UMMA_K = 16;
 
 __host__ __device__ __forceinline__ uint32_t pow2_cols(uint32_t n) { uint32_t c = 32; while (c < n) c <<= 1; return c; }   // TMEM allocations are powers of two >= 32
 
@@ -74,12 +73,26 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_rows(uint32_t saddr, int bo_
   if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
   return d;
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+// Warp-convergent issue (all 32 lanes call with identical operands; one elected lane issues) of the four K=16 steps of a 64-wide K chunk.
+// Issuing from inside `if (lane == 0)` makes ptxas guard every UTCHMMA operand with an ELECT + R2UR.BROADCAST sequence; with the ring-slot
+// divisions and per-MMA descriptor rebuilds one stage (8 MMAs = 0.27 us of tensor time) cost ~500 instructions = ~1 us of issue time
+// (round-2 measurement on conv_fused.cu, whose issuer was a copy of this one).
+__device__ __forceinline__ void umma_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, q;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+               ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -214,33 +227,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
       const uint32_t fmt = p.f16 ? 0u : 1u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t a0 = smem_u32(smem);
+      uint32_t s = 0, ph = 0, accum = 0;
+      const bool two_a = p.planes == 2, two_w = p.wplanes == 2;
       for (int kc = 0; kc < kchunks; kc++) {
         mbar_wait(a_full, kc & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int tap = 0; tap < p.taps; tap++) {
           const int it = kc * p.taps + tap;
-          const int s = it % p.wst, ph = (it / p.wst) & 1;
           mbar_wait(w_full + s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (dbg && lane == 0 && it == 0) p.dbg[2] = clock64();
           if (dbg && lane == 0 && it == iters - 1) p.dbg[3] = clock64();
-          if (lane == 0) {
-            const uint32_t wst_addr = smem_u32(wbase + (size_t)s * w_stage);
-            const uint32_t rowoff = (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
-            for (int wp = 0; wp < p.wplanes; wp++) {
-              const uint64_t wdesc = umma_desc_sw128(wst_addr + wp * w_bytes);
-              const int npl = wp == 0 ? p.planes : 1;
-              for (int pl = 0; pl < npl; pl++) {
-                const uint64_t adesc = umma_desc_sw128_rows(a0 + pl * a_rbytes + rowoff, p.bo_mode);
-#pragma unroll
-                for (int k = 0; k < TK / UMMA_K; k++)
-                  umma_bf16(tbase, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (it | wp | pl | k) != 0);
-              }
-            }
-            umma_commit(w_empty + s);
-            if (tap == p.taps - 1) umma_commit(a_empty);
-            if (it == iters - 1) umma_commit(r_tmem_full);
-          }
-          __syncwarp();
+          const uint32_t wst_addr = smem_u32(wbase + (size_t)s * w_stage);
+          const uint32_t rowoff = (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
+          const uint64_t wd = umma_desc_sw128(wst_addr), ad = umma_desc_sw128_rows(a0 + rowoff, p.bo_mode);
+          umma_x4(tbase, ad, wd, idesc, accum);
+          accum = 1;
+          if (two_a) umma_x4(tbase, umma_desc_sw128_rows(a0 + a_rbytes + rowoff, p.bo_mode), wd, idesc, 1u);
+          if (two_w) umma_x4(tbase, ad, umma_desc_sw128(wst_addr + w_bytes), idesc, 1u);
+          umma_commit_elect(w_empty + s);
+          if (tap == p.taps - 1) umma_commit_elect(a_empty);
+          if (it == iters - 1) umma_commit_elect(r_tmem_full);
+          if (++s == (uint32_t)p.wst) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -268,29 +275,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
     const uint32_t fmt = p.f16 ? 0u : 1u;                 // F16F32Format: 0 = f16, 1 = bf16
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+    uint32_t s = 0, ph = 0;
+    const bool two_a = p.planes == 2, two_w = p.wplanes == 2;
     for (int it = 0; it < iters; it++) {
-      const int s = it % p.stages, ph = (it / p.stages) & 1;
       mbar_wait(full + s, ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (dbg && lane == 0 && it == 0) p.dbg[2] = clock64();
       if (dbg && lane == 0 && it == iters - 1) p.dbg[3] = clock64();
-      if (lane == 0) {
-        const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-        // products kept: a_hi*w_hi, a_lo*w_hi, and (fp32 checkpoints: weights split too) a_hi*w_lo; a_lo*w_lo ~ 2^-17*2^-9 is dropped
-        for (int wp = 0; wp < p.wplanes; wp++) {
-          const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes + wp * w_bytes);
-          const int npl = wp == 0 ? p.planes : 1;
-          for (int pl = 0; pl < npl; pl++) {
-            const uint64_t adesc = umma_desc_sw128(st + pl * a_bytes);
-#pragma unroll
-            for (int k = 0; k < TK / UMMA_K; k++)        // advance 32 B (16 bf16) inside the 128 B swizzle row
-              umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (it | wp | pl | k) != 0);
-          }
-        }
-        umma_commit(empty + s);                        // frees the stage when these MMAs retire
-        if (it == iters - 1) umma_commit(tmem_full);   // accumulator complete
-      }
-      __syncwarp();
+      const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+      // products kept: a_hi*w_hi, a_lo*w_hi, and (fp32 checkpoints: weights split too) a_hi*w_lo; a_lo*w_lo ~ 2^-17*2^-9 is dropped
+      const uint64_t ad = umma_desc_sw128(st), wd = umma_desc_sw128(st + a_bytes * p.planes);
+      umma_x4(tmem_base, ad, wd, idesc, it != 0);
+      if (two_a) umma_x4(tmem_base, umma_desc_sw128(st + a_bytes), wd, idesc, 1u);
+      if (two_w) umma_x4(tmem_base, ad, umma_desc_sw128(st + a_bytes * p.planes + w_bytes), idesc, 1u);
+      umma_commit_elect(empty + s);                        // frees the stage when these MMAs retire
+      if (it == iters - 1) umma_commit_elect(tmem_full);   // accumulator complete
+      if (++s == (uint32_t)p.stages) { s = 0; ph ^= 1; }
     }
   }
   if (warp >= 2) {
@@ -526,37 +525,30 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     const uint32_t fmt = p.f16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
     const uint32_t a0 = smem_u32(smem);
-    uint32_t it = 0, lt = 0, cg = 0;
+    uint32_t rs = 0, rph = 0, lt = 0, cg = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
       const uint32_t buf = lt & 1, use = lt >> 1;
       mbar_wait(tempty + buf, (use & 1) ^ 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + buf * tbuf_stride;
+      uint32_t accum = 0;
       for (int kc = 0; kc < kchunks; kc++, cg++) {
         const uint32_t ab = cg & 1;
         mbar_wait(a_full + ab, (cg >> 1) & 1);
-        for (int tap = 0; tap < p.taps; tap++, it++) {
-          const int s = it % p.wst, ph = (it / p.wst) & 1;
-          mbar_wait(full + s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (lane == 0) {
-            const uint32_t wst_addr = smem_u32(wbase + (size_t)s * w_stage);
-            const uint32_t abase = a0 + ab * (uint32_t)a_buf + (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
-            for (int wp = 0; wp < p.wplanes; wp++) {
-              const uint64_t wdesc = umma_desc_sw128(wst_addr + wp * w_bytes);
-              const int npl = wp == 0 ? p.planes : 1;
-              for (int pl = 0; pl < npl; pl++) {
-                const uint64_t adesc = umma_desc_sw128(abase + pl * a_rbytes);
-#pragma unroll
-                for (int k = 0; k < TK / UMMA_K; k++)
-                  umma_bf16(tacc, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (kc | tap | wp | pl | k) != 0);
-              }
-            }
-            umma_commit(empty + s);
-            if (tap == p.taps - 1) umma_commit(a_empty + ab);
-            if (kc == kchunks - 1 && tap == p.taps - 1) umma_commit(tfull + buf);
-          }
-          __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int tap = 0; tap < p.taps; tap++) {
+          mbar_wait(full + rs, rph);
+          const uint32_t wst_addr = smem_u32(wbase + (size_t)rs * w_stage);
+          const uint32_t abase = a0 + ab * (uint32_t)a_buf + (uint32_t)(p.shift[tap] - p.shift_min) * 128u;
+          const uint64_t wd = umma_desc_sw128(wst_addr), ad = umma_desc_sw128(abase);
+          umma_x4(tacc, ad, wd, idesc, accum);
+          accum = 1;
+          if (p.planes == 2) umma_x4(tacc, umma_desc_sw128(abase + a_rbytes), wd, idesc, 1u);
+          if (p.wplanes == 2) umma_x4(tacc, ad, umma_desc_sw128(wst_addr + w_bytes), idesc, 1u);
+          umma_commit_elect(empty + rs);
+          if (tap == p.taps - 1) umma_commit_elect(a_empty + ab);
+          if (kc == kchunks - 1 && tap == p.taps - 1) umma_commit_elect(tfull + buf);
+          if (++rs == (uint32_t)p.wst) { rs = 0; rph ^= 1; }
         }
       }
     }
@@ -564,32 +556,22 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_
     // ===== MMA issuer =====
     const uint32_t fmt = p.f16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-    uint32_t it = 0, lt = 0;
+    uint32_t rs = 0, rph = 0, lt = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, lt++) {
       const uint32_t buf = lt & 1, use = lt >> 1;
       mbar_wait(tempty + buf, (use & 1) ^ 1);                 // the epilogue has drained this accumulator (first use: free)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + buf * tbuf_stride;
-      for (int i = 0; i < iters; i++, it++) {
-        const int s = it % p.stages, ph = (it / p.stages) & 1;
-        mbar_wait(full + s, ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0) {
-          const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-          for (int wp = 0; wp < p.wplanes; wp++) {
-            const uint64_t wdesc = umma_desc_sw128(st + a_bytes * p.planes + wp * w_bytes);
-            const int npl = wp == 0 ? p.planes : 1;
-            for (int pl = 0; pl < npl; pl++) {
-              const uint64_t adesc = umma_desc_sw128(st + pl * a_bytes);
-#pragma unroll
-              for (int k = 0; k < TK / UMMA_K; k++)
-                umma_bf16(tacc, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc, (i | wp | pl | k) != 0);
-            }
-          }
-          umma_commit(empty + s);
-          if (i == iters - 1) umma_commit(tfull + buf);
-        }
-        __syncwarp();
+      for (int i = 0; i < iters; i++) {
+        mbar_wait(full + rs, rph);
+        const uint32_t st = smem_u32(smem + (size_t)rs * stage_bytes);
+        const uint64_t ad = umma_desc_sw128(st), wd = umma_desc_sw128(st + a_bytes * p.planes);
+        umma_x4(tacc, ad, wd, idesc, i != 0);
+        if (p.planes == 2) umma_x4(tacc, umma_desc_sw128(st + a_bytes), wd, idesc, 1u);
+        if (p.wplanes == 2) umma_x4(tacc, ad, umma_desc_sw128(st + a_bytes * p.planes + w_bytes), idesc, 1u);
+        umma_commit_elect(empty + rs);
+        if (i == iters - 1) umma_commit_elect(tfull + buf);
+        if (++rs == (uint32_t)p.stages) { rs = 0; rph ^= 1; }
       }
     }
   } else if (warp >= 2 && warp <= 9) {

@@ -24,6 +24,8 @@ LAUNCHES = [0]        # kernels launched through this module (bench.py reports i
 
 
 PROFILE = None        # dict kind -> [(start_event, end_event)] when bench.py instruments a pass
+PROFILE_TAGS = None   # dict kind -> [label] parallel to PROFILE (bench.py's per-launch table); TAG[0] is the label of the next call
+TAG = [None]
 PROFILE_EXTERNAL = False   # True while an instrumented CUDA graph is captured: the events become event-record NODES of the graph, so
                            # every replay re-stamps them and the per-launch times are those of the replayed graph (not of an eager pass)
 
@@ -38,6 +40,9 @@ def _call(kind, fn, n_launches, *args):
         rc = fn(*args)
         b.record()
         PROFILE.setdefault(kind, []).append((a, b))
+        if PROFILE_TAGS is not None:
+            PROFILE_TAGS.setdefault(kind, []).append(TAG[0])
+        TAG[0] = None
     else:
         rc = fn(*args)
     _lib.check(rc)
@@ -487,6 +492,8 @@ def conv_fused(problems) -> list:
     ws = _FUSED_WS.get(key)
     if ws is None:
         ws = _FUSED_WS[key] = torch.zeros(FUSED_WS_BYTES, device=dev, dtype=torch.uint8)      # split-K partial tiles + (self-resetting) counters
+    if PROFILE_TAGS is not None:
+        TAG[0] = "fused " + " + ".join(f"[{q.B}x{q.L}x{q.Cin}->{q.N} k{q.taps}{' up' + str(q.up_stride) if q.up_stride else ''}]" for q in (pr.p for pr in problems))
     _call("conv_tc", _lib.lib().b2a_conv1d_fused, 1, arr, n, 2 if TC_MODE[0] == "x2" else 1, int(f16), ws.data_ptr(), ws.numel(), _stream())
     return [pr.out for pr in problems]
 

@@ -69,27 +69,48 @@ def test_mimi_reference_length_pin_and_prefix_causality(mimi):
     y = model.decode(codes)
     assert y.shape == (1, 1, 120960)
     y2 = model.decode(codes[:, :, :40])
-    assert torch.allclose(y2, y[:, :, : 40 * 1920], atol=1e-5, rtol=1e-4)
+    # the fused conv kernel splits K across CTAs when a layer has few output tiles, and how many ways depends on the length: the two decodes
+    # add the same fp32 partial products in a different order (measured 4e-5 on a 5.9 full scale)
+    assert torch.allclose(y2, y[:, :, : 40 * 1920], atol=3e-4, rtol=1e-4)
+    from mlx_audio_b200 import ops
+    ops.FUSED[0] = False                               # without split-K the prefix property is exact
+    try:
+        assert torch.equal(model.decode(codes[:, :, :40]), model.decode(codes)[:, :, : 40 * 1920])
+    finally:
+        ops.FUSED[0] = True
 
 
 @pytest.mark.parametrize("parts", [2, 3])
 def test_snac_span_decodes_stitch_to_the_one_shot_decode(snac, parts):
     """SURVEY.md section 8e (config 5): one stream sharded by contiguous frame spans with a 16-frame halo per side; the per-channel
-    NoiseBlock draws are shared.  The stitched waveform equals the one-shot decode (different tile positions only: <= 1e-5 of full scale)."""
+    NoiseBlock draws are shared.  The stitched waveform equals the one-shot decode: bit for bit on the kernels without split-K; with the
+    fused kernel's length-dependent split-K factor the same fp32 partial products are added in a different order, which four Snake stages
+    amplify to 2-4e-4 of full scale (measured)."""
+    from mlx_audio_b200 import ops
     from mlx_audio_b200.parallel import shard_span
     model, _ = snac
     T = 236
     codes = synth.snac_codes(OC.SNAC_24K, T)
     noises = synth.snac_noises(OC.SNAC_24K)
-    full = model.decode(codes, noises=noises)
-    pieces = []
-    for r in range(parts):
-        _, _, cs, ce = shard_span(T, r, parts, multiple=max(model.vq_strides))
-        if ce > cs:
-            pieces.append(model.decode_span(codes, cs, ce, noises=noises))
-    got = torch.cat(pieces, dim=1)
+
+    def both():
+        full = model.decode(codes, noises=noises)
+        pieces = []
+        for r in range(parts):
+            _, _, cs, ce = shard_span(T, r, parts, multiple=max(model.vq_strides))
+            if ce > cs:
+                pieces.append(model.decode_span(codes, cs, ce, noises=noises))
+        return torch.cat(pieces, dim=1), full
+
+    got, full = both()
     assert got.shape == full.shape == (1, 120907, 1)
-    assert float((got - full).abs().max()) <= 1e-5
+    assert float((got - full).abs().max()) <= 1.5e-3
+    ops.FUSED[0] = False
+    try:
+        got, full = both()
+        assert torch.equal(got, full)
+    finally:
+        ops.FUSED[0] = True
     with pytest.raises(ValueError):
         model.decode_span(codes, 2, 40, noises=noises)
 
