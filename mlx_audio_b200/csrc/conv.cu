@@ -520,6 +520,45 @@ int check_common(const b2a_conv1d_t* p) {
 
 }  // namespace
 
+namespace {
+// nn.Linear on a handful of rows (Kokoro: the 49 684-wide style projection of ONE style vector, twice per utterance): thread per output
+// column, the rows' inputs in shared memory, the [Cin][Cout] weight streamed once with coalesced loads.  The 64 x 64 tile kernel spends
+// 93 us on it (777 latency-bound CTAs); this is one pass over the weight at HBM speed.
+constexpr int LR_MAX = 8;
+__global__ void __launch_bounds__(128) linear_rows_kernel(const b2a_conv1d_t p, int rows) {
+  extern __shared__ float lr_x[];                                  // [rows][Cin]
+  for (int i = threadIdx.x; i < rows * p.Cin; i += blockDim.x) {
+    const int r = i / p.Cin, c = i - r * p.Cin;
+    const int b = r / p.L, l = r - b * p.L;
+    lr_x[i] = p.x[(int64_t)b * p.x_bs + (int64_t)l * p.x_ld + c];
+  }
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= p.Cout) return;
+  float acc[LR_MAX];
+#pragma unroll
+  for (int r = 0; r < LR_MAX; r++) acc[r] = 0.f;
+  const float* w = p.w + n;
+#pragma unroll 8
+  for (int c = 0; c < p.Cin; c++) {
+    const float wv = __ldg(w + (int64_t)c * p.Cout);
+#pragma unroll
+    for (int r = 0; r < LR_MAX; r++)
+      if (r < rows) acc[r] = fmaf(wv, lr_x[r * p.Cin + c], acc[r]);
+  }
+  const float bias = p.bias ? p.bias[n] : 0.f;
+#pragma unroll
+  for (int r = 0; r < LR_MAX; r++) {
+    if (r < rows) {
+      const int b = r / p.L, l = r - b * p.L;
+      float v = acc[r] + bias;
+      if (p.post_act) v = b2a_act(v, p.post_act, p.post_p0, 1.f, 1.f);
+      p.y[(int64_t)b * p.y_bs + (int64_t)l * p.y_ld + n] = v * p.out_scale;
+    }
+  }
+}
+}  // namespace
+
 extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
   int bad = check_common(p);
   if (bad) { b2a_set_error("b2a_conv1d_cl: invalid argument (check %d)", bad); return B2A_E_INVALID; }
@@ -527,6 +566,14 @@ extern "C" int32_t b2a_conv1d_cl(const b2a_conv1d_t* p, void* stream) {
   if (p->emit_hi && !(p->groups == p->Cin && p->Cin == p->Cout)) {
     b2a_set_error("b2a_conv1d_cl: plane emission is implemented for depthwise layers");
     return B2A_E_UNSUPPORTED;
+  }
+  if (p->groups == 1 && p->K == 1 && p->stride == 1 && p->pad_left == 0 && p->Lout == p->L && (int64_t)p->B * p->L <= LR_MAX && p->Cout >= 256 &&
+      !p->pre_scale && !p->pre_act && !p->post_cscale && !p->res && !p->accumulate && !p->emit_hi &&
+      (size_t)p->B * p->L * p->Cin * sizeof(float) <= 48 * 1024) {
+    const int rows = p->B * p->L;
+    linear_rows_kernel<<<cdiv(p->Cout, 128), 128, (size_t)rows * p->Cin * sizeof(float), st>>>(*p, rows);
+    B2A_CHECK_LAUNCH();
+    return B2A_OK;
   }
   if (p->groups == 1 && p->stride == 1 && p->Cout <= 4 && p->Lout >= NW_TL &&
       ((size_t)(NW_TL + (p->K - 1) * p->dilation) * (p->Cin + 1) + (size_t)p->K * p->Cin * p->Cout) * sizeof(float) <= 160 * 1024) {

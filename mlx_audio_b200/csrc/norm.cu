@@ -120,6 +120,66 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int64_t x_ld, cons
   }
 }
 
+// Same operator with the row held in registers: one warp per row, float4 loads all issued before the first use (the three-pass scalar
+// version above is three dependent chains of C/32 L2 round trips: 16 us per launch for ALBERT's 130 x 768 rows, 0.5 ms per utterance).
+// NV = float4 slots per lane (C <= 128 * NV); rows and all row strides 16-byte aligned.
+template <int NV>
+__global__ void __launch_bounds__(128) layernorm_vec_kernel(const float* __restrict__ x, int64_t x_ld, const float* __restrict__ res, int64_t res_ld,
+                                                            float* __restrict__ y, int64_t y_ld, int64_t rows, int C, const float* __restrict__ w,
+                                                            const float* __restrict__ bb, const float* __restrict__ ada, float eps, int rms,
+                                                            int post_act, float post_p0) {
+  const int64_t row = (int64_t)blockIdx.x * 4 + threadIdx.x / 32;
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float4* xp = reinterpret_cast<const float4*>(x + row * x_ld);
+  const float4* rp = res ? reinterpret_cast<const float4*>(res + row * res_ld) : nullptr;
+  const int nv = C >> 2;
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const int i = lane + 32 * j;
+    v[j] = i < nv ? xp[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (rp) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+      const int i = lane + 32 * j;
+      if (i < nv) { const float4 r = rp[i]; v[j].x += r.x; v[j].y += r.y; v[j].z += r.z; v[j].w += r.w; }
+    }
+  }
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) s1 += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  s1 = warp_sum(s1);
+  const float mean = rms ? 0.f : s1 / C;
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    if (lane + 32 * j < nv) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      s2 = fmaf(a, a, s2); s2 = fmaf(b, b, s2); s2 = fmaf(c, c, s2); s2 = fmaf(d, d, s2);
+    }
+  }
+  s2 = warp_sum(s2);
+  const float rstd = rsqrtf(s2 / C + eps);
+  float4* yp = reinterpret_cast<float4*>(y + row * y_ld);
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      float o[4] = {(v[j].x - mean) * rstd, (v[j].y - mean) * rstd, (v[j].z - mean) * rstd, (v[j].w - mean) * rstd};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int c = 4 * i + q;
+        if (ada) o[q] = fmaf(1.f + ada[c], o[q], ada[C + c]);
+        else { if (w) o[q] *= w[c]; if (bb) o[q] += bb[c]; }
+        if (post_act) o[q] = b2a_act(o[q], post_act, post_p0, 1.f, 1.f);
+      }
+      yp[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int64_t b2a_adain_ws_bytes(int32_t B, int32_t L, int32_t C) {
@@ -172,7 +232,14 @@ extern "C" int32_t b2a_layernorm(const float* x, int64_t x_ld, const float* res,
                                  int32_t rms, int32_t post_act, float post_p0, void* stream) {
   B2A_CHECK_ARG(x && y && rows >= 0 && C > 0, "bad pointers/shape");
   if (rows == 0) return B2A_OK;
-  layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, x_ld, res, res_ld, y, y_ld, rows, C, w, b, ada, eps,
+  const bool al = C % 4 == 0 && C <= 1024 && x_ld % 4 == 0 && y_ld % 4 == 0 && (!res || res_ld % 4 == 0) && ((uintptr_t)x & 15) == 0 &&
+                  ((uintptr_t)y & 15) == 0 && (!res || ((uintptr_t)res & 15) == 0);
+  if (al && C <= 512)
+    layernorm_vec_kernel<4><<<cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, x_ld, res, res_ld, y, y_ld, rows, C, w, b, ada, eps, rms, post_act, post_p0);
+  else if (al)
+    layernorm_vec_kernel<8><<<cdiv(rows, 4), 128, 0, (cudaStream_t)stream>>>(x, x_ld, res, res_ld, y, y_ld, rows, C, w, b, ada, eps, rms, post_act, post_p0);
+  else
+    layernorm_kernel<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, x_ld, res, res_ld, y, y_ld, rows, C, w, b, ada, eps,
                                                                       rms, post_act, post_p0);
   B2A_CHECK_LAUNCH();
   return B2A_OK;

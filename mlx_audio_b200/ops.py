@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import contextlib
 import os
 from dataclasses import dataclass
 from typing import Optional
@@ -233,7 +234,7 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     # Tiny GEMMs (a few rows: ALBERT at T = 130, decode-time prefills) are latency chains, not throughput problems: the fused kernel's
     # converter -> MMA -> split-K fix-up chain measured 30-40 us per launch there against ~14 us for the pre-split planes + TMA pipeline.
     small_gemm = SMALL_GEMM_SPLIT_PATH[0] and cw.K == 1 and B * L <= 256 and _tc_eligible(cw, L, stride, transpose, pad_mode, dilation)
-    if emit is None and not small_gemm and fused_eligible(x, cw, stride, dilation, transpose, pad_mode, out, res):
+    if FUSED_DISPATCH[0] and emit is None and not small_gemm and fused_eligible(x, cw, stride, dilation, transpose, pad_mode, out, res):
         y = conv_fused(FusedProblem(x, cw, stride=stride, dilation=dilation, pad_left=pad_left, lout=lout, pre=pre, post_act=post_act,
                                     post_p0=post_p0, cscale=cscale, res=res, res_div=res_div, out_scale=out_scale, out=out,
                                     accumulate=accumulate, transpose=transpose))[0]
@@ -277,6 +278,8 @@ def conv1d(x: torch.Tensor, cw: ConvW, *, stride=1, dilation=1, pad_left=0, lout
     p.res_div = res_div
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     fn = _lib.lib().b2a_convtr1d_cl if transpose else _lib.lib().b2a_conv1d_cl
+    if PROFILE_TAGS is not None:
+        TAG[0] = f"cuda-core conv [{B}x{L}x{cw.cin}->{cw.cout} k{cw.K} s{stride} d{dilation} g{cw.groups}{' T' if transpose else ''}]"
     _call("conv" if cw.groups == 1 and cw.cin * cw.K >= 64 else "other", fn, 1, C.byref(p), _stream())
     if planes is not None:
         return planes
@@ -351,6 +354,23 @@ def _conv1d_tc(x, cw, dilation, pad_left, lout, pre, post_act, post_p0, cscale, 
 # One launch per layer (or per GROUP of independent layers): InstanceNorm / AdaIN coefficients from the producer's (sum, sumsq), the
 # input activation, the 16-bit hi/lo split, the tap-summed GEMM, the epilogue and the output's (sum, sumsq) -- csrc/conv_fused.cu.
 FUSED = [os.environ.get("B2A_FUSED", "1") != "0"]
+# conv1d() / linear() route single layers to the fused kernel only on request: its A operand is converted by the CTA's own warps, which
+# pays off where it removes whole passes (Kokoro's AdaIN statistics + prologue, called explicitly through conv_fused) but loses to the
+# pre-split planes + TMA pipeline on plain wide GEMMs (measured, round 2: Whisper encoder GEMMs 23 -> 89 ms, Mimi 34 -> 89 ms, SNAC 22 -> 33 ms
+# with the fused kernel as the default route).
+FUSED_DISPATCH = [os.environ.get("B2A_FUSED_DISPATCH", "0") == "1"]
+
+
+@contextlib.contextmanager
+def fused_dispatch(on: bool = True):
+    """Route eligible conv1d() / linear() calls inside the block through the fused kernel (Kokoro: thin layers at L <= 780 where the
+    prologue pass of the split path is a separate launch on the critical path)."""
+    old = FUSED_DISPATCH[0]
+    FUSED_DISPATCH[0] = bool(on) and FUSED[0]
+    try:
+        yield
+    finally:
+        FUSED_DISPATCH[0] = old
 SMALL_GEMM_SPLIT_PATH = [os.environ.get("B2A_SMALL_GEMM_SPLIT", "1") != "0"]
 FUSED_WS_BYTES = 16 << 20
 _FUSED_WS = {}

@@ -15,6 +15,7 @@ B200-first structure (not a translation of the MLX graph):
 """
 from __future__ import annotations
 
+import functools
 import math
 import time
 from dataclasses import dataclass
@@ -26,6 +27,15 @@ import torch
 from .... import ops
 from ....ops import ACT, ConvW, Pre
 from ..base import BaseModelArgs, GenerationResult, check_array_shape
+
+
+def _fused_layers(fn):
+    """Kokoro's single layers (text-encoder convs, asr_res, the LSTM input projections) take the fused conv kernel; see ops.FUSED_DISPATCH."""
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        with ops.fused_dispatch(True):
+            return fn(*a, **k)
+    return wrapped
 
 
 @dataclass
@@ -214,8 +224,13 @@ class Model:
             W["dur_lstms"].append(self._lstm(P, f"predictor.text_encoder.lstms.{2 * i}"))
             ada.add(f"adaln.{i}", P[f"predictor.text_encoder.lstms.{2 * i + 1}.fc.weight"], P[f"predictor.text_encoder.lstms.{2 * i + 1}.fc.bias"])
         W["pred_lstm"] = self._lstm(P, "predictor.lstm")
-        W["dur_proj"] = self._lin(P, "predictor.duration_proj.linear_layer")
-        W["dur_sum"] = ops.pack_linear(torch.ones(1, cfg.max_dur), None, dev)
+        # duration head: Linear(512 -> max_dur = 50) -> sigmoid -> sum.  50 outputs miss the tensor-core kernels' Cout % 32 rule and the
+        # CUDA-core tile kernel needs 170 us for it on the text side's critical path; zero-padded to 64 outputs it is one small GEMM, and
+        # the padded columns (sigmoid(0) = 0.5) get weight 0 in the sum.
+        dpad = -cfg.max_dur % 32
+        dw, db = P["predictor.duration_proj.linear_layer.weight"].float(), P["predictor.duration_proj.linear_layer.bias"].float()
+        W["dur_proj"] = ops.pack_linear(torch.cat([dw, dw.new_zeros(dpad, dw.shape[1])], 0), torch.cat([db, db.new_zeros(dpad)], 0), dev)
+        W["dur_sum"] = ops.pack_linear(torch.cat([torch.ones(1, cfg.max_dur), torch.zeros(1, dpad)], 1), None, dev)
         W["shared"] = self._lstm(P, "predictor.shared")
         for name in ("F0", "N"):
             W[name] = [self._resblk1d(P, f"predictor.{name}.0", ada), self._resblk1d(P, f"predictor.{name}.1", ada, True),
@@ -510,6 +525,7 @@ class Model:
     # heads, decoder, generator, iSTFT head) on (T, F).  `forward_ids` runs both eagerly; `synthesize_ids` replays one CUDA graph per
     # side with a single host read of F in between (the reference syncs once per phoneme, kokoro.py:148-152).
     @torch.no_grad()
+    @_fused_layers
     def _text_side(self, ids, ref_s, speed: float = 1.0, pred_dur=None):
         """ids int64 [T] + style [1,256] (device) -> state dict: X [T,640] = [d_en | style], t_en [T,512], pred_dur, alignment
         indices (first `total` valid), total (device int64 [1]), the two style-projection rows."""
@@ -584,6 +600,7 @@ class Model:
         self._gb_pred, self._gb_dec = st["gb_pred"], st["gb_dec"]
 
     @torch.no_grad()
+    @_fused_layers
     def _acoustic_side(self, st, F: int, noise=None, f0n_override=None):
         """State of `_text_side` + the frame count -> waveform [600 F] samples."""
         if ops.FUSED[0] and ops.TC_MODE[0] != "off":

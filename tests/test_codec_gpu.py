@@ -69,22 +69,22 @@ def test_mimi_reference_length_pin_and_prefix_causality(mimi):
     y = model.decode(codes)
     assert y.shape == (1, 1, 120960)
     y2 = model.decode(codes[:, :, :40])
-    # the fused conv kernel splits K across CTAs when a layer has few output tiles, and how many ways depends on the length: the two decodes
-    # add the same fp32 partial products in a different order (measured 4e-5 on a 5.9 full scale)
-    assert torch.allclose(y2, y[:, :, : 40 * 1920], atol=3e-4, rtol=1e-4)
+    assert torch.equal(y2, y[:, :, : 40 * 1920])        # default route (pre-split planes + TMA pipeline): no length-dependent split-K, exact
     from mlx_audio_b200 import ops
-    ops.FUSED[0] = False                               # without split-K the prefix property is exact
+    ops.FUSED_DISPATCH[0] = True
     try:
-        assert torch.equal(model.decode(codes[:, :, :40]), model.decode(codes)[:, :, : 40 * 1920])
+        # the fused conv kernel splits K across CTAs when a layer has few output tiles, and how many ways depends on the length: the two
+        # decodes add the same fp32 partial products in a different order (measured 4e-5 on a 5.9 full scale)
+        assert torch.allclose(model.decode(codes[:, :, :40]), model.decode(codes)[:, :, : 40 * 1920], atol=3e-4, rtol=1e-4)
     finally:
-        ops.FUSED[0] = True
+        ops.FUSED_DISPATCH[0] = False
 
 
 @pytest.mark.parametrize("parts", [2, 3])
 def test_snac_span_decodes_stitch_to_the_one_shot_decode(snac, parts):
     """SURVEY.md section 8e (config 5): one stream sharded by contiguous frame spans with a 16-frame halo per side; the per-channel
-    NoiseBlock draws are shared.  The stitched waveform equals the one-shot decode: bit for bit on the kernels without split-K; with the
-    fused kernel's length-dependent split-K factor the same fp32 partial products are added in a different order, which four Snake stages
+    NoiseBlock draws are shared.  The stitched waveform equals the one-shot decode: bit for bit on the default route; routed through the
+    fused kernel (length-dependent split-K factor) the same fp32 partial products are added in a different order, which four Snake stages
     amplify to 2-4e-4 of full scale (measured)."""
     from mlx_audio_b200 import ops
     from mlx_audio_b200.parallel import shard_span
@@ -104,13 +104,13 @@ def test_snac_span_decodes_stitch_to_the_one_shot_decode(snac, parts):
 
     got, full = both()
     assert got.shape == full.shape == (1, 120907, 1)
-    assert float((got - full).abs().max()) <= 1.5e-3
-    ops.FUSED[0] = False
+    assert torch.equal(got, full)                         # default route
+    ops.FUSED_DISPATCH[0] = True
     try:
         got, full = both()
-        assert torch.equal(got, full)
+        assert float((got - full).abs().max()) <= 1.5e-3
     finally:
-        ops.FUSED[0] = True
+        ops.FUSED_DISPATCH[0] = False
     with pytest.raises(ValueError):
         model.decode_span(codes, 2, 40, noises=noises)
 

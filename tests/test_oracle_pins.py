@@ -596,12 +596,17 @@ WHISPER_GEN_CASES = {
 }
 
 
-def _segments_match(got, want, tol=1e-6):
+def _segments_match(got, want, tol=1e-6, score_tol=2e-4):
+    """Token ids, seek positions and texts identical; times and temperatures to ``tol``; the scores to ``score_tol``: the stand-in runs the
+    reference in the checkpoint's float32 and the oracle runs in float64, and a window's summed log-probability over logits of +-40..60
+    carries ~4e-5 of float32 rounding (measured)."""
     assert len(got) == len(want), (len(got), len(want))
     for a, b in zip(got, want):
         assert a["tokens"] == b["tokens"] and a["seek"] == b["seek"] and a["text"] == b["text"] and a["id"] == b["id"], (a, b)
-        for k in ("start", "end", "temperature", "avg_logprob", "compression_ratio", "no_speech_prob"):
+        for k in ("start", "end", "temperature", "compression_ratio"):
             assert abs(a[k] - b[k]) <= tol * max(1.0, abs(b[k])), (k, a[k], b[k])
+        for k in ("avg_logprob", "no_speech_prob"):
+            assert (a[k] != a[k] and b[k] != b[k]) or abs(a[k] - b[k]) <= score_tol * max(1.0, abs(b[k])), (k, a[k], b[k])
 
 
 def test_oracle_whisper_generate_matches_the_reference_generate():

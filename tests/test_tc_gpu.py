@@ -23,9 +23,10 @@ def path(request):
     """Every dense-conv case runs through both tensor-core kernels: round 1's prologue pass + conv_tc_persist_kernel (csrc/gemm_tc.cu) and
     the fused kernel that converts the activations on the fly (csrc/conv_fused.cu)."""
     from mlx_audio_b200 import ops
-    old, ops.FUSED[0] = ops.FUSED[0], request.param == "fused"
+    old, oldd = ops.FUSED[0], ops.FUSED_DISPATCH[0]
+    ops.FUSED[0] = ops.FUSED_DISPATCH[0] = request.param == "fused"
     yield request.param
-    ops.FUSED[0] = old
+    ops.FUSED[0], ops.FUSED_DISPATCH[0] = old, oldd
 
 
 CASES = [

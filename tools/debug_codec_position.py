@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Position independence of the codec decoders (run on the GPU box): decode a stream whole and as prefix / spans, print the differences
-under the dispatch toggles (B2A_FUSED, B2A_TC)."""
+under the dispatch toggles (ops.FUSED_DISPATCH, ops.TC_MODE)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -25,8 +25,8 @@ def run(tag):
           idx[:3].tolist(), idx[-3:].tolist()))
 
 run("default")
-ops.FUSED[0] = False
-run("fused off")
-ops.FUSED[0] = True
+ops.FUSED_DISPATCH[0] = True
+run("routed through the fused kernel")
+ops.FUSED_DISPATCH[0] = False
 ops.TC_MODE[0] = "off"
 run("tensor cores off")

@@ -10,7 +10,8 @@ import sys
 from collections import defaultdict
 
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "bytes": 1}
-CONV = ("conv_tc_kernel", "conv_tc_persist_kernel", "prep_bf16_kernel", "conv1d_dense_kernel", "convtr1d_dense_kernel")
+CONV = ("conv_fused_kernel", "conv_tc_kernel", "conv_tc_persist_kernel", "prep_bf16_kernel", "conv1d_dense_kernel", "convtr1d_dense_kernel",
+        "channel_stats_kernel", "coeffs_from_stats_kernel")
 
 
 def main(path, out):
