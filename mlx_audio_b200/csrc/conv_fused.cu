@@ -28,7 +28,7 @@ namespace {
 
 constexpr int TM = 128;
 constexpr int TK = 64;
-constexpr int UMMA_K = 16;
+
 constexpr int MAXG = B2A_CONVF_MAX_PROBLEMS;
 constexpr int NWORK = 16;                      // worker warps: every one converts A chunks AND runs epilogues (see the kernel's worker section)
 constexpr int W_WORK0 = 2;
@@ -91,7 +91,6 @@ __device__ __forceinline__ float back16(__half v) { return __half2float(v); }
 __device__ __noinline__ float act_slow(float v, int act, float p0) { return b2a_act(v, act, p0, 1.f, 1.f); }
 __device__ __noinline__ float act_slow2(float v, int act, float p0, float a, float b) { return b2a_act(v, act, p0, a, b); }
 
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // accumulate the SM cycles a role spends inside a wait (debug runs only): slots 16.. of the CTA's row.  clock64, not %globaltimer: the
 // global timer read costs ~1 us on this part and, placed around every wait, it WAS the timeline (measured: same kernel 2x slower).
 #define TIMED_WAIT(p, acc, stmt) do { if (DBG && (p).dbg) { const long long t0_ = clock64(); stmt; acc += (unsigned long long)(clock64() - t0_); } else { stmt; } } while (0)
@@ -672,7 +671,16 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
   for (int i = 0; i < n; i++) { order[i] = i; cost[i] = (double)pr[i].taps * pr[i].cin_pad; }
   for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (cost[order[j]] > cost[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
   int maxR = 0, maxBN = 0, maxWst = 0, tiles_total = 0;
-  int64_t base_tiles = 0;
+  int64_t base_tiles = 0, sum_base = 0, cnt_used = 0, ws_used = 0;
+  for (int gi = 0; gi < n; gi++) {                         // output tiles of the whole launch before any split (same tile rule as below)
+    const b2a_convf_t& q = pr[gi];
+    if (q.N <= 0 || q.N % 32) continue;                    // rejected by the argument checks below
+    const int C_ = q.up_stride > 0 ? q.N / q.up_stride : q.N;
+    int bn = 32;
+    for (int c = 128; c >= 32; c -= 32) if (q.N % c == 0 && C_ % c == 0) { bn = c; break; }
+    const int mrows = q.up_stride > 0 ? q.L + q.taps - 1 : q.Lout;
+    sum_base += (int64_t)cdiv(mrows, TM) * (q.N / bn) * q.B;
+  }
   for (int gi = 0; gi < n; gi++) {
     const b2a_convf_t& q = pr[order[gi]];
     B2A_CHECK_ARG(q.x && q.w_hi && q.y && q.B > 0 && q.L > 0 && q.Lout > 0 && q.Cin > 0 && q.taps > 0 && q.taps <= 32 && q.cin_pad % 64 == 0 && q.cin_pad >= q.Cin,
@@ -702,11 +710,12 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
     for (int c = 128; c >= 32; c -= 32) if (q.N % c == 0 && P.C % c == 0) { bn = c; break; }
     P.BN = bn; P.ntn = q.N / bn;
     base_tiles = (int64_t)P.ntm * P.ntn * q.B;
-    // split K across CTAs when the problem alone cannot give every SM a tile (single-problem launches only)
+    // split K across CTAs when the whole launch cannot give every SM a tile (every problem of a group by the same rule: the decoder
+    // blocks -- a k=3 conv over 390 rows grouped with its 1x1 shortcut -- are 48 tiles with 54 tap steps each)
     const int kchunks = q.cin_pad / TK;
     P.ksplit = 1;
-    if (ksplit_on && n == 1 && base_tiles * 2 <= nsm && kchunks >= 4 && ws) {
-      int ks = (int)(nsm / base_tiles);
+    if (ksplit_on && sum_base * 2 <= nsm && kchunks >= 4 && ws) {
+      int ks = (int)(nsm / sum_base);
       if (ks > 8) ks = 8;
       if (ks > kchunks / 2) ks = kchunks / 2;
       if (ks >= 2) P.ksplit = ks;
@@ -721,9 +730,12 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
       // workspace layout: [4 KB of arrival counters (one per output tile; a split launch has < 148 of them)] [partial tiles].  The counter region
       // has a FIXED size: were it sized per launch, the partial tiles of a launch with fewer tiles would overwrite counters that a later launch
       // with more tiles expects to be zero (they are self-resetting, never re-zeroed).
-      const int64_t need = 4096 + base_tiles * P.ksplit * (TM * P.BN) * 4;
-      if (need > ws_bytes || base_tiles > 1024) { P.ksplit = 1; P.kper = kchunks; }
-      else { P.counters = (int*)ws; P.ws = (float*)((uint8_t*)ws + 4096); }
+      const int64_t bytes = base_tiles * P.ksplit * (TM * P.BN) * 4;
+      if (4096 + ws_used + bytes > ws_bytes || cnt_used + base_tiles > 1024) { P.ksplit = 1; P.kper = kchunks; }
+      else {
+        P.counters = (int*)ws + cnt_used; P.ws = (float*)((uint8_t*)ws + 4096 + ws_used);       // each problem of a group: its own counters and partial tiles
+        cnt_used += base_tiles; ws_used += bytes;
+      }
     }
     P.tile_begin = tiles_total;
     tiles_total += (int)(base_tiles * P.ksplit);

@@ -102,6 +102,34 @@ def test_grouped_problems_and_folded_average():
     assert rel_err(y, ref) < 2e-5
 
 
+def test_grouped_launch_splits_k_per_problem():
+    """A Kokoro decoder block as it is launched: the k=3 conv over 390 rows grouped with its 1x1 shortcut (64 output tiles for 148 SMs), so
+    every problem of the group splits K with its own counters and partial tiles in the shared workspace.  Equal to the float64 reference,
+    repeatable bit for bit, statistics from the reducing CTAs only."""
+    from mlx_audio_b200 import ops
+    L, Cin, Cout = 390, 1090, 1024
+    ld = -(-Cin // 4) * 4
+    x = _rand(1, L, ld, seed=1).to(DEV)[:, :, :Cin]
+    cw3 = ops.pack_conv(_w(Cout, 3, Cin, 2), _rand(Cout, seed=3, scale=0.1), 1, DEV)
+    cw1 = ops.pack_conv(_w(Cout, 1, Cin, 4), None, 1, DEV)
+
+    def run():
+        sts = [ops.new_stats(1, Cout, DEV) for _ in range(2)]
+        outs = ops.conv_fused([ops.FusedProblem(x, cw3, pad_left=1, stats_out=sts[0]), ops.FusedProblem(x, cw1, stats_out=sts[1])])
+        torch.cuda.synchronize()
+        return outs, sts
+
+    (y3, y1), sts = run()
+    (z3, z1), sts2 = run()
+    assert torch.equal(y3, z3) and torch.equal(y1, z1) and torch.equal(sts[0], sts2[0]) and torch.equal(sts[1], sts2[1])
+    xd = x.double().cpu()
+    assert rel_err(y3, ON.conv1d(xd, cw3.w.permute(2, 0, 1).double().cpu(), 1, 1, 1, 1, cw3.bias.double().cpu())) < 2e-5
+    assert rel_err(y1, ON.conv1d(xd, cw1.w.permute(2, 0, 1).double().cpu(), 1, 0, 1, 1)) < 2e-5
+    for y, st in ((y3, sts[0]), (y1, sts[1])):
+        sv = ops.stats_value(st)
+        assert rel_err(sv[0, :, 0], y.double().sum(dim=1)[0]) < 1e-6 and rel_err(sv[0, :, 1], (y.double() ** 2).sum(dim=1)[0]) < 1e-6
+
+
 @pytest.mark.parametrize("L,Cin,Cout,K", [(390, 1090, 1024, 3), (130, 768, 2304, 1), (390, 514, 1024, 3), (20, 512, 512, 5)])
 def test_split_k_small_m(L, Cin, Cout, K):
     """Decoder-sized problems (4 M tiles) split K across CTAs; the fixed-order reduction of the partial tiles is deterministic and equals
