@@ -12,7 +12,7 @@ graph and reads back 16 integers per frame for the EOS test (the reference also 
 from __future__ import annotations
 
 import time
-from typing import Optional
+from typing import Dict, List, Optional
 
 import torch
 
@@ -293,7 +293,7 @@ class Model:
         self._cp_in = torch.zeros(B, H, device=dev)
         self._err = torch.zeros(1, dtype=torch.int32, device=dev)
         out = torch.zeros(B, max_tokens, g, dtype=torch.int64, device=dev)
-        lengths = torch.zeros(B, dtype=torch.int64)
+        lengths_dev = torch.zeros(B, dtype=torch.int64, device=dev)
         done = torch.zeros(B, dtype=torch.bool)
         n = 0
         graph = None
@@ -327,16 +327,19 @@ class Model:
                 l0 = ops.LAUNCHES[0]
                 self._frame(self._x_in, sp)
                 self._frame_launches = ops.LAUNCHES[0] - l0
-            codes_h = self._codes.cpu()                                             # the per-frame sync (EOS test)
-            hit = codes_h[:, 0] == eos
             if batch_mode:
-                fin = self._finished.cpu().bool()
-                if bool(fin.all()):
+                # No per-frame host read: a finished row is masked on the device (its frame keeps the zeros `out` starts with, its length
+                # stops growing) and the all-finished test is a sync every 8th frame only -- the frames replayed past the last EOS record
+                # nothing.  (One .cpu() per frame held the loop at ~12 ms per frame; the graph itself replays in under 5.)
+                fin = self._finished.bool()
+                out[:, n] = torch.where(fin[:, None], out[:, n], self._codes)
+                lengths_dev += (~fin).to(torch.int64)
+                n += 1
+                if (step & 7) == 7 and bool(fin.all()):
                     break
-                live = ~fin
-                out[live.to(dev), n] = self._codes[live.to(dev)]
-                lengths[live] += 1
-            elif stop_on_eos:
+                continue
+            if stop_on_eos:
+                hit = self._codes[:, 0].cpu() == eos                                 # the per-frame sync (EOS test)
                 done |= hit
                 if bool(done.all()):
                     break
@@ -349,6 +352,8 @@ class Model:
             raise ValueError("generate_codes: a sampled code indexed outside its embedding table")
         self._graph = graph
         if batch_mode:
+            lengths = lengths_dev.cpu()
+            n = int(lengths.max()) if lengths.numel() else 0
             return out[:, :n], lengths
         return out[:, :n]
 
@@ -395,7 +400,17 @@ class Model:
         if stream:
             audios, _ = self.speech_tokenizer.batch_decode([s_ for s_ in seqs if s_.shape[0] > 0])
         else:
-            audios = [self._decode_generated_codes(s_) for s_ in seqs if s_.shape[0] > 0]
+            # rows of equal length share their decode launches: the chunks of _decode_generated_codes do not interact, so chunk j of every
+            # row goes through the vocoder as one batch (identical samples; 8 rows x 3 chunks: 24 decoder passes -> 2)
+            live = [s_ for s_ in seqs if s_.shape[0] > 0]
+            by_len: Dict[int, List[int]] = {}
+            for i, s_ in enumerate(live):
+                by_len.setdefault(int(s_.shape[0]), []).append(i)
+            audios = [None] * len(live)
+            for n_, idxs in by_len.items():
+                wav = self.speech_tokenizer.decoder.chunked_decode(torch.stack([live[i] for i in idxs]).transpose(1, 2), chunk_size=15, left_context_size=5)
+                for j, i in enumerate(idxs):
+                    audios[i] = wav[j, 0]
         torch.cuda.synchronize(self.device)
         dt = time.perf_counter() - t0
         it = iter(audios)
