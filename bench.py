@@ -454,6 +454,9 @@ def main_kokoro(args, rank, world, local_rank):
 
 
 def main():
+    # rank 0 prints ONE JSON line on stdout: NCCL's version banner (NCCL_DEBUG=VERSION, set by some launch environments) would be a second one
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
