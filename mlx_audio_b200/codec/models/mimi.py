@@ -9,6 +9,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import math
+
 import torch
 
 from ... import ops
@@ -164,6 +166,19 @@ class Mimi:
         W["proj_first"] = ops.pack_conv(P["quantizer.rvq_first.output_proj.weight"].float(), None, 1, dev)
         W["proj_rest"] = ops.pack_conv(P["quantizer.rvq_rest.output_proj.weight"].float(), None, 1, dev) if cfg.nq > 1 else None
         W["upsample"] = ops.pack_conv(P["upsample.convtr.convtr.convtr.weight"].float(), None, cfg.dimension, dev)
+        def tlayers(root):
+            out = []
+            for li in range(cfg.num_layers):
+                L = f"{root}.transformer.layers.{li}"
+                out.append({
+                    "n1": (f(P[L + ".norm1.weight"]), f(P[L + ".norm1.bias"])), "n2": (f(P[L + ".norm2.weight"]), f(P[L + ".norm2.bias"])),
+                    "in_proj": ops.pack_linear(P[L + ".self_attn.in_proj.weight"].float(), None, dev),
+                    "out_proj": ops.pack_linear(P[L + ".self_attn.out_proj.weight"].float(), None, dev),
+                    "l1": ops.pack_linear(P[L + ".gating.linear1.weight"].float(), None, dev),
+                    "l2": ops.pack_linear(P[L + ".gating.linear2.weight"].float(), None, dev),
+                    "ls1": f(P[L + ".layer_scale_1.scale"]), "ls2": f(P[L + ".layer_scale_2.scale"])})
+            return out
+
         W["layers"] = []
         for li in range(cfg.num_layers):
             L = f"decoder_transformer.transformer.layers.{li}"
@@ -184,6 +199,20 @@ class Mimi:
         W["final"] = cw("decoder.final_conv1d.conv.conv")
         del bf
         self._w = W
+        self._enc = None
+        if "encoder.init_conv1d.conv.conv.weight" in P:                 # encode side (seanet.py:194-199, mimi.py:146-153, quantization.py:178-185)
+            E = {"init": cw("encoder.init_conv1d.conv.conv"), "layers": [], "final": cw("encoder.final_conv1d.conv.conv"),
+                 "tr": tlayers("encoder_transformer"), "down": cw("downsample.conv.conv.conv")}
+            for li, r in enumerate(reversed(cfg.ratios)):
+                L = f"encoder.layers.{li}"
+                E["layers"].append({"r": r, "c0": cw(L + ".residuals.0.block.0.conv.conv"), "c1": cw(L + ".residuals.0.block.1.conv.conv"),
+                                    "down": cw(L + ".downsample.conv.conv")})
+            for name, cb in (("first", W["cb_first"]), ("rest", W["cb_rest"])):
+                if cb is None:
+                    continue
+                E["in_" + name] = ops.pack_conv(P[f"quantizer.rvq_{name}.input_proj.weight"].float(), None, 1, dev)
+                E["c2_" + name] = ((cb.double() ** 2).sum(-1) / 2).contiguous()             # |e|^2 / 2 of argmin(|e|^2 / 2 - x.e)
+            self._enc = E
         return self
 
     @torch.no_grad()
@@ -200,18 +229,7 @@ class Mimi:
             x = ops.conv1d(q2, W["proj_rest"], res=x)
         s = cfg.upsample_stride
         x = ops.conv1d(x, W["upsample"], stride=s, pad_left=0, lout=T * s, transpose=True)         # causal: trim k-s on the right
-        d, nh = cfg.dimension, cfg.num_heads
-        for lw in W["layers"]:
-            n1 = ops.layernorm(x, *lw["n1"], eps=1e-5)
-            qkv = ops.linear(n1, lw["in_proj"])
-            ops.rope_(qkv[:, :, :d], nh, offset=0, base=cfg.max_period, traditional=True)
-            ops.rope_(qkv[:, :, d:2 * d], nh, offset=0, base=cfg.max_period, traditional=True)
-            att = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], n_heads=nh, scale=(d // nh) ** -0.5,
-                                causal=True, window=cfg.context)
-            x = ops.linear(att, lw["out_proj"], cscale=lw["ls1"], res=x)
-            n2 = ops.layernorm(x, *lw["n2"], eps=1e-5)
-            m = ops.linear(n2, lw["l1"], post_act=ACT["gelu_tanh"])
-            x = ops.linear(m, lw["l2"], cscale=lw["ls2"], res=x)
+        x = self._transformer(x, W["layers"])
         elu = Pre(act=ACT["elu"])
         x = ops.conv1d(x, W["init"], pad_left=cfg.ksize - 1, lout=x.shape[1])
         for lw in W["dec"]:
@@ -222,8 +240,66 @@ class Mimi:
         pcm = ops.conv1d(x, W["final"], pad_left=cfg.last_ksize - 1, lout=x.shape[1], pre=elu)      # [B, L, 1]
         return pcm.reshape(B, 1, -1)
 
-    def encode(self, xs):
-        raise NotImplementedError("Mimi.encode is the 'next' row 2 of SURVEY.md section 8f (codec encode side)")
+    def _transformer(self, x: torch.Tensor, layers) -> torch.Tensor:
+        """ProjectedTransformer (mimi/modules/transformer.py:63-261), fresh cache: pre-norm layers, traditional RoPE, causal attention
+        inside a ``context``-position window, LayerScale on both residual branches."""
+        cfg = self.cfg
+        d, nh = cfg.dimension, cfg.num_heads
+        for lw in layers:
+            n1 = ops.layernorm(x, *lw["n1"], eps=1e-5)
+            qkv = ops.linear(n1, lw["in_proj"])
+            ops.rope_(qkv[:, :, :d], nh, offset=0, base=cfg.max_period, traditional=True)
+            ops.rope_(qkv[:, :, d:2 * d], nh, offset=0, base=cfg.max_period, traditional=True)
+            att = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], n_heads=nh, scale=(d // nh) ** -0.5,
+                                causal=True, window=cfg.context)
+            x = ops.linear(att, lw["out_proj"], cscale=lw["ls1"], res=x)
+            n2 = ops.layernorm(x, *lw["n2"], eps=1e-5)
+            m = ops.linear(n2, lw["l1"], post_act=ACT["gelu_tanh"])
+            x = ops.linear(m, lw["l2"], cscale=lw["ls2"], res=x)
+        return x
+
+    @staticmethod
+    def _cconv(x, cw, ksize, stride=1, pre=None, pad_mode=0, res=None):
+        """StreamableConv1d (mimi/modules/conv.py:224-243), causal: k - stride samples of left padding, the right edge padded up to a whole
+        last frame (zeros, or the edge sample for ``pad_mode=1``)."""
+        L = x.shape[1]
+        pad_total = ksize - stride
+        lout = int(math.ceil(max(L + pad_total - ksize, 0) / stride + 1.0))
+        return ops.conv1d(x, cw, stride=stride, pad_left=pad_total, lout=lout, pad_mode=pad_mode, pre=pre, res=res)
+
+    @torch.no_grad()
+    def encode_latent(self, xs: torch.Tensor) -> torch.Tensor:
+        """pcm [B, 1, n] -> the 12.5 Hz latent [B, ceil(n / 1920), 512] in front of the quantiser (mimi.py:146-152)."""
+        if self._enc is None:
+            raise ValueError("Mimi.encode: the loaded weights have no encoder (encoder.*, encoder_transformer.*, downsample.*)")
+        E, cfg = self._enc, self.cfg
+        x = xs.to(device=self.device, dtype=torch.float32)
+        x = x.reshape(x.shape[0], -1, 1)                                 # [B, 1, n] -> [B, n, 1] (one channel: same memory)
+        elu = Pre(act=ACT["elu"])
+        x = self._cconv(x, E["init"], cfg.ksize)
+        for lw in E["layers"]:
+            t = self._cconv(x, lw["c0"], cfg.residual_ksize, pre=elu)
+            y = self._cconv(t, lw["c1"], 1, pre=elu, res=x)               # block(x) + x  (seanet.py:61-66)
+            x = self._cconv(y, lw["down"], 2 * lw["r"], stride=lw["r"], pre=elu)
+        x = self._cconv(x, E["final"], cfg.last_ksize, pre=elu)
+        x = self._transformer(x, E["tr"])
+        s = cfg.upsample_stride
+        return self._cconv(x, E["down"], 2 * s, stride=s, pad_mode=1)
+
+    @torch.no_grad()
+    def encode(self, xs: torch.Tensor) -> torch.Tensor:
+        """mimi.py:146-153: pcm [B, 1, n] -> int64 codes [B, nq, ceil(n / 1920)]: SEANet encoder, encoder transformer, stride-2 replicate-padded
+        down-sampling conv, then the split residual quantiser (quantization.py:178-185): the first codebook on its own projection, the other
+        nq - 1 as a residual chain on theirs -- `rvq_encode_kernel` runs the chain (argmin |e|^2 / 2 - x.e, first index on ties)."""
+        z = self.encode_latent(xs)
+        E, W = self._enc, self._w
+        B, T, _ = z.shape
+        r1 = ops.conv1d(z, E["in_first"])
+        codes = [ops.rvq_encode(r1.reshape(B * T, -1), W["cb_first"], E["c2_first"]).reshape(B, T, 1)]
+        if W["cb_rest"] is not None:
+            r2 = ops.conv1d(z, E["in_rest"])
+            codes.append(ops.rvq_encode(r2.reshape(B * T, -1), W["cb_rest"], E["c2_rest"]).reshape(B, T, -1))
+        return torch.cat(codes, dim=2).transpose(1, 2).contiguous()
 
 
 class MimiStreamingDecoder:

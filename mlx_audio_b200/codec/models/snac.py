@@ -116,6 +116,27 @@ class SNAC:
         W["out_snake"] = snake(f"{pre}.{li}.alpha"); li += 1
         W["out_conv"] = wnconv(f"{pre}.{li}")
         self._w = W
+        self._enc = None
+        if "encoder.block.layers.0.weight_v" in P:                     # encode side (snac/layers.py:133-158, vq.py:22-109)
+            E = {"in": wnconv("encoder.block.layers.0"), "blocks": [], "q": []}
+            pre, li, d = "encoder.block.layers", 1, self.encoder_dim
+            for stride in self.encoder_rates:
+                bp = f"{pre}.{li}.block.layers"; li += 1
+                blk = {"stride": stride, "res": [], "snake": snake(f"{bp}.3.alpha"), "down": wnconv(f"{bp}.4")}
+                for bi, dil in enumerate((1, 3, 9)):
+                    rp = f"{bp}.{bi}.block.layers"
+                    blk["res"].append({"d": dil, "s1": snake(rp + ".0.alpha"), "c1": wnconv(rp + ".1", groups=d if self.depthwise else 1),
+                                       "s2": snake(rp + ".2.alpha"), "c2": wnconv(rp + ".3")})
+                E["blocks"].append(blk)
+                d *= 2
+            E["out"] = wnconv(f"{pre}.{li}", groups=d if self.depthwise else 1)
+            for i in range(self.n_codebooks):
+                q = f"quantizer.quantizers.{i}"
+                cb = P[q + ".codebook.weight"].double()
+                cn = (cb / cb.norm(dim=1, keepdim=True).clamp(min=1e-12)).float()            # the cosine search runs on the L2-normalised table (vq.py:62-66)
+                E["q"].append({"in_proj": wnconv(q + ".in_proj"), "cn": f(cn)[None].contiguous(),
+                               "c2": (cn.double() ** 2).sum(1)[None].to(dev).contiguous()})
+            self._enc = E
         return self
 
     @torch.no_grad()
@@ -194,5 +215,56 @@ class SNAC:
         audio = full_audio[..., context_samples:] if full_audio.shape[-1] > context_samples else full_audio
         return audio, new_context
 
-    def encode(self, audio_data):
-        raise NotImplementedError("SNAC.encode is the 'next' row 2 of SURVEY.md section 8f (codec encode side)")
+    def preprocess(self, audio_data: torch.Tensor) -> torch.Tensor:
+        """snac.py:67-84: right-pad [B, 1, n] to a multiple of hop x lcm(vq_strides)."""
+        lcm = 1
+        for v in self.vq_strides:
+            lcm = lcm * v // math.gcd(lcm, v)
+        pad_to = self.hop_length * lcm
+        n = audio_data.shape[-1]
+        return torch.nn.functional.pad(audio_data, (0, -n % pad_to))
+
+    @torch.no_grad()
+    def encode(self, audio_data: torch.Tensor) -> List[torch.Tensor]:
+        """snac.py:95-99: audio [B, 1, n] -> codes, coarse to fine: [B, T/4], [B, T/2], [B, T] for the 24 kHz model.
+
+        Encoder = the decoder's building blocks mirrored (k7 conv; per rate three Snake -> depthwise k7 (dilation 1 / 3 / 9) -> Snake -> 1x1
+        residual units, Snake, strided conv k = 2s; depthwise k7 out conv), then per level of the residual quantiser: average-pool by the
+        level's stride, 1x1 projection to 8 dims, cosine nearest-code search (`rvq_encode_kernel`, first index on ties), project the code
+        back, repeat by the stride, subtract from the residual (vq.py:22-109).  Needs a checkpoint that carries the encoder."""
+        residual = self.encode_latent(audio_data)                                                              # [B, T, latent]
+        E = self._enc
+        B, T, D = residual.shape
+        codes = []
+        for i, stride in enumerate(self.vq_strides):
+            q = E["q"][i]
+            xl = residual
+            if stride > 1:
+                t_ = (T - stride) // stride + 1
+                xl = (residual[:, : t_ * stride].reshape(B, t_, stride, D).sum(dim=2) / stride).contiguous()
+            ze = ops.conv1d(xl, q["in_proj"])                                                                  # [B, T', cd]
+            idx = ops.rvq_encode(ze.reshape(-1, ze.shape[-1]), q["cn"], q["c2"], mode=1)[:, 0].reshape(B, -1).contiguous()
+            codes.append(idx)
+            if i + 1 < len(self.vq_strides):
+                zq = ops.snac_from_codes([idx], [stride], [self._w["emb"][i]], [self._w["proj_w"][i]], [self._w["proj_b"][i]], D, check=False)
+                residual = residual - zq[:, :T] if zq.shape[1] >= T else residual - torch.nn.functional.pad(zq, (0, 0, 0, T - zq.shape[1]))
+        return codes
+
+    @torch.no_grad()
+    def encode_latent(self, audio_data: torch.Tensor) -> torch.Tensor:
+        """The encoder alone (snac/layers.py:133-158): audio [B, 1, n] -> z [B, T, latent] in front of the quantiser."""
+        if self._enc is None:
+            raise ValueError("SNAC.encode: the loaded weights have no encoder (encoder.block.layers.*)")
+        E, dev = self._enc, self.device
+        x = self.preprocess(audio_data.to(device=dev, dtype=torch.float32))
+        x = x.reshape(x.shape[0], -1, 1)                                                                       # [B, 1, n] -> [B, n, 1] (one channel: same memory)
+        y = ops.conv1d(x, E["in"], pad_left=3)
+        for blk in E["blocks"]:
+            for ru in blk["res"]:
+                s1 = Pre(act=ACT["snake"], a=ru["s1"][0], b=ru["s1"][1])
+                s2 = Pre(act=ACT["snake"], a=ru["s2"][0], b=ru["s2"][1])
+                t = ops.conv1d(y, ru["c1"], dilation=ru["d"], pad_left=3 * ru["d"], pre=s1)
+                y = ops.conv1d(t, ru["c2"], pre=s2, res=y)
+            s = blk["stride"]
+            y = ops.conv1d(y, blk["down"], stride=s, pad_left=math.ceil(s / 2), pre=Pre(act=ACT["snake"], a=blk["snake"][0], b=blk["snake"][1]))
+        return ops.conv1d(y, E["out"], pad_left=3)

@@ -179,9 +179,9 @@ def _fan(g, name, *shape, fan_in):
 FINAL_GAIN_DIV = 1.0e6     # keeps the pre-tanh signal O(0.5) so the tanh is not saturated in parity tests
 
 
-def snac_weights(cfg, seed=6):
-    """Parameter tree of codec/models/snac/snac.py:SNAC (decode side: quantizer + decoder), random values.
-    weight_v ~ N(0, 1/fan_in), weight_g = ||v|| (so the effective weight is v), Snake alpha ~ U(0.5, 1.5)."""
+def snac_weights(cfg, seed=6, encoder=False):
+    """Parameter tree of codec/models/snac/snac.py:SNAC (quantizer + decoder; ``encoder=True`` adds the encoder and the quantizers'
+    in_proj), random values.  weight_v ~ N(0, 1/fan_in), weight_g = ||v|| (so the effective weight is v), Snake alpha ~ U(0.5, 1.5)."""
     g = _Gen(seed)
     gen = g.g
 
@@ -222,6 +222,25 @@ def snac_weights(cfg, seed=6):
             wn(rp + ".3", (cout, 1, cout), cout, bias=cout)
     alpha(f"{pre}.{li}.alpha", cout); li += 1
     wn(f"{pre}.{li}", (1, 7, cout), 7 * cout * FINAL_GAIN_DIV, bias=1)
+    if encoder:                                                   # snac/layers.py:133-158 (drawn AFTER the decode-side tensors: those keep their values)
+        for i, _ in enumerate(cfg["vq_strides"]):
+            wn(f"quantizer.quantizers.{i}.in_proj", (cd, 1, latent), latent, bias=cd)
+        pre = "encoder.block.layers"
+        d = cfg["encoder_dim"]
+        wn(f"{pre}.0", (d, 7, 1), 7, bias=d)
+        li = 1
+        for stride in cfg["encoder_rates"]:
+            bp = f"{pre}.{li}.block.layers"; li += 1
+            for bi in range(3):
+                rp = f"{bp}.{bi}.block.layers"
+                alpha(rp + ".0.alpha", d)
+                wn(rp + ".1", (d, 7, 1) if cfg["depthwise"] else (d, 7, d), 7 if cfg["depthwise"] else 7 * d, bias=d)
+                alpha(rp + ".2.alpha", d)
+                wn(rp + ".3", (d, 1, d), d, bias=d)
+            alpha(f"{bp}.3.alpha", d)
+            wn(f"{bp}.4", (2 * d, 2 * stride, d), 2 * stride * d, bias=2 * d)
+            d *= 2
+        wn(f"{pre}.{li}", (d, 7, 1) if cfg["depthwise"] else (d, 7, d), 7 if cfg["depthwise"] else 7 * d, bias=d)
     return g.P
 
 
@@ -237,8 +256,9 @@ def snac_noises(cfg, batch=1, seed=7):
     return [torch.randn(batch, 1, cfg["decoder_dim"] // (2 ** (i + 1)), generator=gen) for i in range(len(cfg["decoder_rates"]))]
 
 
-def mimi_weights(cfg, seed=5):
-    """Parameter tree of codec/models/mimi/mimi.py:Mimi (decode side), random values at the mimi_202407 shapes."""
+def mimi_weights(cfg, seed=5, encoder=False):
+    """Parameter tree of codec/models/mimi/mimi.py:Mimi (decode side; ``encoder=True`` adds the SEANet encoder, the encoder transformer, the
+    down-sampling conv and the quantisers' input projections), random values at the mimi_202407 shapes."""
     g = _Gen(seed)
     gen = g.g
     d, nf = cfg["dimension"], cfg["nfilters"]
@@ -276,6 +296,35 @@ def mimi_weights(cfg, seed=5):
         mult //= 2
     _fan(g, "decoder.final_conv1d.conv.conv.weight", 1, cfg["last_ksize"], nf, fan_in=cfg["last_ksize"] * nf)
     g.normal("decoder.final_conv1d.conv.conv.bias", 1, std=0.05)
+    if encoder:                                                   # drawn AFTER the decode-side tensors, which keep their values
+        _fan(g, "encoder.init_conv1d.conv.conv.weight", nf, cfg["ksize"], 1, fan_in=cfg["ksize"])
+        g.normal("encoder.init_conv1d.conv.conv.bias", nf, std=0.05)
+        c = nf
+        for li, r in enumerate(reversed(cfg["ratios"])):
+            L = f"encoder.layers.{li}"
+            hid = c // cfg["compress"]
+            _fan(g, L + ".residuals.0.block.0.conv.conv.weight", hid, cfg["residual_ksize"], c, fan_in=cfg["residual_ksize"] * c)
+            g.normal(L + ".residuals.0.block.0.conv.conv.bias", hid, std=0.05)
+            _fan(g, L + ".residuals.0.block.1.conv.conv.weight", c, 1, hid, fan_in=hid)
+            g.normal(L + ".residuals.0.block.1.conv.conv.bias", c, std=0.05)
+            _fan(g, L + ".downsample.conv.conv.weight", 2 * c, 2 * r, c, fan_in=2 * r * c)
+            g.normal(L + ".downsample.conv.conv.bias", 2 * c, std=0.05)
+            c *= 2
+        _fan(g, "encoder.final_conv1d.conv.conv.weight", d, cfg["last_ksize"], c, fan_in=cfg["last_ksize"] * c)
+        g.normal("encoder.final_conv1d.conv.conv.bias", d, std=0.05)
+        for li in range(cfg["num_layers"]):
+            L = f"encoder_transformer.transformer.layers.{li}"
+            g.layer_norm(L + ".norm1", d)
+            g.layer_norm(L + ".norm2", d)
+            _fan(g, L + ".self_attn.in_proj.weight", 3 * d, d, fan_in=d)
+            _fan(g, L + ".self_attn.out_proj.weight", d, d, fan_in=d)
+            _fan(g, L + ".gating.linear1.weight", cfg["dim_feedforward"], d, fan_in=d)
+            _fan(g, L + ".gating.linear2.weight", d, cfg["dim_feedforward"], fan_in=cfg["dim_feedforward"])
+            g.P[L + ".layer_scale_1.scale"] = _bf16(torch.full((d,), 0.3) + 0.1 * torch.rand(d, generator=gen))
+            g.P[L + ".layer_scale_2.scale"] = _bf16(torch.full((d,), 0.3) + 0.1 * torch.rand(d, generator=gen))
+        _fan(g, "downsample.conv.conv.conv.weight", d, 2 * s, d, fan_in=2 * s * d)
+        for name in ("rvq_first", "rvq_rest"):
+            _fan(g, f"quantizer.{name}.input_proj.weight", cfg["qdim"], 1, d, fan_in=d)
     return g.P
 
 

@@ -129,3 +129,55 @@ def test_mimi_span_decodes_stitch_to_the_one_shot_decode(mimi):
     assert got.shape == full.shape and float((got - full).abs().max()) <= 1e-5 * max(1.0, float(full.abs().max()))
     short = model.decode_span(codes, 1200, 2400, halo=40)
     assert float((short - full[..., 1200 * 1920:]).abs().max()) > 1e-4 * float(full.abs().max())
+
+
+def test_snac_encode_matches_the_oracle():
+    """SURVEY.md section 8f row 2 (codec encode side), SNAC: the product's encoder + residual cosine quantiser against oracle.codec.snac_encode
+    (itself pinned to the reference's SNAC.encode, tests/test_oracle_pins.py).  The latent in front of the quantiser to 2e-4; the code streams
+    identical except where two codes are within the fp32 error of the latent of being equally near (a 4096-way arg-max over 8-dim cosines)."""
+    from mlx_audio_b200.codec import SNAC
+    P = synth.snac_weights(OC.SNAC_24K, encoder=True)
+    model = SNAC.from_config(OC.SNAC_24K, device="cuda:0").load_weights(P)
+    P64 = {k: v.double() for k, v in P.items()}
+    g = torch.Generator().manual_seed(3)
+    audio = torch.randn(2, 1, 9000, generator=g) * 0.3                  # 9000 -> right-padded to 10 240 = 20 finest frames
+    z = model.encode_latent(audio)
+    z_ref = OC.snac_encoder(P64, OC.snac_preprocess(audio.double(), OC.SNAC_24K).transpose(1, 2), OC.SNAC_24K)
+    assert z.shape == z_ref.shape == (2, 20, 768)
+    assert float((z.double().cpu() - z_ref).abs().max() / z_ref.abs().max()) < 2e-4
+    codes = model.encode(audio)
+    want = OC.snac_encode(P64, audio.double(), OC.SNAC_24K)
+    assert [tuple(c.shape) for c in codes] == [tuple(w.shape) for w in want] == [(2, 5), (2, 10), (2, 20)]
+    same = [float((c.cpu() == w).float().mean()) for c, w in zip(codes, want)]
+    assert min(same) >= 0.9, same
+    assert all(int(c.min()) >= 0 and int(c.max()) < 4096 and c.dtype == torch.int64 for c in codes)
+    y = model.decode(codes)                                              # the code streams are valid decoder input
+    assert y.shape[0] == 2 and bool(torch.isfinite(y).all())
+    with pytest.raises(ValueError):
+        SNAC.from_config(OC.SNAC_24K, device="cuda:0").load_weights(synth.snac_weights(OC.SNAC_24K)).encode(audio)
+
+
+def test_mimi_encode_matches_the_oracle():
+    """SURVEY.md section 8f row 2, Mimi: SEANet encoder + encoder transformer + replicate-padded stride-2 conv against the oracle's latent
+    (2e-4), then the split residual quantiser against oracle.codec.mimi_encode (pinned to the reference's Mimi.encode).  32 codebooks deep
+    the residual is small and fp32 differences of the latent move some arg-mins: the first codebooks must agree almost everywhere."""
+    from mlx_audio_b200.codec import Mimi, mimi_202407
+    cfg = OC.MIMI_202407
+    P = synth.mimi_weights(cfg, encoder=True)
+    model = Mimi(mimi_202407(32), device="cuda:0").load_weights(P)
+    P64 = {k: v.double() for k, v in P.items()}
+    g = torch.Generator().manual_seed(4)
+    pcm = torch.randn(2, 1, 1920 * 6 + 700, generator=g) * 0.3          # 6 frames + 700 samples -> 7 frames
+    z = model.encode_latent(pcm)
+    x = OC.mimi_seanet_encoder(P64, pcm.double(), cfg)
+    x = OC.mimi_transformer(P64, "encoder_transformer", x, cfg)
+    z_ref = OC.mimi_causal_conv(P64, "downsample.conv", x, 4, stride=2, pad_mode="edge").transpose(1, 2)
+    assert z.shape == z_ref.shape == (2, 7, 512)
+    assert float((z.double().cpu() - z_ref).abs().max() / z_ref.abs().max()) < 2e-4
+    codes = model.encode(pcm)
+    want = OC.mimi_encode(P64, pcm.double(), cfg)
+    assert codes.shape == want.shape == (2, 32, 7) and codes.dtype == torch.int64
+    same = (codes.cpu() == want).float()
+    assert float(same[:, :4].mean()) >= 0.9 and float(same.mean()) >= 0.6, (float(same[:, :4].mean()), float(same.mean()))
+    y = model.decode(codes)
+    assert y.shape == (2, 1, 7 * 1920) and bool(torch.isfinite(y).all())
