@@ -59,6 +59,8 @@ struct FProb {
 
 struct FParams {
   int G, ntiles, planes, f16, wst, w_stage, a_plane, tmem_stride;
+  int interleave;                              // 1: tile i belongs to problem i % G (equal tile counts, no split-K) -- see decode_tile
+  int ct_stride;                               // channels per problem in the coefficient table (CT_MAX, or CT_MAX / 4 when interleaved)
   unsigned long long* dbg;                     // optional [gridDim][32] globaltimer stamps (b2a_conv1d_fused_debug)
   int dbg_flags;                               // experiments (env B2A_FUSED_DBGFLAGS): 1 = converter skips the global loads, 2 = skips the smem stores,
                                                // 4 = skips fence.proxy.async, 16 = workers skip the conversion, 32 = skip the epilogue body;
@@ -68,12 +70,18 @@ struct FParams {
 
 struct TileRef { int g, b, mt, nt, ks; };
 
+// Tile order.  Contiguous: the tiles of the heaviest problem first.  Interleaved (groups whose problems have the same tile count, e.g. the
+// k = 3 / 7 / 11 resblocks of a generator stage): tile i belongs to problem i % G, so every CTA alternates between MMA-bound tiles (k = 11:
+// the workers wait for A buffers) and worker-bound ones (k = 3: the MMA warp waits for A chunks) and the two kinds overlap.
 __device__ __forceinline__ TileRef decode_tile(const FParams& p, int tile) {
-  int g = 0;
+  int g = 0, local;
+  if (p.interleave) { g = tile % p.G; local = tile / p.G; }
+  else {
 #pragma unroll
-  for (int i = 1; i < MAXG; i++) if (i < p.G && tile >= p.pr[i].tile_begin) g = i;
+    for (int i = 1; i < MAXG; i++) if (i < p.G && tile >= p.pr[i].tile_begin) g = i;
+    local = tile - p.pr[g].tile_begin;
+  }
   const FProb& P = p.pr[g];
-  int local = tile - P.tile_begin;
   TileRef t;
   t.g = g;
   t.ks = local % P.ksplit; local /= P.ksplit;
@@ -205,8 +213,8 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
   uint8_t* wbase = smem + (size_t)2 * a_buf;
   float* staging = reinterpret_cast<float*>(wbase + (size_t)p.wst * p.w_stage);
   float* sacc = staging + STAGING / 4;
-  float* ctab = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sacc) + SACC);      // [2][CT_MAX]: scale | shift of the input transform
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ctab) + CTAB);
+  float* ctab_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sacc) + SACC);  // [slots][2][ct_stride]: scale | shift of the input transform
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ctab_all) + CTAB);
   uint64_t* empty = full + p.wst;
   uint64_t* tfull = empty + p.wst;           // [2]
   uint64_t* tempty = tfull + 2;              // [2]
@@ -338,7 +346,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
     const int et = wt;
     float* stage = staging + ww * (32 * 33);
     uint32_t cg = 0;
-    int cur_key = -1;
+    int cur_key[MAXG] = {-1, -1, -1, -1};             // batch whose coefficients problem g's table holds (interleaved: one table per problem)
     unsigned long long w_aempty = 0, w_tfull = 0;
 
     auto convert_tile = [&](const int tile) {
@@ -371,18 +379,25 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
       const int R = P.R;
       // (scale, shift) of every input channel: computed once per (problem, batch) by the 512 worker threads -- the float64 statistics
       // arithmetic costs ~150 double-precision operations per channel, far too much to repeat in every K chunk of every tile
-      const bool tabled = P.pre_mode != 0 && P.Cin <= CT_MAX;
+      const bool tabled = P.pre_mode != 0 && P.Cin <= p.ct_stride;
+      const int slot = p.interleave ? t.g : 0;
+      float* ctab = ctab_all + slot * 2 * p.ct_stride;
+      const int CTS = p.ct_stride;
       const int key = (t.g << 16) | t.b;
-      if (tabled && key != cur_key) {
+      int have = cur_key[0];
+#pragma unroll
+      for (int i = 1; i < MAXG; i++) if (slot == i) have = cur_key[i];
+      if (tabled && key != have) {
         bar_sync(3, NWORK * 32);                       // nobody still reads the previous table
         for (int c = wt; c < P.Cin; c += NWORK * 32) {
           float sc_ = P.in_scale, sh_ = 0.f;
           if (P.pre_mode == 1) { sc_ = __ldg(P.pre_scale + (int64_t)t.b * P.Cin + c) * P.in_scale; sh_ = __ldg(P.pre_shift + (int64_t)t.b * P.Cin + c); }
           else stats_coeffs(P, t.b, c, sc_, sh_);
-          ctab[c] = sc_; ctab[CT_MAX + c] = sh_;
+          ctab[c] = sc_; ctab[CTS + c] = sh_;
         }
         bar_sync(3, NWORK * 32);
-        cur_key = key;
+#pragma unroll
+        for (int i = 0; i < MAXG; i++) if (slot == i) cur_key[i] = key;
       }
       for (int kc = kc0; kc < kc1; kc++, cg++) {
         const uint32_t ab = cg & 1;
@@ -395,7 +410,7 @@ conv_fused_kernel(const __grid_constant__ FParams gp, const __grid_constant__ CU
           chok[q] = c < P.Cin;
           sc[q] = P.in_scale; sh[q] = 0.f; aa[q] = 1.f; bb[q] = 1.f;
           if (chok[q]) {
-            if (tabled) { sc[q] = ctab[c]; sh[q] = ctab[CT_MAX + c]; }
+            if (tabled) { sc[q] = ctab[c]; sh[q] = ctab[CTS + c]; }
             else if (P.pre_mode == 1) { sc[q] = __ldg(P.pre_scale + (int64_t)t.b * P.Cin + c) * P.in_scale; sh[q] = __ldg(P.pre_shift + (int64_t)t.b * P.Cin + c); }
             else if (P.pre_mode == 2) stats_coeffs(P, t.b, c, sc[q], sh[q]);
             if (P.pre_a) aa[q] = __ldg(P.pre_a + c);
@@ -671,7 +686,8 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
   for (int i = 0; i < n; i++) { order[i] = i; cost[i] = (double)pr[i].taps * pr[i].cin_pad; }
   for (int i = 0; i < n; i++) for (int j = i + 1; j < n; j++) if (cost[order[j]] > cost[order[i]]) { int t = order[i]; order[i] = order[j]; order[j] = t; }
   int maxR = 0, maxBN = 0, maxWst = 0, tiles_total = 0;
-  int64_t base_tiles = 0, sum_base = 0, cnt_used = 0, ws_used = 0;
+  int64_t base_tiles = 0, sum_base = 0, cnt_used = 0, ws_used = 0, first_base = 0;
+  bool can_interleave = true;
   for (int gi = 0; gi < n; gi++) {                         // output tiles of the whole launch before any split (same tile rule as below)
     const b2a_convf_t& q = pr[gi];
     if (q.N <= 0 || q.N % 32) continue;                    // rejected by the argument checks below
@@ -739,11 +755,20 @@ extern "C" int32_t b2a_conv1d_fused(const b2a_convf_t* pr, int32_t n, int32_t pl
     }
     P.tile_begin = tiles_total;
     tiles_total += (int)(base_tiles * P.ksplit);
+    if (gi == 0) first_base = base_tiles;
+    if (base_tiles != first_base || P.ksplit != 1 || q.Cin > CT_MAX / MAXG) can_interleave = false;
     maxR = P.R > maxR ? P.R : maxR; maxBN = P.BN > maxBN ? P.BN : maxBN;
     const int wsz = P.BN * 128 * P.wplanes;
     maxWst = wsz > maxWst ? wsz : maxWst;
   }
   p.ntiles = tiles_total;
+  {
+    static int il = -1;
+    // opt-in: 138 -> 125 us on the warm-L2 microbenchmark of the stage-1 group, but no gain inside the replayed utterance (5.34 vs 5.33 ms)
+    if (il < 0) { const char* e = getenv("B2A_FUSED_INTERLEAVE"); il = (e && e[0] == '1') ? 1 : 0; }
+    p.interleave = (il && n > 1 && can_interleave) ? 1 : 0;
+    p.ct_stride = p.interleave ? CT_MAX / MAXG : CT_MAX;
+  }
   p.a_plane = maxR * 128;
   p.w_stage = maxWst;
   p.tmem_stride = (int)(maxBN <= 32 ? 32 : maxBN <= 64 ? 64 : maxBN <= 128 ? 128 : 256);
