@@ -53,12 +53,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+// warp-convergent issue of four K=16 steps (see gemm_tc.cu: issuing from inside `if (lane == 0)` costs ~25 instructions per MMA)
+__device__ __forceinline__ void umma_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred e, p, q;\n\t.reg .b64 a1, b1, a2, b2, a3, b3;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "add.s64 a1, %1, 2;\n\tadd.s64 b1, %2, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 a3, %1, 6;\n\tadd.s64 b3, %2, 6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+               ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* r) {
   uint32_t* u = reinterpret_cast<uint32_t*>(r);
@@ -188,22 +199,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
     const uint32_t sb = smem_u32(smem);
     // S is double-buffered in TMEM (columns [0,64) and [128,192)): S(t+1) = Q K(t+1)^T is issued BEFORE waiting for P(t), so the
     // score MMA of the next key tile runs underneath the softmax of the current one.
+    static_assert(HD / 16 == 4 && BN / 16 == 4, "umma_x4 issues four K steps");
+    const uint64_t dqh = umma_desc_sw128(sb + OFF_QH), dql = umma_desc_sw128(sb + OFF_QL), dkh = umma_desc_sw128(sb + OFF_KH),
+                   dkl = umma_desc_sw128(sb + OFF_KL), dph = umma_desc_sw128(sb + OFF_PH), dpl = umma_desc_sw128(sb + OFF_PL),
+                   dvh = umma_desc_sw128(sb + OFF_VH), dvl = umma_desc_sw128(sb + OFF_VL);
     auto issue_s = [&](int t) {
       mbar_wait(k_full, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        const uint32_t d = tmem_base + ((t & 1) ? 128u : 0u);
-#pragma unroll
-        for (int pr = 0; pr < 3; pr++) {                       // S = Qh Kh^T + Ql Kh^T + Qh Kl^T
-          const uint64_t ad = umma_desc_sw128(sb + (pr == 1 ? OFF_QL : OFF_QH));
-          const uint64_t bd = umma_desc_sw128(sb + (pr == 2 ? OFF_KL : OFF_KH));
-#pragma unroll
-          for (int k = 0; k < HD / 16; k++) umma_f16(d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (pr | k) != 0);
-        }
-        umma_commit(k_empty);
-        umma_commit(s_full + (t & 1));
-      }
-      __syncwarp();
+      const uint32_t d = tmem_base + ((t & 1) ? 128u : 0u);
+      umma_x4(d, dqh, dkh, idesc, 0u);                         // S = Qh Kh^T + Ql Kh^T + Qh Kl^T
+      umma_x4(d, dql, dkh, idesc, 1u);
+      umma_x4(d, dqh, dkl, idesc, 1u);
+      umma_commit_elect(k_empty);
+      umma_commit_elect(s_full + (t & 1));
     };
     if (nt > 0) { mbar_wait(q_full, 0); issue_s(0); }
     for (int t = 0; t < nt; t++) {
@@ -211,19 +219,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant
       mbar_wait(p_full, t & 1);
       mbar_wait(v_full, t & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0) {
-        // O_tile = Ph Vh + Pl Vh + Ph Vl   (A = P [128 x 64 keys], B = V^T tile [64 dims x 64 keys])
-#pragma unroll
-        for (int pr = 0; pr < 3; pr++) {
-          const uint64_t ad = umma_desc_sw128(sb + (pr == 1 ? OFF_PL : OFF_PH));
-          const uint64_t bd = umma_desc_sw128(sb + (pr == 2 ? OFF_VL : OFF_VH));
-#pragma unroll
-          for (int k = 0; k < BN / 16; k++) umma_f16(tmem_base + 64, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (pr | k) != 0);
-        }
-        umma_commit(v_empty);
-        umma_commit(o_full);
-      }
-      __syncwarp();
+      // O_tile = Ph Vh + Pl Vh + Ph Vl   (A = P [128 x 64 keys], B = V^T tile [64 dims x 64 keys])
+      umma_x4(tmem_base + 64, dph, dvh, idesc, 0u);
+      umma_x4(tmem_base + 64, dpl, dvh, idesc, 1u);
+      umma_x4(tmem_base + 64, dph, dvl, idesc, 1u);
+      umma_commit_elect(v_empty);
+      umma_commit_elect(o_full);
     }
   } else {
     // ===== softmax / accumulate: thread <-> query row =====
