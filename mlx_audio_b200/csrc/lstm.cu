@@ -109,7 +109,7 @@ __device__ __forceinline__ void bar_wait_cluster(uint32_t bar, uint32_t parity) 
 
 __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(256, 1)
 lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ wh, float* __restrict__ out,
-                     int64_t out_ld, int T, int bulk) {
+                     int64_t out_ld, int T) {
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int dir = blockIdx.y, b = blockIdx.z;
@@ -119,7 +119,6 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
   __shared__ __align__(16) float hbuf[2][LH];
   __shared__ float gates[2 * 4 * UPC];
   __shared__ __align__(8) uint64_t hbar[2];                         // hbar[i]: "hbuf[i] holds the complete h of a step"
-  __shared__ __align__(16) float hstage[2][UPC];                    // this CTA's 32 new h values, source of the bulk copies (by step parity)
 
   float w[128];
   {
@@ -141,11 +140,9 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
   float xp_cur = 0.f;
   if (half == 0 && T > 0) xp_cur = __ldg(xp_base + (int64_t)(dir == 0 ? 0 : T - 1) * 2 * 4 * LH);
   uint32_t rh[NCTA], rb[NCTA];                                      // cluster addresses of every CTA's hbuf / hbar
-  uint32_t rh_l = 0, rb_l = 0;                                      // lane q < 8: CTA q's hbuf / hbar (bulk-copy path)
   if (tid < UPC) {
 #pragma unroll
     for (int q = 0; q < NCTA; q++) { rh[q] = mapa(smem_addr(&hbuf[0][0]), q); rb[q] = mapa(smem_addr(&hbar[0]), q); }
-    rh_l = mapa(smem_addr(&hbuf[0][0]), tid & (NCTA - 1)); rb_l = mapa(smem_addr(&hbar[0]), tid & (NCTA - 1));
   }
   cluster.sync();                                                   // zeros + barrier inits visible cluster-wide
 
@@ -173,32 +170,21 @@ lstm_bidir_kernel_v2(const float* __restrict__ xproj, const float* __restrict__ 
     float* gbuf = gates + cur * (4 * UPC);                           // double-buffered: no second block barrier per step
     if (half == 0) gbuf[r] = s + xp_cur;
     __syncthreads();
+    // gate activations: warp g applies gate g's nonlinearity to its 32 units, then warp 0 combines (see lstm_bidir_kernel)
+    if (tid < 4 * UPC) {
+      const float v = gbuf[tid];
+      gbuf[tid] = (tid >> 5) == 2 ? 1.f - __fdividef(2.f, 1.f + __expf(2.f * v)) : __fdividef(1.f, 1.f + __expf(-v));
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     if (tid < UPC) {
-      // sigmoid / tanh through the SFU exponential (abs error ~1e-7: far inside the 1e-4 stage tolerance); libm's expf / tanhf cost
-      // ~150 cycles each on the recurrence's critical path
-      const float gi = 1.f / (1.f + __expf(-gbuf[tid]));
-      const float gf = 1.f / (1.f + __expf(-gbuf[UPC + tid]));
-      const float gg = 1.f - 2.f / (1.f + __expf(2.f * gbuf[2 * UPC + tid]));
-      const float go = 1.f / (1.f + __expf(-gbuf[3 * UPC + tid]));
+      const float gi = gbuf[tid], gf = gbuf[UPC + tid], gg = gbuf[2 * UPC + tid], go = gbuf[3 * UPC + tid];
       c = fmaf(gf, c, gi * gg);
-      const float hval = go * (1.f - 2.f / (1.f + __expf(2.f * c)));
+      const float hval = go * (1.f - __fdividef(2.f, 1.f + __expf(2.f * c)));
       out[((int64_t)b * T + t) * out_ld + dir * LH + rank * UPC + tid] = hval;
       const uint32_t off = (uint32_t)((nxt * LH + rank * UPC + tid) * 4);
       if (step + 1 < T) {                                           // the last step has no consumer: no store may outlive the CTA
-        if (bulk) {
-          // B2A_LSTM_BULK=1: one 128-byte bulk copy per peer instead of 32 four-byte st.async (each its own complete_tx on the destination's
-          // mbarrier).  Hypothesis: the 256 barrier updates per step pace the recurrence.  Measured: no -- the bulk path is 17 % slower.
-          hstage[nxt][tid] = hval;
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk copy's async-proxy read
-          __syncwarp();
-          if (tid < NCTA)
-            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(rh_l + (uint32_t)((nxt * LH + rank * UPC) * 4)), "r"(smem_addr(&hstage[nxt][0])), "r"(UPC * 4),
-                           "r"(rb_l + (uint32_t)(nxt * 8)) : "memory");
-        } else {
 #pragma unroll
-          for (int q = 0; q < NCTA; q++) st_async_f32(rh[q] + off, hval, rb[q] + (uint32_t)(nxt * 8));
-        }
+        for (int q = 0; q < NCTA; q++) st_async_f32(rh[q] + off, hval, rb[q] + (uint32_t)(nxt * 8));
       }
     }
     xp_cur = xp_next;                                               // gates[] of the next step live in the other half: no barrier here
@@ -215,10 +201,7 @@ extern "C" int32_t b2a_lstm_bidir(const float* xproj, const float* wh, float* ou
   dim3 grid(NCTA, 2, B);
   static int v2 = -1;
   if (v2 < 0) { const char* e = getenv("B2A_LSTM"); v2 = (e && e[0] == '1') ? 0 : 1; }      // B2A_LSTM=1 selects the cluster-barrier version
-  static int bulk = -1;
-  // opt-in experiment: one 128-byte cp.async.bulk per peer instead of 32 st.async -- measured SLOWER (1.23 -> 1.43 ms of LSTM per Kokoro utterance)
-  if (bulk < 0) { const char* e = getenv("B2A_LSTM_BULK"); bulk = (e && e[0] == '1') ? 1 : 0; }
-  if (v2) lstm_bidir_kernel_v2<<<grid, 256, 0, (cudaStream_t)stream>>>(xproj, wh, out, out_ld, T, bulk);
+  if (v2) lstm_bidir_kernel_v2<<<grid, 256, 0, (cudaStream_t)stream>>>(xproj, wh, out, out_ld, T);
   else lstm_bidir_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xproj, wh, out, out_ld, T);
   B2A_CHECK_LAUNCH();
   return B2A_OK;
